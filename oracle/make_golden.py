@@ -1,0 +1,67 @@
+"""Generate tests/golden/*.npz by running the UNCHANGED reference modules (build container only).
+
+TEST INFRASTRUCTURE.  Usage:  python -m oracle.make_golden
+Each fixture stores the seeds/shapes that regenerate inputs and weights (oracle/weights.py),
+a checksum of those weights, and the reference module's output on CPU fp32.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from oracle import refshim, weights
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+TCN_KW = dict(ninputs=1, noutputs=1, nblocks=20, channel_growth=0, channel_width=256, kernel_size=7,
+              stack_size=10, dilation_growth=2, condition=False, latent_dim=2, norm_type="identity",
+              causal=False, estimate_loudness=False)
+
+
+def _save(name, **arrs):
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name), **arrs)
+    print("wrote", name, {k: getattr(v, "shape", v) for k, v in arrs.items()})
+
+
+def main():
+    torch.set_flush_denormal(True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    R = refshim.ref_modules()
+
+    # --- STFT / iSTFT known-answer (torch.stft as TorchSTFT calls it, transforms.py:106-116)
+    x = weights.synth_audio(11, 2, 8192)[:, 0]
+    win = torch.hann_window(2048)
+    Z = torch.stft(x, 2048, 512, window=win, center=True, normalized=False, onesided=True, pad_mode="reflect", return_complex=True)
+    y = torch.istft(Z, 2048, 512, window=win, center=True, normalized=False, onesided=True, length=8192)
+    _save("stft_kat.npz", seed=11, B=2, T=8192, n_fft=2048, hop=512, Z=torch.view_as_real(Z).numpy(), y=y.numpy())
+
+    # --- Open-Unmix wrapper: sample() and forward() (remfx/models.py:294-304), eval mode
+    sd = weights.umx_state(0)
+    m = R.models.OpenUnmixModel(n_fft=2048, hop_length=512, n_channels=1, alpha=0.3, sample_rate=48000)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    xa, ta = weights.synth_audio(21, 2, 16384), weights.synth_audio(22, 2, 16384)
+    with torch.no_grad():
+        out = m.sample(xa)
+        loss, out2 = m((xa, ta))
+    assert torch.equal(out, out2)
+    _save("umx_sample.npz", wseed=0, xseed=21, tseed=22, B=2, T=16384, wsum=weights.checksum(sd),
+          out=out.numpy(), loss=float(loss))
+
+    # --- TCN wrapper (remfx/models.py:379-390), cfg/model/tcn.yaml hyper-parameters
+    sdt = weights.tcn_state(0)
+    tm = R.models.TCNModel(sample_rate=48000, num_bins=1025, **TCN_KW)
+    tm.load_state_dict(sdt, strict=True)
+    tm.eval()
+    xt, tt = weights.synth_audio(31, 1, 16384), weights.synth_audio(32, 1, 16384)
+    with torch.no_grad():
+        loss, out = tm((xt, tt))
+    _save("tcn_forward.npz", wseed=0, xseed=31, tseed=32, B=1, T=16384, wsum=weights.checksum(sdt),
+          out=out.numpy(), loss=float(loss))
+
+
+if __name__ == "__main__":
+    main()
