@@ -1,0 +1,108 @@
+/* remfx_b200 -- C ABI of the Blackwell-native RemFx hot path (libremfx_b200.so).
+ *
+ * Plain C: opaque handles, raw device pointers, sizes; no torch / C++ types.  Every pointer named
+ * `*_dev` (or undecorated) is a CUDA device pointer on the current device unless the function name ends
+ * in `_host`.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All functions
+ * return 0 on success; on failure they return non-zero and rfx_last_error() describes the problem
+ * (thread-local).  Work is enqueued asynchronously on `stream` unless stated otherwise.
+ *
+ * Each entry point replaces one piece of the reference's Python plug-in surface (file:line under
+ * mhrice/RemFx @ 85d5030); see INTEGRATION.md for the reference-side binding.
+ */
+#ifndef REMFX_B200_H
+#define REMFX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFX_ABI_VERSION 1
+
+int rfx_abi_version(void);
+/* Description of the most recent failure on the calling thread ("" if none). */
+const char* rfx_last_error(void);
+/* 1 if the current device is a compute-capability 10.x part the library was built for. */
+int rfx_device_supported(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * S1/S2/S4  torch.stft(center=True, reflect, onesided) + epilogue
+ *   replaces umx/openunmix/transforms.py:89-120 (TorchSTFT.forward), :198-216 (ComplexNorm),
+ *            remfx/utils.py:138-159 (spectrogram)
+ * x: (B, T) fp32.  window: n_fft taps (caller zero-pads shorter windows, as torch.stft does).
+ * Output layout is FRAME-major: Z[(b*F + t)*bins + k] (re,im interleaved), A likewise (real), with
+ * F = T/hop + 1, bins = n_fft/2 + 1.  mode: 0 complex only (A unused), 2 |Z|, 3 |Z|^2,
+ * 4 sqrt(max(|Z|^2,1e-8)), 5 (|Z|+1e-8)^alpha.  Z may be NULL when only A is wanted.
+ * n_fft in {512, 1024, 2048, 4096}.
+ * ------------------------------------------------------------------------------------------- */
+int rfx_stft(const float* x, int B, int T, int n_fft, int hop, const float* window, int normalized,
+             int mode, float alpha, float* Z_ri, float* A, void* stream);
+
+/* S3  torch.istft(center=True, length=length)
+ *   replaces umx/openunmix/transforms.py:164-181 (TorchISTFT.forward)
+ * Z_ri: frame-major complex [(b*F + t)*bins + k]; mask (optional, same indexing, real) is multiplied in. */
+int rfx_istft(const float* Z_ri, const float* mask, int B, int F, int n_fft, int hop, const float* window,
+              int normalized, int length, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense layer  C[m,n] = act(((A[m,:] . W[n,:]) * s1[n] + t1[n]) * s2[n] + t2[n])
+ *   the primitive behind nn.Linear + BatchNorm1d(eval) + activation in umx/openunmix/model.py:119-161
+ * impl: 0 = tcgen05 bf16x3 tensor-core kernel, 1 = fp32 FFMA kernel.  act: 0 none, 1 tanh, 2 relu,
+ * 3 sigmoid.  s1/t1/s2/t2 may be NULL.  W is the raw nn.Linear weight [N, K] (row-major); for impl 0
+ * it is packed on the fly into `scratch` (rfx_gemm_scratch_bytes).  Test / utility entry point -- the
+ * model handles below keep their weights pre-packed.
+ * ------------------------------------------------------------------------------------------- */
+size_t rfx_gemm_scratch_bytes(int N, int K);
+int rfx_gemm(int impl, const float* A, int lda, int M, const float* W, int N, int K, float* C, int ldc,
+             const float* s1, const float* t1, const float* s2, const float* t2, int act,
+             void* scratch, void* stream);
+
+/* One bidirectional LSTM layer recurrence (torch.nn.LSTM, gate order i,f,g,o; zero initial state)
+ *   replaces the recurrent half of umx/openunmix/model.py:141 (self.lstm)
+ * G: [B*F, 8H] input projections incl. both biases, column = dir*4H + gate*H + unit, row = b*F + t.
+ * Whh: [2, 4H, H].  Hout: [B*F, ldh], column = dir*H + unit.  H must be 256. */
+int rfx_lstm_layer(const float* G, const float* Whh, float* Hout, int ldh, int B, int F, int H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * U1-U5  Open-Unmix effect-removal model
+ *   replaces remfx/models.py:259-304 (OpenUnmixModel.sample / eval-mode forward output) =
+ *   umx/openunmix/model.py:242-319 (Separator.forward) around :107-166 (OpenUnmix.forward) and
+ *   umx/openunmix/filtering.py:442-459 (wiener, niter=0)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rfx_umx rfx_umx_t;
+
+typedef struct {
+  int n_fft;       /* 2048 */
+  int hop;         /* 512  */
+  int hidden;      /* 512 (LSTM hidden = hidden/2 per direction; must be 512) */
+  int nb_layers;   /* 3 */
+  int gemm_impl;   /* 0 tcgen05 bf16x3 (default), 1 fp32 FFMA */
+} rfx_umx_config;
+
+int rfx_umx_create(const rfx_umx_config* cfg, rfx_umx_t** out);
+void rfx_umx_destroy(rfx_umx_t* h);
+/* Copy one tensor of the reference state_dict into the handle (device-to-device, on `stream`).
+ * `key` is the OpenUnmix parameter name without the wrapper prefix, e.g. "fc1.weight",
+ * "bn1.running_var", "lstm.weight_hh_l0_reverse", "input_mean", or "window" for the STFT window. */
+int rfx_umx_load_param(rfx_umx_t* h, const char* key, const float* src, int64_t numel, void* stream);
+/* Fold BatchNorm statistics, add LSTM biases and pack the GEMM weights; call after loading params. */
+int rfx_umx_finalize(rfx_umx_t* h, void* stream);
+size_t rfx_umx_workspace_bytes(const rfx_umx_t* h, int B, int T);
+/* x: (B, 1, T) fp32 device -> out: (B, 1, T) fp32 device.  workspace: >= rfx_umx_workspace_bytes. */
+int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* Same, from / to (pinned) HOST buffers: H2D copy, kernels, D2H copy on `stream`, then a stream sync. */
+int rfx_umx_sample_host(rfx_umx_t* h, const float* x_host, int B, int T, float* out_host, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* Number of kernels one rfx_umx_sample call launches (for bench.py's gpu_launches). */
+int rfx_umx_launches_per_call(const rfx_umx_t* h);
+/* Debug taps: copy an internal activation of the last call into dst (fp32 device).  what: 0 = |STFT|
+ * front-end output (M x lda), 1 = fc1/tanh (M x 512), 2 = last LSTM layer output (M x 512),
+ * 3 = mask (M x ldm).  Returns the row stride through *ld. */
+int rfx_umx_debug_tap(rfx_umx_t* h, int what, const void* workspace, int B, int T, float* dst, int* ld, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REMFX_B200_H */

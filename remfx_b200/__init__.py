@@ -1,0 +1,8 @@
+"""remfx_b200 -- Blackwell-native (sm_100a) compute path for RemFx audio-effect removal.
+
+Public surface mirrors the reference's plug-in boundary (remfx/models.py:259-390):
+`remfx_b200.models.{OpenUnmixModel, ...}` with `forward((x, target)) -> (loss, out)` and
+`sample(x) -> out`; `remfx_b200.ops` for the stand-alone STFT/iSTFT/crop helpers.  All math runs
+in hand-written CUDA kernels behind the C ABI in include/remfx_b200.h (libremfx_b200.so).
+"""
+__version__ = "0.1.0"

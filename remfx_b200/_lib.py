@@ -1,0 +1,93 @@
+"""ctypes binding of libremfx_b200.so (the C ABI declared in include/remfx_b200.h).
+
+The product path has NO fallback: if the CUDA library is missing or the device is not a
+Blackwell (sm_100) part, the ops raise instead of silently computing elsewhere.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libremfx_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+
+class RfxError(RuntimeError):
+    pass
+
+
+class UmxConfig(C.Structure):
+    _fields_ = [("n_fft", C.c_int), ("hop", C.c_int), ("hidden", C.c_int), ("nb_layers", C.c_int), ("gemm_impl", C.c_int)]
+
+
+_f32p = C.c_void_p  # device pointers travel as integers
+_SIGNATURES = {
+    "rfx_abi_version": (C.c_int, []),
+    "rfx_last_error": (C.c_char_p, []),
+    "rfx_device_supported": (C.c_int, []),
+    "rfx_stft": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_float, _f32p, _f32p, C.c_void_p]),
+    "rfx_istft": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, _f32p, C.c_void_p]),
+    "rfx_gemm_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "rfx_gemm": (C.c_int, [C.c_int, _f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, _f32p, C.c_int, _f32p, _f32p, _f32p, _f32p,
+                           C.c_int, C.c_void_p, C.c_void_p]),
+    "rfx_lstm_layer": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "rfx_umx_create": (C.c_int, [C.POINTER(UmxConfig), C.POINTER(C.c_void_p)]),
+    "rfx_umx_destroy": (None, [C.c_void_p]),
+    "rfx_umx_load_param": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int64, C.c_void_p]),
+    "rfx_umx_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rfx_umx_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "rfx_umx_sample": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rfx_umx_sample_host": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rfx_umx_launches_per_call": (C.c_int, [C.c_void_p]),
+    "rfx_umx_debug_tap": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int), C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raises RfxError when it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RfxError(
+                    f"{LIB_PATH} not found: build it with `python -m remfx_b200.build` "
+                    "(remfx_b200 has no CPU or eager-PyTorch fallback)"
+                )
+            handle = C.CDLL(LIB_PATH)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(handle, name)
+                fn.restype = res
+                fn.argtypes = args
+            if handle.rfx_abi_version() != 1:
+                raise RfxError("libremfx_b200.so ABI version mismatch; rebuild")
+            _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().rfx_last_error().decode("utf-8", "replace")
+        exc = ValueError if rc == 2 else RfxError
+        raise exc(f"{what}: {msg}" if what else msg)
+
+
+def require_device(t) -> None:
+    """Raise unless tensor `t` lives on a supported CUDA device."""
+    if not t.is_cuda:
+        raise RfxError("remfx_b200 kernels need CUDA tensors on a B200 (sm_100a); got a CPU tensor and there is no CPU fallback")
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def cur_stream() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

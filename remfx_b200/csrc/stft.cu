@@ -1,0 +1,231 @@
+// STFT / iSTFT kernels (cuFFT-free).  Reference semantics: torch.stft / torch.istft with center=True,
+// pad_mode="reflect", onesided, as called by
+//   umx/openunmix/transforms.py:106-116 (TorchSTFT), :168-177 (TorchISTFT), :198-216 (ComplexNorm),
+//   remfx/utils.py:138-159 (spectrogram), torchaudio MelSpectrogram (remfx/classifier.py:156-161),
+//   auraloss STFTLoss (remfx/models.py:289-291).
+// Data layout is frame-major: row m = b * F + t, bins contiguous (so the FC layers that follow read
+// K-contiguous rows and no transpose is ever materialised).
+#include "kernels.h"
+#include "fft.cuh"
+
+#include <map>
+#include <mutex>
+#include <vector>
+#include <cmath>
+
+namespace rfx {
+
+// -------------------------------------------------------------------------------------------------
+// Twiddle tables exp(-2 pi i m / n_fft), computed in double on the host, cached per (device, n_fft).
+// -------------------------------------------------------------------------------------------------
+static std::mutex g_tw_mu;
+static std::map<std::pair<int, int>, float2*> g_tw;
+
+const float2* twiddles(int n_fft) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_tw_mu);
+  auto key = std::make_pair(dev, n_fft);
+  auto it = g_tw.find(key);
+  if (it != g_tw.end()) return it->second;
+  std::vector<float2> h(n_fft);
+  for (int m = 0; m < n_fft; ++m) {
+    const double a = -2.0 * M_PI * (double)m / (double)n_fft;
+    h[m] = make_float2((float)cos(a), (float)sin(a));
+  }
+  float2* d = nullptr;
+  if (cudaMalloc(&d, sizeof(float2) * n_fft) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, h.data(), sizeof(float2) * n_fft, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  g_tw[key] = d;
+  return d;
+}
+
+__device__ __forceinline__ int reflect_index(int i, int T) {
+  if (i < 0) i = -i;
+  if (i >= T) i = 2 * (T - 1) - i;
+  return i;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Forward STFT.  grid = (ceil(F / FPC), B), block = NC/4 threads; each CTA transforms FPC frames.
+// -------------------------------------------------------------------------------------------------
+constexpr int STFT_FPC = 4;
+
+template <int LOG2NC>
+__global__ void __launch_bounds__((1 << LOG2NC) / 4) stft_kernel(StftParams p) {
+  constexpr int NC = 1 << LOG2NC;
+  constexpr int T4 = NC / 4;
+  constexpr int NFFT = 2 * NC;
+  __shared__ float2 sa[NC];
+  __shared__ float2 sb[NC];
+  const int j = threadIdx.x;
+  const int b = blockIdx.y;
+  const float* __restrict__ x = p.x + (size_t)b * p.x_bstride;
+  const int f_end = min(p.F, (int)(blockIdx.x + 1) * STFT_FPC);
+  for (int f = blockIdx.x * STFT_FPC; f < f_end; ++f) {
+    const int base = f * p.hop - NC;  // first sample of the frame (n_fft/2 = NC samples of centre padding)
+    const bool interior = (base >= 0) && (base + NFFT <= p.T);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int n = j + r * T4;
+      const float2 w = *reinterpret_cast<const float2*>(p.window + 2 * n);
+      float2 v;
+      if (interior && p.x_aligned8) {
+        v = *reinterpret_cast<const float2*>(x + base + 2 * n);
+      } else {
+        v.x = x[reflect_index(base + 2 * n, p.T)];
+        v.y = x[reflect_index(base + 2 * n + 1, p.T)];
+      }
+      sa[n] = make_float2(v.x * w.x, v.y * w.y);
+    }
+    const float2* Zp = fft_block<LOG2NC>(sa, sb, p.tw, j);
+    const size_t m = (size_t)b * p.F + f;
+    for (int k = j; k <= NC; k += T4) {
+      float2 X = rfft_post(Zp, p.tw, NC, k);
+      X.x *= p.scale;
+      X.y *= p.scale;
+      if (p.Z) p.Z[m * p.ldz + k] = X;
+      if (p.mode == STFT_UMX_MAG) {
+        // ComplexNorm (transforms.py:211) then OpenUnmix input shift/scale (model.py:127-128)
+        const float mag = sqrtf(X.x * X.x + X.y * X.y);
+        p.A[m * p.lda + k] = (mag + p.in_mean[k]) * p.in_scale[k];
+      } else if (p.mode == STFT_MAG) {
+        p.A[m * p.lda + k] = sqrtf(X.x * X.x + X.y * X.y);
+      } else if (p.mode == STFT_POWER) {
+        p.A[m * p.lda + k] = X.x * X.x + X.y * X.y;
+      } else if (p.mode == STFT_MAG_CLAMP) {
+        p.A[m * p.lda + k] = sqrtf(fmaxf(X.x * X.x + X.y * X.y, 1e-8f));
+      } else if (p.mode == STFT_MAG_POW) {
+        p.A[m * p.lda + k] = powf(sqrtf(X.x * X.x + X.y * X.y) + 1e-8f, p.alpha);
+      }
+    }
+    if (p.A && p.lda > NC + 1) {
+      for (int k = NC + 1 + j; k < p.lda; k += T4) p.A[m * p.lda + k] = 0.0f;
+    }
+    __syncthreads();  // sa/sb are reused by the next frame
+  }
+}
+
+int launch_stft(const StftParams& p, int B, cudaStream_t stream) {
+  RFX_REQUIRE(p.tw != nullptr, "twiddle table");
+  RFX_REQUIRE(p.T > p.n_fft / 2, "reflect padding needs T > n_fft/2");
+  dim3 grid(ceil_div(p.F, STFT_FPC), B);
+  switch (p.n_fft) {
+    case 512: stft_kernel<8><<<grid, 64, 0, stream>>>(p); break;
+    case 1024: stft_kernel<9><<<grid, 128, 0, stream>>>(p); break;
+    case 2048: stft_kernel<10><<<grid, 256, 0, stream>>>(p); break;
+    case 4096: stft_kernel<11><<<grid, 512, 0, stream>>>(p); break;
+    default: set_error("stft: n_fft must be 512, 1024, 2048 or 4096"); return 2;
+  }
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Inverse STFT with fused mask multiply, window, overlap-add in shared memory, envelope division and
+// crop.  grid = (ceil(length / S), B) with S = hops_per_cta * hop output samples per CTA; each CTA
+// inverse-transforms every frame overlapping its segment (sequentially, so the OLA needs no atomics).
+// -------------------------------------------------------------------------------------------------
+template <int LOG2NC>
+__global__ void __launch_bounds__((1 << LOG2NC) / 4) istft_kernel(IstftParams p) {
+  constexpr int NC = 1 << LOG2NC;
+  constexpr int T4 = NC / 4;
+  constexpr int NFFT = 2 * NC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* sa = reinterpret_cast<float2*>(smem_raw);
+  float2* sb = sa + NC;
+  float* ola = reinterpret_cast<float*>(sb + NC);
+  const int j = threadIdx.x;
+  const int b = blockIdx.y;
+  const int S = p.hops_per_cta * p.hop;
+  const int s0 = blockIdx.x * S;  // first output sample of this segment
+  for (int i = j; i < S; i += T4) ola[i] = 0.0f;
+  // frames whose support [t*hop - NC, t*hop + NC) (output coordinates) intersects [s0, s0 + S)
+  int t_lo = (s0 - NC) / p.hop + 1;
+  if (s0 - NC < 0) t_lo = 0;
+  int t_hi = (s0 + S + NC + p.hop - 1) / p.hop - 1;
+  if (t_hi > p.F - 1) t_hi = p.F - 1;
+  const float inv = p.scale / (float)NC;
+  for (int t = t_lo; t <= t_hi; ++t) {
+    const size_t m = (size_t)b * p.F + t;
+    const float2* __restrict__ Zr = p.Z + m * p.ldz;
+    const float* __restrict__ Mr = p.mask ? p.mask + m * p.ldm : nullptr;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int k = j + r * T4;  // k in [0, NC/2)
+      float2 xk = Zr[k], xn = Zr[NC - k];
+      if (Mr) {
+        const float mk = Mr[k], mn = Mr[NC - k];
+        xk.x *= mk; xk.y *= mk; xn.x *= mn; xn.y *= mn;
+      }
+      if (k == 0) {  // irfft ignores the imaginary part of the DC and Nyquist bins
+        xk.y = 0.0f;
+        xn.y = 0.0f;
+        sa[0] = irfft_pre(xk, xn, p.tw[0]);
+      } else {
+        sa[k] = irfft_pre(xk, xn, p.tw[k]);
+        sa[NC - k] = irfft_pre(xn, xk, p.tw[NC - k]);
+      }
+    }
+    if (j == 0) {
+      float2 xh = Zr[NC / 2];
+      if (Mr) { const float mh = Mr[NC / 2]; xh.x *= mh; xh.y *= mh; }
+      sa[NC / 2] = irfft_pre(xh, xh, p.tw[NC / 2]);
+    }
+    const float2* res = fft_block<LOG2NC>(sa, sb, p.tw, j);
+    const int off = t * p.hop - NC - s0;  // segment-relative position of frame sample 0
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int n = j + r * T4;
+      const float2 v = res[n];
+      const float2 w = *reinterpret_cast<const float2*>(p.window + 2 * n);
+      const int q = off + 2 * n;
+      if (q >= 0 && q < S) ola[q] += v.x * inv * w.x;
+      if (q + 1 >= 0 && q + 1 < S) ola[q + 1] += -v.y * inv * w.y;
+    }
+    __syncthreads();
+  }
+  // envelope sum_t w^2 (torch.istft window_envelop), then crop to `length`
+  float* __restrict__ out = p.out + (size_t)b * p.out_bstride;
+  for (int i = j; i < S; i += T4) {
+    const int s = s0 + i;
+    if (s >= p.length) break;
+    const int q = s + NC;  // coordinate in the centre-padded signal
+    int ta = (q - NFFT + p.hop) / p.hop;  // ceil((q - NFFT + 1) / hop) for q - NFFT + 1 >= 0
+    if (q - NFFT + 1 <= 0) ta = 0;
+    int tb = q / p.hop;
+    if (tb > p.F - 1) tb = p.F - 1;
+    float env = 0.0f;
+    for (int t = ta; t <= tb; ++t) {
+      const float w = p.window[q - t * p.hop];
+      env += w * w;
+    }
+    out[s] = (env > 1e-11f) ? ola[i] / env : 0.0f;
+  }
+}
+
+template <int LOG2NC>
+static int launch_istft_t(const IstftParams& p, int B, cudaStream_t stream) {
+  constexpr int NC = 1 << LOG2NC;
+  const int S = p.hops_per_cta * p.hop;
+  const size_t smem = sizeof(float2) * 2 * NC + sizeof(float) * S;
+  RFX_CHECK_CUDA(cudaFuncSetAttribute(istft_kernel<LOG2NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(p.length, S), B);
+  istft_kernel<LOG2NC><<<grid, NC / 4, smem, stream>>>(p);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_istft(const IstftParams& p, int B, cudaStream_t stream) {
+  RFX_REQUIRE(p.tw != nullptr, "twiddle table");
+  RFX_REQUIRE(p.hops_per_cta > 0, "hops_per_cta");
+  switch (p.n_fft) {
+    case 512: return launch_istft_t<8>(p, B, stream);
+    case 1024: return launch_istft_t<9>(p, B, stream);
+    case 2048: return launch_istft_t<10>(p, B, stream);
+    case 4096: return launch_istft_t<11>(p, B, stream);
+    default: set_error("istft: n_fft must be 512, 1024, 2048 or 4096"); return 2;
+  }
+}
+
+}  // namespace rfx

@@ -1,0 +1,327 @@
+// Open-Unmix effect-removal model on the GPU: the whole of remfx/models.py:303-304
+// (OpenUnmixModel.sample) = Separator.forward (umx/openunmix/model.py:242-319) as 11 kernel launches:
+//
+//   STFT+|.|+input affine -> fc1+bn1+tanh -> 3 x [W_ih GEMM ; BiLSTM recurrence] -> fc2+bn2+ReLU
+//   -> fc3+bn3+output affine+ReLU (= ratio mask) -> mask x STFT -> iSTFT (OLA, envelope, crop)
+//
+// Everything is frame-major ([B*F, features]); no transposes, no phase (atan2/cos/sin) detour:
+// wiener(niter=0, softmask=False) (filtering.py:442-451) is algebraically mask * STFT(x).
+#include "kernels.h"
+#include "../../include/remfx_b200.h"
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace rfx {
+
+struct DevBuf {
+  float* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    release();
+    RFX_CHECK_CUDA(cudaMalloc(&p, count * sizeof(float)));
+    n = count;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+__global__ void bn_fold_kernel(const float* g, const float* b, const float* mean, const float* var, float eps, float* scale, float* shift, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float s = g[i] / sqrtf(var[i] + eps);
+    scale[i] = s;
+    shift[i] = b[i] - mean[i] * s;
+  }
+}
+__global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = a[i] + b[i];
+}
+
+int launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale, float* shift,
+                   int n, cudaStream_t stream) {
+  bn_fold_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(gamma, beta, mean, var, eps, scale, shift, n);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_add_vec(const float* a, const float* b, float* out, int n, cudaStream_t stream) {
+  add_vec_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(a, b, out, n);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rfx
+
+using namespace rfx;
+
+struct rfx_umx {
+  rfx_umx_config cfg;
+  int bins = 0, H = 0;
+  std::map<std::string, DevBuf> params;
+  // derived at finalize()
+  DevBuf bn_s[3], bn_t[3];
+  std::vector<DevBuf> lstm_bias, wih_cat, whh_cat;
+  std::vector<DevBuf> packed_store;
+  PackedW fc1p, fc2p, fc3p;
+  std::vector<PackedW> wihp;
+  bool finalized = false;
+
+  ~rfx_umx() {
+    for (auto& kv : params) kv.second.release();
+    for (int i = 0; i < 3; ++i) { bn_s[i].release(); bn_t[i].release(); }
+    for (auto& b : lstm_bias) b.release();
+    for (auto& b : wih_cat) b.release();
+    for (auto& b : whh_cat) b.release();
+    for (auto& b : packed_store) b.release();
+  }
+};
+
+namespace {
+
+struct UmxLayout {
+  int F, M, lda1, ldm;
+  size_t off_x, off_out, off_Z, off_A1, off_XC, off_G, off_H1, off_H2, off_Y2, off_mask, total;
+};
+
+UmxLayout umx_layout(const rfx_umx* h, int B, int T) {
+  UmxLayout L;
+  L.F = T / h->cfg.hop + 1;
+  L.M = B * L.F;
+  L.lda1 = ceil_div(h->bins, 64) * 64;
+  L.ldm = ceil_div(h->bins, 4) * 4;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
+  const size_t M = L.M;
+  L.off_x = take((size_t)B * T * 4);
+  L.off_out = take((size_t)B * T * 4);
+  L.off_Z = take(M * h->bins * 8);
+  L.off_A1 = take(M * L.lda1 * 4);
+  L.off_XC = take(M * 2 * h->cfg.hidden * 4);
+  L.off_G = take(M * 8 * h->H * 4);
+  L.off_H1 = take(M * h->cfg.hidden * 4);
+  L.off_H2 = take(M * h->cfg.hidden * 4);
+  L.off_Y2 = take(M * h->cfg.hidden * 4);
+  L.off_mask = take(M * L.ldm * 4);
+  L.total = o;
+  return L;
+}
+
+const float* P(const rfx_umx* h, const std::string& k) {
+  auto it = h->params.find(k);
+  return it == h->params.end() ? nullptr : it->second.p;
+}
+
+int gemm(const rfx_umx* h, const float* A, int lda, int M, const PackedW& Wp, const float* Wraw, float* C, int ldc, const Epilogue& e,
+         cudaStream_t s) {
+  if (h->cfg.gemm_impl == 1) return launch_gemm_simt(A, lda, M, Wraw, Wp.K, Wp.N, Wp.K, C, ldc, e, s);
+  return launch_gemm_tc(A, lda, M, Wp, C, ldc, e, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rfx_umx_create(const rfx_umx_config* cfg, rfx_umx_t** out) {
+  RFX_REQUIRE(cfg && out, "null argument");
+  RFX_REQUIRE(cfg->n_fft == 512 || cfg->n_fft == 1024 || cfg->n_fft == 2048 || cfg->n_fft == 4096, "n_fft must be 512/1024/2048/4096");
+  RFX_REQUIRE(cfg->hop > 0 && cfg->hop % 2 == 0 && cfg->n_fft % cfg->hop == 0, "hop must be even and divide n_fft");
+  RFX_REQUIRE(cfg->hidden == 512, "hidden must be 512 (LSTM kernel is specialised for 256 units per direction)");
+  RFX_REQUIRE(cfg->nb_layers >= 1 && cfg->nb_layers <= 8, "nb_layers in [1,8]");
+  RFX_REQUIRE(cfg->gemm_impl == 0 || cfg->gemm_impl == 1, "gemm_impl 0 or 1");
+  rfx_umx* h = new rfx_umx();
+  h->cfg = *cfg;
+  h->bins = cfg->n_fft / 2 + 1;
+  h->H = cfg->hidden / 2;
+  *out = h;
+  return 0;
+}
+
+void rfx_umx_destroy(rfx_umx_t* h) { delete h; }
+
+int rfx_umx_load_param(rfx_umx_t* h, const char* key, const float* src, int64_t numel, void* stream) {
+  RFX_REQUIRE(h && key && src && numel > 0, "bad argument");
+  DevBuf& b = h->params[key];
+  if (b.n != (size_t)numel) {
+    if (b.alloc((size_t)numel)) return 1;
+  }
+  RFX_CHECK_CUDA(cudaMemcpyAsync(b.p, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  h->finalized = false;
+  return 0;
+}
+
+int rfx_umx_finalize(rfx_umx_t* h, void* stream) {
+  RFX_REQUIRE(h, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int hid = h->cfg.hidden, H = h->H, bins = h->bins, L = h->cfg.nb_layers;
+  auto need = [&](const std::string& k, size_t n) -> int {
+    auto it = h->params.find(k);
+    if (it == h->params.end()) { set_error("umx: missing parameter '" + k + "'"); return 2; }
+    if (it->second.n != n) { set_error("umx: parameter '" + k + "' has " + std::to_string(it->second.n) + " elements, expected " + std::to_string(n)); return 2; }
+    return 0;
+  };
+  int rc;
+  if ((rc = need("window", h->cfg.n_fft))) return rc;
+  if ((rc = need("input_mean", bins)) || (rc = need("input_scale", bins)) || (rc = need("output_scale", bins)) || (rc = need("output_mean", bins))) return rc;
+  if ((rc = need("fc1.weight", (size_t)hid * bins)) || (rc = need("fc2.weight", (size_t)hid * 2 * hid)) || (rc = need("fc3.weight", (size_t)bins * hid))) return rc;
+  const int bn_n[3] = {hid, hid, bins};
+  for (int i = 0; i < 3; ++i) {
+    const std::string p = "bn" + std::to_string(i + 1);
+    for (const char* f : {".weight", ".bias", ".running_mean", ".running_var"})
+      if ((rc = need(p + f, bn_n[i]))) return rc;
+    if (h->bn_s[i].alloc(bn_n[i]) || h->bn_t[i].alloc(bn_n[i])) return 1;
+    // BatchNorm1d eval (model.py:135,151,157): (x - mean) / sqrt(var + 1e-5) * gamma + beta = x * s + t
+    if ((rc = launch_bn_fold(P(h, p + ".weight"), P(h, p + ".bias"), P(h, p + ".running_mean"), P(h, p + ".running_var"), 1e-5f,
+                             h->bn_s[i].p, h->bn_t[i].p, bn_n[i], s)))
+      return rc;
+  }
+  for (auto& b : h->lstm_bias) b.release();
+  for (auto& b : h->wih_cat) b.release();
+  for (auto& b : h->whh_cat) b.release();
+  for (auto& b : h->packed_store) b.release();
+  h->lstm_bias.assign(L, DevBuf());
+  h->wih_cat.assign(L, DevBuf());
+  h->whh_cat.assign(L, DevBuf());
+  h->wihp.assign(L, PackedW());
+  h->packed_store.assign(L + 3, DevBuf());
+  for (int l = 0; l < L; ++l) {
+    if (h->lstm_bias[l].alloc(8 * H) || h->wih_cat[l].alloc((size_t)8 * H * hid) || h->whh_cat[l].alloc((size_t)8 * H * H)) return 1;
+    for (int d = 0; d < 2; ++d) {
+      const std::string sfx = "_l" + std::to_string(l) + (d ? "_reverse" : "");
+      if ((rc = need("lstm.weight_ih" + sfx, (size_t)4 * H * hid)) || (rc = need("lstm.weight_hh" + sfx, (size_t)4 * H * H)) ||
+          (rc = need("lstm.bias_ih" + sfx, 4 * H)) || (rc = need("lstm.bias_hh" + sfx, 4 * H)))
+        return rc;
+      RFX_CHECK_CUDA(cudaMemcpyAsync(h->wih_cat[l].p + (size_t)d * 4 * H * hid, P(h, "lstm.weight_ih" + sfx), (size_t)4 * H * hid * 4,
+                                     cudaMemcpyDeviceToDevice, s));
+      RFX_CHECK_CUDA(cudaMemcpyAsync(h->whh_cat[l].p + (size_t)d * 4 * H * H, P(h, "lstm.weight_hh" + sfx), (size_t)4 * H * H * 4,
+                                     cudaMemcpyDeviceToDevice, s));
+      if ((rc = launch_add_vec(P(h, "lstm.bias_ih" + sfx), P(h, "lstm.bias_hh" + sfx), h->lstm_bias[l].p + d * 4 * H, 4 * H, s))) return rc;
+    }
+    const int BN = choose_bn(8 * H);
+    if (h->packed_store[l].alloc(packed_weight_bytes(8 * H, hid, BN) / 4)) return 1;
+    if ((rc = pack_weights(h->wih_cat[l].p, hid, 8 * H, hid, BN, h->packed_store[l].p, &h->wihp[l], s))) return rc;
+  }
+  struct { const char* key; int N, K; PackedW* dst; } fcs[3] = {
+      {"fc1.weight", hid, bins, &h->fc1p}, {"fc2.weight", hid, 2 * hid, &h->fc2p}, {"fc3.weight", bins, hid, &h->fc3p}};
+  for (int i = 0; i < 3; ++i) {
+    const int BN = choose_bn(fcs[i].N);
+    if (h->packed_store[L + i].alloc(packed_weight_bytes(fcs[i].N, fcs[i].K, BN) / 4)) return 1;
+    if ((rc = pack_weights(P(h, fcs[i].key), fcs[i].K, fcs[i].N, fcs[i].K, BN, h->packed_store[L + i].p, fcs[i].dst, s))) return rc;
+  }
+  h->finalized = true;
+  return 0;
+}
+
+size_t rfx_umx_workspace_bytes(const rfx_umx_t* h, int B, int T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  return umx_layout(h, B, T).total;
+}
+
+int rfx_umx_launches_per_call(const rfx_umx_t* h) { return h ? 5 + 2 * h->cfg.nb_layers : 0; }
+
+int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  RFX_REQUIRE(h && x && out && workspace, "null argument");
+  RFX_REQUIRE(h->finalized, "rfx_umx_finalize has not been called since the last parameter load");
+  RFX_REQUIRE(B > 0 && T > h->cfg.n_fft / 2, "need B > 0 and T > n_fft/2 (reflect padding)");
+  RFX_REQUIRE(T % h->cfg.hop == 0, "T must be a multiple of the hop length");
+  const UmxLayout L = umx_layout(h, B, T);
+  RFX_REQUIRE(workspace_bytes >= L.total, "workspace too small (see rfx_umx_workspace_bytes)");
+  RFX_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float2* Z = reinterpret_cast<float2*>(ws + L.off_Z);
+  float* A1 = reinterpret_cast<float*>(ws + L.off_A1);
+  float* XC = reinterpret_cast<float*>(ws + L.off_XC);
+  float* G = reinterpret_cast<float*>(ws + L.off_G);
+  float* Hb[2] = {reinterpret_cast<float*>(ws + L.off_H1), reinterpret_cast<float*>(ws + L.off_H2)};
+  float* Y2 = reinterpret_cast<float*>(ws + L.off_Y2);
+  float* mask = reinterpret_cast<float*>(ws + L.off_mask);
+  const int hid = h->cfg.hidden, H = h->H, nl = h->cfg.nb_layers;
+  const float2* tw = twiddles(h->cfg.n_fft);
+  RFX_REQUIRE(tw != nullptr, "twiddle table allocation failed");
+  int rc;
+
+  // (1) STFT (transforms.py:106-116) + ComplexNorm (:211) + input shift/scale (model.py:127-128)
+  StftParams sp{};
+  sp.x = x; sp.x_bstride = T; sp.T = T;
+  sp.x_aligned8 = (((uintptr_t)x & 7) == 0 && (T % 2 == 0)) ? 1 : 0;
+  sp.window = P(h, "window"); sp.tw = tw;
+  sp.n_fft = h->cfg.n_fft; sp.hop = h->cfg.hop; sp.F = L.F;
+  sp.scale = 1.0f; sp.alpha = 1.0f; sp.mode = STFT_UMX_MAG;
+  sp.Z = Z; sp.ldz = h->bins; sp.A = A1; sp.lda = L.lda1;
+  sp.in_mean = P(h, "input_mean"); sp.in_scale = P(h, "input_scale");
+  if ((rc = launch_stft(sp, B, s))) return rc;
+
+  // (2) fc1 + bn1 + tanh (model.py:132-138) -> first half of the skip-concat buffer
+  Epilogue e1; e1.s1 = h->bn_s[0].p; e1.t1 = h->bn_t[0].p; e1.act = ACT_TANH;
+  if ((rc = gemm(h, A1, L.lda1, L.M, h->fc1p, P(h, "fc1.weight"), XC, 2 * hid, e1, s))) return rc;
+
+  // (3) BiLSTM stack (model.py:141): per layer one input-projection GEMM + one recurrent cluster kernel
+  const float* lin = XC; int ldin = 2 * hid;
+  for (int l = 0; l < nl; ++l) {
+    Epilogue eb; eb.t1 = h->lstm_bias[l].p;
+    if ((rc = gemm(h, lin, ldin, L.M, h->wihp[l], h->wih_cat[l].p, G, 8 * H, eb, s))) return rc;
+    float* hout; int ldh;
+    if (l == nl - 1) { hout = XC + hid; ldh = 2 * hid; }  // torch.cat([x, lstm_out], -1) (model.py:144) for free
+    else { hout = Hb[l & 1]; ldh = hid; }
+    if ((rc = launch_lstm_layer(G, 8 * H, h->whh_cat[l].p, hout, ldh, B, L.F, H, s))) return rc;
+    lin = hout; ldin = ldh;
+  }
+
+  // (4) fc2 + bn2 + ReLU (model.py:147-150)
+  Epilogue e2; e2.s1 = h->bn_s[1].p; e2.t1 = h->bn_t[1].p; e2.act = ACT_RELU;
+  if ((rc = gemm(h, XC, 2 * hid, L.M, h->fc2p, P(h, "fc2.weight"), Y2, hid, e2, s))) return rc;
+
+  // (5) fc3 + bn3 + output scale/mean + ReLU (model.py:153-164) = the non-negative ratio mask
+  Epilogue e3; e3.s1 = h->bn_s[2].p; e3.t1 = h->bn_t[2].p; e3.s2 = P(h, "output_scale"); e3.t2 = P(h, "output_mean"); e3.act = ACT_RELU;
+  if ((rc = gemm(h, Y2, hid, L.M, h->fc3p, P(h, "fc3.weight"), mask, L.ldm, e3, s))) return rc;
+
+  // (6) `* mix` (model.py:164) + wiener niter=0 (filtering.py:442-451) + iSTFT (transforms.py:168-177)
+  IstftParams ip{};
+  ip.Z = Z; ip.ldz = h->bins; ip.mask = mask; ip.ldm = L.ldm;
+  ip.window = P(h, "window"); ip.tw = tw;
+  ip.n_fft = h->cfg.n_fft; ip.hop = h->cfg.hop; ip.F = L.F; ip.length = T;
+  ip.scale = 1.0f; ip.out = out; ip.out_bstride = T; ip.hops_per_cta = 16;
+  return launch_istft(ip, B, s);
+}
+
+int rfx_umx_sample_host(rfx_umx_t* h, const float* x_host, int B, int T, float* out_host, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  RFX_REQUIRE(h && x_host && out_host && workspace, "null argument");
+  const UmxLayout L = umx_layout(h, B, T);
+  RFX_REQUIRE(workspace_bytes >= L.total, "workspace too small (see rfx_umx_workspace_bytes)");
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* xd = reinterpret_cast<float*>(ws + L.off_x);
+  float* od = reinterpret_cast<float*>(ws + L.off_out);
+  RFX_CHECK_CUDA(cudaMemcpyAsync(xd, x_host, (size_t)B * T * 4, cudaMemcpyHostToDevice, s));
+  int rc = rfx_umx_sample(h, xd, B, T, od, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  RFX_CHECK_CUDA(cudaMemcpyAsync(out_host, od, (size_t)B * T * 4, cudaMemcpyDeviceToHost, s));
+  RFX_CHECK_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int rfx_umx_debug_tap(rfx_umx_t* h, int what, const void* workspace, int B, int T, float* dst, int* ld, void* stream) {
+  RFX_REQUIRE(h && workspace && dst && ld, "null argument");
+  const UmxLayout L = umx_layout(h, B, T);
+  const uint8_t* ws = reinterpret_cast<const uint8_t*>(workspace);
+  const float* src = nullptr;
+  size_t count = 0;
+  switch (what) {
+    case 0: src = reinterpret_cast<const float*>(ws + L.off_A1); *ld = L.lda1; count = (size_t)L.M * L.lda1; break;
+    case 1:
+    case 2: src = reinterpret_cast<const float*>(ws + L.off_XC); *ld = 2 * h->cfg.hidden; count = (size_t)L.M * 2 * h->cfg.hidden; break;
+    case 3: src = reinterpret_cast<const float*>(ws + L.off_mask); *ld = L.ldm; count = (size_t)L.M * L.ldm; break;
+    default: set_error("umx debug tap: unknown id"); return 2;
+  }
+  RFX_CHECK_CUDA(cudaMemcpyAsync(dst, src, count * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+"""Drop-in network wrappers: the reference's plug-in boundary (`cfg/model/*.yaml` `_target_`s).
+
+Same constructor kwargs, `forward((x, target)) -> (loss, output)` / `sample(x) -> output`
+signatures and `state_dict` key layout as `remfx.models.{OpenUnmixModel, TCNModel, DemucsModel}`
+(remfx/models.py:259-390), so `cfg/exp/*` can select them by overriding `model.network._target_`.
+The torch.nn sub-modules below are *parameter containers only* (they give the reference's
+state_dict keys and default initialisation); their `forward` is never called -- all math runs in
+the hand-written sm_100a kernels behind the C ABI (include/remfx_b200.h).  There is no CPU or
+eager fallback: calling these modules with CPU tensors raises.
+
+Parity is defined in eval mode: BatchNorm uses running statistics
+and dropout is off, which is how the reference's chain/test scripts are meant to run the models.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+
+
+class _OpenUnmixParams(nn.Module):
+    """Parameter layout of umx/openunmix/model.py:33-98 (OpenUnmix.__init__), bidirectional."""
+
+    def __init__(self, nb_bins: int, nb_channels: int = 1, hidden_size: int = 512, nb_layers: int = 3):
+        super().__init__()
+        self.nb_bins = nb_bins
+        self.hidden_size = hidden_size
+        self.nb_layers = nb_layers
+        self.fc1 = nn.Linear(nb_bins * nb_channels, hidden_size, bias=False)
+        self.bn1 = nn.BatchNorm1d(hidden_size)
+        self.lstm = nn.LSTM(input_size=hidden_size, hidden_size=hidden_size // 2, num_layers=nb_layers, bidirectional=True,
+                            batch_first=False, dropout=0.4 if nb_layers > 1 else 0)
+        self.fc2 = nn.Linear(hidden_size * 2, hidden_size, bias=False)
+        self.bn2 = nn.BatchNorm1d(hidden_size)
+        self.fc3 = nn.Linear(hidden_size, nb_bins * nb_channels, bias=False)
+        self.bn3 = nn.BatchNorm1d(nb_bins * nb_channels)
+        self.input_mean = nn.Parameter(torch.zeros(nb_bins))
+        self.input_scale = nn.Parameter(torch.ones(nb_bins))
+        self.output_scale = nn.Parameter(torch.ones(nb_bins))
+        self.output_mean = nn.Parameter(torch.ones(nb_bins))
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container; the computation lives in libremfx_b200.so")
+
+
+class _WindowHolder(nn.Module):
+    def __init__(self, n_fft: int):
+        super().__init__()
+        self.window = nn.Parameter(torch.hann_window(n_fft), requires_grad=False)
+
+
+class _SeparatorParams(nn.Module):
+    """State layout of umx/openunmix/model.py:197-240 (Separator.__init__)."""
+
+    def __init__(self, target_models, sample_rate: float, n_fft: int):
+        super().__init__()
+        self.stft = _WindowHolder(n_fft)
+        self.istft = _WindowHolder(n_fft)
+        self.target_models = nn.ModuleDict(target_models)
+        self.register_buffer("sample_rate", torch.as_tensor(float(sample_rate)))
+
+
+class OpenUnmixModel(nn.Module):
+    """B200-native drop-in for `remfx.models.OpenUnmixModel` (remfx/models.py:259-304)."""
+
+    def __init__(self, n_fft: int = 2048, hop_length: int = 512, n_channels: int = 1, alpha: float = 0.3,
+                 sample_rate: int = 22050, gemm_impl: str = "tc"):
+        super().__init__()
+        if n_channels != 1:
+            raise ValueError("remfx_b200.OpenUnmixModel supports mono audio only (RemFx uses n_channels=1)")
+        self.n_channels = n_channels
+        self.n_fft = n_fft
+        self.hop_length = hop_length
+        self.alpha = alpha
+        self.register_buffer("window", torch.hann_window(n_fft))
+        self.num_bins = n_fft // 2 + 1
+        self.sample_rate = sample_rate
+        self.model = _OpenUnmixParams(nb_bins=self.num_bins, nb_channels=n_channels)
+        self.separator = _SeparatorParams({"other": self.model}, sample_rate, n_fft)
+        self.gemm_impl = gemm_impl
+        self._handle: Optional[C.c_void_p] = None
+        self._stamp = None
+        self._ws: Optional[Tensor] = None
+
+    # ------------------------------------------------------------------ C-ABI handle management
+    def _tensors(self):
+        core = {k: v for k, v in self.model.state_dict(keep_vars=True).items() if v.dtype == torch.float32}
+        core["window"] = self.separator.stft.window
+        return core
+
+    def _sync(self, device) -> C.c_void_p:
+        tensors = self._tensors()
+        stamp = (str(device),) + tuple((k, t.data_ptr(), t._version) for k, t in tensors.items())
+        L = _lib.lib()
+        if self._handle is not None and stamp == self._stamp:
+            return self._handle
+        if self._handle is None:
+            cfg = _lib.UmxConfig(self.n_fft, self.hop_length, self.model.hidden_size, self.model.nb_layers,
+                                 0 if self.gemm_impl == "tc" else 1)
+            h = C.c_void_p()
+            _lib.check(L.rfx_umx_create(C.byref(cfg), C.byref(h)), "rfx_umx_create")
+            self._handle = h
+        stream = _lib.cur_stream()
+        for k, t in tensors.items():
+            if t.device != device:
+                raise _lib.RfxError(f"parameter {k} is on {t.device}, input on {device}: call .to(device) first")
+            tc = t.detach().contiguous()
+            _lib.check(L.rfx_umx_load_param(self._handle, k.encode(), tc.data_ptr(), tc.numel(), stream), f"load {k}")
+        _lib.check(L.rfx_umx_finalize(self._handle, stream), "rfx_umx_finalize")
+        self._stamp = stamp
+        return self._handle
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h is not None:
+            try:
+                _lib.lib().rfx_umx_destroy(h)
+            except Exception:
+                pass
+
+    def _workspace(self, h, B: int, T: int, device) -> Tensor:
+        need = _lib.lib().rfx_umx_workspace_bytes(h, B, T)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    # ------------------------------------------------------------------ reference API
+    def sample(self, x: Tensor) -> Tensor:
+        """(B, 1, T) -> (B, 1, T): `self.separator(x).squeeze(1)` of the reference (models.py:303-304)."""
+        if x.dim() != 3 or x.shape[1] != 1:
+            raise ValueError(f"expected input of shape (batch, 1, time), got {tuple(x.shape)}")
+        _lib.require_device(x)
+        if x.dtype != torch.float32:
+            raise ValueError("expected float32 audio")
+        x = x.contiguous()
+        B, _, T = x.shape
+        with torch.cuda.device(x.device):
+            h = self._sync(x.device)
+            ws = self._workspace(h, B, T, x.device)
+            out = torch.empty_like(x)
+            rc = _lib.lib().rfx_umx_sample(h, x.data_ptr(), B, T, out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.cur_stream())
+            _lib.check(rc, "rfx_umx_sample")
+        return out
+
+    def sample_host(self, x_host: Tensor, out_host: Optional[Tensor] = None, device="cuda:0") -> Tensor:
+        """End-to-end call on HOST buffers (pinned recommended): H2D, kernels, D2H, stream sync."""
+        if x_host.is_cuda or x_host.dim() != 3 or x_host.shape[1] != 1 or x_host.dtype != torch.float32:
+            raise ValueError("expected a float32 CPU tensor of shape (batch, 1, time)")
+        device = torch.device(device)
+        x_host = x_host.contiguous()
+        B, _, T = x_host.shape
+        if out_host is None:
+            out_host = torch.empty_like(x_host, pin_memory=True)
+        with torch.cuda.device(device):
+            h = self._sync(device)
+            ws = self._workspace(h, B, T, device)
+            rc = _lib.lib().rfx_umx_sample_host(h, x_host.data_ptr(), B, T, out_host.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                _lib.cur_stream())
+            _lib.check(rc, "rfx_umx_sample_host")
+        return out_host
+
+    def forward(self, batch):
+        """(x, target) -> (loss, sep_out) with loss = MRSTFT + 100 * L1 (models.py:294-301)."""
+        from .losses import remfx_loss
+
+        x, target = batch
+        sep_out = self.sample(x)
+        return remfx_loss(sep_out, target), sep_out
+
+    def launches_per_call(self) -> int:
+        return 5 + 2 * self.model.nb_layers

@@ -1,0 +1,71 @@
+// Host emulation of the shared-memory FFT index arithmetic in remfx_b200/csrc/fft.cuh.
+// Build:  nvcc -O2 -o /tmp/fft_emul tests/host/fft_emul.cu   (runs on the CPU; no GPU needed)
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../remfx_b200/csrc/fft.cuh"
+using namespace rfx;
+
+static int run(int n_fft) {
+  const int NC = n_fft / 2;
+  int log2nc = 0;
+  while ((1 << log2nc) < NC) ++log2nc;
+  std::vector<float2> tw(n_fft);
+  for (int m = 0; m < n_fft; ++m) tw[m] = make_float2((float)cos(-2.0 * M_PI * m / n_fft), (float)sin(-2.0 * M_PI * m / n_fft));
+  std::vector<float> x(n_fft);
+  srand(n_fft);
+  for (auto& v : x) v = (float)rand() / RAND_MAX - 0.5f;
+  std::vector<float2> a(NC), b(NC);
+  for (int n = 0; n < NC; ++n) a[n] = make_float2(x[2 * n], x[2 * n + 1]);
+  float2 *in = a.data(), *out = b.data();
+  for (int Ns = 1; Ns * 4 <= NC; Ns *= 4) {
+    for (int j = 0; j < NC / 4; ++j) fft_pass_r4(in, out, tw.data(), NC, Ns, n_fft / (4 * Ns), j);
+    std::swap(in, out);
+  }
+  if (log2nc & 1) {
+    for (int j = 0; j < NC / 2; ++j) fft_pass_r2_last(in, out, tw.data(), NC, j);
+    std::swap(in, out);
+  }
+  double maxerr = 0, maxref = 0;
+  std::vector<float2> X(NC + 1);
+  for (int k = 0; k <= NC; ++k) {
+    X[k] = rfft_post(in, tw.data(), NC, k);
+    double re = 0, im = 0;
+    for (int n = 0; n < n_fft; ++n) {
+      re += x[n] * cos(-2.0 * M_PI * k * n / n_fft);
+      im += x[n] * sin(-2.0 * M_PI * k * n / n_fft);
+    }
+    maxerr = fmax(maxerr, hypot(X[k].x - re, X[k].y - im));
+    maxref = fmax(maxref, hypot(re, im));
+  }
+  // inverse
+  for (int k = 0; k < NC; ++k) {
+    float2 xk = X[k], xn = X[NC - k];
+    if (k == 0) { xk.y = 0; xn.y = 0; }
+    a[k] = irfft_pre(xk, xn, tw[k]);
+  }
+  in = a.data(); out = b.data();
+  for (int Ns = 1; Ns * 4 <= NC; Ns *= 4) {
+    for (int j = 0; j < NC / 4; ++j) fft_pass_r4(in, out, tw.data(), NC, Ns, n_fft / (4 * Ns), j);
+    std::swap(in, out);
+  }
+  if (log2nc & 1) {
+    for (int j = 0; j < NC / 2; ++j) fft_pass_r2_last(in, out, tw.data(), NC, j);
+    std::swap(in, out);
+  }
+  double ierr = 0;
+  for (int n = 0; n < NC; ++n) {
+    ierr = fmax(ierr, fabs(in[n].x / NC - x[2 * n]));
+    ierr = fmax(ierr, fabs(-in[n].y / NC - x[2 * n + 1]));
+  }
+  printf("n_fft %d  fwd max err %.3e (max |X| %.2f)  inverse max err %.3e\n", n_fft, maxerr, maxref, ierr);
+  return (maxerr < 2e-5 * maxref + 1e-5 && ierr < 1e-5) ? 0 : 1;
+}
+
+int main() {
+  int bad = 0;
+  for (int n : {64, 128, 512, 1024, 2048, 4096}) bad += run(n);
+  printf(bad ? "FAIL\n" : "OK\n");
+  return bad;
+}

@@ -1,0 +1,52 @@
+"""`not gpu`: the C-ABI library builds, loads and exports every symbol include/remfx_b200.h declares;
+the Python drop-ins expose the reference's state_dict layout.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    from remfx_b200 import build
+
+    return build.build()
+
+
+def test_header_symbols_are_exported(libpath):
+    hdr = open(os.path.join(ROOT, "include", "remfx_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rfx_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 10
+    lib = ctypes.CDLL(libpath)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/remfx_b200.h but not exported"
+    from remfx_b200 import _lib
+
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert _lib.lib().rfx_abi_version() == 1
+
+
+def test_umx_state_dict_layout_matches_reference():
+    from remfx_b200.models import OpenUnmixModel
+
+    m = OpenUnmixModel(n_fft=2048, hop_length=512, n_channels=1, alpha=0.3, sample_rate=48000)
+    ref_keys = set(weights.umx_state(0).keys())  # pinned against the real reference in test_oracle_cpu / make_golden
+    assert set(m.state_dict().keys()) == ref_keys
+    m.load_state_dict(weights.umx_state(0), strict=True)
+    assert m.model.fc1.weight is m.separator.target_models["other"].fc1.weight
+
+
+def test_no_cpu_fallback():
+    from remfx_b200 import _lib
+    from remfx_b200.models import OpenUnmixModel
+
+    m = OpenUnmixModel()
+    with pytest.raises(_lib.RfxError):
+        m.sample(torch.zeros(1, 1, 8192))

@@ -1,0 +1,79 @@
+"""-m gpu: Open-Unmix drop-in (remfx_b200.models.OpenUnmixModel) vs the oracle and the reference golden."""
+import pytest
+import torch
+
+from oracle import umx as oumx
+from oracle import weights
+from tests.util import golden, relrms
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # BASELINE.json north_star: 1e-4 relative RMS (fp32)
+
+
+def _model(sd, impl="tc"):
+    from remfx_b200.models import OpenUnmixModel
+
+    m = OpenUnmixModel(n_fft=2048, hop_length=512, n_channels=1, alpha=0.3, sample_rate=48000, gemm_impl=impl)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_sample_matches_reference_golden(impl):
+    g = golden("umx_sample.npz")
+    sd = weights.umx_state(int(g["wseed"]))
+    x = weights.synth_audio(int(g["xseed"]), int(g["B"]), int(g["T"]))
+    out = _model(sd, impl).sample(x.cuda())
+    assert out.shape == (2, 1, 16384)
+    err = relrms(out, torch.from_numpy(g["out"]))
+    assert err < TOL, err
+
+
+@pytest.mark.parametrize("B,T", [(1, 8192), (3, 32768), (5, 262144)])
+def test_sample_matches_oracle(B, T):
+    sd = weights.umx_state(7)
+    x = weights.synth_audio(100 + B, B, T)
+    out = _model(sd).sample(x.cuda())
+    ref = oumx.sample(x, sd)
+    err = relrms(out, ref)
+    assert err < TOL, err
+
+
+def test_sample_host_equals_device_path():
+    sd = weights.umx_state(7)
+    x = weights.synth_audio(55, 2, 16384)
+    m = _model(sd)
+    a = m.sample(x.cuda()).cpu()
+    b = m.sample_host(x.pin_memory())
+    assert torch.equal(a, b)
+
+
+def test_items_are_independent():
+    """Size-independent property: the path is per-item, so batching must not change an item's output."""
+    sd = weights.umx_state(7)
+    x = weights.synth_audio(77, 4, 16384)
+    m = _model(sd)
+    full = m.sample(x.cuda())
+    single = m.sample(x[2:3].cuda())
+    assert relrms(full[2:3], single) < 1e-6
+
+
+def test_param_update_is_picked_up():
+    sd = weights.umx_state(7)
+    x = weights.synth_audio(78, 1, 8192).cuda()
+    m = _model(sd)
+    a = m.sample(x)
+    with torch.no_grad():
+        m.model.output_scale.mul_(0.5)
+    b = m.sample(x)
+    assert relrms(a, b) > 1e-3
+
+
+def test_bad_inputs_raise():
+    sd = weights.umx_state(7)
+    m = _model(sd)
+    with pytest.raises(ValueError):
+        m.sample(torch.zeros(2, 16384, device="cuda"))
+    with pytest.raises(RuntimeError):
+        m.sample(torch.zeros(1, 1, 16384))

@@ -1,0 +1,104 @@
+"""`not gpu`: pin the oracle restatements against the golden vectors produced by the UNCHANGED
+reference modules (oracle/make_golden.py), against torch.stft/istft (the calls the reference makes),
+and -- when /root/reference is present -- against the live reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss as oloss
+from oracle import refshim
+from oracle import stft as ostft
+from oracle import tcn as otcn
+from oracle import umx as oumx
+from oracle import weights
+from tests.util import golden, relrms
+
+
+def test_stft_matches_torch_and_golden():
+    g = golden("stft_kat.npz")
+    x = weights.synth_audio(int(g["seed"]), int(g["B"]), int(g["T"]))[:, 0]
+    win = torch.hann_window(2048)
+    Z = ostft.stft(x, 2048, 512, win)
+    Zt = torch.stft(x, 2048, 512, window=win, return_complex=True)
+    assert relrms(torch.view_as_real(Z), torch.view_as_real(Zt)) < 1e-6
+    assert relrms(torch.view_as_real(Z), torch.from_numpy(g["Z"])) < 1e-6
+    y = ostft.istft(Z, 2048, 512, win, length=x.shape[-1])
+    assert relrms(y, torch.from_numpy(g["y"])) < 1e-6
+
+
+@pytest.mark.parametrize("nfft", [1024, 2048, 4096])
+@pytest.mark.parametrize("hopdiv", [2, 4])
+@pytest.mark.parametrize("T", [4096, 44100])
+def test_stft_istft_roundtrip(nfft, hopdiv, T):
+    """umx/tests/test_transforms.py:42-51: round trip RMSE < 1e-6."""
+    hop = nfft // hopdiv
+    x = torch.rand(2, T, generator=torch.Generator().manual_seed(T + nfft))
+    win = torch.hann_window(nfft)
+    Z = ostft.stft(x, nfft, hop, win)
+    Zt = torch.stft(x, nfft, hop, window=win, return_complex=True)
+    assert (Z - Zt).abs().max() < 1e-3 * Zt.abs().max()
+    y = ostft.istft(Z, nfft, hop, win, length=T)
+    assert float(torch.sqrt(((x - y) ** 2).mean())) < 1e-6
+
+
+def test_short_window_padding_matches_torch():
+    x = weights.synth_audio(5, 1, 8192)[:, 0]
+    for n_fft, hop, win in oloss.RESOLUTIONS:
+        w = torch.hann_window(win)
+        Zt = torch.stft(x, n_fft, hop, win, w, return_complex=True)
+        Z = ostft.stft(x, n_fft, hop, ostft.padded_window(win, n_fft))
+        assert relrms(torch.view_as_real(Z), torch.view_as_real(Zt)) < 1e-6
+
+
+def test_mrstft_anchors():
+    a = weights.synth_audio(7, 2, 16384)
+    assert float(oloss.mrstft(a, a)) == 0.0
+    assert abs(float(oloss.mrstft(0.5 * a, a)) - (0.5 + np.log(2.0))) < 1e-5
+
+
+def test_crops():
+    x = torch.arange(10.0)[None]
+    assert ostft.center_crop(x, 4).tolist() == [[3.0, 4.0, 5.0, 6.0]]
+    assert ostft.causal_crop(x, 4).tolist() == [[5.0, 6.0, 7.0, 8.0]]  # drops the last sample (reference quirk)
+
+
+def test_umx_oracle_matches_golden():
+    g = golden("umx_sample.npz")
+    sd = weights.umx_state(int(g["wseed"]))
+    assert abs(weights.checksum(sd) - float(g["wsum"])) < 1e-6 * abs(float(g["wsum"]))
+    x = weights.synth_audio(int(g["xseed"]), int(g["B"]), int(g["T"]))
+    t = weights.synth_audio(int(g["tseed"]), int(g["B"]), int(g["T"]))
+    ref = torch.from_numpy(g["out"])
+    assert relrms(oumx.sample(x, sd), ref) < 1e-5
+    assert relrms(oumx.sample(x, sd, fast_lstm=False, wiener_trig=False), ref) < 1e-5
+    loss, _ = oumx.forward((x, t), sd)
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+
+
+def test_tcn_oracle_matches_golden():
+    g = golden("tcn_forward.npz")
+    sd = weights.tcn_state(int(g["wseed"]))
+    assert abs(weights.checksum(sd) - float(g["wsum"])) < 1e-6 * abs(float(g["wsum"]))
+    x = weights.synth_audio(int(g["xseed"]), int(g["B"]), int(g["T"]))
+    t = weights.synth_audio(int(g["tseed"]), int(g["B"]), int(g["T"]))
+    ref = torch.from_numpy(g["out"])
+    loss, out = otcn.forward((x, t), sd)
+    assert out.shape == ref.shape
+    assert relrms(out, ref) < 1e-5
+    assert relrms(otcn.sample(x, sd, fused=True), ref) < 1e-5
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+
+
+@pytest.mark.skipif(not refshim.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_matches_live_reference():
+    R = refshim.ref_modules()
+    sd = weights.umx_state(3)
+    m = R.models.OpenUnmixModel(n_fft=2048, hop_length=512, n_channels=1, alpha=0.3, sample_rate=48000)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x = weights.synth_audio(41, 1, 8192)
+    with torch.no_grad():
+        ref = m.sample(x)
+    assert relrms(oumx.sample(x, sd), ref) < 1e-5
+    X = R.utils.spectrogram(x, torch.hann_window(2048), 2048, 512, 0.3)
+    assert relrms(ostft.spectrogram(x, torch.hann_window(2048), 2048, 512, 0.3), X) < 1e-6

@@ -1,0 +1,29 @@
+"""Quick device-side timing of the Open-Unmix path (development aid; bench.py is the contract)."""
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from oracle import weights  # noqa: E402
+from remfx_b200.models import OpenUnmixModel  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+T = 262144
+for impl in ("tc", "simt"):
+    m = OpenUnmixModel(sample_rate=48000, gemm_impl=impl)
+    m.load_state_dict(weights.umx_state(0))
+    m = m.cuda().eval()
+    x = weights.synth_audio(1, B, T).cuda()
+    for _ in range(3):
+        m.sample(x)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    n = 10
+    ev[0].record()
+    for _ in range(n):
+        m.sample(x)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / n
+    print(f"impl={impl} B={B} ms/call={ms:.3f} audio_s_per_s={B * T / 48000 / (ms / 1e3):.1f}", flush=True)
