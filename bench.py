@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the RemFx hot path on B200 (contract: see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
+  Open-Unmix distortion-removal forward = `OpenUnmixModel.sample`, batch 32 x 262144 samples, 48 kHz mono,
+  synthetic audio (clamp(0.1 N(0,1))) and seeded random-init weights (no network for data / checkpoints).
+A "step" is one pass of the hot path over one batch.  Metric: audio-seconds per second (whole job).
+
+  value      device-timed (CUDA events on the launching stream), inputs already resident in HBM
+  e2e        same call through the public API on pinned HOST buffers (H2D + kernels + D2H inside the timed region)
+  roofline   dominant kernel (BiLSTM recurrence): algorithmic bytes / live per-launch duration vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference path (torch-CPU, all host threads) on a bounded sample (rank 0, N=1)
+
+`--impl reference` times the reference's CPU implementation of the same path (oracle port; the reference itself
+is Python that cannot travel to the GPU box) on the host cores and prints the same JSON line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 48000
+T = 262144
+BATCH = 32
+CHUNK_S = T / SR
+METRIC = "audio-seconds/sec @48kHz 262144-sample chunks"
+WORKLOAD = "Open-Unmix (umx) distortion-removal forward (OpenUnmixModel.sample), batch 32x262144, fp32-parity mode"
+NBUF = 5  # distinct input batches rotated through the timed loop: 5 x 33.5 MB = 168 MB > 126 MB L2
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+def _cpu_reference(steps: int, warmup: int, items: int):
+    """Reference CPU path (oracle port of OpenUnmixModel.sample) on all host threads."""
+    import torch
+
+    from oracle import umx as oumx
+    from oracle import weights
+
+    torch.set_flush_denormal(True)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = weights.umx_state(0)
+    x = weights.synth_audio(12345, items, T)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            oumx.sample(x, sd, fast_lstm=True, wiener_trig=True)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return times, cores, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank, _, world = _dist_env()
+    if rank != 0:
+        return
+    items = 8  # bounded sample of the batch-32 workload per step
+    times, cores, threads = _cpu_reference(args.steps, args.warmup, items)
+    tot = sum(times)
+    value = items * CHUNK_S * len(times) / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "device": "host CPU", "step": f"{items} of the 32 chunks per step (bounded sample)"},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                         "sample": f"oracle port (torch-CPU fused LSTM) of OpenUnmixModel.sample, {items}x262144 per step, "
+                                   f"{len(times)} steps, os.cpu_count()={cores}"},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+
+    from remfx_b200 import _lib
+    from remfx_b200.models import OpenUnmixModel
+    from remfx_b200.synth import synth_audio
+
+    rank, local, world = _dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()  # fail loudly if the CUDA library is missing
+
+    torch.manual_seed(0)
+    model = OpenUnmixModel(n_fft=2048, hop_length=512, n_channels=1, alpha=0.3, sample_rate=SR)  # random-init weights
+    model = model.to(dev).eval()
+    xs_host = [synth_audio(12345 + rank * 100 + i, BATCH, T).pin_memory() for i in range(NBUF)]
+    xs = [x.to(dev) for x in xs_host]
+    out_host = torch.empty(BATCH, 1, T, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+
+    def reduce_max(v: float) -> float:
+        if not use_dist:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ------------------------------------------------------------------
+    model.set_profiling(True, dev)
+    for i in range(max(3, args.warmup)):
+        model.sample(xs[i % NBUF])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_acc = {}
+    barrier()
+    ev0.record()
+    for k in range(args.steps):
+        model.sample(xs[k % NBUF])
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    # per-stage durations of the last step (cudaEvents recorded between the launches, same stream)
+    stage_acc = model.stage_times_ms()
+    ms_total = reduce_max(ms_total)
+    ms_step = ms_total / args.steps
+    value = world * BATCH * CHUNK_S / (ms_step / 1e3)
+
+    # average the dominant kernel over a few more profiled steps (cheap; keeps the number live)
+    lstm_ms = []
+    for k in range(min(args.steps, 10)):
+        model.sample(xs[k % NBUF])
+        torch.cuda.synchronize()
+        st = model.stage_times_ms()
+        lstm_ms.append(sum(v for n, v in st.items() if n.startswith("lstm")) / model.model.nb_layers)
+    model.set_profiling(False, dev)
+
+    # ---- end-to-end through the public API on host buffers ---------------------------------------------
+    for i in range(2):
+        model.sample_host(xs_host[i % NBUF], out_host, dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for k in range(args.steps):
+        model.sample_host(xs_host[k % NBUF], out_host, dev)
+    e1.record()
+    torch.cuda.synchronize()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), wall_ms)  # every step ends with a stream sync
+    e2e_ms = reduce_max(e2e_ms) / args.steps
+    clocks = sampler.stop()
+    e2e_value = world * BATCH * CHUNK_S / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant kernel (BiLSTM recurrence, one launch = one layer, both directions) ----
+    peaks, peak_src = _peaks()
+    F = T // 512 + 1
+    M = BATCH * F
+    H = 256
+    lstm_bytes = M * 8 * H * 4 + M * 2 * H * 4 + 2 * 4 * H * H * 4  # read G, write h, read W_hh once
+    lstm_t = statistics.mean(lstm_ms) / 1e3
+    achieved = lstm_bytes / lstm_t / 1e9
+    roofline = {
+        "kernel": "lstm_rec_kernel (BiLSTM recurrence, 1 launch per layer)", "bound": "hbm", "achieved": achieved,
+        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": lstm_bytes, "ms_per_launch": lstm_t * 1e3,
+        "note": "513 strictly dependent steps per launch: latency-bound by construction, see DESIGN.md",
+        "stage_ms_last_step": {k: round(v, 4) for k, v in stage_acc.items()},
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "chunk_samples": T, "sample_rate": SR,
+                   "parallelism": f"dp{world} (items sharded, no data-path collective)",
+                   "gemm": "tcgen05 bf16x3 (fp32-grade)", "l2": f"inputs rotate over {NBUF} buffers (168 MB > 126 MB L2); "
+                   "~575 MB of intermediates stream through HBM every step"},
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": BATCH * T * 4,
+                "d2h_bytes_per_step": BATCH * T * 4},
+        "gpu_launches": args.steps * model.launches_per_call(),
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, cores, threads = _cpu_reference(steps=3, warmup=1, items=BATCH)
+        best = min(times)
+        line["cpu_baseline"] = {"value": BATCH * CHUNK_S / best, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                                "sample": f"oracle port of OpenUnmixModel.sample on the full batch (32x262144), best of 3, "
+                                          f"os.cpu_count()={cores}, median {statistics.median(times):.2f}s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -97,10 +97,29 @@ int rfx_umx_sample_host(rfx_umx_t* h, const float* x_host, int B, int T, float* 
                         size_t workspace_bytes, void* stream);
 /* Number of kernels one rfx_umx_sample call launches (for bench.py's gpu_launches). */
 int rfx_umx_launches_per_call(const rfx_umx_t* h);
+/* Per-stage device timing: when enabled, rfx_umx_sample records a cudaEvent on `stream` between its
+ * kernel launches; after the stream has been synchronised rfx_umx_stage_times returns the elapsed ms of
+ * the last call's stages in launch order: stft, fc1, (w_ih GEMM, lstm recurrence) x nb_layers, fc2, fc3, istft. */
+int rfx_umx_set_profiling(rfx_umx_t* h, int on);
+int rfx_umx_stage_times(rfx_umx_t* h, float* ms, int capacity, int* n_out);
 /* Debug taps: copy an internal activation of the last call into dst (fp32 device).  what: 0 = |STFT|
  * front-end output (M x lda), 1 = fc1/tanh (M x 512), 2 = last LSTM layer output (M x 512),
  * 3 = mask (M x ldm).  Returns the row stride through *ld. */
 int rfx_umx_debug_tap(rfx_umx_t* h, int what, const void* workspace, int B, int T, float* dst, int* ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * L1/L2  RemFx loss = MultiResolutionSTFTLoss(out, target) + l1_weight * mean|out - target|
+ *   replaces `self.mrstftloss(out, target) + self.l1loss(out, target) * 100`
+ *   (remfx/models.py:299,320,385; auraloss.freq.MultiResolutionSTFTLoss defaults, see oracle/loss.py)
+ * out/target: (B, T) with the given batch strides (in floats), so a cropped view of a longer target can
+ * be passed directly.  win1024/win2048/win512: the hann windows of length 600/1200/240 zero-padded
+ * (centred) to n_fft, as torch.stft does.  result (device, 9 floats): [0] loss, [1] MR-STFT term,
+ * [2] mean|out-target|, [3+2r] spectral-convergence and [4+2r] log-magnitude term of resolution r.
+ * ------------------------------------------------------------------------------------------- */
+size_t rfx_loss_workspace_bytes(int B, int T);
+int rfx_remfx_loss(const float* out, long long out_bstride, const float* target, long long target_bstride, int B, int T,
+                   const float* win1024, const float* win2048, const float* win512, float l1_weight, float* result,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

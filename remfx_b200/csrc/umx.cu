@@ -71,8 +71,12 @@ struct rfx_umx {
   PackedW fc1p, fc2p, fc3p;
   std::vector<PackedW> wihp;
   bool finalized = false;
+  // optional per-stage timing (cudaEvents recorded on the caller's stream between the launches)
+  bool profiling = false;
+  std::vector<cudaEvent_t> events;
 
   ~rfx_umx() {
+    for (auto e : events) cudaEventDestroy(e);
     for (auto& kv : params) kv.second.release();
     for (int i = 0; i < 3; ++i) { bn_s[i].release(); bn_t[i].release(); }
     for (auto& b : lstm_bias) b.release();
@@ -245,6 +249,19 @@ int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void*
   const float2* tw = twiddles(h->cfg.n_fft);
   RFX_REQUIRE(tw != nullptr, "twiddle table allocation failed");
   int rc;
+  const int n_stage = 5 + 2 * nl;
+  if (h->profiling && (int)h->events.size() != n_stage + 1) {
+    for (auto e : h->events) cudaEventDestroy(e);
+    h->events.assign(n_stage + 1, nullptr);
+    for (auto& e : h->events) RFX_CHECK_CUDA(cudaEventCreate(&e));
+  }
+  int stage = 0;
+  auto mark = [&]() -> int {
+    if (h->profiling) RFX_CHECK_CUDA(cudaEventRecord(h->events[stage], s));
+    ++stage;
+    return 0;
+  };
+  if ((rc = mark())) return rc;
 
   // (1) STFT (transforms.py:106-116) + ComplexNorm (:211) + input shift/scale (model.py:127-128)
   StftParams sp{};
@@ -255,31 +272,31 @@ int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void*
   sp.scale = 1.0f; sp.alpha = 1.0f; sp.mode = STFT_UMX_MAG;
   sp.Z = Z; sp.ldz = h->bins; sp.A = A1; sp.lda = L.lda1;
   sp.in_mean = P(h, "input_mean"); sp.in_scale = P(h, "input_scale");
-  if ((rc = launch_stft(sp, B, s))) return rc;
+  if ((rc = launch_stft(sp, B, s)) || (rc = mark())) return rc;
 
   // (2) fc1 + bn1 + tanh (model.py:132-138) -> first half of the skip-concat buffer
   Epilogue e1; e1.s1 = h->bn_s[0].p; e1.t1 = h->bn_t[0].p; e1.act = ACT_TANH;
-  if ((rc = gemm(h, A1, L.lda1, L.M, h->fc1p, P(h, "fc1.weight"), XC, 2 * hid, e1, s))) return rc;
+  if ((rc = gemm(h, A1, L.lda1, L.M, h->fc1p, P(h, "fc1.weight"), XC, 2 * hid, e1, s)) || (rc = mark())) return rc;
 
   // (3) BiLSTM stack (model.py:141): per layer one input-projection GEMM + one recurrent cluster kernel
   const float* lin = XC; int ldin = 2 * hid;
   for (int l = 0; l < nl; ++l) {
     Epilogue eb; eb.t1 = h->lstm_bias[l].p;
-    if ((rc = gemm(h, lin, ldin, L.M, h->wihp[l], h->wih_cat[l].p, G, 8 * H, eb, s))) return rc;
+    if ((rc = gemm(h, lin, ldin, L.M, h->wihp[l], h->wih_cat[l].p, G, 8 * H, eb, s)) || (rc = mark())) return rc;
     float* hout; int ldh;
     if (l == nl - 1) { hout = XC + hid; ldh = 2 * hid; }  // torch.cat([x, lstm_out], -1) (model.py:144) for free
     else { hout = Hb[l & 1]; ldh = hid; }
-    if ((rc = launch_lstm_layer(G, 8 * H, h->whh_cat[l].p, hout, ldh, B, L.F, H, s))) return rc;
+    if ((rc = launch_lstm_layer(G, 8 * H, h->whh_cat[l].p, hout, ldh, B, L.F, H, s)) || (rc = mark())) return rc;
     lin = hout; ldin = ldh;
   }
 
   // (4) fc2 + bn2 + ReLU (model.py:147-150)
   Epilogue e2; e2.s1 = h->bn_s[1].p; e2.t1 = h->bn_t[1].p; e2.act = ACT_RELU;
-  if ((rc = gemm(h, XC, 2 * hid, L.M, h->fc2p, P(h, "fc2.weight"), Y2, hid, e2, s))) return rc;
+  if ((rc = gemm(h, XC, 2 * hid, L.M, h->fc2p, P(h, "fc2.weight"), Y2, hid, e2, s)) || (rc = mark())) return rc;
 
   // (5) fc3 + bn3 + output scale/mean + ReLU (model.py:153-164) = the non-negative ratio mask
   Epilogue e3; e3.s1 = h->bn_s[2].p; e3.t1 = h->bn_t[2].p; e3.s2 = P(h, "output_scale"); e3.t2 = P(h, "output_mean"); e3.act = ACT_RELU;
-  if ((rc = gemm(h, Y2, hid, L.M, h->fc3p, P(h, "fc3.weight"), mask, L.ldm, e3, s))) return rc;
+  if ((rc = gemm(h, Y2, hid, L.M, h->fc3p, P(h, "fc3.weight"), mask, L.ldm, e3, s)) || (rc = mark())) return rc;
 
   // (6) `* mix` (model.py:164) + wiener niter=0 (filtering.py:442-451) + iSTFT (transforms.py:168-177)
   IstftParams ip{};
@@ -287,7 +304,24 @@ int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void*
   ip.window = P(h, "window"); ip.tw = tw;
   ip.n_fft = h->cfg.n_fft; ip.hop = h->cfg.hop; ip.F = L.F; ip.length = T;
   ip.scale = 1.0f; ip.out = out; ip.out_bstride = T; ip.hops_per_cta = 16;
-  return launch_istft(ip, B, s);
+  if ((rc = launch_istft(ip, B, s)) || (rc = mark())) return rc;
+  return 0;
+}
+
+int rfx_umx_set_profiling(rfx_umx_t* h, int on) {
+  RFX_REQUIRE(h, "null handle");
+  h->profiling = on != 0;
+  return 0;
+}
+
+int rfx_umx_stage_times(rfx_umx_t* h, float* ms, int capacity, int* n_out) {
+  RFX_REQUIRE(h && ms && n_out, "null argument");
+  RFX_REQUIRE(h->profiling && h->events.size() >= 2, "profiling was not enabled for the last call");
+  const int n = (int)h->events.size() - 1;
+  RFX_REQUIRE(capacity >= n, "output too small");
+  for (int i = 0; i < n; ++i) RFX_CHECK_CUDA(cudaEventElapsedTime(&ms[i], h->events[i], h->events[i + 1]));
+  *n_out = n;
+  return 0;
 }
 
 int rfx_umx_sample_host(rfx_umx_t* h, const float* x_host, int B, int T, float* out_host, void* workspace, size_t workspace_bytes,

@@ -1,0 +1,60 @@
+"""RemFx loss on the GPU: MRSTFT(out, target) + 100 * L1(out, target) (remfx/models.py:299,320,385).
+
+Forward value only (inference / evaluation configs); the fused kernels never materialise a
+spectrogram in HBM.  See csrc/loss.cu and oracle/loss.py (auraloss restatement, parity unpinned).
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .ops import padded_window
+
+_WIN_CACHE: dict = {}
+_RES = ((1024, 600), (2048, 1200), (512, 240))
+
+
+def _windows(device):
+    key = str(device)
+    if key not in _WIN_CACHE:
+        _WIN_CACHE[key] = [padded_window(torch.hann_window(w, device=device), n) for n, w in _RES]
+    return _WIN_CACHE[key]
+
+
+def remfx_loss_terms(out: Tensor, target: Tensor, l1_weight: float = 100.0) -> Tensor:
+    """out, target: (B, C, T) or (B, T) fp32 CUDA (last-dim contiguous views are fine) -> 9-float device tensor
+    [loss, mrstft, mean|d|, sc_1024, lm_1024, sc_2048, lm_2048, sc_512, lm_512]."""
+    _lib.require_device(out)
+    _lib.require_device(target)
+    if out.shape != target.shape:
+        raise ValueError(f"shape mismatch {tuple(out.shape)} vs {tuple(target.shape)}")
+    T = out.shape[-1]
+    o2 = out.reshape(-1, T)
+    t2 = target.reshape(-1, T)
+    if o2.stride(-1) != 1:
+        o2 = o2.contiguous()
+    if t2.stride(-1) != 1:
+        t2 = t2.contiguous()
+    if o2.dtype != torch.float32 or t2.dtype != torch.float32:
+        raise ValueError("expected float32")
+    B = o2.shape[0]
+    L = _lib.lib()
+    with torch.cuda.device(out.device):
+        ws = torch.empty(L.rfx_loss_workspace_bytes(B, T), dtype=torch.uint8, device=out.device)
+        res = torch.empty(9, dtype=torch.float32, device=out.device)
+        w = _windows(out.device)
+        rc = L.rfx_remfx_loss(o2.data_ptr(), o2.stride(0) if B > 1 else T, t2.data_ptr(), t2.stride(0) if B > 1 else T, B, T,
+                              w[0].data_ptr(), w[1].data_ptr(), w[2].data_ptr(), float(l1_weight), res.data_ptr(),
+                              ws.data_ptr(), ws.numel(), _lib.cur_stream())
+        _lib.check(rc, "rfx_remfx_loss")
+    return res
+
+
+def remfx_loss(out: Tensor, target: Tensor) -> Tensor:
+    """0-d loss tensor, as the reference wrappers return."""
+    return remfx_loss_terms(out, target)[0]
+
+
+def mrstft_loss(out: Tensor, target: Tensor) -> Tensor:
+    return remfx_loss_terms(out, target)[1]

@@ -115,12 +115,31 @@ class OpenUnmixModel(nn.Module):
         return self._handle
 
     def __del__(self):
-        h, self._handle = getattr(self, "_handle", None), None
+        h = self.__dict__.get("_handle")
         if h is not None:
+            self.__dict__["_handle"] = None
             try:
                 _lib.lib().rfx_umx_destroy(h)
             except Exception:
                 pass
+
+    STAGES = ("stft", "fc1", "wih0", "lstm0", "wih1", "lstm1", "wih2", "lstm2", "fc2", "fc3", "istft")
+
+    def set_profiling(self, on: bool, device="cuda:0") -> None:
+        """Record cudaEvents between the kernel launches of subsequent sample() calls."""
+        with torch.cuda.device(torch.device(device)):
+            h = self._sync(torch.device(device))
+        _lib.check(_lib.lib().rfx_umx_set_profiling(h, int(on)), "rfx_umx_set_profiling")
+
+    def stage_times_ms(self) -> dict:
+        """Per-stage device time (ms) of the last profiled sample(); the stream must be synchronised first."""
+        buf = (C.c_float * 32)()
+        n = C.c_int()
+        _lib.check(_lib.lib().rfx_umx_stage_times(self._handle, buf, 32, C.byref(n)), "rfx_umx_stage_times")
+        vals = [buf[i] for i in range(n.value)]
+        L = self.model.nb_layers
+        names = ["stft", "fc1"] + [f"{k}{l}" for l in range(L) for k in ("wih", "lstm")] + ["fc2", "fc3", "istft"]
+        return dict(zip(names, vals))
 
     def _workspace(self, h, B: int, T: int, device) -> Tensor:
         need = _lib.lib().rfx_umx_workspace_bytes(h, B, T)
