@@ -63,6 +63,9 @@ int rfx_gemm(int impl, const float* A, int lda, int M, const float* W, int N, in
  *   replaces the recurrent half of umx/openunmix/model.py:141 (self.lstm)
  * G: [B*F, 8H] input projections incl. both biases, column = dir*4H + gate*H + unit, row = b*F + t.
  * Whh: [2, 4H, H].  Hout: [B*F, ldh], column = dir*H + unit.  H must be 256. */
+/* Scheduling facts of the recurrence kernel on the current device: how many 8-CTA clusters are co-resident
+ * and how many batch items each cluster takes for batch size B (all clusters of a launch run as one wave). */
+int rfx_lstm_info(int B, int* max_active_clusters, int* batch_per_cluster);
 int rfx_lstm_layer(const float* G, const float* Whh, float* Hout, int ldh, int B, int F, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -80,6 +80,13 @@ int rfx_gemm(int impl, const float* A, int lda, int M, const float* W, int N, in
   return launch_gemm_tc(A, lda, M, pw, C, ldc, e, s);
 }
 
+int rfx_lstm_info(int B, int* max_active_clusters, int* batch_per_cluster) {
+  RFX_REQUIRE(B > 0 && max_active_clusters && batch_per_cluster, "bad argument");
+  *max_active_clusters = lstm_max_active_clusters();
+  *batch_per_cluster = lstm_choose_nb(B);
+  return 0;
+}
+
 int rfx_lstm_layer(const float* G, const float* Whh, float* Hout, int ldh, int B, int F, int H, void* stream) {
   RFX_REQUIRE(G && Whh && Hout, "null argument");
   return launch_lstm_layer(G, 8 * H, Whh, Hout, ldh, B, F, H, (cudaStream_t)stream);

@@ -87,6 +87,8 @@ int launch_gemm_simt(const float* A, int lda, int M, const float* W, int ldw, in
 // One direction-pair of one layer: G [B*F, ldg] holds W_ih x + b_ih + b_hh for both directions
 // (column = dir * 4H + gate * H + unit, gate order i,f,g,o), Whh [2][4H][H]; writes h to
 // Hout[b*F + t][dir*H + unit].
+int lstm_max_active_clusters();  // co-resident 8-CTA clusters of the recurrence kernel on this device
+int lstm_choose_nb(int B);       // batch items per cluster used for batch size B
 int launch_lstm_layer(const float* G, int ldg, const float* Whh, float* Hout, int ldh, int B, int F, int H, cudaStream_t stream);
 
 // ---------------------------------------------------------------- small utility kernels (util.cu)

@@ -4,14 +4,23 @@
 //
 // The input projections W_ih x + b_ih + b_hh of all time steps are one big tensor-core GEMM (gemm.cu);
 // this kernel only runs the recurrent part  g_t = G_t + W_hh h_{t-1}.  Mapping:
-//   * one thread-block CLUSTER of 8 CTAs per (direction, group of NB = 4 batch items);
-//     grid = 8 x ceil(B/4) x 2  (= 128 CTAs at B = 32: one per SM, both directions concurrently);
-//   * CTA rank r owns hidden units [32 r, 32 r + 32) = 128 gate rows of W_hh, held ENTIRELY IN REGISTERS
-//     (128 fp32 per thread: row = tid % 128, K-half = tid / 128) for the whole sequence, so a step reads no
-//     weights from memory at all;
-//   * h_{t-1} (NB x 256 fp32) lives in every CTA's shared memory (double-buffered); after the gate math
-//     the 32 new h values per batch item are pushed to all 8 CTAs with st.shared::cluster (DSMEM) and one
-//     cluster barrier per step orders the exchange -- no global-memory round trip, no grid sync.
+//   * one thread-block CLUSTER of 8 CTAs per (direction, group of NB batch items), NB in 4..8 chosen so
+//     that every cluster of the launch is co-resident (B = 32 -> NB = 5: 14 clusters = 112 SMs, both
+//     directions concurrently);
+//   * CTA rank r owns hidden units [32 r, 32 r + 32); warp w of the CTA owns units 4w..4w+3, i.e. 16 gate
+//     rows of W_hh, held ENTIRELY IN REGISTERS for the whole sequence (lane = unit-in-warp x K-slice:
+//     4 gates x 32 K-values = 128 fp32 per thread), so a step reads no weights from memory at all;
+//   * h_{t-1} (NB x 256 fp32) lives in every CTA's shared memory, double-buffered, laid out
+//     [source CTA][batch][32 units] so that each CTA's contribution is one contiguous 512-byte block.
+//     A step is: 128 NB FFMA/thread against float4 LDS of h, a 28-shuffle reduce-scatter over the 8
+//     K-slices (lane ks ends up owning batch slot ks), gate math, the new h values staged in local smem,
+//     one __syncthreads, then
+//     8 DSMEM BULK copies (cp.async.bulk shared::cta -> shared::cluster, 512 B each) push them to all 8
+//     CTAs with mbarrier complete_tx signalling -- 8 remote transactions per CTA per step instead of
+//     hundreds of small remote stores (measured: fine-grained st.async/st.shared::cluster exchange cost
+//     ~7 k cycles per step).  No cluster barrier and no memory fence in the loop: the only cross-CTA wait
+//     is the mbarrier counting the 4 KB of h_t arriving; double buffering + data dependence make the
+//     buffers hazard-free.
 // fp32 FFMA throughout (the recurrence amplifies rounding over 513 steps; bf16 would fail the 1e-4 gate).
 #include "kernels.h"
 
@@ -20,118 +29,205 @@ namespace rfx {
 constexpr int LSTM_H = 256;
 constexpr int LSTM_CL = 8;                  // CTAs per cluster
 constexpr int LSTM_UPC = LSTM_H / LSTM_CL;  // hidden units per CTA (32)
-constexpr int LSTM_ROWS = 4 * LSTM_UPC;     // gate rows per CTA (128)
-constexpr int LSTM_NB = 4;                  // batch items per cluster
-constexpr int LSTM_KH = LSTM_H / 2;         // K elements per thread (128)
+constexpr int LSTM_WARPS = 8;
 
-__global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(256, 1)
+// local shared memory -> (possibly remote) shared memory of a CTA in the cluster; completion on the
+// destination CTA's mbarrier.
+__device__ __forceinline__ void bulk_s2cluster(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t cluster_mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster_addr),
+               "r"(src_cta_addr), "r"(bytes), "r"(cluster_mbar)
+               : "memory");
+}
+
+// NB = batch items per cluster (4..8).  All clusters of a launch must be co-resident (only ~15 clusters of
+// 8 CTAs fit on a B200 at once: a 16th would run as a second wave and double the time), so the host picks
+// the smallest NB for which 2 * ceil(B / NB) clusters fit (cudaOccupancyMaxActiveClusters).
+template <int NB>
+__global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 32, 1)
     lstm_rec_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Whh, float* __restrict__ Hout, int ldh, int B, int F) {
-  __shared__ __align__(16) float h_buf[2][LSTM_NB][LSTM_H];
-  __shared__ float part[2][LSTM_NB][LSTM_ROWS];
+  constexpr int TX_BYTES = LSTM_CL * NB * LSTM_UPC * 4;  // bytes of h_t every CTA receives per step
+  __shared__ __align__(128) float h_buf[2][LSTM_CL][NB][LSTM_UPC];  // [buffer][source CTA][batch][unit]
+  __shared__ __align__(128) float stage[2][NB][LSTM_UPC];           // this CTA's new h values
+  __shared__ __align__(8) uint64_t h_bar[2];
 
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int dir = blockIdx.z;
-  const int b0 = blockIdx.y * LSTM_NB;
-  const int row_local = tid & (LSTM_ROWS - 1);  // gate * 32 + unit
-  const int khalf = tid >> 7;
-  const int gate = row_local >> 5, unit = row_local & 31;
+  const int b0 = blockIdx.y * NB;
+  const int rg = lane >> 3;  // unit within the warp (0..3)
+  const int ks = lane & 7;   // K slice during the mat-vec; batch slot after the reduce-scatter
+  const int unit = rank * LSTM_UPC + warp * 4 + rg;  // hidden unit this lane group works on
 
-  // W_hh slice -> registers (one-time, 512 B per thread)
-  float w[LSTM_KH];
-  {
-    const float* wrow = Whh + ((size_t)dir * 4 * LSTM_H + (size_t)gate * LSTM_H + rank * LSTM_UPC + unit) * LSTM_H + khalf * LSTM_KH;
+  // ---- W_hh rows of the 4 gates of `unit`, K-slice ks: k = 4*(8c + ks) + e, c = 0..7, e = 0..3 ----
+  float w[4][32];
 #pragma unroll
-    for (int i = 0; i < LSTM_KH; i += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(wrow + i);
-      w[i] = t.x; w[i + 1] = t.y; w[i + 2] = t.z; w[i + 3] = t.w;
+  for (int g = 0; g < 4; ++g) {
+    const float* wrow = Whh + ((size_t)dir * 4 * LSTM_H + (size_t)g * LSTM_H + unit) * LSTM_H;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 t = *reinterpret_cast<const float4*>(wrow + 4 * (8 * c + ks));
+      w[g][4 * c + 0] = t.x; w[g][4 * c + 1] = t.y; w[g][4 * c + 2] = t.z; w[g][4 * c + 3] = t.w;
     }
   }
-  for (int i = tid; i < 2 * LSTM_NB * LSTM_H; i += 256) (&h_buf[0][0][0])[i] = 0.0f;
+  for (int i = tid; i < 2 * LSTM_CL * NB * LSTM_UPC; i += LSTM_WARPS * 32) (&h_buf[0][0][0][0])[i] = 0.0f;
+  if (tid == 0) {
+    mbar_init(&h_bar[0], 1);
+    mbar_init(&h_bar[1], 1);
+    mbar_fence_init();
+  }
 
-  // finalize role (threads 0..127): batch item fb, unit fu; cell state lives in a register
-  const int fb = tid >> 5, fu = tid & 31;
-  const bool fin = tid < LSTM_NB * LSTM_UPC;
-  const bool fvalid = fin && (b0 + fb < B);
+  // After the reduce-scatter lane (rg, ks) holds all four gate pre-activations of (unit, batch slot ks).
+  const bool bslot = ks < NB;
+  const bool bvalid = bslot && (b0 + ks) < B;
+  const size_t gcol = (size_t)dir * 4 * LSTM_H + unit;  // + gate * H
   float c_state = 0.0f;
-  const size_t gcol = (size_t)dir * 4 * LSTM_H + rank * LSTM_UPC + fu;  // + gate * H
   float gin[4] = {0.f, 0.f, 0.f, 0.f};
-  if (fvalid) {
-    const int tt0 = dir ? F - 1 : 0;
-    const float* g = G + ((size_t)(b0 + fb) * F + tt0) * ldg + gcol;
+  if (bvalid) {
+    const float* g = G + ((size_t)(b0 + ks) * F + (dir ? F - 1 : 0)) * ldg + gcol;
 #pragma unroll
     for (int q = 0; q < 4; ++q) gin[q] = g[q * LSTM_H];
   }
-  // remote addresses of h_buf[0][fb][rank*32 + fu] in every CTA of the cluster
-  uint32_t remote[LSTM_CL];
-  {
-    const uint32_t local = smem_u32(&h_buf[0][fb & (LSTM_NB - 1)][rank * LSTM_UPC + fu]);
-#pragma unroll
-    for (int r = 0; r < LSTM_CL; ++r) remote[r] = mapa_u32(local, r);
-  }
+  // Sender role (warp 0, lanes 0..7): lane d bulk-copies this CTA's block to CTA d.
+  const uint32_t dst_h = mapa_u32(smem_u32(&h_buf[0][rank][0][0]), lane & 7);
+  const uint32_t dst_bar = mapa_u32(smem_u32(&h_bar[0]), lane & 7);
+  // Global writer role (threads 0 .. NB*32-1): batch item tid >> 5, unit tid & 31.
+  const int wb = tid >> 5, wu = tid & 31;
+  const bool wvalid = wb < NB && (b0 + wb) < B;
+
   __syncthreads();
-  cluster_arrive();
+  cluster_arrive();  // barriers initialised and h_buf zeroed everywhere before anyone sends
   cluster_wait();
 
   for (int step = 0; step < F; ++step) {
     const int cur = step & 1;
     const int tt = dir ? F - 1 - step : step;
-    // prefetch next step's input-projection values (independent of the recurrence)
-    float gnext[4] = {0.f, 0.f, 0.f, 0.f};
-    if (fvalid && step + 1 < F) {
-      const int tn = dir ? tt - 1 : tt + 1;
-      const float* g = G + ((size_t)(b0 + fb) * F + tn) * ldg + gcol;
+    if (tid == 0) mbar_arrive_expect_tx(&h_bar[cur ^ 1], TX_BYTES);  // phase that will receive h_t
+    // prefetch next step's input projections (independent of the recurrence)
+    float gn[4] = {0.f, 0.f, 0.f, 0.f};
+    if (bvalid && step + 1 < F) {
+      const float* g = G + ((size_t)(b0 + ks) * F + (dir ? tt - 1 : tt + 1)) * ldg + gcol;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) gnext[q] = g[q * LSTM_H];
+      for (int q = 0; q < 4; ++q) gn[q] = g[q * LSTM_H];
     }
-    // partial dot products over this thread's K half for the NB batch items
-    float acc[LSTM_NB];
+    if (step > 0) mbar_wait(&h_bar[cur], ((step - 1) >> 1) & 1);  // all of h_{t-1} has landed
+
+    float acc[4][8];
 #pragma unroll
-    for (int b = 0; b < LSTM_NB; ++b) acc[b] = 0.0f;
-    const float* hb = &h_buf[cur][0][khalf * LSTM_KH];
+    for (int g = 0; g < 4; ++g)
 #pragma unroll
-    for (int i = 0; i < LSTM_KH; i += 4) {
+      for (int b = 0; b < 8; ++b) acc[g][b] = 0.0f;
+    const float* hb = &h_buf[cur][0][0][4 * ks];  // k = 32 c + 4 ks + e lives at [c][b][4 ks + e]
 #pragma unroll
-      for (int b = 0; b < LSTM_NB; ++b) {
-        const float4 hv = *reinterpret_cast<const float4*>(hb + b * LSTM_H + i);
-        acc[b] = fmaf(w[i], hv.x, acc[b]);
-        acc[b] = fmaf(w[i + 1], hv.y, acc[b]);
-        acc[b] = fmaf(w[i + 2], hv.z, acc[b]);
-        acc[b] = fmaf(w[i + 3], hv.w, acc[b]);
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float4 hv = *reinterpret_cast<const float4*>(hb + c * (NB * LSTM_UPC) + b * LSTM_UPC);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          acc[g][b] = fmaf(w[g][4 * c + 0], hv.x, acc[g][b]);
+          acc[g][b] = fmaf(w[g][4 * c + 1], hv.y, acc[g][b]);
+          acc[g][b] = fmaf(w[g][4 * c + 2], hv.z, acc[g][b]);
+          acc[g][b] = fmaf(w[g][4 * c + 3], hv.w, acc[g][b]);
+        }
       }
     }
+    // ---- reduce-scatter over the 8 K-slices (lanes 8 rg .. 8 rg + 7): lane ks ends with batch slot ks ----
+    float r1[4][4];
 #pragma unroll
-    for (int b = 0; b < LSTM_NB; ++b) part[khalf][b][row_local] = acc[b];
-    __syncthreads();
-    if (fin) {
-      const float pi = part[0][fb][0 * LSTM_UPC + fu] + part[1][fb][0 * LSTM_UPC + fu] + gin[0];
-      const float pf = part[0][fb][1 * LSTM_UPC + fu] + part[1][fb][1 * LSTM_UPC + fu] + gin[1];
-      const float pg = part[0][fb][2 * LSTM_UPC + fu] + part[1][fb][2 * LSTM_UPC + fu] + gin[2];
-      const float po = part[0][fb][3 * LSTM_UPC + fu] + part[1][fb][3 * LSTM_UPC + fu] + gin[3];
-      const float ig = sigmoidf_acc(pi), fg = sigmoidf_acc(pf), gg = tanhf(pg), og = sigmoidf_acc(po);
-      c_state = fg * c_state + ig * gg;
-      const float h = og * tanhf(c_state);
-      if (fvalid) Hout[((size_t)(b0 + fb) * F + tt) * ldh + dir * LSTM_H + rank * LSTM_UPC + fu] = h;
-      const uint32_t boff = (uint32_t)((cur ^ 1) * LSTM_NB * LSTM_H * sizeof(float));
+    for (int g = 0; g < 4; ++g)
 #pragma unroll
-      for (int r = 0; r < LSTM_CL; ++r) st_cluster_f32(remote[r] + boff, h);
+      for (int bb = 0; bb < 4; ++bb) {
+        const float send = (ks & 4) ? acc[g][bb] : acc[g][bb + 4];
+        const float keep = (ks & 4) ? acc[g][bb + 4] : acc[g][bb];
+        r1[g][bb] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+    float r2[4][2];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) gin[q] = gnext[q];
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        const float send = (ks & 2) ? r1[g][bb] : r1[g][bb + 2];
+        const float keep = (ks & 2) ? r1[g][bb + 2] : r1[g][bb];
+        r2[g][bb] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+    float pre[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float send = (ks & 1) ? r2[g][0] : r2[g][1];
+      const float keep = (ks & 1) ? r2[g][1] : r2[g][0];
+      pre[g] = keep + __shfl_xor_sync(0xffffffffu, send, 1) + gin[g];
     }
-    // orders: DSMEM writes of h_t (release) before anyone reads them (acquire); also protects part[]
-    cluster_arrive();
-    cluster_wait();
+    // ---- gate math (i, f, g, o) for (unit, batch slot ks) ----
+    if (bslot) {
+      const float ig = sigmoidf_acc(pre[0]), fg = sigmoidf_acc(pre[1]), gg = tanhf(pre[2]), og = sigmoidf_acc(pre[3]);
+      c_state = fg * c_state + ig * gg;
+      stage[cur ^ 1][ks][warp * 4 + rg] = og * tanhf(c_state);
+    }
+    // ---- 8 bulk DSMEM copies per CTA push the new h block to every CTA of the cluster ----
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy (async proxy) reads
+    __syncthreads();
+    if (warp == 0 && lane < LSTM_CL) {
+      const uint32_t boff = (uint32_t)((cur ^ 1) * LSTM_CL * NB * LSTM_UPC * sizeof(float));
+      bulk_s2cluster(dst_h + boff, smem_u32(&stage[cur ^ 1][0][0]), NB * LSTM_UPC * sizeof(float),
+                     dst_bar + (uint32_t)((cur ^ 1) * sizeof(uint64_t)));
+    }
+    if (wvalid) Hout[((size_t)(b0 + wb) * F + tt) * ldh + dir * LSTM_H + rank * LSTM_UPC + wu] = stage[cur ^ 1][wb][wu];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gin[q] = gn[q];
   }
+  // Nobody may exit while peers can still write into its shared memory / barriers: wait for the last h to land.
+  mbar_wait(&h_bar[F & 1], ((F - 1) >> 1) & 1);
+  cluster_arrive();
+  cluster_wait();
+}
+
+template <int NB>
+static int max_clusters() {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(LSTM_CL, 64, 2);
+  cfg.blockDim = dim3(LSTM_WARPS * 32);
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = LSTM_CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, lstm_rec_kernel<NB>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+template <int NB>
+static int launch_nb(const float* G, int ldg, const float* Whh, float* Hout, int ldh, int B, int F, cudaStream_t stream) {
+  dim3 grid(LSTM_CL, ceil_div(B, NB), 2);
+  lstm_rec_kernel<NB><<<grid, LSTM_WARPS * 32, 0, stream>>>(G, ldg, Whh, Hout, ldh, B, F);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lstm_max_active_clusters() {
+  static int cached = -1;
+  if (cached < 0) cached = max_clusters<4>();
+  return cached;
+}
+
+int lstm_choose_nb(int B) {
+  const int maxc = lstm_max_active_clusters();
+  for (int nb = 4; nb <= 8; ++nb)
+    if (2 * ceil_div(B, nb) <= maxc) return nb;
+  return 8;  // more clusters than fit: several waves of the widest variant
 }
 
 int launch_lstm_layer(const float* G, int ldg, const float* Whh, float* Hout, int ldh, int B, int F, int H, cudaStream_t stream) {
   RFX_REQUIRE(H == LSTM_H, "lstm: hidden size per direction must be 256");
   RFX_REQUIRE(B > 0 && F > 0, "lstm: positive sizes");
   RFX_REQUIRE(((uintptr_t)Whh & 15) == 0, "lstm: W_hh must be 16-byte aligned");
-  dim3 grid(LSTM_CL, ceil_div(B, LSTM_NB), 2);
-  lstm_rec_kernel<<<grid, 256, 0, stream>>>(G, ldg, Whh, Hout, ldh, B, F);
-  RFX_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  switch (lstm_choose_nb(B)) {
+    case 4: return launch_nb<4>(G, ldg, Whh, Hout, ldh, B, F, stream);
+    case 5: return launch_nb<5>(G, ldg, Whh, Hout, ldh, B, F, stream);
+    case 6: return launch_nb<6>(G, ldg, Whh, Hout, ldh, B, F, stream);
+    case 7: return launch_nb<7>(G, ldg, Whh, Hout, ldh, B, F, stream);
+    default: return launch_nb<8>(G, ldg, Whh, Hout, ldh, B, F, stream);
+  }
 }
 
 }  // namespace rfx

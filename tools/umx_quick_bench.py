@@ -1,20 +1,20 @@
-"""Quick device-side timing of the Open-Unmix path (development aid; bench.py is the contract)."""
+"""Quick device-side timing of the Open-Unmix path with per-stage breakdown (development aid; bench.py is the contract)."""
 import sys
-import time
 
 import torch
 
 sys.path.insert(0, ".")
-from oracle import weights  # noqa: E402
 from remfx_b200.models import OpenUnmixModel  # noqa: E402
+from remfx_b200.synth import synth_audio  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+impls = sys.argv[2].split(",") if len(sys.argv) > 2 else ["tc"]
 T = 262144
-for impl in ("tc", "simt"):
-    m = OpenUnmixModel(sample_rate=48000, gemm_impl=impl)
-    m.load_state_dict(weights.umx_state(0))
-    m = m.cuda().eval()
-    x = weights.synth_audio(1, B, T).cuda()
+for impl in impls:
+    torch.manual_seed(0)
+    m = OpenUnmixModel(sample_rate=48000, gemm_impl=impl).cuda().eval()
+    x = synth_audio(1, B, T).cuda()
+    m.set_profiling(True)
     for _ in range(3):
         m.sample(x)
     torch.cuda.synchronize()
@@ -26,4 +26,6 @@ for impl in ("tc", "simt"):
     ev[1].record()
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[1]) / n
+    st = m.stage_times_ms()
     print(f"impl={impl} B={B} ms/call={ms:.3f} audio_s_per_s={B * T / 48000 / (ms / 1e3):.1f}", flush=True)
+    print("  " + " ".join(f"{k}={v:.3f}" for k, v in st.items()), flush=True)
