@@ -49,12 +49,12 @@ int rfx_istft(const float* Z_ri, const float* mask, int B, int F, int n_fft, int
 /* ---------------------------------------------------------------------------------------------
  * Dense layer  C[m,n] = act(((A[m,:] . W[n,:]) * s1[n] + t1[n]) * s2[n] + t2[n])
  *   the primitive behind nn.Linear + BatchNorm1d(eval) + activation in umx/openunmix/model.py:119-161
- * impl: 0 = tcgen05 bf16x3 tensor-core kernel, 1 = fp32 FFMA kernel.  act: 0 none, 1 tanh, 2 relu,
- * 3 sigmoid.  s1/t1/s2/t2 may be NULL.  W is the raw nn.Linear weight [N, K] (row-major); for impl 0
- * it is packed on the fly into `scratch` (rfx_gemm_scratch_bytes).  Test / utility entry point -- the
- * model handles below keep their weights pre-packed.
+ * impl: 0 = TMA-fed tcgen05 bf16x3 tensor-core engine, 1 = fp32 FFMA cross-check kernel.  act: 0 none,
+ * 1 tanh, 2 relu, 3 sigmoid.  s1/t1/s2/t2 may be NULL.  W is the raw nn.Linear weight [N, K] (row-major);
+ * for impl 0 both operands are split into bf16 hi/lo planes in `scratch` (rfx_gemm_scratch_bytes) first.
+ * Test / utility entry point -- the model handles below keep weights pre-split and activations split.
  * ------------------------------------------------------------------------------------------- */
-size_t rfx_gemm_scratch_bytes(int N, int K);
+size_t rfx_gemm_scratch_bytes(int M, int N, int K);
 int rfx_gemm(int impl, const float* A, int lda, int M, const float* W, int N, int K, float* C, int ldc,
              const float* s1, const float* t1, const float* s2, const float* t2, int act,
              void* scratch, void* stream);
@@ -81,7 +81,7 @@ typedef struct {
   int hop;         /* 512  */
   int hidden;      /* 512 (LSTM hidden = hidden/2 per direction; must be 512) */
   int nb_layers;   /* 3 */
-  int gemm_impl;   /* 0 tcgen05 bf16x3 (default), 1 fp32 FFMA */
+  int gemm_impl;   /* must be 0: TMA-fed tcgen05 bf16x3 engine */
 } rfx_umx_config;
 
 int rfx_umx_create(const rfx_umx_config* cfg, rfx_umx_t** out);
@@ -105,9 +105,7 @@ int rfx_umx_launches_per_call(const rfx_umx_t* h);
  * the last call's stages in launch order: stft, fc1, (w_ih GEMM, lstm recurrence) x nb_layers, fc2, fc3, istft. */
 int rfx_umx_set_profiling(rfx_umx_t* h, int on);
 int rfx_umx_stage_times(rfx_umx_t* h, float* ms, int capacity, int* n_out);
-/* Debug taps: copy an internal activation of the last call into dst (fp32 device).  what: 0 = |STFT|
- * front-end output (M x lda), 1 = fc1/tanh (M x 512), 2 = last LSTM layer output (M x 512),
- * 3 = mask (M x ldm).  Returns the row stride through *ld. */
+/* Debug tap: copy the ratio mask (what = 3; M x ldm fp32) of the last call into dst; row stride via *ld. */
 int rfx_umx_debug_tap(rfx_umx_t* h, int what, const void* workspace, int B, int T, float* dst, int* ld, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -31,7 +31,7 @@ _SIGNATURES = {
     "rfx_device_supported": (C.c_int, []),
     "rfx_stft": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, C.c_float, _f32p, _f32p, C.c_void_p]),
     "rfx_istft": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, _f32p, C.c_void_p]),
-    "rfx_gemm_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "rfx_gemm_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "rfx_gemm": (C.c_int, [C.c_int, _f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, _f32p, C.c_int, _f32p, _f32p, _f32p, _f32p,
                            C.c_int, C.c_void_p, C.c_void_p]),
     "rfx_lstm_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

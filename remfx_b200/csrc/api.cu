@@ -63,21 +63,35 @@ int rfx_istft(const float* Z_ri, const float* mask, int B, int F, int n_fft, int
   return launch_istft(p, B, (cudaStream_t)stream);
 }
 
-size_t rfx_gemm_scratch_bytes(int N, int K) { return packed_weight_bytes(N, K, choose_bn(N)); }
+size_t rfx_gemm_scratch_bytes(int M, int N, int K) {
+  const size_t kpad = (size_t)ceil_div(K, 64) * 64;
+  return align_up((size_t)M * kpad * 2 * 2, 256) + align_up(split_weight_elems(N, K, g2_choose_bn(N)) * 2 * 2, 256);
+}
 
 int rfx_gemm(int impl, const float* A, int lda, int M, const float* W, int N, int K, float* C, int ldc, const float* s1, const float* t1,
              const float* s2, const float* t2, int act, void* scratch, void* stream) {
   RFX_REQUIRE(A && W && C, "null argument");
   RFX_REQUIRE(impl == 0 || impl == 1, "impl 0 or 1");
+  RFX_REQUIRE(M > 0 && N > 0 && K > 0, "positive sizes");
   Epilogue e;
   e.s1 = s1; e.t1 = t1; e.s2 = s2; e.t2 = t2; e.act = act;
   cudaStream_t s = (cudaStream_t)stream;
   if (impl == 1) return launch_gemm_simt(A, lda, M, W, K, N, K, C, ldc, e, s);
-  RFX_REQUIRE(scratch != nullptr, "impl 0 needs scratch (rfx_gemm_scratch_bytes)");
-  PackedW pw;
-  int rc = pack_weights(W, K, N, K, choose_bn(N), scratch, &pw, s);
+  RFX_REQUIRE(scratch != nullptr && ((uintptr_t)scratch & 255) == 0, "impl 0 needs 256-byte aligned scratch (rfx_gemm_scratch_bytes)");
+  // split both operands into bf16 hi/lo planes, then run the TMA-fed tcgen05 engine
+  const int kpad = ceil_div(K, 64) * 64;
+  __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(scratch);
+  __nv_bfloat16* a_lo = a_hi + (size_t)M * kpad;
+  int rc = launch_split_rows(A, lda, M, K, a_hi, a_lo, kpad, M, kpad, s);
   if (rc) return rc;
-  return launch_gemm_tc(A, lda, M, pw, C, ldc, e, s);
+  __nv_bfloat16* wdst = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(scratch) + align_up((size_t)M * kpad * 4, 256));
+  G2Problem pr;
+  if ((rc = pack_split_weights(W, K, N, K, g2_choose_bn(N), wdst, &pr.W, s))) return rc;
+  pr.A.hi = a_hi; pr.A.rows = M; pr.A.ld = kpad; pr.A.batch_stride = 0; pr.A.plane_stride = (long long)M * kpad;
+  pr.M = M; pr.N = N; pr.batch = 1; pr.Ktap = K; pr.taps = 1;
+  pr.Cf = C; pr.ldcf = ldc; pr.bscf = 0;
+  pr.epi = e;
+  return launch_gemm2(pr, s);
 }
 
 int rfx_lstm_info(int B, int* max_active_clusters, int* batch_per_cluster) {
@@ -89,7 +103,7 @@ int rfx_lstm_info(int B, int* max_active_clusters, int* batch_per_cluster) {
 
 int rfx_lstm_layer(const float* G, const float* Whh, float* Hout, int ldh, int B, int F, int H, void* stream) {
   RFX_REQUIRE(G && Whh && Hout, "null argument");
-  return launch_lstm_layer(G, 8 * H, Whh, Hout, ldh, B, F, H, (cudaStream_t)stream);
+  return launch_lstm_layer(G, 8 * H, Whh, Hout, ldh, nullptr, nullptr, 0, B, F, H, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,81 +1,12 @@
-// Dense layers of the hot path (Open-Unmix fc1/fc2/fc3 and the LSTM input projections,
-// umx/openunmix/model.py:53,62-69,72,76) as C = epilogue(A . W^T):
-//
-//   * gemm_tc_kernel  -- tcgen05 tensor cores with fp32-grade accuracy ("bf16x3"): both fp32 operands are
-//     split v = hi + lo into two bf16 values and three MMAs (lo*hi, hi*lo, hi*hi) accumulate into one
-//     fp32 TMEM accumulator.  The dropped lo*lo term is O(2^-16) relative, so the result meets the
-//     reference's 1e-4 rel-RMS parity gate where a single bf16/TF32 pass does not.
-//     A (activations, fp32 in HBM) is split on the fly by 4 producer warps while they stage it into the
-//     SWIZZLE_128B K-major layout; W is split and pre-tiled once at load time into ready-made shared-
-//     memory images fetched with one bulk async copy (UBLKCP) per stage.  One thread issues the MMAs;
-//     accumulators live in TMEM and are drained with tcgen05.ld by the same 4 warps for the fused
-//     epilogue (BatchNorm-eval affine, output scale/mean, tanh / ReLU).
-//   * gemm_simt_kernel -- plain fp32 FFMA GEMM with the same contract, kept as an on-device cross-check
-//     and selectable with RFX_GEMM=simt.
+// Plain fp32 FFMA GEMM  C = epilogue(A . W^T)  with the same epilogue contract as the tensor-core engine
+// (gemm2.cu).  It is NOT on the product path: it exists as an on-device cross-check for the tcgen05 kernels
+// (tests/test_gpu_gemm_lstm.py) and as a debugging aid (rfx_gemm impl = 1).
 #include "kernels.h"
 
 namespace rfx {
 
-constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;
-constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // one bf16 plane of the A tile (16 KB)
-
 // ------------------------------------------------------------------------------------------------
-// Weight packing
-// ------------------------------------------------------------------------------------------------
-size_t packed_weight_bytes(int N, int K, int BN) {
-  const size_t Npad = (size_t)ceil_div(N, BN) * BN;
-  const size_t Kpad = (size_t)ceil_div(K, GEMM_BK) * GEMM_BK;
-  return Npad * Kpad * 2 /*bf16*/ * 2 /*hi, lo*/;
-}
-
-int choose_bn(int N) { return (N % 256 == 0) ? 256 : 128; }
-
-__global__ void pack_w_kernel(const float* __restrict__ W, int ldw, int N, int K, int BN, int KB, int Npad, uint8_t* __restrict__ dst) {
-  const long long total = (long long)Npad * KB * 8;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx & 7);
-    const int kb = (int)((idx >> 3) % KB);
-    const int n = (int)((idx >> 3) / KB);
-    const int nt = n / BN, rl = n % BN;
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      const int k0 = kb * GEMM_BK + c * 8 + 2 * e;
-      const float v0 = (n < N && k0 < K) ? W[(size_t)n * ldw + k0] : 0.0f;
-      const float v1 = (n < N && k0 + 1 < K) ? W[(size_t)n * ldw + k0 + 1] : 0.0f;
-      split_bf16(v0, h0, l0);
-      split_bf16(v1, h1, l1);
-      hi[e] = pack_bf16x2(h0, h1);
-      lo[e] = pack_bf16x2(l0, l1);
-    }
-    uint8_t* base = dst + ((size_t)(nt * KB + kb) * 2) * ((size_t)BN * 128);
-    const uint32_t off = sw128_offset(rl, c);
-    *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(base + (size_t)BN * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  }
-}
-
-int pack_weights(const float* W, int ldw, int N, int K, int BN, void* dst, PackedW* out, cudaStream_t stream) {
-  RFX_REQUIRE(BN == 128 || BN == 256, "BN must be 128 or 256");
-  out->data = dst;
-  out->N = N;
-  out->K = K;
-  out->BN = BN;
-  out->Npad = ceil_div(N, BN) * BN;
-  out->Kpad = ceil_div(K, GEMM_BK) * GEMM_BK;
-  out->bytes = packed_weight_bytes(N, K, BN);
-  const int KB = out->Kpad / GEMM_BK;
-  const long long total = (long long)out->Npad * KB * 8;
-  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  pack_w_kernel<<<blocks, 256, 0, stream>>>(W, ldw, N, K, BN, KB, out->Npad, reinterpret_cast<uint8_t*>(dst));
-  RFX_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Epilogue shared by both GEMM kernels
+// Epilogue
 // ------------------------------------------------------------------------------------------------
 struct EpiDev {
   const float* s1;
@@ -94,201 +25,6 @@ __device__ __forceinline__ float apply_epi(float v, int n, const EpiDev& e) {
   else if (e.act == ACT_RELU) v = fmaxf(v, 0.0f);
   else if (e.act == ACT_SIGMOID) v = sigmoidf_acc(v);
   return v;
-}
-
-// ------------------------------------------------------------------------------------------------
-// tcgen05 bf16x3 GEMM
-// ------------------------------------------------------------------------------------------------
-struct GemmTcParams {
-  const float* A;
-  int lda, M, Kvalid, KB;
-  const uint8_t* Wp;
-  int N;
-  float* C;
-  int ldc;
-  int c_vec4;  // C rows are 16B aligned (ldc % 4 == 0 and base aligned)
-  EpiDev epi;
-};
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const GemmTcParams p) {
-  constexpr int B_BYTES = BN * GEMM_BK * 2;                  // one bf16 plane of the W tile
-  constexpr int STAGE_BYTES = 2 * GEMM_A_BYTES + 2 * B_BYTES;  // A_hi | A_lo | B_hi | B_lo
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B tiles need 1024 B alignment
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* acc_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * GEMM_BM;
-  const int nt = blockIdx.y;
-  const int n0 = nt * BN;
-  const int KB = p.KB;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 128 + 1);  // 128 A-producer threads + the W bulk-copy issuer (expect_tx)
-      mbar_init(&empty_bar[s], 1);       // one tcgen05.commit
-    }
-    mbar_init(acc_bar, 1);
-    mbar_fence_init();
-  }
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, BN);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    // ===================== A producers: fp32 HBM -> (hi, lo) bf16 planes in swizzled smem ==========
-    const int tid = threadIdx.x;
-    const int c4 = tid & 15;  // which float4 of the 64-float row slice
-    const int r0 = tid >> 4;  // 0..7
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % STAGES;
-      const int it = kb / STAGES;
-      float4 v[16];
-      const int col = kb * GEMM_BK + c4 * 4;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int m = m0 + r0 + i * 8;
-        if (m < p.M && col < p.Kvalid)
-          v[i] = *reinterpret_cast<const float4*>(p.A + (size_t)m * p.lda + col);
-        else
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      mbar_wait(&empty_bar[s], (it & 1) ^ 1);
-      uint8_t* a_hi = smem + s * STAGE_BYTES;
-      uint8_t* a_lo = a_hi + GEMM_A_BYTES;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int row = r0 + i * 8;
-        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(v[i].x, h0, l0);
-        split_bf16(v[i].y, h1, l1);
-        split_bf16(v[i].z, h2, l2);
-        split_bf16(v[i].w, h3, l3);
-        const uint32_t off = sw128_offset(row, c4 >> 1) + (c4 & 1) * 8;
-        *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-        *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(&full_bar[s]);
-    }
-    // ===================== epilogue: TMEM -> registers -> fused affine/activation -> HBM ===========
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
-    const int m = m0 + warp * 32 + lane;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(trow + c * 32, r);
-      tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (m < p.M && nb < p.N) {
-        float* crow = p.C + (size_t)m * p.ldc + nb;
-        if (p.c_vec4 && nb + 32 <= p.N) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 o;
-            o.x = apply_epi(__uint_as_float(r[4 * q + 0]), nb + 4 * q + 0, p.epi);
-            o.y = apply_epi(__uint_as_float(r[4 * q + 1]), nb + 4 * q + 1, p.epi);
-            o.z = apply_epi(__uint_as_float(r[4 * q + 2]), nb + 4 * q + 2, p.epi);
-            o.w = apply_epi(__uint_as_float(r[4 * q + 3]), nb + 4 * q + 3, p.epi);
-            *reinterpret_cast<float4*>(crow + 4 * q) = o;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < p.N) crow[i] = apply_epi(__uint_as_float(r[i]), nb + i, p.epi);
-        }
-      }
-    }
-    tc_fence_before();
-  } else if (warp == 4) {
-    // ===================== W producer: one bulk async copy (hi+lo planes) per stage =================
-    if (lane == 0) {
-      const uint8_t* wsrc = p.Wp + (size_t)nt * KB * (2 * B_BYTES);
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % STAGES;
-        const int it = kb / STAGES;
-        mbar_wait(&empty_bar[s], (it & 1) ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], 2 * B_BYTES);
-        bulk_g2s(smem + s * STAGE_BYTES + 2 * GEMM_A_BYTES, wsrc + (size_t)kb * (2 * B_BYTES), 2 * B_BYTES, &full_bar[s]);
-      }
-    }
-  } else {
-    // ===================== MMA issuer ===============================================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % STAGES;
-        const int it = kb / STAGES;
-        mbar_wait(&full_bar[s], it & 1);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t a_lo = a_hi + GEMM_A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * GEMM_A_BYTES;
-        const uint32_t b_lo = b_hi + B_BYTES;
-#pragma unroll
-        for (int ks = 0; ks < GEMM_BK / 16; ++ks) {
-          const uint32_t ko = ks * 32;  // 16 bf16 = 32 bytes along K inside the 128-byte swizzle row
-          const uint64_t dah = umma_desc_sw128(a_hi + ko), dal = umma_desc_sw128(a_lo + ko);
-          const uint64_t dbh = umma_desc_sw128(b_hi + ko), dbl = umma_desc_sw128(b_lo + ko);
-          umma_f16(tmem_base, dal, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-          umma_f16(tmem_base, dah, dbl, idesc, 1u);
-          umma_f16(tmem_base, dah, dbh, idesc, 1u);
-        }
-        umma_commit(&empty_bar[s]);  // frees the stage once the MMAs above have read it
-      }
-      umma_commit(acc_bar);  // accumulator complete
-    }
-  }
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
-  }
-}
-
-template <int BN, int STAGES>
-static int launch_tc(const GemmTcParams& p, int mt, int ntiles, cudaStream_t stream) {
-  constexpr int STAGE_BYTES = 2 * GEMM_A_BYTES + 2 * BN * GEMM_BK * 2;
-  const int smem = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  gemm_tc_kernel<BN, STAGES><<<dim3(mt, ntiles), 192, smem, stream>>>(p);
-  RFX_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-int launch_gemm_tc(const float* A, int lda, int M, const PackedW& W, float* C, int ldc, const Epilogue& e, cudaStream_t stream) {
-  RFX_REQUIRE(W.data != nullptr, "weights not packed");
-  RFX_REQUIRE((lda & 3) == 0 && ((uintptr_t)A & 15) == 0, "A must be 16-byte aligned with lda % 4 == 0");
-  RFX_REQUIRE(M > 0, "M > 0");
-  GemmTcParams p;
-  p.A = A;
-  p.lda = lda;
-  p.M = M;
-  p.Kvalid = (W.Kpad <= lda) ? W.Kpad : (W.K / 4 * 4);
-  RFX_REQUIRE(p.Kvalid >= W.K, "A rows must be readable (and zero-padded) up to a multiple of 4 covering K");
-  p.KB = W.Kpad / GEMM_BK;
-  p.Wp = reinterpret_cast<const uint8_t*>(W.data);
-  p.N = W.N;
-  p.C = C;
-  p.ldc = ldc;
-  p.c_vec4 = ((ldc & 3) == 0 && ((uintptr_t)C & 15) == 0) ? 1 : 0;
-  p.epi = EpiDev{e.s1, e.t1, e.s2, e.t2, e.act};
-  const int mt = ceil_div(M, GEMM_BM);
-  if (W.BN == 256) return launch_tc<256, 2>(p, mt, W.Npad / 256, stream);
-  return launch_tc<128, 3>(p, mt, W.Npad / 128, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

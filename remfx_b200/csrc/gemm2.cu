@@ -1,0 +1,388 @@
+// gemm2: TMA-fed, warp-specialised, persistent tcgen05 GEMM / implicit-GEMM engine with fp32-grade accuracy.
+//
+//   C[b, m, n] = epilogue( sum_{tap} sum_{k} A[b, m + row_off[tap], k] * W[n, tap * Ktap + k] )
+//
+// Plain dense layers use one "tap" (row_off = 0); the TCN dilated Conv1d (remfx/tcn.py:28-36,48-59) uses
+// 7 taps at row offsets j * dilation plus an 8th tap for the 1x1 residual at the centre offset, on
+// channel-last activations -- an im2col-free implicit GEMM: the TMA box simply starts at a shifted row.
+//
+// Numerics ("bf16x3"): every fp32 value v lives in HBM as TWO bf16 planes (hi = bf16(v), lo = bf16(v - hi)),
+// 4 bytes per element like fp32; per K-step three MMAs (lo*hi, hi*lo, hi*hi) accumulate into one fp32
+// TMEM accumulator.  The dropped lo*lo term is O(2^-16): results meet the reference's 1e-4 rel-RMS gate
+// where a single bf16 or TF32 pass does not.
+//
+// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0    TMA producer: one 4-D tensor-map load per operand per stage (hi+lo planes in one box),
+//             SWIZZLE_128B, mbarrier complete_tx; K / M / N tails are zero-filled by the TMA unit
+//   warp 1    MMA issuer: a single thread issues tcgen05.mma (M=128, N=BN, K=16) from smem descriptors,
+//             tcgen05.commit releases smem stages and publishes finished accumulators
+//   warps 2-5 epilogue: tcgen05.ld the accumulator (TMEM is double-buffered: 2 x BN columns, so the
+//             epilogue of tile i overlaps the main loop of tile i+1), fused per-column affine(s) +
+//             activation, then either fp32 rows or re-split bf16 hi/lo planes for the next layer
+#include "kernels.h"
+
+#include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+
+namespace rfx {
+
+constexpr int G2_BM = 128;
+constexpr int G2_BK = 64;
+constexpr int G2_A_STAGE = 2 * G2_BM * G2_BK * 2;  // hi + lo planes of the A tile (32 KB)
+
+// ------------------------------------------------------------------------------------------------
+// Tensor maps (driver entry point fetched at run time: no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 4-D bf16 map over split planes: dims {cols, rows, batch, 2 planes}; box {64, box_rows, 1, 2}.
+static int make_split_map(CUtensorMap* map, const void* base, long long cols, long long rows, long long batch, long long ld_elems,
+                          long long batch_stride_elems, long long plane_stride_elems, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  RFX_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable");
+  RFX_REQUIRE(((uintptr_t)base & 15) == 0 && (ld_elems % 8) == 0 && (batch_stride_elems % 8) == 0 && (plane_stride_elems % 8) == 0,
+              "split-bf16 operand must be 16-byte aligned with strides that are multiples of 8 elements");
+  cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch, 2};
+  cuuint64_t strides[3] = {(cuuint64_t)ld_elems * 2, (cuuint64_t)batch_stride_elems * 2, (cuuint64_t)plane_stride_elems * 2};
+  cuuint32_t box[4] = {(cuuint32_t)G2_BK, (cuuint32_t)box_rows, 1, 2};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return 1;
+  }
+  return 0;
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> split bf16 planes (weights at load time; also a stand-alone op for tests)
+// ------------------------------------------------------------------------------------------------
+__global__ void split_rows_kernel(const float* __restrict__ src, long long ld_src, int rows, int cols, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long ld_dst, int rows_pad, int cols_pad) {
+  const long long total = (long long)rows_pad * cols_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols_pad), c = (int)(i % cols_pad);
+    const float v = (r < rows && c < cols) ? src[(size_t)r * ld_src + c] : 0.0f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[(size_t)r * ld_dst + c] = h;
+    lo[(size_t)r * ld_dst + c] = l;
+  }
+}
+
+int launch_split_rows(const float* src, long long ld_src, int rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo, long long ld_dst,
+                      int rows_pad, int cols_pad, cudaStream_t stream) {
+  const long long total = (long long)rows_pad * cols_pad;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  split_rows_kernel<<<blocks, 256, 0, stream>>>(src, ld_src, rows, cols, hi, lo, ld_dst, rows_pad, cols_pad);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------------
+struct G2Params {
+  int M;           // valid output rows per batch item
+  int N;           // valid output columns
+  int batch;       // batch items (grid tiles = batch * m_tiles * n_tiles)
+  int m_tiles, n_tiles;
+  int kb_per_tap;  // 64-wide K blocks per tap
+  int taps;
+  int row_off[16];  // A row offset of each tap
+  // outputs: fp32 (Cf) and/or split planes (Chi/Clo); row stride ld*, batch stride bs* (elements)
+  float* Cf;
+  long long ldcf, bscf;
+  __nv_bfloat16* Chi;
+  __nv_bfloat16* Clo;
+  long long ldcs, bscs;
+  // epilogue: v = acc * s1[n] + t1[n]; v = act(v) with optional per-column PReLU slope; v = v * s2[n] + t2[n] (if post) ...
+  const float* s1;
+  const float* t1;
+  const float* s2;
+  const float* t2;
+  const float* slope;  // ACT_PRELU: per-column negative slope
+  int act;
+};
+
+__device__ __forceinline__ float g2_epi(float v, int n, const G2Params& p) {
+  if (p.s1) v *= p.s1[n];
+  if (p.t1) v += p.t1[n];
+  if (p.s2) v *= p.s2[n];
+  if (p.t2) v += p.t2[n];
+  switch (p.act) {
+    case ACT_TANH: v = tanhf(v); break;
+    case ACT_RELU: v = fmaxf(v, 0.0f); break;
+    case ACT_SIGMOID: v = sigmoidf_acc(v); break;
+    case ACT_PRELU: v = v >= 0.0f ? v : v * p.slope[n]; break;
+    default: break;
+  }
+  return v;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+    gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const G2Params p) {
+  constexpr int B_STAGE = 2 * BN * G2_BK * 2;  // hi + lo planes of the W tile
+  constexpr int STAGE_BYTES = G2_A_STAGE + B_STAGE;
+  constexpr uint32_t IDESC = umma_idesc_bf16(G2_BM, BN);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int KB = p.kb_per_tap * p.taps;
+  const int tiles_per_batch = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.batch * tiles_per_batch;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      prefetch_tmap(&mapA);
+      prefetch_tmap(&mapW);
+      int it = 0;  // global k-block counter across tiles (stage ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_batch;
+        const int r = tile % tiles_per_batch;
+        const int m0 = (r / p.n_tiles) * G2_BM;
+        const int n0 = (r % p.n_tiles) * BN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          const int tap = kb / p.kb_per_tap;
+          const int kc = (kb % p.kb_per_tap) * G2_BK;
+          uint8_t* st = smem + s * STAGE_BYTES;
+          tma_load_4d(st, &mapA, kc, m0 + p.row_off[tap], b, 0, &full_bar[s]);
+          tma_load_4d(st + G2_A_STAGE, &mapW, kb * G2_BK, n0, 0, 0, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const int as = local & 1;
+        mbar_wait(&tempty_bar[as], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t a_lo = a_hi + G2_BM * G2_BK * 2;
+          const uint32_t b_hi = a_hi + G2_A_STAGE;
+          const uint32_t b_lo = b_hi + BN * G2_BK * 2;
+#pragma unroll
+          for (int ks = 0; ks < G2_BK / 16; ++ks) {
+            const uint32_t ko = ks * 32;
+            const uint64_t dah = umma_desc_sw128(a_hi + ko), dal = umma_desc_sw128(a_lo + ko);
+            const uint64_t dbh = umma_desc_sw128(b_hi + ko), dbl = umma_desc_sw128(b_lo + ko);
+            umma_f16(d_tmem, dal, dbh, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
+            umma_f16(d_tmem, dah, dbl, IDESC, 1u);
+            umma_f16(d_tmem, dah, dbh, IDESC, 1u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int b = tile / tiles_per_batch;
+      const int r = tile % tiles_per_batch;
+      const int m0 = (r / p.n_tiles) * G2_BM;
+      const int n0 = (r % p.n_tiles) * BN;
+      const int as = local & 1;
+      mbar_wait(&tfull_bar[as], (local >> 1) & 1);
+      tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const uint32_t trow = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+      const bool row_ok = m < p.M;
+      float* cf = p.Cf ? p.Cf + (size_t)b * p.bscf + (size_t)m * p.ldcf : nullptr;
+      __nv_bfloat16* chi = p.Chi ? p.Chi + (size_t)b * p.bscs + (size_t)m * p.ldcs : nullptr;
+      __nv_bfloat16* clo = p.Clo ? p.Clo + (size_t)b * p.bscs + (size_t)m * p.ldcs : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(trow + c * 32, v);
+        tmem_ld_wait();
+        const int nb = n0 + c * 32;
+        if (row_ok && nb < p.N) {
+          const bool full = nb + 32 <= p.N;
+          float o[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = (full || nb + i < p.N) ? g2_epi(__uint_as_float(v[i]), nb + i, p) : 0.0f;
+          if (cf) {
+            if (full && ((p.ldcf & 3) == 0) && ((((uintptr_t)(cf + nb)) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(cf + nb + 4 * i) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (nb + i < p.N) cf[nb + i] = o[i];
+            }
+          }
+          if (chi) {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(o[2 * i], h0, l0);
+              split_bf16(o[2 * i + 1], h1, l1);
+              ph[i] = pack_bf16x2(h0, h1);
+              pl[i] = pack_bf16x2(l0, l1);
+            }
+            if (full && ((p.ldcs & 7) == 0) && ((((uintptr_t)(chi + nb)) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                *reinterpret_cast<uint4*>(chi + nb + 8 * i) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+                *reinterpret_cast<uint4*>(clo + nb + 8 * i) = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (nb + i < p.N) {
+                  __nv_bfloat16 h, l;
+                  split_bf16(o[i], h, l);
+                  chi[nb + i] = h;
+                  clo[nb + i] = l;
+                }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+int g2_choose_bn(int N) { return (N >= 256 && N % 256 == 0) ? 256 : 128; }
+
+int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
+  RFX_REQUIRE(pr.A.hi && pr.W.hi, "null operand");
+  RFX_REQUIRE(pr.taps >= 1 && pr.taps <= 16, "1..16 taps");
+  RFX_REQUIRE(pr.Ktap % G2_BK == 0 || pr.taps == 1, "multi-tap problems need Ktap % 64 == 0");
+  RFX_REQUIRE(pr.Cf || pr.Chi, "at least one output");
+  const int BN = pr.W.BN;
+  RFX_REQUIRE(BN == 128 || BN == 256, "weights must be packed with BN 128 or 256");
+  G2Params p{};
+  p.M = pr.M; p.N = pr.N; p.batch = pr.batch;
+  p.m_tiles = ceil_div(pr.M, G2_BM);
+  p.n_tiles = ceil_div(pr.N, BN);
+  p.kb_per_tap = ceil_div(pr.Ktap, G2_BK);
+  p.taps = pr.taps;
+  for (int i = 0; i < pr.taps; ++i) p.row_off[i] = pr.row_off[i];
+  p.Cf = pr.Cf; p.ldcf = pr.ldcf; p.bscf = pr.bscf;
+  p.Chi = pr.Chi; p.Clo = pr.Clo; p.ldcs = pr.ldcs; p.bscs = pr.bscs;
+  p.s1 = pr.epi.s1; p.t1 = pr.epi.t1; p.s2 = pr.epi.s2; p.t2 = pr.epi.t2; p.slope = pr.epi.slope; p.act = pr.epi.act;
+  RFX_REQUIRE(pr.W.Kpad >= p.kb_per_tap * p.taps * G2_BK, "packed weight K extent too small for taps * Ktap");
+  CUtensorMap mapA, mapW;
+  int rc;
+  if ((rc = make_split_map(&mapA, pr.A.hi, pr.Ktap, pr.A.rows, pr.batch, pr.A.ld, pr.A.batch_stride, pr.A.plane_stride, G2_BM))) return rc;
+  if ((rc = make_split_map(&mapW, pr.W.hi, pr.W.Kpad, pr.W.Npad, 1, pr.W.Kpad, 0, (long long)pr.W.Npad * pr.W.Kpad, BN))) return rc;
+  const int total = p.batch * p.m_tiles * p.n_tiles;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = total < sms ? total : sms;
+  if (BN == 256) {
+    constexpr int STAGES = 2;
+    const int smem = STAGES * (G2_A_STAGE + 2 * 256 * G2_BK * 2) + 1024 + 256;
+    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    gemm2_kernel<256, STAGES><<<grid, 192, smem, stream>>>(mapA, mapW, p);
+  } else {
+    constexpr int STAGES = 3;
+    const int smem = STAGES * (G2_A_STAGE + 2 * 128 * G2_BK * 2) + 1024 + 256;
+    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    gemm2_kernel<128, STAGES><<<grid, 192, smem, stream>>>(mapA, mapW, p);
+  }
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t split_weight_elems(int N, int K, int BN) {
+  return (size_t)(ceil_div(N, BN) * BN) * (size_t)(ceil_div(K, G2_BK) * G2_BK);
+}
+
+int pack_split_weights(const float* W, long long ldw, int N, int K, int BN, __nv_bfloat16* dst, SplitW* out, cudaStream_t stream) {
+  RFX_REQUIRE(BN == 128 || BN == 256, "BN must be 128 or 256");
+  out->N = N; out->K = K; out->BN = BN;
+  out->Npad = ceil_div(N, BN) * BN;
+  out->Kpad = ceil_div(K, G2_BK) * G2_BK;
+  out->hi = dst;
+  out->lo = dst + (size_t)out->Npad * out->Kpad;
+  return launch_split_rows(W, ldw, N, K, dst, dst + (size_t)out->Npad * out->Kpad, out->Kpad, out->Npad, out->Kpad, stream);
+}
+
+}  // namespace rfx

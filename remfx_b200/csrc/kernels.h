@@ -29,6 +29,9 @@ struct StftParams {
   int ldz;
   float* A;             // [B*F, lda] real, may be null; columns [bins, lda) are zero-filled
   int lda;
+  __nv_bfloat16* Ahi;   // optional split-bf16 copy of A (planes hi / lo, row stride ldas) for the tensor-core layers
+  __nv_bfloat16* Alo;
+  int ldas;
   const float* in_mean;   // STFT_UMX_MAG only
   const float* in_scale;
 };
@@ -53,35 +56,52 @@ int launch_istft(const IstftParams& p, int B, cudaStream_t stream);
 
 // ---------------------------------------------------------------- GEMM (gemm.cu)
 // C[m, n] = act( ((sum_k A[m,k] W[n,k]) * s1[n] + t1[n]) * s2[n] + t2[n] )   (null vectors = identity)
-enum Act { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
+enum Act { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2, ACT_SIGMOID = 3, ACT_PRELU = 4 };
 
 struct Epilogue {
   const float* s1 = nullptr;
   const float* t1 = nullptr;
   const float* s2 = nullptr;
   const float* t2 = nullptr;
+  const float* slope = nullptr;  // ACT_PRELU: per-column negative slope (gemm2 only)
   int act = ACT_NONE;
 };
 
-// Weight matrix W[N, K] (row-major fp32, as torch.nn.Linear stores it) pre-split into bf16 hi/lo and
-// pre-tiled into the exact SWIZZLE_128B shared-memory images the tcgen05 kernel consumes.
-struct PackedW {
-  void* data = nullptr;   // device; owned by whoever called pack_weights
-  size_t bytes = 0;
-  int N = 0, K = 0;       // logical
-  int Npad = 0, Kpad = 0; // padded to BN / 64
-  int BN = 0;             // 128 or 256
-};
-size_t packed_weight_bytes(int N, int K, int BN);
-int choose_bn(int N);
-int pack_weights(const float* W, int ldw, int N, int K, int BN, void* dst, PackedW* out, cudaStream_t stream);
-
-// bf16x3 tensor-core GEMM (tcgen05, fp32-grade accuracy). A: fp32 [M, lda] with lda % 4 == 0, 16B aligned,
-// readable and zero (or finite * zero weight) up to Kpad columns.
-int launch_gemm_tc(const float* A, int lda, int M, const PackedW& W, float* C, int ldc, const Epilogue& e, cudaStream_t stream);
-// plain fp32 FFMA GEMM with the same contract on raw weights (cross-check / RFX_GEMM=simt mode).
+// plain fp32 FFMA GEMM on raw fp32 operands (cross-check only; the product path is gemm2 below).
 int launch_gemm_simt(const float* A, int lda, int M, const float* W, int ldw, int N, int K, float* C, int ldc, const Epilogue& e,
                      cudaStream_t stream);
+
+// ---------------------------------------------------------------- gemm2 (gemm2.cu): TMA-fed persistent engine
+// Activations between tensor-core layers live in HBM as two bf16 planes (hi, lo): v ~= hi + lo.
+struct SplitAct {
+  const __nv_bfloat16* hi = nullptr;  // element (b, r, c) at hi[b * batch_stride + r * ld + c]; lo plane at + plane_stride
+  long long rows = 0;                 // rows per batch item (rows beyond it read as zero)
+  long long ld = 0, batch_stride = 0, plane_stride = 0;  // in elements; multiples of 8
+};
+struct SplitW {
+  const __nv_bfloat16* hi = nullptr;  // [Npad][Kpad] row-major, zero padded; lo plane follows at + Npad * Kpad
+  const __nv_bfloat16* lo = nullptr;
+  int N = 0, K = 0, Npad = 0, Kpad = 0, BN = 0;
+};
+struct G2Problem {
+  SplitAct A;
+  SplitW W;
+  int M = 0, N = 0, batch = 1;  // output rows per batch item, output columns
+  int Ktap = 0, taps = 1;       // K extent per tap (A columns); W column index = tap * ceil64(Ktap) + k
+  int row_off[16] = {0};        // A row offset per tap (implicit-GEMM convolution)
+  float* Cf = nullptr;          // fp32 output (optional)
+  long long ldcf = 0, bscf = 0;
+  __nv_bfloat16* Chi = nullptr;  // split-bf16 output (optional)
+  __nv_bfloat16* Clo = nullptr;
+  long long ldcs = 0, bscs = 0;
+  Epilogue epi;
+};
+int g2_choose_bn(int N);
+size_t split_weight_elems(int N, int K, int BN);  // elements of ONE plane
+int pack_split_weights(const float* W, long long ldw, int N, int K, int BN, __nv_bfloat16* dst, SplitW* out, cudaStream_t stream);
+int launch_split_rows(const float* src, long long ld_src, int rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo, long long ld_dst,
+                      int rows_pad, int cols_pad, cudaStream_t stream);
+int launch_gemm2(const G2Problem& pr, cudaStream_t stream);
 
 // ---------------------------------------------------------------- LSTM recurrence (lstm.cu)
 // One direction-pair of one layer: G [B*F, ldg] holds W_ih x + b_ih + b_hh for both directions
@@ -89,7 +109,9 @@ int launch_gemm_simt(const float* A, int lda, int M, const float* W, int ldw, in
 // Hout[b*F + t][dir*H + unit].
 int lstm_max_active_clusters();  // co-resident 8-CTA clusters of the recurrence kernel on this device
 int lstm_choose_nb(int B);       // batch items per cluster used for batch size B
-int launch_lstm_layer(const float* G, int ldg, const float* Whh, float* Hout, int ldh, int B, int F, int H, cudaStream_t stream);
+// Hout (fp32) and/or Hhi/Hlo (split bf16 planes, row stride ldhs) may be given.
+int launch_lstm_layer(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs,
+                      int B, int F, int H, cudaStream_t stream);
 
 // ---------------------------------------------------------------- small utility kernels (util.cu)
 int launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale, float* shift,

@@ -44,7 +44,8 @@ __device__ __forceinline__ void bulk_s2cluster(uint32_t dst_cluster_addr, uint32
 // the smallest NB for which 2 * ceil(B / NB) clusters fit (cudaOccupancyMaxActiveClusters).
 template <int NB>
 __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 32, 1)
-    lstm_rec_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Whh, float* __restrict__ Hout, int ldh, int B, int F) {
+    lstm_rec_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Whh, float* __restrict__ Hout, int ldh,
+                    __nv_bfloat16* __restrict__ Hhi, __nv_bfloat16* __restrict__ Hlo, int ldhs, int B, int F) {
   constexpr int TX_BYTES = LSTM_CL * NB * LSTM_UPC * 4;  // bytes of h_t every CTA receives per step
   __shared__ __align__(128) float h_buf[2][LSTM_CL][NB][LSTM_UPC];  // [buffer][source CTA][batch][unit]
   __shared__ __align__(128) float stage[2][NB][LSTM_UPC];           // this CTA's new h values
@@ -172,7 +173,18 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 3
       bulk_s2cluster(dst_h + boff, smem_u32(&stage[cur ^ 1][0][0]), NB * LSTM_UPC * sizeof(float),
                      dst_bar + (uint32_t)((cur ^ 1) * sizeof(uint64_t)));
     }
-    if (wvalid) Hout[((size_t)(b0 + wb) * F + tt) * ldh + dir * LSTM_H + rank * LSTM_UPC + wu] = stage[cur ^ 1][wb][wu];
+    if (wvalid) {
+      const float hv = stage[cur ^ 1][wb][wu];
+      const size_t row = (size_t)(b0 + wb) * F + tt;
+      const int col = dir * LSTM_H + rank * LSTM_UPC + wu;
+      if (Hout) Hout[row * ldh + col] = hv;
+      if (Hhi) {  // the next tensor-core layer consumes split-bf16 planes
+        __nv_bfloat16 h, l;
+        split_bf16(hv, h, l);
+        Hhi[row * ldhs + col] = h;
+        Hlo[row * ldhs + col] = l;
+      }
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) gin[q] = gn[q];
   }
@@ -197,9 +209,10 @@ static int max_clusters() {
 }
 
 template <int NB>
-static int launch_nb(const float* G, int ldg, const float* Whh, float* Hout, int ldh, int B, int F, cudaStream_t stream) {
+static int launch_nb(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs, int B,
+                     int F, cudaStream_t stream) {
   dim3 grid(LSTM_CL, ceil_div(B, NB), 2);
-  lstm_rec_kernel<NB><<<grid, LSTM_WARPS * 32, 0, stream>>>(G, ldg, Whh, Hout, ldh, B, F);
+  lstm_rec_kernel<NB><<<grid, LSTM_WARPS * 32, 0, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F);
   RFX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -217,16 +230,18 @@ int lstm_choose_nb(int B) {
   return 8;  // more clusters than fit: several waves of the widest variant
 }
 
-int launch_lstm_layer(const float* G, int ldg, const float* Whh, float* Hout, int ldh, int B, int F, int H, cudaStream_t stream) {
+int launch_lstm_layer(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs,
+                      int B, int F, int H, cudaStream_t stream) {
   RFX_REQUIRE(H == LSTM_H, "lstm: hidden size per direction must be 256");
   RFX_REQUIRE(B > 0 && F > 0, "lstm: positive sizes");
   RFX_REQUIRE(((uintptr_t)Whh & 15) == 0, "lstm: W_hh must be 16-byte aligned");
+  RFX_REQUIRE(Hout || (Hhi && Hlo), "lstm: no output given");
   switch (lstm_choose_nb(B)) {
-    case 4: return launch_nb<4>(G, ldg, Whh, Hout, ldh, B, F, stream);
-    case 5: return launch_nb<5>(G, ldg, Whh, Hout, ldh, B, F, stream);
-    case 6: return launch_nb<6>(G, ldg, Whh, Hout, ldh, B, F, stream);
-    case 7: return launch_nb<7>(G, ldg, Whh, Hout, ldh, B, F, stream);
-    default: return launch_nb<8>(G, ldg, Whh, Hout, ldh, B, F, stream);
+    case 4: return launch_nb<4>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);
+    case 5: return launch_nb<5>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);
+    case 6: return launch_nb<6>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);
+    case 7: return launch_nb<7>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);
+    default: return launch_nb<8>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);
   }
 }
 

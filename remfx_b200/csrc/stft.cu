@@ -88,7 +88,14 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) stft_kernel(StftParams p) {
       if (p.mode == STFT_UMX_MAG) {
         // ComplexNorm (transforms.py:211) then OpenUnmix input shift/scale (model.py:127-128)
         const float mag = sqrtf(X.x * X.x + X.y * X.y);
-        p.A[m * p.lda + k] = (mag + p.in_mean[k]) * p.in_scale[k];
+        const float a = (mag + p.in_mean[k]) * p.in_scale[k];
+        if (p.A) p.A[m * p.lda + k] = a;
+        if (p.Ahi) {
+          __nv_bfloat16 h, l;
+          split_bf16(a, h, l);
+          p.Ahi[m * p.ldas + k] = h;
+          p.Alo[m * p.ldas + k] = l;
+        }
       } else if (p.mode == STFT_MAG) {
         p.A[m * p.lda + k] = sqrtf(X.x * X.x + X.y * X.y);
       } else if (p.mode == STFT_POWER) {

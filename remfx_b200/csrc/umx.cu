@@ -67,9 +67,9 @@ struct rfx_umx {
   // derived at finalize()
   DevBuf bn_s[3], bn_t[3];
   std::vector<DevBuf> lstm_bias, wih_cat, whh_cat;
-  std::vector<DevBuf> packed_store;
-  PackedW fc1p, fc2p, fc3p;
-  std::vector<PackedW> wihp;
+  std::vector<DevBuf> packed_store;  // split-bf16 (hi, lo) weight planes
+  SplitW fc1p, fc2p, fc3p;
+  std::vector<SplitW> wihp;
   bool finalized = false;
   // optional per-stage timing (cudaEvents recorded on the caller's stream between the launches)
   bool profiling = false;
@@ -88,29 +88,36 @@ struct rfx_umx {
 
 namespace {
 
+// Workspace layout.  Activations between tensor-core layers are split-bf16 planes (hi then lo).
 struct UmxLayout {
   int F, M, lda1, ldm;
   size_t off_x, off_out, off_Z, off_A1, off_XC, off_G, off_H1, off_H2, off_Y2, off_mask, total;
+  size_t plane_A1, plane_XC, plane_H, plane_Y2;  // elements per plane
 };
 
 UmxLayout umx_layout(const rfx_umx* h, int B, int T) {
   UmxLayout L;
   L.F = T / h->cfg.hop + 1;
   L.M = B * L.F;
-  L.lda1 = ceil_div(h->bins, 64) * 64;
+  L.lda1 = ceil_div(h->bins, 8) * 8;
   L.ldm = ceil_div(h->bins, 4) * 4;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
   const size_t M = L.M;
+  const int hid = h->cfg.hidden;
+  L.plane_A1 = M * L.lda1;
+  L.plane_XC = M * 2 * hid;
+  L.plane_H = M * hid;
+  L.plane_Y2 = M * hid;
   L.off_x = take((size_t)B * T * 4);
   L.off_out = take((size_t)B * T * 4);
   L.off_Z = take(M * h->bins * 8);
-  L.off_A1 = take(M * L.lda1 * 4);
-  L.off_XC = take(M * 2 * h->cfg.hidden * 4);
+  L.off_A1 = take(L.plane_A1 * 2 * 2);
+  L.off_XC = take(L.plane_XC * 2 * 2);
   L.off_G = take(M * 8 * h->H * 4);
-  L.off_H1 = take(M * h->cfg.hidden * 4);
-  L.off_H2 = take(M * h->cfg.hidden * 4);
-  L.off_Y2 = take(M * h->cfg.hidden * 4);
+  L.off_H1 = take(L.plane_H * 2 * 2);
+  L.off_H2 = take(L.plane_H * 2 * 2);
+  L.off_Y2 = take(L.plane_Y2 * 2 * 2);
   L.off_mask = take(M * L.ldm * 4);
   L.total = o;
   return L;
@@ -121,10 +128,17 @@ const float* P(const rfx_umx* h, const std::string& k) {
   return it == h->params.end() ? nullptr : it->second.p;
 }
 
-int gemm(const rfx_umx* h, const float* A, int lda, int M, const PackedW& Wp, const float* Wraw, float* C, int ldc, const Epilogue& e,
-         cudaStream_t s) {
-  if (h->cfg.gemm_impl == 1) return launch_gemm_simt(A, lda, M, Wraw, Wp.K, Wp.N, Wp.K, C, ldc, e, s);
-  return launch_gemm_tc(A, lda, M, Wp, C, ldc, e, s);
+// One dense layer on the tensor-core engine: A (split planes, K columns) x W^T -> fp32 and/or split output.
+int dense(const __nv_bfloat16* a_hi, size_t a_plane, int lda, int M, int K, const SplitW& W, float* Cf, int ldcf, __nv_bfloat16* c_hi,
+          size_t c_plane, int ldcs, const Epilogue& e, cudaStream_t s) {
+  G2Problem pr;
+  pr.A.hi = a_hi; pr.A.rows = M; pr.A.ld = lda; pr.A.batch_stride = 0; pr.A.plane_stride = (long long)a_plane;
+  pr.W = W;
+  pr.M = M; pr.N = W.N; pr.batch = 1; pr.Ktap = K; pr.taps = 1;
+  pr.Cf = Cf; pr.ldcf = ldcf;
+  pr.Chi = c_hi; pr.Clo = c_hi ? c_hi + c_plane : nullptr; pr.ldcs = ldcs;
+  pr.epi = e;
+  return launch_gemm2(pr, s);
 }
 
 }  // namespace
@@ -137,7 +151,7 @@ int rfx_umx_create(const rfx_umx_config* cfg, rfx_umx_t** out) {
   RFX_REQUIRE(cfg->hop > 0 && cfg->hop % 2 == 0 && cfg->n_fft % cfg->hop == 0, "hop must be even and divide n_fft");
   RFX_REQUIRE(cfg->hidden == 512, "hidden must be 512 (LSTM kernel is specialised for 256 units per direction)");
   RFX_REQUIRE(cfg->nb_layers >= 1 && cfg->nb_layers <= 8, "nb_layers in [1,8]");
-  RFX_REQUIRE(cfg->gemm_impl == 0 || cfg->gemm_impl == 1, "gemm_impl 0 or 1");
+  RFX_REQUIRE(cfg->gemm_impl == 0, "gemm_impl must be 0 (tcgen05 bf16x3 engine)");
   rfx_umx* h = new rfx_umx();
   h->cfg = *cfg;
   h->bins = cfg->n_fft / 2 + 1;
@@ -191,7 +205,7 @@ int rfx_umx_finalize(rfx_umx_t* h, void* stream) {
   h->lstm_bias.assign(L, DevBuf());
   h->wih_cat.assign(L, DevBuf());
   h->whh_cat.assign(L, DevBuf());
-  h->wihp.assign(L, PackedW());
+  h->wihp.assign(L, SplitW());
   h->packed_store.assign(L + 3, DevBuf());
   for (int l = 0; l < L; ++l) {
     if (h->lstm_bias[l].alloc(8 * H) || h->wih_cat[l].alloc((size_t)8 * H * hid) || h->whh_cat[l].alloc((size_t)8 * H * H)) return 1;
@@ -206,16 +220,20 @@ int rfx_umx_finalize(rfx_umx_t* h, void* stream) {
                                      cudaMemcpyDeviceToDevice, s));
       if ((rc = launch_add_vec(P(h, "lstm.bias_ih" + sfx), P(h, "lstm.bias_hh" + sfx), h->lstm_bias[l].p + d * 4 * H, 4 * H, s))) return rc;
     }
-    const int BN = choose_bn(8 * H);
-    if (h->packed_store[l].alloc(packed_weight_bytes(8 * H, hid, BN) / 4)) return 1;
-    if ((rc = pack_weights(h->wih_cat[l].p, hid, 8 * H, hid, BN, h->packed_store[l].p, &h->wihp[l], s))) return rc;
+    const int BN = g2_choose_bn(8 * H);
+    if (h->packed_store[l].alloc(split_weight_elems(8 * H, hid, BN))) return 1;  // 2 planes x 2 bytes = 4 bytes / element
+    if ((rc = pack_split_weights(h->wih_cat[l].p, hid, 8 * H, hid, BN, reinterpret_cast<__nv_bfloat16*>(h->packed_store[l].p),
+                                 &h->wihp[l], s)))
+      return rc;
   }
-  struct { const char* key; int N, K; PackedW* dst; } fcs[3] = {
+  struct { const char* key; int N, K; SplitW* dst; } fcs[3] = {
       {"fc1.weight", hid, bins, &h->fc1p}, {"fc2.weight", hid, 2 * hid, &h->fc2p}, {"fc3.weight", bins, hid, &h->fc3p}};
   for (int i = 0; i < 3; ++i) {
-    const int BN = choose_bn(fcs[i].N);
-    if (h->packed_store[L + i].alloc(packed_weight_bytes(fcs[i].N, fcs[i].K, BN) / 4)) return 1;
-    if ((rc = pack_weights(P(h, fcs[i].key), fcs[i].K, fcs[i].N, fcs[i].K, BN, h->packed_store[L + i].p, fcs[i].dst, s))) return rc;
+    const int BN = g2_choose_bn(fcs[i].N);
+    if (h->packed_store[L + i].alloc(split_weight_elems(fcs[i].N, fcs[i].K, BN))) return 1;
+    if ((rc = pack_split_weights(P(h, fcs[i].key), fcs[i].K, fcs[i].N, fcs[i].K, BN,
+                                 reinterpret_cast<__nv_bfloat16*>(h->packed_store[L + i].p), fcs[i].dst, s)))
+      return rc;
   }
   h->finalized = true;
   return 0;
@@ -239,11 +257,11 @@ int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void*
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   float2* Z = reinterpret_cast<float2*>(ws + L.off_Z);
-  float* A1 = reinterpret_cast<float*>(ws + L.off_A1);
-  float* XC = reinterpret_cast<float*>(ws + L.off_XC);
+  __nv_bfloat16* A1 = reinterpret_cast<__nv_bfloat16*>(ws + L.off_A1);
+  __nv_bfloat16* XC = reinterpret_cast<__nv_bfloat16*>(ws + L.off_XC);
   float* G = reinterpret_cast<float*>(ws + L.off_G);
-  float* Hb[2] = {reinterpret_cast<float*>(ws + L.off_H1), reinterpret_cast<float*>(ws + L.off_H2)};
-  float* Y2 = reinterpret_cast<float*>(ws + L.off_Y2);
+  __nv_bfloat16* Hb[2] = {reinterpret_cast<__nv_bfloat16*>(ws + L.off_H1), reinterpret_cast<__nv_bfloat16*>(ws + L.off_H2)};
+  __nv_bfloat16* Y2 = reinterpret_cast<__nv_bfloat16*>(ws + L.off_Y2);
   float* mask = reinterpret_cast<float*>(ws + L.off_mask);
   const int hid = h->cfg.hidden, H = h->H, nl = h->cfg.nb_layers;
   const float2* tw = twiddles(h->cfg.n_fft);
@@ -263,40 +281,41 @@ int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void*
   };
   if ((rc = mark())) return rc;
 
-  // (1) STFT (transforms.py:106-116) + ComplexNorm (:211) + input shift/scale (model.py:127-128)
+  // (1) STFT (transforms.py:106-116) + ComplexNorm (:211) + input shift/scale (model.py:127-128) -> split planes
   StftParams sp{};
   sp.x = x; sp.x_bstride = T; sp.T = T;
   sp.x_aligned8 = (((uintptr_t)x & 7) == 0 && (T % 2 == 0)) ? 1 : 0;
   sp.window = P(h, "window"); sp.tw = tw;
   sp.n_fft = h->cfg.n_fft; sp.hop = h->cfg.hop; sp.F = L.F;
   sp.scale = 1.0f; sp.alpha = 1.0f; sp.mode = STFT_UMX_MAG;
-  sp.Z = Z; sp.ldz = h->bins; sp.A = A1; sp.lda = L.lda1;
+  sp.Z = Z; sp.ldz = h->bins; sp.A = nullptr; sp.lda = 0;
+  sp.Ahi = A1; sp.Alo = A1 + L.plane_A1; sp.ldas = L.lda1;
   sp.in_mean = P(h, "input_mean"); sp.in_scale = P(h, "input_scale");
   if ((rc = launch_stft(sp, B, s)) || (rc = mark())) return rc;
 
   // (2) fc1 + bn1 + tanh (model.py:132-138) -> first half of the skip-concat buffer
   Epilogue e1; e1.s1 = h->bn_s[0].p; e1.t1 = h->bn_t[0].p; e1.act = ACT_TANH;
-  if ((rc = gemm(h, A1, L.lda1, L.M, h->fc1p, P(h, "fc1.weight"), XC, 2 * hid, e1, s)) || (rc = mark())) return rc;
+  if ((rc = dense(A1, L.plane_A1, L.lda1, L.M, h->bins, h->fc1p, nullptr, 0, XC, L.plane_XC, 2 * hid, e1, s)) || (rc = mark())) return rc;
 
   // (3) BiLSTM stack (model.py:141): per layer one input-projection GEMM + one recurrent cluster kernel
-  const float* lin = XC; int ldin = 2 * hid;
+  const __nv_bfloat16* lin = XC; size_t lin_plane = L.plane_XC; int ldin = 2 * hid;
   for (int l = 0; l < nl; ++l) {
     Epilogue eb; eb.t1 = h->lstm_bias[l].p;
-    if ((rc = gemm(h, lin, ldin, L.M, h->wihp[l], h->wih_cat[l].p, G, 8 * H, eb, s)) || (rc = mark())) return rc;
-    float* hout; int ldh;
-    if (l == nl - 1) { hout = XC + hid; ldh = 2 * hid; }  // torch.cat([x, lstm_out], -1) (model.py:144) for free
-    else { hout = Hb[l & 1]; ldh = hid; }
-    if ((rc = launch_lstm_layer(G, 8 * H, h->whh_cat[l].p, hout, ldh, B, L.F, H, s)) || (rc = mark())) return rc;
-    lin = hout; ldin = ldh;
+    if ((rc = dense(lin, lin_plane, ldin, L.M, hid, h->wihp[l], G, 8 * H, nullptr, 0, 0, eb, s)) || (rc = mark())) return rc;
+    __nv_bfloat16* hout; size_t hplane; int ldh;
+    if (l == nl - 1) { hout = XC + hid; hplane = L.plane_XC; ldh = 2 * hid; }  // torch.cat([x, lstm_out], -1) (model.py:144) for free
+    else { hout = Hb[l & 1]; hplane = L.plane_H; ldh = hid; }
+    if ((rc = launch_lstm_layer(G, 8 * H, h->whh_cat[l].p, nullptr, 0, hout, hout + hplane, ldh, B, L.F, H, s)) || (rc = mark())) return rc;
+    lin = hout; lin_plane = hplane; ldin = ldh;
   }
 
   // (4) fc2 + bn2 + ReLU (model.py:147-150)
   Epilogue e2; e2.s1 = h->bn_s[1].p; e2.t1 = h->bn_t[1].p; e2.act = ACT_RELU;
-  if ((rc = gemm(h, XC, 2 * hid, L.M, h->fc2p, P(h, "fc2.weight"), Y2, hid, e2, s)) || (rc = mark())) return rc;
+  if ((rc = dense(XC, L.plane_XC, 2 * hid, L.M, 2 * hid, h->fc2p, nullptr, 0, Y2, L.plane_Y2, hid, e2, s)) || (rc = mark())) return rc;
 
   // (5) fc3 + bn3 + output scale/mean + ReLU (model.py:153-164) = the non-negative ratio mask
   Epilogue e3; e3.s1 = h->bn_s[2].p; e3.t1 = h->bn_t[2].p; e3.s2 = P(h, "output_scale"); e3.t2 = P(h, "output_mean"); e3.act = ACT_RELU;
-  if ((rc = gemm(h, Y2, hid, L.M, h->fc3p, P(h, "fc3.weight"), mask, L.ldm, e3, s)) || (rc = mark())) return rc;
+  if ((rc = dense(Y2, L.plane_Y2, hid, L.M, hid, h->fc3p, mask, L.ldm, nullptr, 0, 0, e3, s)) || (rc = mark())) return rc;
 
   // (6) `* mix` (model.py:164) + wiener niter=0 (filtering.py:442-451) + iSTFT (transforms.py:168-177)
   IstftParams ip{};
@@ -345,16 +364,9 @@ int rfx_umx_debug_tap(rfx_umx_t* h, int what, const void* workspace, int B, int 
   RFX_REQUIRE(h && workspace && dst && ld, "null argument");
   const UmxLayout L = umx_layout(h, B, T);
   const uint8_t* ws = reinterpret_cast<const uint8_t*>(workspace);
-  const float* src = nullptr;
-  size_t count = 0;
-  switch (what) {
-    case 0: src = reinterpret_cast<const float*>(ws + L.off_A1); *ld = L.lda1; count = (size_t)L.M * L.lda1; break;
-    case 1:
-    case 2: src = reinterpret_cast<const float*>(ws + L.off_XC); *ld = 2 * h->cfg.hidden; count = (size_t)L.M * 2 * h->cfg.hidden; break;
-    case 3: src = reinterpret_cast<const float*>(ws + L.off_mask); *ld = L.ldm; count = (size_t)L.M * L.ldm; break;
-    default: set_error("umx debug tap: unknown id"); return 2;
-  }
-  RFX_CHECK_CUDA(cudaMemcpyAsync(dst, src, count * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  RFX_REQUIRE(what == 3, "only the mask tap (3) is available: other activations are stored as split bf16 planes");
+  *ld = L.ldm;
+  RFX_CHECK_CUDA(cudaMemcpyAsync(dst, ws + L.off_mask, (size_t)L.M * L.ldm * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 

@@ -68,7 +68,7 @@ class OpenUnmixModel(nn.Module):
     """B200-native drop-in for `remfx.models.OpenUnmixModel` (remfx/models.py:259-304)."""
 
     def __init__(self, n_fft: int = 2048, hop_length: int = 512, n_channels: int = 1, alpha: float = 0.3,
-                 sample_rate: int = 22050, gemm_impl: str = "tc"):
+                 sample_rate: int = 22050):
         super().__init__()
         if n_channels != 1:
             raise ValueError("remfx_b200.OpenUnmixModel supports mono audio only (RemFx uses n_channels=1)")
@@ -81,7 +81,6 @@ class OpenUnmixModel(nn.Module):
         self.sample_rate = sample_rate
         self.model = _OpenUnmixParams(nb_bins=self.num_bins, nb_channels=n_channels)
         self.separator = _SeparatorParams({"other": self.model}, sample_rate, n_fft)
-        self.gemm_impl = gemm_impl
         self._handle: Optional[C.c_void_p] = None
         self._stamp = None
         self._ws: Optional[Tensor] = None
@@ -99,8 +98,7 @@ class OpenUnmixModel(nn.Module):
         if self._handle is not None and stamp == self._stamp:
             return self._handle
         if self._handle is None:
-            cfg = _lib.UmxConfig(self.n_fft, self.hop_length, self.model.hidden_size, self.model.nb_layers,
-                                 0 if self.gemm_impl == "tc" else 1)
+            cfg = _lib.UmxConfig(self.n_fft, self.hop_length, self.model.hidden_size, self.model.nb_layers, 0)
             h = C.c_void_p()
             _lib.check(L.rfx_umx_create(C.byref(cfg), C.byref(h)), "rfx_umx_create")
             self._handle = h
@@ -122,8 +120,6 @@ class OpenUnmixModel(nn.Module):
                 _lib.lib().rfx_umx_destroy(h)
             except Exception:
                 pass
-
-    STAGES = ("stft", "fc1", "wih0", "lstm0", "wih1", "lstm1", "wih2", "lstm2", "fc2", "fc3", "istft")
 
     def set_profiling(self, on: bool, device="cuda:0") -> None:
         """Record cudaEvents between the kernel launches of subsequent sample() calls."""

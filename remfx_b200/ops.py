@@ -122,14 +122,10 @@ def linear(A: torch.Tensor, W: torch.Tensor, s1=None, t1=None, s2=None, t2=None,
         raise ValueError("linear: K mismatch")
     L = _lib.lib()
     Ain, lda = A, K
-    if impl == "tc" and K % 64 != 0:  # the tensor-core kernel reads whole 64-wide K blocks: give it zero padding
-        lda = (K + 63) // 64 * 64
-        Ain = torch.zeros(M, lda, dtype=torch.float32, device=A.device)
-        Ain[:, :K] = A
     Cout = torch.empty(M, N, dtype=torch.float32, device=A.device)
     scratch = None
     if impl == "tc":
-        scratch = torch.empty(L.rfx_gemm_scratch_bytes(N, K), dtype=torch.uint8, device=A.device)
+        scratch = torch.empty(L.rfx_gemm_scratch_bytes(M, N, K), dtype=torch.uint8, device=A.device)
     vecs = [None if v is None else _prep(v) for v in (s1, t1, s2, t2)]
     rc = L.rfx_gemm(0 if impl == "tc" else 1, _lib.ptr(Ain), lda, M, _lib.ptr(W), N, K, _lib.ptr(Cout), N, *[_lib.ptr(v) for v in vecs],
                     _ACTS[act], _lib.ptr(scratch), _lib.cur_stream())

@@ -11,20 +11,19 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4  # BASELINE.json north_star: 1e-4 relative RMS (fp32)
 
 
-def _model(sd, impl="tc"):
+def _model(sd):
     from remfx_b200.models import OpenUnmixModel
 
-    m = OpenUnmixModel(n_fft=2048, hop_length=512, n_channels=1, alpha=0.3, sample_rate=48000, gemm_impl=impl)
+    m = OpenUnmixModel(n_fft=2048, hop_length=512, n_channels=1, alpha=0.3, sample_rate=48000)
     m.load_state_dict(sd, strict=True)
     return m.cuda().eval()
 
 
-@pytest.mark.parametrize("impl", ["simt", "tc"])
-def test_sample_matches_reference_golden(impl):
+def test_sample_matches_reference_golden():
     g = golden("umx_sample.npz")
     sd = weights.umx_state(int(g["wseed"]))
     x = weights.synth_audio(int(g["xseed"]), int(g["B"]), int(g["T"]))
-    out = _model(sd, impl).sample(x.cuda())
+    out = _model(sd).sample(x.cuda())
     assert out.shape == (2, 1, 16384)
     err = relrms(out, torch.from_numpy(g["out"]))
     assert err < TOL, err

@@ -12,7 +12,7 @@ impls = sys.argv[2].split(",") if len(sys.argv) > 2 else ["tc"]
 T = 262144
 for impl in impls:
     torch.manual_seed(0)
-    m = OpenUnmixModel(sample_rate=48000, gemm_impl=impl).cuda().eval()
+    m = OpenUnmixModel(sample_rate=48000).cuda().eval()
     x = synth_audio(1, B, T).cuda()
     m.set_profiling(True)
     for _ in range(3):
