@@ -11,14 +11,17 @@
 // TMEM accumulator.  The dropped lo*lo term is O(2^-16): results meet the reference's 1e-4 rel-RMS gate
 // where a single bf16 or TF32 pass does not.
 //
-// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+// Structure (one CTA per SM, persistent over output tiles, 320 threads):
 //   warp 0    TMA producer: one 4-D tensor-map load per operand per stage (hi+lo planes in one box),
 //             SWIZZLE_128B, mbarrier complete_tx; K / M / N tails are zero-filled by the TMA unit
 //   warp 1    MMA issuer: a single thread issues tcgen05.mma (M=128, N=BN, K=16) from smem descriptors,
 //             tcgen05.commit releases smem stages and publishes finished accumulators
-//   warps 2-5 epilogue: tcgen05.ld the accumulator (TMEM is double-buffered: 2 x BN columns, so the
-//             epilogue of tile i overlaps the main loop of tile i+1), fused per-column affine(s) +
-//             activation, then either fp32 rows or re-split bf16 hi/lo planes for the next layer
+//   warps 2-9 epilogue (two warps per TMEM lane quarter, each draining half of the columns): tcgen05.ld the
+//             accumulator (TMEM is double-buffered: 2 x BN columns, so the epilogue of tile i overlaps the
+//             main loop of tile i+1), fused per-column affine(s) + activation, then either fp32 rows or
+//             re-split bf16 hi/lo planes for the next layer
+// DUAL mode (TCN block): the last tap accumulates into a second TMEM region and is added AFTER the
+// activation:  out = PReLU(conv + bias) + W_res x  (remfx/tcn.py:50-57); BN = 256, no TMEM double buffering.
 #include "kernels.h"
 
 #include <cuda.h>
@@ -133,23 +136,60 @@ struct G2Params {
   int act;
 };
 
-__device__ __forceinline__ float g2_epi(float v, int n, const G2Params& p) {
-  if (p.s1) v *= p.s1[n];
-  if (p.t1) v += p.t1[n];
-  if (p.s2) v *= p.s2[n];
-  if (p.t2) v += p.t2[n];
-  switch (p.act) {
-    case ACT_TANH: v = tanhf(v); break;
-    case ACT_RELU: v = fmaxf(v, 0.0f); break;
-    case ACT_SIGMOID: v = sigmoidf_acc(v); break;
-    case ACT_PRELU: v = v >= 0.0f ? v : v * p.slope[n]; break;
-    default: break;
+// Apply the epilogue to 8 consecutive columns [n, n+8) held in v[0..7].  Null vectors act as 1 / 0, which is
+// exact in fp32 (v * 1 + 0 == v), so the result equals the conditional form while the inner loop stays branch-free.
+__device__ __forceinline__ void load8(const float* vec, int n, float fill, bool aligned, float (&o)[8]) {
+  if (!vec) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fill;
+  } else if (aligned) {
+    const float4 a = *reinterpret_cast<const float4*>(vec + n);
+    const float4 b = *reinterpret_cast<const float4*>(vec + n + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = vec[n + i];
   }
-  return v;
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__device__ __forceinline__ void g2_epi8(float (&v)[8], int n, const G2Params& p, bool aligned) {
+  float s[8], t[8];
+  load8(p.s1, n, 1.0f, aligned, s);
+  load8(p.t1, n, 0.0f, aligned, t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], s[i], t[i]);
+  if (p.s2 || p.t2) {
+    load8(p.s2, n, 1.0f, aligned, s);
+    load8(p.t2, n, 0.0f, aligned, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], s[i], t[i]);
+  }
+  switch (p.act) {
+    case ACT_TANH:
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = tanhf(v[i]);
+      break;
+    case ACT_RELU:
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+      break;
+    case ACT_SIGMOID:
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = sigmoidf_acc(v[i]);
+      break;
+    case ACT_PRELU:
+      load8(p.slope, n, 0.0f, aligned, s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = v[i] >= 0.0f ? v[i] : v[i] * s[i];
+      break;
+    default: break;
+  }
+}
+
+constexpr int G2_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+
+template <int BN, int STAGES, bool DUAL>
+__global__ void __launch_bounds__(G2_THREADS, 1)
     gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const G2Params p) {
   constexpr int B_STAGE = 2 * BN * G2_BK * 2;  // hi + lo planes of the W tile
   constexpr int STAGE_BYTES = G2_A_STAGE + B_STAGE;
@@ -176,7 +216,7 @@ __global__ void __launch_bounds__(192, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], 8);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -217,11 +257,14 @@ __global__ void __launch_bounds__(192, 1)
     if (lane == 0) {
       int it = 0, local = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-        const int as = local & 1;
-        mbar_wait(&tempty_bar[as], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        const int as = DUAL ? 0 : (local & 1);
+        const int aphase = DUAL ? (local & 1) : ((local >> 1) & 1);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const int kb_res = DUAL ? (p.taps - 1) * p.kb_per_tap : KB;  // first k-block of the residual tap
         for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t d_tmem = tmem_base + (DUAL ? (kb >= kb_res ? BN : 0) : as * BN);
+          const bool first_kb = (kb == 0) || (kb == kb_res);
           const int s = it % STAGES;
           mbar_wait(&full_bar[s], (it / STAGES) & 1);
           tc_fence_after();
@@ -234,7 +277,7 @@ __global__ void __launch_bounds__(192, 1)
             const uint32_t ko = ks * 32;
             const uint64_t dah = umma_desc_sw128(a_hi + ko), dal = umma_desc_sw128(a_lo + ko);
             const uint64_t dbh = umma_desc_sw128(b_hi + ko), dbl = umma_desc_sw128(b_lo + ko);
-            umma_f16(d_tmem, dal, dbh, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
+            umma_f16(d_tmem, dal, dbh, IDESC, (!first_kb || ks > 0) ? 1u : 0u);
             umma_f16(d_tmem, dah, dbl, IDESC, 1u);
             umma_f16(d_tmem, dah, dbh, IDESC, 1u);
           }
@@ -244,70 +287,100 @@ __global__ void __launch_bounds__(192, 1)
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;   // which half of the tile's columns this warp drains
+    constexpr int CH = BN / 64;         // 32-column chunks per warp
+    const bool vec_al = (((uintptr_t)p.s1 | (uintptr_t)p.t1 | (uintptr_t)p.s2 | (uintptr_t)p.t2 | (uintptr_t)p.slope) & 15) == 0;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int b = tile / tiles_per_batch;
       const int r = tile % tiles_per_batch;
       const int m0 = (r / p.n_tiles) * G2_BM;
       const int n0 = (r % p.n_tiles) * BN;
-      const int as = local & 1;
-      mbar_wait(&tfull_bar[as], (local >> 1) & 1);
+      const int as = DUAL ? 0 : (local & 1);
+      const int aphase = DUAL ? (local & 1) : ((local >> 1) & 1);
+      mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
-      const uint32_t trow = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t trow = tmem_base + (DUAL ? 0 : as * BN) + ((uint32_t)(q * 32) << 16);
       const bool row_ok = m < p.M;
       float* cf = p.Cf ? p.Cf + (size_t)b * p.bscf + (size_t)m * p.ldcf : nullptr;
       __nv_bfloat16* chi = p.Chi ? p.Chi + (size_t)b * p.bscs + (size_t)m * p.ldcs : nullptr;
       __nv_bfloat16* clo = p.Clo ? p.Clo + (size_t)b * p.bscs + (size_t)m * p.ldcs : nullptr;
+      const bool cf_vec = cf && ((p.ldcf & 3) == 0) && ((p.bscf & 3) == 0) && (((uintptr_t)p.Cf & 15) == 0);
+      const bool cs_vec = chi && ((p.ldcs & 7) == 0) && ((p.bscs & 7) == 0) && (((uintptr_t)p.Chi & 15) == 0) && (((uintptr_t)p.Clo & 15) == 0);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < CH; ++cc) {
+        const int c = half * CH + cc;
         uint32_t v[32];
         tmem_ld32(trow + c * 32, v);
+        uint32_t v2[32];
+        if (DUAL) tmem_ld32(trow + BN + c * 32, v2);
         tmem_ld_wait();
         const int nb = n0 + c * 32;
         if (row_ok && nb < p.N) {
           const bool full = nb + 32 <= p.N;
-          float o[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = (full || nb + i < p.N) ? g2_epi(__uint_as_float(v[i]), nb + i, p) : 0.0f;
-          if (cf) {
-            if (full && ((p.ldcf & 3) == 0) && ((((uintptr_t)(cf + nb)) & 15) == 0)) {
+          for (int j = 0; j < 4; ++j) {
+            const int n8 = nb + 8 * j;
+            if (n8 >= p.N) break;
+            float o[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4*>(cf + nb + 4 * i) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-            } else {
+            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * j + i]);
+            if (full) {
+              g2_epi8(o, n8, p, vec_al);
+            } else {  // ragged last chunk (at most one per output row): per-column slow path
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (nb + i < p.N) cf[nb + i] = o[i];
+              for (int i = 0; i < 8; ++i) {
+                const int n = n8 + i < p.N ? n8 + i : p.N - 1;
+                float val = fmaf(o[i], p.s1 ? p.s1[n] : 1.0f, p.t1 ? p.t1[n] : 0.0f);
+                if (p.s2 || p.t2) val = fmaf(val, p.s2 ? p.s2[n] : 1.0f, p.t2 ? p.t2[n] : 0.0f);
+                switch (p.act) {
+                  case ACT_TANH: val = tanhf(val); break;
+                  case ACT_RELU: val = fmaxf(val, 0.0f); break;
+                  case ACT_SIGMOID: val = sigmoidf_acc(val); break;
+                  case ACT_PRELU: val = val >= 0.0f ? val : val * p.slope[n]; break;
+                  default: break;
+                }
+                o[i] = val;
+              }
             }
-          }
-          if (chi) {
-            uint32_t ph[16], pl[16];
+            if (DUAL) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(o[2 * i], h0, l0);
-              split_bf16(o[2 * i + 1], h1, l1);
-              ph[i] = pack_bf16x2(h0, h1);
-              pl[i] = pack_bf16x2(l0, l1);
+              for (int i = 0; i < 8; ++i) o[i] += __uint_as_float(v2[8 * j + i]);
             }
-            if (full && ((p.ldcs & 7) == 0) && ((((uintptr_t)(chi + nb)) & 15) == 0)) {
+            if (cf) {
+              if (full && cf_vec) {
+                *reinterpret_cast<float4*>(cf + n8) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(cf + n8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (n8 + i < p.N) cf[n8 + i] = o[i];
+              }
+            }
+            if (chi) {
+              uint32_t ph[4], pl[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                *reinterpret_cast<uint4*>(chi + nb + 8 * i) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
-                *reinterpret_cast<uint4*>(clo + nb + 8 * i) = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+                const float2 hf = __bfloat1622float2(h2);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(o[2 * i] - hf.x, o[2 * i + 1] - hf.y);
+                ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
               }
-            } else {
+              if (full && cs_vec) {
+                *reinterpret_cast<uint4*>(chi + n8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<uint4*>(clo + n8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+              } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (nb + i < p.N) {
-                  __nv_bfloat16 h, l;
-                  split_bf16(o[i], h, l);
-                  chi[nb + i] = h;
-                  clo[nb + i] = l;
-                }
+                for (int i = 0; i < 8; ++i)
+                  if (n8 + i < p.N) {
+                    chi[n8 + i] = reinterpret_cast<const __nv_bfloat16*>(ph)[i];
+                    clo[n8 + i] = reinterpret_cast<const __nv_bfloat16*>(pl)[i];
+                  }
+              }
             }
           }
         }
@@ -356,16 +429,22 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = total < sms ? total : sms;
-  if (BN == 256) {
+  if (pr.dual) {
+    RFX_REQUIRE(BN == 256 && pr.N <= 256 * p.n_tiles && pr.taps >= 2, "dual-accumulator mode needs BN = 256 and >= 2 taps");
     constexpr int STAGES = 2;
     const int smem = STAGES * (G2_A_STAGE + 2 * 256 * G2_BK * 2) + 1024 + 256;
-    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gemm2_kernel<256, STAGES><<<grid, 192, smem, stream>>>(mapA, mapW, p);
+    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    gemm2_kernel<256, STAGES, true><<<grid, G2_THREADS, smem, stream>>>(mapA, mapW, p);
+  } else if (BN == 256) {
+    constexpr int STAGES = 2;
+    const int smem = STAGES * (G2_A_STAGE + 2 * 256 * G2_BK * 2) + 1024 + 256;
+    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    gemm2_kernel<256, STAGES, false><<<grid, G2_THREADS, smem, stream>>>(mapA, mapW, p);
   } else {
     constexpr int STAGES = 3;
     const int smem = STAGES * (G2_A_STAGE + 2 * 128 * G2_BK * 2) + 1024 + 256;
-    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gemm2_kernel<128, STAGES><<<grid, 192, smem, stream>>>(mapA, mapW, p);
+    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    gemm2_kernel<128, STAGES, false><<<grid, G2_THREADS, smem, stream>>>(mapA, mapW, p);
   }
   RFX_CHECK_CUDA(cudaGetLastError());
   return 0;

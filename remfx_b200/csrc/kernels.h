@@ -89,6 +89,7 @@ struct G2Problem {
   int M = 0, N = 0, batch = 1;  // output rows per batch item, output columns
   int Ktap = 0, taps = 1;       // K extent per tap (A columns); W column index = tap * ceil64(Ktap) + k
   int row_off[16] = {0};        // A row offset per tap (implicit-GEMM convolution)
+  bool dual = false;            // last tap -> second accumulator, added after the activation (TCN residual)
   float* Cf = nullptr;          // fp32 output (optional)
   long long ldcf = 0, bscf = 0;
   __nv_bfloat16* Chi = nullptr;  // split-bf16 output (optional)
