@@ -66,6 +66,8 @@ int rfx_gemm(int impl, const float* A, int lda, int M, const float* W, int N, in
 /* Scheduling facts of the recurrence kernel on the current device: how many 8-CTA clusters are co-resident
  * and how many batch items each cluster takes for batch size B (all clusters of a launch run as one wave). */
 int rfx_lstm_info(int B, int* max_active_clusters, int* batch_per_cluster);
+/* Process-wide choice of the recurrence kernel: 0 = tensor-core (mma.sync bf16x3, default), 1 = fp32 FFMA. */
+int rfx_lstm_set_impl(int impl);
 int rfx_lstm_layer(const float* G, const float* Whh, float* Hout, int ldh, int B, int F, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -107,6 +109,35 @@ int rfx_umx_set_profiling(rfx_umx_t* h, int on);
 int rfx_umx_stage_times(rfx_umx_t* h, float* ms, int capacity, int* n_out);
 /* Debug tap: copy the ratio mask (what = 3; M x ldm fp32) of the last call into dst; row stride via *ld. */
 int rfx_umx_debug_tap(rfx_umx_t* h, int what, const void* workspace, int B, int T, float* dst, int* ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * T1-T3  TCN effect-removal model
+ *   replaces remfx/models.py:370-390 (TCNModel.forward / sample) = remfx/tcn.py:126-130 (TCN.forward):
+ *   nblocks x TCNBlock (remfx/tcn.py:48-59: dilated Conv1d, PReLU, 1x1 residual + crop) then tanh(1x1 conv).
+ * Parameter keys are the reference's names below `model.`: "process_blocks.3.conv1.weight", "output.bias", ...
+ * x: (B, 1, T) fp32 device -> out: (B, 1, rfx_tcn_out_length(T)) fp32 device.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rfx_tcn rfx_tcn_t;
+
+typedef struct {
+  int ninputs;         /* 1 */
+  int noutputs;        /* 1 */
+  int nblocks;         /* 20 */
+  int channel_width;   /* 256 (multiple of 64, <= 256) */
+  int kernel_size;     /* 7 (odd, <= 15) */
+  int stack_size;      /* 10 */
+  int dilation_growth; /* 2 */
+  int causal;          /* 0: center_crop residual (cfg/model/tcn.yaml), 1: causal_crop */
+} rfx_tcn_config;
+
+int rfx_tcn_create(const rfx_tcn_config* cfg, rfx_tcn_t** out);
+void rfx_tcn_destroy(rfx_tcn_t* h);
+int rfx_tcn_load_param(rfx_tcn_t* h, const char* key, const float* src, int64_t numel, void* stream);
+int rfx_tcn_finalize(rfx_tcn_t* h, void* stream);
+long long rfx_tcn_out_length(const rfx_tcn_t* h, long long T);
+size_t rfx_tcn_workspace_bytes(const rfx_tcn_t* h, int B, long long T);
+int rfx_tcn_forward(rfx_tcn_t* h, const float* x, int B, long long T, float* out, void* workspace, size_t workspace_bytes, void* stream);
+int rfx_tcn_launches_per_call(const rfx_tcn_t* h);
 
 /* ---------------------------------------------------------------------------------------------
  * L1/L2  RemFx loss = MultiResolutionSTFTLoss(out, target) + l1_weight * mean|out - target|

@@ -20,6 +20,11 @@ class RfxError(RuntimeError):
     pass
 
 
+class TcnConfig(C.Structure):
+    _fields_ = [("ninputs", C.c_int), ("noutputs", C.c_int), ("nblocks", C.c_int), ("channel_width", C.c_int), ("kernel_size", C.c_int),
+                ("stack_size", C.c_int), ("dilation_growth", C.c_int), ("causal", C.c_int)]
+
+
 class UmxConfig(C.Structure):
     _fields_ = [("n_fft", C.c_int), ("hop", C.c_int), ("hidden", C.c_int), ("nb_layers", C.c_int), ("gemm_impl", C.c_int)]
 
@@ -35,6 +40,7 @@ _SIGNATURES = {
     "rfx_gemm": (C.c_int, [C.c_int, _f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, _f32p, C.c_int, _f32p, _f32p, _f32p, _f32p,
                            C.c_int, C.c_void_p, C.c_void_p]),
     "rfx_lstm_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rfx_lstm_set_impl": (C.c_int, [C.c_int]),
     "rfx_lstm_layer": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "rfx_umx_create": (C.c_int, [C.POINTER(UmxConfig), C.POINTER(C.c_void_p)]),
     "rfx_umx_destroy": (None, [C.c_void_p]),
@@ -47,6 +53,14 @@ _SIGNATURES = {
     "rfx_umx_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "rfx_umx_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
     "rfx_umx_debug_tap": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int), C.c_void_p]),
+    "rfx_tcn_create": (C.c_int, [C.POINTER(TcnConfig), C.POINTER(C.c_void_p)]),
+    "rfx_tcn_destroy": (None, [C.c_void_p]),
+    "rfx_tcn_load_param": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int64, C.c_void_p]),
+    "rfx_tcn_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rfx_tcn_out_length": (C.c_longlong, [C.c_void_p, C.c_longlong]),
+    "rfx_tcn_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_longlong]),
+    "rfx_tcn_forward": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_longlong, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rfx_tcn_launches_per_call": (C.c_int, [C.c_void_p]),
     "rfx_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "rfx_remfx_loss": (C.c_int, [_f32p, C.c_longlong, _f32p, C.c_longlong, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_float, _f32p,
                                  C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -101,6 +101,12 @@ int rfx_lstm_info(int B, int* max_active_clusters, int* batch_per_cluster) {
   return 0;
 }
 
+int rfx_lstm_set_impl(int impl) {
+  RFX_REQUIRE(impl == 0 || impl == 1, "impl 0 (tensor-core) or 1 (fp32 FFMA)");
+  lstm_set_impl(impl);
+  return 0;
+}
+
 int rfx_lstm_layer(const float* G, const float* Whh, float* Hout, int ldh, int B, int F, int H, void* stream) {
   RFX_REQUIRE(G && Whh && Hout, "null argument");
   return launch_lstm_layer(G, 8 * H, Whh, Hout, ldh, nullptr, nullptr, 0, B, F, H, (cudaStream_t)stream);

@@ -109,7 +109,9 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream);
 // (column = dir * 4H + gate * H + unit, gate order i,f,g,o), Whh [2][4H][H]; writes h to
 // Hout[b*F + t][dir*H + unit].
 int lstm_max_active_clusters();  // co-resident 8-CTA clusters of the recurrence kernel on this device
-int lstm_choose_nb(int B);       // batch items per cluster used for batch size B
+int lstm_choose_nb(int B);       // batch items per cluster used for batch size B (FFMA variant)
+void lstm_set_impl(int impl);    // 0 = tensor-core mma.sync bf16x3 (default), 1 = fp32 FFMA
+int lstm_get_impl();
 // Hout (fp32) and/or Hhi/Hlo (split bf16 planes, row stride ldhs) may be given.
 int launch_lstm_layer(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs,
                       int B, int F, int H, cudaStream_t stream);

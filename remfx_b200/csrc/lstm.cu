@@ -194,6 +194,192 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 3
   cluster_wait();
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Tensor-core variant of the recurrence: the per-step mat-vec W_hh h_{t-1} runs on mma.sync.m16n8k16 (bf16,
+// fp32 accumulate) with the bf16x3 split (W_lo*h_hi + W_hi*h_lo + W_hi*h_hi), so one warp needs 48 HMMA
+// instead of ~640 FFMA + 28 shuffles per step.  Each warp owns 16 gate rows (4 units x {i,f,g,o}) as the M
+// dimension, the 8 batch slots of the cluster are the N dimension, K = 256.  W_hh hi/lo fragments live in
+// registers for the whole sequence; h is exchanged between the 8 CTAs as split-bf16 (hi, lo) -- exactly the
+// B-fragment format -- laid out [source CTA][plane][slot][32 units] so that (i) every CTA's contribution is
+// one contiguous 1 KB block (one DSMEM bulk copy per destination) and (ii) a lane's B fragments for two
+// K-steps are one conflict-free LDS.128 (K is permuted consistently in the A fragments).
+// Gate math uses ex2-based sigmoid/tanh (abs error ~1e-7), c and the emitted h stay fp32.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hmma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_hi2(float x, float y, float& rx, float& ry) {
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(x, y);
+  const float2 hf = __bfloat1622float2(h2);
+  rx = x - hf.x;
+  ry = y - hf.y;
+  return *reinterpret_cast<const uint32_t*>(&h2);
+}
+__device__ __forceinline__ uint32_t pack2(float x, float y) {
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(x, y);
+  return *reinterpret_cast<const uint32_t*>(&h2);
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+constexpr int LSTM_SLOTS = 8;                                      // batch slots per cluster (MMA N)
+constexpr int LSTM_BLK_BYTES = 2 * LSTM_SLOTS * LSTM_UPC * 2;      // one CTA's h block: 2 planes x 8 slots x 32 units bf16
+constexpr int LSTM_MMA_TX = LSTM_CL * LSTM_BLK_BYTES;              // bytes every CTA receives per step (8 KB)
+
+__global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 32, 1)
+    lstm_rec_mma_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Whh, float* __restrict__ Hout, int ldh,
+                        __nv_bfloat16* __restrict__ Hhi, __nv_bfloat16* __restrict__ Hlo, int ldhs, int B, int F, int NB) {
+  __shared__ __align__(128) __nv_bfloat16 h_buf[2][LSTM_CL][2][LSTM_SLOTS][LSTM_UPC];  // [buffer][source CTA][plane][slot][unit]
+  __shared__ __align__(128) __nv_bfloat16 stage[2][2][LSTM_SLOTS][LSTM_UPC];           // this CTA's new h (hi, lo)
+  __shared__ __align__(8) uint64_t h_bar[2];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int dir = blockIdx.z;
+  const int b0 = blockIdx.y * NB;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int u = gid >> 1, pp = gid & 1;  // unit within the warp; pp = 0: rows (i, g), pp = 1: rows (f, o)
+  const int unit = rank * LSTM_UPC + warp * 4 + u;
+  const int gate0 = pp ? 1 : 0, gate1 = pp ? 3 : 2;
+
+  // ---- A fragments: W_hh rows (gate0, unit) and (gate1, unit), true k = 32 P + 8 tig + [0, 8) for P = 0..7 ----
+  uint32_t a_hi[16][4], a_lo[16][4];
+  {
+    const float* w0 = Whh + ((size_t)dir * 4 * LSTM_H + (size_t)gate0 * LSTM_H + unit) * LSTM_H + 8 * tig;
+    const float* w1 = Whh + ((size_t)dir * 4 * LSTM_H + (size_t)gate1 * LSTM_H + unit) * LSTM_H + 8 * tig;
+#pragma unroll
+    for (int P = 0; P < 8; ++P) {
+      const float4 x0 = *reinterpret_cast<const float4*>(w0 + 32 * P), x1 = *reinterpret_cast<const float4*>(w0 + 32 * P + 4);
+      const float4 y0 = *reinterpret_cast<const float4*>(w1 + 32 * P), y1 = *reinterpret_cast<const float4*>(w1 + 32 * P + 4);
+      float rx, ry;
+      // K-step 2P: slots (2tig, 2tig+1) <- k+0,1 ; slots (2tig+8, +9) <- k+2,3.  K-step 2P+1: k+4,5 ; k+6,7.
+      a_hi[2 * P][0] = pack_hi2(x0.x, x0.y, rx, ry); a_lo[2 * P][0] = pack2(rx, ry);
+      a_hi[2 * P][1] = pack_hi2(y0.x, y0.y, rx, ry); a_lo[2 * P][1] = pack2(rx, ry);
+      a_hi[2 * P][2] = pack_hi2(x0.z, x0.w, rx, ry); a_lo[2 * P][2] = pack2(rx, ry);
+      a_hi[2 * P][3] = pack_hi2(y0.z, y0.w, rx, ry); a_lo[2 * P][3] = pack2(rx, ry);
+      a_hi[2 * P + 1][0] = pack_hi2(x1.x, x1.y, rx, ry); a_lo[2 * P + 1][0] = pack2(rx, ry);
+      a_hi[2 * P + 1][1] = pack_hi2(y1.x, y1.y, rx, ry); a_lo[2 * P + 1][1] = pack2(rx, ry);
+      a_hi[2 * P + 1][2] = pack_hi2(x1.z, x1.w, rx, ry); a_lo[2 * P + 1][2] = pack2(rx, ry);
+      a_hi[2 * P + 1][3] = pack_hi2(y1.z, y1.w, rx, ry); a_lo[2 * P + 1][3] = pack2(rx, ry);
+    }
+  }
+  for (int i = tid; i < (int)(sizeof(h_buf) / 4); i += LSTM_WARPS * 32) reinterpret_cast<uint32_t*>(&h_buf[0][0][0][0][0])[i] = 0u;
+  if (tid == 0) {
+    mbar_init(&h_bar[0], 1);
+    mbar_init(&h_bar[1], 1);
+    mbar_fence_init();
+  }
+
+  // This lane's accumulator columns are batch slots n0 = 2 tig and n0 + 1.
+  const int n0 = 2 * tig;
+  const bool v0 = n0 < NB && (b0 + n0) < B, v1 = (n0 + 1) < NB && (b0 + n0 + 1) < B;
+  const size_t gc0 = (size_t)dir * 4 * LSTM_H + (size_t)gate0 * LSTM_H + unit;
+  const size_t gc1 = (size_t)dir * 4 * LSTM_H + (size_t)gate1 * LSTM_H + unit;
+  float c_state[2] = {0.f, 0.f};
+  // Input projections are prefetched PF steps ahead (scattered 4-byte loads from HBM: ~1-2 us of latency must
+  // stay off the per-step critical path).  gq[j] holds the values for step (current + j).
+  constexpr int PF = 3;
+  float gq[PF][4];  // (gate0, n0), (gate0, n0+1), (gate1, n0), (gate1, n0+1)
+  auto load_g = [&](int st, float (&dst)[4]) {
+    dst[0] = dst[1] = dst[2] = dst[3] = 0.f;
+    if (st < F) {
+      const int tq = dir ? F - 1 - st : st;
+      if (v0) { const float* g = G + ((size_t)(b0 + n0) * F + tq) * ldg; dst[0] = g[gc0]; dst[2] = g[gc1]; }
+      if (v1) { const float* g = G + ((size_t)(b0 + n0 + 1) * F + tq) * ldg; dst[1] = g[gc0]; dst[3] = g[gc1]; }
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < PF; ++j) load_g(j, gq[j]);
+  const uint32_t dst_h = mapa_u32(smem_u32(&h_buf[0][rank][0][0][0]), lane & 7);
+  const uint32_t dst_bar = mapa_u32(smem_u32(&h_bar[0]), lane & 7);
+
+  __syncthreads();
+  cluster_arrive();
+  cluster_wait();
+
+  for (int step = 0; step < F; ++step) {
+    const int cur = step & 1;
+    const int tt = dir ? F - 1 - step : step;
+    if (tid == 0) mbar_arrive_expect_tx(&h_bar[cur ^ 1], LSTM_MMA_TX);
+    float gin[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gin[q] = gq[0][q];
+#pragma unroll
+    for (int j = 0; j + 1 < PF; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gq[j][q] = gq[j + 1][q];
+    load_g(step + PF, gq[PF - 1]);
+    if (step > 0) mbar_wait(&h_bar[cur], ((step - 1) >> 1) & 1);
+
+    // ---- mat-vec on the tensor cores: three independent accumulation chains ----
+    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint8_t* hb = reinterpret_cast<const uint8_t*>(&h_buf[cur][0][0][0][0]) + gid * (LSTM_UPC * 2) + tig * 16;
+#pragma unroll
+    for (int P = 0; P < 8; ++P) {
+      const uint4 bh = *reinterpret_cast<const uint4*>(hb + P * LSTM_BLK_BYTES);
+      const uint4 bl = *reinterpret_cast<const uint4*>(hb + P * LSTM_BLK_BYTES + LSTM_SLOTS * LSTM_UPC * 2);
+      hmma16816(d0, a_lo[2 * P], bh.x, bh.y);
+      hmma16816(d1, a_hi[2 * P], bl.x, bl.y);
+      hmma16816(d2, a_hi[2 * P], bh.x, bh.y);
+      hmma16816(d0, a_lo[2 * P + 1], bh.z, bh.w);
+      hmma16816(d1, a_hi[2 * P + 1], bl.z, bl.w);
+      hmma16816(d2, a_hi[2 * P + 1], bh.z, bh.w);
+    }
+    // d[0], d[1]: row gate0, slots n0, n0+1 ; d[2], d[3]: row gate1
+    float pre[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pre[i] = (d0[i] + d1[i]) + d2[i] + gin[i];
+    // ---- gate math.  pp = 0: (i, g) -> i * tanh(g);  pp = 1: (f, o).  tanh(x) = 2 sigmoid(2x) - 1 keeps it branch-free ----
+    const float sa0 = fast_sigmoid(pre[0]), sa1 = fast_sigmoid(pre[1]);  // sigmoid(i) | sigmoid(f)
+    const float sc = pp ? 1.0f : 2.0f;
+    float sb0 = fast_sigmoid(sc * pre[2]), sb1 = fast_sigmoid(sc * pre[3]);  // sigmoid(o) | sigmoid(2g)
+    if (!pp) { sb0 = 2.0f * sb0 - 1.0f; sb1 = 2.0f * sb1 - 1.0f; }          // tanh(g)
+    const float ig0 = __shfl_xor_sync(0xffffffffu, sa0 * sb0, 4);           // partner lane (gid ^ 1): i * tanh(g)
+    const float ig1 = __shfl_xor_sync(0xffffffffu, sa1 * sb1, 4);
+    float h0 = 0.f, h1 = 0.f;
+    uint32_t hh = 0u, hl = 0u;
+    if (pp) {
+      c_state[0] = sa0 * c_state[0] + ig0;
+      c_state[1] = sa1 * c_state[1] + ig1;
+      h0 = sb0 * (2.0f * fast_sigmoid(2.0f * c_state[0]) - 1.0f);
+      h1 = sb1 * (2.0f * fast_sigmoid(2.0f * c_state[1]) - 1.0f);
+      float r0, r1;
+      hh = pack_hi2(h0, h1, r0, r1);
+      hl = pack2(r0, r1);
+      __nv_bfloat16* st = &stage[cur ^ 1][0][n0][warp * 4 + u];
+      st[0] = reinterpret_cast<const __nv_bfloat16*>(&hh)[0];
+      st[LSTM_UPC] = reinterpret_cast<const __nv_bfloat16*>(&hh)[1];
+      st[LSTM_SLOTS * LSTM_UPC] = reinterpret_cast<const __nv_bfloat16*>(&hl)[0];
+      st[LSTM_SLOTS * LSTM_UPC + LSTM_UPC] = reinterpret_cast<const __nv_bfloat16*>(&hl)[1];
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0 && lane < LSTM_CL) {
+      const uint32_t boff = (uint32_t)((cur ^ 1) * LSTM_CL * LSTM_BLK_BYTES);
+      bulk_s2cluster(dst_h + boff, smem_u32(&stage[cur ^ 1][0][0][0]), LSTM_BLK_BYTES, dst_bar + (uint32_t)((cur ^ 1) * sizeof(uint64_t)));
+    }
+    // layer output to HBM: off the critical path (overlaps the DSMEM exchange)
+    if (pp) {
+      const int col = dir * LSTM_H + unit;
+      if (v0) {
+        const size_t row = (size_t)(b0 + n0) * F + tt;
+        if (Hout) Hout[row * ldh + col] = h0;
+        if (Hhi) { Hhi[row * ldhs + col] = reinterpret_cast<const __nv_bfloat16*>(&hh)[0]; Hlo[row * ldhs + col] = reinterpret_cast<const __nv_bfloat16*>(&hl)[0]; }
+      }
+      if (v1) {
+        const size_t row = (size_t)(b0 + n0 + 1) * F + tt;
+        if (Hout) Hout[row * ldh + col] = h1;
+        if (Hhi) { Hhi[row * ldhs + col] = reinterpret_cast<const __nv_bfloat16*>(&hh)[1]; Hlo[row * ldhs + col] = reinterpret_cast<const __nv_bfloat16*>(&hl)[1]; }
+      }
+    }
+  }
+  mbar_wait(&h_bar[F & 1], ((F - 1) >> 1) & 1);
+  cluster_arrive();
+  cluster_wait();
+}
+
 template <int NB>
 static int max_clusters() {
   cudaLaunchConfig_t cfg{};
@@ -230,12 +416,27 @@ int lstm_choose_nb(int B) {
   return 8;  // more clusters than fit: several waves of the widest variant
 }
 
+static int g_lstm_impl = 0;  // 0 = tensor-core (mma.sync bf16x3), 1 = fp32 FFMA
+void lstm_set_impl(int impl) { g_lstm_impl = impl; }
+int lstm_get_impl() { return g_lstm_impl; }
+
 int launch_lstm_layer(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs,
                       int B, int F, int H, cudaStream_t stream) {
   RFX_REQUIRE(H == LSTM_H, "lstm: hidden size per direction must be 256");
   RFX_REQUIRE(B > 0 && F > 0, "lstm: positive sizes");
   RFX_REQUIRE(((uintptr_t)Whh & 15) == 0, "lstm: W_hh must be 16-byte aligned");
   RFX_REQUIRE(Hout || (Hhi && Hlo), "lstm: no output given");
+  if (g_lstm_impl == 0) {
+    // batch slots per cluster: as few as possible while all clusters stay co-resident (the MMA cost does not depend on it)
+    const int maxc = lstm_max_active_clusters();
+    int nb = LSTM_SLOTS;
+    for (int cand = 1; cand <= LSTM_SLOTS; ++cand)
+      if (2 * ceil_div(B, cand) <= maxc) { nb = cand; break; }
+    dim3 grid(LSTM_CL, ceil_div(B, nb), 2);
+    lstm_rec_mma_kernel<<<grid, LSTM_WARPS * 32, 0, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb);
+    RFX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   switch (lstm_choose_nb(B)) {
     case 4: return launch_nb<4>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);
     case 5: return launch_nb<5>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);

@@ -1,0 +1,285 @@
+// TCN effect-removal model (remfx/tcn.py:62-138 behind remfx/models.py:370-390) on the GPU.
+//
+//   block 0  (1 -> C channels): SIMT kernel, 7 taps + bias -> PReLU -> + 1x1 residual on the centre sample
+//   blocks 1..N-1 (C -> C):     gemm2 implicit GEMM in dual-accumulator mode (tcgen05, bf16x3):
+//                               D1 = sum_j W_j x[t + j d]  (7 taps), D2 = W_res x[t + 3 d];
+//                               out = PReLU_c(D1 + b) + D2        (remfx/tcn.py:48-59, centre crop = offset 3d)
+//   tail:    tanh(1x1 conv C -> 1)  (remfx/tcn.py:129)
+// Activations are channel-last ([B][L][C]) split-bf16 planes, so every tap of the dilated convolution is a
+// plain 2-D TMA box at a shifted row -- no im2col, no padding copies.  Two ping-pong buffers.
+#include "kernels.h"
+#include "../../include/remfx_b200.h"
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace rfx {
+
+// ---- block 0: x (B, L0) fp32 -> split planes [B][L1][C], one thread per (time step, 8 channels) ----
+__global__ void __launch_bounds__(256) tcn_first_kernel(const float* __restrict__ x, long long x_bs, int L1, int C, int K, int dil, int res_off,
+                                                        const float* __restrict__ w /*[C][K]*/, const float* __restrict__ bias,
+                                                        const float* __restrict__ wres /*[C]*/, const float* __restrict__ slope,
+                                                        __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo, long long o_bs) {
+  const int groups = C / 8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= (long long)L1 * groups) return;
+  const int t = (int)(idx / groups);
+  const int c0 = (int)(idx % groups) * 8;
+  const float* xr = x + (size_t)b * x_bs + t;
+  float xs[16];
+  for (int j = 0; j < K; ++j) xs[j] = xr[j * dil];
+  const float xc = xr[res_off];
+  uint32_t ph[4], pl[4];
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    float acc = bias[c];
+    for (int j = 0; j < K; ++j) acc = fmaf(w[c * K + j], xs[j], acc);
+    acc = acc >= 0.0f ? acc : acc * slope[c];
+    o[i] = acc + wres[c] * xc;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(o[2 * i] - hf.x, o[2 * i + 1] - hf.y);
+    ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  const size_t off = (size_t)b * o_bs + (size_t)t * C + c0;
+  *reinterpret_cast<uint4*>(ohi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  *reinterpret_cast<uint4*>(olo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+// ---- tail: out[b][t] = tanh(sum_c w[c] * x[b][t][c] + bias); one warp per time step ----
+__global__ void __launch_bounds__(256) tcn_tail_kernel(const __nv_bfloat16* __restrict__ xhi, const __nv_bfloat16* __restrict__ xlo, long long x_bs,
+                                                       int L, int C, const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ out, long long o_bs) {
+  const int lane = threadIdx.x & 31;
+  const long long t = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (t >= L) return;
+  const __nv_bfloat16* rh = xhi + (size_t)b * x_bs + (size_t)t * C;
+  const __nv_bfloat16* rl = xlo + (size_t)b * x_bs + (size_t)t * C;
+  float acc = 0.0f;
+  for (int c = lane * 8; c < C; c += 256) {
+    const uint4 h = *reinterpret_cast<const uint4*>(rh + c);
+    const uint4 l = *reinterpret_cast<const uint4*>(rl + c);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[i]));
+      const float2 lf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[i]));
+      acc = fmaf(w[c + 2 * i], hf.x + lf.x, acc);
+      acc = fmaf(w[c + 2 * i + 1], hf.y + lf.y, acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[(size_t)b * o_bs + t] = tanhf(acc + bias[0]);
+}
+
+// ---- gather conv1.weight [C][C][K] and res.weight [C][C][1] into Wcat [C][(K+1)*C] (tap-major) ----
+__global__ void tcn_gather_w_kernel(const float* __restrict__ wconv, const float* __restrict__ wres, int C, int K, float* __restrict__ wcat) {
+  const long long total = (long long)C * (K + 1) * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % C);
+    const int tap = (int)((i / C) % (K + 1));
+    const int co = (int)(i / ((long long)C * (K + 1)));
+    wcat[i] = tap < K ? wconv[((size_t)co * C + ci) * K + tap] : wres[(size_t)co * C + ci];
+  }
+}
+
+struct TcnBuf {
+  float* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    RFX_CHECK_CUDA(cudaMalloc(&p, count * sizeof(float)));
+    n = count;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+}  // namespace rfx
+
+using namespace rfx;
+
+struct rfx_tcn {
+  rfx_tcn_config cfg;
+  std::map<std::string, TcnBuf> params;
+  std::vector<TcnBuf> wsplit;  // per block >= 1: split-bf16 planes of Wcat
+  std::vector<SplitW> wpack;
+  bool finalized = false;
+  ~rfx_tcn() {
+    for (auto& kv : params) kv.second.release();
+    for (auto& b : wsplit) b.release();
+  }
+};
+
+namespace {
+int dilation_of(const rfx_tcn* h, int n) {
+  int d = 1;
+  for (int i = 0; i < n % h->cfg.stack_size; ++i) d *= h->cfg.dilation_growth;
+  return d;
+}
+const float* TP(const rfx_tcn* h, const std::string& k) {
+  auto it = h->params.find(k);
+  return it == h->params.end() ? nullptr : it->second.p;
+}
+long long len_after(const rfx_tcn* h, long long T, int nblocks) {
+  long long L = T;
+  for (int n = 0; n < nblocks; ++n) L -= (long long)(h->cfg.kernel_size - 1) * dilation_of(h, n);
+  return L;
+}
+}  // namespace
+
+extern "C" {
+
+int rfx_tcn_create(const rfx_tcn_config* cfg, rfx_tcn_t** out) {
+  RFX_REQUIRE(cfg && out, "null argument");
+  RFX_REQUIRE(cfg->ninputs == 1 && cfg->noutputs == 1, "TCN: ninputs and noutputs must be 1 (mono audio, cfg/model/tcn.yaml)");
+  RFX_REQUIRE(cfg->nblocks >= 1 && cfg->nblocks <= 64, "TCN: nblocks in [1, 64]");
+  RFX_REQUIRE(cfg->channel_width % 64 == 0 && cfg->channel_width >= 64 && cfg->channel_width <= 256,
+              "TCN: channel_width must be 64, 128, 192 or 256");
+  RFX_REQUIRE(cfg->kernel_size >= 2 && cfg->kernel_size <= 15 && cfg->kernel_size % 2 == 1, "TCN: odd kernel_size in [3, 15]");
+  RFX_REQUIRE(cfg->stack_size >= 1 && cfg->dilation_growth >= 1, "TCN: stack_size, dilation_growth >= 1");
+  rfx_tcn* h = new rfx_tcn();
+  h->cfg = *cfg;
+  *out = h;
+  return 0;
+}
+
+void rfx_tcn_destroy(rfx_tcn_t* h) { delete h; }
+
+int rfx_tcn_load_param(rfx_tcn_t* h, const char* key, const float* src, int64_t numel, void* stream) {
+  RFX_REQUIRE(h && key && src && numel > 0, "bad argument");
+  TcnBuf& b = h->params[key];
+  if (b.n != (size_t)numel) {
+    if (b.alloc((size_t)numel)) return 1;
+  }
+  RFX_CHECK_CUDA(cudaMemcpyAsync(b.p, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  h->finalized = false;
+  return 0;
+}
+
+int rfx_tcn_finalize(rfx_tcn_t* h, void* stream) {
+  RFX_REQUIRE(h, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int C = h->cfg.channel_width, K = h->cfg.kernel_size, NBk = h->cfg.nblocks;
+  auto need = [&](const std::string& k, size_t n) -> int {
+    auto it = h->params.find(k);
+    if (it == h->params.end()) { set_error("tcn: missing parameter '" + k + "'"); return 2; }
+    if (it->second.n != n) { set_error("tcn: parameter '" + k + "' has " + std::to_string(it->second.n) + " elements, expected " + std::to_string(n)); return 2; }
+    return 0;
+  };
+  int rc;
+  for (auto& b : h->wsplit) b.release();
+  h->wsplit.assign(NBk, TcnBuf());
+  h->wpack.assign(NBk, SplitW());
+  TcnBuf wcat;
+  if (NBk > 1 && wcat.alloc((size_t)C * (K + 1) * C)) return 1;
+  for (int n = 0; n < NBk; ++n) {
+    const std::string p = "process_blocks." + std::to_string(n);
+    const int cin = n == 0 ? 1 : C;
+    if ((rc = need(p + ".conv1.weight", (size_t)C * cin * K)) || (rc = need(p + ".conv1.bias", C)) || (rc = need(p + ".res.weight", (size_t)C * cin)) ||
+        (rc = need(p + ".relu.weight", C))) {
+      wcat.release();
+      return rc;
+    }
+    if (n == 0) continue;
+    tcn_gather_w_kernel<<<148 * 4, 256, 0, s>>>(TP(h, p + ".conv1.weight"), TP(h, p + ".res.weight"), C, K, wcat.p);
+    RFX_CHECK_CUDA(cudaGetLastError());
+    if (h->wsplit[n].alloc(split_weight_elems(C, (K + 1) * C, 256))) { wcat.release(); return 1; }
+    if ((rc = pack_split_weights(wcat.p, (long long)(K + 1) * C, C, (K + 1) * C, 256, reinterpret_cast<__nv_bfloat16*>(h->wsplit[n].p), &h->wpack[n], s))) {
+      wcat.release();
+      return rc;
+    }
+  }
+  if ((rc = need("output.weight", C)) || (rc = need("output.bias", 1))) { wcat.release(); return rc; }
+  RFX_CHECK_CUDA(cudaStreamSynchronize(s));  // wcat is a temporary
+  wcat.release();
+  h->finalized = true;
+  return 0;
+}
+
+long long rfx_tcn_out_length(const rfx_tcn_t* h, long long T) { return h ? len_after(h, T, h->cfg.nblocks) : 0; }
+
+size_t rfx_tcn_workspace_bytes(const rfx_tcn_t* h, int B, long long T) {
+  if (!h || B <= 0) return 0;
+  const long long L1 = len_after(h, T, 1);
+  if (L1 <= 0) return 0;
+  const size_t plane = align_up((size_t)B * L1 * h->cfg.channel_width * 2, 256);
+  return 4 * plane;  // two ping-pong buffers x (hi, lo)
+}
+
+int rfx_tcn_forward(rfx_tcn_t* h, const float* x, int B, long long T, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  RFX_REQUIRE(h && x && out && workspace, "null argument");
+  RFX_REQUIRE(h->finalized, "rfx_tcn_finalize has not been called since the last parameter load");
+  const int C = h->cfg.channel_width, K = h->cfg.kernel_size, NBk = h->cfg.nblocks;
+  const long long Lout = len_after(h, T, NBk);
+  RFX_REQUIRE(B > 0 && Lout > 0, "input shorter than the receptive field");
+  RFX_REQUIRE(T < (1ll << 31), "T too large");
+  RFX_REQUIRE(workspace_bytes >= rfx_tcn_workspace_bytes(h, B, T), "workspace too small (rfx_tcn_workspace_bytes)");
+  RFX_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long L1 = len_after(h, T, 1);
+  const size_t plane_bytes = align_up((size_t)B * L1 * C * 2, 256);
+  const long long plane_elems = (long long)(plane_bytes / 2);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* buf[2] = {reinterpret_cast<__nv_bfloat16*>(ws), reinterpret_cast<__nv_bfloat16*>(ws + 2 * plane_bytes)};
+  const long long bs = L1 * C;  // batch stride (elements) of every activation buffer
+  const int centre = h->cfg.causal ? -1 : 0;  // causal_crop drops the last sample: offset (K-1) d - 1; center_crop: (K-1) d / 2
+
+  // block 0
+  {
+    const int d = dilation_of(h, 0);
+    const int res_off = h->cfg.causal ? (K - 1) * d - 1 : ((K - 1) * d) / 2;
+    (void)centre;
+    const long long items = L1 * (C / 8);
+    dim3 grid((unsigned)((items + 255) / 256), B);
+    tcn_first_kernel<<<grid, 256, 0, s>>>(x, T, (int)L1, C, K, d, res_off, TP(h, "process_blocks.0.conv1.weight"), TP(h, "process_blocks.0.conv1.bias"),
+                                          TP(h, "process_blocks.0.res.weight"), TP(h, "process_blocks.0.relu.weight"), buf[0], buf[0] + plane_elems, bs);
+    RFX_CHECK_CUDA(cudaGetLastError());
+  }
+  long long Lin = L1;
+  int cur = 0;
+  for (int n = 1; n < NBk; ++n) {
+    const int d = dilation_of(h, n);
+    const long long Lo = Lin - (long long)(K - 1) * d;
+    const std::string p = "process_blocks." + std::to_string(n);
+    G2Problem pr;
+    pr.A.hi = buf[cur]; pr.A.rows = Lin; pr.A.ld = C; pr.A.batch_stride = bs; pr.A.plane_stride = plane_elems;
+    pr.W = h->wpack[n];
+    pr.M = (int)Lo; pr.N = C; pr.batch = B; pr.Ktap = C; pr.taps = K + 1;
+    for (int j = 0; j < K; ++j) pr.row_off[j] = j * d;
+    pr.row_off[K] = h->cfg.causal ? (K - 1) * d - 1 : ((K - 1) * d) / 2;
+    pr.dual = true;
+    pr.Chi = buf[cur ^ 1]; pr.Clo = buf[cur ^ 1] + plane_elems; pr.ldcs = C; pr.bscs = bs;
+    pr.epi.t1 = TP(h, p + ".conv1.bias");
+    pr.epi.slope = TP(h, p + ".relu.weight");
+    pr.epi.act = ACT_PRELU;
+    int rc = launch_gemm2(pr, s);
+    if (rc) return rc;
+    Lin = Lo;
+    cur ^= 1;
+  }
+  {
+    dim3 grid((unsigned)((Lin + 7) / 8), B);
+    tcn_tail_kernel<<<grid, 256, 0, s>>>(buf[cur], buf[cur] + plane_elems, bs, (int)Lin, C, TP(h, "output.weight"), TP(h, "output.bias"), out, Lout);
+    RFX_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int rfx_tcn_launches_per_call(const rfx_tcn_t* h) { return h ? h->cfg.nblocks + 1 : 0; }
+
+}  // extern "C"

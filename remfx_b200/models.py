@@ -188,3 +188,130 @@ class OpenUnmixModel(nn.Module):
 
     def launches_per_call(self) -> int:
         return 5 + 2 * self.model.nb_layers
+
+
+# ======================================================================================================
+# TCN
+# ======================================================================================================
+class _TCNBlockParams(nn.Module):
+    """Parameter layout of remfx/tcn.py:11-46 (TCNBlock.__init__)."""
+
+    def __init__(self, in_ch: int, out_ch: int, kernel_size: int, dilation: int):
+        super().__init__()
+        self.conv1 = nn.Conv1d(in_ch, out_ch, kernel_size, stride=1, padding=0, dilation=dilation, bias=True)
+        self.res = nn.Conv1d(in_ch, out_ch, kernel_size=1, groups=1, stride=1, bias=False)
+        self.relu = nn.PReLU(out_ch)
+
+
+class _TCNParams(nn.Module):
+    """Parameter layout of remfx/tcn.py:62-124 (TCN.__init__); same ctor kwargs as cfg/model/tcn.yaml."""
+
+    def __init__(self, ninputs: int = 1, noutputs: int = 1, nblocks: int = 4, channel_growth: int = 0, channel_width: int = 32,
+                 kernel_size: int = 13, stack_size: int = 10, dilation_growth: int = 10, condition: bool = False, latent_dim: int = 2,
+                 norm_type: str = "identity", causal: bool = False, estimate_loudness: bool = False):
+        super().__init__()
+        if channel_growth > 1:
+            raise ValueError("remfx_b200 TCN supports channel_growth <= 1 (constant channel_width), as in cfg/model/tcn.yaml")
+        if condition or estimate_loudness:
+            raise ValueError("remfx_b200 TCN does not implement the unused `condition` / `estimate_loudness` options")
+        self.ninputs, self.noutputs, self.nblocks = ninputs, noutputs, nblocks
+        self.channel_width, self.kernel_size = channel_width, kernel_size
+        self.stack_size, self.dilation_growth, self.causal = stack_size, dilation_growth, causal
+        self.process_blocks = nn.ModuleList()
+        for n in range(nblocks):
+            in_ch = channel_width if n > 0 else ninputs
+            self.process_blocks.append(_TCNBlockParams(in_ch, channel_width, kernel_size, dilation_growth ** (n % stack_size)))
+        self.output = nn.Conv1d(channel_width, noutputs, kernel_size=1)
+        self.receptive_field = self.compute_receptive_field()
+
+    def compute_receptive_field(self) -> int:
+        """remfx/tcn.py:132-138."""
+        rf = self.kernel_size
+        for n in range(1, self.nblocks):
+            rf += (self.kernel_size - 1) * self.dilation_growth ** (n % self.stack_size)
+        return rf
+
+
+class TCNModel(nn.Module):
+    """B200-native drop-in for `remfx.models.TCNModel` (remfx/models.py:370-390)."""
+
+    def __init__(self, sample_rate, num_bins, **kwargs):
+        super().__init__()
+        self.model = _TCNParams(**kwargs)
+        self.sample_rate = sample_rate
+        self.num_bins = num_bins
+        self._handle: Optional[C.c_void_p] = None
+        self._stamp = None
+        self._ws: Optional[Tensor] = None
+
+    def _sync(self, device) -> C.c_void_p:
+        tensors = dict(self.model.state_dict(keep_vars=True))
+        stamp = (str(device),) + tuple((k, t.data_ptr(), t._version) for k, t in tensors.items())
+        L = _lib.lib()
+        if self._handle is not None and stamp == self._stamp:
+            return self._handle
+        m = self.model
+        if self._handle is None:
+            cfg = _lib.TcnConfig(m.ninputs, m.noutputs, m.nblocks, m.channel_width, m.kernel_size, m.stack_size, m.dilation_growth,
+                                 int(bool(m.causal)))
+            h = C.c_void_p()
+            _lib.check(L.rfx_tcn_create(C.byref(cfg), C.byref(h)), "rfx_tcn_create")
+            self._handle = h
+        stream = _lib.cur_stream()
+        for k, t in tensors.items():
+            if t.device != device:
+                raise _lib.RfxError(f"parameter {k} is on {t.device}, input on {device}: call .to(device) first")
+            tc = t.detach().contiguous()
+            _lib.check(L.rfx_tcn_load_param(self._handle, k.encode(), tc.data_ptr(), tc.numel(), stream), f"load {k}")
+        _lib.check(L.rfx_tcn_finalize(self._handle, stream), "rfx_tcn_finalize")
+        self._stamp = stamp
+        return self._handle
+
+    def __del__(self):
+        h = self.__dict__.get("_handle")
+        if h is not None:
+            self.__dict__["_handle"] = None
+            try:
+                _lib.lib().rfx_tcn_destroy(h)
+            except Exception:
+                pass
+
+    def out_length(self, T: int) -> int:
+        return T - (self.model.receptive_field - 1)
+
+    def sample(self, x: Tensor) -> Tensor:
+        """(B, 1, T) -> (B, 1, T - receptive_field + 1) (remfx/models.py:388-390)."""
+        if x.dim() != 3 or x.shape[1] != 1:
+            raise ValueError(f"expected input of shape (batch, 1, time), got {tuple(x.shape)}")
+        _lib.require_device(x)
+        if x.dtype != torch.float32:
+            raise ValueError("expected float32 audio")
+        x = x.contiguous()
+        B, _, T = x.shape
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            h = self._sync(x.device)
+            Lout = L.rfx_tcn_out_length(h, T)
+            if Lout <= 0:
+                raise ValueError(f"input length {T} is shorter than the receptive field {self.model.receptive_field}")
+            need = L.rfx_tcn_workspace_bytes(h, B, T)
+            if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            out = torch.empty(B, 1, Lout, dtype=torch.float32, device=x.device)
+            rc = L.rfx_tcn_forward(h, x.data_ptr(), B, T, out.data_ptr(), self._ws.data_ptr(), self._ws.numel(), _lib.cur_stream())
+            _lib.check(rc, "rfx_tcn_forward")
+        return out
+
+    def forward(self, batch):
+        """(x, target) -> (loss, output); the target is causal-cropped to the output length (models.py:379-386)."""
+        from .losses import remfx_loss
+        from .ops import causal_crop
+
+        x, target = batch
+        output = self.sample(x)
+        if output.shape[-1] < target.shape[-1]:
+            target = causal_crop(target, output.shape[-1])
+        return remfx_loss(output, target), output
+
+    def launches_per_call(self) -> int:
+        return self.model.nblocks + 1

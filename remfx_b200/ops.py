@@ -133,9 +133,17 @@ def linear(A: torch.Tensor, W: torch.Tensor, s1=None, t1=None, s2=None, t2=None,
     return Cout
 
 
-def lstm_layer(G: torch.Tensor, Whh: torch.Tensor, B: int, F: int) -> torch.Tensor:
+def lstm_layer(G: torch.Tensor, Whh: torch.Tensor, B: int, F: int, impl: str = "mma") -> torch.Tensor:
     """Recurrent half of one bidirectional LSTM layer.  G: (B*F, 8H) input projections (+biases),
-    Whh: (2, 4H, H) -> (B*F, 2H)."""
+    Whh: (2, 4H, H) -> (B*F, 2H).  impl: "mma" (tensor-core bf16x3, default) or "ffma" (fp32)."""
+    _lib.check(_lib.lib().rfx_lstm_set_impl({"mma": 0, "ffma": 1}[impl]), "rfx_lstm_set_impl")
+    try:
+        return _lstm_layer(G, Whh, B, F)
+    finally:
+        _lib.lib().rfx_lstm_set_impl(0)
+
+
+def _lstm_layer(G: torch.Tensor, Whh: torch.Tensor, B: int, F: int) -> torch.Tensor:
     G = _prep(G)
     Whh = _prep(Whh)
     H = Whh.shape[-1]

@@ -43,6 +43,17 @@ def test_umx_state_dict_layout_matches_reference():
     assert m.model.fc1.weight is m.separator.target_models["other"].fc1.weight
 
 
+def test_tcn_state_dict_layout_matches_reference():
+    from remfx_b200.models import TCNModel
+
+    m = TCNModel(sample_rate=48000, num_bins=1025, ninputs=1, noutputs=1, nblocks=20, channel_growth=0, channel_width=256,
+                 kernel_size=7, stack_size=10, dilation_growth=2, condition=False, latent_dim=2, norm_type="identity", causal=False,
+                 estimate_loudness=False)
+    assert set(m.state_dict().keys()) == set(weights.tcn_state(0).keys())
+    assert len(m.state_dict()) == 82
+    assert m.model.receptive_field == 12277 and m.out_length(262144) == 249868
+
+
 def test_no_cpu_fallback():
     from remfx_b200 import _lib
     from remfx_b200.models import OpenUnmixModel
