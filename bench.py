@@ -248,8 +248,10 @@ def run_ours(args):
     lstm_t = statistics.mean(lstm_ms) / 1e3
     achieved = lstm_bytes / lstm_t / 1e9
     roofline = {
-        "kernel": "lstm_rec_kernel (BiLSTM recurrence, 1 launch per layer)", "bound": "hbm", "achieved": achieved,
-        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+        "kernel": "lstm_rec_mma_kernel (BiLSTM recurrence, 1 launch per layer)", "bound": "hbm", "achieved": achieved,
+        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+        "traffic": 155.4e6,  # dram read+write bytes per launch, ncu --set full (profiles/r1/ncu_lstm_rec_mma.txt)
+        "peak_source": peak_src,
         "algorithmic_bytes_per_launch": lstm_bytes, "ms_per_launch": lstm_t * 1e3,
         "note": "513 strictly dependent steps per launch: latency-bound by construction, see DESIGN.md",
         "stage_ms_last_step": {k: round(v, 4) for k, v in stage_acc.items()},
