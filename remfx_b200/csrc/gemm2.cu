@@ -1,10 +1,12 @@
 // gemm2: TMA-fed, warp-specialised, persistent tcgen05 GEMM / implicit-GEMM engine with fp32-grade accuracy.
 //
-//   C[b, m, n] = epilogue( sum_{tap} sum_{k} A[b, m + row_off[tap], k] * W[n, tap * Ktap + k] )
+//   C[b, y, x, n] = epilogue( sum_{tap} sum_{k} A[b, y + dy[tap], x + dx[tap], k] * W[n, tap * Ktap + k] )
 //
-// Plain dense layers use one "tap" (row_off = 0); the TCN dilated Conv1d (remfx/tcn.py:28-36,48-59) uses
-// 7 taps at row offsets j * dilation plus an 8th tap for the 1x1 residual at the centre offset, on
-// channel-last activations -- an im2col-free implicit GEMM: the TMA box simply starts at a shifted row.
+// Plain dense layers use one "tap" on a 1-D row space (Y = 1); the TCN dilated Conv1d (remfx/tcn.py:28-36,
+// 48-59) uses 7 taps at row offsets j * dilation plus an 8th tap for the 1x1 residual at the centre offset;
+// 3x3 Conv2d layers (Cnn14, remfx/classifier.py:240-256) use 9 taps on a 2-D pixel space.  Activations are
+// channel-last, so this is an im2col-free implicit GEMM: each tap is one TMA box of (xt x yt) pixels at a
+// shifted origin, and zero padding comes from the TMA unit's out-of-bounds fill (signed coordinates).
 //
 // Numerics ("bf16x3"): every fp32 value v lives in HBM as TWO bf16 planes (hi = bf16(v), lo = bf16(v - hi)),
 // 4 bytes per element like fp32; per K-step three MMAs (lo*hi, hi*lo, hi*hi) accumulate into one fp32
@@ -54,18 +56,22 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 4-D bf16 map over split planes: dims {cols, rows, batch, 2 planes}; box {64, box_rows, 1, 2}.
-static int make_split_map(CUtensorMap* map, const void* base, long long cols, long long rows, long long batch, long long ld_elems,
-                          long long batch_stride_elems, long long plane_stride_elems, int box_rows) {
+// 5-D bf16 map over split planes: dims {cols, X, Y, batch, 2 planes}; box {64, xt, yt, 1, 2}.
+static int make_split_map(CUtensorMap* map, const void* base, long long cols, long long X, long long Y, long long batch, long long ldx,
+                          long long ldy, long long batch_stride, long long plane_stride, int xt, int yt) {
   EncodeTiledFn fn = encode_fn();
   RFX_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable");
-  RFX_REQUIRE(((uintptr_t)base & 15) == 0 && (ld_elems % 8) == 0 && (batch_stride_elems % 8) == 0 && (plane_stride_elems % 8) == 0,
+  RFX_REQUIRE(((uintptr_t)base & 15) == 0 && (ldx % 8) == 0 && (ldy % 8) == 0 && (batch_stride % 8) == 0 && (plane_stride % 8) == 0,
               "split-bf16 operand must be 16-byte aligned with strides that are multiples of 8 elements");
-  cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch, 2};
-  cuuint64_t strides[3] = {(cuuint64_t)ld_elems * 2, (cuuint64_t)batch_stride_elems * 2, (cuuint64_t)plane_stride_elems * 2};
-  cuuint32_t box[4] = {(cuuint32_t)G2_BK, (cuuint32_t)box_rows, 1, 2};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  RFX_REQUIRE(xt >= 1 && yt >= 1 && xt <= 256 && yt <= 256, "tile extents");
+  cuuint64_t dims[5] = {(cuuint64_t)cols, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)batch, 2};
+  // a stride of 0 is not accepted by the encoder: degenerate dimensions get any valid stride
+  const long long ldy_e = Y > 1 ? ldy : ldx * X, bs_e = batch > 1 ? batch_stride : (ldy_e * (Y > 1 ? Y : 1));
+  cuuint64_t strides[4] = {(cuuint64_t)ldx * 2, (cuuint64_t)(ldy_e > 0 ? ldy_e : 8) * 2, (cuuint64_t)(bs_e > 0 ? bs_e : 8) * 2,
+                           (cuuint64_t)plane_stride * 2};
+  cuuint32_t box[5] = {(cuuint32_t)G2_BK, (cuuint32_t)xt, (cuuint32_t)yt, 1, 2};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
@@ -74,11 +80,11 @@ static int make_split_map(CUtensorMap* map, const void* base, long long cols, lo
   return 0;
 }
 
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
           smem_u32(smem_dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -114,13 +120,16 @@ int launch_split_rows(const float* src, long long ld_src, int rows, int cols, __
 // The kernel
 // ------------------------------------------------------------------------------------------------
 struct G2Params {
-  int M;           // valid output rows per batch item
+  int X, Y;        // valid output extent per batch item (Y = 1 for plain row spaces)
+  int xt, yt;      // pixel tile (xt * yt = 128)
+  int tiles_x;     // m_tiles = tiles_x * tiles_y
   int N;           // valid output columns
   int batch;       // batch items (grid tiles = batch * m_tiles * n_tiles)
   int m_tiles, n_tiles;
   int kb_per_tap;  // 64-wide K blocks per tap
   int taps;
-  int row_off[16];  // A row offset of each tap
+  int dx[16], dy[16];  // A origin offset of each tap
+  long long ldcy_f, ldcy_s;  // output y strides (elements) for the fp32 / split outputs
   // outputs: fp32 (Cf) and/or split planes (Chi/Clo); row stride ld*, batch stride bs* (elements)
   float* Cf;
   long long ldcf, bscf;
@@ -238,7 +247,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int b = tile / tiles_per_batch;
         const int r = tile % tiles_per_batch;
-        const int m0 = (r / p.n_tiles) * G2_BM;
+        const int mt = r / p.n_tiles;
+        const int x0 = (mt % p.tiles_x) * p.xt, y0 = (mt / p.tiles_x) * p.yt;
         const int n0 = (r % p.n_tiles) * BN;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % STAGES;
@@ -247,8 +257,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
           const int tap = kb / p.kb_per_tap;
           const int kc = (kb % p.kb_per_tap) * G2_BK;
           uint8_t* st = smem + s * STAGE_BYTES;
-          tma_load_4d(st, &mapA, kc, m0 + p.row_off[tap], b, 0, &full_bar[s]);
-          tma_load_4d(st + G2_A_STAGE, &mapW, kb * G2_BK, n0, 0, 0, &full_bar[s]);
+          tma_load_5d(st, &mapA, kc, x0 + p.dx[tap], y0 + p.dy[tap], b, 0, &full_bar[s]);
+          tma_load_5d(st + G2_A_STAGE, &mapW, kb * G2_BK, n0, 0, 0, 0, &full_bar[s]);
         }
       }
     }
@@ -296,20 +306,23 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int b = tile / tiles_per_batch;
       const int r = tile % tiles_per_batch;
-      const int m0 = (r / p.n_tiles) * G2_BM;
+      const int mt = r / p.n_tiles;
       const int n0 = (r % p.n_tiles) * BN;
       const int as = DUAL ? 0 : (local & 1);
       const int aphase = DUAL ? (local & 1) : ((local >> 1) & 1);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int m = m0 + q * 32 + lane;
+      const int rt = q * 32 + lane;  // row inside the tile = TMEM lane
+      const int px = (mt % p.tiles_x) * p.xt + rt % p.xt;
+      const int py = (mt / p.tiles_x) * p.yt + rt / p.xt;
       const uint32_t trow = tmem_base + (DUAL ? 0 : as * BN) + ((uint32_t)(q * 32) << 16);
-      const bool row_ok = m < p.M;
-      float* cf = p.Cf ? p.Cf + (size_t)b * p.bscf + (size_t)m * p.ldcf : nullptr;
-      __nv_bfloat16* chi = p.Chi ? p.Chi + (size_t)b * p.bscs + (size_t)m * p.ldcs : nullptr;
-      __nv_bfloat16* clo = p.Clo ? p.Clo + (size_t)b * p.bscs + (size_t)m * p.ldcs : nullptr;
-      const bool cf_vec = cf && ((p.ldcf & 3) == 0) && ((p.bscf & 3) == 0) && (((uintptr_t)p.Cf & 15) == 0);
-      const bool cs_vec = chi && ((p.ldcs & 7) == 0) && ((p.bscs & 7) == 0) && (((uintptr_t)p.Chi & 15) == 0) && (((uintptr_t)p.Clo & 15) == 0);
+      const bool row_ok = px < p.X && py < p.Y;
+      float* cf = p.Cf ? p.Cf + (size_t)b * p.bscf + (size_t)py * p.ldcy_f + (size_t)px * p.ldcf : nullptr;
+      __nv_bfloat16* chi = p.Chi ? p.Chi + (size_t)b * p.bscs + (size_t)py * p.ldcy_s + (size_t)px * p.ldcs : nullptr;
+      __nv_bfloat16* clo = p.Clo ? p.Clo + (size_t)b * p.bscs + (size_t)py * p.ldcy_s + (size_t)px * p.ldcs : nullptr;
+      const bool cf_vec = cf && ((p.ldcf & 3) == 0) && ((p.bscf & 3) == 0) && ((p.ldcy_f & 3) == 0) && (((uintptr_t)p.Cf & 15) == 0);
+      const bool cs_vec = chi && ((p.ldcs & 7) == 0) && ((p.bscs & 7) == 0) && ((p.ldcy_s & 7) == 0) && (((uintptr_t)p.Chi & 15) == 0) &&
+                          (((uintptr_t)p.Clo & 15) == 0);
 #pragma unroll 1
       for (int cc = 0; cc < CH; ++cc) {
         const int c = half * CH + cc;
@@ -410,20 +423,27 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   const int BN = pr.W.BN;
   RFX_REQUIRE(BN == 128 || BN == 256, "weights must be packed with BN 128 or 256");
   G2Params p{};
-  p.M = pr.M; p.N = pr.N; p.batch = pr.batch;
-  p.m_tiles = ceil_div(pr.M, G2_BM);
+  const int Yo = pr.My > 0 ? pr.My : 1;
+  int xt = pr.xt > 0 ? pr.xt : G2_BM;
+  RFX_REQUIRE(xt <= G2_BM && G2_BM % xt == 0, "pixel tile width must divide 128");
+  p.X = pr.M; p.Y = Yo; p.xt = xt; p.yt = G2_BM / xt;
+  p.tiles_x = ceil_div(pr.M, p.xt);
+  p.N = pr.N; p.batch = pr.batch;
+  p.m_tiles = p.tiles_x * ceil_div(Yo, p.yt);
   p.n_tiles = ceil_div(pr.N, BN);
   p.kb_per_tap = ceil_div(pr.Ktap, G2_BK);
   p.taps = pr.taps;
-  for (int i = 0; i < pr.taps; ++i) p.row_off[i] = pr.row_off[i];
-  p.Cf = pr.Cf; p.ldcf = pr.ldcf; p.bscf = pr.bscf;
-  p.Chi = pr.Chi; p.Clo = pr.Clo; p.ldcs = pr.ldcs; p.bscs = pr.bscs;
+  for (int i = 0; i < pr.taps; ++i) { p.dx[i] = pr.row_off[i]; p.dy[i] = pr.row_off_y[i]; }
+  p.Cf = pr.Cf; p.ldcf = pr.ldcf; p.bscf = pr.bscf; p.ldcy_f = pr.ldcf_y;
+  p.Chi = pr.Chi; p.Clo = pr.Clo; p.ldcs = pr.ldcs; p.bscs = pr.bscs; p.ldcy_s = pr.ldcs_y;
   p.s1 = pr.epi.s1; p.t1 = pr.epi.t1; p.s2 = pr.epi.s2; p.t2 = pr.epi.t2; p.slope = pr.epi.slope; p.act = pr.epi.act;
   RFX_REQUIRE(pr.W.Kpad >= p.kb_per_tap * p.taps * G2_BK, "packed weight K extent too small for taps * Ktap");
   CUtensorMap mapA, mapW;
   int rc;
-  if ((rc = make_split_map(&mapA, pr.A.hi, pr.Ktap, pr.A.rows, pr.batch, pr.A.ld, pr.A.batch_stride, pr.A.plane_stride, G2_BM))) return rc;
-  if ((rc = make_split_map(&mapW, pr.W.hi, pr.W.Kpad, pr.W.Npad, 1, pr.W.Kpad, 0, (long long)pr.W.Npad * pr.W.Kpad, BN))) return rc;
+  if ((rc = make_split_map(&mapA, pr.A.hi, pr.Ktap, pr.A.rows, pr.A.rows_y > 0 ? pr.A.rows_y : 1, pr.batch, pr.A.ld, pr.A.ld_y,
+                           pr.A.batch_stride, pr.A.plane_stride, p.xt, p.yt)))
+    return rc;
+  if ((rc = make_split_map(&mapW, pr.W.hi, pr.W.Kpad, pr.W.Npad, 1, 1, pr.W.Kpad, 0, 0, (long long)pr.W.Npad * pr.W.Kpad, BN, 1))) return rc;
   const int total = p.batch * p.m_tiles * p.n_tiles;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -74,9 +74,10 @@ int launch_gemm_simt(const float* A, int lda, int M, const float* W, int ldw, in
 // ---------------------------------------------------------------- gemm2 (gemm2.cu): TMA-fed persistent engine
 // Activations between tensor-core layers live in HBM as two bf16 planes (hi, lo): v ~= hi + lo.
 struct SplitAct {
-  const __nv_bfloat16* hi = nullptr;  // element (b, r, c) at hi[b * batch_stride + r * ld + c]; lo plane at + plane_stride
-  long long rows = 0;                 // rows per batch item (rows beyond it read as zero)
-  long long ld = 0, batch_stride = 0, plane_stride = 0;  // in elements; multiples of 8
+  const __nv_bfloat16* hi = nullptr;  // element (b, y, x, c) at hi[b * batch_stride + y * ld_y + x * ld + c]; lo plane at + plane_stride
+  long long rows = 0;                 // X extent per batch item (positions outside [0, rows) read as zero)
+  long long rows_y = 0;               // Y extent (0 / 1 = plain 1-D row space)
+  long long ld = 0, ld_y = 0, batch_stride = 0, plane_stride = 0;  // in elements; multiples of 8
 };
 struct SplitW {
   const __nv_bfloat16* hi = nullptr;  // [Npad][Kpad] row-major, zero padded; lo plane follows at + Npad * Kpad
@@ -86,15 +87,18 @@ struct SplitW {
 struct G2Problem {
   SplitAct A;
   SplitW W;
-  int M = 0, N = 0, batch = 1;  // output rows per batch item, output columns
+  int M = 0, N = 0, batch = 1;  // output X extent per batch item, output columns
+  int My = 0;                   // output Y extent (0 / 1 = 1-D); pixel tiles are xt x (128 / xt)
+  int xt = 0;                   // pixel tile width (0 = 128)
   int Ktap = 0, taps = 1;       // K extent per tap (A columns); W column index = tap * ceil64(Ktap) + k
-  int row_off[16] = {0};        // A row offset per tap (implicit-GEMM convolution)
+  int row_off[16] = {0};        // A x-offset per tap (implicit-GEMM convolution)
+  int row_off_y[16] = {0};      // A y-offset per tap
   bool dual = false;            // last tap -> second accumulator, added after the activation (TCN residual)
-  float* Cf = nullptr;          // fp32 output (optional)
-  long long ldcf = 0, bscf = 0;
+  float* Cf = nullptr;          // fp32 output (optional): element (b, y, x, n) at b * bscf + y * ldcf_y + x * ldcf + n
+  long long ldcf = 0, ldcf_y = 0, bscf = 0;
   __nv_bfloat16* Chi = nullptr;  // split-bf16 output (optional)
   __nv_bfloat16* Clo = nullptr;
-  long long ldcs = 0, bscs = 0;
+  long long ldcs = 0, ldcs_y = 0, bscs = 0;
   Epilogue epi;
 };
 int g2_choose_bn(int N);
