@@ -140,6 +140,32 @@ int rfx_tcn_forward(rfx_tcn_t* h, const float* x, int B, long long T, float* out
 int rfx_tcn_launches_per_call(const rfx_tcn_t* h);
 
 /* ---------------------------------------------------------------------------------------------
+ * C1-C4  Cnn14 effect classifier (eval mode)
+ *   replaces remfx/classifier.py:193-233 (Cnn14.forward) as called by FXClassifier.forward
+ *   (remfx/models.py:490-491) and the cascade (remfx/models.py:63).
+ * Parameter keys are the reference state_dict names ("conv_block3.bn2.running_var", "melspec.mel_scale.fb",
+ * "heads.4.bias", ...).  x: (B, 1, T) fp32 device.  probs: (B, num_classes) sigmoid outputs (row-major, i.e.
+ * torch.hstack of the reference's list); logits (optional, may be NULL): pre-sigmoid values.
+ * The model and input sample rates must be equal (no resampler on this path).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rfx_cnn14 rfx_cnn14_t;
+
+typedef struct {
+  int num_classes; /* 5 */
+  int n_fft;       /* 2048 */
+  int hop;         /* 512 */
+  int n_mels;      /* 128 */
+} rfx_cnn14_config;
+
+int rfx_cnn14_create(const rfx_cnn14_config* cfg, rfx_cnn14_t** out);
+void rfx_cnn14_destroy(rfx_cnn14_t* h);
+int rfx_cnn14_load_param(rfx_cnn14_t* h, const char* key, const float* src, int64_t numel, void* stream);
+int rfx_cnn14_finalize(rfx_cnn14_t* h, void* stream);
+size_t rfx_cnn14_workspace_bytes(const rfx_cnn14_t* h, int B, int T);
+int rfx_cnn14_forward(rfx_cnn14_t* h, const float* x, int B, int T, float* probs, float* logits, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * L1/L2  RemFx loss = MultiResolutionSTFTLoss(out, target) + l1_weight * mean|out - target|
  *   replaces `self.mrstftloss(out, target) + self.l1loss(out, target) * 100`
  *   (remfx/models.py:299,320,385; auraloss.freq.MultiResolutionSTFTLoss defaults, see oracle/loss.py)

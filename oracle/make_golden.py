@@ -62,6 +62,29 @@ def main():
     _save("tcn_forward.npz", wseed=0, xseed=31, tseed=32, B=1, T=16384, wsum=weights.checksum(sdt),
           out=out.numpy(), loss=float(loss))
 
+    cnn14_golden(R)
+
+
+def cnn14_golden(R, n_chunks: int = 1024, T: int = 262144):
+    """Cnn14 (remfx/classifier.py:193-233, eval): logits + decisions of the reference on 1024 seeded diverse chunks
+    (generated in 64 batches of 16 with seeds 1000..1063) -- the bit-exact per-effect decision gate of BASELINE.json."""
+    sd = weights.cnn14_state(0)
+    m = R.classifier.Cnn14(num_classes=5, n_fft=2048, hop_length=512, n_mels=128, sample_rate=48000, model_sample_rate=48000,
+                           specaugment=True)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    probs = []
+    with torch.no_grad():
+        for i in range(n_chunks // 16):
+            x = weights.synth_diverse(1000 + i, 16, T)
+            probs.append(torch.hstack(m(x)))
+            if i % 8 == 0:
+                print("cnn14 batch", i, flush=True)
+    probs = torch.cat(probs)
+    logits = torch.log(probs.double() / (1 - probs.double())).float()
+    _save("cnn14_decisions.npz", wseed=0, first_xseed=1000, batch=16, n_chunks=n_chunks, T=T, wsum=weights.checksum(sd),
+          probs=probs.numpy(), logits=logits.numpy(), decisions=(probs > 0.5).numpy())
+
 
 if __name__ == "__main__":
     main()

@@ -98,6 +98,89 @@ def tcn_state(seed: int = 0, nblocks: int = 20, width: int = 256, kernel: int = 
     return sd
 
 
+def synth_diverse(seed: int, B: int, T: int) -> torch.Tensor:
+    """Spectrally diverse test signals (B, 1, T): white / red noise, tone stacks, chirps, AM bursts at random
+    gains -- white noise alone looks identical to the classifier after its per-item standardisation."""
+    import math
+
+    g = _gen(seed)
+    t = torch.arange(T, dtype=torch.float32) / 48000.0
+    out = []
+    for i in range(B):
+        kind = int(torch.randint(0, 5, (1,), generator=g))
+        if kind == 0:
+            s = torch.randn(T, generator=g)
+        elif kind == 1:
+            s = torch.cumsum(torch.randn(T, generator=g), 0)
+            s = s - torch.nn.functional.avg_pool1d(s[None, None], 2047, 1, 1023, count_include_pad=False)[0, 0]
+        elif kind == 2:
+            f = 60.0 * (1.0 + 60.0 * torch.rand(6, generator=g))
+            s = sum(torch.sin(2 * math.pi * fi * t + float(torch.rand(1, generator=g)) * 6.28) / (k + 1) for k, fi in enumerate(f))
+        elif kind == 3:
+            f0, f1 = 50.0 + 500.0 * float(torch.rand(1, generator=g)), 2000.0 + 15000.0 * float(torch.rand(1, generator=g))
+            s = torch.sin(2 * math.pi * (f0 * t + 0.5 * (f1 - f0) * t * t / t[-1]))
+        else:
+            env = (torch.sin(2 * math.pi * (1.0 + 8.0 * float(torch.rand(1, generator=g))) * t) > 0.3).float()
+            s = env * torch.randn(T, generator=g)
+        s = s / s.abs().max().clamp_min(1e-6) * (0.02 + 0.3 * float(torch.rand(1, generator=g)))
+        out.append(s + 0.002 * torch.randn(T, generator=g))
+    return torch.stack(out)[:, None, :].contiguous()
+
+
+_CNN14_CACHE: dict = {}
+
+
+def cnn14_state(seed: int = 0, num_classes: int = 5, n_fft: int = 2048, n_mels: int = 128, sample_rate: int = 48000,
+                calibrate: bool = True):
+    """Cached per process (the calibration runs the oracle on 8 full-length chunks); returns a fresh shallow copy."""
+    key = (seed, num_classes, n_fft, n_mels, sample_rate, calibrate)
+    if key not in _CNN14_CACHE:
+        _CNN14_CACHE[key] = _cnn14_state(seed, num_classes, n_fft, n_mels, sample_rate, calibrate)
+    return OrderedDict(_CNN14_CACHE[key])
+
+
+def _cnn14_state(seed, num_classes, n_fft, n_mels, sample_rate, calibrate):
+    """State dict with the key layout of `remfx.classifier.Cnn14` (92 tensors).  Conditioned so that features do
+    not wash out (default init gives 0.495-0.505 for every input): He-scaled convs, randomised
+    BN statistics, head weights/biases scaled so the five logits spread over roughly +-3 and vary per input."""
+    import torchaudio
+
+    g = _gen(seed)
+    sd = OrderedDict()
+    win = torch.hann_window(n_fft)
+    sd["window"] = win
+    sd["melspec.spectrogram.window"] = win.clone()
+    sd["melspec.mel_scale.fb"] = torchaudio.functional.melscale_fbanks(n_fft // 2 + 1, 0.0, float(sample_rate // 2), n_mels, sample_rate,
+                                                                        norm=None, mel_scale="htk")
+    _bn(sd, g, "bn0", n_mels)
+    chans = [1, 64, 128, 256, 512, 1024, 2048]
+    for i in range(6):
+        cin, cout = chans[i], chans[i + 1]
+        p = f"conv_block{i + 1}"
+        sd[p + ".conv1.weight"] = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+        sd[p + ".conv2.weight"] = torch.randn(cout, cout, 3, 3, generator=g) * (2.0 / (cout * 9)) ** 0.5
+        _bn(sd, g, p + ".bn1", cout)
+        _bn(sd, g, p + ".bn2", cout)
+    sd["fc1.weight"] = torch.randn(2048, 2048, generator=g) * (2.0 / 2048) ** 0.5
+    sd["fc1.bias"] = 0.1 * torch.randn(2048, generator=g)
+    for k in range(num_classes):
+        sd[f"heads.{k}.weight"] = torch.randn(1, 2048, generator=g) * (4.0 / 2048 ** 0.5)
+        sd[f"heads.{k}.bias"] = torch.randn(1, generator=g)
+    if calibrate:
+        # centre and scale the heads on a small fixed calibration set so decisions sit near the 0.5 threshold
+        from oracle import cnn14 as _c
+
+        with torch.no_grad():
+            emb = _c.features(synth_diverse(seed + 7919, 8, 262144), sd)
+            for k in range(num_classes):
+                w = sd[f"heads.{k}.weight"]
+                z = (emb @ w.t())[:, 0]
+                scale = 2.0 / float(z.std().clamp_min(1e-6))
+                sd[f"heads.{k}.weight"] = w * scale
+                sd[f"heads.{k}.bias"] = (-(z * scale).median()).reshape(1) + 0.3 * torch.randn(1, generator=g)
+    return sd
+
+
 def checksum(sd) -> float:
     """Order-dependent fp64 checksum of a state dict (guards golden files against RNG drift)."""
     tot = 0.0

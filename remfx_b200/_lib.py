@@ -25,6 +25,10 @@ class TcnConfig(C.Structure):
                 ("stack_size", C.c_int), ("dilation_growth", C.c_int), ("causal", C.c_int)]
 
 
+class Cnn14Config(C.Structure):
+    _fields_ = [("num_classes", C.c_int), ("n_fft", C.c_int), ("hop", C.c_int), ("n_mels", C.c_int)]
+
+
 class UmxConfig(C.Structure):
     _fields_ = [("n_fft", C.c_int), ("hop", C.c_int), ("hidden", C.c_int), ("nb_layers", C.c_int), ("gemm_impl", C.c_int)]
 
@@ -61,6 +65,12 @@ _SIGNATURES = {
     "rfx_tcn_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_longlong]),
     "rfx_tcn_forward": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_longlong, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rfx_tcn_launches_per_call": (C.c_int, [C.c_void_p]),
+    "rfx_cnn14_create": (C.c_int, [C.POINTER(Cnn14Config), C.POINTER(C.c_void_p)]),
+    "rfx_cnn14_destroy": (None, [C.c_void_p]),
+    "rfx_cnn14_load_param": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int64, C.c_void_p]),
+    "rfx_cnn14_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rfx_cnn14_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "rfx_cnn14_forward": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_int, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rfx_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "rfx_remfx_loss": (C.c_int, [_f32p, C.c_longlong, _f32p, C.c_longlong, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_float, _f32p,
                                  C.c_void_p, C.c_size_t, C.c_void_p]),

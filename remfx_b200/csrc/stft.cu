@@ -85,25 +85,23 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) stft_kernel(StftParams p) {
       X.x *= p.scale;
       X.y *= p.scale;
       if (p.Z) p.Z[m * p.ldz + k] = X;
-      if (p.mode == STFT_UMX_MAG) {
-        // ComplexNorm (transforms.py:211) then OpenUnmix input shift/scale (model.py:127-128)
-        const float mag = sqrtf(X.x * X.x + X.y * X.y);
-        const float a = (mag + p.in_mean[k]) * p.in_scale[k];
+      if (p.mode != STFT_COMPLEX) {
+        const float pw = X.x * X.x + X.y * X.y;
+        float a;
+        switch (p.mode) {
+          case STFT_UMX_MAG: a = (sqrtf(pw) + p.in_mean[k]) * p.in_scale[k]; break;  // ComplexNorm (transforms.py:211) + input affine (model.py:127-128)
+          case STFT_MAG: a = sqrtf(pw); break;
+          case STFT_POWER: a = pw; break;
+          case STFT_MAG_CLAMP: a = sqrtf(fmaxf(pw, 1e-8f)); break;
+          default: a = powf(sqrtf(pw) + 1e-8f, p.alpha); break;  // STFT_MAG_POW
+        }
         if (p.A) p.A[m * p.lda + k] = a;
-        if (p.Ahi) {
+        if (p.Ahi) {  // split-bf16 copy for the tensor-core layer that consumes it
           __nv_bfloat16 h, l;
           split_bf16(a, h, l);
           p.Ahi[m * p.ldas + k] = h;
           p.Alo[m * p.ldas + k] = l;
         }
-      } else if (p.mode == STFT_MAG) {
-        p.A[m * p.lda + k] = sqrtf(X.x * X.x + X.y * X.y);
-      } else if (p.mode == STFT_POWER) {
-        p.A[m * p.lda + k] = X.x * X.x + X.y * X.y;
-      } else if (p.mode == STFT_MAG_CLAMP) {
-        p.A[m * p.lda + k] = sqrtf(fmaxf(X.x * X.x + X.y * X.y, 1e-8f));
-      } else if (p.mode == STFT_MAG_POW) {
-        p.A[m * p.lda + k] = powf(sqrtf(X.x * X.x + X.y * X.y) + 1e-8f, p.alpha);
       }
     }
     if (p.A && p.lda > NC + 1) {

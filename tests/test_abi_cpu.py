@@ -54,6 +54,17 @@ def test_tcn_state_dict_layout_matches_reference():
     assert m.model.receptive_field == 12277 and m.out_length(262144) == 249868
 
 
+def test_cnn14_state_dict_layout_matches_reference():
+    from remfx_b200.classifier import Cnn14
+
+    m = Cnn14(num_classes=5, sample_rate=48000, model_sample_rate=48000, n_fft=2048, hop_length=512, n_mels=128, specaugment=True)
+    ref = weights.cnn14_state(0, calibrate=False)
+    assert set(m.state_dict().keys()) == set(ref.keys()) and len(ref) == 92
+    m.load_state_dict(ref, strict=True)
+    with pytest.raises(ValueError):
+        Cnn14(num_classes=5, sample_rate=44100, model_sample_rate=48000)
+
+
 def test_no_cpu_fallback():
     from remfx_b200 import _lib
     from remfx_b200.models import OpenUnmixModel

@@ -89,6 +89,18 @@ def test_tcn_oracle_matches_golden():
     assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
 
 
+def test_cnn14_oracle_matches_golden():
+    from oracle import cnn14 as ocnn
+
+    g = golden("cnn14_decisions.npz")
+    sd = weights.cnn14_state(int(g["wseed"]))
+    assert abs(weights.checksum(sd) - float(g["wsum"])) < 1e-6 * abs(float(g["wsum"]))
+    x = weights.synth_diverse(int(g["first_xseed"]), 4, int(g["T"]))
+    lg = ocnn.logits(x, sd)
+    assert (lg - torch.from_numpy(g["logits"][:4])).abs().max() < 1e-3
+    assert torch.equal(ocnn.decisions(x, sd), torch.from_numpy(g["decisions"][:4]).long())
+
+
 @pytest.mark.skipif(not refshim.available(), reason="/root/reference not present (GPU box)")
 def test_oracle_matches_live_reference():
     R = refshim.ref_modules()
