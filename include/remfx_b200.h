@@ -179,6 +179,13 @@ int rfx_remfx_loss(const float* out, long long out_bstride, const float* target,
                    const float* win1024, const float* win2048, const float* win512, float l1_weight, float* result,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* L3  SI-SDR metric: auraloss.time.SISDRLoss() as constructed at remfx/models.py:41,173 (zero_mean, eps 1e-8, mean
+ * over the batch; returns the NEGATIVE SI-SDR in dB -- the reference negates it again when logging, models.py:230-233).
+ * x = estimate, y = target, (B, T) with batch strides in floats.  result: 1 float (device). */
+size_t rfx_sisdr_workspace_bytes(int B);
+int rfx_sisdr_loss(const float* x, long long x_bstride, const float* y, long long y_bstride, int B, int T, float* result,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

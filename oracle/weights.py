@@ -172,8 +172,12 @@ def _cnn14_state(seed, num_classes, n_fft, n_mels, sample_rate, calibrate):
 
         with torch.no_grad():
             emb = _c.features(synth_diverse(seed + 7919, 8, 262144), sd)
+            ebar = emb.mean(0, keepdim=True)
             for k in range(num_classes):
                 w = sd[f"heads.{k}.weight"]
+                # remove the common-mode component: a logit must not be the small difference of two large numbers,
+                # otherwise ANY fp32 implementation (including the reference's own) decides by rounding noise
+                w = w - (w @ ebar.t()) / (ebar @ ebar.t()) * ebar
                 z = (emb @ w.t())[:, 0]
                 scale = 2.0 / float(z.std().clamp_min(1e-6))
                 sd[f"heads.{k}.weight"] = w * scale

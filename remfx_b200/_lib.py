@@ -74,6 +74,8 @@ _SIGNATURES = {
     "rfx_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "rfx_remfx_loss": (C.c_int, [_f32p, C.c_longlong, _f32p, C.c_longlong, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_float, _f32p,
                                  C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rfx_sisdr_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "rfx_sisdr_loss": (C.c_int, [_f32p, C.c_longlong, _f32p, C.c_longlong, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -252,3 +252,74 @@ int rfx_remfx_loss(const float* out, long long out_bstride, const float* target,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// L3  SI-SDR metric (auraloss.time.SISDRLoss(zero_mean=True, eps=1e-8, reduction="mean"); oracle/loss.py):
+//   x, y zero-meaned per item; alpha = <x,y>/(|y|^2 + eps); loss = -mean_b 10 log10(|alpha y|^2 / (|x - alpha y|^2 + eps) + eps)
+// Five raw sums per item are accumulated in fp64 (fixed order: deterministic), the rest is closed form.
+// ---------------------------------------------------------------------------------------------------------
+namespace rfx {
+constexpr int SISDR_BLOCKS = 64;
+
+__global__ void __launch_bounds__(256) sisdr_partial_kernel(const float* __restrict__ x, const float* __restrict__ y, long long xbs, long long ybs,
+                                                            int T, double* __restrict__ partials /*[B][SISDR_BLOCKS][5]*/) {
+  __shared__ double red[5][8];
+  const int b = blockIdx.y;
+  const float* xr = x + (size_t)b * xbs;
+  const float* yr = y + (size_t)b * ybs;
+  double s[5] = {0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) {
+    const double a = xr[i], c = yr[i];
+    s[0] += a; s[1] += c; s[2] += a * c; s[3] += a * a; s[4] += c * c;
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = s[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    partials[((size_t)b * gridDim.x + blockIdx.x) * 5 + threadIdx.x] = t;
+  }
+}
+
+__global__ void sisdr_final_kernel(const double* __restrict__ partials, int B, int T, float* __restrict__ result) {
+  if (threadIdx.x != 0) return;
+  const double eps = 1e-8;
+  double acc = 0.0;
+  for (int b = 0; b < B; ++b) {
+    double s[5] = {0, 0, 0, 0, 0};
+    for (int k = 0; k < SISDR_BLOCKS; ++k)
+      for (int j = 0; j < 5; ++j) s[j] += partials[((size_t)b * SISDR_BLOCKS + k) * 5 + j];
+    const double n = (double)T, mx = s[0] / n, my = s[1] / n;
+    const double sxy = s[2] - n * mx * my, sxx = s[3] - n * mx * mx, syy = s[4] - n * my * my;
+    const double alpha = sxy / (syy + eps);
+    const double et = alpha * alpha * syy;
+    const double er = sxx - 2.0 * alpha * sxy + alpha * alpha * syy;
+    acc += 10.0 * log10(et / (er + eps) + eps);
+  }
+  result[0] = (float)(-acc / B);
+}
+}  // namespace rfx
+
+extern "C" {
+
+size_t rfx_sisdr_workspace_bytes(int B) { return B > 0 ? (size_t)B * rfx::SISDR_BLOCKS * 5 * sizeof(double) : 0; }
+
+int rfx_sisdr_loss(const float* x, long long x_bstride, const float* y, long long y_bstride, int B, int T, float* result, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  RFX_REQUIRE(x && y && result && workspace, "null argument");
+  RFX_REQUIRE(B > 0 && T > 0, "positive sizes");
+  RFX_REQUIRE(workspace_bytes >= rfx_sisdr_workspace_bytes(B) && ((uintptr_t)workspace & 7) == 0, "workspace too small or misaligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  double* part = reinterpret_cast<double*>(workspace);
+  rfx::sisdr_partial_kernel<<<dim3(rfx::SISDR_BLOCKS, B), 256, 0, s>>>(x, y, x_bstride, y_bstride, T, part);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  rfx::sisdr_final_kernel<<<1, 32, 0, s>>>(part, B, T, result);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -58,3 +58,31 @@ def remfx_loss(out: Tensor, target: Tensor) -> Tensor:
 
 def mrstft_loss(out: Tensor, target: Tensor) -> Tensor:
     return remfx_loss_terms(out, target)[1]
+
+
+def _rows(t: Tensor):
+    T = t.shape[-1]
+    t2 = t.reshape(-1, T)
+    if t2.stride(-1) != 1:
+        t2 = t2.contiguous()
+    return t2, (t2.stride(0) if t2.shape[0] > 1 else T)
+
+
+def sisdr_loss(inp: Tensor, target: Tensor) -> Tensor:
+    """auraloss SISDRLoss() value (negative SI-SDR in dB, batch mean) as a 0-d device tensor (remfx/models.py:41,173)."""
+    _lib.require_device(inp)
+    _lib.require_device(target)
+    if inp.shape != target.shape:
+        raise ValueError(f"shape mismatch {tuple(inp.shape)} vs {tuple(target.shape)}")
+    if inp.dtype != torch.float32 or target.dtype != torch.float32:
+        raise ValueError("expected float32")
+    a, abs_ = _rows(inp)
+    b, bbs = _rows(target)
+    B, T = a.shape
+    L = _lib.lib()
+    with torch.cuda.device(inp.device):
+        ws = torch.empty(L.rfx_sisdr_workspace_bytes(B), dtype=torch.uint8, device=inp.device)
+        res = torch.empty(1, dtype=torch.float32, device=inp.device)
+        rc = L.rfx_sisdr_loss(a.data_ptr(), abs_, b.data_ptr(), bbs, B, T, res.data_ptr(), ws.data_ptr(), ws.numel(), _lib.cur_stream())
+        _lib.check(rc, "rfx_sisdr_loss")
+    return res[0]

@@ -63,3 +63,37 @@ def run_sharded(fn: Callable[[torch.Tensor], torch.Tensor], x: torch.Tensor, gat
             dist.broadcast(buf, src=r, group=group)
         pieces.append(buf)
     return torch.cat(pieces, 0)
+
+
+def _demo_item_op(x: torch.Tensor) -> torch.Tensor:
+    """A per-item stand-in for `model.sample` used by the gloo self-test (items independent, like the real path)."""
+    y = torch.cumsum(x, dim=-1)
+    return (y - y.mean(dim=-1, keepdim=True)) / y.std(dim=-1, keepdim=True).clamp_min(1e-6)
+
+
+def _gloo_selftest_worker(rank: int, world: int, port: int, n_items: int, q) -> None:
+    """Entry point of the world_size>1 CPU test (tests/test_parallel_cpu.py); lives here so spawned workers can import it."""
+    import os
+
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(n_items, 1, 4096, generator=g)
+        calls = []
+
+        def fn(xs):
+            calls.append(xs.shape[0])
+            return _demo_item_op(xs)
+
+        full = run_sharded(fn, x, gather=True)
+        ref = _demo_item_op(x)
+        lo, hi = shard_range(n_items, rank, world)
+        ok = full.shape == ref.shape and torch.allclose(full, ref, rtol=1e-5, atol=1e-6) and sum(calls) == hi - lo
+        local = run_sharded(fn, x, gather=False)
+        ok = ok and (local is None if hi == lo else torch.allclose(local, ref[lo:hi], rtol=1e-5, atol=1e-6))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()

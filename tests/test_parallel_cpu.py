@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from remfx_b200.parallel import run_sharded, shard_range, shard_sizes
+from remfx_b200.parallel import _gloo_selftest_worker, shard_range, shard_sizes
 
 
 def test_shard_range_partitions_exactly():
@@ -30,37 +30,14 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_items, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        from oracle import stft as ostft  # a real per-item op of the path (CPU stand-in for model.sample)
-
-        g = torch.Generator().manual_seed(0)
-        x = torch.randn(n_items, 1, 4096, generator=g)
-        calls = []
-
-        def fn(xs):
-            calls.append(xs.shape[0])
-            return ostft.spectrogram(xs, torch.hann_window(512), 512, 128, 0.3)
-
-        full = run_sharded(fn, x, gather=True)
-        ref = ostft.spectrogram(x, torch.hann_window(512), 512, 128, 0.3)
-        lo, hi = shard_range(n_items, rank, world)
-        ok = full.shape == ref.shape and torch.allclose(full, ref, rtol=1e-5, atol=1e-7) and sum(calls) == hi - lo
-        local = run_sharded(fn, x, gather=False)
-        ok = ok and (local is None if hi == lo else torch.allclose(local, ref[lo:hi], rtol=1e-5, atol=1e-7))
-        q.put((rank, bool(ok)))
-    finally:
-        dist.destroy_process_group()
-
-
 @pytest.mark.parametrize("world,n_items", [(2, 5), (2, 4), (3, 2)])
-def test_run_sharded_gloo(world, n_items):
+def test_run_sharded_gloo(world, n_items, monkeypatch):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.setenv("PYTHONPATH", root + os.pathsep + os.environ.get("PYTHONPATH", ""))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_items, q)) for r in range(world)]
+    procs = [ctx.Process(target=_gloo_selftest_worker, args=(r, world, port, n_items, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
