@@ -166,6 +166,50 @@ int rfx_cnn14_forward(rfx_cnn14_t* h, const float* x, int B, int T, float* probs
                       size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * D1-D10  Hybrid Demucs effect-removal model
+ *   replaces remfx/models.py:308-324 (DemucsModel.forward / sample) = torchaudio.models.HDemucs.forward
+ *   (torchaudio/models/_hdemucs.py:523-634, the un-vendored third-party module the reference imports).
+ * Parameter keys are the HDemucs state_dict names ("freq_encoder.2.dconv.layers.1.3.weight", ...) plus
+ * "__window__" = hann_window(nfft).  x: (B, 1, T) fp32 device -> out: (B, 1, T) fp32 device; T % 1024 == 0.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct rfx_hdemucs rfx_hdemucs_t;
+
+typedef struct {
+  int audio_channels; /* 1 */
+  int n_sources;      /* 1 (sources = ["mixture"]) */
+  int channels;       /* 48 */
+  int growth;         /* 2 */
+  int nfft;           /* 4096 */
+  int depth;          /* 6 */
+  int kernel_size;    /* 8 */
+  int stride;         /* 4 */
+  int time_stride;    /* 2 */
+  int context;        /* 1 */
+  int context_enc;    /* 0 */
+  int norm_starts;    /* 4 */
+  int norm_groups;    /* 4 */
+  int dconv_depth;    /* 2 */
+  int dconv_comp;     /* 4 */
+  int dconv_attn;     /* 4 */
+  int dconv_lstm;     /* 4 */
+  float freq_emb_weight; /* 0.2 (0 disables the frequency embedding) */
+  float freq_emb_scale;  /* 10 */
+} rfx_hdemucs_config;
+
+int rfx_hdemucs_create(const rfx_hdemucs_config* cfg, rfx_hdemucs_t** out);
+void rfx_hdemucs_destroy(rfx_hdemucs_t* h);
+int rfx_hdemucs_load_param(rfx_hdemucs_t* h, const char* key, const float* src, int64_t numel, void* stream);
+int rfx_hdemucs_finalize(rfx_hdemucs_t* h, void* stream);
+size_t rfx_hdemucs_workspace_bytes(rfx_hdemucs_t* h, int B, int T);
+int rfx_hdemucs_forward(rfx_hdemucs_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes,
+                        void* stream);
+int rfx_hdemucs_launches_per_call(rfx_hdemucs_t* h, int B, int T);
+/* Debug taps: when enabled, the next forward records named intermediate activations; rfx_hdemucs_tap copies one
+ * as fp32 in (B, Y, X, C) channel-last order (dst may be NULL to query dims[4] only). */
+int rfx_hdemucs_set_taps(rfx_hdemucs_t* h, int on);
+int rfx_hdemucs_tap(rfx_hdemucs_t* h, const char* name, float* dst, int64_t capacity, int* dims, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * L1/L2  RemFx loss = MultiResolutionSTFTLoss(out, target) + l1_weight * mean|out - target|
  *   replaces `self.mrstftloss(out, target) + self.l1loss(out, target) * 100`
  *   (remfx/models.py:299,320,385; auraloss.freq.MultiResolutionSTFTLoss defaults, see oracle/loss.py)

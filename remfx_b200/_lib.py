@@ -29,6 +29,12 @@ class Cnn14Config(C.Structure):
     _fields_ = [("num_classes", C.c_int), ("n_fft", C.c_int), ("hop", C.c_int), ("n_mels", C.c_int)]
 
 
+class HDemucsConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("audio_channels", "n_sources", "channels", "growth", "nfft", "depth", "kernel_size", "stride",
+                                        "time_stride", "context", "context_enc", "norm_starts", "norm_groups", "dconv_depth", "dconv_comp",
+                                        "dconv_attn", "dconv_lstm")] + [("freq_emb_weight", C.c_float), ("freq_emb_scale", C.c_float)]
+
+
 class UmxConfig(C.Structure):
     _fields_ = [("n_fft", C.c_int), ("hop", C.c_int), ("hidden", C.c_int), ("nb_layers", C.c_int), ("gemm_impl", C.c_int)]
 
@@ -71,6 +77,15 @@ _SIGNATURES = {
     "rfx_cnn14_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rfx_cnn14_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "rfx_cnn14_forward": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_int, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rfx_hdemucs_create": (C.c_int, [C.POINTER(HDemucsConfig), C.POINTER(C.c_void_p)]),
+    "rfx_hdemucs_destroy": (None, [C.c_void_p]),
+    "rfx_hdemucs_load_param": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int64, C.c_void_p]),
+    "rfx_hdemucs_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rfx_hdemucs_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "rfx_hdemucs_forward": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rfx_hdemucs_launches_per_call": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "rfx_hdemucs_set_taps": (C.c_int, [C.c_void_p, C.c_int]),
+    "rfx_hdemucs_tap": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int64, C.POINTER(C.c_int), C.c_void_p]),
     "rfx_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "rfx_remfx_loss": (C.c_int, [_f32p, C.c_longlong, _f32p, C.c_longlong, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_float, _f32p,
                                  C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -39,6 +39,7 @@ int rfx_stft(const float* x, int B, int T, int n_fft, int hop, const float* wind
   p.window = window;
   p.tw = twiddles(n_fft);
   p.n_fft = n_fft; p.hop = hop; p.F = T / hop + 1;
+  p.frame_off = n_fft / 2; p.nbins = n_fft / 2 + 1;
   p.scale = normalized ? 1.0f / sqrtf((float)n_fft) : 1.0f;
   p.alpha = alpha; p.mode = mode;
   p.Z = reinterpret_cast<float2*>(Z_ri); p.ldz = n_fft / 2 + 1;
@@ -56,6 +57,7 @@ int rfx_istft(const float* Z_ri, const float* mask, int B, int F, int n_fft, int
   p.mask = mask; p.ldm = n_fft / 2 + 1;
   p.window = window; p.tw = twiddles(n_fft);
   p.n_fft = n_fft; p.hop = hop; p.F = F; p.length = length;
+  p.frame_off = n_fft / 2; p.env_pad = 0; p.nbins = n_fft / 2 + 1;
   p.scale = normalized ? sqrtf((float)n_fft) : 1.0f;
   p.out = out; p.out_bstride = length;
   p.hops_per_cta = 16;

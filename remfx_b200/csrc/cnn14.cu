@@ -357,6 +357,7 @@ int rfx_cnn14_forward(rfx_cnn14_t* h, const float* x, int B, int T, float* probs
   sp.x_aligned8 = (((uintptr_t)x & 7) == 0 && (T % 2 == 0)) ? 1 : 0;
   sp.window = CP(h, "melspec.spectrogram.window"); sp.tw = twiddles(h->cfg.n_fft);
   sp.n_fft = h->cfg.n_fft; sp.hop = h->cfg.hop; sp.F = L.F;
+  sp.frame_off = h->cfg.n_fft / 2; sp.nbins = bins;
   sp.scale = 1.0f; sp.alpha = 1.0f; sp.mode = STFT_POWER;
   sp.Z = nullptr; sp.A = nullptr; sp.Ahi = P; sp.Alo = P + L.plane_P; sp.ldas = ldp;
   if ((rc = launch_stft(sp, B, s))) return rc;

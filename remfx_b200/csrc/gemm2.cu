@@ -191,7 +191,11 @@ __device__ __forceinline__ void g2_epi8(float (&v)[8], int n, const G2Params& p,
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = v[i] >= 0.0f ? v[i] : v[i] * s[i];
       break;
-    default: break;
+    case ACT_GELU:  // exact erf form (torch F.gelu default)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752440f));
+      break;
+    default: break;  // ACT_GLU_PAIR is resolved by the caller (needs pairs of columns)
   }
 }
 
@@ -354,6 +358,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
                   case ACT_RELU: val = fmaxf(val, 0.0f); break;
                   case ACT_SIGMOID: val = sigmoidf_acc(val); break;
                   case ACT_PRELU: val = val >= 0.0f ? val : val * p.slope[n]; break;
+                  case ACT_GELU: val = 0.5f * val * (1.0f + erff(val * 0.70710678118654752440f)); break;
                   default: break;
                 }
                 o[i] = val;
@@ -362,6 +367,46 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
             if (DUAL) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] += __uint_as_float(v2[8 * j + i]);
+            }
+            if (p.act == ACT_GLU_PAIR) {  // (value, gate) column pairs -> 4 output columns starting at n8 / 2
+              float g4[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) g4[i] = o[2 * i] * sigmoidf_acc(o[2 * i + 1]);
+              const int c4 = n8 >> 1;
+              const int Nout = p.N >> 1;
+              if (cf) {
+                if (c4 + 4 <= Nout && cf_vec) {
+                  *reinterpret_cast<float4*>(cf + c4) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    if (c4 + i < Nout) cf[c4 + i] = g4[i];
+                }
+              }
+              if (chi) {
+                uint32_t ph2[2], pl2[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(g4[2 * i], g4[2 * i + 1]);
+                  const float2 hf = __bfloat1622float2(h2);
+                  const __nv_bfloat162 l2 = __floats2bfloat162_rn(g4[2 * i] - hf.x, g4[2 * i + 1] - hf.y);
+                  ph2[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                  pl2[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                if (c4 + 4 <= Nout && ((p.ldcs & 3) == 0) && ((p.bscs & 3) == 0) && ((p.ldcy_s & 3) == 0) && (((uintptr_t)p.Chi & 7) == 0) &&
+                    (((uintptr_t)p.Clo & 7) == 0)) {
+                  *reinterpret_cast<uint2*>(chi + c4) = make_uint2(ph2[0], ph2[1]);
+                  *reinterpret_cast<uint2*>(clo + c4) = make_uint2(pl2[0], pl2[1]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    if (c4 + i < Nout) {
+                      chi[c4 + i] = reinterpret_cast<const __nv_bfloat16*>(ph2)[i];
+                      clo[c4 + i] = reinterpret_cast<const __nv_bfloat16*>(pl2)[i];
+                    }
+                }
+              }
+              continue;
             }
             if (cf) {
               if (full && cf_vec) {

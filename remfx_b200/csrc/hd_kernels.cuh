@@ -1,0 +1,353 @@
+// Element-wise / reduction / small SIMT kernels of the Hybrid-Demucs path (torchaudio/models/_hdemucs.py).
+// Activations are channel-last (B, Y, X, C): freq-branch tensors use Y = time frame, X = frequency bin group;
+// time-branch tensors use Y = 1, X = time.  "split" = two bf16 planes (hi, lo), see gemm2.cu.
+#pragma once
+#include "kernels.h"
+
+namespace rfx {
+namespace hd {
+
+__device__ __forceinline__ float gelu_exact(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ void store_split8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, const float (&o)[8]) {
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(o[2 * i] - hf.x, o[2 * i + 1] - hf.y);
+    ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  *reinterpret_cast<uint4*>(lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+__device__ __forceinline__ void load_split8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t off, float (&o)[8]) {
+  const uint4 h = *reinterpret_cast<const uint4*>(hi + off);
+  const uint4 l = *reinterpret_cast<const uint4*>(lo + off);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[i]));
+    const float2 lf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[i]));
+    o[2 * i] = hf.x + lf.x;
+    o[2 * i + 1] = hf.y + lf.y;
+  }
+}
+
+// ---- per-item mean / unbiased std of a contiguous fp32 block (HDemucs input normalisation, _hdemucs.py:553-563) ----
+// stats[2b] = mean, stats[2b+1] = std.  One block per item.
+__global__ void __launch_bounds__(1024) item_stats_kernel(const float* __restrict__ x, long long n, float* __restrict__ stats) {
+  __shared__ double r0[32], r1[32];
+  const float* p = x + (size_t)blockIdx.x * n;
+  double s = 0.0, ss = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = p[i];
+    s += v;
+    ss += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0) { r0[threadIdx.x >> 5] = s; r1[threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += r0[w]; b += r1[w]; }
+    const double mean = a / (double)n;
+    const double var = (b - a * mean) / (double)(n - 1);
+    stats[2 * blockIdx.x] = (float)mean;
+    stats[2 * blockIdx.x + 1] = (float)sqrt(var > 0.0 ? var : 0.0);
+  }
+}
+
+// (v - mean_b) / (1e-5 + std_b): fp32 [B][n] -> split planes [B][n] (n % 8 == 0), or fp32 when ohi == nullptr
+__global__ void __launch_bounds__(256) item_normalize_kernel(const float* __restrict__ x, long long n, const float* __restrict__ stats,
+                                                             __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo,
+                                                             float* __restrict__ of) {
+  const int b = blockIdx.y;
+  const long long i8 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
+  if (i8 >= n) return;
+  const float mean = stats[2 * b], inv = 1.0f / (1e-5f + stats[2 * b + 1]);
+  const float4 a = *reinterpret_cast<const float4*>(x + (size_t)b * n + i8);
+  const float4 c = *reinterpret_cast<const float4*>(x + (size_t)b * n + i8 + 4);
+  float o[8] = {(a.x - mean) * inv, (a.y - mean) * inv, (a.z - mean) * inv, (a.w - mean) * inv,
+                (c.x - mean) * inv, (c.y - mean) * inv, (c.z - mean) * inv, (c.w - mean) * inv};
+  if (ohi) {
+    store_split8(ohi, olo, (size_t)b * n + i8, o);
+  } else {
+    *reinterpret_cast<float4*>(of + (size_t)b * n + i8) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(of + (size_t)b * n + i8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// ---- first time-branch conv: Conv1d(1 -> C, k, stride s, pad p) + bias + GELU on the normalised waveform ----
+// xt fp32 [B][T] -> split [B][T/s][C]; one thread per (output step, 8 channels)
+__global__ void __launch_bounds__(256) time_first_kernel(const float* __restrict__ xt, int T, int Lo, int C, int K, int S, int P,
+                                                         const float* __restrict__ w /*[C][K]*/, const float* __restrict__ bias,
+                                                         __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo) {
+  const int groups = C / 8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= (long long)Lo * groups) return;
+  const int c0 = (int)(idx % groups) * 8;
+  const int t = (int)(idx / groups);
+  float xs[16];
+  for (int j = 0; j < K; ++j) {
+    const int i = t * S + j - P;
+    xs[j] = (i >= 0 && i < T) ? xt[(size_t)b * T + i] : 0.0f;
+  }
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float acc = bias[c0 + i];
+    for (int j = 0; j < K; ++j) acc = fmaf(w[(c0 + i) * K + j], xs[j], acc);
+    o[i] = gelu_exact(acc);
+  }
+  store_split8(ohi, olo, ((size_t)b * Lo + t) * C + c0, o);
+}
+
+// ---- GroupNorm statistics over an fp32 tensor (B, Y, X, C): one segment per (b [, x]) and group ----
+// accum[(seg * G + g) * 2 + {0,1}] += (sum, sum of squares) in fp64; grid = (nsplit, nseg).
+__global__ void __launch_bounds__(256) gn_accum_kernel(const float* __restrict__ raw, int Y, int X, int C, int G, int per_x,
+                                                       double* __restrict__ accum) {
+  __shared__ double red[8][8];
+  const int seg = blockIdx.y;
+  const int b = per_x ? seg / X : seg;
+  const int xk = per_x ? seg % X : 0;
+  const int cpg = C / G;
+  const long long npix = per_x ? Y : (long long)Y * X;
+  double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long wid = blockIdx.x * 8ll + warp, nw = gridDim.x * 8ll;
+  for (long long p = wid; p < npix; p += nw) {
+    const size_t pix = per_x ? ((size_t)b * Y + p) * X + xk : (size_t)b * Y * X + p;
+    const float* r = raw + pix * C;
+    for (int c = lane; c < C; c += 32) {
+      const double v = r[c];
+      const int g = c / cpg;
+      s[g] += v;
+      ss[g] += v * v;
+    }
+  }
+  for (int g = 0; g < G; ++g) {
+    for (int o = 16; o > 0; o >>= 1) {
+      s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
+      ss[g] += __shfl_xor_sync(0xffffffffu, ss[g], o);
+    }
+    if (lane == 0) { red[warp][2 * g] = s[g]; red[warp][2 * g + 1] = ss[g]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * G) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(&accum[(size_t)seg * G * 2 + threadIdx.x], t);
+  }
+}
+// stats[(seg * G + g) * 2] = mean, [+1] = 1 / sqrt(biased var + eps)
+__global__ void gn_final_kernel(const double* __restrict__ accum, long long count, int n, float eps, float* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mean = accum[2 * i] / (double)count;
+  double var = accum[2 * i + 1] / (double)count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[2 * i] = (float)mean;
+  stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ---- GroupNorm apply + activation; raw fp32 (B, Y, Xr, Cr) -> split (B, Y, Xo, Co), reading x + x_off (crop) ----
+// mode 0: y = gn(raw)                     (Co >= Cr; padded channels are written as zero)
+// mode 1: y = gelu(gn(raw))
+// mode 2: y = gn(raw)[c] * sigmoid(gn(raw)[c + Co'])  with Co' = Cr / 2 (GLU over channels)
+// then  y = y * scale[c] (if scale) ; y += res (if res: split (B, Y, Xo, Co)).  stats == nullptr -> identity norm.
+struct GnApply {
+  const float* raw; int Y, Xr, Cr;
+  const float* stats; int G, per_x;
+  const float* gamma; const float* beta;
+  int mode;
+  const float* scale;
+  const __nv_bfloat16* rhi; const __nv_bfloat16* rlo;
+  __nv_bfloat16* ohi; __nv_bfloat16* olo; int Xo, Co, x_off;
+};
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApply a) {
+  const int groups = a.Co / 8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= (long long)a.Y * a.Xo * groups) return;
+  const int c0 = (int)(idx % groups) * 8;
+  const int x = (int)((idx / groups) % a.Xo);
+  const int y = (int)(idx / ((long long)groups * a.Xo));
+  const int xr = x + a.x_off;
+  const float* r = a.raw + (((size_t)b * a.Y + y) * a.Xr + xr) * a.Cr;
+  const int seg = a.per_x ? b * a.Xr + xr : b;
+  const int cvalid = a.mode == 2 ? a.Cr / 2 : a.Cr;
+  const int cpg = a.Cr / a.G;
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    float v = 0.0f;
+    if (c < cvalid) {
+      float u = r[c];
+      if (a.stats) {
+        const float* st = a.stats + ((size_t)seg * a.G + c / cpg) * 2;
+        u = (u - st[0]) * st[1] * a.gamma[c] + a.beta[c];
+      }
+      if (a.mode == 1) {
+        v = gelu_exact(u);
+      } else if (a.mode == 2) {
+        const int c2 = c + cvalid;
+        float gte = r[c2];
+        if (a.stats) {
+          const float* st = a.stats + ((size_t)seg * a.G + c2 / cpg) * 2;
+          gte = (gte - st[0]) * st[1] * a.gamma[c2] + a.beta[c2];
+        }
+        v = u * sigmoidf_acc(gte);
+      } else {
+        v = u;
+      }
+      if (a.scale) v *= a.scale[c];
+    }
+    o[i] = v;
+  }
+  const size_t off = (((size_t)b * a.Y + y) * a.Xo + x) * a.Co + c0;
+  if (a.rhi) {
+    float rr[8];
+    load_split8(a.rhi, a.rlo, off, rr);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] += rr[i];
+  }
+  store_split8(a.ohi, a.olo, off, o);
+}
+
+// ---- out = a[(b, y, x + x_off)] + skip[(b, y, x)]  (decoder `x + skip` with the transposed-conv crop folded in) ----
+__global__ void __launch_bounds__(256) add_crop_kernel(const __nv_bfloat16* __restrict__ ahi, const __nv_bfloat16* __restrict__ alo, int Xa, int x_off,
+                                                       const __nv_bfloat16* __restrict__ shi, const __nv_bfloat16* __restrict__ slo,
+                                                       __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo, int Y, int X, int C) {
+  const int groups = C / 8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= (long long)Y * X * groups) return;
+  const int c0 = (int)(idx % groups) * 8;
+  const int x = (int)((idx / groups) % X);
+  const int y = (int)(idx / ((long long)groups * X));
+  float u[8], v[8];
+  load_split8(ahi, alo, (((size_t)b * Y + y) * Xa + x + x_off) * C + c0, u);
+  const size_t off = (((size_t)b * Y + y) * X + x) * C + c0;
+  load_split8(shi, slo, off, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) u[i] += v[i];
+  store_split8(ohi, olo, off, u);
+}
+
+// ---- z[b][y][x][c] += w * emb[x][c]  (frequency embedding after freq layer 0, _hdemucs.py:586-591), in place ----
+__global__ void __launch_bounds__(256) freq_emb_kernel(__nv_bfloat16* __restrict__ zhi, __nv_bfloat16* __restrict__ zlo, int Y, int X, int C,
+                                                       const float* __restrict__ emb /*[X][C]*/, float w) {
+  const int groups = C / 8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= (long long)Y * X * groups) return;
+  const int c0 = (int)(idx % groups) * 8;
+  const int x = (int)((idx / groups) % X);
+  const size_t off = ((size_t)b * Y * X) * C + (size_t)(idx / groups) * C + c0;
+  float u[8];
+  load_split8(zhi, zlo, off, u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) u[i] += w * emb[(size_t)x * C + c0 + i];
+  store_split8(zhi, zlo, off, u);
+}
+
+// ---- a + b on fp32 tensors (time-branch injection into freq layer 4, _hdemucs.py:164-169) ----
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) o[i] = a[i] + b[i];
+}
+
+// ---- last freq decoder: transposed-conv output (fp32 [B][T][Xg][4*2], bias included) -> de-normalised complex Z ----
+// bin k of frame t = position k + pad in the (Xg * 4)-long output; channel 0 = re, 1 = im; Z = v * std + mean.
+__global__ void __launch_bounds__(256) final_freq_kernel(const float* __restrict__ raw, int Tf, int Xg, int pad, int bins,
+                                                         const float* __restrict__ stats, float2* __restrict__ Z) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= (long long)Tf * bins) return;
+  const int k = (int)(idx % bins), t = (int)(idx / bins);
+  const int pos = k + pad;
+  const float* r = raw + (((size_t)b * Tf + t) * Xg + pos / 4) * 8 + (pos % 4) * 2;
+  const float mean = stats[2 * b], sd = stats[2 * b + 1];
+  Z[((size_t)b * Tf + t) * bins + k] = make_float2(r[0] * sd + mean, r[1] * sd + mean);
+}
+
+// ---- last time decoder: ConvTranspose1d(C -> 1, k, stride s) + bias, crop [pad, pad + T), de-normalise, add to out ----
+// y split [B][L][C]; out[b][t] += (convtr(y)[t + pad]) * std_t + mean_t.  One thread per output sample.
+__global__ void __launch_bounds__(256) final_time_kernel(const __nv_bfloat16* __restrict__ yhi, const __nv_bfloat16* __restrict__ ylo, int L, int C,
+                                                         int K, int S, int pad, const float* __restrict__ w /*[C][1][K]*/,
+                                                         const float* __restrict__ bias, const float* __restrict__ stats, int T,
+                                                         float* __restrict__ out) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= T) return;
+  const int pos = (int)t + pad;
+  float acc = bias[0];
+  for (int j = pos % S; j < K; j += S) {
+    const int i = (pos - j) / S;
+    if (i < 0 || i >= L) continue;
+    const size_t off = ((size_t)b * L + i) * C;
+    for (int c = 0; c < C; c += 8) {
+      float u[8];
+      load_split8(yhi, ylo, off + c, u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc = fmaf(w[(c + e) * K + j], u[e], acc);
+    }
+  }
+  out[(size_t)b * T + t] += acc * stats[2 * b + 1] + stats[2 * b];
+}
+
+// ---- weight gather for the implicit-GEMM convolutions (see hdemucs.cu: ConvSpec) ----
+struct GatherSpec {
+  int kind;      // 0 plain (taps = k, or kh*kw), 1 strided (regrouped by s), 2 transposed (regrouped by s)
+  int Co, Ci, k; // logical conv dims; k = kernel extent along the conv axis (kh * kw for 2-D plain)
+  int s, p;      // stride / padding (kinds 1, 2)
+  int tau_min;   // first group offset (kind 1)
+  int taps;      // number of GEMM taps
+  int Kp;        // padded K per tap (multiple of 64)
+  int glu;       // interleave output rows (value c, gate c) -> (2c, 2c+1)
+  int Nout;      // GEMM N
+};
+__global__ void gather_w_kernel(const float* __restrict__ w, const float* __restrict__ bias, GatherSpec g, float* __restrict__ wcat,
+                                float* __restrict__ bcat) {
+  const long long total = (long long)g.Nout * g.taps * g.Kp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % g.Kp);
+    const int tap = (int)((i / g.Kp) % g.taps);
+    const int n = (int)(i / ((long long)g.Kp * g.taps));
+    float v = 0.0f;
+    if (g.kind == 0) {
+      int co = n;
+      if (g.glu) co = (n & 1) ? (g.Co / 2 + n / 2) : n / 2;
+      if (col < g.Ci) v = w[((size_t)co * g.Ci + col) * g.k + tap];
+    } else if (g.kind == 1) {
+      int co = n;
+      const int r = col / g.Ci, ci = col % g.Ci;
+      const int j = g.s * (g.tau_min + tap) + r + g.p;
+      if (col < g.s * g.Ci && j >= 0 && j < g.k) v = w[((size_t)co * g.Ci + ci) * g.k + j];
+    } else {
+      const int r = n / g.Co, co = n % g.Co;  // weight [Ci][Co][k]
+      const int j = r + g.s * tap;
+      if (col < g.Ci && j < g.k) v = w[((size_t)col * g.Co + co) * g.k + j];
+    }
+    wcat[i] = v;
+    if (tap == 0 && col == 0 && bcat) {
+      float bv = 0.0f;
+      if (bias) {
+        if (g.kind == 2) bv = bias[n % g.Co];
+        else if (g.glu) bv = bias[(n & 1) ? (g.Co / 2 + n / 2) : n / 2];
+        else bv = bias[n];
+      }
+      bcat[n] = bv;
+    }
+  }
+}
+
+}  // namespace hd
+}  // namespace rfx

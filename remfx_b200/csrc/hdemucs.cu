@@ -1,0 +1,688 @@
+// Hybrid Demucs (torchaudio.models.HDemucs as RemFx instantiates it: remfx/models.py:308-324,
+// cfg/model/demucs.yaml:11-16) forward pass on the GPU.  torchaudio/models/_hdemucs.py line references: "TA:".
+//
+// Every convolution runs on the gemm2 tcgen05 engine as an implicit GEMM over channel-last split-bf16 activations:
+//   * strided encoder convs (k=8, s=4, TA:124)  -> the input is VIEWED as (X/4, 4C) (free regrouping), which turns the
+//     strided conv into a stride-1 3-tap conv with K = 4C;
+//   * transposed decoder convs (k=8, s=4, TA:243) -> a 2-tap stride-1 conv producing N = 4*Cout, whose output VIEWED as
+//     (4X, Cout) is the upsampled signal (the crop TA:288-294 is folded into the consumer);
+//   * DConv dilated k=3 convs (TA:694), 1x1 convs, the decoder's 3x3 Conv2d "rewrite" (TA:249): plain multi-tap.
+// GroupNorm needs whole-tensor statistics, so norm'd convs write fp32, a reduction kernel accumulates (sum, sum^2) in
+// fp64 and a fused apply kernel does norm + GELU / GLU + LayerScale + residual and re-splits.  Un-normalised layers fuse
+// bias + GELU or GLU into the GEMM epilogue.  Layout: freq branch (B, T, Fr, C), time branch (B, 1, L, C).
+#include "hd_kernels.cuh"
+#include "../../include/remfx_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace rfx {
+namespace hd {
+
+struct Buf {
+  float* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    release();
+    RFX_CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(float)));
+    n = count;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+// channel-last activation (B, Y, X, C): split planes (hi, lo = hi + plane) or fp32
+struct Ten {
+  int B = 0, Y = 1, X = 0, C = 0;
+  __nv_bfloat16* hi = nullptr;
+  size_t plane = 0;
+  float* f = nullptr;
+  __nv_bfloat16* lo() const { return hi + plane; }
+  size_t elems() const { return (size_t)B * Y * X * C; }
+};
+
+// one convolution prepared for gemm2
+struct Conv {
+  GatherSpec g{};
+  SplitW w;
+  Buf wbuf;   // split planes
+  Buf bias;   // [Nout] (re-ordered like the GEMM columns)
+  int Ci = 0, Co = 0;
+  int kh = 1, kw = 1;  // 2-D plain convs (kh along X = freq, kw along Y = time)
+  int crop = 0;        // transposed convs: samples cropped on each side of the output (TA:288-294)
+};
+
+}  // namespace hd
+}  // namespace rfx
+
+using namespace rfx;
+using namespace rfx::hd;
+
+struct rfx_hdemucs {
+  rfx_hdemucs_config cfg;
+  std::map<std::string, Buf> params;
+  std::map<std::string, Conv> convs;
+  bool finalized = false;
+  // debug taps of the last call: name -> tensor descriptor
+  std::map<std::string, Ten> taps;
+  bool want_taps = false;
+  ~rfx_hdemucs() {
+    for (auto& kv : params) kv.second.release();
+    for (auto& kv : convs) { kv.second.wbuf.release(); kv.second.bias.release(); }
+  }
+};
+
+__global__ void hd_unsplit_kernel(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* o, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) o[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+static void hd_unsplit(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* o, long long n, cudaStream_t s) {
+  hd_unsplit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(hi, lo, o, n);
+}
+
+namespace {
+
+const float* HP(const rfx_hdemucs* h, const std::string& k) {
+  auto it = h->params.find(k);
+  return it == h->params.end() ? nullptr : it->second.p;
+}
+
+int prep_conv(rfx_hdemucs* h, const std::string& name, int kind, int Co, int Ci, int k, int s, int p, int glu, int kh, int kw, Buf& tmp,
+              cudaStream_t st) {
+  auto wit = h->params.find(name + ".weight");
+  if (wit == h->params.end()) { set_error("hdemucs: missing parameter '" + name + ".weight'"); return 2; }
+  const size_t expect = (size_t)Co * Ci * k;
+  if (wit->second.n != expect) {
+    set_error("hdemucs: parameter '" + name + ".weight' has " + std::to_string(wit->second.n) + " elements, expected " + std::to_string(expect));
+    return 2;
+  }
+  Conv& c = h->convs[name];
+  c.Ci = Ci; c.Co = Co; c.kh = kh; c.kw = kw;
+  GatherSpec& g = c.g;
+  g.kind = kind; g.Co = Co; g.Ci = Ci; g.k = k; g.s = s; g.p = p; g.glu = glu;
+  if (kind == 0) {
+    g.taps = k; g.Kp = ceil_div(Ci, 64) * 64; g.Nout = Co; g.tau_min = 0;
+  } else if (kind == 1) {
+    const int qlo = -p, qhi = k - 1 - p;
+    auto fl = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
+    g.tau_min = fl(qlo, s);
+    g.taps = fl(qhi, s) - g.tau_min + 1;
+    g.Kp = ceil_div(s * Ci, 64) * 64; g.Nout = Co;
+  } else {
+    g.taps = k / s; g.Kp = ceil_div(Ci, 64) * 64; g.Nout = s * Co; g.tau_min = 0;
+  }
+  const size_t wn = (size_t)g.Nout * g.taps * g.Kp;
+  if (tmp.n < wn) { if (tmp.alloc(wn)) return 1; }
+  if (c.bias.alloc(g.Nout)) return 1;
+  gather_w_kernel<<<148 * 4, 256, 0, st>>>(wit->second.p, HP(h, name + ".bias"), g, tmp.p, c.bias.p);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  const int BN = g2_choose_bn(g.Nout);
+  if (c.wbuf.alloc(split_weight_elems(g.Nout, g.taps * g.Kp, BN))) return 1;
+  int rc = pack_split_weights(tmp.p, (long long)g.taps * g.Kp, g.Nout, g.taps * g.Kp, BN, reinterpret_cast<__nv_bfloat16*>(c.wbuf.p), &c.w, st);
+  if (rc) return rc;
+  RFX_CHECK_CUDA(cudaStreamSynchronize(st));  // tmp is reused by the next conv
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One forward pass (or a dry run that only sizes the workspace)
+// ------------------------------------------------------------------------------------------------
+struct Runner {
+  rfx_hdemucs* h;
+  int B, T;
+  uint8_t* ws;
+  size_t off = 0;
+  bool dry;
+  cudaStream_t s;
+  int rc = 0;
+  int launches = 0;
+
+  void* take(size_t bytes) {
+    const size_t r = off;
+    off += align_up(bytes, 256);
+    return dry ? nullptr : ws + r;
+  }
+  Ten split(int Bn, int Y, int X, int C) {
+    Ten t; t.B = Bn; t.Y = Y; t.X = X; t.C = C;
+    t.plane = align_up(t.elems() * 2, 256) / 2;
+    t.hi = reinterpret_cast<__nv_bfloat16*>(take(t.plane * 2 * 2));
+    return t;
+  }
+  Ten f32(int Bn, int Y, int X, int C) {
+    Ten t; t.B = Bn; t.Y = Y; t.X = X; t.C = C;
+    t.f = reinterpret_cast<float*>(take(t.elems() * 4));
+    return t;
+  }
+  void tap(const std::string& name, const Ten& t) {
+    if (h->want_taps && !dry) h->taps[name] = t;
+  }
+  bool ok() const { return rc == 0; }
+  void chk() {
+    if (!dry && rc == 0) {
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) { set_error(std::string("hdemucs kernel launch: ") + cudaGetErrorString(e)); rc = 1; }
+    }
+    ++launches;
+  }
+
+  // ---- generic implicit-GEMM convolution -------------------------------------------------------
+  // axis: 0 = taps along X, 1 = taps along Y (plain 1-D convs); dil = dilation; pad = zero padding (plain)
+  // out_f32: write fp32 (pre-norm) instead of split; act: epilogue activation (ACT_NONE / GELU / GLU_PAIR)
+  Ten conv(const std::string& name, const Ten& in, int axis, int dil, int pad, bool out_f32, int act) {
+    auto it = h->convs.find(name);
+    if (it == h->convs.end()) { set_error("hdemucs: conv '" + name + "' was not prepared"); rc = 2; return Ten(); }
+    Conv& c = it->second;
+    const GatherSpec& g = c.g;
+    G2Problem pr;
+    int Xv = in.X, Cv = in.C;  // input view
+    int Xo = in.X, Yo = in.Y;  // output pixel grid
+    if (g.kind == 1) {
+      Xv = in.X / g.s; Cv = in.C * g.s;
+      Xo = (in.X + 2 * g.p - g.k) / g.s + 1;
+      for (int t = 0; t < g.taps; ++t) { pr.row_off[t] = g.tau_min + t; pr.row_off_y[t] = 0; }
+    } else if (g.kind == 2) {
+      Xo = in.X + g.taps - 1;
+      for (int t = 0; t < g.taps; ++t) { pr.row_off[t] = -t; pr.row_off_y[t] = 0; }
+    } else if (c.kh * c.kw > 1 && c.kh > 1 && c.kw > 1) {  // 2-D plain (kh along X, kw along Y), pad 1
+      for (int a = 0; a < c.kh; ++a)
+        for (int b2 = 0; b2 < c.kw; ++b2) { pr.row_off[a * c.kw + b2] = a - c.kh / 2; pr.row_off_y[a * c.kw + b2] = b2 - c.kw / 2; }
+    } else {
+      for (int t = 0; t < g.taps; ++t) {
+        const int o = t * dil - pad;
+        pr.row_off[t] = axis == 0 ? o : 0;
+        pr.row_off_y[t] = axis == 0 ? 0 : o;
+      }
+    }
+    const int Nout = g.Nout;
+    const int Cout_store = act == ACT_GLU_PAIR ? Nout / 2 : Nout;
+    Ten out = out_f32 ? f32(in.B, Yo, Xo, Cout_store) : split(in.B, Yo, Xo, Cout_store);
+    if (dry || rc) { ++launches; return out; }
+    pr.A.hi = in.hi; pr.A.rows = Xv; pr.A.rows_y = in.Y; pr.A.ld = Cv; pr.A.ld_y = (long long)Xv * Cv;
+    pr.A.batch_stride = (long long)in.Y * Xv * Cv; pr.A.plane_stride = (long long)in.plane;
+    pr.W = c.w;
+    pr.M = Xo; pr.My = Yo; pr.N = Nout; pr.batch = in.B; pr.Ktap = Cv; pr.taps = g.taps;
+    int xt = 128;
+    while (xt > Xo && xt > 1) xt >>= 1;  // largest power of two <= Xo (pixel tile width), at most 128
+    pr.xt = xt;
+    if (out_f32) { pr.Cf = out.f; pr.ldcf = Cout_store; pr.ldcf_y = (long long)Xo * Cout_store; pr.bscf = (long long)Yo * Xo * Cout_store; }
+    else { pr.Chi = out.hi; pr.Clo = out.lo(); pr.ldcs = Cout_store; pr.ldcs_y = (long long)Xo * Cout_store; pr.bscs = (long long)Yo * Xo * Cout_store; }
+    pr.epi.t1 = c.bias.p;
+    pr.epi.act = act;
+    rc = launch_gemm2(pr, s);
+    ++launches;
+    return out;
+  }
+
+  // ---- GroupNorm statistics of an fp32 tensor -> stats (mean, rstd) per (segment, group) ----
+  float* gn_stats(const Ten& raw, int G, int per_x) {
+    const int nseg = per_x ? raw.B * raw.X : raw.B;
+    double* acc = reinterpret_cast<double*>(take((size_t)nseg * G * 2 * 8));
+    float* st = reinterpret_cast<float*>(take((size_t)nseg * G * 2 * 4));
+    if (dry || rc) { launches += 3; return st; }
+    if (cudaMemsetAsync(acc, 0, (size_t)nseg * G * 2 * 8, s) != cudaSuccess) { set_error("memset failed"); rc = 1; return st; }
+    const long long npix = per_x ? raw.Y : (long long)raw.Y * raw.X;
+    int nsplit = (int)std::max<long long>(1, std::min<long long>((npix + 63) / 64, std::max(1, 1184 / nseg)));
+    gn_accum_kernel<<<dim3(nsplit, nseg), 256, 0, s>>>(raw.f, raw.Y, raw.X, raw.C, G, per_x, acc);
+    chk();
+    const long long count = npix * (raw.C / G);
+    gn_final_kernel<<<ceil_div(nseg * G, 256), 256, 0, s>>>(acc, count, nseg * G, 1e-5f, st);
+    chk();
+    ++launches;
+    return st;
+  }
+
+  // ---- norm (optional) + activation (+ LayerScale, + residual) -> split ----
+  Ten gn_apply(const Ten& raw, const float* stats, int G, int per_x, const float* gamma, const float* beta, int mode, const float* scale,
+               const Ten* res, int Xo, int x_off, int Cpad) {
+    const int Cvalid = mode == 2 ? raw.C / 2 : raw.C;
+    const int Co = Cpad > 0 ? Cpad : ceil_div(Cvalid, 8) * 8;
+    Ten out = split(raw.B, raw.Y, Xo, Co);
+    if (dry || rc) { ++launches; return out; }
+    GnApply a{};
+    a.raw = raw.f; a.Y = raw.Y; a.Xr = raw.X; a.Cr = raw.C;
+    a.stats = stats; a.G = G; a.per_x = per_x; a.gamma = gamma; a.beta = beta; a.mode = mode; a.scale = scale;
+    a.rhi = res ? res->hi : nullptr; a.rlo = res ? res->lo() : nullptr;
+    a.ohi = out.hi; a.olo = out.lo(); a.Xo = Xo; a.Co = Co; a.x_off = x_off;
+    const long long items = (long long)raw.Y * Xo * (Co / 8);
+    gn_apply_kernel<<<dim3((unsigned)((items + 255) / 256), raw.B), 256, 0, s>>>(a);
+    chk();
+    return out;
+  }
+
+  Ten add_crop(const Ten& a, int x_off, const Ten& skip) {
+    Ten out = split(skip.B, skip.Y, skip.X, skip.C);
+    if (dry || rc) { ++launches; return out; }
+    const long long items = (long long)skip.Y * skip.X * (skip.C / 8);
+    add_crop_kernel<<<dim3((unsigned)((items + 255) / 256), skip.B), 256, 0, s>>>(a.hi, a.lo(), a.X, x_off, skip.hi, skip.lo(), out.hi, out.lo(),
+                                                                                  skip.Y, skip.X, skip.C);
+    chk();
+    return out;
+  }
+
+  // ---- DConv residual branch (TA:709-721); y: split (B, Y, X, C); axis = conv axis (1 = Y for the freq branch) ----
+  Ten dconv(const std::string& base, Ten y, int axis, int per_x, bool lstm_attn) {
+    const int depth = h->cfg.dconv_depth;
+    for (int d = 0; d < depth && ok(); ++d) {
+      const std::string L = base + ".layers." + std::to_string(d);
+      const int dil = 1 << d;
+      // conv k=3 (dilated) -> GroupNorm(1, h) -> GELU
+      Ten r1 = conv(L + ".0", y, axis, dil, dil, true, ACT_NONE);
+      float* st1 = gn_stats(r1, 1, per_x);
+      Ten a1 = gn_apply(r1, st1, 1, per_x, HP(h, L + ".1.weight"), HP(h, L + ".1.bias"), 1, nullptr, nullptr, r1.X, 0, 0);
+      tap(L + ".2", a1);
+      int ci = 3;
+      if (lstm_attn) {
+        set_error("hdemucs: BLSTM / LocalState layers are not implemented yet");
+        rc = 3;
+        return y;
+      }
+      // 1x1 conv h -> 2C -> GroupNorm(1, 2C) -> GLU -> LayerScale -> residual
+      Ten r2 = conv(L + "." + std::to_string(ci), a1, 0, 1, 0, true, ACT_NONE);
+      float* st2 = gn_stats(r2, 1, per_x);
+      const std::string gn2 = L + "." + std::to_string(ci + 1), ls = L + "." + std::to_string(ci + 3);
+      y = gn_apply(r2, st2, 1, per_x, HP(h, gn2 + ".weight"), HP(h, gn2 + ".bias"), 2, HP(h, ls + ".scale"), &y, r2.X, 0, 0);
+    }
+    return y;
+  }
+};
+
+int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_t* ws, bool dry, cudaStream_t s, size_t* bytes, int* launches) {
+  Runner R{h, B, T, ws, 0, dry, s};
+  const int nfft = h->cfg.nfft, hl = nfft / 4, bins = nfft / 2, depth = h->cfg.depth, ch0 = h->cfg.channels;
+  const int le = ceil_div(T, hl);
+  const bool lstm_attn_from = true;
+  (void)lstm_attn_from;
+  if (!dry) h->taps.clear();
+
+  // ---------------- D1 / D2: spectrogram, (re, im) as channels, per-item normalisation (TA:465-487, 509-514, 553-563) ----
+  float2* Z = reinterpret_cast<float2*>(R.take((size_t)B * le * bins * 8));
+  float* st_f = reinterpret_cast<float*>(R.take((size_t)B * 2 * 4));
+  float* st_t = reinterpret_cast<float*>(R.take((size_t)B * 2 * 4));
+  Ten xf = R.split(B, le, bins, 2);           // (B, T, Fr, 2)
+  float* xt = reinterpret_cast<float*>(R.take((size_t)B * T * 4));
+  if (!dry) {
+    StftParams sp{};
+    sp.x = x; sp.x_bstride = T; sp.T = T; sp.x_aligned8 = 0;
+    sp.window = HP(h, "__window__"); sp.tw = twiddles(nfft);
+    sp.n_fft = nfft; sp.hop = hl; sp.F = le; sp.frame_off = hl / 2 * 3; sp.nbins = bins;
+    sp.scale = 1.0f / sqrtf((float)nfft); sp.alpha = 1.0f; sp.mode = STFT_COMPLEX;
+    sp.Z = Z; sp.ldz = bins;
+    if ((R.rc = launch_stft(sp, B, s))) return R.rc;
+    item_stats_kernel<<<B, 1024, 0, s>>>(reinterpret_cast<const float*>(Z), (long long)le * bins * 2, st_f);
+    item_stats_kernel<<<B, 1024, 0, s>>>(x, (long long)T, st_t);
+    const long long nf = (long long)le * bins * 2;
+    item_normalize_kernel<<<dim3((unsigned)((nf / 8 + 255) / 256), B), 256, 0, s>>>(reinterpret_cast<const float*>(Z), nf, st_f, xf.hi, xf.lo(), nullptr);
+    item_normalize_kernel<<<dim3((unsigned)((T / 8 + 255) / 256), B), 256, 0, s>>>(x, (long long)T, st_t, nullptr, nullptr, xt);
+    R.chk();
+  }
+  R.launches += 5;
+  R.tap("spec_norm", xf);
+
+  // ---------------- encoders (TA:565-593) ----------------
+  std::vector<Ten> saved, saved_t;
+  Ten xcur = xf;   // freq branch
+  Ten tcur;        // time branch (split) after layer 0
+  Ten inject;      // fp32, time conv output of the merge layer
+  int freqs = bins;
+  for (int idx = 0; idx < depth && R.ok(); ++idx) {
+    const bool lstm_attn = idx >= h->cfg.dconv_lstm;  // lstm and attn start at the same layer in RemFx's config
+    const bool normed = idx >= h->cfg.norm_starts;
+    const bool freq = freqs > 1;
+    const std::string fe = "freq_encoder." + std::to_string(idx), te = "time_encoder." + std::to_string(idx);
+    if (freq) {
+      const bool last_freq = freqs <= h->cfg.kernel_size;
+      // ---- time branch ----
+      if (idx == 0) {
+        const int Lo = T / h->cfg.stride;
+        tcur = R.split(B, 1, Lo, ch0);
+        if (!dry) {
+          const long long items = (long long)Lo * (ch0 / 8);
+          time_first_kernel<<<dim3((unsigned)((items + 255) / 256), B), 256, 0, s>>>(xt, T, Lo, ch0, h->cfg.kernel_size, h->cfg.stride,
+                                                                                     h->cfg.kernel_size / 4, HP(h, te + ".conv.weight"),
+                                                                                     HP(h, te + ".conv.bias"), tcur.hi, tcur.lo());
+          R.chk();
+        } else ++R.launches;
+      } else if (!last_freq) {
+        tcur = R.conv(te + ".conv", tcur, 0, 1, 0, false, ACT_GELU);
+      } else {
+        inject = R.conv(te + ".conv", tcur, 0, 1, 0, true, ACT_NONE);  // "empty" layer: just the conv (TA:159-160)
+      }
+      if (!last_freq) {
+        tcur = R.dconv(te + ".dconv", tcur, 0, 0, lstm_attn);
+        tcur = R.conv(te + ".rewrite", tcur, 0, 1, 0, false, ACT_GLU_PAIR);
+        R.tap(te, tcur);
+        saved_t.push_back(tcur);
+      }
+      // ---- freq branch ----
+      if (!normed) {
+        xcur = R.conv(fe + ".conv", xcur, 0, 1, 0, false, ACT_GELU);
+      } else {
+        Ten raw = R.conv(fe + ".conv", xcur, 0, 1, 0, true, ACT_NONE);  // (B, T, 1, C)
+        if (last_freq) {  // y = y + inject (TA:164-169); both are [B][T][C] in memory
+          Ten sum = R.f32(raw.B, raw.Y, raw.X, raw.C);
+          if (!dry && R.ok()) {
+            add_f32_kernel<<<(unsigned)((raw.elems() + 255) / 256), 256, 0, s>>>(raw.f, inject.f, sum.f, (long long)raw.elems());
+            R.chk();
+          } else ++R.launches;
+          raw = sum;
+        }
+        float* st = R.gn_stats(raw, h->cfg.norm_groups, 0);
+        xcur = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fe + ".norm1.weight"), HP(h, fe + ".norm1.bias"), 1, nullptr, nullptr, raw.X, 0, 0);
+      }
+      R.tap(fe + ".act1", xcur);
+      xcur = R.dconv(fe + ".dconv", xcur, 1, 1, lstm_attn);
+      if (!normed) {
+        xcur = R.conv(fe + ".rewrite", xcur, 0, 1, 0, false, ACT_GLU_PAIR);
+      } else {
+        Ten raw = R.conv(fe + ".rewrite", xcur, 0, 1, 0, true, ACT_NONE);
+        float* st = R.gn_stats(raw, h->cfg.norm_groups, 0);
+        xcur = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fe + ".norm2.weight"), HP(h, fe + ".norm2.bias"), 2, nullptr, nullptr, raw.X, 0, 0);
+      }
+      if (idx == 0 && h->cfg.freq_emb_weight != 0.0f) {  // TA:586-591
+        if (!dry && R.ok()) {
+          const long long items = (long long)xcur.Y * xcur.X * (xcur.C / 8);
+          freq_emb_kernel<<<dim3((unsigned)((items + 255) / 256), B), 256, 0, s>>>(xcur.hi, xcur.lo(), xcur.Y, xcur.X, xcur.C,
+                                                                                   HP(h, "freq_emb.embedding.weight"),
+                                                                                   h->cfg.freq_emb_weight * h->cfg.freq_emb_scale);
+          R.chk();
+        } else ++R.launches;
+      }
+      R.tap(fe, xcur);
+      saved.push_back(xcur);
+      freqs = last_freq ? 1 : freqs / h->cfg.stride;
+    } else {
+      // merged layer (freq == false): Conv1d(k = 2*time_stride, s = time_stride, pad) on (B, 1, T, C) (TA:389-399)
+      Ten xin = xcur;  // (B, T, 1, C) has the same memory order as (B, 1, T, C)
+      xin.X = xcur.Y; xin.Y = 1;
+      Ten raw = R.conv(fe + ".conv", xin, 0, 1, 0, true, ACT_NONE);
+      float* st = R.gn_stats(raw, h->cfg.norm_groups, 0);
+      Ten y = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fe + ".norm1.weight"), HP(h, fe + ".norm1.bias"), 1, nullptr, nullptr, raw.X, 0, 0);
+      y = R.dconv(fe + ".dconv", y, 0, 0, lstm_attn);
+      Ten raw2 = R.conv(fe + ".rewrite", y, 0, 1, 0, true, ACT_NONE);
+      float* st2 = R.gn_stats(raw2, h->cfg.norm_groups, 0);
+      xcur = R.gn_apply(raw2, st2, h->cfg.norm_groups, 0, HP(h, fe + ".norm2.weight"), HP(h, fe + ".norm2.bias"), 2, nullptr, nullptr, raw2.X, 0, 0);
+      R.tap(fe, xcur);
+      saved.push_back(xcur);
+    }
+  }
+
+  // ---------------- decoders (TA:595-615); the decoder input is all-zero, so `x + skip` = skip at the first layer ----
+  Ten xd, xtd;          // current decoder activations (split; transposed-conv outputs are kept UNcropped, see crop_*)
+  int crop_f = 0, crop_t = 0;  // pending crop offset of xd / xtd along X
+  bool have_x = false;
+  const int n_tdec = (int)saved_t.size() + 1;  // time decoders incl. the "empty" one
+  const int offset = depth - n_tdec;
+  for (int idx = 0; idx < depth && R.ok(); ++idx) {
+    const std::string fd = "freq_decoder." + std::to_string(idx);
+    const int enc_idx = depth - 1 - idx;
+    const bool normed = enc_idx >= h->cfg.norm_starts;
+    const bool last = enc_idx == 0;
+    Ten skip = saved.back();
+    saved.pop_back();
+    const bool freq_layer = skip.Y > 1 || (enc_idx < depth - 1);  // only the innermost layer is the merged (time-like) one
+    Ten xin;
+    if (!have_x) { xin = skip; have_x = true; }
+    else {
+      Ten xv = xd;
+      if (freq_layer && xv.Y == 1) { xv.Y = xv.X; xv.X = 1; }  // (B, 1, T, C) -> (B, T, 1, C): same memory (TA:282-284)
+      xin = R.add_crop(xv, crop_f, skip);
+    }
+    // rewrite (k=3 / 3x3, C -> 2C) [+ norm1] + GLU
+    Ten y;
+    const bool conv2d = h->convs[fd + ".rewrite"].kh > 1 && h->convs[fd + ".rewrite"].kw > 1;
+    (void)conv2d;
+    if (!normed) {
+      y = R.conv(fd + ".rewrite", xin, 0, 1, 1, false, ACT_GLU_PAIR);
+    } else {
+      Ten raw = R.conv(fd + ".rewrite", xin, xin.Y > 1 ? 1 : 0, 1, 1, true, ACT_NONE);
+      float* st = R.gn_stats(raw, h->cfg.norm_groups, 0);
+      y = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fd + ".norm1.weight"), HP(h, fd + ".norm1.bias"), 2, nullptr, nullptr, raw.X, 0, 0);
+    }
+    R.tap(fd + ".pre", y);
+    // transposed conv [+ norm2] [+ GELU]
+    const Conv& ctr = h->convs[fd + ".conv_tr"];
+    const int pad = ctr.crop;  // (k - s) / 2, or 0 for the last_freq layer (TA:419-423)
+    if (last) {
+      Ten raw = R.conv(fd + ".conv_tr", y, 0, 1, 0, true, ACT_NONE);  // (B, T, Fr/4 + 1, 4 * 2)
+      R.tap(fd + ".raw", raw);
+      // de-normalise, to complex, iSTFT (TA:516-521, 489-497, 624-633)
+      float2* Zo = reinterpret_cast<float2*>(R.take((size_t)B * le * bins * 8));
+      if (!dry && R.ok()) {
+        const long long items = (long long)le * bins;
+        final_freq_kernel<<<dim3((unsigned)((items + 255) / 256), B), 256, 0, s>>>(raw.f, le, raw.X, pad, bins, st_f, Zo);
+        R.chk();
+        IstftParams ip{};
+        ip.Z = Zo; ip.ldz = bins; ip.mask = nullptr; ip.ldm = 0;
+        ip.window = HP(h, "__window__"); ip.tw = twiddles(nfft);
+        ip.n_fft = nfft; ip.hop = hl; ip.F = le; ip.length = T;
+        ip.frame_off = hl / 2 * 3; ip.env_pad = 2; ip.nbins = bins;
+        ip.scale = sqrtf((float)nfft); ip.out = out; ip.out_bstride = T; ip.hops_per_cta = 8;
+        if ((R.rc = launch_istft(ip, B, s))) return R.rc;
+      }
+      R.launches += 2;
+    } else if (!normed) {
+      xd = R.conv(fd + ".conv_tr", y, 0, 1, 0, false, ACT_GELU);  // bias + GELU fused; crop deferred to the next add
+      xd.X *= ctr.g.s; xd.C /= ctr.g.s;                           // view (Xg, s*Co) as (Xg*s, Co)
+      crop_f = pad;
+    } else {
+      Ten raw = R.conv(fd + ".conv_tr", y, 0, 1, 0, true, ACT_NONE);
+      raw.X *= ctr.g.s; raw.C /= ctr.g.s;
+      float* st = R.gn_stats(raw, h->cfg.norm_groups, 0);
+      const int len = raw.X - 2 * pad;
+      xd = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fd + ".norm2.weight"), HP(h, fd + ".norm2.bias"), 1, nullptr, nullptr, len, pad, 0);
+      crop_f = 0;
+    }
+    if (!last) R.tap(fd, xd);
+
+    // ---- time decoder ----
+    if (idx >= offset) {
+      const int ti = idx - offset;
+      const std::string td = "time_decoder." + std::to_string(ti);
+      const Conv& ttr = h->convs[td + ".conv_tr"];
+      const int tpad = ttr.crop;
+      const bool tnormed = normed;
+      Ten yt;
+      if (ti == 0) {
+        yt = y;  // "empty" decoder: pre[:, :, 0] (TA:603-607); (B, T, 1, C) == (B, 1, T, C) in memory
+        yt.X = y.Y * y.X; yt.Y = 1;
+      } else {
+        Ten tskip = saved_t.back();
+        saved_t.pop_back();
+        Ten tin = R.add_crop(xtd, crop_t, tskip);
+        yt = R.conv(td + ".rewrite", tin, 0, 1, 1, false, ACT_GLU_PAIR);
+      }
+      if (last) {
+        if (!dry && R.ok()) {
+          final_time_kernel<<<dim3((unsigned)((T + 255) / 256), B), 256, 0, s>>>(yt.hi, yt.lo(), yt.X, yt.C, ttr.g.k, ttr.g.s, tpad,
+                                                                                 HP(h, td + ".conv_tr.weight"), HP(h, td + ".conv_tr.bias"),
+                                                                                 st_t, T, out);
+          R.chk();
+        } else ++R.launches;
+      } else if (!tnormed) {
+        xtd = R.conv(td + ".conv_tr", yt, 0, 1, 0, false, ACT_GELU);
+        xtd.X *= ttr.g.s; xtd.C /= ttr.g.s;
+        crop_t = tpad;
+      } else {
+        Ten raw = R.conv(td + ".conv_tr", yt, 0, 1, 0, true, ACT_NONE);
+        raw.X *= ttr.g.s; raw.C /= ttr.g.s;
+        float* st = R.gn_stats(raw, h->cfg.norm_groups, 0);
+        const int len = raw.X - 2 * tpad;
+        xtd = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, td + ".norm2.weight"), HP(h, td + ".norm2.bias"), 1, nullptr, nullptr, len, tpad, 0);
+        crop_t = 0;
+      }
+      if (!last) R.tap(td, xtd);
+    }
+  }
+  if (bytes) *bytes = R.off;
+  if (launches) *launches = R.launches;
+  return R.rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rfx_hdemucs_create(const rfx_hdemucs_config* cfg, rfx_hdemucs_t** out) {
+  RFX_REQUIRE(cfg && out, "null argument");
+  RFX_REQUIRE(cfg->audio_channels == 1 && cfg->n_sources == 1, "HDemucs: only audio_channels = 1, one source (cfg/model/demucs.yaml)");
+  RFX_REQUIRE(cfg->nfft == 4096, "HDemucs: nfft must be 4096");
+  RFX_REQUIRE(cfg->depth == 6 && cfg->kernel_size == 8 && cfg->stride == 4 && cfg->time_stride == 2 && cfg->growth == 2,
+              "HDemucs: depth 6, kernel 8, stride 4, time_stride 2, growth 2 only");
+  RFX_REQUIRE(cfg->channels % 8 == 0 && cfg->channels >= 16, "HDemucs: channels must be a multiple of 8");
+  RFX_REQUIRE(cfg->context == 1 && cfg->context_enc == 0, "HDemucs: context 1 / context_enc 0 only");
+  RFX_REQUIRE(cfg->dconv_depth >= 1 && cfg->dconv_comp == 4, "HDemucs: dconv_comp 4 only");
+  RFX_REQUIRE(cfg->dconv_lstm == cfg->dconv_attn, "HDemucs: dconv_lstm and dconv_attn must start at the same layer");
+  rfx_hdemucs* h = new rfx_hdemucs();
+  h->cfg = *cfg;
+  *out = h;
+  return 0;
+}
+
+void rfx_hdemucs_destroy(rfx_hdemucs_t* h) { delete h; }
+
+int rfx_hdemucs_load_param(rfx_hdemucs_t* h, const char* key, const float* src, int64_t numel, void* stream) {
+  RFX_REQUIRE(h && key && src && numel > 0, "bad argument");
+  Buf& b = h->params[key];
+  if (b.n != (size_t)numel) {
+    if (b.alloc((size_t)numel)) return 1;
+  }
+  RFX_CHECK_CUDA(cudaMemcpyAsync(b.p, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  h->finalized = false;
+  return 0;
+}
+
+int rfx_hdemucs_finalize(rfx_hdemucs_t* h, void* stream) {
+  RFX_REQUIRE(h, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  const rfx_hdemucs_config& c = h->cfg;
+  RFX_REQUIRE(h->params.count("__window__") && h->params["__window__"].n == (size_t)c.nfft, "hdemucs: load the hann window as '__window__'");
+  Buf tmp;
+  int rc = 0;
+  int chin = c.audio_channels, chin_z = 2 * c.audio_channels, chout = c.channels, chout_z = c.channels;
+  int freqs = c.nfft / 2;
+  for (int idx = 0; idx < c.depth && !rc; ++idx) {
+    const bool la = idx >= c.dconv_lstm;
+    const bool freq = freqs > 1;
+    int ker = c.kernel_size, stri = c.stride;
+    bool pad = true, last_freq = false;
+    if (!freq) { ker = c.time_stride * 2; stri = c.time_stride; }
+    if (freq && freqs <= c.kernel_size) { ker = freqs; pad = false; last_freq = true; }
+    if (last_freq) { chout_z = std::max(chout, chout_z); chout = chout_z; }
+    const std::string fe = "freq_encoder." + std::to_string(idx), te = "time_encoder." + std::to_string(idx);
+    const std::string fd = "freq_decoder." + std::to_string(c.depth - 1 - idx), td = "time_decoder." + std::to_string(c.depth - 2 - idx);
+    // encoder convs
+    rc = prep_conv(h, fe + ".conv", 1, chout_z, chin_z, ker, stri, pad ? ker / 4 : 0, 0, 1, 1, tmp, s);
+    if (!rc) rc = prep_conv(h, fe + ".rewrite", 0, 2 * chout_z, chout_z, 1, 1, 0, idx < c.norm_starts ? 1 : 0, 1, 1, tmp, s);
+    auto prep_dconv = [&](const std::string& base, int C) -> int {
+      const int hid = C / c.dconv_comp;
+      for (int d = 0; d < c.dconv_depth; ++d) {
+        const std::string L = base + ".layers." + std::to_string(d);
+        int r = prep_conv(h, L + ".0", 0, hid, C, 3, 1, 0, 0, 1, 1, tmp, s);
+        if (r) return r;
+        const int ci = la ? 5 : 3;
+        r = prep_conv(h, L + "." + std::to_string(ci), 0, 2 * C, hid, 1, 1, 0, 0, 1, 1, tmp, s);
+        if (r) return r;
+      }
+      return 0;
+    };
+    if (!rc) rc = prep_dconv(fe + ".dconv", chout_z);
+    if (freq && !rc) {
+      if (idx > 0) rc = prep_conv(h, te + ".conv", 1, chout, chin, c.kernel_size, c.stride, c.kernel_size / 4, 0, 1, 1, tmp, s);
+      if (!last_freq && !rc) {
+        rc = prep_conv(h, te + ".rewrite", 0, 2 * chout, chout, 1, 1, 0, 1, 1, 1, tmp, s);
+        if (!rc) rc = prep_dconv(te + ".dconv", chout);
+      }
+    }
+    // decoder convs (decoder i mirrors encoder depth-1-i)
+    const int cin_dec = (idx == 0) ? c.audio_channels * c.n_sources : chin;
+    const int cin_dec_z = (idx == 0) ? 2 * c.audio_channels * c.n_sources : chin_z;
+    if (!rc) {
+      const bool two_d = freq;  // Conv2d rewrite on the freq branch: 3x3 (TA:249); the merged layer uses Conv1d k=3
+      rc = prep_conv(h, fd + ".rewrite", 0, 2 * chout_z, chout_z, two_d ? 9 : 3, 1, 1, idx < c.norm_starts ? 1 : 0, two_d ? 3 : 1, two_d ? 3 : 3, tmp, s);
+      if (!rc && two_d) { h->convs[fd + ".rewrite"].kh = 3; h->convs[fd + ".rewrite"].kw = 3; }
+    }
+    if (!rc) rc = prep_conv(h, fd + ".conv_tr", 2, cin_dec_z, chout_z, ker, stri, 0, 0, 1, 1, tmp, s);
+    if (!rc) h->convs[fd + ".conv_tr"].crop = pad ? (ker - stri) / 2 : 0;
+    if (freq && !rc) {
+      if (!last_freq) rc = prep_conv(h, td + ".rewrite", 0, 2 * chout, chout, 3, 1, 1, idx < c.norm_starts ? 1 : 0, 1, 1, tmp, s);
+      if (!rc && idx > 0) rc = prep_conv(h, td + ".conv_tr", 2, cin_dec, chout, c.kernel_size, c.stride, 0, 0, 1, 1, tmp, s);
+      if (!rc) h->convs[td + ".conv_tr"].crop = (c.kernel_size - c.stride) / 2;
+      if (!rc && idx == 0) {  // the last time decoder (C -> 1) is a SIMT kernel; it still needs a descriptor for (k, s)
+        Conv& cc = h->convs[td + ".conv_tr"];
+        cc.g.kind = 2; cc.g.k = c.kernel_size; cc.g.s = c.stride; cc.Ci = chout; cc.Co = cin_dec;
+        cc.crop = (c.kernel_size - c.stride) / 2;
+      }
+    }
+    chin = chout; chin_z = chout_z;
+    chout *= c.growth; chout_z *= c.growth;
+    if (freq) freqs = (freqs <= c.kernel_size) ? 1 : freqs / c.stride;
+  }
+  tmp.release();
+  if (rc) return rc;
+  h->finalized = true;
+  return 0;
+}
+
+size_t rfx_hdemucs_workspace_bytes(rfx_hdemucs_t* h, int B, int T) {
+  if (!h || !h->finalized || B <= 0 || T <= 0) return 0;
+  size_t bytes = 0;
+  int launches = 0;
+  if (run_forward(h, nullptr, B, T, nullptr, nullptr, true, nullptr, &bytes, &launches)) return 0;
+  return bytes;
+}
+
+int rfx_hdemucs_forward(rfx_hdemucs_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  RFX_REQUIRE(h && x && out && workspace, "null argument");
+  RFX_REQUIRE(h->finalized, "rfx_hdemucs_finalize has not been called since the last parameter load");
+  RFX_REQUIRE(B > 0 && T > 0 && T % (h->cfg.nfft / 4) == 0 && T % 1024 == 0, "T must be a positive multiple of 1024");
+  RFX_REQUIRE(T > h->cfg.nfft / 8 * 3, "input shorter than the reflect padding");
+  RFX_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  size_t need = 0;
+  int launches = 0;
+  int rc = run_forward(h, nullptr, B, T, nullptr, nullptr, true, nullptr, &need, &launches);
+  if (rc) return rc;
+  RFX_REQUIRE(workspace_bytes >= need, "workspace too small (rfx_hdemucs_workspace_bytes)");
+  return run_forward(h, x, B, T, out, reinterpret_cast<uint8_t*>(workspace), false, (cudaStream_t)stream, nullptr, nullptr);
+}
+
+int rfx_hdemucs_launches_per_call(rfx_hdemucs_t* h, int B, int T) {
+  if (!h || !h->finalized) return 0;
+  size_t bytes = 0;
+  int launches = 0;
+  run_forward(h, nullptr, B, T, nullptr, nullptr, true, nullptr, &bytes, &launches);
+  return launches;
+}
+
+int rfx_hdemucs_set_taps(rfx_hdemucs_t* h, int on) {
+  RFX_REQUIRE(h, "null handle");
+  h->want_taps = on != 0;
+  return 0;
+}
+
+/* Copy a named intermediate activation of the last forward (taps enabled) as fp32 (B, Y, X, C); dims -> 4 ints. */
+int rfx_hdemucs_tap(rfx_hdemucs_t* h, const char* name, float* dst, int64_t capacity, int* dims, void* stream) {
+  RFX_REQUIRE(h && name && dims, "null argument");
+  auto it = h->taps.find(name);
+  RFX_REQUIRE(it != h->taps.end(), "no such tap (enable taps and run a forward first)");
+  const Ten& t = it->second;
+  dims[0] = t.B; dims[1] = t.Y; dims[2] = t.X; dims[3] = t.C;
+  if (!dst) return 0;
+  RFX_REQUIRE((size_t)capacity >= t.elems(), "destination too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (t.f) {
+    RFX_CHECK_CUDA(cudaMemcpyAsync(dst, t.f, t.elems() * 4, cudaMemcpyDeviceToDevice, s));
+  } else {
+    hd_unsplit(t.hi, t.lo(), dst, (long long)t.elems(), s);
+    RFX_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // extern "C"

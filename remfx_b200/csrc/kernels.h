@@ -22,6 +22,8 @@ struct StftParams {
   const float* window;  // n_fft taps (already zero-padded / centred to n_fft)
   const float2* tw;     // exp(-2 pi i m / n_fft)
   int n_fft, hop, F;
+  int frame_off;        // frame f starts at sample f * hop - frame_off (n_fft/2 for torch.stft(center=True))
+  int nbins;            // bins written per frame (n_fft/2 + 1, or n_fft/2 to drop the Nyquist bin)
   float scale;          // 1, or n_fft^-1/2 for normalized=True
   float alpha;
   int mode;
@@ -44,6 +46,9 @@ struct IstftParams {
   const float* window;
   const float2* tw;
   int n_fft, hop, F, length;
+  int frame_off;      // frame t starts at output sample t * hop - frame_off (n_fft/2 for torch.istft(center=True))
+  int env_pad;        // extra (all-zero) frames on each side that still count in the window envelope (HDemucs: 2)
+  int nbins;          // bins present per frame in Z (n_fft/2 + 1, or n_fft/2 when the Nyquist bin is implicitly zero)
   float scale;  // 1, or n_fft^1/2 for normalized=True
   float* out;   // (B, length)
   long long out_bstride;
@@ -56,7 +61,8 @@ int launch_istft(const IstftParams& p, int B, cudaStream_t stream);
 
 // ---------------------------------------------------------------- GEMM (gemm.cu)
 // C[m, n] = act( ((sum_k A[m,k] W[n,k]) * s1[n] + t1[n]) * s2[n] + t2[n] )   (null vectors = identity)
-enum Act { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2, ACT_SIGMOID = 3, ACT_PRELU = 4 };
+enum Act { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2, ACT_SIGMOID = 3, ACT_PRELU = 4, ACT_GELU = 5,
+           ACT_GLU_PAIR = 6 /* columns (2c, 2c+1) = (value, gate) -> output column c = value * sigmoid(gate); gemm2 only */ };
 
 struct Epilogue {
   const float* s1 = nullptr;

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) stft_kernel(StftParams p) {
   const float* __restrict__ x = p.x + (size_t)b * p.x_bstride;
   const int f_end = min(p.F, (int)(blockIdx.x + 1) * STFT_FPC);
   for (int f = blockIdx.x * STFT_FPC; f < f_end; ++f) {
-    const int base = f * p.hop - NC;  // first sample of the frame (n_fft/2 = NC samples of centre padding)
+    const int base = f * p.hop - p.frame_off;  // first sample of the frame (frame_off = n_fft/2 for centre padding)
     const bool interior = (base >= 0) && (base + NFFT <= p.T);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) stft_kernel(StftParams p) {
     }
     const float2* Zp = fft_block<LOG2NC>(sa, sb, p.tw, j);
     const size_t m = (size_t)b * p.F + f;
-    for (int k = j; k <= NC; k += T4) {
+    for (int k = j; k < p.nbins; k += T4) {
       float2 X = rfft_post(Zp, p.tw, NC, k);
       X.x *= p.scale;
       X.y *= p.scale;
@@ -114,6 +114,7 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) stft_kernel(StftParams p) {
 int launch_stft(const StftParams& p, int B, cudaStream_t stream) {
   RFX_REQUIRE(p.tw != nullptr, "twiddle table");
   RFX_REQUIRE(p.T > p.n_fft / 2, "reflect padding needs T > n_fft/2");
+  RFX_REQUIRE(p.frame_off >= 0 && p.frame_off < p.T && p.nbins >= 1 && p.nbins <= p.n_fft / 2 + 1, "stft frame_off / nbins");
   dim3 grid(ceil_div(p.F, STFT_FPC), B);
   switch (p.n_fft) {
     case 512: stft_kernel<8><<<grid, 64, 0, stream>>>(p); break;
@@ -146,9 +147,10 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) istft_kernel(IstftParams p)
   const int s0 = blockIdx.x * S;  // first output sample of this segment
   for (int i = j; i < S; i += T4) ola[i] = 0.0f;
   // frames whose support [t*hop - NC, t*hop + NC) (output coordinates) intersects [s0, s0 + S)
-  int t_lo = (s0 - NC) / p.hop + 1;
-  if (s0 - NC < 0) t_lo = 0;
-  int t_hi = (s0 + S + NC + p.hop - 1) / p.hop - 1;
+  // frame t covers output samples [t*hop - frame_off, t*hop - frame_off + NFFT)
+  const int lo_num = s0 + p.frame_off - NFFT;  // t*hop > lo_num
+  int t_lo = lo_num < 0 ? 0 : lo_num / p.hop + 1;
+  int t_hi = (s0 + S + p.frame_off + p.hop - 1) / p.hop - 1;
   if (t_hi > p.F - 1) t_hi = p.F - 1;
   const float inv = p.scale / (float)NC;
   for (int t = t_lo; t <= t_hi; ++t) {
@@ -158,9 +160,9 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) istft_kernel(IstftParams p)
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int k = j + r * T4;  // k in [0, NC/2)
-      float2 xk = Zr[k], xn = Zr[NC - k];
+      float2 xk = Zr[k], xn = (NC - k < p.nbins) ? Zr[NC - k] : make_float2(0.f, 0.f);
       if (Mr) {
-        const float mk = Mr[k], mn = Mr[NC - k];
+        const float mk = Mr[k], mn = (NC - k < p.nbins) ? Mr[NC - k] : 0.f;
         xk.x *= mk; xk.y *= mk; xn.x *= mn; xn.y *= mn;
       }
       if (k == 0) {  // irfft ignores the imaginary part of the DC and Nyquist bins
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) istft_kernel(IstftParams p)
       sa[NC / 2] = irfft_pre(xh, xh, p.tw[NC / 2]);
     }
     const float2* res = fft_block<LOG2NC>(sa, sb, p.tw, j);
-    const int off = t * p.hop - NC - s0;  // segment-relative position of frame sample 0
+    const int off = t * p.hop - p.frame_off - s0;  // segment-relative position of frame sample 0
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int n = j + r * T4;
@@ -195,11 +197,13 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) istft_kernel(IstftParams p)
   for (int i = j; i < S; i += T4) {
     const int s = s0 + i;
     if (s >= p.length) break;
-    const int q = s + NC;  // coordinate in the centre-padded signal
+    // window envelope: frames t in [-env_pad, F + env_pad) with 0 <= q - t*hop < NFFT, q = s + frame_off
+    const int q = s + p.frame_off + p.env_pad * p.hop;  // shift so that frame indices start at 0
+    const int Fe = p.F + 2 * p.env_pad;
     int ta = (q - NFFT + p.hop) / p.hop;  // ceil((q - NFFT + 1) / hop) for q - NFFT + 1 >= 0
     if (q - NFFT + 1 <= 0) ta = 0;
     int tb = q / p.hop;
-    if (tb > p.F - 1) tb = p.F - 1;
+    if (tb > Fe - 1) tb = Fe - 1;
     float env = 0.0f;
     for (int t = ta; t <= tb; ++t) {
       const float w = p.window[q - t * p.hop];

@@ -287,6 +287,7 @@ int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void*
   sp.x_aligned8 = (((uintptr_t)x & 7) == 0 && (T % 2 == 0)) ? 1 : 0;
   sp.window = P(h, "window"); sp.tw = tw;
   sp.n_fft = h->cfg.n_fft; sp.hop = h->cfg.hop; sp.F = L.F;
+  sp.frame_off = h->cfg.n_fft / 2; sp.nbins = h->bins;
   sp.scale = 1.0f; sp.alpha = 1.0f; sp.mode = STFT_UMX_MAG;
   sp.Z = Z; sp.ldz = h->bins; sp.A = nullptr; sp.lda = 0;
   sp.Ahi = A1; sp.Alo = A1 + L.plane_A1; sp.ldas = L.lda1;
@@ -322,6 +323,7 @@ int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void*
   ip.Z = Z; ip.ldz = h->bins; ip.mask = mask; ip.ldm = L.ldm;
   ip.window = P(h, "window"); ip.tw = tw;
   ip.n_fft = h->cfg.n_fft; ip.hop = h->cfg.hop; ip.F = L.F; ip.length = T;
+  ip.frame_off = h->cfg.n_fft / 2; ip.env_pad = 0; ip.nbins = h->bins;
   ip.scale = 1.0f; ip.out = out; ip.out_bstride = T; ip.hops_per_cta = 16;
   if ((rc = launch_istft(ip, B, s)) || (rc = mark())) return rc;
   return 0;

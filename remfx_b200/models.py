@@ -315,3 +315,113 @@ class TCNModel(nn.Module):
 
     def launches_per_call(self) -> int:
         return self.model.nblocks + 1
+
+
+# ======================================================================================================
+# Hybrid Demucs
+# ======================================================================================================
+class DemucsModel(nn.Module):
+    """B200-native drop-in for `remfx.models.DemucsModel` (remfx/models.py:308-324).
+
+    `self.model` is a `torchaudio.models.HDemucs` instance used ONLY as the parameter container (it gives the
+    reference's 397 state_dict keys and its initialisation, incl. `_rescale_module`); its forward is never called --
+    the computation is csrc/hdemucs.cu.  kwargs as in cfg/model/demucs.yaml:12-16."""
+
+    def __init__(self, sample_rate, **kwargs) -> None:
+        super().__init__()
+        from torchaudio.models import HDemucs
+
+        self.model = HDemucs(**kwargs)
+        self.num_bins = kwargs["nfft"] // 2 + 1
+        self.sample_rate = sample_rate
+        self._kw = dict(kwargs)
+        self.register_buffer("_hann", torch.hann_window(kwargs["nfft"]), persistent=False)
+        self._handle: Optional[C.c_void_p] = None
+        self._stamp = None
+        self._ws: Optional[Tensor] = None
+
+    def _cfg(self) -> "_lib.HDemucsConfig":
+        kw, m = self._kw, self.model
+        g = lambda k, d: kw.get(k, d)  # noqa: E731
+        return _lib.HDemucsConfig(m.audio_channels, len(m.sources), m.channels, g("growth", 2), m.nfft, m.depth, m.kernel_size, m.stride,
+                                  g("time_stride", 2), m.context, g("context_enc", 0), g("norm_starts", 4), g("norm_groups", 4),
+                                  g("dconv_depth", 2), g("dconv_comp", 4), g("dconv_attn", 4), g("dconv_lstm", 4),
+                                  float(g("freq_emb", 0.2)), float(g("emb_scale", 10)))
+
+    def _sync(self, device) -> C.c_void_p:
+        tensors = {k: v for k, v in self.model.state_dict(keep_vars=True).items() if v.dtype == torch.float32}
+        tensors["__window__"] = self._hann
+        stamp = (str(device),) + tuple((k, t.data_ptr(), t._version) for k, t in tensors.items())
+        L = _lib.lib()
+        if self._handle is not None and stamp == self._stamp:
+            return self._handle
+        if self._handle is None:
+            cfg = self._cfg()
+            h = C.c_void_p()
+            _lib.check(L.rfx_hdemucs_create(C.byref(cfg), C.byref(h)), "rfx_hdemucs_create")
+            self._handle = h
+        stream = _lib.cur_stream()
+        for k, t in tensors.items():
+            if t.device != device:
+                raise _lib.RfxError(f"parameter {k} is on {t.device}, input on {device}: call .to(device) first")
+            tc = t.detach().contiguous()
+            _lib.check(L.rfx_hdemucs_load_param(self._handle, k.encode(), tc.data_ptr(), tc.numel(), stream), f"load {k}")
+        _lib.check(L.rfx_hdemucs_finalize(self._handle, stream), "rfx_hdemucs_finalize")
+        self._stamp = stamp
+        return self._handle
+
+    def __del__(self):
+        h = self.__dict__.get("_handle")
+        if h is not None:
+            self.__dict__["_handle"] = None
+            try:
+                _lib.lib().rfx_hdemucs_destroy(h)
+            except Exception:
+                pass
+
+    def sample(self, x: Tensor, taps: bool = False) -> Tensor:
+        """(B, 1, T) -> (B, 1, T): `self.model(x).squeeze(1)` of the reference (models.py:323-324)."""
+        if x.ndim != 3:
+            raise ValueError(f"Expected 3D tensor with dimensions (batch, channel, frames). Found: {x.shape}")
+        if x.shape[1] != self.model.audio_channels:
+            raise ValueError("The channel dimension of input Tensor must match `audio_channels` of HDemucs model. "
+                             f"Found:{x.shape[1]}.")
+        _lib.require_device(x)
+        if x.dtype != torch.float32:
+            raise ValueError("expected float32 audio")
+        x = x.contiguous()
+        B, _, T = x.shape
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            h = self._sync(x.device)
+            _lib.check(L.rfx_hdemucs_set_taps(h, int(taps)), "rfx_hdemucs_set_taps")
+            need = L.rfx_hdemucs_workspace_bytes(h, B, T)
+            if need == 0:
+                raise ValueError(f"unsupported input size (B={B}, T={T}): T must be a multiple of 1024")
+            if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
+                self._ws = None
+                self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            out = torch.empty_like(x)
+            rc = L.rfx_hdemucs_forward(h, x.data_ptr(), B, T, out.data_ptr(), self._ws.data_ptr(), self._ws.numel(), _lib.cur_stream())
+            _lib.check(rc, "rfx_hdemucs_forward")
+        return out
+
+    def tap(self, name: str) -> Tensor:
+        """Named intermediate activation of the last `sample(..., taps=True)` as fp32 (B, Y, X, C) channel-last."""
+        L = _lib.lib()
+        dims = (C.c_int * 4)()
+        _lib.check(L.rfx_hdemucs_tap(self._handle, name.encode(), None, 0, dims, _lib.cur_stream()), f"tap {name}")
+        shape = tuple(dims)
+        out = torch.empty(shape, dtype=torch.float32, device=self._ws.device)
+        _lib.check(L.rfx_hdemucs_tap(self._handle, name.encode(), out.data_ptr(), out.numel(), dims, _lib.cur_stream()), f"tap {name}")
+        return out
+
+    def forward(self, batch):
+        from .losses import remfx_loss
+
+        x, target = batch
+        output = self.sample(x)
+        return remfx_loss(output, target), output
+
+    def launches_per_call(self, B: int = 1, T: int = 262144) -> int:
+        return _lib.lib().rfx_hdemucs_launches_per_call(self._handle, B, T) if self._handle is not None else 0
