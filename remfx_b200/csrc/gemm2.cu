@@ -463,7 +463,8 @@ int g2_choose_bn(int N) { return (N >= 256 && N % 256 == 0) ? 256 : 128; }
 int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   RFX_REQUIRE(pr.A.hi && pr.W.hi, "null operand");
   RFX_REQUIRE(pr.taps >= 1 && pr.taps <= 16, "1..16 taps");
-  RFX_REQUIRE(pr.Ktap % G2_BK == 0 || pr.taps == 1, "multi-tap problems need Ktap % 64 == 0");
+  // Ktap need not be a multiple of 64: W is packed with every tap padded to ceil64(Ktap) columns, and the TMA unit
+  // zero-fills A columns >= Ktap.
   RFX_REQUIRE(pr.Cf || pr.Chi, "at least one output");
   const int BN = pr.W.BN;
   RFX_REQUIRE(BN == 128 || BN == 256, "weights must be packed with BN 128 or 256");

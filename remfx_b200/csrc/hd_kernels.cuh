@@ -303,6 +303,125 @@ __global__ void __launch_bounds__(256) final_time_kernel(const __nv_bfloat16* __
   out[(size_t)b * T + t] += acc * stats[2 * b + 1] + stats[2 * b];
 }
 
+// ---- _BLSTM framing (TA:758-768): frames of `width` with stride width/2, zero padded; in (B,1,T,C) -> (B*nf,1,width,C) ----
+__global__ void __launch_bounds__(256) blstm_frame_kernel(const __nv_bfloat16* __restrict__ ihi, const __nv_bfloat16* __restrict__ ilo, int T, int C,
+                                                          int nf, int width, int stride, __nv_bfloat16* __restrict__ ohi,
+                                                          __nv_bfloat16* __restrict__ olo) {
+  const int groups = C / 8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int bf = blockIdx.y;  // b * nf + k
+  if (idx >= (long long)width * groups) return;
+  const int c0 = (int)(idx % groups) * 8;
+  const int pos = (int)(idx / groups);
+  const int b = bf / nf, k = bf % nf;
+  const int t = k * stride + pos;
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (t < T) load_split8(ihi, ilo, ((size_t)b * T + t) * C + c0, o);
+  store_split8(ohi, olo, ((size_t)bf * width + pos) * C + c0, o);
+}
+// ---- _BLSTM stitch + skip (TA:772-788): lin fp32 (B*nf, width, C) -> out split (B,1,T,C) = lin[frame(t)][pos(t)] + skip ----
+__global__ void __launch_bounds__(256) blstm_merge_kernel(const float* __restrict__ lin, int T, int C, int nf, int width, int stride,
+                                                          const __nv_bfloat16* __restrict__ shi, const __nv_bfloat16* __restrict__ slo,
+                                                          __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo) {
+  const int groups = C / 8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= (long long)T * groups) return;
+  const int c0 = (int)(idx % groups) * 8;
+  const int t = (int)(idx / groups);
+  int k = 0, pos = t;
+  if (nf > 1) {
+    k = (t - stride / 2) / stride;
+    if (t < stride / 2) k = 0;
+    if (k > nf - 1) k = nf - 1;
+    pos = t - k * stride;
+  }
+  const float* r = lin + (((size_t)b * nf + k) * width + pos) * C + c0;
+  float o[8];
+  load_split8(shi, slo, ((size_t)b * T + t) * C + c0, o);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] += r[i];
+  store_split8(ohi, olo, ((size_t)b * T + t) * C + c0, o);
+}
+
+// ---- _LocalState attention core (TA:832-857) ----
+// qkv fp32 [(b*T + t)][ld]: columns [0,C) queries, [C,2C) keys, [2C,3C) content, [3C, 3C + heads*ndecay) decay logits.
+// For head h (channels h*Ch .. +Ch):  dots[t][s] = k_t . q_s / sqrt(Ch) - sum_f (f+1) |t-s| / sqrt(nd) * sigmoid(dq[f][s]) / 2,
+// diagonal = -100, softmax over t, result[s][c] = sum_t w[t][s] content[t][c].  Output split [(b*T + s)][C].
+// grid = (ceil(T / 32), heads, B), 256 threads; dynamic smem: K[T][Ch+1] + V[T][Ch+1] + W[T][33] + Q[32][Ch+1].
+constexpr int LA_QT = 32;
+__global__ void __launch_bounds__(256) local_attn_kernel(const float* __restrict__ qkv, int ld, int T, int C, int heads, int nd,
+                                                         __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo) {
+  extern __shared__ float la_smem[];
+  const int Ch = C / heads, Chp = Ch + 1;
+  float* Ks = la_smem;                 // [T][Chp]
+  float* Vs = Ks + (size_t)T * Chp;    // [T][Chp]
+  float* Ws = Vs + (size_t)T * Chp;    // [T][LA_QT + 1]
+  float* Qs = Ws + (size_t)T * (LA_QT + 1);  // [LA_QT][Chp]
+  float* Ds = Qs + LA_QT * Chp;        // [LA_QT]: sum_f (f+1) * sigmoid(dq)/2 / sqrt(nd)
+  const int tid = threadIdx.x;
+  const int hd = blockIdx.y, b = blockIdx.z;
+  const int s0 = blockIdx.x * LA_QT;
+  const float* base = qkv + (size_t)b * T * ld;
+  for (int i = tid; i < T * Ch; i += 256) {
+    const int t = i / Ch, c = i % Ch;
+    Ks[t * Chp + c] = base[(size_t)t * ld + C + hd * Ch + c];
+    Vs[t * Chp + c] = base[(size_t)t * ld + 2 * C + hd * Ch + c];
+  }
+  for (int i = tid; i < LA_QT * Ch; i += 256) {
+    const int sl = i / Ch, c = i % Ch;
+    Qs[sl * Chp + c] = (s0 + sl < T) ? base[(size_t)(s0 + sl) * ld + hd * Ch + c] : 0.0f;
+  }
+  if (tid < LA_QT) {
+    float d = 0.0f;
+    if (s0 + tid < T)
+      for (int f = 0; f < nd; ++f) d += (float)(f + 1) * (sigmoidf_acc(base[(size_t)(s0 + tid) * ld + 3 * C + hd * nd + f]) * 0.5f);
+    Ds[tid] = d / sqrtf((float)nd);
+  }
+  __syncthreads();
+  const float inv = 1.0f / sqrtf((float)Ch);
+  for (int i = tid; i < T * LA_QT; i += 256) {
+    const int t = i / LA_QT, sl = i % LA_QT;
+    const int s = s0 + sl;
+    float acc = 0.0f;
+    for (int c = 0; c < Ch; ++c) acc = fmaf(Ks[t * Chp + c], Qs[sl * Chp + c], acc);
+    float v = acc * inv - fabsf((float)(t - s)) * Ds[sl];
+    if (t == s) v = -100.0f;
+    Ws[t * (LA_QT + 1) + sl] = v;
+  }
+  __syncthreads();
+  {  // softmax over t for each query: one warp handles 4 queries
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int sl = warp * 4; sl < warp * 4 + 4; ++sl) {
+      float mx = -INFINITY;
+      for (int t = lane; t < T; t += 32) mx = fmaxf(mx, Ws[t * (LA_QT + 1) + sl]);
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.0f;
+      for (int t = lane; t < T; t += 32) {
+        const float e = expf(Ws[t * (LA_QT + 1) + sl] - mx);
+        Ws[t * (LA_QT + 1) + sl] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      const float r = 1.0f / sum;
+      for (int t = lane; t < T; t += 32) Ws[t * (LA_QT + 1) + sl] *= r;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < LA_QT * Ch; i += 256) {
+    const int sl = i / Ch, c = i % Ch;
+    const int s = s0 + sl;
+    if (s >= T) continue;
+    float acc = 0.0f;
+    for (int t = 0; t < T; ++t) acc = fmaf(Ws[t * (LA_QT + 1) + sl], Vs[t * Chp + c], acc);
+    __nv_bfloat16 hh, ll;
+    split_bf16(acc, hh, ll);
+    const size_t off = ((size_t)b * T + s) * C + hd * Ch + c;
+    ohi[off] = hh;
+    olo[off] = ll;
+  }
+}
+
 // ---- weight gather for the implicit-GEMM convolutions (see hdemucs.cu: ConvSpec) ----
 struct GatherSpec {
   int kind;      // 0 plain (taps = k, or kh*kw), 1 strided (regrouped by s), 2 transposed (regrouped by s)

@@ -69,6 +69,7 @@ struct rfx_hdemucs {
   rfx_hdemucs_config cfg;
   std::map<std::string, Buf> params;
   std::map<std::string, Conv> convs;
+  std::map<std::string, Buf> whh;  // "<blstm>.l<layer>": W_hh of both directions [2][4H][H]
   bool finalized = false;
   // debug taps of the last call: name -> tensor descriptor
   std::map<std::string, Ten> taps;
@@ -76,6 +77,7 @@ struct rfx_hdemucs {
   ~rfx_hdemucs() {
     for (auto& kv : params) kv.second.release();
     for (auto& kv : convs) { kv.second.wbuf.release(); kv.second.bias.release(); }
+    for (auto& kv : whh) kv.second.release();
   }
 };
 
@@ -95,12 +97,14 @@ const float* HP(const rfx_hdemucs* h, const std::string& k) {
 }
 
 int prep_conv(rfx_hdemucs* h, const std::string& name, int kind, int Co, int Ci, int k, int s, int p, int glu, int kh, int kw, Buf& tmp,
-              cudaStream_t st) {
-  auto wit = h->params.find(name + ".weight");
-  if (wit == h->params.end()) { set_error("hdemucs: missing parameter '" + name + ".weight'"); return 2; }
+              cudaStream_t st, const std::string& wkey_in = "", const std::string& bkey_in = "") {
+  const std::string wkey = wkey_in.empty() ? name + ".weight" : wkey_in;
+  const std::string bkey = bkey_in.empty() ? name + ".bias" : bkey_in;
+  auto wit = h->params.find(wkey);
+  if (wit == h->params.end()) { set_error("hdemucs: missing parameter '" + wkey + "'"); return 2; }
   const size_t expect = (size_t)Co * Ci * k;
   if (wit->second.n != expect) {
-    set_error("hdemucs: parameter '" + name + ".weight' has " + std::to_string(wit->second.n) + " elements, expected " + std::to_string(expect));
+    set_error("hdemucs: parameter '" + wkey + "' has " + std::to_string(wit->second.n) + " elements, expected " + std::to_string(expect));
     return 2;
   }
   Conv& c = h->convs[name];
@@ -121,7 +125,7 @@ int prep_conv(rfx_hdemucs* h, const std::string& name, int kind, int Co, int Ci,
   const size_t wn = (size_t)g.Nout * g.taps * g.Kp;
   if (tmp.n < wn) { if (tmp.alloc(wn)) return 1; }
   if (c.bias.alloc(g.Nout)) return 1;
-  gather_w_kernel<<<148 * 4, 256, 0, st>>>(wit->second.p, HP(h, name + ".bias"), g, tmp.p, c.bias.p);
+  gather_w_kernel<<<148 * 4, 256, 0, st>>>(wit->second.p, HP(h, bkey), g, tmp.p, c.bias.p);
   RFX_CHECK_CUDA(cudaGetLastError());
   const int BN = g2_choose_bn(g.Nout);
   if (c.wbuf.alloc(split_weight_elems(g.Nout, g.taps * g.Kp, BN))) return 1;
@@ -175,7 +179,8 @@ struct Runner {
   // ---- generic implicit-GEMM convolution -------------------------------------------------------
   // axis: 0 = taps along X, 1 = taps along Y (plain 1-D convs); dil = dilation; pad = zero padding (plain)
   // out_f32: write fp32 (pre-norm) instead of split; act: epilogue activation (ACT_NONE / GELU / GLU_PAIR)
-  Ten conv(const std::string& name, const Ten& in, int axis, int dil, int pad, bool out_f32, int act) {
+  Ten conv(const std::string& name, const Ten& in, int axis, int dil, int pad, bool out_f32, int act, const Ten* dst = nullptr,
+           int dst_col = 0) {
     auto it = h->convs.find(name);
     if (it == h->convs.end()) { set_error("hdemucs: conv '" + name + "' was not prepared"); rc = 2; return Ten(); }
     Conv& c = it->second;
@@ -202,7 +207,9 @@ struct Runner {
     }
     const int Nout = g.Nout;
     const int Cout_store = act == ACT_GLU_PAIR ? Nout / 2 : Nout;
-    Ten out = out_f32 ? f32(in.B, Yo, Xo, Cout_store) : split(in.B, Yo, Xo, Cout_store);
+    Ten out;
+    if (dst) out = *dst;  // write columns [dst_col, dst_col + N) of an existing fp32 tensor
+    else out = out_f32 ? f32(in.B, Yo, Xo, Cout_store) : split(in.B, Yo, Xo, Cout_store);
     if (dry || rc) { ++launches; return out; }
     pr.A.hi = in.hi; pr.A.rows = Xv; pr.A.rows_y = in.Y; pr.A.ld = Cv; pr.A.ld_y = (long long)Xv * Cv;
     pr.A.batch_stride = (long long)in.Y * Xv * Cv; pr.A.plane_stride = (long long)in.plane;
@@ -211,7 +218,8 @@ struct Runner {
     int xt = 128;
     while (xt > Xo && xt > 1) xt >>= 1;  // largest power of two <= Xo (pixel tile width), at most 128
     pr.xt = xt;
-    if (out_f32) { pr.Cf = out.f; pr.ldcf = Cout_store; pr.ldcf_y = (long long)Xo * Cout_store; pr.bscf = (long long)Yo * Xo * Cout_store; }
+    if (dst) { pr.Cf = out.f + dst_col; pr.ldcf = out.C; pr.ldcf_y = (long long)Xo * out.C; pr.bscf = (long long)Yo * Xo * out.C; }
+    else if (out_f32) { pr.Cf = out.f; pr.ldcf = Cout_store; pr.ldcf_y = (long long)Xo * Cout_store; pr.bscf = (long long)Yo * Xo * Cout_store; }
     else { pr.Chi = out.hi; pr.Clo = out.lo(); pr.ldcs = Cout_store; pr.ldcs_y = (long long)Xo * Cout_store; pr.bscs = (long long)Yo * Xo * Cout_store; }
     pr.epi.t1 = c.bias.p;
     pr.epi.act = act;
@@ -266,6 +274,66 @@ struct Runner {
     return out;
   }
 
+  // ---- _BLSTM (TA:742-788): 2-layer BiLSTM (hidden = C) over overlapping 200-step frames, Linear(2C -> C), stitch, + skip ----
+  Ten blstm(const std::string& base, const Ten& x) {  // x: split (B, 1, T, C)
+    const int C = x.C, Tn = x.X, Bn = x.B;
+    const int width = 200, stride = 100;
+    const bool framed = Tn > width;
+    const int nf = framed ? ceil_div(Tn, stride) : 1;
+    const int Tf = framed ? width : Tn;
+    Ten cur = x;
+    if (framed) {
+      cur = split(Bn * nf, 1, Tf, C);
+      if (!dry && ok()) {
+        const long long items = (long long)Tf * (C / 8);
+        blstm_frame_kernel<<<dim3((unsigned)((items + 255) / 256), Bn * nf), 256, 0, s>>>(x.hi, x.lo(), Tn, C, nf, width, stride, cur.hi, cur.lo());
+        chk();
+      } else ++launches;
+    }
+    const int Bs = Bn * nf;
+    for (int l = 0; l < 2 && ok(); ++l) {
+      Ten G = f32(Bs, 1, Tf, 8 * C);
+      conv(base + ".lstm.ih" + std::to_string(l) + "f", cur, 0, 1, 0, true, ACT_NONE, &G, 0);
+      conv(base + ".lstm.ih" + std::to_string(l) + "r", cur, 0, 1, 0, true, ACT_NONE, &G, 4 * C);
+      Ten hout = split(Bs, 1, Tf, 2 * C);
+      if (!dry && ok()) {
+        rc = launch_lstm_layer(G.f, 8 * C, h->whh[base + ".l" + std::to_string(l)].p, nullptr, 0, hout.hi, hout.lo(), 2 * C, Bs, Tf, C, s);
+      }
+      ++launches;
+      cur = hout;
+    }
+    Ten lin = conv(base + ".linear", cur, 0, 1, 0, true, ACT_NONE);  // fp32 (Bs, 1, Tf, C)
+    Ten out = split(Bn, 1, Tn, C);
+    if (!dry && ok()) {
+      const long long items = (long long)Tn * (C / 8);
+      blstm_merge_kernel<<<dim3((unsigned)((items + 255) / 256), Bn), 256, 0, s>>>(lin.f, Tn, C, nf, Tf, stride, x.hi, x.lo(), out.hi, out.lo());
+      chk();
+    } else ++launches;
+    return out;
+  }
+
+  // ---- _LocalState (TA:822-857): x + proj(attention(x)) ----
+  Ten local_state(const std::string& base, const Ten& x) {  // x: split (B, 1, T, C)
+    const int C = x.C, Tn = x.X, Bn = x.B, heads = 4, nd = 4;
+    const int ld = 3 * C + heads * nd;
+    Ten qkv = f32(Bn, 1, Tn, ld);
+    conv(base + ".query", x, 0, 1, 0, true, ACT_NONE, &qkv, 0);
+    conv(base + ".key", x, 0, 1, 0, true, ACT_NONE, &qkv, C);
+    conv(base + ".content", x, 0, 1, 0, true, ACT_NONE, &qkv, 2 * C);
+    conv(base + ".query_decay", x, 0, 1, 0, true, ACT_NONE, &qkv, 3 * C);
+    Ten res = split(Bn, 1, Tn, C);
+    if (!dry && ok()) {
+      const int Ch = C / heads;
+      const size_t smem = ((size_t)2 * Tn * (Ch + 1) + (size_t)Tn * (LA_QT + 1) + (size_t)LA_QT * (Ch + 1) + LA_QT) * 4;
+      if (smem > 220 * 1024) { set_error("hdemucs: LocalState sequence too long for the shared-memory attention kernel"); rc = 2; return res; }
+      cudaFuncSetAttribute(local_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      local_attn_kernel<<<dim3(ceil_div(Tn, LA_QT), heads, Bn), 256, smem, s>>>(qkv.f, ld, Tn, C, heads, nd, res.hi, res.lo());
+      chk();
+    } else ++launches;
+    Ten pr = conv(base + ".proj", res, 0, 1, 0, true, ACT_NONE);
+    return gn_apply(pr, nullptr, 1, 0, nullptr, nullptr, 0, nullptr, &x, pr.X, 0, 0);
+  }
+
   // ---- DConv residual branch (TA:709-721); y: split (B, Y, X, C); axis = conv axis (1 = Y for the freq branch) ----
   Ten dconv(const std::string& base, Ten y, int axis, int per_x, bool lstm_attn) {
     const int depth = h->cfg.dconv_depth;
@@ -279,9 +347,15 @@ struct Runner {
       tap(L + ".2", a1);
       int ci = 3;
       if (lstm_attn) {
-        set_error("hdemucs: BLSTM / LocalState layers are not implemented yet");
-        rc = 3;
-        return y;
+        // the tensors here are (B, T, 1, C) / (B, 1, T, C): the same memory; work on the time-like view
+        Ten z = a1;
+        if (z.Y > 1) { z.X = z.Y * z.X; z.Y = 1; }
+        z = blstm(L + ".3", z);
+        z = local_state(L + ".4", z);
+        tap(L + ".4", z);
+        a1 = z;
+        if (y.Y > 1) { a1.Y = y.Y; a1.X = y.X; }
+        ci = 5;
       }
       // 1x1 conv h -> 2C -> GroupNorm(1, 2C) -> GLU -> LayerScale -> residual
       Ten r2 = conv(L + "." + std::to_string(ci), a1, 0, 1, 0, true, ACT_NONE);
@@ -589,6 +663,35 @@ int rfx_hdemucs_finalize(rfx_hdemucs_t* h, void* stream) {
         const int ci = la ? 5 : 3;
         r = prep_conv(h, L + "." + std::to_string(ci), 0, 2 * C, hid, 1, 1, 0, 0, 1, 1, tmp, s);
         if (r) return r;
+        if (la) {
+          const std::string lb = L + ".3";
+          for (int l = 0; l < 2; ++l) {
+            const int in = l == 0 ? hid : 2 * hid;
+            Buf& whh = h->whh[lb + ".l" + std::to_string(l)];
+            if (whh.alloc((size_t)2 * 4 * hid * hid)) return 1;
+            for (int d2 = 0; d2 < 2; ++d2) {
+              const std::string sfx = "_l" + std::to_string(l) + (d2 ? "_reverse" : "");
+              const float* bi = HP(h, lb + ".lstm.bias_ih" + sfx);
+              const float* bh = HP(h, lb + ".lstm.bias_hh" + sfx);
+              const float* wh = HP(h, lb + ".lstm.weight_hh" + sfx);
+              if (!bi || !bh || !wh) { set_error("hdemucs: missing LSTM parameters under '" + lb + ".lstm'"); return 2; }
+              Buf& bsum = h->params[lb + ".lstm.bias_sum" + sfx];
+              if (bsum.alloc(4 * hid)) return 1;
+              if ((r = launch_add_vec(bi, bh, bsum.p, 4 * hid, s))) return r;
+              RFX_CHECK_CUDA(cudaMemcpyAsync(whh.p + (size_t)d2 * 4 * hid * hid, wh, (size_t)4 * hid * hid * 4, cudaMemcpyDeviceToDevice, s));
+              r = prep_conv(h, lb + ".lstm.ih" + std::to_string(l) + (d2 ? "r" : "f"), 0, 4 * hid, in, 1, 1, 0, 0, 1, 1, tmp, s,
+                            lb + ".lstm.weight_ih" + sfx, lb + ".lstm.bias_sum" + sfx);
+              if (r) return r;
+            }
+          }
+          if ((r = prep_conv(h, lb + ".linear", 0, hid, 2 * hid, 1, 1, 0, 0, 1, 1, tmp, s))) return r;
+          const std::string ab = L + ".4";
+          if ((r = prep_conv(h, ab + ".query", 0, hid, hid, 1, 1, 0, 0, 1, 1, tmp, s))) return r;
+          if ((r = prep_conv(h, ab + ".key", 0, hid, hid, 1, 1, 0, 0, 1, 1, tmp, s))) return r;
+          if ((r = prep_conv(h, ab + ".content", 0, hid, hid, 1, 1, 0, 0, 1, 1, tmp, s))) return r;
+          if ((r = prep_conv(h, ab + ".query_decay", 0, 16, hid, 1, 1, 0, 0, 1, 1, tmp, s))) return r;
+          if ((r = prep_conv(h, ab + ".proj", 0, hid, hid, 1, 1, 0, 0, 1, 1, tmp, s))) return r;
+        }
       }
       return 0;
     };

@@ -223,16 +223,28 @@ __device__ __forceinline__ uint32_t pack2(float x, float y) {
 }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
-constexpr int LSTM_SLOTS = 8;                                      // batch slots per cluster (MMA N)
-constexpr int LSTM_BLK_BYTES = 2 * LSTM_SLOTS * LSTM_UPC * 2;      // one CTA's h block: 2 planes x 8 slots x 32 units bf16
-constexpr int LSTM_MMA_TX = LSTM_CL * LSTM_BLK_BYTES;              // bytes every CTA receives per step (8 KB)
+constexpr int LSTM_SLOTS = 8;  // batch slots per cluster (MMA N)
 
-__global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 32, 1)
+// H = hidden units per direction (multiple of 32 with H/8 a multiple of 8: 192, 256, 384).  Each of the 8 CTAs owns
+// UPC = H/8 units (UPC/4 warps).  The W_hh hi fragments always live in registers (H/16 k-steps x 4 regs); when they
+// would not both fit (H = 384) the lo fragments are kept in shared memory instead (LO_SMEM) and re-read every step.
+template <int H, bool LO_SMEM>
+__global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(H / 8 / 4 * 32, 1)
     lstm_rec_mma_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Whh, float* __restrict__ Hout, int ldh,
                         __nv_bfloat16* __restrict__ Hhi, __nv_bfloat16* __restrict__ Hlo, int ldhs, int B, int F, int NB) {
-  __shared__ __align__(128) __nv_bfloat16 h_buf[2][LSTM_CL][2][LSTM_SLOTS][LSTM_UPC];  // [buffer][source CTA][plane][slot][unit]
-  __shared__ __align__(128) __nv_bfloat16 stage[2][2][LSTM_SLOTS][LSTM_UPC];           // this CTA's new h (hi, lo)
-  __shared__ __align__(8) uint64_t h_bar[2];
+  constexpr int UPC = H / LSTM_CL;          // units per CTA
+  constexpr int WARPS = UPC / 4;
+  constexpr int THREADS = WARPS * 32;
+  constexpr int KS = H / 16;                // MMA k-steps
+  constexpr int NP = H / 32;                // k-step pairs (one LDS.128 of h per plane each)
+  constexpr int BLK_BYTES = 2 * LSTM_SLOTS * UPC * 2;  // one CTA's h block: 2 planes x 8 slots x UPC units bf16
+  constexpr int TX = LSTM_CL * BLK_BYTES;
+  static_assert(UPC % 8 == 0 && H % 32 == 0, "unsupported hidden size");
+  extern __shared__ __align__(128) uint8_t lstm_smem[];
+  __nv_bfloat16* h_buf = reinterpret_cast<__nv_bfloat16*>(lstm_smem);                         // [2][CL][2][SLOTS][UPC]
+  __nv_bfloat16* stage = h_buf + 2 * LSTM_CL * 2 * LSTM_SLOTS * UPC;                           // [2][2][SLOTS][UPC]
+  uint64_t* h_bar = reinterpret_cast<uint64_t*>(stage + 2 * 2 * LSTM_SLOTS * UPC);             // [2]
+  uint4* alo_smem = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(h_bar) + 128);         // [KS][THREADS] (LO_SMEM only)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -241,31 +253,40 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 3
   const int b0 = blockIdx.y * NB;
   const int gid = lane >> 2, tig = lane & 3;
   const int u = gid >> 1, pp = gid & 1;  // unit within the warp; pp = 0: rows (i, g), pp = 1: rows (f, o)
-  const int unit = rank * LSTM_UPC + warp * 4 + u;
+  const int unit = rank * UPC + warp * 4 + u;
   const int gate0 = pp ? 1 : 0, gate1 = pp ? 3 : 2;
 
-  // ---- A fragments: W_hh rows (gate0, unit) and (gate1, unit), true k = 32 P + 8 tig + [0, 8) for P = 0..7 ----
-  uint32_t a_hi[16][4], a_lo[16][4];
+  // ---- A fragments: W_hh rows (gate0, unit) and (gate1, unit), true k = 32 P + 8 tig + [0, 8) for P = 0..NP-1 ----
+  uint32_t a_hi[KS][4];
+  uint32_t a_lo[LO_SMEM ? 1 : KS][4];
   {
-    const float* w0 = Whh + ((size_t)dir * 4 * LSTM_H + (size_t)gate0 * LSTM_H + unit) * LSTM_H + 8 * tig;
-    const float* w1 = Whh + ((size_t)dir * 4 * LSTM_H + (size_t)gate1 * LSTM_H + unit) * LSTM_H + 8 * tig;
+    const float* w0 = Whh + ((size_t)dir * 4 * H + (size_t)gate0 * H + unit) * H + 8 * tig;
+    const float* w1 = Whh + ((size_t)dir * 4 * H + (size_t)gate1 * H + unit) * H + 8 * tig;
 #pragma unroll
-    for (int P = 0; P < 8; ++P) {
+    for (int P = 0; P < NP; ++P) {
       const float4 x0 = *reinterpret_cast<const float4*>(w0 + 32 * P), x1 = *reinterpret_cast<const float4*>(w0 + 32 * P + 4);
       const float4 y0 = *reinterpret_cast<const float4*>(w1 + 32 * P), y1 = *reinterpret_cast<const float4*>(w1 + 32 * P + 4);
       float rx, ry;
+      uint32_t lo0[4], lo1[4];
       // K-step 2P: slots (2tig, 2tig+1) <- k+0,1 ; slots (2tig+8, +9) <- k+2,3.  K-step 2P+1: k+4,5 ; k+6,7.
-      a_hi[2 * P][0] = pack_hi2(x0.x, x0.y, rx, ry); a_lo[2 * P][0] = pack2(rx, ry);
-      a_hi[2 * P][1] = pack_hi2(y0.x, y0.y, rx, ry); a_lo[2 * P][1] = pack2(rx, ry);
-      a_hi[2 * P][2] = pack_hi2(x0.z, x0.w, rx, ry); a_lo[2 * P][2] = pack2(rx, ry);
-      a_hi[2 * P][3] = pack_hi2(y0.z, y0.w, rx, ry); a_lo[2 * P][3] = pack2(rx, ry);
-      a_hi[2 * P + 1][0] = pack_hi2(x1.x, x1.y, rx, ry); a_lo[2 * P + 1][0] = pack2(rx, ry);
-      a_hi[2 * P + 1][1] = pack_hi2(y1.x, y1.y, rx, ry); a_lo[2 * P + 1][1] = pack2(rx, ry);
-      a_hi[2 * P + 1][2] = pack_hi2(x1.z, x1.w, rx, ry); a_lo[2 * P + 1][2] = pack2(rx, ry);
-      a_hi[2 * P + 1][3] = pack_hi2(y1.z, y1.w, rx, ry); a_lo[2 * P + 1][3] = pack2(rx, ry);
+      a_hi[2 * P][0] = pack_hi2(x0.x, x0.y, rx, ry); lo0[0] = pack2(rx, ry);
+      a_hi[2 * P][1] = pack_hi2(y0.x, y0.y, rx, ry); lo0[1] = pack2(rx, ry);
+      a_hi[2 * P][2] = pack_hi2(x0.z, x0.w, rx, ry); lo0[2] = pack2(rx, ry);
+      a_hi[2 * P][3] = pack_hi2(y0.z, y0.w, rx, ry); lo0[3] = pack2(rx, ry);
+      a_hi[2 * P + 1][0] = pack_hi2(x1.x, x1.y, rx, ry); lo1[0] = pack2(rx, ry);
+      a_hi[2 * P + 1][1] = pack_hi2(y1.x, y1.y, rx, ry); lo1[1] = pack2(rx, ry);
+      a_hi[2 * P + 1][2] = pack_hi2(x1.z, x1.w, rx, ry); lo1[2] = pack2(rx, ry);
+      a_hi[2 * P + 1][3] = pack_hi2(y1.z, y1.w, rx, ry); lo1[3] = pack2(rx, ry);
+      if (LO_SMEM) {
+        alo_smem[(2 * P) * THREADS + tid] = make_uint4(lo0[0], lo0[1], lo0[2], lo0[3]);
+        alo_smem[(2 * P + 1) * THREADS + tid] = make_uint4(lo1[0], lo1[1], lo1[2], lo1[3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { a_lo[LO_SMEM ? 0 : 2 * P][q] = lo0[q]; a_lo[LO_SMEM ? 0 : 2 * P + 1][q] = lo1[q]; }
+      }
     }
   }
-  for (int i = tid; i < (int)(sizeof(h_buf) / 4); i += LSTM_WARPS * 32) reinterpret_cast<uint32_t*>(&h_buf[0][0][0][0][0])[i] = 0u;
+  for (int i = tid; i < 2 * LSTM_CL * 2 * LSTM_SLOTS * UPC / 2; i += THREADS) reinterpret_cast<uint32_t*>(h_buf)[i] = 0u;
   if (tid == 0) {
     mbar_init(&h_bar[0], 1);
     mbar_init(&h_bar[1], 1);
@@ -275,11 +296,10 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 3
   // This lane's accumulator columns are batch slots n0 = 2 tig and n0 + 1.
   const int n0 = 2 * tig;
   const bool v0 = n0 < NB && (b0 + n0) < B, v1 = (n0 + 1) < NB && (b0 + n0 + 1) < B;
-  const size_t gc0 = (size_t)dir * 4 * LSTM_H + (size_t)gate0 * LSTM_H + unit;
-  const size_t gc1 = (size_t)dir * 4 * LSTM_H + (size_t)gate1 * LSTM_H + unit;
+  const size_t gc0 = (size_t)dir * 4 * H + (size_t)gate0 * H + unit;
+  const size_t gc1 = (size_t)dir * 4 * H + (size_t)gate1 * H + unit;
   float c_state[2] = {0.f, 0.f};
-  // Input projections are prefetched PF steps ahead (scattered 4-byte loads from HBM: ~1-2 us of latency must
-  // stay off the per-step critical path).  gq[j] holds the values for step (current + j).
+  // Input projections are prefetched PF steps ahead (scattered 4-byte loads from HBM stay off the critical path).
   constexpr int PF = 3;
   float gq[PF][4];  // (gate0, n0), (gate0, n0+1), (gate1, n0), (gate1, n0+1)
   auto load_g = [&](int st, float (&dst)[4]) {
@@ -292,8 +312,15 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 3
   };
 #pragma unroll
   for (int j = 0; j < PF; ++j) load_g(j, gq[j]);
-  const uint32_t dst_h = mapa_u32(smem_u32(&h_buf[0][rank][0][0][0]), lane & 7);
+  const uint32_t dst_h = mapa_u32(smem_u32(h_buf) + rank * BLK_BYTES, lane & 7);
   const uint32_t dst_bar = mapa_u32(smem_u32(&h_bar[0]), lane & 7);
+  // B-fragment byte offsets inside one h buffer: true k0 = 32 P + 8 tig lives in source CTA k0 / UPC at unit k0 % UPC
+  uint32_t boffs[NP];
+#pragma unroll
+  for (int P = 0; P < NP; ++P) {
+    const int k0 = 32 * P + 8 * tig;
+    boffs[P] = (uint32_t)((k0 / UPC) * BLK_BYTES + gid * (UPC * 2) + (k0 % UPC) * 2);
+  }
 
   __syncthreads();
   cluster_arrive();
@@ -302,7 +329,7 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 3
   for (int step = 0; step < F; ++step) {
     const int cur = step & 1;
     const int tt = dir ? F - 1 - step : step;
-    if (tid == 0) mbar_arrive_expect_tx(&h_bar[cur ^ 1], LSTM_MMA_TX);
+    if (tid == 0) mbar_arrive_expect_tx(&h_bar[cur ^ 1], TX);
     float gin[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) gin[q] = gq[0][q];
@@ -315,17 +342,28 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 3
 
     // ---- mat-vec on the tensor cores: three independent accumulation chains ----
     float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
-    const uint8_t* hb = reinterpret_cast<const uint8_t*>(&h_buf[cur][0][0][0][0]) + gid * (LSTM_UPC * 2) + tig * 16;
+    const uint8_t* hb = reinterpret_cast<const uint8_t*>(h_buf) + cur * (LSTM_CL * BLK_BYTES);
 #pragma unroll
-    for (int P = 0; P < 8; ++P) {
-      const uint4 bh = *reinterpret_cast<const uint4*>(hb + P * LSTM_BLK_BYTES);
-      const uint4 bl = *reinterpret_cast<const uint4*>(hb + P * LSTM_BLK_BYTES + LSTM_SLOTS * LSTM_UPC * 2);
-      hmma16816(d0, a_lo[2 * P], bh.x, bh.y);
-      hmma16816(d1, a_hi[2 * P], bl.x, bl.y);
-      hmma16816(d2, a_hi[2 * P], bh.x, bh.y);
-      hmma16816(d0, a_lo[2 * P + 1], bh.z, bh.w);
-      hmma16816(d1, a_hi[2 * P + 1], bl.z, bl.w);
-      hmma16816(d2, a_hi[2 * P + 1], bh.z, bh.w);
+    for (int P = 0; P < NP; ++P) {
+      const uint4 bh = *reinterpret_cast<const uint4*>(hb + boffs[P]);
+      const uint4 bl = *reinterpret_cast<const uint4*>(hb + boffs[P] + LSTM_SLOTS * UPC * 2);
+      if (LO_SMEM) {
+        const uint4 l0 = alo_smem[(2 * P) * THREADS + tid], l1 = alo_smem[(2 * P + 1) * THREADS + tid];
+        const uint32_t al0[4] = {l0.x, l0.y, l0.z, l0.w}, al1[4] = {l1.x, l1.y, l1.z, l1.w};
+        hmma16816(d0, al0, bh.x, bh.y);
+        hmma16816(d1, a_hi[2 * P], bl.x, bl.y);
+        hmma16816(d2, a_hi[2 * P], bh.x, bh.y);
+        hmma16816(d0, al1, bh.z, bh.w);
+        hmma16816(d1, a_hi[2 * P + 1], bl.z, bl.w);
+        hmma16816(d2, a_hi[2 * P + 1], bh.z, bh.w);
+      } else {
+        hmma16816(d0, a_lo[LO_SMEM ? 0 : 2 * P], bh.x, bh.y);
+        hmma16816(d1, a_hi[2 * P], bl.x, bl.y);
+        hmma16816(d2, a_hi[2 * P], bh.x, bh.y);
+        hmma16816(d0, a_lo[LO_SMEM ? 0 : 2 * P + 1], bh.z, bh.w);
+        hmma16816(d1, a_hi[2 * P + 1], bl.z, bl.w);
+        hmma16816(d2, a_hi[2 * P + 1], bh.z, bh.w);
+      }
     }
     // d[0], d[1]: row gate0, slots n0, n0+1 ; d[2], d[3]: row gate1
     float pre[4];
@@ -340,6 +378,7 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 3
     const float ig1 = __shfl_xor_sync(0xffffffffu, sa1 * sb1, 4);
     float h0 = 0.f, h1 = 0.f;
     uint32_t hh = 0u, hl = 0u;
+    __nv_bfloat16* stg = stage + (cur ^ 1) * (2 * LSTM_SLOTS * UPC);
     if (pp) {
       c_state[0] = sa0 * c_state[0] + ig0;
       c_state[1] = sa1 * c_state[1] + ig1;
@@ -348,21 +387,21 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 3
       float r0, r1;
       hh = pack_hi2(h0, h1, r0, r1);
       hl = pack2(r0, r1);
-      __nv_bfloat16* st = &stage[cur ^ 1][0][n0][warp * 4 + u];
+      __nv_bfloat16* st = stg + n0 * UPC + warp * 4 + u;
       st[0] = reinterpret_cast<const __nv_bfloat16*>(&hh)[0];
-      st[LSTM_UPC] = reinterpret_cast<const __nv_bfloat16*>(&hh)[1];
-      st[LSTM_SLOTS * LSTM_UPC] = reinterpret_cast<const __nv_bfloat16*>(&hl)[0];
-      st[LSTM_SLOTS * LSTM_UPC + LSTM_UPC] = reinterpret_cast<const __nv_bfloat16*>(&hl)[1];
+      st[UPC] = reinterpret_cast<const __nv_bfloat16*>(&hh)[1];
+      st[LSTM_SLOTS * UPC] = reinterpret_cast<const __nv_bfloat16*>(&hl)[0];
+      st[LSTM_SLOTS * UPC + UPC] = reinterpret_cast<const __nv_bfloat16*>(&hl)[1];
     }
     fence_proxy_async_smem();
     __syncthreads();
     if (warp == 0 && lane < LSTM_CL) {
-      const uint32_t boff = (uint32_t)((cur ^ 1) * LSTM_CL * LSTM_BLK_BYTES);
-      bulk_s2cluster(dst_h + boff, smem_u32(&stage[cur ^ 1][0][0][0]), LSTM_BLK_BYTES, dst_bar + (uint32_t)((cur ^ 1) * sizeof(uint64_t)));
+      const uint32_t boff = (uint32_t)((cur ^ 1) * LSTM_CL * BLK_BYTES);
+      bulk_s2cluster(dst_h + boff, smem_u32(stg), BLK_BYTES, dst_bar + (uint32_t)((cur ^ 1) * sizeof(uint64_t)));
     }
     // layer output to HBM: off the critical path (overlaps the DSMEM exchange)
     if (pp) {
-      const int col = dir * LSTM_H + unit;
+      const int col = dir * H + unit;
       if (v0) {
         const size_t row = (size_t)(b0 + n0) * F + tt;
         if (Hout) Hout[row * ldh + col] = h0;
@@ -378,6 +417,43 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(LSTM_WARPS * 3
   mbar_wait(&h_bar[F & 1], ((F - 1) >> 1) & 1);
   cluster_arrive();
   cluster_wait();
+}
+
+template <int H, bool LO_SMEM>
+static size_t lstm_mma_smem() {
+  constexpr int UPC = H / LSTM_CL;
+  size_t n = (size_t)(2 * LSTM_CL * 2 * LSTM_SLOTS * UPC + 2 * 2 * LSTM_SLOTS * UPC) * 2 + 128;
+  if (LO_SMEM) n += (size_t)(H / 16) * (UPC / 4 * 32) * 16;
+  return n;
+}
+
+template <int H, bool LO_SMEM>
+static int launch_mma(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs, int B,
+                      int F, cudaStream_t stream) {
+  const size_t smem = lstm_mma_smem<H, LO_SMEM>();
+  RFX_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_mma_kernel<H, LO_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // batch slots per cluster: as few as possible while all clusters stay co-resident (the MMA cost does not depend on it)
+  static int maxc = -1;
+  if (maxc < 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(LSTM_CL, 64, 2);
+    cfg.blockDim = dim3(H / 8 / 4 * 32);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = LSTM_CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, lstm_rec_mma_kernel<H, LO_SMEM>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    maxc = n > 0 ? n : 14;
+  }
+  int nb = LSTM_SLOTS;
+  for (int cand = 1; cand <= LSTM_SLOTS; ++cand)
+    if (2 * ceil_div(B, cand) <= maxc) { nb = cand; break; }
+  dim3 grid(LSTM_CL, ceil_div(B, nb), 2);
+  lstm_rec_mma_kernel<H, LO_SMEM><<<grid, H / 8 / 4 * 32, smem, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 template <int NB>
@@ -422,20 +498,14 @@ int lstm_get_impl() { return g_lstm_impl; }
 
 int launch_lstm_layer(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs,
                       int B, int F, int H, cudaStream_t stream) {
-  RFX_REQUIRE(H == LSTM_H, "lstm: hidden size per direction must be 256");
+  RFX_REQUIRE(H == 192 || H == 256 || H == 384, "lstm: hidden size per direction must be 192, 256 or 384");
   RFX_REQUIRE(B > 0 && F > 0, "lstm: positive sizes");
   RFX_REQUIRE(((uintptr_t)Whh & 15) == 0, "lstm: W_hh must be 16-byte aligned");
   RFX_REQUIRE(Hout || (Hhi && Hlo), "lstm: no output given");
-  if (g_lstm_impl == 0) {
-    // batch slots per cluster: as few as possible while all clusters stay co-resident (the MMA cost does not depend on it)
-    const int maxc = lstm_max_active_clusters();
-    int nb = LSTM_SLOTS;
-    for (int cand = 1; cand <= LSTM_SLOTS; ++cand)
-      if (2 * ceil_div(B, cand) <= maxc) { nb = cand; break; }
-    dim3 grid(LSTM_CL, ceil_div(B, nb), 2);
-    lstm_rec_mma_kernel<<<grid, LSTM_WARPS * 32, 0, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb);
-    RFX_CHECK_CUDA(cudaGetLastError());
-    return 0;
+  if (g_lstm_impl == 0 || H != LSTM_H) {
+    if (H == 256) return launch_mma<256, false>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);
+    if (H == 192) return launch_mma<192, false>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);
+    return launch_mma<384, true>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);
   }
   switch (lstm_choose_nb(B)) {
     case 4: return launch_nb<4>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);

@@ -56,11 +56,20 @@ def test_tc_beats_single_pass_bf16_precision():
     assert relrms(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize("H,B,F", [(192, 7, 50), (192, 24, 200), (384, 3, 40), (384, 9, 128)])
+def test_lstm_layer_other_hidden_sizes(H, B, F):
+    """HDemucs BLSTMs: hidden 192 (layer 4) and 384 (layer 5), input size == hidden size (TA:738)."""
+    _lstm_case(H, H, B, F, "mma")
+
+
 @pytest.mark.parametrize("impl", ["mma", "ffma"])
 @pytest.mark.parametrize("B,F", [(1, 5), (4, 33), (6, 40), (19, 70)])
 def test_lstm_layer_vs_oracle(B, F, impl):
+    _lstm_case(256, 512, B, F, impl)
+
+
+def _lstm_case(H, I, B, F, impl):
     ops = _ops()
-    H, I = 256, 512
     g = torch.Generator().manual_seed(B * 100 + F)
     k = H ** -0.5
     st = {}
@@ -78,5 +87,5 @@ def test_lstm_layer_vs_oracle(B, F, impl):
     out = ops.lstm_layer(G.cuda(), Whh.cuda(), B, F, impl=impl)
     out = out.view(B, F, 2 * H).permute(1, 0, 2)
     err = relrms(out, ref)
-    print(f"lstm {impl} B={B} F={F} rel-RMS {err:.3e}")
+    print(f"lstm {impl} H={H} B={B} F={F} rel-RMS {err:.3e}")
     assert err < 1e-5, err
