@@ -143,6 +143,9 @@ struct G2Params {
   const float* t2;
   const float* slope;  // ACT_PRELU: per-column negative slope
   int act;
+  // fused GroupNorm statistics of the (post-bias) output: accum[(seg * G + g) * 2 + {0,1}] += (sum, sum of squares)
+  double* gn_acc;
+  int gn_G, gn_per_x, gn_cpg, gn_cmod;  // group of column n = ((n % cmod) / cpg); seg = per_x ? b * X + px : b
 };
 
 // Apply the epilogue to 8 consecutive columns [n, n+8) held in v[0..7].  Null vectors act as 1 / 0, which is
@@ -327,9 +330,28 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
       const bool cf_vec = cf && ((p.ldcf & 3) == 0) && ((p.bscf & 3) == 0) && ((p.ldcy_f & 3) == 0) && (((uintptr_t)p.Cf & 15) == 0);
       const bool cs_vec = chi && ((p.ldcs & 7) == 0) && ((p.bscs & 7) == 0) && ((p.ldcy_s & 7) == 0) && (((uintptr_t)p.Chi & 15) == 0) &&
                           (((uintptr_t)p.Clo & 15) == 0);
+      float gs = 0.0f, gss = 0.0f;  // running GroupNorm sums of this thread's row for the current group
+      int gcur = -1;
+      auto gn_flush = [&]() {
+        if (gcur < 0) return;
+        const size_t seg = p.gn_per_x ? (size_t)b * p.X + px : (size_t)b;
+        double* dst = p.gn_acc + (seg * p.gn_G + gcur) * 2;
+        if (p.gn_per_x) {
+          if (row_ok) { atomicAdd(dst, (double)gs); atomicAdd(dst + 1, (double)gss); }
+        } else {
+          const float ws = warp_sum(row_ok ? gs : 0.0f), wss = warp_sum(row_ok ? gss : 0.0f);
+          if (lane == 0) { atomicAdd(dst, (double)ws); atomicAdd(dst + 1, (double)wss); }
+        }
+        gs = 0.0f; gss = 0.0f;
+      };
 #pragma unroll 1
       for (int cc = 0; cc < CH; ++cc) {
         const int c = half * CH + cc;
+        if (p.gn_acc) {  // chunk-uniform (hence warp-uniform) group id; flush when it changes
+          const int nbq = n0 + c * 32;
+          const int gnew = nbq < p.N ? ((nbq % p.gn_cmod) / p.gn_cpg) : gcur;
+          if (gnew != gcur) { gn_flush(); gcur = gnew; }
+        }
         uint32_t v[32];
         tmem_ld32(trow + c * 32, v);
         uint32_t v2[32];
@@ -367,6 +389,11 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
             if (DUAL) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] += __uint_as_float(v2[8 * j + i]);
+            }
+            if (p.gn_acc) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (full || n8 + i < p.N) { gs += o[i]; gss += o[i] * o[i]; }
             }
             if (p.act == ACT_GLU_PAIR) {  // (value, gate) column pairs -> 4 output columns starting at n8 / 2
               float g4[4];
@@ -443,6 +470,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
           }
         }
       }
+      if (p.gn_acc) gn_flush();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -483,6 +511,13 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   p.Cf = pr.Cf; p.ldcf = pr.ldcf; p.bscf = pr.bscf; p.ldcy_f = pr.ldcf_y;
   p.Chi = pr.Chi; p.Clo = pr.Clo; p.ldcs = pr.ldcs; p.bscs = pr.bscs; p.ldcy_s = pr.ldcs_y;
   p.s1 = pr.epi.s1; p.t1 = pr.epi.t1; p.s2 = pr.epi.s2; p.t2 = pr.epi.t2; p.slope = pr.epi.slope; p.act = pr.epi.act;
+  p.gn_acc = pr.gn_acc; p.gn_G = pr.gn_G > 0 ? pr.gn_G : 1; p.gn_per_x = pr.gn_per_x;
+  p.gn_cmod = pr.gn_cmod > 0 ? pr.gn_cmod : pr.N;
+  p.gn_cpg = p.gn_cmod / p.gn_G;
+  if (pr.gn_acc) {
+    RFX_REQUIRE(p.gn_cmod % p.gn_G == 0 && (p.gn_G == 1 || p.gn_cpg % 32 == 0), "fused GroupNorm statistics need 32-column aligned groups");
+    RFX_REQUIRE(pr.epi.act == ACT_NONE && !pr.dual, "fused GroupNorm statistics are taken on the linear (bias-only) output");
+  }
   RFX_REQUIRE(pr.W.Kpad >= p.kb_per_tap * p.taps * G2_BK, "packed weight K extent too small for taps * Ktap");
   CUtensorMap mapA, mapW;
   int rc;

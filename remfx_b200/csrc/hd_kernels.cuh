@@ -108,6 +108,74 @@ __global__ void __launch_bounds__(256) time_first_kernel(const float* __restrict
   store_split8(ohi, olo, ((size_t)b * Lo + t) * C + c0, o);
 }
 
+// ---- first freq-branch conv: Conv2d(2 -> C, (k,1), (s,1), pad (p,0)) + bias + GELU, input normalised on the fly ----
+// Z fp32 [B][T][Fr][2] (re, im), stats (mean, std) per item -> split [B][T][Fr/s][C]; one thread per (pixel, 8 channels)
+__global__ void __launch_bounds__(256) freq_first_kernel(const float* __restrict__ Z, const float* __restrict__ stats, int Tf, int Fr, int Fo,
+                                                         int C, int K, int S, int P, const float* __restrict__ w /*[C][2][K]*/,
+                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ ohi,
+                                                         __nv_bfloat16* __restrict__ olo) {
+  const int groups = C / 8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= (long long)Tf * Fo * groups) return;
+  const int c0 = (int)(idx % groups) * 8;
+  const int fo = (int)((idx / groups) % Fo);
+  const int t = (int)(idx / ((long long)groups * Fo));
+  const float mean = stats[2 * b], inv = 1.0f / (1e-5f + stats[2 * b + 1]);
+  const float* zr = Z + (((size_t)b * Tf + t) * Fr) * 2;
+  float xr[16], xi[16];
+  for (int j = 0; j < K; ++j) {
+    const int f = fo * S + j - P;
+    if (f >= 0 && f < Fr) {
+      const float2 v = *reinterpret_cast<const float2*>(zr + 2 * f);
+      xr[j] = (v.x - mean) * inv;
+      xi[j] = (v.y - mean) * inv;
+    } else {
+      xr[j] = 0.0f;
+      xi[j] = 0.0f;
+    }
+  }
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float* wc = w + (size_t)(c0 + i) * 2 * K;
+    float acc = bias[c0 + i];
+    for (int j = 0; j < K; ++j) acc = fmaf(wc[j], xr[j], fmaf(wc[K + j], xi[j], acc));
+    o[i] = gelu_exact(acc);
+  }
+  store_split8(ohi, olo, (((size_t)b * Tf + t) * Fo + fo) * C + c0, o);
+}
+
+// ---- last freq decoder, fused: ConvTranspose2d(C -> 2, (k,1), (s,1)) + bias, crop `pad`, de-normalise -> complex Z ----
+// y split [B][T][Fi][C]; Z[b][t][bin] = (convtr(y)[bin + pad][re, im]) * std + mean.  One thread per (t, bin).
+__global__ void __launch_bounds__(256) final_freq_convtr_kernel(const __nv_bfloat16* __restrict__ yhi, const __nv_bfloat16* __restrict__ ylo,
+                                                                int Tf, int Fi, int C, int K, int S, int pad, int bins,
+                                                                const float* __restrict__ w /*[C][2][K]*/, const float* __restrict__ bias,
+                                                                const float* __restrict__ stats, float2* __restrict__ Z) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= (long long)Tf * bins) return;
+  const int k = (int)(idx % bins), t = (int)(idx / bins);
+  const int pos = k + pad;
+  float re = bias[0], im = bias[1];
+  for (int j = pos % S; j < K; j += S) {
+    const int i = (pos - j) / S;
+    if (i < 0 || i >= Fi) continue;
+    const size_t off = (((size_t)b * Tf + t) * Fi + i) * C;
+    for (int c = 0; c < C; c += 8) {
+      float u[8];
+      load_split8(yhi, ylo, off + c, u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        re = fmaf(w[((size_t)(c + e) * 2 + 0) * K + j], u[e], re);
+        im = fmaf(w[((size_t)(c + e) * 2 + 1) * K + j], u[e], im);
+      }
+    }
+  }
+  const float mean = stats[2 * b], sd = stats[2 * b + 1];
+  Z[((size_t)b * Tf + t) * bins + k] = make_float2(re * sd + mean, im * sd + mean);
+}
+
 // ---- GroupNorm statistics over an fp32 tensor (B, Y, X, C): one segment per (b [, x]) and group ----
 // accum[(seg * G + g) * 2 + {0,1}] += (sum, sum of squares) in fp64; grid = (nsplit, nseg).
 __global__ void __launch_bounds__(256) gn_accum_kernel(const float* __restrict__ raw, int Y, int X, int C, int G, int per_x,

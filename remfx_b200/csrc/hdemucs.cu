@@ -179,8 +179,9 @@ struct Runner {
   // ---- generic implicit-GEMM convolution -------------------------------------------------------
   // axis: 0 = taps along X, 1 = taps along Y (plain 1-D convs); dil = dilation; pad = zero padding (plain)
   // out_f32: write fp32 (pre-norm) instead of split; act: epilogue activation (ACT_NONE / GELU / GLU_PAIR)
+  // gn_G > 0: also accumulate GroupNorm statistics of the output in the GEMM epilogue; *gn_out receives (mean, rstd) stats
   Ten conv(const std::string& name, const Ten& in, int axis, int dil, int pad, bool out_f32, int act, const Ten* dst = nullptr,
-           int dst_col = 0) {
+           int dst_col = 0, int gn_G = 0, int gn_per_x = 0, float** gn_out = nullptr) {
     auto it = h->convs.find(name);
     if (it == h->convs.end()) { set_error("hdemucs: conv '" + name + "' was not prepared"); rc = 2; return Ten(); }
     Conv& c = it->second;
@@ -210,7 +211,21 @@ struct Runner {
     Ten out;
     if (dst) out = *dst;  // write columns [dst_col, dst_col + N) of an existing fp32 tensor
     else out = out_f32 ? f32(in.B, Yo, Xo, Cout_store) : split(in.B, Yo, Xo, Cout_store);
-    if (dry || rc) { ++launches; return out; }
+    double* gacc = nullptr;
+    float* gst = nullptr;
+    int gn_cmod = 0, nseg = 0;
+    long long gcount = 0;
+    if (gn_G > 0) {
+      gn_cmod = g.kind == 2 ? c.Co : Nout;               // transposed convs: channel = column % Cout
+      const int Xs = g.kind == 2 ? Xo * g.s : Xo;        // spatial extent in the (upsampled) view
+      nseg = gn_per_x ? in.B * Xo : in.B;
+      gacc = reinterpret_cast<double*>(take((size_t)nseg * gn_G * 2 * 8));
+      gst = reinterpret_cast<float*>(take((size_t)nseg * gn_G * 2 * 4));
+      gcount = (gn_per_x ? (long long)Yo : (long long)Yo * Xs) * (gn_cmod / gn_G);
+      if (gn_out) *gn_out = gst;
+    }
+    if (dry || rc) { launches += gn_G > 0 ? 3 : 1; return out; }
+    if (gn_G > 0 && cudaMemsetAsync(gacc, 0, (size_t)nseg * gn_G * 2 * 8, s) != cudaSuccess) { set_error("memset failed"); rc = 1; return out; }
     pr.A.hi = in.hi; pr.A.rows = Xv; pr.A.rows_y = in.Y; pr.A.ld = Cv; pr.A.ld_y = (long long)Xv * Cv;
     pr.A.batch_stride = (long long)in.Y * Xv * Cv; pr.A.plane_stride = (long long)in.plane;
     pr.W = c.w;
@@ -223,8 +238,14 @@ struct Runner {
     else { pr.Chi = out.hi; pr.Clo = out.lo(); pr.ldcs = Cout_store; pr.ldcs_y = (long long)Xo * Cout_store; pr.bscs = (long long)Yo * Xo * Cout_store; }
     pr.epi.t1 = c.bias.p;
     pr.epi.act = act;
+    pr.gn_acc = gacc; pr.gn_G = gn_G > 0 ? gn_G : 1; pr.gn_per_x = gn_per_x; pr.gn_cmod = gn_cmod;
     rc = launch_gemm2(pr, s);
     ++launches;
+    if (gn_G > 0 && rc == 0) {
+      gn_final_kernel<<<ceil_div(nseg * gn_G, 256), 256, 0, s>>>(gacc, gcount, nseg * gn_G, 1e-5f, gst);
+      chk();
+      ++launches;
+    }
     return out;
   }
 
@@ -341,8 +362,8 @@ struct Runner {
       const std::string L = base + ".layers." + std::to_string(d);
       const int dil = 1 << d;
       // conv k=3 (dilated) -> GroupNorm(1, h) -> GELU
-      Ten r1 = conv(L + ".0", y, axis, dil, dil, true, ACT_NONE);
-      float* st1 = gn_stats(r1, 1, per_x);
+      float* st1 = nullptr;
+      Ten r1 = conv(L + ".0", y, axis, dil, dil, true, ACT_NONE, nullptr, 0, 1, per_x, &st1);
       Ten a1 = gn_apply(r1, st1, 1, per_x, HP(h, L + ".1.weight"), HP(h, L + ".1.bias"), 1, nullptr, nullptr, r1.X, 0, 0);
       tap(L + ".2", a1);
       int ci = 3;
@@ -358,8 +379,8 @@ struct Runner {
         ci = 5;
       }
       // 1x1 conv h -> 2C -> GroupNorm(1, 2C) -> GLU -> LayerScale -> residual
-      Ten r2 = conv(L + "." + std::to_string(ci), a1, 0, 1, 0, true, ACT_NONE);
-      float* st2 = gn_stats(r2, 1, per_x);
+      float* st2 = nullptr;
+      Ten r2 = conv(L + "." + std::to_string(ci), a1, 0, 1, 0, true, ACT_NONE, nullptr, 0, 1, per_x, &st2);
       const std::string gn2 = L + "." + std::to_string(ci + 1), ls = L + "." + std::to_string(ci + 3);
       y = gn_apply(r2, st2, 1, per_x, HP(h, gn2 + ".weight"), HP(h, gn2 + ".bias"), 2, HP(h, ls + ".scale"), &y, r2.X, 0, 0);
     }
@@ -379,7 +400,6 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
   float2* Z = reinterpret_cast<float2*>(R.take((size_t)B * le * bins * 8));
   float* st_f = reinterpret_cast<float*>(R.take((size_t)B * 2 * 4));
   float* st_t = reinterpret_cast<float*>(R.take((size_t)B * 2 * 4));
-  Ten xf = R.split(B, le, bins, 2);           // (B, T, Fr, 2)
   float* xt = reinterpret_cast<float*>(R.take((size_t)B * T * 4));
   if (!dry) {
     StftParams sp{};
@@ -391,17 +411,14 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
     if ((R.rc = launch_stft(sp, B, s))) return R.rc;
     item_stats_kernel<<<B, 1024, 0, s>>>(reinterpret_cast<const float*>(Z), (long long)le * bins * 2, st_f);
     item_stats_kernel<<<B, 1024, 0, s>>>(x, (long long)T, st_t);
-    const long long nf = (long long)le * bins * 2;
-    item_normalize_kernel<<<dim3((unsigned)((nf / 8 + 255) / 256), B), 256, 0, s>>>(reinterpret_cast<const float*>(Z), nf, st_f, xf.hi, xf.lo(), nullptr);
     item_normalize_kernel<<<dim3((unsigned)((T / 8 + 255) / 256), B), 256, 0, s>>>(x, (long long)T, st_t, nullptr, nullptr, xt);
     R.chk();
   }
-  R.launches += 5;
-  R.tap("spec_norm", xf);
+  R.launches += 4;
 
   // ---------------- encoders (TA:565-593) ----------------
   std::vector<Ten> saved, saved_t;
-  Ten xcur = xf;   // freq branch
+  Ten xcur;        // freq branch
   Ten tcur;        // time branch (split) after layer 0
   Ten inject;      // fp32, time conv output of the merge layer
   int freqs = bins;
@@ -435,7 +452,18 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
         saved_t.push_back(tcur);
       }
       // ---- freq branch ----
-      if (!normed) {
+      if (idx == 0) {  // 2 -> C channels: SIMT kernel that normalises (TA:553-557) on the fly
+        const int Fo = bins / h->cfg.stride;
+        xcur = R.split(B, le, Fo, ch0);
+        if (!dry && R.ok()) {
+          const long long items = (long long)le * Fo * (ch0 / 8);
+          freq_first_kernel<<<dim3((unsigned)((items + 255) / 256), B), 256, 0, s>>>(reinterpret_cast<const float*>(Z), st_f, le, bins, Fo, ch0,
+                                                                                     h->cfg.kernel_size, h->cfg.stride, h->cfg.kernel_size / 4,
+                                                                                     HP(h, fe + ".conv.weight"), HP(h, fe + ".conv.bias"),
+                                                                                     xcur.hi, xcur.lo());
+          R.chk();
+        } else ++R.launches;
+      } else if (!normed) {
         xcur = R.conv(fe + ".conv", xcur, 0, 1, 0, false, ACT_GELU);
       } else {
         Ten raw = R.conv(fe + ".conv", xcur, 0, 1, 0, true, ACT_NONE);  // (B, T, 1, C)
@@ -455,8 +483,8 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
       if (!normed) {
         xcur = R.conv(fe + ".rewrite", xcur, 0, 1, 0, false, ACT_GLU_PAIR);
       } else {
-        Ten raw = R.conv(fe + ".rewrite", xcur, 0, 1, 0, true, ACT_NONE);
-        float* st = R.gn_stats(raw, h->cfg.norm_groups, 0);
+        float* st = nullptr;
+        Ten raw = R.conv(fe + ".rewrite", xcur, 0, 1, 0, true, ACT_NONE, nullptr, 0, h->cfg.norm_groups, 0, &st);
         xcur = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fe + ".norm2.weight"), HP(h, fe + ".norm2.bias"), 2, nullptr, nullptr, raw.X, 0, 0);
       }
       if (idx == 0 && h->cfg.freq_emb_weight != 0.0f) {  // TA:586-591
@@ -475,12 +503,12 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
       // merged layer (freq == false): Conv1d(k = 2*time_stride, s = time_stride, pad) on (B, 1, T, C) (TA:389-399)
       Ten xin = xcur;  // (B, T, 1, C) has the same memory order as (B, 1, T, C)
       xin.X = xcur.Y; xin.Y = 1;
-      Ten raw = R.conv(fe + ".conv", xin, 0, 1, 0, true, ACT_NONE);
-      float* st = R.gn_stats(raw, h->cfg.norm_groups, 0);
+      float* st = nullptr;
+      Ten raw = R.conv(fe + ".conv", xin, 0, 1, 0, true, ACT_NONE, nullptr, 0, h->cfg.norm_groups, 0, &st);
       Ten y = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fe + ".norm1.weight"), HP(h, fe + ".norm1.bias"), 1, nullptr, nullptr, raw.X, 0, 0);
       y = R.dconv(fe + ".dconv", y, 0, 0, lstm_attn);
-      Ten raw2 = R.conv(fe + ".rewrite", y, 0, 1, 0, true, ACT_NONE);
-      float* st2 = R.gn_stats(raw2, h->cfg.norm_groups, 0);
+      float* st2 = nullptr;
+      Ten raw2 = R.conv(fe + ".rewrite", y, 0, 1, 0, true, ACT_NONE, nullptr, 0, h->cfg.norm_groups, 0, &st2);
       xcur = R.gn_apply(raw2, st2, h->cfg.norm_groups, 0, HP(h, fe + ".norm2.weight"), HP(h, fe + ".norm2.bias"), 2, nullptr, nullptr, raw2.X, 0, 0);
       R.tap(fe, xcur);
       saved.push_back(xcur);
@@ -515,8 +543,8 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
     if (!normed) {
       y = R.conv(fd + ".rewrite", xin, 0, 1, 1, false, ACT_GLU_PAIR);
     } else {
-      Ten raw = R.conv(fd + ".rewrite", xin, xin.Y > 1 ? 1 : 0, 1, 1, true, ACT_NONE);
-      float* st = R.gn_stats(raw, h->cfg.norm_groups, 0);
+      float* st = nullptr;
+      Ten raw = R.conv(fd + ".rewrite", xin, xin.Y > 1 ? 1 : 0, 1, 1, true, ACT_NONE, nullptr, 0, h->cfg.norm_groups, 0, &st);
       y = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fd + ".norm1.weight"), HP(h, fd + ".norm1.bias"), 2, nullptr, nullptr, raw.X, 0, 0);
     }
     R.tap(fd + ".pre", y);
@@ -524,13 +552,13 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
     const Conv& ctr = h->convs[fd + ".conv_tr"];
     const int pad = ctr.crop;  // (k - s) / 2, or 0 for the last_freq layer (TA:419-423)
     if (last) {
-      Ten raw = R.conv(fd + ".conv_tr", y, 0, 1, 0, true, ACT_NONE);  // (B, T, Fr/4 + 1, 4 * 2)
-      R.tap(fd + ".raw", raw);
-      // de-normalise, to complex, iSTFT (TA:516-521, 489-497, 624-633)
+      // transposed conv (C -> 2) + crop + de-normalise -> complex, then iSTFT (TA:287-294, 516-521, 489-497, 624-633)
       float2* Zo = reinterpret_cast<float2*>(R.take((size_t)B * le * bins * 8));
       if (!dry && R.ok()) {
         const long long items = (long long)le * bins;
-        final_freq_kernel<<<dim3((unsigned)((items + 255) / 256), B), 256, 0, s>>>(raw.f, le, raw.X, pad, bins, st_f, Zo);
+        final_freq_convtr_kernel<<<dim3((unsigned)((items + 255) / 256), B), 256, 0, s>>>(y.hi, y.lo(), le, y.X, y.C, ctr.g.k, ctr.g.s, pad, bins,
+                                                                                          HP(h, fd + ".conv_tr.weight"), HP(h, fd + ".conv_tr.bias"),
+                                                                                          st_f, Zo);
         R.chk();
         IstftParams ip{};
         ip.Z = Zo; ip.ldz = bins; ip.mask = nullptr; ip.ldm = 0;
@@ -546,9 +574,9 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
       xd.X *= ctr.g.s; xd.C /= ctr.g.s;                           // view (Xg, s*Co) as (Xg*s, Co)
       crop_f = pad;
     } else {
-      Ten raw = R.conv(fd + ".conv_tr", y, 0, 1, 0, true, ACT_NONE);
+      float* st = nullptr;
+      Ten raw = R.conv(fd + ".conv_tr", y, 0, 1, 0, true, ACT_NONE, nullptr, 0, h->cfg.norm_groups, 0, &st);
       raw.X *= ctr.g.s; raw.C /= ctr.g.s;
-      float* st = R.gn_stats(raw, h->cfg.norm_groups, 0);
       const int len = raw.X - 2 * pad;
       xd = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fd + ".norm2.weight"), HP(h, fd + ".norm2.bias"), 1, nullptr, nullptr, len, pad, 0);
       crop_f = 0;
@@ -584,9 +612,9 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
         xtd.X *= ttr.g.s; xtd.C /= ttr.g.s;
         crop_t = tpad;
       } else {
-        Ten raw = R.conv(td + ".conv_tr", yt, 0, 1, 0, true, ACT_NONE);
+        float* st = nullptr;
+        Ten raw = R.conv(td + ".conv_tr", yt, 0, 1, 0, true, ACT_NONE, nullptr, 0, h->cfg.norm_groups, 0, &st);
         raw.X *= ttr.g.s; raw.C /= ttr.g.s;
-        float* st = R.gn_stats(raw, h->cfg.norm_groups, 0);
         const int len = raw.X - 2 * tpad;
         xtd = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, td + ".norm2.weight"), HP(h, td + ".norm2.bias"), 1, nullptr, nullptr, len, tpad, 0);
         crop_t = 0;
@@ -652,7 +680,7 @@ int rfx_hdemucs_finalize(rfx_hdemucs_t* h, void* stream) {
     const std::string fe = "freq_encoder." + std::to_string(idx), te = "time_encoder." + std::to_string(idx);
     const std::string fd = "freq_decoder." + std::to_string(c.depth - 1 - idx), td = "time_decoder." + std::to_string(c.depth - 2 - idx);
     // encoder convs
-    rc = prep_conv(h, fe + ".conv", 1, chout_z, chin_z, ker, stri, pad ? ker / 4 : 0, 0, 1, 1, tmp, s);
+    if (idx > 0) rc = prep_conv(h, fe + ".conv", 1, chout_z, chin_z, ker, stri, pad ? ker / 4 : 0, 0, 1, 1, tmp, s);
     if (!rc) rc = prep_conv(h, fe + ".rewrite", 0, 2 * chout_z, chout_z, 1, 1, 0, idx < c.norm_starts ? 1 : 0, 1, 1, tmp, s);
     auto prep_dconv = [&](const std::string& base, int C) -> int {
       const int hid = C / c.dconv_comp;
@@ -711,7 +739,11 @@ int rfx_hdemucs_finalize(rfx_hdemucs_t* h, void* stream) {
       rc = prep_conv(h, fd + ".rewrite", 0, 2 * chout_z, chout_z, two_d ? 9 : 3, 1, 1, idx < c.norm_starts ? 1 : 0, two_d ? 3 : 1, two_d ? 3 : 3, tmp, s);
       if (!rc && two_d) { h->convs[fd + ".rewrite"].kh = 3; h->convs[fd + ".rewrite"].kw = 3; }
     }
-    if (!rc) rc = prep_conv(h, fd + ".conv_tr", 2, cin_dec_z, chout_z, ker, stri, 0, 0, 1, 1, tmp, s);
+    if (!rc && idx > 0) rc = prep_conv(h, fd + ".conv_tr", 2, cin_dec_z, chout_z, ker, stri, 0, 0, 1, 1, tmp, s);
+    if (!rc && idx == 0) {  // the last freq decoder (C -> 2) is a fused SIMT kernel; it still needs a descriptor for (k, s)
+      Conv& cc = h->convs[fd + ".conv_tr"];
+      cc.g.kind = 2; cc.g.k = ker; cc.g.s = stri; cc.Ci = chout_z; cc.Co = cin_dec_z;
+    }
     if (!rc) h->convs[fd + ".conv_tr"].crop = pad ? (ker - stri) / 2 : 0;
     if (freq && !rc) {
       if (!last_freq) rc = prep_conv(h, td + ".rewrite", 0, 2 * chout, chout, 3, 1, 1, idx < c.norm_starts ? 1 : 0, 1, 1, tmp, s);

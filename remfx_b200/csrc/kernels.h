@@ -106,6 +106,9 @@ struct G2Problem {
   __nv_bfloat16* Clo = nullptr;
   long long ldcs = 0, ldcs_y = 0, bscs = 0;
   Epilogue epi;
+  // optional fused GroupNorm statistics of the output (see gemm2.cu): accum must be zeroed by the caller
+  double* gn_acc = nullptr;
+  int gn_G = 1, gn_per_x = 0, gn_cmod = 0;
 };
 int g2_choose_bn(int N);
 size_t split_weight_elems(int N, int K, int BN);  // elements of ONE plane

@@ -34,8 +34,8 @@ with torch.no_grad():
     mag = ref._magnitude(z)
     mean = mag.mean(dim=(1, 2, 3), keepdim=True); std = mag.std(dim=(1, 2, 3), keepdim=True)
     xn = (mag - mean) / (1e-5 + std)
-g = m.tap("spec_norm")  # (B, T, Fr, 2)
-print("spec_norm", rr(g.permute(0, 3, 2, 1), xn))
+
+
 
 
 def cmp(gname, r, freq):
