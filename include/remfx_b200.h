@@ -230,6 +230,22 @@ size_t rfx_sisdr_workspace_bytes(int B);
 int rfx_sisdr_loss(const float* x, long long x_bstride, const float* y, long long y_bstride, int B, int T, float* result,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* L5  optimiser half of the training step: torch.optim.AdamW as configured at remfx/models.py:185-191 (lr 1e-4, betas
+ * (0.95, 0.999), eps 1e-6, weight_decay 1e-3) + Lightning's `gradient_clip_val: 10.0` (cfg/config.yaml:119 =
+ * torch.nn.utils.clip_grad_norm_) over ONE flat fp32 bucket holding every parameter (16-byte aligned, same length for
+ * param / grad / exp_avg / exp_avg_sq).
+ *   rfx_grad_sumsq : workspace[0] (double) (+)= sum(grad^2); accumulate != 0 adds to the previous value (several buckets)
+ *   rfx_adamw_step : g' = grad * grad_scale * min(1, max_norm / (sqrt(sumsq) * grad_scale + 1e-6)) (no clipping when
+ *                    max_norm <= 0), then the decoupled-decay Adam update with bias correction for the 1-based `step`;
+ *                    grad_scale = 1 / world_size after a SUM all-reduce of the bucket; total_norm (device, optional)
+ *                    receives the pre-clip norm, as clip_grad_norm_ returns it.  The learning rate is an argument so the
+ *                    host applies the MultiStepLR schedule (models.py:192-196). */
+size_t rfx_optim_workspace_bytes(void);
+int rfx_grad_sumsq(const float* grad, long long n, void* workspace, int accumulate, void* stream);
+int rfx_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int step, float grad_scale, float max_norm, const void* workspace, float* total_norm,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,10 @@ _SIGNATURES = {
                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "rfx_sisdr_workspace_bytes": (C.c_size_t, [C.c_int]),
     "rfx_sisdr_loss": (C.c_int, [_f32p, C.c_longlong, _f32p, C.c_longlong, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rfx_optim_workspace_bytes": (C.c_size_t, []),
+    "rfx_grad_sumsq": (C.c_int, [_f32p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]),
+    "rfx_adamw_step": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                 C.c_int, C.c_float, C.c_float, C.c_void_p, _f32p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

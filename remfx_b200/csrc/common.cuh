@@ -193,6 +193,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// GLU gates: ex2.approx + rcp.approx, ~1e-6 relative (2 MUFU + 3 FP32 instead of ~14 instructions)
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 #endif  // __CUDACC__
 

@@ -13,12 +13,12 @@
 // TMEM accumulator.  The dropped lo*lo term is O(2^-16): results meet the reference's 1e-4 rel-RMS gate
 // where a single bf16 or TF32 pass does not.
 //
-// Structure (one CTA per SM, persistent over output tiles, 320 threads):
+// Structure (one CTA per SM, persistent over output tiles, 576 threads):
 //   warp 0    TMA producer: one 4-D tensor-map load per operand per stage (hi+lo planes in one box),
 //             SWIZZLE_128B, mbarrier complete_tx; K / M / N tails are zero-filled by the TMA unit
 //   warp 1    MMA issuer: a single thread issues tcgen05.mma (M=128, N=BN, K=16) from smem descriptors,
 //             tcgen05.commit releases smem stages and publishes finished accumulators
-//   warps 2-9 epilogue (two warps per TMEM lane quarter, each draining half of the columns): tcgen05.ld the
+//   warps 2-17 epilogue (four warps per TMEM lane quarter, each draining a quarter of the columns): tcgen05.ld the
 //             accumulator (TMEM is double-buffered: 2 x BN columns, so the epilogue of tile i overlaps the
 //             main loop of tile i+1), fused per-column affine(s) + activation, then either fp32 rows or
 //             re-split bf16 hi/lo planes for the next layer
@@ -202,10 +202,12 @@ __device__ __forceinline__ void g2_epi8(float (&v)[8], int n, const G2Params& p,
   }
 }
 
-constexpr int G2_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// warp 0 TMA, warp 1 MMA, then the epilogue warps: 16 (8 in DUAL mode, whose second accumulator costs 32 more registers)
+constexpr int g2_epi_warps(bool dual) { return dual ? 8 : 16; }
+constexpr int g2_threads(bool dual) { return 64 + 32 * g2_epi_warps(dual); }
 
 template <int BN, int STAGES, bool DUAL>
-__global__ void __launch_bounds__(G2_THREADS, 1)
+__global__ void __launch_bounds__(g2_threads(DUAL), 1)
     gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const G2Params p) {
   constexpr int B_STAGE = 2 * BN * G2_BK * 2;  // hi + lo planes of the W tile
   constexpr int STAGE_BYTES = G2_A_STAGE + B_STAGE;
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], g2_epi_warps(DUAL));  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -306,8 +308,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;   // which half of the tile's columns this warp drains
-    constexpr int CH = BN / 64;         // 32-column chunks per warp
+    const int half = (warp - 2) >> 2;   // which slice of the tile's columns this warp drains
+    constexpr int CH = BN / (8 * g2_epi_warps(DUAL));  // 32-column chunks per warp
     const bool vec_al = (((uintptr_t)p.s1 | (uintptr_t)p.t1 | (uintptr_t)p.s2 | (uintptr_t)p.t2 | (uintptr_t)p.slope) & 15) == 0;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
             if (p.act == ACT_GLU_PAIR) {  // (value, gate) column pairs -> 4 output columns starting at n8 / 2
               float g4[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) g4[i] = o[2 * i] * sigmoidf_acc(o[2 * i + 1]);
+              for (int i = 0; i < 4; ++i) g4[i] = o[2 * i] * sigmoidf_fast(o[2 * i + 1]);
               const int c4 = n8 >> 1;
               const int Nout = p.N >> 1;
               if (cf) {
@@ -535,17 +537,17 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
     constexpr int STAGES = 2;
     const int smem = STAGES * (G2_A_STAGE + 2 * 256 * G2_BK * 2) + 1024 + 256;
     RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gemm2_kernel<256, STAGES, true><<<grid, G2_THREADS, smem, stream>>>(mapA, mapW, p);
+    gemm2_kernel<256, STAGES, true><<<grid, g2_threads(true), smem, stream>>>(mapA, mapW, p);
   } else if (BN == 256) {
     constexpr int STAGES = 2;
     const int smem = STAGES * (G2_A_STAGE + 2 * 256 * G2_BK * 2) + 1024 + 256;
     RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gemm2_kernel<256, STAGES, false><<<grid, G2_THREADS, smem, stream>>>(mapA, mapW, p);
+    gemm2_kernel<256, STAGES, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
   } else {
     constexpr int STAGES = 3;
     const int smem = STAGES * (G2_A_STAGE + 2 * 128 * G2_BK * 2) + 1024 + 256;
     RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gemm2_kernel<128, STAGES, false><<<grid, G2_THREADS, smem, stream>>>(mapA, mapW, p);
+    gemm2_kernel<128, STAGES, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
   }
   RFX_CHECK_CUDA(cudaGetLastError());
   return 0;

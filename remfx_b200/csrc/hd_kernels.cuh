@@ -83,92 +83,125 @@ __global__ void __launch_bounds__(256) item_normalize_kernel(const float* __rest
 }
 
 // ---- first time-branch conv: Conv1d(1 -> C, k, stride s, pad p) + bias + GELU on the normalised waveform ----
-// xt fp32 [B][T] -> split [B][T/s][C]; one thread per (output step, 8 channels)
-__global__ void __launch_bounds__(256) time_first_kernel(const float* __restrict__ xt, int T, int Lo, int C, int K, int S, int P,
+// xt fp32 [B][T] -> split [B][T/s][C]; one thread per (output step, 8 channels); weights transposed into smem [K][C]
+template <int K>
+__global__ void __launch_bounds__(256) time_first_kernel(const float* __restrict__ xt, int T, int Lo, int C, int S, int P,
                                                          const float* __restrict__ w /*[C][K]*/, const float* __restrict__ bias,
                                                          __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo) {
-  const int groups = C / 8;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  extern __shared__ float hd_smem[];  // [K][C] weights, then [C] bias
+  for (int i = threadIdx.x; i < C * K; i += blockDim.x) hd_smem[(i % K) * C + i / K] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) hd_smem[K * C + i] = bias[i];
+  __syncthreads();
+  const unsigned groups = C / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
-  if (idx >= (long long)Lo * groups) return;
+  if (idx >= (unsigned)Lo * groups) return;
   const int c0 = (int)(idx % groups) * 8;
   const int t = (int)(idx / groups);
-  float xs[16];
+  float xs[K];
+#pragma unroll
   for (int j = 0; j < K; ++j) {
     const int i = t * S + j - P;
-    xs[j] = (i >= 0 && i < T) ? xt[(size_t)b * T + i] : 0.0f;
+    xs[j] = (i >= 0 && i < T) ? __ldg(xt + (size_t)b * T + i) : 0.0f;
   }
   float o[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float acc = bias[c0 + i];
-    for (int j = 0; j < K; ++j) acc = fmaf(w[(c0 + i) * K + j], xs[j], acc);
-    o[i] = gelu_exact(acc);
+  for (int i = 0; i < 8; ++i) o[i] = hd_smem[K * C + c0 + i];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const float4 w0 = *reinterpret_cast<const float4*>(hd_smem + j * C + c0);
+    const float4 w1 = *reinterpret_cast<const float4*>(hd_smem + j * C + c0 + 4);
+    o[0] = fmaf(w0.x, xs[j], o[0]); o[1] = fmaf(w0.y, xs[j], o[1]); o[2] = fmaf(w0.z, xs[j], o[2]); o[3] = fmaf(w0.w, xs[j], o[3]);
+    o[4] = fmaf(w1.x, xs[j], o[4]); o[5] = fmaf(w1.y, xs[j], o[5]); o[6] = fmaf(w1.z, xs[j], o[6]); o[7] = fmaf(w1.w, xs[j], o[7]);
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = gelu_exact(o[i]);
   store_split8(ohi, olo, ((size_t)b * Lo + t) * C + c0, o);
 }
 
 // ---- first freq-branch conv: Conv2d(2 -> C, (k,1), (s,1), pad (p,0)) + bias + GELU, input normalised on the fly ----
 // Z fp32 [B][T][Fr][2] (re, im), stats (mean, std) per item -> split [B][T][Fr/s][C]; one thread per (pixel, 8 channels)
+template <int K>
 __global__ void __launch_bounds__(256) freq_first_kernel(const float* __restrict__ Z, const float* __restrict__ stats, int Tf, int Fr, int Fo,
-                                                         int C, int K, int S, int P, const float* __restrict__ w /*[C][2][K]*/,
+                                                         int C, int S, int P, const float* __restrict__ w /*[C][2][K]*/,
                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ ohi,
                                                          __nv_bfloat16* __restrict__ olo) {
-  const int groups = C / 8;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  extern __shared__ float hd_smem[];  // [2K][C] weights (row = part * K + tap), then [C] bias
+  for (int i = threadIdx.x; i < C * 2 * K; i += blockDim.x) hd_smem[(i % (2 * K)) * C + i / (2 * K)] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) hd_smem[2 * K * C + i] = bias[i];
+  __syncthreads();
+  const unsigned groups = C / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
-  if (idx >= (long long)Tf * Fo * groups) return;
+  if (idx >= (unsigned)Tf * Fo * groups) return;
   const int c0 = (int)(idx % groups) * 8;
-  const int fo = (int)((idx / groups) % Fo);
-  const int t = (int)(idx / ((long long)groups * Fo));
+  const unsigned pix = idx / groups;
+  const int fo = (int)(pix % Fo);
+  const int t = (int)(pix / Fo);
   const float mean = stats[2 * b], inv = 1.0f / (1e-5f + stats[2 * b + 1]);
   const float* zr = Z + (((size_t)b * Tf + t) * Fr) * 2;
-  float xr[16], xi[16];
-  for (int j = 0; j < K; ++j) {
-    const int f = fo * S + j - P;
-    if (f >= 0 && f < Fr) {
-      const float2 v = *reinterpret_cast<const float2*>(zr + 2 * f);
-      xr[j] = (v.x - mean) * inv;
-      xi[j] = (v.y - mean) * inv;
-    } else {
-      xr[j] = 0.0f;
-      xi[j] = 0.0f;
-    }
-  }
   float o[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float* wc = w + (size_t)(c0 + i) * 2 * K;
-    float acc = bias[c0 + i];
-    for (int j = 0; j < K; ++j) acc = fmaf(wc[j], xr[j], fmaf(wc[K + j], xi[j], acc));
-    o[i] = gelu_exact(acc);
+  for (int i = 0; i < 8; ++i) o[i] = hd_smem[2 * K * C + c0 + i];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int f = fo * S + j - P;
+    float2 v = make_float2(0.0f, 0.0f);
+    if (f >= 0 && f < Fr) {
+      v = __ldg(reinterpret_cast<const float2*>(zr + 2 * f));
+      v.x = (v.x - mean) * inv;
+      v.y = (v.y - mean) * inv;
+    }
+    const float4 r0 = *reinterpret_cast<const float4*>(hd_smem + j * C + c0);
+    const float4 r1 = *reinterpret_cast<const float4*>(hd_smem + j * C + c0 + 4);
+    const float4 i0 = *reinterpret_cast<const float4*>(hd_smem + (K + j) * C + c0);
+    const float4 i1 = *reinterpret_cast<const float4*>(hd_smem + (K + j) * C + c0 + 4);
+    // same summation order as before: acc = w_re * x_re + (w_im * x_im + acc)
+    o[0] = fmaf(r0.x, v.x, fmaf(i0.x, v.y, o[0])); o[1] = fmaf(r0.y, v.x, fmaf(i0.y, v.y, o[1]));
+    o[2] = fmaf(r0.z, v.x, fmaf(i0.z, v.y, o[2])); o[3] = fmaf(r0.w, v.x, fmaf(i0.w, v.y, o[3]));
+    o[4] = fmaf(r1.x, v.x, fmaf(i1.x, v.y, o[4])); o[5] = fmaf(r1.y, v.x, fmaf(i1.y, v.y, o[5]));
+    o[6] = fmaf(r1.z, v.x, fmaf(i1.z, v.y, o[6])); o[7] = fmaf(r1.w, v.x, fmaf(i1.w, v.y, o[7]));
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = gelu_exact(o[i]);
   store_split8(ohi, olo, (((size_t)b * Tf + t) * Fo + fo) * C + c0, o);
 }
 
 // ---- last freq decoder, fused: ConvTranspose2d(C -> 2, (k,1), (s,1)) + bias, crop `pad`, de-normalise -> complex Z ----
 // y split [B][T][Fi][C]; Z[b][t][bin] = (convtr(y)[bin + pad][re, im]) * std + mean.  One thread per (t, bin).
+template <int K, int S>
 __global__ void __launch_bounds__(256) final_freq_convtr_kernel(const __nv_bfloat16* __restrict__ yhi, const __nv_bfloat16* __restrict__ ylo,
-                                                                int Tf, int Fi, int C, int K, int S, int pad, int bins,
+                                                                int Tf, int Fi, int C, int pad, int bins,
                                                                 const float* __restrict__ w /*[C][2][K]*/, const float* __restrict__ bias,
                                                                 const float* __restrict__ stats, float2* __restrict__ Z) {
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  extern __shared__ float hd_smem[];  // [K][C + 1] float2 (re, im) weights; the odd row pitch spreads the S tap phases over banks
+  const int pitch = 2 * (C + 1);
+  for (int i = threadIdx.x; i < C * 2 * K; i += blockDim.x) {
+    const int c = i / (2 * K), part = (i / K) & 1, j = i % K;
+    hd_smem[j * pitch + 2 * c + part] = w[i];
+  }
+  __syncthreads();
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
-  if (idx >= (long long)Tf * bins) return;
+  if (idx >= (unsigned)Tf * bins) return;
   const int k = (int)(idx % bins), t = (int)(idx / bins);
   const int pos = k + pad;
   float re = bias[0], im = bias[1];
-  for (int j = pos % S; j < K; j += S) {
+#pragma unroll
+  for (int jj = 0; jj < K / S; ++jj) {
+    const int j = pos % S + jj * S;
     const int i = (pos - j) / S;
     if (i < 0 || i >= Fi) continue;
     const size_t off = (((size_t)b * Tf + t) * Fi + i) * C;
+    const float2* wj = reinterpret_cast<const float2*>(hd_smem + j * pitch);
     for (int c = 0; c < C; c += 8) {
       float u[8];
       load_split8(yhi, ylo, off + c, u);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        re = fmaf(w[((size_t)(c + e) * 2 + 0) * K + j], u[e], re);
-        im = fmaf(w[((size_t)(c + e) * 2 + 1) * K + j], u[e], im);
+        const float2 wv = wj[c + e];
+        re = fmaf(wv.x, u[e], re);
+        im = fmaf(wv.y, u[e], im);
       }
     }
   }
@@ -238,46 +271,94 @@ struct GnApply {
   const __nv_bfloat16* rhi; const __nv_bfloat16* rlo;
   __nv_bfloat16* ohi; __nv_bfloat16* olo; int Xo, Co, x_off;
 };
+__device__ __forceinline__ void ld8f(const float* p, float (&o)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+// VEC: channel counts are multiples of 8, every 8-channel run sits in one group and all vectors are 16-byte aligned
+template <bool VEC>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApply a) {
-  const int groups = a.Co / 8;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const unsigned groups = a.Co / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
-  if (idx >= (long long)a.Y * a.Xo * groups) return;
+  if (idx >= (unsigned)a.Y * a.Xo * groups) return;
   const int c0 = (int)(idx % groups) * 8;
-  const int x = (int)((idx / groups) % a.Xo);
-  const int y = (int)(idx / ((long long)groups * a.Xo));
+  const unsigned pix = idx / groups;
+  const int x = (int)(pix % a.Xo);
+  const int y = (int)(pix / a.Xo);
   const int xr = x + a.x_off;
   const float* r = a.raw + (((size_t)b * a.Y + y) * a.Xr + xr) * a.Cr;
   const int seg = a.per_x ? b * a.Xr + xr : b;
   const int cvalid = a.mode == 2 ? a.Cr / 2 : a.Cr;
   const int cpg = a.Cr / a.G;
   float o[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = c0 + i;
-    float v = 0.0f;
-    if (c < cvalid) {
-      float u = r[c];
+  if (VEC) {
+    if (c0 < cvalid) {
+      ld8f(r + c0, o);
       if (a.stats) {
-        const float* st = a.stats + ((size_t)seg * a.G + c / cpg) * 2;
-        u = (u - st[0]) * st[1] * a.gamma[c] + a.beta[c];
+        const float2 st = *reinterpret_cast<const float2*>(a.stats + ((size_t)seg * a.G + c0 / cpg) * 2);
+        float ga[8], be[8];
+        ld8f(a.gamma + c0, ga);
+        ld8f(a.beta + c0, be);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (o[i] - st.x) * st.y * ga[i] + be[i];
       }
       if (a.mode == 1) {
-        v = gelu_exact(u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = gelu_exact(o[i]);
       } else if (a.mode == 2) {
-        const int c2 = c + cvalid;
-        float gte = r[c2];
+        const int c2 = c0 + cvalid;
+        float gt[8];
+        ld8f(r + c2, gt);
         if (a.stats) {
-          const float* st = a.stats + ((size_t)seg * a.G + c2 / cpg) * 2;
-          gte = (gte - st[0]) * st[1] * a.gamma[c2] + a.beta[c2];
+          const float2 st = *reinterpret_cast<const float2*>(a.stats + ((size_t)seg * a.G + c2 / cpg) * 2);
+          float ga[8], be[8];
+          ld8f(a.gamma + c2, ga);
+          ld8f(a.beta + c2, be);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gt[i] = (gt[i] - st.x) * st.y * ga[i] + be[i];
         }
-        v = u * sigmoidf_acc(gte);
-      } else {
-        v = u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] *= sigmoidf_fast(gt[i]);
       }
-      if (a.scale) v *= a.scale[c];
+      if (a.scale) {
+        float sc[8];
+        ld8f(a.scale + c0, sc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] *= sc[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = 0.0f;
     }
-    o[i] = v;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      float v = 0.0f;
+      if (c < cvalid) {
+        float u = r[c];
+        if (a.stats) {
+          const float* st = a.stats + ((size_t)seg * a.G + c / cpg) * 2;
+          u = (u - st[0]) * st[1] * a.gamma[c] + a.beta[c];
+        }
+        if (a.mode == 1) {
+          v = gelu_exact(u);
+        } else if (a.mode == 2) {
+          const int c2 = c + cvalid;
+          float gte = r[c2];
+          if (a.stats) {
+            const float* st = a.stats + ((size_t)seg * a.G + c2 / cpg) * 2;
+            gte = (gte - st[0]) * st[1] * a.gamma[c2] + a.beta[c2];
+          }
+          v = u * sigmoidf_fast(gte);
+        } else {
+          v = u;
+        }
+        if (a.scale) v *= a.scale[c];
+      }
+      o[i] = v;
+    }
   }
   const size_t off = (((size_t)b * a.Y + y) * a.Xo + x) * a.Co + c0;
   if (a.rhi) {

@@ -280,7 +280,11 @@ struct Runner {
     a.rhi = res ? res->hi : nullptr; a.rlo = res ? res->lo() : nullptr;
     a.ohi = out.hi; a.olo = out.lo(); a.Xo = Xo; a.Co = Co; a.x_off = x_off;
     const long long items = (long long)raw.Y * Xo * (Co / 8);
-    gn_apply_kernel<<<dim3((unsigned)((items + 255) / 256), raw.B), 256, 0, s>>>(a);
+    if (items >= (1LL << 31)) { set_error("gn_apply: item count overflows 32 bits"); rc = 2; return out; }
+    const bool al16 = ((((uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)scale | (uintptr_t)raw.f) & 15) == 0);
+    const bool vec = al16 && Cvalid % 8 == 0 && raw.C % 4 == 0 && (!stats || (raw.C / G) % 8 == 0);
+    if (vec) gn_apply_kernel<true><<<dim3((unsigned)((items + 255) / 256), raw.B), 256, 0, s>>>(a);
+    else gn_apply_kernel<false><<<dim3((unsigned)((items + 255) / 256), raw.B), 256, 0, s>>>(a);
     chk();
     return out;
   }
@@ -435,9 +439,8 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
         tcur = R.split(B, 1, Lo, ch0);
         if (!dry) {
           const long long items = (long long)Lo * (ch0 / 8);
-          time_first_kernel<<<dim3((unsigned)((items + 255) / 256), B), 256, 0, s>>>(xt, T, Lo, ch0, h->cfg.kernel_size, h->cfg.stride,
-                                                                                     h->cfg.kernel_size / 4, HP(h, te + ".conv.weight"),
-                                                                                     HP(h, te + ".conv.bias"), tcur.hi, tcur.lo());
+          time_first_kernel<8><<<dim3((unsigned)((items + 255) / 256), B), 256, (8 + 1) * ch0 * 4, s>>>(
+              xt, T, Lo, ch0, h->cfg.stride, h->cfg.kernel_size / 4, HP(h, te + ".conv.weight"), HP(h, te + ".conv.bias"), tcur.hi, tcur.lo());
           R.chk();
         } else ++R.launches;
       } else if (!last_freq) {
@@ -457,10 +460,9 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
         xcur = R.split(B, le, Fo, ch0);
         if (!dry && R.ok()) {
           const long long items = (long long)le * Fo * (ch0 / 8);
-          freq_first_kernel<<<dim3((unsigned)((items + 255) / 256), B), 256, 0, s>>>(reinterpret_cast<const float*>(Z), st_f, le, bins, Fo, ch0,
-                                                                                     h->cfg.kernel_size, h->cfg.stride, h->cfg.kernel_size / 4,
-                                                                                     HP(h, fe + ".conv.weight"), HP(h, fe + ".conv.bias"),
-                                                                                     xcur.hi, xcur.lo());
+          freq_first_kernel<8><<<dim3((unsigned)((items + 255) / 256), B), 256, (2 * 8 + 1) * ch0 * 4, s>>>(
+              reinterpret_cast<const float*>(Z), st_f, le, bins, Fo, ch0, h->cfg.stride, h->cfg.kernel_size / 4, HP(h, fe + ".conv.weight"),
+              HP(h, fe + ".conv.bias"), xcur.hi, xcur.lo());
           R.chk();
         } else ++R.launches;
       } else if (!normed) {
@@ -556,9 +558,8 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
       float2* Zo = reinterpret_cast<float2*>(R.take((size_t)B * le * bins * 8));
       if (!dry && R.ok()) {
         const long long items = (long long)le * bins;
-        final_freq_convtr_kernel<<<dim3((unsigned)((items + 255) / 256), B), 256, 0, s>>>(y.hi, y.lo(), le, y.X, y.C, ctr.g.k, ctr.g.s, pad, bins,
-                                                                                          HP(h, fd + ".conv_tr.weight"), HP(h, fd + ".conv_tr.bias"),
-                                                                                          st_f, Zo);
+        final_freq_convtr_kernel<8, 4><<<dim3((unsigned)((items + 255) / 256), B), 256, 8 * 2 * (y.C + 1) * 4, s>>>(
+            y.hi, y.lo(), le, y.X, y.C, pad, bins, HP(h, fd + ".conv_tr.weight"), HP(h, fd + ".conv_tr.bias"), st_f, Zo);
         R.chk();
         IstftParams ip{};
         ip.Z = Zo; ip.ldz = bins; ip.mask = nullptr; ip.ldm = 0;

@@ -1,0 +1,187 @@
+"""L5 -- the optimiser half of the reference's training step on the GPU.
+
+Reference: `RemFX.configure_optimizers` (remfx/models.py:185-206) = torch.optim.AdamW(lr 1e-4, betas (0.95, 0.999),
+eps 1e-6, weight_decay 1e-3) + MultiStepLR([0.8, 0.95] * max_steps, gamma 0.1) stepped every batch, with Lightning's
+`gradient_clip_val: 10.0` (cfg/config.yaml:119) and DDP gradient averaging.
+
+Here every parameter / gradient / moment lives in ONE flat fp32 bucket (`FlatBucket`), so a step is
+    [all-reduce(bucket) over NCCL]  ->  rfx_grad_sumsq  ->  rfx_adamw_step   (csrc/optim.cu)
+i.e. one collective and two streaming kernels for the whole model; averaging (1 / world) and the clip coefficient are
+folded into the update kernel.  `FusedAdamW` is a torch.optim.Optimizer, so the reference's MultiStepLR (and Lightning)
+drive it unchanged.  The kernels have no CPU fallback: `step()` on CPU tensors raises RfxError.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+_ALIGN = 64  # elements (256 B): every parameter view starts on a 256-byte boundary of the bucket
+
+
+class FlatBucket:
+    """Flat fp32 storage for a parameter list.  After construction every `p.data` (and `p.grad`) is a view into
+    `self.param` (`self.grad`); padding between views stays zero so whole-bucket kernels are safe."""
+
+    def __init__(self, params: Iterable[Tensor]):
+        self.params: List[Tensor] = [p for p in params]
+        if not self.params:
+            raise ValueError("FlatBucket needs at least one parameter")
+        dev = self.params[0].device
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise ValueError("FlatBucket holds fp32 parameters only (the reference trains in fp32, cfg/config.yaml:112)")
+            if p.device != dev:
+                raise ValueError("all parameters must live on one device")
+        self.offsets: List[int] = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = max(off, _ALIGN)
+        self.param = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                view = self.param[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                old_grad = p.grad
+                p.data = view
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+                if old_grad is not None:
+                    p.grad.copy_(old_grad)
+
+    def grad_view(self, i: int) -> Tensor:
+        p, o = self.params[i], self.offsets[i]
+        return self.grad[o:o + p.numel()].view(p.shape)
+
+    def collect_grads(self) -> None:
+        """Make `self.grad` hold every parameter's gradient: a no-op while `.grad` still aliases the bucket (autograd
+        accumulates in place), a copy for gradients that were re-created (e.g. after zero_grad(set_to_none=True))."""
+        with torch.no_grad():
+            for i, p in enumerate(self.params):
+                view = self.grad_view(i)
+                g = p.grad
+                if g is None:
+                    view.zero_()
+                    p.grad = view
+                elif g.data_ptr() != view.data_ptr():
+                    view.copy_(g)
+                    p.grad = view
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+        for i, p in enumerate(self.params):
+            if p.grad is None or p.grad.data_ptr() != self.grad_view(i).data_ptr():
+                p.grad = self.grad_view(i)
+
+
+def sync_grads(bucket_grad: Tensor, group=None) -> float:
+    """SUM all-reduce of the flat gradient bucket across data-parallel ranks (one collective for the whole model);
+    returns the scale (1 / world) the update kernel folds in.  gloo on CPU in the tests, NCCL over NVLink on the box."""
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized():
+        return 1.0
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 1.0
+    dist.all_reduce(bucket_grad, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
+def multistep_lr(step: int, max_steps: int, base_lr: float = 1e-4, gamma: float = 0.1) -> float:
+    """Learning rate in force for the optimiser update number `step` (0-based count of completed scheduler steps), as
+    MultiStepLR([0.8 * max_steps, 0.95 * max_steps], gamma) stepped every batch yields (remfx/models.py:192-196)."""
+    m1, m2 = 0.8 * max_steps, 0.95 * max_steps
+    return base_lr * (gamma ** (int(step >= m1) + int(step >= m2)))
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """Drop-in for the reference's `torch.optim.AdamW(list(model.parameters()), ...)` with gradient averaging across
+    ranks and clip-by-global-norm folded in.  One parameter group (what the reference builds)."""
+
+    def __init__(self, params, lr: float = 1e-4, betas=(0.95, 0.999), eps: float = 1e-6, weight_decay: float = 1e-3,
+                 max_grad_norm: Optional[float] = 10.0, process_group=None):
+        params = list(params)
+        if params and isinstance(params[0], dict):
+            raise ValueError("FusedAdamW takes a flat parameter list (one group), like the reference")
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.max_grad_norm = max_grad_norm
+        self.process_group = process_group
+        self.bucket = FlatBucket(self.param_groups[0]["params"])
+        dev = self.bucket.param.device
+        self.exp_avg = torch.zeros_like(self.bucket.param)
+        self.exp_avg_sq = torch.zeros_like(self.bucket.param)
+        self.step_count = 0
+        self._ws = torch.zeros(32, dtype=torch.float64, device=dev)      # [0] = sum of squares
+        self.total_norm = torch.zeros(1, dtype=torch.float32, device=dev)  # pre-clip global norm of the last step
+
+    def zero_grad(self, set_to_none: bool = False) -> None:  # gradients stay views of the bucket
+        self.bucket.zero_grad()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        b = self.bucket
+        _lib.require_device(b.param)
+        b.collect_grads()
+        scale = sync_grads(b.grad, self.process_group)
+        g = self.param_groups[0]
+        self.step_count += 1
+        L = _lib.lib()
+        clip = float(self.max_grad_norm) if self.max_grad_norm else 0.0
+        with torch.cuda.device(b.param.device):
+            s = _lib.cur_stream()
+            if clip > 0:
+                _lib.check(L.rfx_grad_sumsq(b.grad.data_ptr(), b.numel, self._ws.data_ptr(), 0, s), "rfx_grad_sumsq")
+            _lib.check(L.rfx_adamw_step(b.param.data_ptr(), b.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                        b.numel, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                                        float(g["weight_decay"]), self.step_count, float(scale), clip, self._ws.data_ptr(),
+                                        self.total_norm.data_ptr(), s), "rfx_adamw_step")
+        return loss
+
+    # state_dict in torch.optim.AdamW's layout (per-parameter exp_avg / exp_avg_sq / step) so checkpoints interchange
+    def state_dict(self):
+        b = self.bucket
+        state = {}
+        for i, (p, o) in enumerate(zip(b.params, b.offsets)):
+            state[i] = {
+                "step": torch.tensor(float(self.step_count)),
+                "exp_avg": self.exp_avg[o:o + p.numel()].view(p.shape).clone(),
+                "exp_avg_sq": self.exp_avg_sq[o:o + p.numel()].view(p.shape).clone(),
+            }
+        g = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        g["params"] = list(range(len(b.params)))
+        return {"state": state, "param_groups": [g]}
+
+    def load_state_dict(self, sd) -> None:
+        b = self.bucket
+        for k, v in sd["param_groups"][0].items():
+            if k != "params":
+                self.param_groups[0][k] = v
+        with torch.no_grad():
+            for i, (p, o) in enumerate(zip(b.params, b.offsets)):
+                st = sd["state"].get(i)
+                if st is None:
+                    continue
+                self.exp_avg[o:o + p.numel()].view(p.shape).copy_(st["exp_avg"])
+                self.exp_avg_sq[o:o + p.numel()].view(p.shape).copy_(st["exp_avg_sq"])
+                self.step_count = int(float(st["step"]))
+
+
+def configure_optimizers(module: torch.nn.Module, max_steps: int, lr: float = 1e-4, lr_beta1: float = 0.95, lr_beta2: float = 0.999,
+                         lr_eps: float = 1e-6, lr_weight_decay: float = 1e-3, gradient_clip_val: float = 10.0, process_group=None):
+    """Same return structure as `RemFX.configure_optimizers` (remfx/models.py:185-206)."""
+    optimizer = FusedAdamW(list(module.parameters()), lr=lr, betas=(lr_beta1, lr_beta2), eps=lr_eps, weight_decay=lr_weight_decay,
+                           max_grad_norm=gradient_clip_val, process_group=process_group)
+    lr_scheduler = torch.optim.lr_scheduler.MultiStepLR(optimizer, [0.8 * max_steps, 0.95 * max_steps], gamma=0.1)
+    return {"optimizer": optimizer,
+            "lr_scheduler": {"scheduler": lr_scheduler, "monitor": "val_loss", "interval": "step", "frequency": 1}}

@@ -97,3 +97,33 @@ def _gloo_selftest_worker(rank: int, world: int, port: int, n_items: int, q) -> 
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
+
+
+def _gloo_optim_worker(rank: int, world: int, port: int, q) -> None:
+    """world_size>1 CPU test of the L5 host logic (tests/test_optim_cpu.py): every rank holds different gradients in its
+    flat bucket; after `sync_grads` the bucket holds the SUM and the returned scale turns it into the DDP mean."""
+    import os
+
+    import torch.distributed as dist
+
+    from .optim import FlatBucket, sync_grads
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+        bucket = FlatBucket(net.parameters())
+        x = torch.randn(4, 7, generator=torch.Generator().manual_seed(100 + rank))
+        net(x).square().sum().backward()   # autograd accumulates straight into the bucket views
+        local = [p.grad.clone() for p in net.parameters()]
+        gathered = [[torch.zeros_like(g) for _ in range(world)] for g in local]
+        for g, outs in zip(local, gathered):
+            dist.all_gather(outs, g)
+        scale = sync_grads(bucket.grad)
+        ok = abs(scale - 1.0 / world) < 1e-12
+        for p, outs in zip(net.parameters(), gathered):
+            ok = ok and torch.allclose(p.grad * scale, sum(outs) / world, rtol=1e-6, atol=1e-7)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
