@@ -97,9 +97,19 @@ int rfx_umx_finalize(rfx_umx_t* h, void* stream);
 size_t rfx_umx_workspace_bytes(const rfx_umx_t* h, int B, int T);
 /* x: (B, 1, T) fp32 device -> out: (B, 1, T) fp32 device.  workspace: >= rfx_umx_workspace_bytes. */
 int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, void* stream);
-/* Same, from / to (pinned) HOST buffers: H2D copy, kernels, D2H copy on `stream`, then a stream sync. */
+/* Same, from / to (pinned) HOST buffers.  The batch travels in up to 4 item chunks on two internal copy streams: the STFT of
+ * chunk c starts as soon as chunk c is in HBM, and each chunk's iSTFT is followed by its own D2H copy, so most of the PCIe
+ * time hides behind the kernels; returns when out_host is complete. */
 int rfx_umx_sample_host(rfx_umx_t* h, const float* x_host, int B, int T, float* out_host, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* Pipelined form of the above: submit returns as soon as the work is enqueued; wait blocks until that slot's out_host is
+ * complete.  Two slots (0, 1) with private device staging inside the workspace: submit(slot k+1) overlaps its H2D with the
+ * kernels of slot k, whose D2H in turn overlaps the kernels of slot k+1.  Re-submitting a slot waits for its previous use.
+ * x_host / out_host must stay valid (and should be pinned) until the matching wait; all submits of one handle must use the
+ * same compute `stream` and the same workspace. */
+int rfx_umx_submit_host(rfx_umx_t* h, int slot, const float* x_host, int B, int T, float* out_host, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int rfx_umx_wait_host(rfx_umx_t* h, int slot);
 /* Number of kernels one rfx_umx_sample call launches (for bench.py's gpu_launches). */
 int rfx_umx_launches_per_call(const rfx_umx_t* h);
 /* Per-stage device timing: when enabled, rfx_umx_sample records a cudaEvent on `stream` between its

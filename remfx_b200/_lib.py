@@ -59,6 +59,8 @@ _SIGNATURES = {
     "rfx_umx_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "rfx_umx_sample": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rfx_umx_sample_host": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rfx_umx_submit_host": (C.c_int, [C.c_void_p, C.c_int, _f32p, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rfx_umx_wait_host": (C.c_int, [C.c_void_p, C.c_int]),
     "rfx_umx_launches_per_call": (C.c_int, [C.c_void_p]),
     "rfx_umx_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "rfx_umx_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),

@@ -74,8 +74,22 @@ struct rfx_umx {
   // optional per-stage timing (cudaEvents recorded on the caller's stream between the launches)
   bool profiling = false;
   std::vector<cudaEvent_t> events;
+  // host-buffer pipeline (rfx_umx_sample_host / submit_host / wait_host): two slots, item-chunked copies on two internal streams
+  static constexpr int kSlots = 2, kChunks = 4;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_in[kSlots][kChunks] = {}, ev_ist[kSlots][kChunks] = {}, ev_out[kSlots] = {};
+  bool pending[kSlots] = {false, false};
 
   ~rfx_umx() {
+    if (copy_in) cudaStreamDestroy(copy_in);
+    if (copy_out) cudaStreamDestroy(copy_out);
+    for (int i = 0; i < kSlots; ++i) {
+      for (int c = 0; c < kChunks; ++c) {
+        if (ev_in[i][c]) cudaEventDestroy(ev_in[i][c]);
+        if (ev_ist[i][c]) cudaEventDestroy(ev_ist[i][c]);
+      }
+      if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+    }
     for (auto e : events) cudaEventDestroy(e);
     for (auto& kv : params) kv.second.release();
     for (int i = 0; i < 3; ++i) { bn_s[i].release(); bn_t[i].release(); }
@@ -91,7 +105,7 @@ namespace {
 // Workspace layout.  Activations between tensor-core layers are split-bf16 planes (hi then lo).
 struct UmxLayout {
   int F, M, lda1, ldm;
-  size_t off_x, off_out, off_Z, off_A1, off_XC, off_G, off_H1, off_H2, off_Y2, off_mask, total;
+  size_t off_x[2], off_out[2], off_Z, off_A1, off_XC, off_G, off_H1, off_H2, off_Y2, off_mask, total;
   size_t plane_A1, plane_XC, plane_H, plane_Y2;  // elements per plane
 };
 
@@ -109,8 +123,10 @@ UmxLayout umx_layout(const rfx_umx* h, int B, int T) {
   L.plane_XC = M * 2 * hid;
   L.plane_H = M * hid;
   L.plane_Y2 = M * hid;
-  L.off_x = take((size_t)B * T * 4);
-  L.off_out = take((size_t)B * T * 4);
+  for (int i = 0; i < 2; ++i) {  // device staging of the host-buffer entry points (one pair per pipeline slot)
+    L.off_x[i] = take((size_t)B * T * 4);
+    L.off_out[i] = take((size_t)B * T * 4);
+  }
   L.off_Z = take(M * h->bins * 8);
   L.off_A1 = take(L.plane_A1 * 2 * 2);
   L.off_XC = take(L.plane_XC * 2 * 2);
@@ -246,7 +262,22 @@ size_t rfx_umx_workspace_bytes(const rfx_umx_t* h, int B, int T) {
 
 int rfx_umx_launches_per_call(const rfx_umx_t* h) { return h ? 5 + 2 * h->cfg.nb_layers : 0; }
 
+namespace {
+// Host-buffer plan of one call: inputs arrive in item chunks on the copy-in stream (ev_in[c] fires when chunk c is in HBM), the
+// STFT of chunk c waits only for that event; each chunk's iSTFT is followed by its own D2H on the copy-out stream.
+struct HostIO {
+  const float* x_host; float* out_host;
+  int slot;
+};
+int umx_forward(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, void* stream, const HostIO* io);
+}  // namespace
+
 int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return umx_forward(h, x, B, T, out, workspace, workspace_bytes, stream, nullptr);
+}
+
+namespace {
+int umx_forward(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, void* stream, const HostIO* io) {
   RFX_REQUIRE(h && x && out && workspace, "null argument");
   RFX_REQUIRE(h->finalized, "rfx_umx_finalize has not been called since the last parameter load");
   RFX_REQUIRE(B > 0 && T > h->cfg.n_fft / 2, "need B > 0 and T > n_fft/2 (reflect padding)");
@@ -292,7 +323,25 @@ int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void*
   sp.Z = Z; sp.ldz = h->bins; sp.A = nullptr; sp.lda = 0;
   sp.Ahi = A1; sp.Alo = A1 + L.plane_A1; sp.ldas = L.lda1;
   sp.in_mean = P(h, "input_mean"); sp.in_scale = P(h, "input_scale");
-  if ((rc = launch_stft(sp, B, s)) || (rc = mark())) return rc;
+  const int nch = io ? std::min(B, (int)rfx_umx::kChunks) : 1;
+  for (int c = 0; c < nch; ++c) {
+    const int i0 = (int)((long long)B * c / nch), i1 = (int)((long long)B * (c + 1) / nch);
+    if (io) {
+      RFX_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(x) + (size_t)i0 * T, io->x_host + (size_t)i0 * T, (size_t)(i1 - i0) * T * 4,
+                                     cudaMemcpyHostToDevice, h->copy_in));
+      RFX_CHECK_CUDA(cudaEventRecord(h->ev_in[io->slot][c], h->copy_in));
+    }
+  }
+  for (int c = 0; c < nch; ++c) {
+    const int i0 = (int)((long long)B * c / nch), i1 = (int)((long long)B * (c + 1) / nch);
+    StftParams sc = sp;
+    sc.x = x + (size_t)i0 * T;
+    sc.Z = Z + (size_t)i0 * L.F * h->bins;
+    sc.Ahi = A1 + (size_t)i0 * L.F * L.lda1; sc.Alo = sc.Ahi + L.plane_A1;
+    if (io) RFX_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_in[io->slot][c], 0));
+    if ((rc = launch_stft(sc, i1 - i0, s))) return rc;
+  }
+  if ((rc = mark())) return rc;
 
   // (2) fc1 + bn1 + tanh (model.py:132-138) -> first half of the skip-concat buffer
   Epilogue e1; e1.s1 = h->bn_s[0].p; e1.t1 = h->bn_t[0].p; e1.act = ACT_TANH;
@@ -325,9 +374,39 @@ int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void*
   ip.n_fft = h->cfg.n_fft; ip.hop = h->cfg.hop; ip.F = L.F; ip.length = T;
   ip.frame_off = h->cfg.n_fft / 2; ip.env_pad = 0; ip.nbins = h->bins;
   ip.scale = 1.0f; ip.out = out; ip.out_bstride = T; ip.hops_per_cta = 16;
-  if ((rc = launch_istft(ip, B, s)) || (rc = mark())) return rc;
+  for (int c = 0; c < nch; ++c) {
+    const int i0 = (int)((long long)B * c / nch), i1 = (int)((long long)B * (c + 1) / nch);
+    IstftParams ic = ip;
+    ic.Z = Z + (size_t)i0 * L.F * h->bins;
+    ic.mask = mask + (size_t)i0 * L.F * L.ldm;
+    ic.out = out + (size_t)i0 * T;
+    if ((rc = launch_istft(ic, i1 - i0, s))) return rc;
+    if (io) {
+      RFX_CHECK_CUDA(cudaEventRecord(h->ev_ist[io->slot][c], s));
+      RFX_CHECK_CUDA(cudaStreamWaitEvent(h->copy_out, h->ev_ist[io->slot][c], 0));
+      RFX_CHECK_CUDA(cudaMemcpyAsync(io->out_host + (size_t)i0 * T, out + (size_t)i0 * T, (size_t)(i1 - i0) * T * 4, cudaMemcpyDeviceToHost,
+                                     h->copy_out));
+    }
+  }
+  if (io) RFX_CHECK_CUDA(cudaEventRecord(h->ev_out[io->slot], h->copy_out));
+  if ((rc = mark())) return rc;
   return 0;
 }
+
+int umx_host_setup(rfx_umx_t* h) {
+  if (h->copy_in) return 0;
+  RFX_CHECK_CUDA(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+  RFX_CHECK_CUDA(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+  for (int i = 0; i < rfx_umx::kSlots; ++i) {
+    for (int c = 0; c < rfx_umx::kChunks; ++c) {
+      RFX_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_in[i][c], cudaEventDisableTiming));
+      RFX_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_ist[i][c], cudaEventDisableTiming));
+    }
+    RFX_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+  }
+  return 0;
+}
+}  // namespace
 
 int rfx_umx_set_profiling(rfx_umx_t* h, int on) {
   RFX_REQUIRE(h, "null handle");
@@ -345,21 +424,38 @@ int rfx_umx_stage_times(rfx_umx_t* h, float* ms, int capacity, int* n_out) {
   return 0;
 }
 
-int rfx_umx_sample_host(rfx_umx_t* h, const float* x_host, int B, int T, float* out_host, void* workspace, size_t workspace_bytes,
+int rfx_umx_wait_host(rfx_umx_t* h, int slot) {
+  RFX_REQUIRE(h && slot >= 0 && slot < rfx_umx::kSlots, "bad handle / slot");
+  if (h->pending[slot]) {
+    RFX_CHECK_CUDA(cudaEventSynchronize(h->ev_out[slot]));
+    h->pending[slot] = false;
+  }
+  return 0;
+}
+
+int rfx_umx_submit_host(rfx_umx_t* h, int slot, const float* x_host, int B, int T, float* out_host, void* workspace, size_t workspace_bytes,
                         void* stream) {
   RFX_REQUIRE(h && x_host && out_host && workspace, "null argument");
+  RFX_REQUIRE(slot >= 0 && slot < rfx_umx::kSlots, "slot must be 0 or 1");
+  RFX_REQUIRE(B > 0 && T > 0, "positive sizes");
   const UmxLayout L = umx_layout(h, B, T);
   RFX_REQUIRE(workspace_bytes >= L.total, "workspace too small (see rfx_umx_workspace_bytes)");
-  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if ((rc = umx_host_setup(h)) || (rc = rfx_umx_wait_host(h, slot))) return rc;  // the slot's staging buffers must be free
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  float* xd = reinterpret_cast<float*>(ws + L.off_x);
-  float* od = reinterpret_cast<float*>(ws + L.off_out);
-  RFX_CHECK_CUDA(cudaMemcpyAsync(xd, x_host, (size_t)B * T * 4, cudaMemcpyHostToDevice, s));
-  int rc = rfx_umx_sample(h, xd, B, T, od, workspace, workspace_bytes, stream);
+  HostIO io{x_host, out_host, slot};
+  rc = umx_forward(h, reinterpret_cast<float*>(ws + L.off_x[slot]), B, T, reinterpret_cast<float*>(ws + L.off_out[slot]), workspace,
+                   workspace_bytes, stream, &io);
   if (rc) return rc;
-  RFX_CHECK_CUDA(cudaMemcpyAsync(out_host, od, (size_t)B * T * 4, cudaMemcpyDeviceToHost, s));
-  RFX_CHECK_CUDA(cudaStreamSynchronize(s));
+  h->pending[slot] = true;
   return 0;
+}
+
+int rfx_umx_sample_host(rfx_umx_t* h, const float* x_host, int B, int T, float* out_host, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  int rc = rfx_umx_submit_host(h, 0, x_host, B, T, out_host, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return rfx_umx_wait_host(h, 0);
 }
 
 int rfx_umx_debug_tap(rfx_umx_t* h, int what, const void* workspace, int B, int T, float* dst, int* ld, void* stream) {

@@ -140,6 +140,8 @@ class OpenUnmixModel(nn.Module):
     def _workspace(self, h, B: int, T: int, device) -> Tensor:
         need = _lib.lib().rfx_umx_workspace_bytes(h, B, T)
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            for slot in (0, 1):  # in-flight host-pipeline calls still use the old workspace
+                _lib.check(_lib.lib().rfx_umx_wait_host(h, slot), "rfx_umx_wait_host")
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
         return self._ws
 
@@ -177,6 +179,30 @@ class OpenUnmixModel(nn.Module):
                                                 _lib.cur_stream())
             _lib.check(rc, "rfx_umx_sample_host")
         return out_host
+
+    def submit_host(self, x_host: Tensor, out_host: Tensor, slot: int = 0, device="cuda:0") -> None:
+        """Pipelined `sample_host`: enqueue H2D + kernels + D2H for this batch and return; `wait_host(slot)` blocks until
+        `out_host` is complete.  Two slots: submitting slot 1 while slot 0 is in flight overlaps the copies of one batch with
+        the kernels of the other.  Both tensors must be pinned and stay alive until the wait."""
+        if x_host.is_cuda or x_host.dim() != 3 or x_host.shape[1] != 1 or x_host.dtype != torch.float32 or not x_host.is_contiguous():
+            raise ValueError("expected a contiguous float32 CPU tensor of shape (batch, 1, time)")
+        if out_host.is_cuda or out_host.shape != x_host.shape or out_host.dtype != torch.float32 or not out_host.is_contiguous():
+            raise ValueError("out_host must be a contiguous float32 CPU tensor shaped like x_host")
+        if not (x_host.is_pinned() and out_host.is_pinned()):
+            raise ValueError("submit_host needs pinned host tensors (pageable memory would make the copies synchronous)")
+        device = torch.device(device)
+        B, _, T = x_host.shape
+        with torch.cuda.device(device):
+            h = self._sync(device)
+            ws = self._workspace(h, B, T, device)
+            rc = _lib.lib().rfx_umx_submit_host(h, int(slot), x_host.data_ptr(), B, T, out_host.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                _lib.cur_stream())
+            _lib.check(rc, "rfx_umx_submit_host")
+
+    def wait_host(self, slot: int = 0) -> None:
+        h = self.__dict__.get("_handle")
+        if h:
+            _lib.check(_lib.lib().rfx_umx_wait_host(h, int(slot)), "rfx_umx_wait_host")
 
     def forward(self, batch):
         """(x, target) -> (loss, sep_out) with loss = MRSTFT + 100 * L1 (models.py:294-301)."""

@@ -48,6 +48,24 @@ def test_sample_host_equals_device_path():
     assert torch.equal(a, b)
 
 
+def test_host_pipeline_slots_match_device_path():
+    """submit_host / wait_host: two batches in flight (different inputs, 7 items -> ragged 4-chunk split) give bit-identical
+    results to the device path, also when a slot is re-used."""
+    sd = weights.umx_state(7)
+    m = _model(sd)
+    xs = [weights.synth_audio(60 + i, 7, 16384).pin_memory() for i in range(5)]
+    want = [m.sample(x.cuda()).cpu() for x in xs]
+    outs = [torch.empty_like(x).pin_memory() for x in xs]
+    for i, x in enumerate(xs):
+        m.submit_host(x, outs[i], i % 2)
+    m.wait_host(0)
+    m.wait_host(1)
+    for o, w in zip(outs, want):
+        assert torch.equal(o, w)
+    with pytest.raises(ValueError):
+        m.submit_host(weights.synth_audio(1, 2, 16384), outs[0][:2], 0)   # pageable memory is refused
+
+
 def test_items_are_independent():
     """Size-independent property: the path is per-item, so batching must not change an item's output."""
     sd = weights.umx_state(7)
