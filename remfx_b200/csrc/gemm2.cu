@@ -164,41 +164,203 @@ __device__ __forceinline__ void load8(const float* vec, int n, float fill, bool 
   }
 }
 
-__device__ __forceinline__ void g2_epi8(float (&v)[8], int n, const G2Params& p, bool aligned) {
-  float s[8], t[8];
-  load8(p.s1, n, 1.0f, aligned, s);
-  load8(p.t1, n, 0.0f, aligned, t);
+template <int ACT>
+__device__ __forceinline__ float g2_act(float v, float slope) {
+  if (ACT == ACT_TANH) return tanhf(v);
+  if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
+  if (ACT == ACT_SIGMOID) return sigmoidf_acc(v);
+  if (ACT == ACT_PRELU) return v >= 0.0f ? v : v * slope;
+  if (ACT == ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // exact erf form (torch F.gelu default)
+  return v;  // ACT_NONE; ACT_GLU_PAIR is resolved by the caller (needs pairs of columns)
+}
+
+struct G2Row {  // where this thread's output row lives
+  float* cf;
+  __nv_bfloat16* chi;
+  __nv_bfloat16* clo;
+  bool cf_vec, cs_vec, vec_al;
+};
+
+// One full 32-column chunk [nb, nb + 32) of this thread's row, activation known at compile time: straight-line code, so the
+// compiler hoists every scale / bias load to the top and the instruction cache only holds the variant in use.
+// gs / gss accumulate the fused GroupNorm statistics when GN is set.
+template <int ACT, bool DUAL, bool GN>
+__device__ __forceinline__ void g2_chunk(const uint32_t (&v)[32], const uint32_t (&v2)[32], int nb, const G2Params& p, const G2Row& r, float& gs,
+                                         float& gss) {
+  float o[32];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], s[i], t[i]);
-  if (p.s2 || p.t2) {
-    load8(p.s2, n, 1.0f, aligned, s);
-    load8(p.t2, n, 0.0f, aligned, t);
+  for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
+  if (p.s1) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], s[i], t[i]);
+    for (int j = 0; j < 4; ++j) {
+      float sc[8];
+      load8(p.s1, nb + 8 * j, 1.0f, r.vec_al, sc);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[8 * j + i] *= sc[i];
+    }
   }
-  switch (p.act) {
-    case ACT_TANH:
+  if (p.t1) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = tanhf(v[i]);
-      break;
-    case ACT_RELU:
+    for (int j = 0; j < 4; ++j) {
+      float sh[8];
+      load8(p.t1, nb + 8 * j, 0.0f, r.vec_al, sh);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
-      break;
-    case ACT_SIGMOID:
+      for (int i = 0; i < 8; ++i) o[8 * j + i] += sh[i];
+    }
+  }
+  if (p.s2 || p.t2) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = sigmoidf_acc(v[i]);
-      break;
-    case ACT_PRELU:
-      load8(p.slope, n, 0.0f, aligned, s);
+    for (int j = 0; j < 4; ++j) {
+      float sc[8], sh[8];
+      load8(p.s2, nb + 8 * j, 1.0f, r.vec_al, sc);
+      load8(p.t2, nb + 8 * j, 0.0f, r.vec_al, sh);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = v[i] >= 0.0f ? v[i] : v[i] * s[i];
-      break;
-    case ACT_GELU:  // exact erf form (torch F.gelu default)
+      for (int i = 0; i < 8; ++i) o[8 * j + i] = fmaf(o[8 * j + i], sc[i], sh[i]);
+    }
+  }
+  if (ACT == ACT_PRELU) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752440f));
-      break;
-    default: break;  // ACT_GLU_PAIR is resolved by the caller (needs pairs of columns)
+    for (int j = 0; j < 4; ++j) {
+      float sl[8];
+      load8(p.slope, nb + 8 * j, 0.0f, r.vec_al, sl);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[8 * j + i] = g2_act<ACT_PRELU>(o[8 * j + i], sl[i]);
+    }
+  } else if (ACT != ACT_NONE && ACT != ACT_GLU_PAIR) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = g2_act<ACT>(o[i], 0.0f);
+  }
+  if (DUAL) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(v2[i]);
+  }
+  if (GN) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { gs += o[i]; gss = fmaf(o[i], o[i], gss); }
+  }
+  if (ACT == ACT_GLU_PAIR) {  // (value, gate) column pairs -> 16 output columns starting at nb / 2
+    float g[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) g[i] = o[2 * i] * sigmoidf_fast(o[2 * i + 1]);
+    const int c0 = nb >> 1;
+    if (r.cf) {
+      if (r.cf_vec) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(r.cf + c0 + 4 * i) = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r.cf[c0 + i] = g[i];
+      }
+    }
+    if (r.chi) {
+      uint32_t ph[8], pl[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(g[2 * i], g[2 * i + 1]);
+        const float2 hf = __bfloat1622float2(h2);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(g[2 * i] - hf.x, g[2 * i + 1] - hf.y);
+        ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+      if (r.cs_vec) {  // 16 columns = 32 bytes per plane; c0 is a multiple of 16
+        *reinterpret_cast<uint4*>(r.chi + c0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        *reinterpret_cast<uint4*>(r.chi + c0 + 8) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+        *reinterpret_cast<uint4*>(r.clo + c0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        *reinterpret_cast<uint4*>(r.clo + c0 + 8) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          *reinterpret_cast<uint32_t*>(r.chi + c0 + 2 * i) = ph[i];
+          *reinterpret_cast<uint32_t*>(r.clo + c0 + 2 * i) = pl[i];
+        }
+      }
+    }
+    return;
+  }
+  if (r.cf) {
+    if (r.cf_vec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(r.cf + nb + 4 * i) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r.cf[nb + i] = o[i];
+    }
+  }
+  if (r.chi) {
+    uint32_t ph[16], pl[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+      const float2 hf = __bfloat1622float2(h2);
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(o[2 * i] - hf.x, o[2 * i + 1] - hf.y);
+      ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
+      pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    if (r.cs_vec) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        *reinterpret_cast<uint4*>(r.chi + nb + 8 * i) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+        *reinterpret_cast<uint4*>(r.clo + nb + 8 * i) = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        r.chi[nb + i] = __ushort_as_bfloat16((unsigned short)((ph[i >> 1] >> (16 * (i & 1))) & 0xffffu));
+        r.clo[nb + i] = __ushort_as_bfloat16((unsigned short)((pl[i >> 1] >> (16 * (i & 1))) & 0xffffu));
+      }
+    }
+  }
+}
+
+// Ragged chunks (N % 32 != 0, or an activation without a specialised path): per-column code with run-time switches that
+// reads the accumulator one column at a time (run-time TMEM address, no register arrays).  Warp-collective: every lane of
+// the warp must call it; only lanes with row_ok store.
+template <bool DUAL>
+__device__ __forceinline__ void g2_chunk_ragged(uint32_t taddr, uint32_t taddr2, int nb, const G2Params& p, const G2Row& r, bool row_ok, float& gs,
+                                             float& gss) {
+  const int ncol = min(32, p.N - nb);
+  float prev = 0.0f;
+#pragma unroll 1
+  for (int i = 0; i < ncol; ++i) {
+    const int n = nb + i;
+    const uint32_t a1 = tmem_ld1(taddr + i);
+    const uint32_t a2 = DUAL ? tmem_ld1(taddr2 + i) : 0u;
+    tmem_ld_wait();
+    if (!row_ok) continue;
+    float val = fmaf(__uint_as_float(a1), p.s1 ? p.s1[n] : 1.0f, p.t1 ? p.t1[n] : 0.0f);
+    if (p.s2 || p.t2) val = fmaf(val, p.s2 ? p.s2[n] : 1.0f, p.t2 ? p.t2[n] : 0.0f);
+    switch (p.act) {
+      case ACT_TANH: val = tanhf(val); break;
+      case ACT_RELU: val = fmaxf(val, 0.0f); break;
+      case ACT_SIGMOID: val = sigmoidf_acc(val); break;
+      case ACT_PRELU: val = val >= 0.0f ? val : val * p.slope[n]; break;
+      case ACT_GELU: val = 0.5f * val * (1.0f + erff(val * 0.70710678118654752440f)); break;
+      default: break;
+    }
+    if (DUAL) val += __uint_as_float(a2);
+    if (p.gn_acc) { gs += val; gss = fmaf(val, val, gss); }
+    if (p.act == ACT_GLU_PAIR) {
+      if (i & 1) {
+        const float gv = prev * sigmoidf_fast(val);
+        const int c = n >> 1;
+        if (r.cf) r.cf[c] = gv;
+        if (r.chi) {
+          __nv_bfloat16 h, l;
+          split_bf16(gv, h, l);
+          r.chi[c] = h;
+          r.clo[c] = l;
+        }
+      }
+      prev = val;
+      continue;
+    }
+    if (r.cf) r.cf[n] = val;
+    if (r.chi) {
+      __nv_bfloat16 h, l;
+      split_bf16(val, h, l);
+      r.chi[n] = h;
+      r.clo[n] = l;
+    }
   }
 }
 
@@ -329,9 +491,11 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
       float* cf = p.Cf ? p.Cf + (size_t)b * p.bscf + (size_t)py * p.ldcy_f + (size_t)px * p.ldcf : nullptr;
       __nv_bfloat16* chi = p.Chi ? p.Chi + (size_t)b * p.bscs + (size_t)py * p.ldcy_s + (size_t)px * p.ldcs : nullptr;
       __nv_bfloat16* clo = p.Clo ? p.Clo + (size_t)b * p.bscs + (size_t)py * p.ldcy_s + (size_t)px * p.ldcs : nullptr;
-      const bool cf_vec = cf && ((p.ldcf & 3) == 0) && ((p.bscf & 3) == 0) && ((p.ldcy_f & 3) == 0) && (((uintptr_t)p.Cf & 15) == 0);
-      const bool cs_vec = chi && ((p.ldcs & 7) == 0) && ((p.bscs & 7) == 0) && ((p.ldcy_s & 7) == 0) && (((uintptr_t)p.Chi & 15) == 0) &&
-                          (((uintptr_t)p.Clo & 15) == 0);
+      G2Row row;
+      row.cf = cf; row.chi = chi; row.clo = clo; row.vec_al = vec_al;
+      row.cf_vec = cf && ((p.ldcf & 3) == 0) && ((p.bscf & 3) == 0) && ((p.ldcy_f & 3) == 0) && (((uintptr_t)p.Cf & 15) == 0);
+      row.cs_vec = chi && ((p.ldcs & 7) == 0) && ((p.bscs & 7) == 0) && ((p.ldcy_s & 7) == 0) && (((uintptr_t)p.Chi & 15) == 0) &&
+                   (((uintptr_t)p.Clo & 15) == 0);
       float gs = 0.0f, gss = 0.0f;  // running GroupNorm sums of this thread's row for the current group
       int gcur = -1;
       auto gn_flush = [&]() {
@@ -349,130 +513,40 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
 #pragma unroll 1
       for (int cc = 0; cc < CH; ++cc) {
         const int c = half * CH + cc;
-        if (p.gn_acc) {  // chunk-uniform (hence warp-uniform) group id; flush when it changes
-          const int nbq = n0 + c * 32;
-          const int gnew = nbq < p.N ? ((nbq % p.gn_cmod) / p.gn_cpg) : gcur;
+        const int nb = n0 + c * 32;
+        if (!DUAL && p.gn_acc) {  // chunk-uniform (hence warp-uniform) group id; flush when it changes
+          const int gnew = nb < p.N ? ((nb % p.gn_cmod) / p.gn_cpg) : gcur;
           if (gnew != gcur) { gn_flush(); gcur = gnew; }
+        }
+        if (nb >= p.N) continue;  // warp-uniform: nothing to drain
+        const bool generic = (nb + 32 > p.N) || (DUAL && p.act != ACT_PRELU);  // warp-uniform
+        if (generic) {
+          g2_chunk_ragged<DUAL>(trow + c * 32, trow + BN + c * 32, nb, p, row, row_ok, gs, gss);
+          continue;
         }
         uint32_t v[32];
         tmem_ld32(trow + c * 32, v);
         uint32_t v2[32];
         if (DUAL) tmem_ld32(trow + BN + c * 32, v2);
         tmem_ld_wait();
-        const int nb = n0 + c * 32;
-        if (row_ok && nb < p.N) {
-          const bool full = nb + 32 <= p.N;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int n8 = nb + 8 * j;
-            if (n8 >= p.N) break;
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[8 * j + i]);
-            if (full) {
-              g2_epi8(o, n8, p, vec_al);
-            } else {  // ragged last chunk (at most one per output row): per-column slow path
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int n = n8 + i < p.N ? n8 + i : p.N - 1;
-                float val = fmaf(o[i], p.s1 ? p.s1[n] : 1.0f, p.t1 ? p.t1[n] : 0.0f);
-                if (p.s2 || p.t2) val = fmaf(val, p.s2 ? p.s2[n] : 1.0f, p.t2 ? p.t2[n] : 0.0f);
-                switch (p.act) {
-                  case ACT_TANH: val = tanhf(val); break;
-                  case ACT_RELU: val = fmaxf(val, 0.0f); break;
-                  case ACT_SIGMOID: val = sigmoidf_acc(val); break;
-                  case ACT_PRELU: val = val >= 0.0f ? val : val * p.slope[n]; break;
-                  case ACT_GELU: val = 0.5f * val * (1.0f + erff(val * 0.70710678118654752440f)); break;
-                  default: break;
-                }
-                o[i] = val;
-              }
-            }
-            if (DUAL) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] += __uint_as_float(v2[8 * j + i]);
-            }
-            if (p.gn_acc) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (full || n8 + i < p.N) { gs += o[i]; gss += o[i] * o[i]; }
-            }
-            if (p.act == ACT_GLU_PAIR) {  // (value, gate) column pairs -> 4 output columns starting at n8 / 2
-              float g4[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) g4[i] = o[2 * i] * sigmoidf_fast(o[2 * i + 1]);
-              const int c4 = n8 >> 1;
-              const int Nout = p.N >> 1;
-              if (cf) {
-                if (c4 + 4 <= Nout && cf_vec) {
-                  *reinterpret_cast<float4*>(cf + c4) = make_float4(g4[0], g4[1], g4[2], g4[3]);
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i)
-                    if (c4 + i < Nout) cf[c4 + i] = g4[i];
-                }
-              }
-              if (chi) {
-                uint32_t ph2[2], pl2[2];
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(g4[2 * i], g4[2 * i + 1]);
-                  const float2 hf = __bfloat1622float2(h2);
-                  const __nv_bfloat162 l2 = __floats2bfloat162_rn(g4[2 * i] - hf.x, g4[2 * i + 1] - hf.y);
-                  ph2[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                  pl2[i] = *reinterpret_cast<const uint32_t*>(&l2);
-                }
-                if (c4 + 4 <= Nout && ((p.ldcs & 3) == 0) && ((p.bscs & 3) == 0) && ((p.ldcy_s & 3) == 0) && (((uintptr_t)p.Chi & 7) == 0) &&
-                    (((uintptr_t)p.Clo & 7) == 0)) {
-                  *reinterpret_cast<uint2*>(chi + c4) = make_uint2(ph2[0], ph2[1]);
-                  *reinterpret_cast<uint2*>(clo + c4) = make_uint2(pl2[0], pl2[1]);
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i)
-                    if (c4 + i < Nout) {
-                      chi[c4 + i] = reinterpret_cast<const __nv_bfloat16*>(ph2)[i];
-                      clo[c4 + i] = reinterpret_cast<const __nv_bfloat16*>(pl2)[i];
-                    }
-                }
-              }
-              continue;
-            }
-            if (cf) {
-              if (full && cf_vec) {
-                *reinterpret_cast<float4*>(cf + n8) = make_float4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<float4*>(cf + n8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  if (n8 + i < p.N) cf[n8 + i] = o[i];
-              }
-            }
-            if (chi) {
-              uint32_t ph[4], pl[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-                const float2 hf = __bfloat1622float2(h2);
-                const __nv_bfloat162 l2 = __floats2bfloat162_rn(o[2 * i] - hf.x, o[2 * i + 1] - hf.y);
-                ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
-              }
-              if (full && cs_vec) {
-                *reinterpret_cast<uint4*>(chi + n8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                *reinterpret_cast<uint4*>(clo + n8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  if (n8 + i < p.N) {
-                    chi[n8 + i] = reinterpret_cast<const __nv_bfloat16*>(ph)[i];
-                    clo[n8 + i] = reinterpret_cast<const __nv_bfloat16*>(pl)[i];
-                  }
-              }
-            }
+        if (!row_ok) continue;
+        if (DUAL) {
+          g2_chunk<ACT_PRELU, true, false>(v, v2, nb, p, row, gs, gss);
+        } else if (p.gn_acc) {
+          g2_chunk<ACT_NONE, false, true>(v, v2, nb, p, row, gs, gss);
+        } else {
+          switch (p.act) {
+            case ACT_TANH: g2_chunk<ACT_TANH, false, false>(v, v2, nb, p, row, gs, gss); break;
+            case ACT_RELU: g2_chunk<ACT_RELU, false, false>(v, v2, nb, p, row, gs, gss); break;
+            case ACT_SIGMOID: g2_chunk<ACT_SIGMOID, false, false>(v, v2, nb, p, row, gs, gss); break;
+            case ACT_PRELU: g2_chunk<ACT_PRELU, false, false>(v, v2, nb, p, row, gs, gss); break;
+            case ACT_GELU: g2_chunk<ACT_GELU, false, false>(v, v2, nb, p, row, gs, gss); break;
+            case ACT_GLU_PAIR: g2_chunk<ACT_GLU_PAIR, false, false>(v, v2, nb, p, row, gs, gss); break;
+            default: g2_chunk<ACT_NONE, false, false>(v, v2, nb, p, row, gs, gss); break;
           }
         }
       }
-      if (p.gn_acc) gn_flush();
+      if (!DUAL && p.gn_acc) gn_flush();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
