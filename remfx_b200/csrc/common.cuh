@@ -132,11 +132,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
-// one fp32 column of the accumulator (32 lanes x 1 column): used by the ragged-tail epilogue with a run-time column address
-__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
-  uint32_t r;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-  return r;
+// 8 consecutive fp32 columns of the accumulator (32 lanes x 8 columns): the ragged-tail epilogue walks a chunk in groups of 8
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -199,6 +200,22 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// GELU (exact-erf form, torch F.gelu default) without erff: Abramowitz-Stegun 7.1.26 for erfc(z) = poly(t) exp(-z^2),
+// t = 1 / (1 + p z), evaluated on |x| and mirrored so the negative tail 0.5 x erfc(|x| / sqrt 2) has no cancellation.
+// Branch-free, 2 MUFU + ~12 FP32; |error| <= 3.4e-7 absolute (7.6e-8 rms) over [-12, 12] (tools/ check in DESIGN.md).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+  const float h = 0.5f * x * (poly * e);  // 0.5 x erfc(|x| / sqrt 2)
+  return x >= 0.0f ? x - h : h;
+}
 // GLU gates: ex2.approx + rcp.approx, ~1e-6 relative (2 MUFU + 3 FP32 instead of ~14 instructions)
 __device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 

@@ -29,6 +29,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 namespace rfx {
@@ -126,6 +127,14 @@ struct G2Params {
   int N;           // valid output columns
   int batch;       // batch items (grid tiles = batch * m_tiles * n_tiles)
   int m_tiles, n_tiles;
+  // shared-memory plan (host-chosen): [resident W: w_res_bytes][stages x stage_bytes][barriers]
+  int stages;      // ring depth (2..G2_MAX_STAGES)
+  int stage_bytes; // A tile (+ W tile when W is not resident); multiple of 1024
+  int b_bytes;     // one W k-block: 2 planes x n_box rows x 64 columns bf16
+  int n_box;       // W rows per TMA box (= BN, or the 16-rounded N when a single n-tile covers the output)
+  int w_res_bytes; // > 0: all KB k-blocks of W stay in shared memory for the whole kernel (loaded once); needs n_tiles == 1
+  int dbg_skip;    // timing experiments only (RFX_G2_DEBUG_SKIP): 1 = load W only for the first k-block of a tile, 2 = same for A
+  int ktap;        // valid K per tap (the last 64-wide block of a tap may be partial: its dead 16-wide steps are skipped)
   int kb_per_tap;  // 64-wide K blocks per tap
   int taps;
   int dx[16], dy[16];  // A origin offset of each tap
@@ -170,7 +179,7 @@ __device__ __forceinline__ float g2_act(float v, float slope) {
   if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
   if (ACT == ACT_SIGMOID) return sigmoidf_acc(v);
   if (ACT == ACT_PRELU) return v >= 0.0f ? v : v * slope;
-  if (ACT == ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // exact erf form (torch F.gelu default)
+  if (ACT == ACT_GELU) return gelu_fast(v);  // erf form (torch F.gelu default)
   return v;  // ACT_NONE; ACT_GLU_PAIR is resolved by the caller (needs pairs of columns)
 }
 
@@ -312,54 +321,88 @@ __device__ __forceinline__ void g2_chunk(const uint32_t (&v)[32], const uint32_t
   }
 }
 
-// Ragged chunks (N % 32 != 0, or an activation without a specialised path): per-column code with run-time switches that
-// reads the accumulator one column at a time (run-time TMEM address, no register arrays).  Warp-collective: every lane of
-// the warp must call it; only lanes with row_ok store.
+// Ragged chunks (N % 32 != 0, or an activation without a specialised path): groups of 8 columns with per-column bounds
+// predicates and run-time switches.  Warp-collective (tcgen05.ld): every lane must call it; only lanes with row_ok store.
 template <bool DUAL>
 __device__ __forceinline__ void g2_chunk_ragged(uint32_t taddr, uint32_t taddr2, int nb, const G2Params& p, const G2Row& r, bool row_ok, float& gs,
                                              float& gss) {
   const int ncol = min(32, p.N - nb);
-  float prev = 0.0f;
 #pragma unroll 1
-  for (int i = 0; i < ncol; ++i) {
-    const int n = nb + i;
-    const uint32_t a1 = tmem_ld1(taddr + i);
-    const uint32_t a2 = DUAL ? tmem_ld1(taddr2 + i) : 0u;
+  for (int g8 = 0; g8 < ncol; g8 += 8) {
+    uint32_t a1[8], a2[8];
+    tmem_ld8(taddr + g8, a1);
+    if (DUAL) tmem_ld8(taddr2 + g8, a2);
     tmem_ld_wait();
     if (!row_ok) continue;
-    float val = fmaf(__uint_as_float(a1), p.s1 ? p.s1[n] : 1.0f, p.t1 ? p.t1[n] : 0.0f);
-    if (p.s2 || p.t2) val = fmaf(val, p.s2 ? p.s2[n] : 1.0f, p.t2 ? p.t2[n] : 0.0f);
+    const int n8 = nb + g8;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = min(n8 + i, p.N - 1);  // clamped: out-of-range columns are computed but never stored
+      float val = fmaf(__uint_as_float(a1[i]), p.s1 ? p.s1[n] : 1.0f, p.t1 ? p.t1[n] : 0.0f);
+      if (p.s2 || p.t2) val = fmaf(val, p.s2 ? p.s2[n] : 1.0f, p.t2 ? p.t2[n] : 0.0f);
+      o[i] = val;
+    }
     switch (p.act) {
-      case ACT_TANH: val = tanhf(val); break;
-      case ACT_RELU: val = fmaxf(val, 0.0f); break;
-      case ACT_SIGMOID: val = sigmoidf_acc(val); break;
-      case ACT_PRELU: val = val >= 0.0f ? val : val * p.slope[n]; break;
-      case ACT_GELU: val = 0.5f * val * (1.0f + erff(val * 0.70710678118654752440f)); break;
+      case ACT_TANH:
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = tanhf(o[i]);
+        break;
+      case ACT_RELU:
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.0f);
+        break;
+      case ACT_SIGMOID:
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = sigmoidf_acc(o[i]);
+        break;
+      case ACT_PRELU:
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = o[i] >= 0.0f ? o[i] : o[i] * p.slope[min(n8 + i, p.N - 1)];
+        break;
+      case ACT_GELU:
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = gelu_fast(o[i]);
+        break;
       default: break;
     }
-    if (DUAL) val += __uint_as_float(a2);
-    if (p.gn_acc) { gs += val; gss = fmaf(val, val, gss); }
+    if (DUAL) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += __uint_as_float(a2[i]);
+    }
+    if (p.gn_acc) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (n8 + i < p.N) { gs += o[i]; gss = fmaf(o[i], o[i], gss); }
+    }
     if (p.act == ACT_GLU_PAIR) {
-      if (i & 1) {
-        const float gv = prev * sigmoidf_fast(val);
-        const int c = n >> 1;
-        if (r.cf) r.cf[c] = gv;
-        if (r.chi) {
-          __nv_bfloat16 h, l;
-          split_bf16(gv, h, l);
-          r.chi[c] = h;
-          r.clo[c] = l;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (n8 + 2 * i + 1 < p.N) {
+          const float gv = o[2 * i] * sigmoidf_fast(o[2 * i + 1]);
+          const int c = (n8 >> 1) + i;
+          if (r.cf) r.cf[c] = gv;
+          if (r.chi) {
+            __nv_bfloat16 h, l;
+            split_bf16(gv, h, l);
+            r.chi[c] = h;
+            r.clo[c] = l;
+          }
         }
       }
-      prev = val;
       continue;
     }
-    if (r.cf) r.cf[n] = val;
-    if (r.chi) {
-      __nv_bfloat16 h, l;
-      split_bf16(val, h, l);
-      r.chi[n] = h;
-      r.clo[n] = l;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (n8 + i < p.N) {
+        if (r.cf) r.cf[n8 + i] = o[i];
+        if (r.chi) {
+          __nv_bfloat16 h, l;
+          split_bf16(o[i], h, l);
+          r.chi[n8 + i] = h;
+          r.clo[n8 + i] = l;
+        }
+      }
     }
   }
 }
@@ -368,18 +411,24 @@ __device__ __forceinline__ void g2_chunk_ragged(uint32_t taddr, uint32_t taddr2,
 constexpr int g2_epi_warps(bool dual) { return dual ? 8 : 16; }
 constexpr int g2_threads(bool dual) { return 64 + 32 * g2_epi_warps(dual); }
 
-template <int BN, int STAGES, bool DUAL>
+constexpr int G2_MAX_STAGES = 6;
+
+template <int BN, bool DUAL>
 __global__ void __launch_bounds__(g2_threads(DUAL), 1)
     gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const G2Params p) {
-  constexpr int B_STAGE = 2 * BN * G2_BK * 2;  // hi + lo planes of the W tile
-  constexpr int STAGE_BYTES = G2_A_STAGE + B_STAGE;
+  const int STAGES = p.stages;
+  const uint32_t STAGE_BYTES = (uint32_t)p.stage_bytes;
+  const bool w_res = p.w_res_bytes > 0;
   constexpr uint32_t IDESC = umma_idesc_bf16(G2_BM, BN);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
+  uint8_t* wres = smem;                 // resident W k-blocks (w_res)
+  uint8_t* ring = smem + p.w_res_bytes;  // operand stages
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + G2_MAX_STAGES;
+  uint64_t* wfull_bar = empty_bar + G2_MAX_STAGES;  // resident W has landed
+  uint64_t* tfull_bar = wfull_bar + 1;              // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -394,6 +443,7 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    mbar_init(wfull_bar, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], g2_epi_warps(DUAL));  // one arrive per epilogue warp
@@ -414,55 +464,73 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
     if (lane == 0) {
       prefetch_tmap(&mapA);
       prefetch_tmap(&mapW);
-      int it = 0;  // global k-block counter across tiles (stage ring position)
+      if (w_res) {  // the whole (small) weight matrix: once per CTA
+        mbar_arrive_expect_tx(wfull_bar, (uint32_t)(KB * p.b_bytes));
+        for (int kb = 0; kb < KB; ++kb) tma_load_5d(wres + (size_t)kb * p.b_bytes, &mapW, kb * G2_BK, 0, 0, 0, 0, wfull_bar);
+      }
+      int s = 0;
+      uint32_t ph = 0;  // ring position and its phase bit
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int b = tile / tiles_per_batch;
         const int r = tile % tiles_per_batch;
         const int mt = r / p.n_tiles;
         const int x0 = (mt % p.tiles_x) * p.xt, y0 = (mt / p.tiles_x) * p.yt;
         const int n0 = (r % p.n_tiles) * BN;
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const bool ldA = !(p.dbg_skip == 2 && kb > 0), ldW = !w_res && !(p.dbg_skip == 1 && kb > 0);
+          mbar_arrive_expect_tx(&full_bar[s], (ldA ? G2_A_STAGE : 0) + (ldW ? p.b_bytes : 0));
           const int tap = kb / p.kb_per_tap;
           const int kc = (kb % p.kb_per_tap) * G2_BK;
-          uint8_t* st = smem + s * STAGE_BYTES;
-          tma_load_5d(st, &mapA, kc, x0 + p.dx[tap], y0 + p.dy[tap], b, 0, &full_bar[s]);
-          tma_load_5d(st + G2_A_STAGE, &mapW, kb * G2_BK, n0, 0, 0, 0, &full_bar[s]);
+          uint8_t* st = ring + s * STAGE_BYTES;
+          if (ldA) tma_load_5d(st, &mapA, kc, x0 + p.dx[tap], y0 + p.dy[tap], b, 0, &full_bar[s]);
+          if (ldW) tma_load_5d(st + G2_A_STAGE, &mapW, kb * G2_BK, n0, 0, 0, 0, &full_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int it = 0, local = 0;
+      int s = 0, local = 0;
+      uint32_t ph = 0;
+      if (w_res) {
+        mbar_wait(wfull_bar, 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
         const int as = DUAL ? 0 : (local & 1);
         const int aphase = DUAL ? (local & 1) : ((local >> 1) & 1);
         mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const int kb_res = DUAL ? (p.taps - 1) * p.kb_per_tap : KB;  // first k-block of the residual tap
-        for (int kb = 0; kb < KB; ++kb, ++it) {
+        // narrow outputs: shrink the MMA N to the valid columns of this tile (multiple of 16) -- less smem operand traffic
+        const int n0t = ((tile % tiles_per_batch) % p.n_tiles) * BN;
+        const int n_eff = min(BN, ((p.N - n0t) + 15) & ~15);
+        const uint32_t idesc = umma_idesc_bf16(G2_BM, n_eff);
+        for (int kb = 0; kb < KB; ++kb) {
           const uint32_t d_tmem = tmem_base + (DUAL ? (kb >= kb_res ? BN : 0) : as * BN);
           const bool first_kb = (kb == 0) || (kb == kb_res);
-          const int s = it % STAGES;
-          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t a_hi = smem_u32(ring + s * STAGE_BYTES);
           const uint32_t a_lo = a_hi + G2_BM * G2_BK * 2;
-          const uint32_t b_hi = a_hi + G2_A_STAGE;
-          const uint32_t b_lo = b_hi + BN * G2_BK * 2;
+          const uint32_t b_hi = w_res ? smem_u32(wres) + (uint32_t)(kb * p.b_bytes) : a_hi + G2_A_STAGE;
+          const uint32_t b_lo = b_hi + (uint32_t)p.n_box * (G2_BK * 2);
+          const int kvalid = p.ktap - (kb % p.kb_per_tap) * G2_BK;  // valid K columns in this block (rest is TMA zero fill)
+          const int nks = kvalid >= G2_BK ? G2_BK / 16 : (kvalid + 15) >> 4;
 #pragma unroll
           for (int ks = 0; ks < G2_BK / 16; ++ks) {
+            if (ks >= nks) break;
             const uint32_t ko = ks * 32;
             const uint64_t dah = umma_desc_sw128(a_hi + ko), dal = umma_desc_sw128(a_lo + ko);
             const uint64_t dbh = umma_desc_sw128(b_hi + ko), dbl = umma_desc_sw128(b_lo + ko);
-            umma_f16(d_tmem, dal, dbh, IDESC, (!first_kb || ks > 0) ? 1u : 0u);
-            umma_f16(d_tmem, dah, dbl, IDESC, 1u);
-            umma_f16(d_tmem, dah, dbh, IDESC, 1u);
+            umma_f16(d_tmem, dal, dbh, idesc, (!first_kb || ks > 0) ? 1u : 0u);
+            umma_f16(d_tmem, dah, dbl, idesc, 1u);
+            umma_f16(d_tmem, dah, dbh, idesc, 1u);
           }
           umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(&tfull_bar[as]);
       }
@@ -582,6 +650,11 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   p.m_tiles = p.tiles_x * ceil_div(Yo, p.yt);
   p.n_tiles = ceil_div(pr.N, BN);
   p.kb_per_tap = ceil_div(pr.Ktap, G2_BK);
+  p.ktap = pr.Ktap;
+  {
+    static const int dbg = [] { const char* e = getenv("RFX_G2_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
+    p.dbg_skip = dbg;
+  }
   p.taps = pr.taps;
   for (int i = 0; i < pr.taps; ++i) { p.dx[i] = pr.row_off[i]; p.dy[i] = pr.row_off_y[i]; }
   p.Cf = pr.Cf; p.ldcf = pr.ldcf; p.bscf = pr.bscf; p.ldcy_f = pr.ldcf_y;
@@ -600,28 +673,34 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   if ((rc = make_split_map(&mapA, pr.A.hi, pr.Ktap, pr.A.rows, pr.A.rows_y > 0 ? pr.A.rows_y : 1, pr.batch, pr.A.ld, pr.A.ld_y,
                            pr.A.batch_stride, pr.A.plane_stride, p.xt, p.yt)))
     return rc;
-  if ((rc = make_split_map(&mapW, pr.W.hi, pr.W.Kpad, pr.W.Npad, 1, 1, pr.W.Kpad, 0, 0, (long long)pr.W.Npad * pr.W.Kpad, BN, 1))) return rc;
+  // shared-memory plan: narrow single-tile outputs fetch only the rows they need; small weight matrices stay resident
+  constexpr int SMEM_CAP = 227 * 1024 - 2048;  // barriers + 1024-byte alignment slack
+  const int KB = p.kb_per_tap * p.taps;
+  p.n_box = p.n_tiles == 1 ? std::min(BN, ceil_div(pr.N, 16) * 16) : BN;
+  p.b_bytes = 2 * p.n_box * G2_BK * 2;
+  const long long w_total = (long long)KB * p.b_bytes;
+  const bool resident = !pr.dual && p.n_tiles == 1 && w_total + 3 * G2_A_STAGE <= SMEM_CAP;
+  p.w_res_bytes = resident ? (int)w_total : 0;
+  p.stage_bytes = G2_A_STAGE + (resident ? 0 : p.b_bytes);
+  p.stages = std::min(G2_MAX_STAGES, (SMEM_CAP - p.w_res_bytes) / p.stage_bytes);
+  RFX_REQUIRE(p.stages >= 2, "gemm2: operand stages do not fit in shared memory");
+  if ((rc = make_split_map(&mapW, pr.W.hi, pr.W.Kpad, pr.W.Npad, 1, 1, pr.W.Kpad, 0, 0, (long long)pr.W.Npad * pr.W.Kpad, p.n_box, 1))) return rc;
   const int total = p.batch * p.m_tiles * p.n_tiles;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = total < sms ? total : sms;
+  const int smem = p.w_res_bytes + p.stages * p.stage_bytes + 1024 + 256;
   if (pr.dual) {
     RFX_REQUIRE(BN == 256 && pr.N <= 256 * p.n_tiles && pr.taps >= 2, "dual-accumulator mode needs BN = 256 and >= 2 taps");
-    constexpr int STAGES = 2;
-    const int smem = STAGES * (G2_A_STAGE + 2 * 256 * G2_BK * 2) + 1024 + 256;
-    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gemm2_kernel<256, STAGES, true><<<grid, g2_threads(true), smem, stream>>>(mapA, mapW, p);
+    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    gemm2_kernel<256, true><<<grid, g2_threads(true), smem, stream>>>(mapA, mapW, p);
   } else if (BN == 256) {
-    constexpr int STAGES = 2;
-    const int smem = STAGES * (G2_A_STAGE + 2 * 256 * G2_BK * 2) + 1024 + 256;
-    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gemm2_kernel<256, STAGES, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
+    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    gemm2_kernel<256, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
   } else {
-    constexpr int STAGES = 3;
-    const int smem = STAGES * (G2_A_STAGE + 2 * 128 * G2_BK * 2) + 1024 + 256;
-    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gemm2_kernel<128, STAGES, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
+    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    gemm2_kernel<128, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
   }
   RFX_CHECK_CUDA(cudaGetLastError());
   return 0;
