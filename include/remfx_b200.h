@@ -110,6 +110,31 @@ int rfx_umx_sample_host(rfx_umx_t* h, const float* x_host, int B, int T, float* 
 int rfx_umx_submit_host(rfx_umx_t* h, int slot, const float* x_host, int B, int T, float* out_host, void* workspace,
                         size_t workspace_bytes, void* stream);
 int rfx_umx_wait_host(rfx_umx_t* h, int slot);
+/* Multi-lane pipeline: the throughput form of rfx_umx_sample for a stream of equally shaped batches (a serving loop over
+ * remfx/models.py:303-304).  One call is nb_layers stages (stage l = [STFT, fc1 if l = 0] + W_ih GEMM + recurrence of LSTM
+ * layer l [+ fc2, fc3, iSTFT if l = last]); the bidirectional recurrence is a chain of strictly dependent steps that occupies
+ * only 8 * 2 * ceil(B/8) SMs, so push(n) runs stage l of step n - l for every l: the recurrences of nb_layers consecutive
+ * steps go back to back on one internal high-priority stream while all the other kernels of those steps run beside them,
+ * capped to the remaining SMs.  Results are identical to rfx_umx_sample (same kernels, same order per step).
+ *   push   enqueues step `*seq` (0, 1, 2, ... since the handle was created) and returns; x / out are device buffers, or
+ *          (pinned) host buffers when x_on_host / out_on_host is non-zero (H2D / D2H then ride the internal copy streams).
+ *          The lane starts after the work already enqueued on `stream`.  x and out must stay valid and untouched until
+ *          the step's output is complete.  Step s leaves the pipeline during push(s + depth - 1) or flush.
+ *   flush  runs the stages still owed to the steps in flight and makes `stream` wait for every finished output.
+ *   wait / stream_wait  block the host / make `stream` wait until step seq's output is complete (the step must have left the
+ *          pipeline; a lane is reused `depth` pushes later, so wait for a step before pushing `depth` more).
+ * workspace: rfx_umx_pipe_workspace_bytes (= depth private lanes), the same pointer for every push until a flush. */
+size_t rfx_umx_pipe_workspace_bytes(const rfx_umx_t* h, int B, int T);
+int rfx_umx_pipe_depth(const rfx_umx_t* h);
+int rfx_umx_pipe_push(rfx_umx_t* h, const float* x, int x_on_host, int B, int T, float* out, int out_on_host, void* workspace,
+                      size_t workspace_bytes, void* stream, long long* seq);
+int rfx_umx_pipe_flush(rfx_umx_t* h, void* stream);
+int rfx_umx_pipe_wait(rfx_umx_t* h, long long seq);
+int rfx_umx_pipe_stream_wait(rfx_umx_t* h, long long seq, void* stream);
+/* Timing of the pipeline's recurrence launches: set_profiling(n > 0) brackets the next n launches with cudaEvents on the
+ * recurrence stream (0 switches it off); rec_times returns their durations in ms, in launch order, once they have run. */
+int rfx_umx_pipe_set_profiling(rfx_umx_t* h, int max_launches);
+int rfx_umx_pipe_rec_times(rfx_umx_t* h, float* ms, int capacity, int* n_out);
 /* Number of kernels one rfx_umx_sample call launches (for bench.py's gpu_launches). */
 int rfx_umx_launches_per_call(const rfx_umx_t* h);
 /* Per-stage device timing: when enabled, rfx_umx_sample records a cudaEvent on `stream` between its

@@ -689,7 +689,8 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = total < sms ? total : sms;
+  int grid = total < sms ? total : sms;
+  if (pr.max_ctas > 0 && grid > pr.max_ctas) grid = pr.max_ctas;
   const int smem = p.w_res_bytes + p.stages * p.stage_bytes + 1024 + 256;
   if (pr.dual) {
     RFX_REQUIRE(BN == 256 && pr.N <= 256 * p.n_tiles && pr.taps >= 2, "dual-accumulator mode needs BN = 256 and >= 2 taps");

@@ -36,6 +36,7 @@ struct StftParams {
   int ldas;
   const float* in_mean;   // STFT_UMX_MAG only
   const float* in_scale;
+  int max_sms = 0;        // > 0: size the grid to fill at most this many SMs (grid-stride over the frame groups); 0 = one CTA per group
 };
 
 struct IstftParams {
@@ -53,6 +54,7 @@ struct IstftParams {
   float* out;   // (B, length)
   long long out_bstride;
   int hops_per_cta;
+  int max_sms = 0;    // > 0: size the grid to fill at most this many SMs (grid-stride over the output segments)
 };
 
 const float2* twiddles(int n_fft);
@@ -109,6 +111,7 @@ struct G2Problem {
   // optional fused GroupNorm statistics of the output (see gemm2.cu): accum must be zeroed by the caller
   double* gn_acc = nullptr;
   int gn_G = 1, gn_per_x = 0, gn_cmod = 0;
+  int max_ctas = 0;  // > 0: persistent grid of at most this many CTAs (leaves the other SMs to concurrent kernels)
 };
 int g2_choose_bn(int N);
 size_t split_weight_elems(int N, int K, int BN);  // elements of ONE plane
@@ -128,6 +131,11 @@ int lstm_get_impl();
 // Hout (fp32) and/or Hhi/Hlo (split bf16 planes, row stride ldhs) may be given.
 int launch_lstm_layer(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs,
                       int B, int F, int H, cudaStream_t stream);
+// Same, with the batch slots per cluster fixed by the caller (1..8; 0 = as few as keeps the launch one wave).  8 packs the
+// launch into the fewest SMs (2 * ceil(B / 8) clusters of 8), which is what the multi-lane Open-Unmix pipeline wants.
+int launch_lstm_layer_slots(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo,
+                            int ldhs, int B, int F, int H, int slots, cudaStream_t stream);
+int lstm_clusters_for(int B, int slots);  // clusters (of 8 CTAs) one launch of the tensor-core recurrence uses
 
 // ---------------------------------------------------------------- small utility kernels (util.cu)
 int launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale, float* shift,

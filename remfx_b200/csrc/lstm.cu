@@ -429,7 +429,7 @@ static size_t lstm_mma_smem() {
 
 template <int H, bool LO_SMEM>
 static int launch_mma(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs, int B,
-                      int F, cudaStream_t stream) {
+                      int F, int slots, cudaStream_t stream) {
   const size_t smem = lstm_mma_smem<H, LO_SMEM>();
   RFX_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_mma_kernel<H, LO_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // batch slots per cluster: as few as possible while all clusters stay co-resident (the MMA cost does not depend on it)
@@ -448,8 +448,12 @@ static int launch_mma(const float* G, int ldg, const float* Whh, float* Hout, in
     maxc = n > 0 ? n : 14;
   }
   int nb = LSTM_SLOTS;
-  for (int cand = 1; cand <= LSTM_SLOTS; ++cand)
-    if (2 * ceil_div(B, cand) <= maxc) { nb = cand; break; }
+  if (slots > 0) {
+    nb = slots < LSTM_SLOTS ? slots : LSTM_SLOTS;
+  } else {
+    for (int cand = 1; cand <= LSTM_SLOTS; ++cand)
+      if (2 * ceil_div(B, cand) <= maxc) { nb = cand; break; }
+  }
   dim3 grid(LSTM_CL, ceil_div(B, nb), 2);
   lstm_rec_mma_kernel<H, LO_SMEM><<<grid, H / 8 / 4 * 32, smem, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb);
   RFX_CHECK_CUDA(cudaGetLastError());
@@ -496,16 +500,23 @@ static int g_lstm_impl = 0;  // 0 = tensor-core (mma.sync bf16x3), 1 = fp32 FFMA
 void lstm_set_impl(int impl) { g_lstm_impl = impl; }
 int lstm_get_impl() { return g_lstm_impl; }
 
+int lstm_clusters_for(int B, int slots) { return 2 * ceil_div(B, slots > 0 && slots < LSTM_SLOTS ? slots : LSTM_SLOTS); }
+
 int launch_lstm_layer(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs,
                       int B, int F, int H, cudaStream_t stream) {
+  return launch_lstm_layer_slots(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, H, 0, stream);
+}
+
+int launch_lstm_layer_slots(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo,
+                            int ldhs, int B, int F, int H, int slots, cudaStream_t stream) {
   RFX_REQUIRE(H == 192 || H == 256 || H == 384, "lstm: hidden size per direction must be 192, 256 or 384");
   RFX_REQUIRE(B > 0 && F > 0, "lstm: positive sizes");
   RFX_REQUIRE(((uintptr_t)Whh & 15) == 0, "lstm: W_hh must be 16-byte aligned");
   RFX_REQUIRE(Hout || (Hhi && Hlo), "lstm: no output given");
   if (g_lstm_impl == 0 || H != LSTM_H) {
-    if (H == 256) return launch_mma<256, false>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);
-    if (H == 192) return launch_mma<192, false>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);
-    return launch_mma<384, true>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);
+    if (H == 256) return launch_mma<256, false>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
+    if (H == 192) return launch_mma<192, false>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
+    return launch_mma<384, true>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
   }
   switch (lstm_choose_nb(B)) {
     case 4: return launch_nb<4>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, stream);

@@ -52,17 +52,21 @@ __device__ __forceinline__ int reflect_index(int i, int T) {
 constexpr int STFT_FPC = 4;
 
 template <int LOG2NC>
-__global__ void __launch_bounds__((1 << LOG2NC) / 4) stft_kernel(StftParams p) {
+__global__ void __launch_bounds__((1 << LOG2NC) / 4) stft_kernel(StftParams p, int groups, int n_work) {
   constexpr int NC = 1 << LOG2NC;
   constexpr int T4 = NC / 4;
   constexpr int NFFT = 2 * NC;
   __shared__ float2 sa[NC];
   __shared__ float2 sb[NC];
   const int j = threadIdx.x;
-  const int b = blockIdx.y;
+  // work item = (batch item, group of STFT_FPC frames); the grid strides over them (it is capped when other kernels
+  // must keep part of the chip, see StftParams::max_ctas)
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+  const int b = work / groups;
+  const int fg = work - b * groups;
   const float* __restrict__ x = p.x + (size_t)b * p.x_bstride;
-  const int f_end = min(p.F, (int)(blockIdx.x + 1) * STFT_FPC);
-  for (int f = blockIdx.x * STFT_FPC; f < f_end; ++f) {
+  const int f_end = min(p.F, (fg + 1) * STFT_FPC);
+  for (int f = fg * STFT_FPC; f < f_end; ++f) {
     const int base = f * p.hop - p.frame_off;  // first sample of the frame (frame_off = n_fft/2 for centre padding)
     const bool interior = (base >= 0) && (base + NFFT <= p.T);
 #pragma unroll
@@ -109,18 +113,37 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) stft_kernel(StftParams p) {
     }
     __syncthreads();  // sa/sb are reused by the next frame
   }
+  }
 }
 
 int launch_stft(const StftParams& p, int B, cudaStream_t stream) {
   RFX_REQUIRE(p.tw != nullptr, "twiddle table");
   RFX_REQUIRE(p.T > p.n_fft / 2, "reflect padding needs T > n_fft/2");
   RFX_REQUIRE(p.frame_off >= 0 && p.frame_off < p.T && p.nbins >= 1 && p.nbins <= p.n_fft / 2 + 1, "stft frame_off / nbins");
-  dim3 grid(ceil_div(p.F, STFT_FPC), B);
+  const int groups = ceil_div(p.F, STFT_FPC);
+  const long long n_work_ll = (long long)groups * B;
+  RFX_REQUIRE(n_work_ll < (1ll << 31), "stft: too many frames");
+  const int n_work = (int)n_work_ll;
+  int grid = n_work;
+  if (p.max_sms > 0) {
+    int per_sm = 0;
+    cudaError_t e = cudaSuccess;
+    switch (p.n_fft) {
+      case 512: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel<8>, 64, 0); break;
+      case 1024: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel<9>, 128, 0); break;
+      case 2048: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel<10>, 256, 0); break;
+      case 4096: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel<11>, 512, 0); break;
+      default: break;
+    }
+    RFX_CHECK_CUDA(e);
+    const long long cap = (long long)p.max_sms * (per_sm > 0 ? per_sm : 1);
+    if (cap < grid) grid = (int)cap;
+  }
   switch (p.n_fft) {
-    case 512: stft_kernel<8><<<grid, 64, 0, stream>>>(p); break;
-    case 1024: stft_kernel<9><<<grid, 128, 0, stream>>>(p); break;
-    case 2048: stft_kernel<10><<<grid, 256, 0, stream>>>(p); break;
-    case 4096: stft_kernel<11><<<grid, 512, 0, stream>>>(p); break;
+    case 512: stft_kernel<8><<<grid, 64, 0, stream>>>(p, groups, n_work); break;
+    case 1024: stft_kernel<9><<<grid, 128, 0, stream>>>(p, groups, n_work); break;
+    case 2048: stft_kernel<10><<<grid, 256, 0, stream>>>(p, groups, n_work); break;
+    case 4096: stft_kernel<11><<<grid, 512, 0, stream>>>(p, groups, n_work); break;
     default: set_error("stft: n_fft must be 512, 1024, 2048 or 4096"); return 2;
   }
   RFX_CHECK_CUDA(cudaGetLastError());
@@ -133,7 +156,7 @@ int launch_stft(const StftParams& p, int B, cudaStream_t stream) {
 // inverse-transforms every frame overlapping its segment (sequentially, so the OLA needs no atomics).
 // -------------------------------------------------------------------------------------------------
 template <int LOG2NC>
-__global__ void __launch_bounds__((1 << LOG2NC) / 4) istft_kernel(IstftParams p) {
+__global__ void __launch_bounds__((1 << LOG2NC) / 4) istft_kernel(IstftParams p, int segs, int n_work) {
   constexpr int NC = 1 << LOG2NC;
   constexpr int T4 = NC / 4;
   constexpr int NFFT = 2 * NC;
@@ -142,9 +165,10 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) istft_kernel(IstftParams p)
   float2* sb = sa + NC;
   float* ola = reinterpret_cast<float*>(sb + NC);
   const int j = threadIdx.x;
-  const int b = blockIdx.y;
   const int S = p.hops_per_cta * p.hop;
-  const int s0 = blockIdx.x * S;  // first output sample of this segment
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {  // work item = (batch item, output segment)
+  const int b = work / segs;
+  const int s0 = (work - b * segs) * S;  // first output sample of this segment
   for (int i = j; i < S; i += T4) ola[i] = 0.0f;
   // frames whose support [t*hop - NC, t*hop + NC) (output coordinates) intersects [s0, s0 + S)
   // frame t covers output samples [t*hop - frame_off, t*hop - frame_off + NFFT)
@@ -211,6 +235,8 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) istft_kernel(IstftParams p)
     }
     out[s] = (env > 1e-11f) ? ola[i] / env : 0.0f;
   }
+  __syncthreads();  // ola is zeroed again by the next work item
+  }
 }
 
 template <int LOG2NC>
@@ -219,8 +245,18 @@ static int launch_istft_t(const IstftParams& p, int B, cudaStream_t stream) {
   const int S = p.hops_per_cta * p.hop;
   const size_t smem = sizeof(float2) * 2 * NC + sizeof(float) * S;
   RFX_CHECK_CUDA(cudaFuncSetAttribute(istft_kernel<LOG2NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(ceil_div(p.length, S), B);
-  istft_kernel<LOG2NC><<<grid, NC / 4, smem, stream>>>(p);
+  const int segs = ceil_div(p.length, S);
+  const long long n_work_ll = (long long)segs * B;
+  RFX_REQUIRE(n_work_ll < (1ll << 31), "istft: too many segments");
+  const int n_work = (int)n_work_ll;
+  int grid = n_work;
+  if (p.max_sms > 0) {
+    int per_sm = 0;
+    RFX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, istft_kernel<LOG2NC>, NC / 4, smem));
+    const long long cap = (long long)p.max_sms * (per_sm > 0 ? per_sm : 1);
+    if (cap < grid) grid = (int)cap;
+  }
+  istft_kernel<LOG2NC><<<grid, NC / 4, smem, stream>>>(p, segs, n_work);
   RFX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

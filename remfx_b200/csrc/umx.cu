@@ -9,6 +9,7 @@
 #include "kernels.h"
 #include "../../include/remfx_b200.h"
 
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -74,11 +75,36 @@ struct rfx_umx {
   // optional per-stage timing (cudaEvents recorded on the caller's stream between the launches)
   bool profiling = false;
   std::vector<cudaEvent_t> events;
-  // host-buffer pipeline (rfx_umx_sample_host / submit_host / wait_host): two slots, item-chunked copies on two internal streams
-  static constexpr int kSlots = 2, kChunks = 4;
+  int mark_idx = 0;
+  // host-buffer pipeline (rfx_umx_sample_host / submit_host / wait_host): two slots, item-chunked copies on two internal streams.
+  // The multi-lane pipeline (rfx_umx_pipe_*) reuses the same copy streams and per-slot events with slot = lane.
+  static constexpr int kSlots = 4, kHostSlots = 2, kChunks = 4;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev_in[kSlots][kChunks] = {}, ev_ist[kSlots][kChunks] = {}, ev_out[kSlots] = {};
-  bool pending[kSlots] = {false, false};
+  bool pending[kSlots] = {false, false, false, false};
+  // multi-lane pipeline state (see rfx_umx_pipe_push)
+  struct Lane {
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev_x = nullptr, ev_pre = nullptr, ev_rec = nullptr, ev_stft = nullptr, ev_done = nullptr;
+    const float* x = nullptr; float* out = nullptr;          // device buffers of the step in the lane
+    const float* x_host = nullptr; float* out_host = nullptr;  // host buffers (null = device-resident)
+    long long seq = -1;
+    int next_stage = 0;
+    bool live = false, done_recorded = false, stft_recorded = false, host_out_pending = false;
+  };
+  struct Pipe {
+    bool ready = false;
+    int depth = 0, B = 0, T = 0;
+    cudaStream_t rec = nullptr;  // all recurrence launches, in issue order, at the highest stream priority
+    Lane lane[kSlots];
+    long long pushed = 0;
+    void* ws = nullptr;
+    int sms = 0, max_sms = 0, lstm_slots = 0;
+    // optional timing of the recurrence launches (a pair of timing events around each, on the recurrence stream)
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;
+    int prof_n = 0;
+  } pipe;
 
   ~rfx_umx() {
     if (copy_in) cudaStreamDestroy(copy_in);
@@ -89,7 +115,13 @@ struct rfx_umx {
         if (ev_ist[i][c]) cudaEventDestroy(ev_ist[i][c]);
       }
       if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+      Lane& l = pipe.lane[i];
+      if (l.s) cudaStreamDestroy(l.s);
+      for (cudaEvent_t e : {l.ev_x, l.ev_pre, l.ev_rec, l.ev_stft, l.ev_done})
+        if (e) cudaEventDestroy(e);
     }
+    if (pipe.rec) cudaStreamDestroy(pipe.rec);
+    for (auto e : pipe.prof_ev) cudaEventDestroy(e);
     for (auto e : events) cudaEventDestroy(e);
     for (auto& kv : params) kv.second.release();
     for (int i = 0; i < 3; ++i) { bn_s[i].release(); bn_t[i].release(); }
@@ -146,8 +178,9 @@ const float* P(const rfx_umx* h, const std::string& k) {
 
 // One dense layer on the tensor-core engine: A (split planes, K columns) x W^T -> fp32 and/or split output.
 int dense(const __nv_bfloat16* a_hi, size_t a_plane, int lda, int M, int K, const SplitW& W, float* Cf, int ldcf, __nv_bfloat16* c_hi,
-          size_t c_plane, int ldcs, const Epilogue& e, cudaStream_t s) {
+          size_t c_plane, int ldcs, const Epilogue& e, cudaStream_t s, int max_ctas = 0) {
   G2Problem pr;
+  pr.max_ctas = max_ctas;
   pr.A.hi = a_hi; pr.A.rows = M; pr.A.ld = lda; pr.A.batch_stride = 0; pr.A.plane_stride = (long long)a_plane;
   pr.W = W;
   pr.M = M; pr.N = W.N; pr.batch = 1; pr.Ktap = K; pr.taps = 1;
@@ -262,31 +295,35 @@ size_t rfx_umx_workspace_bytes(const rfx_umx_t* h, int B, int T) {
 
 int rfx_umx_launches_per_call(const rfx_umx_t* h) { return h ? 5 + 2 * h->cfg.nb_layers : 0; }
 
+
 namespace {
 // Host-buffer plan of one call: inputs arrive in item chunks on the copy-in stream (ev_in[c] fires when chunk c is in HBM), the
 // STFT of chunk c waits only for that event; each chunk's iSTFT is followed by its own D2H on the copy-out stream.
 struct HostIO {
-  const float* x_host; float* out_host;
+  const float* x_host; float* out_host;  // either may be null (that side is device-resident)
   int slot;
 };
-int umx_forward(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, void* stream, const HostIO* io);
-}  // namespace
 
-int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, void* stream) {
-  return umx_forward(h, x, B, T, out, workspace, workspace_bytes, stream, nullptr);
-}
+// One call = nb_layers STAGES.  Stage l: [l == 0: STFT, fc1] -> W_ih GEMM of layer l -> recurrence of layer l ->
+// [l == last: fc2, fc3, iSTFT].  rfx_umx_sample runs the stages back to back on one stream; the multi-lane pipeline runs
+// stage l of step n - l in super-step n, with every recurrence on one shared high-priority stream.
+struct UmxCall {
+  const float* x; float* out;
+  int B, T;
+  uint8_t* ws;
+  UmxLayout L;
+  cudaStream_t s;       // stream of everything but the recurrences
+  cudaStream_t s_rec;   // stream of the recurrence launches (== s outside the pipeline)
+  cudaEvent_t ev_pre, ev_rec, ev_stft;  // pipeline only: W_ih done -> recurrence may start; recurrence done; x consumed
+  const HostIO* io;
+  int max_sms;          // > 0: non-recurrent kernels keep to this many SMs
+  int lstm_slots;       // batch slots per recurrence cluster (0 = automatic)
+};
 
-namespace {
-int umx_forward(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, void* stream, const HostIO* io) {
-  RFX_REQUIRE(h && x && out && workspace, "null argument");
-  RFX_REQUIRE(h->finalized, "rfx_umx_finalize has not been called since the last parameter load");
-  RFX_REQUIRE(B > 0 && T > h->cfg.n_fft / 2, "need B > 0 and T > n_fft/2 (reflect padding)");
-  RFX_REQUIRE(T % h->cfg.hop == 0, "T must be a multiple of the hop length");
-  const UmxLayout L = umx_layout(h, B, T);
-  RFX_REQUIRE(workspace_bytes >= L.total, "workspace too small (see rfx_umx_workspace_bytes)");
-  RFX_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
-  cudaStream_t s = (cudaStream_t)stream;
-  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+int umx_stage(rfx_umx_t* h, const UmxCall& c, int l) {
+  const UmxLayout& L = c.L;
+  cudaStream_t s = c.s;
+  uint8_t* ws = c.ws;
   float2* Z = reinterpret_cast<float2*>(ws + L.off_Z);
   __nv_bfloat16* A1 = reinterpret_cast<__nv_bfloat16*>(ws + L.off_A1);
   __nv_bfloat16* XC = reinterpret_cast<__nv_bfloat16*>(ws + L.off_XC);
@@ -294,102 +331,155 @@ int umx_forward(rfx_umx_t* h, const float* x, int B, int T, float* out, void* wo
   __nv_bfloat16* Hb[2] = {reinterpret_cast<__nv_bfloat16*>(ws + L.off_H1), reinterpret_cast<__nv_bfloat16*>(ws + L.off_H2)};
   __nv_bfloat16* Y2 = reinterpret_cast<__nv_bfloat16*>(ws + L.off_Y2);
   float* mask = reinterpret_cast<float*>(ws + L.off_mask);
-  const int hid = h->cfg.hidden, H = h->H, nl = h->cfg.nb_layers;
+  const int hid = h->cfg.hidden, H = h->H, nl = h->cfg.nb_layers, B = c.B, T = c.T;
   const float2* tw = twiddles(h->cfg.n_fft);
   RFX_REQUIRE(tw != nullptr, "twiddle table allocation failed");
+  const HostIO* io = c.io;
+  const bool serial = (c.s_rec == c.s);  // plain call: stage marks for the profiler
   int rc;
+  auto mark = [&]() -> int {
+    if (serial && h->profiling) RFX_CHECK_CUDA(cudaEventRecord(h->events[h->mark_idx], s));
+    ++h->mark_idx;
+    return 0;
+  };
+  const int nch = io ? std::min(B, (int)rfx_umx::kChunks) : 1;
+
+  if (l == 0) {
+    // (1) STFT (transforms.py:106-116) + ComplexNorm (:211) + input shift/scale (model.py:127-128) -> split planes
+    StftParams sp{};
+    sp.x = c.x; sp.x_bstride = T; sp.T = T;
+    sp.x_aligned8 = (((uintptr_t)c.x & 7) == 0 && (T % 2 == 0)) ? 1 : 0;
+    sp.window = P(h, "window"); sp.tw = tw;
+    sp.n_fft = h->cfg.n_fft; sp.hop = h->cfg.hop; sp.F = L.F;
+    sp.frame_off = h->cfg.n_fft / 2; sp.nbins = h->bins;
+    sp.scale = 1.0f; sp.alpha = 1.0f; sp.mode = STFT_UMX_MAG;
+    sp.Z = Z; sp.ldz = h->bins; sp.A = nullptr; sp.lda = 0;
+    sp.Ahi = A1; sp.Alo = A1 + L.plane_A1; sp.ldas = L.lda1;
+    sp.in_mean = P(h, "input_mean"); sp.in_scale = P(h, "input_scale");
+    sp.max_sms = c.max_sms;
+    const bool h2d = io && io->x_host;
+    for (int ch = 0; ch < nch; ++ch) {
+      const int i0 = (int)((long long)B * ch / nch), i1 = (int)((long long)B * (ch + 1) / nch);
+      if (h2d) {
+        RFX_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(c.x) + (size_t)i0 * T, io->x_host + (size_t)i0 * T, (size_t)(i1 - i0) * T * 4,
+                                       cudaMemcpyHostToDevice, h->copy_in));
+        RFX_CHECK_CUDA(cudaEventRecord(h->ev_in[io->slot][ch], h->copy_in));
+      }
+    }
+    for (int ch = 0; ch < nch; ++ch) {
+      const int i0 = (int)((long long)B * ch / nch), i1 = (int)((long long)B * (ch + 1) / nch);
+      StftParams sc = sp;
+      sc.x = c.x + (size_t)i0 * T;
+      sc.Z = Z + (size_t)i0 * L.F * h->bins;
+      sc.Ahi = A1 + (size_t)i0 * L.F * L.lda1; sc.Alo = sc.Ahi + L.plane_A1;
+      if (h2d) RFX_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_in[io->slot][ch], 0));
+      if ((rc = launch_stft(sc, i1 - i0, s))) return rc;
+    }
+    if (c.ev_stft) RFX_CHECK_CUDA(cudaEventRecord(c.ev_stft, s));  // the input staging buffer may be refilled
+    if ((rc = mark())) return rc;
+
+    // (2) fc1 + bn1 + tanh (model.py:132-138) -> first half of the skip-concat buffer
+    Epilogue e1; e1.s1 = h->bn_s[0].p; e1.t1 = h->bn_t[0].p; e1.act = ACT_TANH;
+    if ((rc = dense(A1, L.plane_A1, L.lda1, L.M, h->bins, h->fc1p, nullptr, 0, XC, L.plane_XC, 2 * hid, e1, s, c.max_sms)) || (rc = mark()))
+      return rc;
+  }
+
+  // (3) BiLSTM layer l (model.py:141): one input-projection GEMM + one recurrent cluster kernel
+  {
+    const __nv_bfloat16* lin; size_t lin_plane; int ldin;
+    if (l == 0) { lin = XC; lin_plane = L.plane_XC; ldin = 2 * hid; }
+    else { lin = Hb[(l - 1) & 1]; lin_plane = L.plane_H; ldin = hid; }
+    Epilogue eb; eb.t1 = h->lstm_bias[l].p;
+    if ((rc = dense(lin, lin_plane, ldin, L.M, hid, h->wihp[l], G, 8 * H, nullptr, 0, 0, eb, s, c.max_sms)) || (rc = mark())) return rc;
+    __nv_bfloat16* hout; size_t hplane; int ldh;
+    if (l == nl - 1) { hout = XC + hid; hplane = L.plane_XC; ldh = 2 * hid; }  // torch.cat([x, lstm_out], -1) (model.py:144) for free
+    else { hout = Hb[l & 1]; hplane = L.plane_H; ldh = hid; }
+    if (!serial) {
+      RFX_CHECK_CUDA(cudaEventRecord(c.ev_pre, s));
+      RFX_CHECK_CUDA(cudaStreamWaitEvent(c.s_rec, c.ev_pre, 0));
+    }
+    const bool timed = !serial && h->pipe.prof && 2 * h->pipe.prof_n + 1 < (int)h->pipe.prof_ev.size();
+    if (timed) RFX_CHECK_CUDA(cudaEventRecord(h->pipe.prof_ev[2 * h->pipe.prof_n], c.s_rec));
+    if ((rc = launch_lstm_layer_slots(G, 8 * H, h->whh_cat[l].p, nullptr, 0, hout, hout + hplane, ldh, B, L.F, H, c.lstm_slots, c.s_rec)))
+      return rc;
+    if (timed) { RFX_CHECK_CUDA(cudaEventRecord(h->pipe.prof_ev[2 * h->pipe.prof_n + 1], c.s_rec)); ++h->pipe.prof_n; }
+    if (!serial) {
+      RFX_CHECK_CUDA(cudaEventRecord(c.ev_rec, c.s_rec));
+      RFX_CHECK_CUDA(cudaStreamWaitEvent(s, c.ev_rec, 0));
+    }
+    if ((rc = mark())) return rc;
+  }
+
+  if (l == nl - 1) {
+    // (4) fc2 + bn2 + ReLU (model.py:147-150)
+    Epilogue e2; e2.s1 = h->bn_s[1].p; e2.t1 = h->bn_t[1].p; e2.act = ACT_RELU;
+    if ((rc = dense(XC, L.plane_XC, 2 * hid, L.M, 2 * hid, h->fc2p, nullptr, 0, Y2, L.plane_Y2, hid, e2, s, c.max_sms)) || (rc = mark())) return rc;
+
+    // (5) fc3 + bn3 + output scale/mean + ReLU (model.py:153-164) = the non-negative ratio mask
+    Epilogue e3; e3.s1 = h->bn_s[2].p; e3.t1 = h->bn_t[2].p; e3.s2 = P(h, "output_scale"); e3.t2 = P(h, "output_mean"); e3.act = ACT_RELU;
+    if ((rc = dense(Y2, L.plane_Y2, hid, L.M, hid, h->fc3p, mask, L.ldm, nullptr, 0, 0, e3, s, c.max_sms)) || (rc = mark())) return rc;
+
+    // (6) `* mix` (model.py:164) + wiener niter=0 (filtering.py:442-451) + iSTFT (transforms.py:168-177)
+    IstftParams ip{};
+    ip.Z = Z; ip.ldz = h->bins; ip.mask = mask; ip.ldm = L.ldm;
+    ip.window = P(h, "window"); ip.tw = tw;
+    ip.n_fft = h->cfg.n_fft; ip.hop = h->cfg.hop; ip.F = L.F; ip.length = T;
+    ip.frame_off = h->cfg.n_fft / 2; ip.env_pad = 0; ip.nbins = h->bins;
+    ip.scale = 1.0f; ip.out = c.out; ip.out_bstride = T; ip.hops_per_cta = 16;
+    ip.max_sms = c.max_sms;
+    const bool d2h = io && io->out_host;
+    const int nco = d2h ? nch : 1;
+    for (int ch = 0; ch < nco; ++ch) {
+      const int i0 = (int)((long long)B * ch / nco), i1 = (int)((long long)B * (ch + 1) / nco);
+      IstftParams ic = ip;
+      ic.Z = Z + (size_t)i0 * L.F * h->bins;
+      ic.mask = mask + (size_t)i0 * L.F * L.ldm;
+      ic.out = c.out + (size_t)i0 * T;
+      if ((rc = launch_istft(ic, i1 - i0, s))) return rc;
+      if (d2h) {
+        RFX_CHECK_CUDA(cudaEventRecord(h->ev_ist[io->slot][ch], s));
+        RFX_CHECK_CUDA(cudaStreamWaitEvent(h->copy_out, h->ev_ist[io->slot][ch], 0));
+        RFX_CHECK_CUDA(cudaMemcpyAsync(io->out_host + (size_t)i0 * T, c.out + (size_t)i0 * T, (size_t)(i1 - i0) * T * 4,
+                                       cudaMemcpyDeviceToHost, h->copy_out));
+      }
+    }
+    if (d2h) RFX_CHECK_CUDA(cudaEventRecord(h->ev_out[io->slot], h->copy_out));
+    if ((rc = mark())) return rc;
+  }
+  return 0;
+}
+
+int umx_check_call(rfx_umx_t* h, const void* x, int B, int T, const void* out, const void* workspace) {
+  RFX_REQUIRE(h && x && out && workspace, "null argument");
+  RFX_REQUIRE(h->finalized, "rfx_umx_finalize has not been called since the last parameter load");
+  RFX_REQUIRE(B > 0 && T > h->cfg.n_fft / 2, "need B > 0 and T > n_fft/2 (reflect padding)");
+  RFX_REQUIRE(T % h->cfg.hop == 0, "T must be a multiple of the hop length");
+  RFX_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  return 0;
+}
+
+int umx_forward(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, void* stream, const HostIO* io) {
+  int rc;
+  if ((rc = umx_check_call(h, x, B, T, out, workspace))) return rc;
+  UmxCall c{};
+  c.x = x; c.out = out; c.B = B; c.T = T;
+  c.ws = reinterpret_cast<uint8_t*>(workspace);
+  c.L = umx_layout(h, B, T);
+  RFX_REQUIRE(workspace_bytes >= c.L.total, "workspace too small (see rfx_umx_workspace_bytes)");
+  c.s = c.s_rec = (cudaStream_t)stream;
+  c.io = io;
+  const int nl = h->cfg.nb_layers;
   const int n_stage = 5 + 2 * nl;
   if (h->profiling && (int)h->events.size() != n_stage + 1) {
     for (auto e : h->events) cudaEventDestroy(e);
     h->events.assign(n_stage + 1, nullptr);
     for (auto& e : h->events) RFX_CHECK_CUDA(cudaEventCreate(&e));
   }
-  int stage = 0;
-  auto mark = [&]() -> int {
-    if (h->profiling) RFX_CHECK_CUDA(cudaEventRecord(h->events[stage], s));
-    ++stage;
-    return 0;
-  };
-  if ((rc = mark())) return rc;
-
-  // (1) STFT (transforms.py:106-116) + ComplexNorm (:211) + input shift/scale (model.py:127-128) -> split planes
-  StftParams sp{};
-  sp.x = x; sp.x_bstride = T; sp.T = T;
-  sp.x_aligned8 = (((uintptr_t)x & 7) == 0 && (T % 2 == 0)) ? 1 : 0;
-  sp.window = P(h, "window"); sp.tw = tw;
-  sp.n_fft = h->cfg.n_fft; sp.hop = h->cfg.hop; sp.F = L.F;
-  sp.frame_off = h->cfg.n_fft / 2; sp.nbins = h->bins;
-  sp.scale = 1.0f; sp.alpha = 1.0f; sp.mode = STFT_UMX_MAG;
-  sp.Z = Z; sp.ldz = h->bins; sp.A = nullptr; sp.lda = 0;
-  sp.Ahi = A1; sp.Alo = A1 + L.plane_A1; sp.ldas = L.lda1;
-  sp.in_mean = P(h, "input_mean"); sp.in_scale = P(h, "input_scale");
-  const int nch = io ? std::min(B, (int)rfx_umx::kChunks) : 1;
-  for (int c = 0; c < nch; ++c) {
-    const int i0 = (int)((long long)B * c / nch), i1 = (int)((long long)B * (c + 1) / nch);
-    if (io) {
-      RFX_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(x) + (size_t)i0 * T, io->x_host + (size_t)i0 * T, (size_t)(i1 - i0) * T * 4,
-                                     cudaMemcpyHostToDevice, h->copy_in));
-      RFX_CHECK_CUDA(cudaEventRecord(h->ev_in[io->slot][c], h->copy_in));
-    }
-  }
-  for (int c = 0; c < nch; ++c) {
-    const int i0 = (int)((long long)B * c / nch), i1 = (int)((long long)B * (c + 1) / nch);
-    StftParams sc = sp;
-    sc.x = x + (size_t)i0 * T;
-    sc.Z = Z + (size_t)i0 * L.F * h->bins;
-    sc.Ahi = A1 + (size_t)i0 * L.F * L.lda1; sc.Alo = sc.Ahi + L.plane_A1;
-    if (io) RFX_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_in[io->slot][c], 0));
-    if ((rc = launch_stft(sc, i1 - i0, s))) return rc;
-  }
-  if ((rc = mark())) return rc;
-
-  // (2) fc1 + bn1 + tanh (model.py:132-138) -> first half of the skip-concat buffer
-  Epilogue e1; e1.s1 = h->bn_s[0].p; e1.t1 = h->bn_t[0].p; e1.act = ACT_TANH;
-  if ((rc = dense(A1, L.plane_A1, L.lda1, L.M, h->bins, h->fc1p, nullptr, 0, XC, L.plane_XC, 2 * hid, e1, s)) || (rc = mark())) return rc;
-
-  // (3) BiLSTM stack (model.py:141): per layer one input-projection GEMM + one recurrent cluster kernel
-  const __nv_bfloat16* lin = XC; size_t lin_plane = L.plane_XC; int ldin = 2 * hid;
-  for (int l = 0; l < nl; ++l) {
-    Epilogue eb; eb.t1 = h->lstm_bias[l].p;
-    if ((rc = dense(lin, lin_plane, ldin, L.M, hid, h->wihp[l], G, 8 * H, nullptr, 0, 0, eb, s)) || (rc = mark())) return rc;
-    __nv_bfloat16* hout; size_t hplane; int ldh;
-    if (l == nl - 1) { hout = XC + hid; hplane = L.plane_XC; ldh = 2 * hid; }  // torch.cat([x, lstm_out], -1) (model.py:144) for free
-    else { hout = Hb[l & 1]; hplane = L.plane_H; ldh = hid; }
-    if ((rc = launch_lstm_layer(G, 8 * H, h->whh_cat[l].p, nullptr, 0, hout, hout + hplane, ldh, B, L.F, H, s)) || (rc = mark())) return rc;
-    lin = hout; lin_plane = hplane; ldin = ldh;
-  }
-
-  // (4) fc2 + bn2 + ReLU (model.py:147-150)
-  Epilogue e2; e2.s1 = h->bn_s[1].p; e2.t1 = h->bn_t[1].p; e2.act = ACT_RELU;
-  if ((rc = dense(XC, L.plane_XC, 2 * hid, L.M, 2 * hid, h->fc2p, nullptr, 0, Y2, L.plane_Y2, hid, e2, s)) || (rc = mark())) return rc;
-
-  // (5) fc3 + bn3 + output scale/mean + ReLU (model.py:153-164) = the non-negative ratio mask
-  Epilogue e3; e3.s1 = h->bn_s[2].p; e3.t1 = h->bn_t[2].p; e3.s2 = P(h, "output_scale"); e3.t2 = P(h, "output_mean"); e3.act = ACT_RELU;
-  if ((rc = dense(Y2, L.plane_Y2, hid, L.M, hid, h->fc3p, mask, L.ldm, nullptr, 0, 0, e3, s)) || (rc = mark())) return rc;
-
-  // (6) `* mix` (model.py:164) + wiener niter=0 (filtering.py:442-451) + iSTFT (transforms.py:168-177)
-  IstftParams ip{};
-  ip.Z = Z; ip.ldz = h->bins; ip.mask = mask; ip.ldm = L.ldm;
-  ip.window = P(h, "window"); ip.tw = tw;
-  ip.n_fft = h->cfg.n_fft; ip.hop = h->cfg.hop; ip.F = L.F; ip.length = T;
-  ip.frame_off = h->cfg.n_fft / 2; ip.env_pad = 0; ip.nbins = h->bins;
-  ip.scale = 1.0f; ip.out = out; ip.out_bstride = T; ip.hops_per_cta = 16;
-  for (int c = 0; c < nch; ++c) {
-    const int i0 = (int)((long long)B * c / nch), i1 = (int)((long long)B * (c + 1) / nch);
-    IstftParams ic = ip;
-    ic.Z = Z + (size_t)i0 * L.F * h->bins;
-    ic.mask = mask + (size_t)i0 * L.F * L.ldm;
-    ic.out = out + (size_t)i0 * T;
-    if ((rc = launch_istft(ic, i1 - i0, s))) return rc;
-    if (io) {
-      RFX_CHECK_CUDA(cudaEventRecord(h->ev_ist[io->slot][c], s));
-      RFX_CHECK_CUDA(cudaStreamWaitEvent(h->copy_out, h->ev_ist[io->slot][c], 0));
-      RFX_CHECK_CUDA(cudaMemcpyAsync(io->out_host + (size_t)i0 * T, out + (size_t)i0 * T, (size_t)(i1 - i0) * T * 4, cudaMemcpyDeviceToHost,
-                                     h->copy_out));
-    }
-  }
-  if (io) RFX_CHECK_CUDA(cudaEventRecord(h->ev_out[io->slot], h->copy_out));
-  if ((rc = mark())) return rc;
+  h->mark_idx = 0;
+  if (h->profiling) RFX_CHECK_CUDA(cudaEventRecord(h->events[0], c.s));
+  h->mark_idx = 1;
+  for (int l = 0; l < nl; ++l)
+    if ((rc = umx_stage(h, c, l))) return rc;
   return 0;
 }
 
@@ -406,7 +496,190 @@ int umx_host_setup(rfx_umx_t* h) {
   }
   return 0;
 }
+
+// ---- multi-lane pipeline ------------------------------------------------------------------------------------------
+int umx_pipe_setup(rfx_umx_t* h, int B, int T) {
+  rfx_umx::Pipe& p = h->pipe;
+  int rc;
+  if ((rc = umx_host_setup(h))) return rc;
+  if (!p.ready) {
+    RFX_REQUIRE(h->cfg.nb_layers <= rfx_umx::kSlots, "the pipeline supports at most 4 LSTM layers");
+    p.depth = h->cfg.nb_layers;
+    int lo = 0, hi = 0;  // numerically lowest value = highest priority
+    RFX_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    RFX_CHECK_CUDA(cudaStreamCreateWithPriority(&p.rec, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < p.depth; ++i) {
+      rfx_umx::Lane& l = p.lane[i];
+      RFX_CHECK_CUDA(cudaStreamCreateWithPriority(&l.s, cudaStreamNonBlocking, lo));
+      for (cudaEvent_t* e : {&l.ev_x, &l.ev_pre, &l.ev_rec, &l.ev_stft, &l.ev_done})
+        RFX_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    RFX_CHECK_CUDA(cudaDeviceGetAttribute(&p.sms, cudaDevAttrMultiProcessorCount, dev));
+    p.ready = true;
+  }
+  if (p.B != B || p.T != T) {
+    for (int i = 0; i < p.depth; ++i) RFX_REQUIRE(!p.lane[i].live, "pipeline: batch shape changed while steps are in flight (flush first)");
+    p.B = B; p.T = T;
+    // The recurrences are packed into the fewest SMs (8 batch slots per cluster); every other kernel keeps to the rest of
+    // the chip so that a recurrence launch never waits for SMs.  Too small a remainder -> no partition.
+    const int rec_sms = 8 * lstm_clusters_for(B, 8);
+    if (p.sms - rec_sms >= p.sms / 4) { p.max_sms = p.sms - rec_sms; p.lstm_slots = 8; }
+    else { p.max_sms = 0; p.lstm_slots = 0; }
+    // tuning overrides (experiments only)
+    if (const char* e = getenv("RFX_UMX_PIPE_MAX_SMS")) p.max_sms = atoi(e);
+    if (const char* e = getenv("RFX_UMX_PIPE_SLOTS")) p.lstm_slots = atoi(e);
+  }
+  return 0;
+}
+
+// One super-step: every live lane advances by one stage, deepest stage first, so the recurrences reach the shared
+// stream in the order (last layer of the oldest step, ..., first layer of the newest step).
+int umx_pipe_superstep(rfx_umx_t* h) {
+  rfx_umx::Pipe& p = h->pipe;
+  const int nl = h->cfg.nb_layers;
+  const UmxLayout L = umx_layout(h, p.B, p.T);
+  for (int st = nl - 1; st >= 0; --st) {
+    for (int i = 0; i < p.depth; ++i) {
+      rfx_umx::Lane& ln = p.lane[i];
+      if (!ln.live || ln.next_stage != st) continue;
+      HostIO io{ln.x_host, ln.out_host, i};
+      UmxCall c{};
+      c.B = p.B; c.T = p.T;
+      c.ws = reinterpret_cast<uint8_t*>(p.ws) + (size_t)i * L.total;
+      c.L = L;
+      c.x = ln.x_host ? reinterpret_cast<const float*>(c.ws + L.off_x[0]) : ln.x;
+      c.out = ln.out_host ? reinterpret_cast<float*>(c.ws + L.off_out[0]) : ln.out;
+      c.s = ln.s; c.s_rec = p.rec;
+      c.ev_pre = ln.ev_pre; c.ev_rec = ln.ev_rec; c.ev_stft = ln.ev_stft;
+      c.io = (ln.x_host || ln.out_host) ? &io : nullptr;
+      c.max_sms = p.max_sms; c.lstm_slots = p.lstm_slots;
+      if (st == 0 && ln.x_host && ln.stft_recorded) RFX_CHECK_CUDA(cudaStreamWaitEvent(h->copy_in, ln.ev_stft, 0));  // staging free
+      int rc;
+      if ((rc = umx_stage(h, c, st))) return rc;
+      if (st == 0) ln.stft_recorded = true;
+      ln.next_stage = st + 1;
+      if (st == nl - 1) {
+        if (ln.out_host) {
+          RFX_CHECK_CUDA(cudaStreamWaitEvent(h->copy_out, h->ev_out[i], 0));
+          RFX_CHECK_CUDA(cudaEventRecord(ln.ev_done, h->copy_out));
+          ln.host_out_pending = true;
+        } else {
+          RFX_CHECK_CUDA(cudaEventRecord(ln.ev_done, ln.s));
+        }
+        ln.done_recorded = true;
+        ln.live = false;
+      }
+    }
+  }
+  return 0;
+}
 }  // namespace
+
+int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return umx_forward(h, x, B, T, out, workspace, workspace_bytes, stream, nullptr);
+}
+
+size_t rfx_umx_pipe_workspace_bytes(const rfx_umx_t* h, int B, int T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  return (size_t)h->cfg.nb_layers * umx_layout(h, B, T).total;
+}
+
+int rfx_umx_pipe_depth(const rfx_umx_t* h) { return h ? h->cfg.nb_layers : 0; }
+
+int rfx_umx_pipe_push(rfx_umx_t* h, const float* x, int x_on_host, int B, int T, float* out, int out_on_host, void* workspace,
+                      size_t workspace_bytes, void* stream, long long* seq_out) {
+  int rc;
+  if ((rc = umx_check_call(h, x, B, T, out, workspace))) return rc;
+  RFX_REQUIRE(workspace_bytes >= rfx_umx_pipe_workspace_bytes(h, B, T), "workspace too small (see rfx_umx_pipe_workspace_bytes)");
+  if ((rc = umx_pipe_setup(h, B, T))) return rc;
+  rfx_umx::Pipe& p = h->pipe;
+  bool any_live = false;
+  for (int i = 0; i < p.depth; ++i) any_live = any_live || p.lane[i].live;
+  RFX_REQUIRE(!any_live || p.ws == workspace, "pipeline: the workspace must not change while steps are in flight");
+  p.ws = workspace;
+  const long long seq = p.pushed;
+  rfx_umx::Lane& ln = p.lane[seq % p.depth];
+  RFX_REQUIRE(!ln.live, "pipeline: internal lane accounting error");
+  cudaStream_t caller = (cudaStream_t)stream;
+  // The lane starts after everything the caller has enqueued so far (producer of x, last consumer of out) ...
+  RFX_CHECK_CUDA(cudaEventRecord(ln.ev_x, caller));
+  RFX_CHECK_CUDA(cudaStreamWaitEvent(ln.s, ln.ev_x, 0));
+  // ... and after the previous D2H out of this lane's output staging buffer.
+  if (ln.host_out_pending) { RFX_CHECK_CUDA(cudaStreamWaitEvent(ln.s, ln.ev_done, 0)); ln.host_out_pending = false; }
+  ln.x = x_on_host ? nullptr : x; ln.x_host = x_on_host ? x : nullptr;
+  ln.out = out_on_host ? nullptr : out; ln.out_host = out_on_host ? out : nullptr;
+  ln.seq = seq; ln.next_stage = 0; ln.live = true; ln.done_recorded = false;
+  p.pushed = seq + 1;
+  if (seq_out) *seq_out = seq;
+  return umx_pipe_superstep(h);
+}
+
+int rfx_umx_pipe_flush(rfx_umx_t* h, void* stream) {
+  RFX_REQUIRE(h, "null handle");
+  rfx_umx::Pipe& p = h->pipe;
+  if (!p.ready) return 0;
+  int rc;
+  for (int guard = 0; guard < rfx_umx::kSlots; ++guard) {
+    bool any_live = false;
+    for (int i = 0; i < p.depth; ++i) any_live = any_live || p.lane[i].live;
+    if (!any_live) break;
+    if ((rc = umx_pipe_superstep(h))) return rc;
+  }
+  for (int i = 0; i < p.depth; ++i)
+    if (p.lane[i].done_recorded) RFX_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, p.lane[i].ev_done, 0));
+  return 0;
+}
+
+static int umx_pipe_find(rfx_umx_t* h, long long seq, rfx_umx::Lane** out) {
+  RFX_REQUIRE(h && h->pipe.ready, "pipeline not started");
+  rfx_umx::Pipe& p = h->pipe;
+  RFX_REQUIRE(seq >= 0 && seq < p.pushed, "pipeline: unknown step");
+  rfx_umx::Lane& ln = p.lane[seq % p.depth];
+  RFX_REQUIRE(ln.seq == seq, "pipeline: that step's lane has been reused (wait for a step before pushing `depth` more)");
+  RFX_REQUIRE(ln.done_recorded, "pipeline: that step has not left the pipeline yet (push depth-1 more steps, or flush)");
+  *out = &ln;
+  return 0;
+}
+
+int rfx_umx_pipe_wait(rfx_umx_t* h, long long seq) {
+  rfx_umx::Lane* ln = nullptr;
+  int rc;
+  if ((rc = umx_pipe_find(h, seq, &ln))) return rc;
+  RFX_CHECK_CUDA(cudaEventSynchronize(ln->ev_done));
+  return 0;
+}
+
+int rfx_umx_pipe_stream_wait(rfx_umx_t* h, long long seq, void* stream) {
+  rfx_umx::Lane* ln = nullptr;
+  int rc;
+  if ((rc = umx_pipe_find(h, seq, &ln))) return rc;
+  RFX_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ln->ev_done, 0));
+  return 0;
+}
+
+int rfx_umx_pipe_set_profiling(rfx_umx_t* h, int max_launches) {
+  RFX_REQUIRE(h && max_launches >= 0 && max_launches <= 4096, "bad argument");
+  rfx_umx::Pipe& p = h->pipe;
+  while ((int)p.prof_ev.size() < 2 * max_launches) {
+    cudaEvent_t e;
+    RFX_CHECK_CUDA(cudaEventCreate(&e));
+    p.prof_ev.push_back(e);
+  }
+  p.prof = max_launches > 0;
+  p.prof_n = 0;
+  return 0;
+}
+
+int rfx_umx_pipe_rec_times(rfx_umx_t* h, float* ms, int capacity, int* n_out) {
+  RFX_REQUIRE(h && ms && n_out, "null argument");
+  rfx_umx::Pipe& p = h->pipe;
+  const int n = p.prof_n < capacity ? p.prof_n : capacity;
+  for (int i = 0; i < n; ++i) RFX_CHECK_CUDA(cudaEventElapsedTime(&ms[i], p.prof_ev[2 * i], p.prof_ev[2 * i + 1]));
+  *n_out = n;
+  return 0;
+}
 
 int rfx_umx_set_profiling(rfx_umx_t* h, int on) {
   RFX_REQUIRE(h, "null handle");
@@ -425,7 +698,7 @@ int rfx_umx_stage_times(rfx_umx_t* h, float* ms, int capacity, int* n_out) {
 }
 
 int rfx_umx_wait_host(rfx_umx_t* h, int slot) {
-  RFX_REQUIRE(h && slot >= 0 && slot < rfx_umx::kSlots, "bad handle / slot");
+  RFX_REQUIRE(h && slot >= 0 && slot < rfx_umx::kHostSlots, "bad handle / slot");
   if (h->pending[slot]) {
     RFX_CHECK_CUDA(cudaEventSynchronize(h->ev_out[slot]));
     h->pending[slot] = false;
@@ -436,7 +709,7 @@ int rfx_umx_wait_host(rfx_umx_t* h, int slot) {
 int rfx_umx_submit_host(rfx_umx_t* h, int slot, const float* x_host, int B, int T, float* out_host, void* workspace, size_t workspace_bytes,
                         void* stream) {
   RFX_REQUIRE(h && x_host && out_host && workspace, "null argument");
-  RFX_REQUIRE(slot >= 0 && slot < rfx_umx::kSlots, "slot must be 0 or 1");
+  RFX_REQUIRE(slot >= 0 && slot < rfx_umx::kHostSlots, "slot must be 0 or 1");
   RFX_REQUIRE(B > 0 && T > 0, "positive sizes");
   const UmxLayout L = umx_layout(h, B, T);
   RFX_REQUIRE(workspace_bytes >= L.total, "workspace too small (see rfx_umx_workspace_bytes)");

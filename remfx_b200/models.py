@@ -215,6 +215,95 @@ class OpenUnmixModel(nn.Module):
     def launches_per_call(self) -> int:
         return 5 + 2 * self.model.nb_layers
 
+    def pipeline(self, device="cuda:0") -> "UmxPipeline":
+        """Throughput form of `sample` for a stream of equally shaped batches (see UmxPipeline)."""
+        return UmxPipeline(self, device)
+
+
+class UmxPipeline:
+    """Multi-lane pipelined `OpenUnmixModel.sample` (rfx_umx_pipe_* in include/remfx_b200.h).
+
+    `push(x, out)` enqueues one batch and returns its sequence number; batch n leaves the pipeline during push(n + depth - 1)
+    or `flush()`.  x / out are CUDA tensors, or pinned CPU tensors (the copies then run on the library's copy streams).
+    The per-step results are those of `sample` (same kernels in the same order); only the scheduling differs: the LSTM
+    recurrences of `depth` consecutive batches run back to back on their own stream while every other kernel of those
+    batches runs beside them on the SMs the recurrence does not use.
+    """
+
+    def __init__(self, model: OpenUnmixModel, device="cuda:0"):
+        self.model = model
+        self.device = torch.device(device)
+        self._ws: Optional[Tensor] = None
+        self._shape = None
+        self._keep = {}
+        with torch.cuda.device(self.device):
+            self._h = model._sync(self.device)
+        self.depth = _lib.lib().rfx_umx_pipe_depth(self._h)
+
+    @staticmethod
+    def _check(t: Tensor, name: str) -> bool:
+        if t.dim() != 3 or t.shape[1] != 1 or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"{name}: expected a contiguous float32 tensor of shape (batch, 1, time)")
+        if not t.is_cuda and not t.is_pinned():
+            raise ValueError(f"{name}: host tensors must be pinned (pageable memory would make the copies synchronous)")
+        return not t.is_cuda
+
+    def push(self, x: Tensor, out: Optional[Tensor] = None) -> int:
+        x_host = self._check(x, "x")
+        if out is None:
+            out = torch.empty_like(x, pin_memory=True) if x_host else torch.empty_like(x)
+        out_host = self._check(out, "out")
+        if out.shape != x.shape:
+            raise ValueError("out must be shaped like x")
+        for t in (x, out):
+            if t.is_cuda and t.device != self.device:
+                raise _lib.RfxError(f"tensor on {t.device}, pipeline on {self.device}")
+        B, _, T = x.shape
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            h = self.model._sync(self.device)
+            if self._shape != (B, T):
+                self.flush()
+                need = L.rfx_umx_pipe_workspace_bytes(h, B, T)
+                if self._ws is None or self._ws.numel() < need:
+                    torch.cuda.synchronize(self.device)
+                    self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+                self._shape = (B, T)
+            seq = C.c_longlong(-1)
+            rc = L.rfx_umx_pipe_push(h, x.data_ptr(), int(x_host), B, T, out.data_ptr(), int(out_host), self._ws.data_ptr(),
+                                     self._ws.numel(), _lib.cur_stream(), C.byref(seq))
+            _lib.check(rc, "rfx_umx_pipe_push")
+        self._keep[seq.value] = (x, out)  # keep the buffers alive while the step is in flight
+        for old in [k for k in self._keep if k <= seq.value - 2 * self.depth]:
+            del self._keep[old]
+        return seq.value
+
+    def flush(self) -> None:
+        """Run the stages still owed to the batches in flight; the current stream then waits for all their outputs."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().rfx_umx_pipe_flush(self._h, _lib.cur_stream()), "rfx_umx_pipe_flush")
+
+    def wait(self, seq: int) -> Tensor:
+        """Block the host until batch `seq`'s output is complete; returns the output tensor given to push."""
+        _lib.check(_lib.lib().rfx_umx_pipe_wait(self._h, int(seq)), "rfx_umx_pipe_wait")
+        return self._keep[seq][1] if seq in self._keep else None
+
+    def set_profiling(self, max_launches: int) -> None:
+        """Time the next `max_launches` recurrence launches with cudaEvents on the recurrence stream (0 = off)."""
+        _lib.check(_lib.lib().rfx_umx_pipe_set_profiling(self._h, int(max_launches)), "rfx_umx_pipe_set_profiling")
+
+    def recurrence_times_ms(self) -> list:
+        """Durations of the profiled recurrence launches (device must be synchronised first)."""
+        buf = (C.c_float * 4096)()
+        n = C.c_int()
+        _lib.check(_lib.lib().rfx_umx_pipe_rec_times(self._h, buf, 4096, C.byref(n)), "rfx_umx_pipe_rec_times")
+        return [buf[i] for i in range(n.value)]
+
+    def stream_wait(self, seq: int) -> None:
+        """Make the current CUDA stream wait for batch `seq`'s output (no host blocking)."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().rfx_umx_pipe_stream_wait(self._h, int(seq), _lib.cur_stream()), "rfx_umx_pipe_stream_wait")
+
 
 # ======================================================================================================
 # TCN

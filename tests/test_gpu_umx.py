@@ -94,3 +94,53 @@ def test_bad_inputs_raise():
         m.sample(torch.zeros(2, 16384, device="cuda"))
     with pytest.raises(RuntimeError):
         m.sample(torch.zeros(1, 1, 16384))
+
+
+@pytest.mark.parametrize("host", [False, True])
+def test_pipeline_equals_sample(host):
+    """The multi-lane pipeline runs the same kernels in the same per-step order: outputs are bit-identical to sample()."""
+    sd = weights.umx_state(5)
+    m = _model(sd)
+    B, T, n = 5, 32768, 8
+    xs = [weights.synth_audio(300 + i, B, T) for i in range(n)]
+    refs = [m.sample(x.cuda()).cpu() for x in xs]
+    pipe = m.pipeline("cuda:0")
+    assert pipe.depth == 3
+    if host:
+        ins = [x.pin_memory() for x in xs]
+        outs = [torch.empty(B, 1, T).pin_memory() for _ in range(n)]
+    else:
+        ins = [x.cuda() for x in xs]
+        outs = [torch.empty(B, 1, T, device="cuda") for _ in range(n)]
+    seqs = []
+    for i in range(n):
+        seqs.append(pipe.push(ins[i], outs[i]))
+        if i >= pipe.depth - 1:
+            done = seqs[i - (pipe.depth - 1)]
+            pipe.wait(done)  # step i - 2 has left the pipeline
+            assert torch.equal(outs[i - (pipe.depth - 1)].cpu(), refs[i - (pipe.depth - 1)])
+    pipe.flush()
+    torch.cuda.synchronize()
+    for i in range(n):
+        assert torch.equal(outs[i].cpu(), refs[i]), i
+    # a second burst on the same pipeline object (lanes restart cleanly after a flush), mixed with a shape change
+    s = pipe.push(ins[0], outs[1])
+    pipe.flush()
+    pipe.wait(s)
+    assert torch.equal(outs[1].cpu(), refs[0])
+    x2 = weights.synth_audio(999, 2, 16384)
+    s2 = pipe.push(x2.cuda())
+    pipe.flush()
+    o2 = pipe.wait(s2)
+    assert torch.equal(o2.cpu(), m.sample(x2.cuda()).cpu())
+
+
+def test_pipeline_wait_before_exit_raises():
+    sd = weights.umx_state(5)
+    m = _model(sd)
+    pipe = m.pipeline("cuda:0")
+    s = pipe.push(weights.synth_audio(1, 2, 16384).cuda())
+    with pytest.raises(Exception):
+        pipe.wait(s)  # still inside the pipeline: needs depth-1 more pushes or a flush
+    pipe.flush()
+    pipe.wait(s)
