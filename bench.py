@@ -238,7 +238,7 @@ def run_ours(args):
 
     # ---- end-to-end through the public API on host buffers ---------------------------------------------
     # Headline e2e = the pipeline on pinned HOST tensors: every step does its own H2D (33.5 MB) and D2H (33.5 MB) inside
-    # the timed region and the loop consumes every result (wait() on step k - 2 before pushing k + 1, as a serving loop
+    # the timed region and the loop consumes every result (wait() on step k - 4 before pushing k, as a serving loop
     # would); host wall clock, stopped when the last result is in host memory.  Beside it: one blocking call per step.
     outs_host = [torch.empty(BATCH, 1, T, dtype=torch.float32).pin_memory() for _ in range(nout)]
     out_host = outs_host[0]
@@ -258,13 +258,14 @@ def run_ours(args):
     pipe.flush()
     barrier()
     seqs = []
+    lag = depth + 1   # results are consumed `lag` steps behind the newest push (lag + 1 host buffers in flight <= nout)
     t0 = time.perf_counter()
     for k in range(args.steps):
+        if k >= lag:
+            pipe.wait(seqs[k - lag])
         seqs.append(pipe.push(xs_host[k % NBUF], outs_host[k % nout]))
-        if k >= depth - 1:
-            pipe.wait(seqs[k - (depth - 1)])
     pipe.flush()
-    for sq in seqs[-(depth - 1):]:
+    for sq in seqs[-lag:]:
         pipe.wait(sq)
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0)   # host wall clock: every result is in host memory when it stops

@@ -69,6 +69,9 @@ int rfx_lstm_info(int B, int* max_active_clusters, int* batch_per_cluster);
 /* Process-wide choice of the recurrence kernel: 0 = tensor-core (mma.sync bf16x3, default), 1 = fp32 FFMA. */
 int rfx_lstm_set_impl(int impl);
 int rfx_lstm_layer(const float* G, const float* Whh, float* Hout, int ldh, int B, int F, int H, void* stream);
+/* Same with the batch slots per 8-CTA cluster fixed by the caller: 1..8 = one MMA n-tile, 9..16 = two n-tiles per cluster
+ * (H = 256 only; half the SMs per launch, used by the Open-Unmix pipeline); 0 = automatic as above. */
+int rfx_lstm_layer_slots(const float* G, const float* Whh, float* Hout, int ldh, int B, int F, int H, int slots, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * U1-U5  Open-Unmix effect-removal model
@@ -122,7 +125,8 @@ int rfx_umx_wait_host(rfx_umx_t* h, int slot);
  *          the step's output is complete.  Step s leaves the pipeline during push(s + depth - 1) or flush.
  *   flush  runs the stages still owed to the steps in flight and makes `stream` wait for every finished output.
  *   wait / stream_wait  block the host / make `stream` wait until step seq's output is complete (the step must have left the
- *          pipeline; a lane is reused `depth` pushes later, so wait for a step before pushing `depth` more).
+ *          pipeline; completion records are kept for the last 16 steps).  A consumer that waits for step n - depth - 1
+ *          before push(n) keeps a full super-step queued behind the one that is executing.
  * workspace: rfx_umx_pipe_workspace_bytes (= depth private lanes), the same pointer for every push until a flush. */
 size_t rfx_umx_pipe_workspace_bytes(const rfx_umx_t* h, int B, int T);
 int rfx_umx_pipe_depth(const rfx_umx_t* h);

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "rfx_lstm_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rfx_lstm_set_impl": (C.c_int, [C.c_int]),
     "rfx_lstm_layer": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "rfx_lstm_layer_slots": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "rfx_umx_create": (C.c_int, [C.POINTER(UmxConfig), C.POINTER(C.c_void_p)]),
     "rfx_umx_destroy": (None, [C.c_void_p]),
     "rfx_umx_load_param": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int64, C.c_void_p]),

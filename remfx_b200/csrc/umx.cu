@@ -85,18 +85,24 @@ struct rfx_umx {
   // multi-lane pipeline state (see rfx_umx_pipe_push)
   struct Lane {
     cudaStream_t s = nullptr;
-    cudaEvent_t ev_x = nullptr, ev_pre = nullptr, ev_rec = nullptr, ev_stft = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_x = nullptr, ev_pre = nullptr, ev_rec = nullptr, ev_stft = nullptr;
     const float* x = nullptr; float* out = nullptr;          // device buffers of the step in the lane
     const float* x_host = nullptr; float* out_host = nullptr;  // host buffers (null = device-resident)
     long long seq = -1;
     int next_stage = 0;
-    bool live = false, done_recorded = false, stft_recorded = false, host_out_pending = false;
+    bool live = false, stft_recorded = false;
+    cudaEvent_t host_out_pending = nullptr;  // completion event of the last D2H out of this lane's output staging buffer
   };
+  static constexpr int kRing = 16;  // completion events are kept for the last kRing steps
+  struct Done { cudaEvent_t ev = nullptr; long long seq = -1; bool recorded = false; };
   struct Pipe {
     bool ready = false;
     int depth = 0, B = 0, T = 0;
-    cudaStream_t rec = nullptr;  // all recurrence launches, in issue order, at the highest stream priority
+    cudaStream_t rec[2] = {nullptr, nullptr};  // recurrence launches, round-robin in issue order, at the highest stream priority
+    int rec_n = 1;                              // recurrence streams in use (2 = two launches side by side)
+    long long rec_count = 0;
     Lane lane[kSlots];
+    Done done[kRing];
     long long pushed = 0;
     void* ws = nullptr;
     int sms = 0, max_sms = 0, lstm_slots = 0;
@@ -117,10 +123,13 @@ struct rfx_umx {
       if (ev_out[i]) cudaEventDestroy(ev_out[i]);
       Lane& l = pipe.lane[i];
       if (l.s) cudaStreamDestroy(l.s);
-      for (cudaEvent_t e : {l.ev_x, l.ev_pre, l.ev_rec, l.ev_stft, l.ev_done})
+      for (cudaEvent_t e : {l.ev_x, l.ev_pre, l.ev_rec, l.ev_stft})
         if (e) cudaEventDestroy(e);
     }
-    if (pipe.rec) cudaStreamDestroy(pipe.rec);
+    for (auto& d : pipe.done)
+      if (d.ev) cudaEventDestroy(d.ev);
+    for (auto r : pipe.rec)
+      if (r) cudaStreamDestroy(r);
     for (auto e : pipe.prof_ev) cudaEventDestroy(e);
     for (auto e : events) cudaEventDestroy(e);
     for (auto& kv : params) kv.second.release();
@@ -507,13 +516,14 @@ int umx_pipe_setup(rfx_umx_t* h, int B, int T) {
     p.depth = h->cfg.nb_layers;
     int lo = 0, hi = 0;  // numerically lowest value = highest priority
     RFX_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    RFX_CHECK_CUDA(cudaStreamCreateWithPriority(&p.rec, cudaStreamNonBlocking, hi));
+    for (auto& r : p.rec) RFX_CHECK_CUDA(cudaStreamCreateWithPriority(&r, cudaStreamNonBlocking, hi));
     for (int i = 0; i < p.depth; ++i) {
       rfx_umx::Lane& l = p.lane[i];
       RFX_CHECK_CUDA(cudaStreamCreateWithPriority(&l.s, cudaStreamNonBlocking, lo));
-      for (cudaEvent_t* e : {&l.ev_x, &l.ev_pre, &l.ev_rec, &l.ev_stft, &l.ev_done})
+      for (cudaEvent_t* e : {&l.ev_x, &l.ev_pre, &l.ev_rec, &l.ev_stft})
         RFX_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
+    for (auto& d : p.done) RFX_CHECK_CUDA(cudaEventCreateWithFlags(&d.ev, cudaEventDisableTiming));
     int dev = 0;
     cudaGetDevice(&dev);
     RFX_CHECK_CUDA(cudaDeviceGetAttribute(&p.sms, cudaDevAttrMultiProcessorCount, dev));
@@ -524,12 +534,15 @@ int umx_pipe_setup(rfx_umx_t* h, int B, int T) {
     p.B = B; p.T = T;
     // The recurrences are packed into the fewest SMs (8 batch slots per cluster); every other kernel keeps to the rest of
     // the chip so that a recurrence launch never waits for SMs.  Too small a remainder -> no partition.
-    const int rec_sms = 8 * lstm_clusters_for(B, 8);
-    if (p.sms - rec_sms >= p.sms / 4) { p.max_sms = p.sms - rec_sms; p.lstm_slots = 8; }
-    else { p.max_sms = 0; p.lstm_slots = 0; }
+    int slots = 8, streams = 1;
     // tuning overrides (experiments only)
+    if (const char* e = getenv("RFX_UMX_PIPE_SLOTS")) slots = atoi(e);
+    if (const char* e = getenv("RFX_UMX_PIPE_REC_STREAMS")) streams = atoi(e) == 2 ? 2 : 1;
+    const int rec_sms = streams * 8 * lstm_clusters_for(B, slots);
+    if (slots > 0 && p.sms - rec_sms >= p.sms / 4) { p.max_sms = p.sms - rec_sms; p.lstm_slots = slots; p.rec_n = streams; }
+    else { p.max_sms = 0; p.lstm_slots = slots > 0 ? 0 : slots; p.rec_n = 1; }
+    if (slots == 0) p.lstm_slots = 0;
     if (const char* e = getenv("RFX_UMX_PIPE_MAX_SMS")) p.max_sms = atoi(e);
-    if (const char* e = getenv("RFX_UMX_PIPE_SLOTS")) p.lstm_slots = atoi(e);
   }
   return 0;
 }
@@ -551,7 +564,7 @@ int umx_pipe_superstep(rfx_umx_t* h) {
       c.L = L;
       c.x = ln.x_host ? reinterpret_cast<const float*>(c.ws + L.off_x[0]) : ln.x;
       c.out = ln.out_host ? reinterpret_cast<float*>(c.ws + L.off_out[0]) : ln.out;
-      c.s = ln.s; c.s_rec = p.rec;
+      c.s = ln.s; c.s_rec = p.rec[p.rec_count++ % p.rec_n];
       c.ev_pre = ln.ev_pre; c.ev_rec = ln.ev_rec; c.ev_stft = ln.ev_stft;
       c.io = (ln.x_host || ln.out_host) ? &io : nullptr;
       c.max_sms = p.max_sms; c.lstm_slots = p.lstm_slots;
@@ -561,14 +574,14 @@ int umx_pipe_superstep(rfx_umx_t* h) {
       if (st == 0) ln.stft_recorded = true;
       ln.next_stage = st + 1;
       if (st == nl - 1) {
+        rfx_umx::Done& d = p.done[ln.seq % rfx_umx::kRing];
         if (ln.out_host) {
-          RFX_CHECK_CUDA(cudaStreamWaitEvent(h->copy_out, h->ev_out[i], 0));
-          RFX_CHECK_CUDA(cudaEventRecord(ln.ev_done, h->copy_out));
-          ln.host_out_pending = true;
+          RFX_CHECK_CUDA(cudaEventRecord(d.ev, h->copy_out));  // after the last D2H chunk of this step
+          ln.host_out_pending = d.ev;
         } else {
-          RFX_CHECK_CUDA(cudaEventRecord(ln.ev_done, ln.s));
+          RFX_CHECK_CUDA(cudaEventRecord(d.ev, ln.s));
         }
-        ln.done_recorded = true;
+        d.recorded = true;
         ln.live = false;
       }
     }
@@ -607,10 +620,12 @@ int rfx_umx_pipe_push(rfx_umx_t* h, const float* x, int x_on_host, int B, int T,
   RFX_CHECK_CUDA(cudaEventRecord(ln.ev_x, caller));
   RFX_CHECK_CUDA(cudaStreamWaitEvent(ln.s, ln.ev_x, 0));
   // ... and after the previous D2H out of this lane's output staging buffer.
-  if (ln.host_out_pending) { RFX_CHECK_CUDA(cudaStreamWaitEvent(ln.s, ln.ev_done, 0)); ln.host_out_pending = false; }
+  if (ln.host_out_pending) { RFX_CHECK_CUDA(cudaStreamWaitEvent(ln.s, ln.host_out_pending, 0)); ln.host_out_pending = nullptr; }
+  rfx_umx::Done& dn = p.done[seq % rfx_umx::kRing];
+  dn.seq = seq; dn.recorded = false;
   ln.x = x_on_host ? nullptr : x; ln.x_host = x_on_host ? x : nullptr;
   ln.out = out_on_host ? nullptr : out; ln.out_host = out_on_host ? out : nullptr;
-  ln.seq = seq; ln.next_stage = 0; ln.live = true; ln.done_recorded = false;
+  ln.seq = seq; ln.next_stage = 0; ln.live = true;
   p.pushed = seq + 1;
   if (seq_out) *seq_out = seq;
   return umx_pipe_superstep(h);
@@ -627,35 +642,35 @@ int rfx_umx_pipe_flush(rfx_umx_t* h, void* stream) {
     if (!any_live) break;
     if ((rc = umx_pipe_superstep(h))) return rc;
   }
-  for (int i = 0; i < p.depth; ++i)
-    if (p.lane[i].done_recorded) RFX_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, p.lane[i].ev_done, 0));
+  for (auto& d : p.done)
+    if (d.recorded) RFX_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, d.ev, 0));
   return 0;
 }
 
-static int umx_pipe_find(rfx_umx_t* h, long long seq, rfx_umx::Lane** out) {
+static int umx_pipe_find(rfx_umx_t* h, long long seq, cudaEvent_t* out) {
   RFX_REQUIRE(h && h->pipe.ready, "pipeline not started");
   rfx_umx::Pipe& p = h->pipe;
   RFX_REQUIRE(seq >= 0 && seq < p.pushed, "pipeline: unknown step");
-  rfx_umx::Lane& ln = p.lane[seq % p.depth];
-  RFX_REQUIRE(ln.seq == seq, "pipeline: that step's lane has been reused (wait for a step before pushing `depth` more)");
-  RFX_REQUIRE(ln.done_recorded, "pipeline: that step has not left the pipeline yet (push depth-1 more steps, or flush)");
-  *out = &ln;
+  rfx_umx::Done& d = p.done[seq % rfx_umx::kRing];
+  RFX_REQUIRE(d.seq == seq, "pipeline: completion records are kept for the last 16 steps only");
+  RFX_REQUIRE(d.recorded, "pipeline: that step has not left the pipeline yet (push depth-1 more steps, or flush)");
+  *out = d.ev;
   return 0;
 }
 
 int rfx_umx_pipe_wait(rfx_umx_t* h, long long seq) {
-  rfx_umx::Lane* ln = nullptr;
+  cudaEvent_t ev = nullptr;
   int rc;
-  if ((rc = umx_pipe_find(h, seq, &ln))) return rc;
-  RFX_CHECK_CUDA(cudaEventSynchronize(ln->ev_done));
+  if ((rc = umx_pipe_find(h, seq, &ev))) return rc;
+  RFX_CHECK_CUDA(cudaEventSynchronize(ev));
   return 0;
 }
 
 int rfx_umx_pipe_stream_wait(rfx_umx_t* h, long long seq, void* stream) {
-  rfx_umx::Lane* ln = nullptr;
+  cudaEvent_t ev = nullptr;
   int rc;
-  if ((rc = umx_pipe_find(h, seq, &ln))) return rc;
-  RFX_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ln->ev_done, 0));
+  if ((rc = umx_pipe_find(h, seq, &ev))) return rc;
+  RFX_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ev, 0));
   return 0;
 }
 

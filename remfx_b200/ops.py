@@ -133,21 +133,22 @@ def linear(A: torch.Tensor, W: torch.Tensor, s1=None, t1=None, s2=None, t2=None,
     return Cout
 
 
-def lstm_layer(G: torch.Tensor, Whh: torch.Tensor, B: int, F: int, impl: str = "mma") -> torch.Tensor:
+def lstm_layer(G: torch.Tensor, Whh: torch.Tensor, B: int, F: int, impl: str = "mma", slots: int = 0) -> torch.Tensor:
     """Recurrent half of one bidirectional LSTM layer.  G: (B*F, 8H) input projections (+biases),
-    Whh: (2, 4H, H) -> (B*F, 2H).  impl: "mma" (tensor-core bf16x3, default) or "ffma" (fp32)."""
+    Whh: (2, 4H, H) -> (B*F, 2H).  impl: "mma" (tensor-core bf16x3, default) or "ffma" (fp32).
+    slots: batch slots per cluster (0 = automatic, 9..16 = the two-n-tile kernel, H = 256)."""
     _lib.check(_lib.lib().rfx_lstm_set_impl({"mma": 0, "ffma": 1}[impl]), "rfx_lstm_set_impl")
     try:
-        return _lstm_layer(G, Whh, B, F)
+        return _lstm_layer(G, Whh, B, F, slots)
     finally:
         _lib.lib().rfx_lstm_set_impl(0)
 
 
-def _lstm_layer(G: torch.Tensor, Whh: torch.Tensor, B: int, F: int) -> torch.Tensor:
+def _lstm_layer(G: torch.Tensor, Whh: torch.Tensor, B: int, F: int, slots: int = 0) -> torch.Tensor:
     G = _prep(G)
     Whh = _prep(Whh)
     H = Whh.shape[-1]
     out = torch.empty(B * F, 2 * H, dtype=torch.float32, device=G.device)
-    rc = _lib.lib().rfx_lstm_layer(_lib.ptr(G), _lib.ptr(Whh), _lib.ptr(out), 2 * H, B, F, H, _lib.cur_stream())
-    _lib.check(rc, "rfx_lstm_layer")
+    rc = _lib.lib().rfx_lstm_layer_slots(_lib.ptr(G), _lib.ptr(Whh), _lib.ptr(out), 2 * H, B, F, H, int(slots), _lib.cur_stream())
+    _lib.check(rc, "rfx_lstm_layer_slots")
     return out

@@ -68,7 +68,15 @@ def test_lstm_layer_vs_oracle(B, F, impl):
     _lstm_case(256, 512, B, F, impl)
 
 
-def _lstm_case(H, I, B, F, impl):
+@pytest.mark.parametrize("B,F,slots", [(3, 20, 16), (19, 70, 16), (32, 40, 16), (21, 33, 11)])
+def test_lstm_layer_two_ntile_clusters(B, F, slots):
+    """16 batch slots per cluster (two MMA n-tiles): same result as the one-n-tile kernel, bit for bit, and vs the oracle."""
+    out16 = _lstm_case(256, 512, B, F, "mma", slots=slots)
+    out8 = _lstm_case(256, 512, B, F, "mma", slots=8)
+    assert torch.equal(out16, out8)
+
+
+def _lstm_case(H, I, B, F, impl, slots=0):
     ops = _ops()
     g = torch.Generator().manual_seed(B * 100 + F)
     k = H ** -0.5
@@ -84,8 +92,9 @@ def _lstm_case(H, I, B, F, impl):
     G = torch.cat([x @ st[f"l.weight_ih_l0{s}"].t() + st[f"l.bias_ih_l0{s}"] + st[f"l.bias_hh_l0{s}"] for s in ("", "_reverse")], -1)
     G = G.permute(1, 0, 2).reshape(B * F, 8 * H).contiguous()
     Whh = torch.stack([st["l.weight_hh_l0"], st["l.weight_hh_l0_reverse"]])
-    out = ops.lstm_layer(G.cuda(), Whh.cuda(), B, F, impl=impl)
+    out = ops.lstm_layer(G.cuda(), Whh.cuda(), B, F, impl=impl, slots=slots)
     out = out.view(B, F, 2 * H).permute(1, 0, 2)
     err = relrms(out, ref)
-    print(f"lstm {impl} H={H} B={B} F={F} rel-RMS {err:.3e}")
+    print(f"lstm {impl} H={H} B={B} F={F} slots={slots} rel-RMS {err:.3e}")
     assert err < 1e-5, err
+    return out.cpu()
