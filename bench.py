@@ -196,7 +196,7 @@ def run_ours(args):
     # lane waits for everything enqueued before the push, and flush() makes the current stream wait for every output.
     pipe = model.pipeline(dev)
     depth = pipe.depth
-    nout = 2 * depth
+    nout = 2 * depth + 2
     outs_dev = [torch.empty(BATCH, 1, T, dtype=torch.float32, device=dev) for _ in range(nout)]
     nwarm = max(3, args.warmup)
     for i in range(nwarm):
@@ -238,7 +238,7 @@ def run_ours(args):
 
     # ---- end-to-end through the public API on host buffers ---------------------------------------------
     # Headline e2e = the pipeline on pinned HOST tensors: every step does its own H2D (33.5 MB) and D2H (33.5 MB) inside
-    # the timed region and the loop consumes every result (wait() on step k - 4 before pushing k, as a serving loop
+    # the timed region and the loop consumes every result (wait() on step k - 6 before pushing k, as a serving loop
     # would); host wall clock, stopped when the last result is in host memory.  Beside it: one blocking call per step.
     outs_host = [torch.empty(BATCH, 1, T, dtype=torch.float32).pin_memory() for _ in range(nout)]
     out_host = outs_host[0]
@@ -258,7 +258,7 @@ def run_ours(args):
     pipe.flush()
     barrier()
     seqs = []
-    lag = depth + 1   # results are consumed `lag` steps behind the newest push (lag + 1 host buffers in flight <= nout)
+    lag = 2 * depth   # results are consumed `lag` steps behind the newest push (lag + 1 host buffers in flight <= nout)
     t0 = time.perf_counter()
     for k in range(args.steps):
         if k >= lag:

@@ -98,7 +98,7 @@ struct rfx_umx {
   struct Pipe {
     bool ready = false;
     int depth = 0, B = 0, T = 0;
-    cudaStream_t rec[2] = {nullptr, nullptr};  // recurrence launches, round-robin in issue order, at the highest stream priority
+    cudaStream_t rec[4] = {nullptr, nullptr, nullptr, nullptr};  // recurrence launches, round-robin in issue order, at the highest stream priority
     int rec_n = 1;                              // recurrence streams in use (2 = two launches side by side)
     long long rec_count = 0;
     Lane lane[kSlots];
@@ -537,7 +537,7 @@ int umx_pipe_setup(rfx_umx_t* h, int B, int T) {
     int slots = 8, streams = 1;
     // tuning overrides (experiments only)
     if (const char* e = getenv("RFX_UMX_PIPE_SLOTS")) slots = atoi(e);
-    if (const char* e = getenv("RFX_UMX_PIPE_REC_STREAMS")) streams = atoi(e) == 2 ? 2 : 1;
+    if (const char* e = getenv("RFX_UMX_PIPE_REC_STREAMS")) streams = std::min(4, std::max(1, atoi(e)));
     const int rec_sms = streams * 8 * lstm_clusters_for(B, slots);
     if (slots > 0 && p.sms - rec_sms >= p.sms / 4) { p.max_sms = p.sms - rec_sms; p.lstm_slots = slots; p.rec_n = streams; }
     else { p.max_sms = 0; p.lstm_slots = slots > 0 ? 0 : slots; p.rec_n = 1; }

@@ -68,12 +68,13 @@ def test_lstm_layer_vs_oracle(B, F, impl):
     _lstm_case(256, 512, B, F, impl)
 
 
-@pytest.mark.parametrize("B,F,slots", [(3, 20, 16), (19, 70, 16), (32, 40, 16), (21, 33, 11)])
-def test_lstm_layer_two_ntile_clusters(B, F, slots):
-    """16 batch slots per cluster (two MMA n-tiles): same result as the one-n-tile kernel, bit for bit, and vs the oracle."""
+@pytest.mark.parametrize("B,F,slots", [(3, 20, 16), (19, 70, 16), (32, 40, 16), (21, 33, 11), (32, 50, 32), (29, 37, 24), (45, 21, 32)])
+def test_lstm_layer_multi_group_clusters(B, F, slots):
+    """More than 8 batch slots per cluster (warp-specialised kernel, 2-4 groups out of phase): checked against the oracle and
+    against the one-group kernel (same bf16x3 products; only the fp32 summation order of the partial sums differs)."""
     out16 = _lstm_case(256, 512, B, F, "mma", slots=slots)
     out8 = _lstm_case(256, 512, B, F, "mma", slots=8)
-    assert torch.equal(out16, out8)
+    assert relrms(out16, out8) < 2e-6
 
 
 def _lstm_case(H, I, B, F, impl, slots=0):

@@ -1,10 +1,20 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m remfx_b200.build > /dev/null
-timeout 300 python tools/e2e_diag.py 2>&1 | tail -9
-timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit=$?"; python -c "
-import json; d=json.load(open('gpurun_out/bench.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'])"; tail -n 3 gpurun_out/bench.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches exit=$?"
-ncu --set full --clock-control none --import-source on -k regex:lstm_rec -s 12 -c 1 -o gpurun_out/prof_lstm_pipe python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_lstm.log 2>&1; echo "ncu lstm exit=$?"
-ncu --set full --clock-control none --import-source on -k regex:stft_kernel -s 8 -c 2 -o gpurun_out/prof_stft_pipe python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_stft.log 2>&1; echo "ncu stft exit=$?"
-ls -la gpurun_out | head -30
+timeout 300 python -m pytest tests/test_gpu_gemm_lstm.py -m gpu -q --timeout 120 --no-header -p no:cacheprovider -k lstm > gpurun_out/test_lstm.log 2>&1; echo "tests exit=$? $(tail -n 1 gpurun_out/test_lstm.log)"
+grep -E "FAILED|Error|error|timed out" gpurun_out/test_lstm.log | head -20
+timeout 120 python tools/lstm_bench.py 32 2>&1 | tail -5
+for cfg in "16 1" "16 2" "24 2" "32 2" "32 3"; do set -- $cfg
+RFX_UMX_PIPE_SLOTS=$1 RFX_UMX_PIPE_REC_STREAMS=$2 timeout 120 python tools/pipe_bench.py 32 40 2>&1 | tail -1 | sed "s/^/slots=$1 streams=$2 /"
+done
+cat > /tmp/one.py <<'PY'
+import os, sys, torch
+sys.path.insert(0, os.getcwd())
+from remfx_b200 import ops
+B, F, H = 32, 513, 256
+G = torch.randn(B * F, 8 * H, device="cuda") * 0.5
+Whh = (torch.rand(2, 4 * H, H, device="cuda") * 2 - 1) * H ** -0.5
+for _ in range(3):
+    ops.lstm_layer(G, Whh, B, F, slots=16)
+torch.cuda.synchronize()
+PY
+ncu --set full --clock-control none --import-source on -k regex:lstm_rec_ws -s 2 -c 1 -o gpurun_out/prof_lstm_ws python /tmp/one.py > gpurun_out/ncu_ws.log 2>&1; echo "ncu exit=$?"

@@ -12,7 +12,7 @@ F = 513
 H = 256
 G = torch.randn(B * F, 8 * H, device="cuda") * 0.5
 Whh = (torch.rand(2, 4 * H, H, device="cuda") * 2 - 1) * H ** -0.5
-for slots in (0, 8, 16):
+for slots in (0, 8, 16, 24, 32):
     for _ in range(2):
         ops.lstm_layer(G, Whh, B, F, slots=slots)
     torch.cuda.synchronize()
@@ -22,4 +22,4 @@ for slots in (0, 8, 16):
         ops.lstm_layer(G, Whh, B, F, slots=slots)
     e1.record()
     torch.cuda.synchronize()
-    print(f"B={B} slots={slots} NT2_LO_SMEM={os.environ.get('RFX_LSTM_NT2_LO_SMEM')}: {e0.elapsed_time(e1) / 10:.4f} ms per layer launch")
+    print(f"B={B} slots={slots} LOCKSTEP={os.environ.get('RFX_LSTM_LOCKSTEP')}: {e0.elapsed_time(e1) / 10:.4f} ms per layer launch")
