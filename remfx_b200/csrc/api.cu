@@ -104,7 +104,7 @@ int rfx_lstm_info(int B, int* max_active_clusters, int* batch_per_cluster) {
 }
 
 int rfx_lstm_set_impl(int impl) {
-  RFX_REQUIRE(impl == 0 || impl == 1, "impl 0 (tensor-core) or 1 (fp32 FFMA)");
+  RFX_REQUIRE(impl >= 0 && impl <= 2, "impl 0 (mma.sync tensor-core), 1 (fp32 FFMA) or 2 (tcgen05, H = 256)");
   lstm_set_impl(impl);
   return 0;
 }

@@ -237,6 +237,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // 1 / (1 + 2^(-x log2 e)): two MUFU ops, no range fix-up (ex2 saturates to 0 / inf and rcp(inf) = 0, which is what the
 // sigmoid needs there)
 __device__ __forceinline__ float lean_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return lean_sigmoid(x); }
 
@@ -722,6 +723,290 @@ static int launch_ws(const float* G, int ldg, const float* Whh, float* Hout, int
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// tcgen05 recurrence (H = 256): the per-step product W_hh h_{t-1} on the 5th-generation tensor cores.
+//
+//   D[128 gate rows x 16 slots] (TMEM, fp32)  =  A[128 x 256] (TMEM)  x  B[256 x 16] (shared memory),  bf16x3
+//
+// * A = this CTA's 128 rows of W_hh (gate-major: row = gate * 32 + unit), split into bf16 hi / lo planes and written ONCE
+//   into tensor memory with tcgen05.st (lane = row, two K-elements per 32-bit column: 128 columns per plane).  A from
+//   TMEM (the ".ts" operand form) matters here: with N = 16 an MMA from shared memory would be bound by re-reading the
+//   4 KB A tile every instruction; from TMEM the instruction paces at N/2 = 8 cycles.
+// * B = h_{t-1} of the cluster's 16 batch slots as split-bf16, K-major, NO swizzle: 8 x 8 core matrices (128 B each) laid
+//   out [source CTA][plane][slot group][unit group], so every CTA's contribution is ONE contiguous 2 KB block (one DSMEM
+//   bulk copy per destination, as before) and an MMA k-step (16 units) is two K-adjacent core matrices
+//   (descriptor: LBO = 128 B between K-adjacent core matrices, SBO = 512 B between 8-slot groups).
+// * One thread issues the 48 MMAs of a step (lo*hi, hi*lo, hi*hi over 16 k-steps) and a tcgen05.commit; 8 epilogue warps
+//   read D with tcgen05.ld (thread = gate row, 8 slots each), add the input projections, apply the gate non-linearity,
+//   transpose through shared memory so that one thread owns (unit pair, slot), update c, emit h (fp32 / split planes to
+//   HBM, split planes to the staging block) and the block is pushed to the 8 CTAs.
+// A cluster serves 16 slots, so B = 32 needs 4 clusters = 32 SMs per launch.
+// ------------------------------------------------------------------------------------------------------
+constexpr int TC_N = 16;             // batch slots per cluster = MMA N
+constexpr int TC_BLKP = TC_N * 64;   // bytes of one plane of one CTA's h block: N slots x 32 units bf16
+constexpr int TC_BLK = 2 * TC_BLKP;  // hi + lo
+constexpr int TC_ACT_LD = TC_N + 4;  // padded row of the activation transpose buffer (floats)
+constexpr int TC_ISSUERS = 4;        // MMA-issue warps: each issues the k-steps of a quarter of K into its own accumulator
+constexpr int TC_THREADS = 256 + 32 * TC_ISSUERS;  // 8 epilogue warps + the issue warps
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// same, the shared-memory descriptor given as two 32-bit halves (the low half is the only part that changes between the
+// MMAs of a step, by a compile-time constant, which keeps the single issuing thread's instruction count down)
+__device__ __forceinline__ void umma_ts_f16_split(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// K-major operand without swizzle: 8 x 16-byte core matrices; lbo = bytes between K-adjacent core matrices, sbo = bytes
+// between 8-row groups (cute::UMMA::SmemDescriptor, version 1, layout type 0)
+__device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    lstm_rec_tc_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Whh, float* __restrict__ Hout, int ldh,
+                       __nv_bfloat16* __restrict__ Hhi, __nv_bfloat16* __restrict__ Hlo, int ldhs, int B, int F, int NB) {
+  constexpr int H = 256;
+  constexpr int UPC = H / LSTM_CL;  // 32 units per CTA -> 128 gate rows = MMA M
+  constexpr int TX = LSTM_CL * TC_BLK;
+  extern __shared__ __align__(128) uint8_t lstm_smem[];
+  uint8_t* h_buf = lstm_smem;                                                // [2][CL][TC_BLK]
+  uint8_t* stage = h_buf + 2 * LSTM_CL * TC_BLK;                             // [2][TC_BLK]
+  float* act = reinterpret_cast<float*>(stage + 2 * TC_BLK);                 // [4 gates][32 units][TC_ACT_LD]
+  uint64_t* h_bar = reinterpret_cast<uint64_t*>(act + 4 * UPC * TC_ACT_LD);  // [2]
+  uint64_t* mma_bar = h_bar + 2;                                             // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int dir = blockIdx.z;
+  const int b0 = blockIdx.y * NB;
+
+  for (int i = tid; i < 2 * LSTM_CL * TC_BLK / 4; i += TC_THREADS) reinterpret_cast<uint32_t*>(h_buf)[i] = 0u;
+  if (tid == 0) {
+    mbar_init(&h_bar[0], 1);
+    mbar_init(&h_bar[1], 1);
+    mbar_init(mma_bar, TC_ISSUERS);
+    mbar_fence_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();  // the zeroed h buffer is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_d = tmem_base + 256;  // columns [0,128) A hi, [128,256) A lo, [256, 256 + N) accumulator
+
+  // ---- W_hh -> tensor memory (once).  Warps 0-3: thread = row (gate = warp, unit = lane). ----
+  if (warp < 4) {
+    const float* wrow = Whh + ((size_t)dir * 4 * H + (size_t)warp * H + rank * UPC + lane) * H;
+    const uint32_t t_row = tmem_base + ((uint32_t)(32 * warp) << 16);
+    for (int c0 = 0; c0 < H / 2; c0 += 8) {  // 8 columns = 16 K-elements
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(wrow + 2 * c0 + 4 * q);
+        float r0, r1, r2, r3;  // even K-element in the low half of the column (verified on the device against the oracle)
+        hi[2 * q] = pack_hi2(v.x, v.y, r0, r1); lo[2 * q] = pack2(r0, r1);
+        hi[2 * q + 1] = pack_hi2(v.z, v.w, r2, r3); lo[2 * q + 1] = pack2(r2, r3);
+      }
+      tmem_st8(t_row + c0, hi);
+      tmem_st8(t_row + 128 + c0, lo);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_arrive();  // barriers initialised and h zeroed everywhere before anyone sends
+  cluster_wait();
+
+  if (warp >= 8) {
+    // =============================== MMA issue warps ===============================
+    // Issuer w owns k-steps 4 w .. 4 w + 3 (units 64 w .. 64 w + 63) of all three passes = 12 MMAs into accumulator w: four
+    // threads issue in parallel and the accumulation order inside every accumulator is fixed (deterministic results).
+    // every operand of the MMAs is made provably warp-uniform (shuffles from lane 0) and the issuing lane is picked with
+    // elect.sync, so the compiler feeds UTCHMMA from uniform registers directly instead of a per-MMA broadcast loop
+    const int w = __shfl_sync(0xffffffffu, warp - 8, 0);
+    const uint32_t tb_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t hb_u = __shfl_sync(0xffffffffu, smem_u32(h_buf), 0);
+    const uint32_t mb_u = __shfl_sync(0xffffffffu, smem_u32(mma_bar), 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, TC_N);
+    constexpr uint32_t lbo = 128u, sbo = 512u;
+    constexpr uint32_t desc_hi = (sbo >> 4) | (1u << 14);  // SBO, descriptor version 1, no swizzle
+    const uint32_t d_acc = tb_u + 256u + (uint32_t)(w * TC_N);
+    for (int step = 0; step < F; ++step) {
+      const int cur = step & 1;
+      if (step > 0) mbar_wait(&h_bar[cur], ((step - 1) >> 1) & 1);  // all of h_{t-1} has landed
+      tc_fence_after();
+      // units [16 kk, 16 kk + 16) live in source CTA kk / 2, unit groups 2 (kk & 1), + 1 of its block
+      const uint32_t lo0 = (((hb_u + (uint32_t)cur * (LSTM_CL * TC_BLK) + (uint32_t)(2 * w) * TC_BLK) & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16);
+      const uint32_t a0 = tb_u + 32u * w;
+      if (elect_one()) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {  // W_lo h_hi, W_hi h_lo, W_hi h_hi (small terms first)
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t boff = (uint32_t)((k4 >> 1) * TC_BLK + (k4 & 1) * 256 + (pass == 1 ? TC_BLKP : 0));
+            umma_ts_f16_split(d_acc, a0 + (pass == 0 ? 128u : 0u) + 8u * k4, lo0 + (boff >> 4), desc_hi, idesc, (pass | k4) ? 1u : 0u);
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb_u) : "memory");
+      }
+      __syncwarp();
+    }
+    // Nobody may exit while peers can still write into its shared memory: wait for the last h to land.
+    mbar_wait(&h_bar[F & 1], ((F - 1) >> 1) & 1);
+  } else {
+    // =============================== epilogue warps ===============================
+    const int q = warp & 3;    // TMEM lane quarter = gate
+    const int ch = warp >> 2;  // column half: slots 8 ch .. 8 ch + 7
+    const uint32_t t_ld = tmem_d + ((uint32_t)(32 * q) << 16) + 8u * ch;
+    const uint32_t gcol = (uint32_t)(dir * 4 * H + q * H + rank * UPC + lane);
+    uint32_t vmask = 0;  // bit s: slot 8 ch + s holds a real item
+#pragma unroll
+    for (int s2 = 0; s2 < 8; ++s2)
+      if ((8 * ch + s2) < NB && (b0 + 8 * ch + s2) < B) vmask |= 1u << s2;
+    const uint32_t row0 = (uint32_t)(b0 + 8 * ch) * (uint32_t)F;  // G row of slot 8 ch at t = 0
+    float gq[8];
+    auto load_g = [&](int st) {
+#pragma unroll
+      for (int s2 = 0; s2 < 8; ++s2) {
+        gq[s2] = 0.f;
+        if (st < F && (vmask >> s2 & 1u)) {
+          const uint32_t tq = (uint32_t)(dir ? F - 1 - st : st);
+          gq[s2] = __ldg(G + (size_t)((row0 + (uint32_t)s2 * (uint32_t)F + tq) * (uint32_t)ldg + gcol));
+        }
+      }
+    };
+    load_g(0);
+    const float sc = (q == 2) ? 2.0f : 1.0f;  // tanh(x) = 2 sigmoid(2x) - 1 for the cell gate
+    // phase-2 role: one thread per (unit pair, slot)
+    const int up = tid & 15, cs = tid >> 4;  // units 2 up, 2 up + 1; slot cs (0..15)
+    const bool cvalid = cs < NB && (b0 + cs) < B;
+    const uint32_t crow0 = (uint32_t)(b0 + cs) * (uint32_t)F;
+    const uint32_t ccol = (uint32_t)(dir * H + rank * UPC + 2 * up);
+    const uint32_t st_off = (uint32_t)(((cs >> 3) * 4 + (up >> 2)) * 128 + (cs & 7) * 16 + (up & 3) * 4);  // core-matrix layout
+    float c0 = 0.f, c1 = 0.f;
+    const uint32_t dst_h = mapa_u32(smem_u32(h_buf) + rank * TC_BLK, lane & 7);
+    const uint32_t dst_bar = mapa_u32(smem_u32(&h_bar[0]), lane & 7);
+    for (int step = 0; step < F; ++step) {
+      const int cur = step & 1, nxt = cur ^ 1;
+      const uint32_t tt = (uint32_t)(dir ? F - 1 - step : step);
+      float gin[8];
+#pragma unroll
+      for (int s2 = 0; s2 < 8; ++s2) gin[s2] = gq[s2];
+      load_g(step + 1);  // a whole step ahead of its use
+      mbar_wait(mma_bar, step & 1);
+      tc_fence_after();
+      uint32_t v[TC_ISSUERS][8];
+#pragma unroll
+      for (int a = 0; a < TC_ISSUERS; ++a) tmem_ld8(t_ld + (uint32_t)(a * TC_N), v[a]);
+      tmem_ld_wait();
+      tc_fence_before();
+      float a8[8];
+#pragma unroll
+      for (int s2 = 0; s2 < 8; ++s2) {
+        float acc = __uint_as_float(v[0][s2]);
+#pragma unroll
+        for (int a = 1; a < TC_ISSUERS; ++a) acc += __uint_as_float(v[a][s2]);
+        const float sg = lean_sigmoid(sc * (acc + gin[s2]));
+        a8[s2] = (q == 2) ? 2.0f * sg - 1.0f : sg;
+      }
+      float* arow = act + (q * UPC + lane) * TC_ACT_LD + 8 * ch;
+      *reinterpret_cast<float4*>(arow) = make_float4(a8[0], a8[1], a8[2], a8[3]);
+      *reinterpret_cast<float4*>(arow + 4) = make_float4(a8[4], a8[5], a8[6], a8[7]);
+      named_bar_sync(1, 256);
+      // ---- (unit pair, slot): c = f c + i g ; h = o tanh(c) ----
+      const float* ap = act + (2 * up) * TC_ACT_LD + cs;
+      const float i0 = ap[0], i1 = ap[TC_ACT_LD];
+      const float f0 = ap[UPC * TC_ACT_LD], f1 = ap[UPC * TC_ACT_LD + TC_ACT_LD];
+      const float g0 = ap[2 * UPC * TC_ACT_LD], g1 = ap[2 * UPC * TC_ACT_LD + TC_ACT_LD];
+      const float o0 = ap[3 * UPC * TC_ACT_LD], o1 = ap[3 * UPC * TC_ACT_LD + TC_ACT_LD];
+      c0 = f0 * c0 + i0 * g0;
+      c1 = f1 * c1 + i1 * g1;
+      const float h0 = o0 * (2.0f * lean_sigmoid(2.0f * c0) - 1.0f);
+      const float h1 = o1 * (2.0f * lean_sigmoid(2.0f * c1) - 1.0f);
+      float r0, r1;
+      const uint32_t hh = pack_hi2(h0, h1, r0, r1);
+      const uint32_t hl = pack2(r0, r1);
+      uint8_t* stg = stage + nxt * TC_BLK;
+      *reinterpret_cast<uint32_t*>(stg + st_off) = hh;
+      *reinterpret_cast<uint32_t*>(stg + TC_BLKP + st_off) = hl;
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy (async proxy) reads
+      named_bar_sync(2, 256);
+      if (warp == 0 && lane < LSTM_CL) {
+        if (lane == 0) mbar_arrive_expect_tx(&h_bar[nxt], TX);
+        bulk_s2cluster(dst_h + (uint32_t)(nxt * LSTM_CL * TC_BLK), smem_u32(stg), TC_BLK, dst_bar + (uint32_t)(nxt * sizeof(uint64_t)));
+      }
+      if (cvalid) {  // layer output to HBM: off the critical path
+        const uint32_t row = crow0 + tt;
+        if (Hout) *reinterpret_cast<float2*>(Hout + (size_t)(row * (uint32_t)ldh + ccol)) = make_float2(h0, h1);
+        if (Hhi) {
+          const size_t o = (size_t)(row * (uint32_t)ldhs + ccol);
+          *reinterpret_cast<uint32_t*>(Hhi + o) = hh;
+          *reinterpret_cast<uint32_t*>(Hlo + o) = hl;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_arrive();
+  cluster_wait();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int launch_tc(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs, int B,
+                     int F, int slots, cudaStream_t stream) {
+  const size_t smem = (size_t)2 * LSTM_CL * TC_BLK + 2 * TC_BLK + (size_t)4 * 32 * TC_ACT_LD * 4 + 64 + 128;
+  auto kern = lstm_rec_tc_kernel;
+  RFX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RFX_REQUIRE((long long)B * F * (long long)ldg < (1ll << 32) && (long long)B * F * (long long)std::max(ldh, ldhs) < (1ll << 32),
+              "lstm: tensors too large for 32-bit element offsets");
+  RFX_REQUIRE((!Hout || ldh % 2 == 0) && (!Hhi || ldhs % 2 == 0), "lstm: output row strides must be even");
+  const int nb = (slots > 0 && slots < TC_N) ? slots : TC_N;
+  dim3 grid(LSTM_CL, ceil_div(B, nb), 2);
+  kern<<<grid, TC_THREADS, smem, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int NB>
 static int max_clusters() {
   cudaLaunchConfig_t cfg{};
@@ -758,7 +1043,7 @@ int lstm_choose_nb(int B) {
   return 8;  // more clusters than fit: several waves of the widest variant
 }
 
-static int g_lstm_impl = 0;  // 0 = tensor-core (mma.sync bf16x3), 1 = fp32 FFMA
+static int g_lstm_impl = 0;  // 0 = tensor-core (mma.sync bf16x3), 1 = fp32 FFMA, 2 = tcgen05 (A from TMEM, 16 slots per cluster)
 void lstm_set_impl(int impl) { g_lstm_impl = impl; }
 int lstm_get_impl() { return g_lstm_impl; }
 
@@ -778,6 +1063,7 @@ int launch_lstm_layer_slots(const float* G, int ldg, const float* Whh, float* Ho
   RFX_REQUIRE(B > 0 && F > 0, "lstm: positive sizes");
   RFX_REQUIRE(((uintptr_t)Whh & 15) == 0, "lstm: W_hh must be 16-byte aligned");
   RFX_REQUIRE(Hout || (Hhi && Hlo), "lstm: no output given");
+  if (g_lstm_impl == 2 && H == LSTM_H) return launch_tc(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
   if (g_lstm_impl == 0 || H != LSTM_H) {
     // more than 8 slots per cluster asked for: the warp-specialised multi-group kernel (H = 256 only)
     if (H == 256 && slots > LSTM_SLOTS) {

@@ -137,7 +137,7 @@ def lstm_layer(G: torch.Tensor, Whh: torch.Tensor, B: int, F: int, impl: str = "
     """Recurrent half of one bidirectional LSTM layer.  G: (B*F, 8H) input projections (+biases),
     Whh: (2, 4H, H) -> (B*F, 2H).  impl: "mma" (tensor-core bf16x3, default) or "ffma" (fp32).
     slots: batch slots per cluster (0 = automatic, 9..16 = the two-n-tile kernel, H = 256)."""
-    _lib.check(_lib.lib().rfx_lstm_set_impl({"mma": 0, "ffma": 1}[impl]), "rfx_lstm_set_impl")
+    _lib.check(_lib.lib().rfx_lstm_set_impl({"mma": 0, "ffma": 1, "tc": 2}[impl]), "rfx_lstm_set_impl")
     try:
         return _lstm_layer(G, Whh, B, F, slots)
     finally:

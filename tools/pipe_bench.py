@@ -13,6 +13,9 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 T = 262144
 torch.manual_seed(0)
+if os.environ.get("RFX_LSTM_IMPL"):
+    from remfx_b200 import _lib
+    _lib.check(_lib.lib().rfx_lstm_set_impl(int(os.environ["RFX_LSTM_IMPL"])), "set_impl")
 m = OpenUnmixModel(n_fft=2048, hop_length=512, n_channels=1, alpha=0.3, sample_rate=48000).cuda().eval()
 xs = [synth_audio(10 + i, B, T).cuda() for i in range(5)]
 outs = [torch.empty_like(xs[0]) for _ in range(6)]
@@ -40,4 +43,4 @@ e1.record()
 torch.cuda.synchronize()
 rt = pipe.recurrence_times_ms()
 print(f"pipeline: {e0.elapsed_time(e1) / K:.3f} ms/step  (recurrence launches: n={len(rt)} mean {statistics.mean(rt):.3f} median {statistics.median(rt):.3f} "
-      f"max {max(rt):.3f} ms)  env MAX_SMS={os.environ.get('RFX_UMX_PIPE_MAX_SMS')} SLOTS={os.environ.get('RFX_UMX_PIPE_SLOTS')}")
+      f"max {max(rt):.3f} ms)  env MAX_SMS={os.environ.get('RFX_UMX_PIPE_MAX_SMS')} SLOTS={os.environ.get('RFX_UMX_PIPE_SLOTS')} IMPL={os.environ.get('RFX_LSTM_IMPL')} STREAMS={os.environ.get('RFX_UMX_PIPE_REC_STREAMS')}")
