@@ -130,6 +130,10 @@ int rfx_umx_wait_host(rfx_umx_t* h, int slot);
  * workspace: rfx_umx_pipe_workspace_bytes (= depth private lanes), the same pointer for every push until a flush. */
 size_t rfx_umx_pipe_workspace_bytes(const rfx_umx_t* h, int B, int T);
 int rfx_umx_pipe_depth(const rfx_umx_t* h);
+/* Schedule facts after the first push: SMs owned by the recurrence streams (a CUDA green-context partition; 0 when the driver
+ * could not provide one and the other kernels' grids are capped instead), SMs left to every other kernel, recurrence launches
+ * that run side by side, batch slots per recurrence cluster. */
+int rfx_umx_pipe_info(const rfx_umx_t* h, int* rec_sms, int* rest_sms, int* rec_streams, int* slots_per_cluster);
 int rfx_umx_pipe_push(rfx_umx_t* h, const float* x, int x_on_host, int B, int T, float* out, int out_on_host, void* workspace,
                       size_t workspace_bytes, void* stream, long long* seq);
 int rfx_umx_pipe_flush(rfx_umx_t* h, void* stream);

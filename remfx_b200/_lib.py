@@ -64,6 +64,7 @@ _SIGNATURES = {
     "rfx_umx_wait_host": (C.c_int, [C.c_void_p, C.c_int]),
     "rfx_umx_pipe_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "rfx_umx_pipe_depth": (C.c_int, [C.c_void_p]),
+    "rfx_umx_pipe_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rfx_umx_pipe_push": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
                                     C.POINTER(C.c_longlong)]),
     "rfx_umx_pipe_flush": (C.c_int, [C.c_void_p, C.c_void_p]),

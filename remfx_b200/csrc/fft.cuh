@@ -76,7 +76,137 @@ __host__ __device__ __forceinline__ float2 irfft_pre(float2 xk, float2 xn, float
   return make_float2(e.x - o.y, -(e.y + o.x));
 }
 
+// ------------------------------------------------------------------------------------------------------
+// 1024-point complex FFT (n_fft = 2048) as THREE register passes -- radix 16, 16, 4 -- by 64 threads:
+// two shared-memory exchanges per frame instead of five, 16-point butterflies entirely in registers.
+// Same Stockham indexing as fft_pass_r4, generalised: work item j loads in[j + r N/R], multiplies by
+// exp(-2 pi i r k / (Ns R)) with k = j mod Ns, transforms, and stores to out[(j - k) R + k + r Ns].
+// Intermediate buffers are padded by one element every 16 (fft1024_pad) so that the stride-16 accesses of the
+// radix-16 passes spread over the banks; the last pass writes the natural, unpadded order.
+// ------------------------------------------------------------------------------------------------------
+constexpr int FFT1024_BUF = 1024 + 64;  // float2 elements of one (padded) frame buffer
+
+__host__ __device__ __forceinline__ int fft1024_pad(int i) { return i + (i >> 4); }
+
+__host__ __device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 s02 = make_float2(a0.x + a2.x, a0.y + a2.y), d02 = make_float2(a0.x - a2.x, a0.y - a2.y);
+  const float2 s13 = make_float2(a1.x + a3.x, a1.y + a3.y);
+  const float2 d13 = make_float2(a1.y - a3.y, a3.x - a1.x);  // (a1 - a3) * (-i)
+  a0 = make_float2(s02.x + s13.x, s02.y + s13.y);
+  a1 = make_float2(d02.x + d13.x, d02.y + d13.y);
+  a2 = make_float2(s02.x - s13.x, s02.y - s13.y);
+  a3 = make_float2(d02.x - d13.x, d02.y - d13.y);
+}
+
+// In-register 16-point DFT: v[n], n = g + 4 m  ->  v[k], k = q + 4 p (natural order on return).
+__host__ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
+  // stage 1: DFT4 over m for every g (elements g, g+4, g+8, g+12) -> y[g][q] stored at v[g + 4 q]
+#pragma unroll
+  for (int g = 0; g < 4; ++g) dft4(v[g], v[g + 4], v[g + 8], v[g + 12]);
+  // twiddle y[g][q] *= W16^(g q)
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+  // W16^1 = (C1, -S1), W16^2 = (R2, -R2), W16^3 = (S1, -C1), W16^4 = (0, -1), W16^6 = (-R2, -R2), W16^9 = (-C1, S1)
+  v[1 + 4] = cmul(v[1 + 4], make_float2(C1, -S1));
+  v[1 + 8] = cmul(v[1 + 8], make_float2(R2, -R2));
+  v[1 + 12] = cmul(v[1 + 12], make_float2(S1, -C1));
+  v[2 + 4] = cmul(v[2 + 4], make_float2(R2, -R2));
+  v[2 + 8] = make_float2(v[2 + 8].y, -v[2 + 8].x);  // * (-i)
+  v[2 + 12] = cmul(v[2 + 12], make_float2(-R2, -R2));
+  v[3 + 4] = cmul(v[3 + 4], make_float2(S1, -C1));
+  v[3 + 8] = cmul(v[3 + 8], make_float2(-R2, -R2));
+  v[3 + 12] = cmul(v[3 + 12], make_float2(-C1, S1));
+  // stage 2: DFT4 over g for every q (elements 4 q .. 4 q + 3) -> X[q + 4 p] lands at v[4 q + p]
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dft4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  // v[4 q + p] holds X[q + 4 p]: transpose the 4 x 4 index to natural order
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int p = q + 1; p < 4; ++p) {
+      const float2 t = v[4 * q + p];
+      v[4 * q + p] = v[4 * p + q];
+      v[4 * p + q] = t;
+    }
+}
+
+// Radix-16 pass for work item j in [0, 64), in three steps so that the GPU version can run IN PLACE (all loads of the CTA,
+// barrier, all stores).  IN_PAD / OUT_PAD: the buffer uses the padded index map.
+template <bool IN_PAD>
+__host__ __device__ __forceinline__ void fft1024_r16_load(const float2* __restrict__ in, int j, float2 (&v)[16]) {
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = in[IN_PAD ? fft1024_pad(j + 64 * r) : j + 64 * r];
+}
+__host__ __device__ __forceinline__ void fft1024_r16_compute(const float2* __restrict__ tw, int Ns, int j, float2 (&v)[16]) {
+  if (Ns > 1) {
+    const int m = (j & (Ns - 1)) * (2048 / (Ns * 16));  // exp(-2 pi i r k / (Ns 16)) = tw[r k 2048 / (16 Ns)]
+#pragma unroll
+    for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], tw[r * m]);
+  }
+  dft16(v);
+}
+template <bool OUT_PAD>
+__host__ __device__ __forceinline__ void fft1024_r16_store(float2* __restrict__ out, int Ns, int j, const float2 (&v)[16]) {
+  const int k = j & (Ns - 1);
+  const int j0 = (j - k) * 16 + k;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) out[OUT_PAD ? fft1024_pad(j0 + r * Ns) : j0 + r * Ns] = v[r];
+}
+template <bool IN_PAD, bool OUT_PAD>
+__host__ __device__ __forceinline__ void fft1024_pass_r16(const float2* __restrict__ in, float2* __restrict__ out,
+                                                          const float2* __restrict__ tw, int Ns, int j) {
+  float2 v[16];
+  fft1024_r16_load<IN_PAD>(in, j, v);
+  fft1024_r16_compute(tw, Ns, j, v);
+  fft1024_r16_store<OUT_PAD>(out, Ns, j, v);
+}
+
+// Last pass: radix 4 with Ns = 256 for work item j in [0, 256); padded input, natural output.
+__host__ __device__ __forceinline__ void fft1024_r4_last_load(const float2* __restrict__ in, const float2* __restrict__ tw, int j,
+                                                              float2 (&v)[4]) {
+  v[0] = in[fft1024_pad(j)];
+  const int m = 2 * j;  // exp(-2 pi i r j / 1024) = tw[2 r j]
+  v[1] = cmul(in[fft1024_pad(j + 256)], tw[m]);
+  v[2] = cmul(in[fft1024_pad(j + 512)], tw[2 * m]);
+  v[3] = cmul(in[fft1024_pad(j + 768)], tw[3 * m]);
+  dft4(v[0], v[1], v[2], v[3]);
+}
+__host__ __device__ __forceinline__ void fft1024_pass_r4_last(const float2* __restrict__ in, float2* __restrict__ out,
+                                                              const float2* __restrict__ tw, int j) {
+  float2 v[4];
+  fft1024_r4_last_load(in, tw, j, v);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) out[j + 256 * r] = v[r];
+}
+
 #ifdef __CUDACC__
+// Four 1024-point FFTs at once by a 256-thread CTA, IN PLACE: frame g = tid / 64 lives in buf + g FFT1024_BUF, natural order
+// on entry and on return.  Every pass is load-all / barrier / store-all.  Ends with a __syncthreads().
+__device__ __forceinline__ void fft1024_x4(float2* buf, const float2* __restrict__ tw, int tid) {
+  const int t = tid & 63;
+  float2* f = buf + (tid >> 6) * FFT1024_BUF;
+  float2 v[16];
+  __syncthreads();
+  fft1024_r16_load<false>(f, t, v);
+  fft1024_r16_compute(tw, 1, t, v);
+  __syncthreads();
+  fft1024_r16_store<true>(f, 1, t, v);
+  __syncthreads();
+  fft1024_r16_load<true>(f, t, v);
+  fft1024_r16_compute(tw, 16, t, v);
+  __syncthreads();
+  fft1024_r16_store<true>(f, 16, t, v);
+  __syncthreads();
+  float2 w[4][4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) fft1024_r4_last_load(f, tw, t + 64 * m, w[m]);
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) f[t + 64 * m + 256 * r] = w[m][r];
+  __syncthreads();
+}
+
 // Cooperative complex FFT of NC = 2^LOG2NC points by NC/4 threads.  Input in `a`; returns the buffer
 // (a or b) that holds the result.  Ends with a __syncthreads() so the result is visible to all threads.
 template <int LOG2NC>

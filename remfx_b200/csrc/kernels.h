@@ -135,6 +135,10 @@ int launch_lstm_layer(const float* G, int ldg, const float* Whh, float* Hout, in
 // launch into the fewest SMs (2 * ceil(B / 8) clusters of 8), which is what the multi-lane Open-Unmix pipeline wants.
 int launch_lstm_layer_slots(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo,
                             int ldhs, int B, int F, int H, int slots, cudaStream_t stream);
+// Same with the kernel chosen per call: impl 0 = mma.sync bf16x3, 1 = fp32 FFMA, 2 = tcgen05 (H = 256; 16 slots per cluster),
+// -1 = the process-wide default (lstm_set_impl).
+int launch_lstm_layer_impl(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo,
+                           int ldhs, int B, int F, int H, int impl, int slots, cudaStream_t stream);
 int lstm_clusters_for(int B, int slots);  // clusters (of 8 CTAs) one launch of the tensor-core recurrence uses
 
 // ---------------------------------------------------------------- small utility kernels (util.cu)

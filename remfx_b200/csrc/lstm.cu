@@ -745,7 +745,6 @@ static int launch_ws(const float* G, int ldg, const float* Whh, float* Hout, int
 constexpr int TC_N = 16;             // batch slots per cluster = MMA N
 constexpr int TC_BLKP = TC_N * 64;   // bytes of one plane of one CTA's h block: N slots x 32 units bf16
 constexpr int TC_BLK = 2 * TC_BLKP;  // hi + lo
-constexpr int TC_ACT_LD = TC_N + 4;  // padded row of the activation transpose buffer (floats)
 constexpr int TC_ISSUERS = 4;        // MMA-issue warps: each issues the k-steps of a quarter of K into its own accumulator
 constexpr int TC_THREADS = 256 + 32 * TC_ISSUERS;  // 8 epilogue warps + the issue warps
 
@@ -801,8 +800,8 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
   extern __shared__ __align__(128) uint8_t lstm_smem[];
   uint8_t* h_buf = lstm_smem;                                                // [2][CL][TC_BLK]
   uint8_t* stage = h_buf + 2 * LSTM_CL * TC_BLK;                             // [2][TC_BLK]
-  float* act = reinterpret_cast<float*>(stage + 2 * TC_BLK);                 // [4 gates][32 units][TC_ACT_LD]
-  uint64_t* h_bar = reinterpret_cast<uint64_t*>(act + 4 * UPC * TC_ACT_LD);  // [2]
+  float* act = reinterpret_cast<float*>(stage + 2 * TC_BLK);                 // [4 gates][TC_N slots][32 units]
+  uint64_t* h_bar = reinterpret_cast<uint64_t*>(act + 4 * TC_N * UPC);       // [2]
   uint64_t* mma_bar = h_bar + 2;                                             // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
 
@@ -925,10 +924,6 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
     for (int step = 0; step < F; ++step) {
       const int cur = step & 1, nxt = cur ^ 1;
       const uint32_t tt = (uint32_t)(dir ? F - 1 - step : step);
-      float gin[8];
-#pragma unroll
-      for (int s2 = 0; s2 < 8; ++s2) gin[s2] = gq[s2];
-      load_g(step + 1);  // a whole step ahead of its use
       mbar_wait(mma_bar, step & 1);
       tc_fence_after();
       uint32_t v[TC_ISSUERS][8];
@@ -942,23 +937,23 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
         float acc = __uint_as_float(v[0][s2]);
 #pragma unroll
         for (int a = 1; a < TC_ISSUERS; ++a) acc += __uint_as_float(v[a][s2]);
-        const float sg = lean_sigmoid(sc * (acc + gin[s2]));
+        const float sg = lean_sigmoid(sc * (acc + gq[s2]));
         a8[s2] = (q == 2) ? 2.0f * sg - 1.0f : sg;
       }
-      float* arow = act + (q * UPC + lane) * TC_ACT_LD + 8 * ch;
-      *reinterpret_cast<float4*>(arow) = make_float4(a8[0], a8[1], a8[2], a8[3]);
-      *reinterpret_cast<float4*>(arow + 4) = make_float4(a8[4], a8[5], a8[6], a8[7]);
+      float* acol = act + (q * TC_N + 8 * ch) * UPC + lane;  // [gate][slot][unit]: conflict-free both ways
+#pragma unroll
+      for (int s2 = 0; s2 < 8; ++s2) acol[s2 * UPC] = a8[s2];
       named_bar_sync(1, 256);
       // ---- (unit pair, slot): c = f c + i g ; h = o tanh(c) ----
-      const float* ap = act + (2 * up) * TC_ACT_LD + cs;
-      const float i0 = ap[0], i1 = ap[TC_ACT_LD];
-      const float f0 = ap[UPC * TC_ACT_LD], f1 = ap[UPC * TC_ACT_LD + TC_ACT_LD];
-      const float g0 = ap[2 * UPC * TC_ACT_LD], g1 = ap[2 * UPC * TC_ACT_LD + TC_ACT_LD];
-      const float o0 = ap[3 * UPC * TC_ACT_LD], o1 = ap[3 * UPC * TC_ACT_LD + TC_ACT_LD];
-      c0 = f0 * c0 + i0 * g0;
-      c1 = f1 * c1 + i1 * g1;
-      const float h0 = o0 * (2.0f * lean_sigmoid(2.0f * c0) - 1.0f);
-      const float h1 = o1 * (2.0f * lean_sigmoid(2.0f * c1) - 1.0f);
+      const float* ap = act + cs * UPC + 2 * up;
+      const float2 gi = *reinterpret_cast<const float2*>(ap);
+      const float2 gf = *reinterpret_cast<const float2*>(ap + TC_N * UPC);
+      const float2 gg = *reinterpret_cast<const float2*>(ap + 2 * TC_N * UPC);
+      const float2 go = *reinterpret_cast<const float2*>(ap + 3 * TC_N * UPC);
+      c0 = gf.x * c0 + gi.x * gg.x;
+      c1 = gf.y * c1 + gi.y * gg.y;
+      const float h0 = go.x * (2.0f * lean_sigmoid(2.0f * c0) - 1.0f);
+      const float h1 = go.y * (2.0f * lean_sigmoid(2.0f * c1) - 1.0f);
       float r0, r1;
       const uint32_t hh = pack_hi2(h0, h1, r0, r1);
       const uint32_t hl = pack2(r0, r1);
@@ -971,6 +966,7 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
         if (lane == 0) mbar_arrive_expect_tx(&h_bar[nxt], TX);
         bulk_s2cluster(dst_h + (uint32_t)(nxt * LSTM_CL * TC_BLK), smem_u32(stg), TC_BLK, dst_bar + (uint32_t)(nxt * sizeof(uint64_t)));
       }
+      load_g(step + 1);  // next step's input projections: in flight during the exchange, never in front of the proxy fence
       if (cvalid) {  // layer output to HBM: off the critical path
         const uint32_t row = crow0 + tt;
         if (Hout) *reinterpret_cast<float2*>(Hout + (size_t)(row * (uint32_t)ldh + ccol)) = make_float2(h0, h1);
@@ -994,7 +990,7 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
 
 static int launch_tc(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs, int B,
                      int F, int slots, cudaStream_t stream) {
-  const size_t smem = (size_t)2 * LSTM_CL * TC_BLK + 2 * TC_BLK + (size_t)4 * 32 * TC_ACT_LD * 4 + 64 + 128;
+  const size_t smem = (size_t)2 * LSTM_CL * TC_BLK + 2 * TC_BLK + (size_t)4 * TC_N * 32 * 4 + 64 + 128;
   auto kern = lstm_rec_tc_kernel;
   RFX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RFX_REQUIRE((long long)B * F * (long long)ldg < (1ll << 32) && (long long)B * F * (long long)std::max(ldh, ldhs) < (1ll << 32),
@@ -1059,6 +1055,12 @@ int launch_lstm_layer(const float* G, int ldg, const float* Whh, float* Hout, in
 
 int launch_lstm_layer_slots(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo,
                             int ldhs, int B, int F, int H, int slots, cudaStream_t stream) {
+  return launch_lstm_layer_impl(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, H, -1, slots, stream);
+}
+
+int launch_lstm_layer_impl(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo,
+                           int ldhs, int B, int F, int H, int impl, int slots, cudaStream_t stream) {
+  const int g_lstm_impl = impl >= 0 ? impl : rfx::lstm_get_impl();  // shadows the process-wide default below
   RFX_REQUIRE(H == 192 || H == 256 || H == 384, "lstm: hidden size per direction must be 192, 256 or 384");
   RFX_REQUIRE(B > 0 && F > 0, "lstm: positive sizes");
   RFX_REQUIRE(((uintptr_t)Whh & 15) == 0, "lstm: W_hh must be 16-byte aligned");

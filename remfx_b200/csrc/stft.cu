@@ -8,6 +8,7 @@
 #include "kernels.h"
 #include "fft.cuh"
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -116,11 +117,80 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) stft_kernel(StftParams p, i
   }
 }
 
+// n_fft = 2048 (Open-Unmix, the Cnn14 mel front end, the widest loss resolution): FOUR frames per 256-thread CTA at once, one per
+// 64-thread group, on the register-pass FFT (fft1024_x4: radix 16, 16, 4; two shared-memory exchanges instead of five).
+// Every thread keeps 16 independent loads in flight in the load phase, which is what hides the HBM latency.
+__global__ void __launch_bounds__(256) stft2048_kernel(StftParams p, int groups, int n_work) {
+  constexpr int NC = 1024, NFFT = 2048;
+  __shared__ float2 buf[4 * FFT1024_BUF];
+  const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
+  float2* fb = buf + g * FFT1024_BUF;
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {  // work item = (batch item, group of 4 frames)
+    const int b = work / groups;
+    const int f = (work - b * groups) * 4 + g;
+    const bool active = f < p.F;
+    const float* __restrict__ x = p.x + (size_t)b * p.x_bstride;
+    const int base = f * p.hop - p.frame_off;  // first sample of the frame (frame_off = n_fft/2 for centre padding)
+    const bool interior = active && (base >= 0) && (base + NFFT <= p.T);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int n = t + 64 * r;
+      float2 v = make_float2(0.f, 0.f);
+      if (active) {
+        const float2 w = *reinterpret_cast<const float2*>(p.window + 2 * n);
+        if (interior && p.x_aligned8) {
+          v = *reinterpret_cast<const float2*>(x + base + 2 * n);
+        } else {
+          v.x = x[reflect_index(base + 2 * n, p.T)];
+          v.y = x[reflect_index(base + 2 * n + 1, p.T)];
+        }
+        v.x *= w.x;
+        v.y *= w.y;
+      }
+      fb[n] = v;
+    }
+    fft1024_x4(buf, p.tw, tid);
+    if (active) {
+      const size_t m = (size_t)b * p.F + f;
+      for (int k = t; k < p.nbins; k += 64) {
+        float2 X = rfft_post(fb, p.tw, NC, k);
+        X.x *= p.scale;
+        X.y *= p.scale;
+        if (p.Z) p.Z[m * p.ldz + k] = X;
+        if (p.mode != STFT_COMPLEX) {
+          const float pw = X.x * X.x + X.y * X.y;
+          float a;
+          switch (p.mode) {
+            case STFT_UMX_MAG: a = (sqrtf(pw) + p.in_mean[k]) * p.in_scale[k]; break;  // ComplexNorm (transforms.py:211) + input affine (model.py:127-128)
+            case STFT_MAG: a = sqrtf(pw); break;
+            case STFT_POWER: a = pw; break;
+            case STFT_MAG_CLAMP: a = sqrtf(fmaxf(pw, 1e-8f)); break;
+            default: a = powf(sqrtf(pw) + 1e-8f, p.alpha); break;  // STFT_MAG_POW
+          }
+          if (p.A) p.A[m * p.lda + k] = a;
+          if (p.Ahi) {  // split-bf16 copy for the tensor-core layer that consumes it
+            __nv_bfloat16 h, l;
+            split_bf16(a, h, l);
+            p.Ahi[m * p.ldas + k] = h;
+            p.Alo[m * p.ldas + k] = l;
+          }
+        }
+      }
+      if (p.A && p.lda > NC + 1) {
+        for (int k = NC + 1 + t; k < p.lda; k += 64) p.A[m * p.lda + k] = 0.0f;
+      }
+    }
+    __syncthreads();  // buf is refilled by the next work item
+  }
+}
+
 int launch_stft(const StftParams& p, int B, cudaStream_t stream) {
   RFX_REQUIRE(p.tw != nullptr, "twiddle table");
   RFX_REQUIRE(p.T > p.n_fft / 2, "reflect padding needs T > n_fft/2");
   RFX_REQUIRE(p.frame_off >= 0 && p.frame_off < p.T && p.nbins >= 1 && p.nbins <= p.n_fft / 2 + 1, "stft frame_off / nbins");
-  const int groups = ceil_div(p.F, STFT_FPC);
+  static const bool generic2048 = [] { const char* e = getenv("RFX_STFT_GENERIC"); return e && atoi(e) != 0; }();
+  const bool fast = p.n_fft == 2048 && !generic2048;
+  const int groups = ceil_div(p.F, fast ? 4 : STFT_FPC);
   const long long n_work_ll = (long long)groups * B;
   RFX_REQUIRE(n_work_ll < (1ll << 31), "stft: too many frames");
   const int n_work = (int)n_work_ll;
@@ -131,7 +201,8 @@ int launch_stft(const StftParams& p, int B, cudaStream_t stream) {
     switch (p.n_fft) {
       case 512: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel<8>, 64, 0); break;
       case 1024: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel<9>, 128, 0); break;
-      case 2048: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel<10>, 256, 0); break;
+      case 2048: e = fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft2048_kernel, 256, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel<10>, 256, 0); break;
       case 4096: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel<11>, 512, 0); break;
       default: break;
     }
@@ -142,7 +213,10 @@ int launch_stft(const StftParams& p, int B, cudaStream_t stream) {
   switch (p.n_fft) {
     case 512: stft_kernel<8><<<grid, 64, 0, stream>>>(p, groups, n_work); break;
     case 1024: stft_kernel<9><<<grid, 128, 0, stream>>>(p, groups, n_work); break;
-    case 2048: stft_kernel<10><<<grid, 256, 0, stream>>>(p, groups, n_work); break;
+    case 2048:
+      if (fast) stft2048_kernel<<<grid, 256, 0, stream>>>(p, groups, n_work);
+      else stft_kernel<10><<<grid, 256, 0, stream>>>(p, groups, n_work);
+      break;
     case 4096: stft_kernel<11><<<grid, 512, 0, stream>>>(p, groups, n_work); break;
     default: set_error("stft: n_fft must be 512, 1024, 2048 or 4096"); return 2;
   }
@@ -239,6 +313,114 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) istft_kernel(IstftParams p,
   }
 }
 
+// n_fft = 2048 version: the frames overlapping the CTA's output segment are inverse-transformed FOUR at a time (one per 64-thread
+// group, fft1024_x4), so four frames' spectrum / mask loads are in flight together; the overlap-add of the four results is done by
+// all 256 threads, frame after frame in a fixed order (deterministic, no atomics).
+__global__ void __launch_bounds__(256) istft2048_kernel(IstftParams p, int segs, int n_work) {
+  constexpr int NC = 1024, NFFT = 2048;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* buf = reinterpret_cast<float2*>(smem_raw);          // [4][FFT1024_BUF]
+  float* ola = reinterpret_cast<float*>(buf + 4 * FFT1024_BUF);  // [S]
+  const int tid = threadIdx.x, g = tid >> 6, tl = tid & 63;
+  float2* fb = buf + g * FFT1024_BUF;
+  const int S = p.hops_per_cta * p.hop;
+  const float inv = p.scale / (float)NC;
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {  // work item = (batch item, output segment)
+    const int b = work / segs;
+    const int s0 = (work - b * segs) * S;  // first output sample of this segment
+    for (int i = tid; i < S; i += 256) ola[i] = 0.0f;
+    // frame t covers output samples [t*hop - frame_off, t*hop - frame_off + NFFT): those intersecting [s0, s0 + S)
+    const int lo_num = s0 + p.frame_off - NFFT;  // t*hop > lo_num
+    const int t_lo = lo_num < 0 ? 0 : lo_num / p.hop + 1;
+    int t_hi = (s0 + S + p.frame_off + p.hop - 1) / p.hop - 1;
+    if (t_hi > p.F - 1) t_hi = p.F - 1;
+    for (int tb = t_lo; tb <= t_hi; tb += 4) {
+      const int t = tb + g;
+      if (t <= t_hi) {
+        const size_t m = (size_t)b * p.F + t;
+        const float2* __restrict__ Zr = p.Z + m * p.ldz;
+        const float* __restrict__ Mr = p.mask ? p.mask + m * p.ldm : nullptr;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int k = tl + 64 * r;  // k in [0, NC/2)
+          float2 xk = Zr[k], xn = (NC - k < p.nbins) ? Zr[NC - k] : make_float2(0.f, 0.f);
+          if (Mr) {
+            const float mk = Mr[k], mn = (NC - k < p.nbins) ? Mr[NC - k] : 0.f;
+            xk.x *= mk; xk.y *= mk; xn.x *= mn; xn.y *= mn;
+          }
+          if (k == 0) {  // irfft ignores the imaginary part of the DC and Nyquist bins
+            xk.y = 0.0f;
+            xn.y = 0.0f;
+            fb[0] = irfft_pre(xk, xn, p.tw[0]);
+          } else {
+            fb[k] = irfft_pre(xk, xn, p.tw[k]);
+            fb[NC - k] = irfft_pre(xn, xk, p.tw[NC - k]);
+          }
+        }
+        if (tl == 0) {
+          float2 xh = Zr[NC / 2];
+          if (Mr) { const float mh = Mr[NC / 2]; xh.x *= mh; xh.y *= mh; }
+          fb[NC / 2] = irfft_pre(xh, xh, p.tw[NC / 2]);
+        }
+      }
+      fft1024_x4(buf, p.tw, tid);
+      for (int gg = 0; gg < 4 && tb + gg <= t_hi; ++gg) {  // overlap-add, one frame at a time (CTA-uniform loop)
+        const float2* res = buf + gg * FFT1024_BUF;
+        const int off = (tb + gg) * p.hop - p.frame_off - s0;  // segment-relative position of frame sample 0
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int n = tid + r * 256;
+          const float2 v = res[n];
+          const float2 w = *reinterpret_cast<const float2*>(p.window + 2 * n);
+          const int q = off + 2 * n;
+          if (q >= 0 && q < S) ola[q] += v.x * inv * w.x;
+          if (q + 1 >= 0 && q + 1 < S) ola[q + 1] += -v.y * inv * w.y;
+        }
+        __syncthreads();
+      }
+    }
+    // envelope sum_t w^2 (torch.istft window_envelop), then crop to `length`
+    float* __restrict__ out = p.out + (size_t)b * p.out_bstride;
+    for (int i = tid; i < S; i += 256) {
+      const int s = s0 + i;
+      if (s >= p.length) break;
+      const int q = s + p.frame_off + p.env_pad * p.hop;  // shift so that frame indices start at 0
+      const int Fe = p.F + 2 * p.env_pad;
+      int ta = (q - NFFT + p.hop) / p.hop;  // ceil((q - NFFT + 1) / hop) for q - NFFT + 1 >= 0
+      if (q - NFFT + 1 <= 0) ta = 0;
+      int tbb = q / p.hop;
+      if (tbb > Fe - 1) tbb = Fe - 1;
+      float env = 0.0f;
+      for (int tt = ta; tt <= tbb; ++tt) {
+        const float w = p.window[q - tt * p.hop];
+        env += w * w;
+      }
+      out[s] = (env > 1e-11f) ? ola[i] / env : 0.0f;
+    }
+    __syncthreads();  // ola is zeroed again by the next work item
+  }
+}
+
+static int launch_istft2048(const IstftParams& p, int B, cudaStream_t stream) {
+  const int S = p.hops_per_cta * p.hop;
+  const size_t smem = sizeof(float2) * 4 * FFT1024_BUF + sizeof(float) * S;
+  RFX_CHECK_CUDA(cudaFuncSetAttribute(istft2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int segs = ceil_div(p.length, S);
+  const long long n_work_ll = (long long)segs * B;
+  RFX_REQUIRE(n_work_ll < (1ll << 31), "istft: too many segments");
+  const int n_work = (int)n_work_ll;
+  int grid = n_work;
+  if (p.max_sms > 0) {
+    int per_sm = 0;
+    RFX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, istft2048_kernel, 256, smem));
+    const long long cap = (long long)p.max_sms * (per_sm > 0 ? per_sm : 1);
+    if (cap < grid) grid = (int)cap;
+  }
+  istft2048_kernel<<<grid, 256, smem, stream>>>(p, segs, n_work);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int LOG2NC>
 static int launch_istft_t(const IstftParams& p, int B, cudaStream_t stream) {
   constexpr int NC = 1 << LOG2NC;
@@ -267,7 +449,10 @@ int launch_istft(const IstftParams& p, int B, cudaStream_t stream) {
   switch (p.n_fft) {
     case 512: return launch_istft_t<8>(p, B, stream);
     case 1024: return launch_istft_t<9>(p, B, stream);
-    case 2048: return launch_istft_t<10>(p, B, stream);
+    case 2048: {
+      static const bool generic2048 = [] { const char* e = getenv("RFX_STFT_GENERIC"); return e && atoi(e) != 0; }();
+      return generic2048 ? launch_istft_t<10>(p, B, stream) : launch_istft2048(p, B, stream);
+    }
     case 4096: return launch_istft_t<11>(p, B, stream);
     default: set_error("istft: n_fft must be 512, 1024, 2048 or 4096"); return 2;
   }

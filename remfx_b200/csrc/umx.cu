@@ -9,6 +9,8 @@
 #include "kernels.h"
 #include "../../include/remfx_b200.h"
 
+#include <cuda.h>
+
 #include <cstdlib>
 #include <map>
 #include <string>
@@ -61,6 +63,62 @@ int launch_add_vec(const float* a, const float* b, float* out, int n, cudaStream
 
 using namespace rfx;
 
+// ---- SM partitioning with CUDA green contexts (driver entry points fetched at run time, like the tensor-map encoder) ----
+namespace {
+template <class Fn>
+Fn drv(const char* name) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+  return reinterpret_cast<Fn>(p);
+}
+void umx_green_destroy(CUgreenCtx a, CUgreenCtx b) {
+  auto destroy = drv<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
+  if (!destroy) return;
+  if (a) destroy(a);
+  if (b) destroy(b);
+}
+// Splits the device's SMs into a group of >= want_rec SMs (cluster-capable) and the rest; creates one green context per group
+// and n_rec + n_rest non-blocking streams in them.  Returns false (nothing created) when any step is unsupported.
+bool umx_green_partition(int want_rec, int n_rec, cudaStream_t* rec, int n_rest, cudaStream_t* rest, CUgreenCtx* gr, CUgreenCtx* gs,
+                         int* got_rec, int* got_rest) {
+  auto getRes = drv<CUresult (*)(CUdevice, CUdevResource*, CUdevResourceType)>("cuDeviceGetDevResource");
+  auto split = drv<CUresult (*)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int)>(
+      "cuDevSmResourceSplitByCount");
+  auto genDesc = drv<CUresult (*)(CUdevResourceDesc*, CUdevResource*, unsigned int)>("cuDevResourceGenerateDesc");
+  auto create = drv<CUresult (*)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int)>("cuGreenCtxCreate");
+  auto mkStream = drv<CUresult (*)(CUstream*, CUgreenCtx, unsigned int, int)>("cuGreenCtxStreamCreate");
+  auto destroy = drv<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
+  if (!getRes || !split || !genDesc || !create || !mkStream || !destroy) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  CUdevResource all{}, grp{}, rem{};
+  if (getRes((CUdevice)dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+  unsigned int nb = 1;
+  if (split(&grp, &nb, &all, &rem, 0, (unsigned int)want_rec) != CUDA_SUCCESS || nb != 1) return false;
+  if ((int)grp.sm.smCount < want_rec || rem.sm.smCount == 0) return false;
+  CUdevResourceDesc d_rec{}, d_rest{};
+  if (genDesc(&d_rec, &grp, 1) != CUDA_SUCCESS || genDesc(&d_rest, &rem, 1) != CUDA_SUCCESS) return false;
+  CUgreenCtx a = nullptr, b = nullptr;
+  if (create(&a, d_rec, (CUdevice)dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+  if (create(&b, d_rest, (CUdevice)dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { destroy(a); return false; }
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  bool ok = true;
+  for (int i = 0; i < n_rec && ok; ++i) ok = mkStream((CUstream*)&rec[i], a, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS;
+  for (int i = 0; i < n_rest && ok; ++i) ok = mkStream((CUstream*)&rest[i], b, CU_STREAM_NON_BLOCKING, lo) == CUDA_SUCCESS;
+  if (!ok) {
+    for (int i = 0; i < n_rec; ++i) if (rec[i]) { cudaStreamDestroy(rec[i]); rec[i] = nullptr; }
+    for (int i = 0; i < n_rest; ++i) if (rest[i]) { cudaStreamDestroy(rest[i]); rest[i] = nullptr; }
+    destroy(a); destroy(b);
+    return false;
+  }
+  *gr = a; *gs = b;
+  *got_rec = (int)grp.sm.smCount; *got_rest = (int)rem.sm.smCount;
+  return true;
+}
+}  // namespace
+
 struct rfx_umx {
   rfx_umx_config cfg;
   int bins = 0, H = 0;
@@ -105,7 +163,11 @@ struct rfx_umx {
     Done done[kRing];
     long long pushed = 0;
     void* ws = nullptr;
-    int sms = 0, max_sms = 0, lstm_slots = 0;
+    int sms = 0, max_sms = 0, lstm_slots = 0, lstm_impl = -1;
+    // SM partition (CUDA green contexts): the recurrence streams own `rec_sms_granted` SMs, every other stream the rest.
+    // When the driver cannot provide it the pipeline falls back to capping the grids of the non-recurrent kernels.
+    CUgreenCtx gctx_rec = nullptr, gctx_rest = nullptr;
+    int rec_sms_granted = 0, rest_sms_granted = 0;
     // optional timing of the recurrence launches (a pair of timing events around each, on the recurrence stream)
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -131,6 +193,7 @@ struct rfx_umx {
     for (auto r : pipe.rec)
       if (r) cudaStreamDestroy(r);
     for (auto e : pipe.prof_ev) cudaEventDestroy(e);
+    umx_green_destroy(pipe.gctx_rec, pipe.gctx_rest);
     for (auto e : events) cudaEventDestroy(e);
     for (auto& kv : params) kv.second.release();
     for (int i = 0; i < 3; ++i) { bn_s[i].release(); bn_t[i].release(); }
@@ -327,6 +390,7 @@ struct UmxCall {
   const HostIO* io;
   int max_sms;          // > 0: non-recurrent kernels keep to this many SMs
   int lstm_slots;       // batch slots per recurrence cluster (0 = automatic)
+  int lstm_impl;        // recurrence kernel (-1 = process default: mma.sync; 2 = tcgen05)
 };
 
 int umx_stage(rfx_umx_t* h, const UmxCall& c, int l) {
@@ -409,7 +473,8 @@ int umx_stage(rfx_umx_t* h, const UmxCall& c, int l) {
     }
     const bool timed = !serial && h->pipe.prof && 2 * h->pipe.prof_n + 1 < (int)h->pipe.prof_ev.size();
     if (timed) RFX_CHECK_CUDA(cudaEventRecord(h->pipe.prof_ev[2 * h->pipe.prof_n], c.s_rec));
-    if ((rc = launch_lstm_layer_slots(G, 8 * H, h->whh_cat[l].p, nullptr, 0, hout, hout + hplane, ldh, B, L.F, H, c.lstm_slots, c.s_rec)))
+    if ((rc = launch_lstm_layer_impl(G, 8 * H, h->whh_cat[l].p, nullptr, 0, hout, hout + hplane, ldh, B, L.F, H, c.lstm_impl, c.lstm_slots,
+                                     c.s_rec)))
       return rc;
     if (timed) { RFX_CHECK_CUDA(cudaEventRecord(h->pipe.prof_ev[2 * h->pipe.prof_n + 1], c.s_rec)); ++h->pipe.prof_n; }
     if (!serial) {
@@ -477,6 +542,7 @@ int umx_forward(rfx_umx_t* h, const float* x, int B, int T, float* out, void* wo
   RFX_REQUIRE(workspace_bytes >= c.L.total, "workspace too small (see rfx_umx_workspace_bytes)");
   c.s = c.s_rec = (cudaStream_t)stream;
   c.io = io;
+  c.lstm_impl = -1;
   const int nl = h->cfg.nb_layers;
   const int n_stage = 5 + 2 * nl;
   if (h->profiling && (int)h->events.size() != n_stage + 1) {
@@ -511,39 +577,67 @@ int umx_pipe_setup(rfx_umx_t* h, int B, int T) {
   rfx_umx::Pipe& p = h->pipe;
   int rc;
   if ((rc = umx_host_setup(h))) return rc;
-  if (!p.ready) {
-    RFX_REQUIRE(h->cfg.nb_layers <= rfx_umx::kSlots, "the pipeline supports at most 4 LSTM layers");
-    p.depth = h->cfg.nb_layers;
+  if (p.ready && p.B == B && p.T == T) return 0;
+  if (p.ready)
+    for (int i = 0; i < p.depth; ++i) RFX_REQUIRE(!p.lane[i].live, "pipeline: batch shape changed while steps are in flight (flush first)");
+  RFX_REQUIRE(h->cfg.nb_layers <= rfx_umx::kSlots, "the pipeline supports at most 4 LSTM layers");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  RFX_CHECK_CUDA(cudaDeviceGetAttribute(&p.sms, cudaDevAttrMultiProcessorCount, dev));
+  // Schedule: `slots` batch slots per recurrence cluster, `streams` recurrence launches side by side.  The recurrences are
+  // packed into the fewest SMs; every other kernel keeps to the rest of the chip so that a recurrence launch never waits
+  // for SMs.  Too small a remainder -> no partition.
+  // Default: the tcgen05 recurrence (16 slots per cluster, half the SMs of the mma.sync kernel per launch) on two streams.
+  int impl = h->H == 256 ? 2 : -1, slots = impl == 2 ? 16 : 8, streams = impl == 2 ? 2 : 1;
+  if (const char* e = getenv("RFX_UMX_PIPE_LSTM_IMPL")) { impl = atoi(e); slots = impl == 2 ? 16 : 8; streams = impl == 2 ? 2 : 1; }  // tuning overrides
+  if (const char* e = getenv("RFX_UMX_PIPE_SLOTS")) slots = atoi(e);
+  if (const char* e = getenv("RFX_UMX_PIPE_REC_STREAMS")) streams = std::min(4, std::max(1, atoi(e)));
+  p.lstm_impl = impl;
+  const int rec_sms = streams * 8 * lstm_clusters_for(B, slots);
+  const bool part = slots > 0 && p.sms - rec_sms >= p.sms / 4;
+  if (!part) { slots = 0; streams = 1; }
+  // (re)build the streams for this shape: the SM partition depends on the batch size
+  if (p.ready) {
+    RFX_CHECK_CUDA(cudaDeviceSynchronize());
+    for (auto& r : p.rec) if (r) { cudaStreamDestroy(r); r = nullptr; }
+    for (int i = 0; i < p.depth; ++i) if (p.lane[i].s) { cudaStreamDestroy(p.lane[i].s); p.lane[i].s = nullptr; }
+    umx_green_destroy(p.gctx_rec, p.gctx_rest);
+    p.gctx_rec = p.gctx_rest = nullptr;
+  }
+  p.depth = h->cfg.nb_layers;
+  p.rec_n = streams;
+  p.lstm_slots = slots;
+  p.max_sms = 0;
+  bool green = false;
+  static const bool allow_green = [] { const char* e = getenv("RFX_UMX_PIPE_GREEN"); return !e || atoi(e) != 0; }();
+  if (part && allow_green) {
+    cudaStream_t rs[4] = {nullptr, nullptr, nullptr, nullptr}, ls[rfx_umx::kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    green = umx_green_partition(rec_sms, p.rec_n, rs, p.depth, ls, &p.gctx_rec, &p.gctx_rest, &p.rec_sms_granted, &p.rest_sms_granted);
+    if (green) {
+      for (int i = 0; i < p.rec_n; ++i) p.rec[i] = rs[i];
+      for (int i = 0; i < p.depth; ++i) p.lane[i].s = ls[i];
+    }
+  }
+  if (!green) {
     int lo = 0, hi = 0;  // numerically lowest value = highest priority
     RFX_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    for (auto& r : p.rec) RFX_CHECK_CUDA(cudaStreamCreateWithPriority(&r, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < p.rec_n; ++i) RFX_CHECK_CUDA(cudaStreamCreateWithPriority(&p.rec[i], cudaStreamNonBlocking, hi));
+    for (int i = 0; i < p.depth; ++i) RFX_CHECK_CUDA(cudaStreamCreateWithPriority(&p.lane[i].s, cudaStreamNonBlocking, lo));
+    p.rec_sms_granted = p.rest_sms_granted = 0;
+    if (part) p.max_sms = p.sms - rec_sms;  // fallback: cap the grids of the non-recurrent kernels instead
+  }
+  if (const char* e = getenv("RFX_UMX_PIPE_MAX_SMS")) p.max_sms = atoi(e);
+  if (!p.ready) {
     for (int i = 0; i < p.depth; ++i) {
       rfx_umx::Lane& l = p.lane[i];
-      RFX_CHECK_CUDA(cudaStreamCreateWithPriority(&l.s, cudaStreamNonBlocking, lo));
       for (cudaEvent_t* e : {&l.ev_x, &l.ev_pre, &l.ev_rec, &l.ev_stft})
         RFX_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
     for (auto& d : p.done) RFX_CHECK_CUDA(cudaEventCreateWithFlags(&d.ev, cudaEventDisableTiming));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    RFX_CHECK_CUDA(cudaDeviceGetAttribute(&p.sms, cudaDevAttrMultiProcessorCount, dev));
-    p.ready = true;
   }
-  if (p.B != B || p.T != T) {
-    for (int i = 0; i < p.depth; ++i) RFX_REQUIRE(!p.lane[i].live, "pipeline: batch shape changed while steps are in flight (flush first)");
-    p.B = B; p.T = T;
-    // The recurrences are packed into the fewest SMs (8 batch slots per cluster); every other kernel keeps to the rest of
-    // the chip so that a recurrence launch never waits for SMs.  Too small a remainder -> no partition.
-    int slots = 8, streams = 1;
-    // tuning overrides (experiments only)
-    if (const char* e = getenv("RFX_UMX_PIPE_SLOTS")) slots = atoi(e);
-    if (const char* e = getenv("RFX_UMX_PIPE_REC_STREAMS")) streams = std::min(4, std::max(1, atoi(e)));
-    const int rec_sms = streams * 8 * lstm_clusters_for(B, slots);
-    if (slots > 0 && p.sms - rec_sms >= p.sms / 4) { p.max_sms = p.sms - rec_sms; p.lstm_slots = slots; p.rec_n = streams; }
-    else { p.max_sms = 0; p.lstm_slots = slots > 0 ? 0 : slots; p.rec_n = 1; }
-    if (slots == 0) p.lstm_slots = 0;
-    if (const char* e = getenv("RFX_UMX_PIPE_MAX_SMS")) p.max_sms = atoi(e);
-  }
+  for (int i = 0; i < p.depth; ++i) { p.lane[i].stft_recorded = false; p.lane[i].host_out_pending = nullptr; }
+  p.B = B; p.T = T;
+  p.ready = true;
   return 0;
 }
 
@@ -567,7 +661,7 @@ int umx_pipe_superstep(rfx_umx_t* h) {
       c.s = ln.s; c.s_rec = p.rec[p.rec_count++ % p.rec_n];
       c.ev_pre = ln.ev_pre; c.ev_rec = ln.ev_rec; c.ev_stft = ln.ev_stft;
       c.io = (ln.x_host || ln.out_host) ? &io : nullptr;
-      c.max_sms = p.max_sms; c.lstm_slots = p.lstm_slots;
+      c.max_sms = p.max_sms; c.lstm_slots = p.lstm_slots; c.lstm_impl = p.lstm_impl;
       if (st == 0 && ln.x_host && ln.stft_recorded) RFX_CHECK_CUDA(cudaStreamWaitEvent(h->copy_in, ln.ev_stft, 0));  // staging free
       int rc;
       if ((rc = umx_stage(h, c, st))) return rc;
@@ -600,6 +694,16 @@ size_t rfx_umx_pipe_workspace_bytes(const rfx_umx_t* h, int B, int T) {
 }
 
 int rfx_umx_pipe_depth(const rfx_umx_t* h) { return h ? h->cfg.nb_layers : 0; }
+
+int rfx_umx_pipe_info(const rfx_umx_t* h, int* rec_sms, int* rest_sms, int* rec_streams, int* slots_per_cluster) {
+  RFX_REQUIRE(h && rec_sms && rest_sms && rec_streams && slots_per_cluster, "null argument");
+  const rfx_umx::Pipe& p = h->pipe;
+  *rec_sms = p.rec_sms_granted;    // 0 = no green-context partition (grid caps instead, or no partition at all)
+  *rest_sms = p.rec_sms_granted ? p.rest_sms_granted : p.max_sms;
+  *rec_streams = p.rec_n;
+  *slots_per_cluster = p.lstm_slots;
+  return 0;
+}
 
 int rfx_umx_pipe_push(rfx_umx_t* h, const float* x, int x_on_host, int B, int T, float* out, int out_on_host, void* workspace,
                       size_t workspace_bytes, void* stream, long long* seq_out) {

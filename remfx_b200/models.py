@@ -288,6 +288,13 @@ class UmxPipeline:
         _lib.check(_lib.lib().rfx_umx_pipe_wait(self._h, int(seq)), "rfx_umx_pipe_wait")
         return self._keep[seq][1] if seq in self._keep else None
 
+    def info(self) -> dict:
+        """Schedule facts (valid after the first push): SM partition, recurrence streams, slots per recurrence cluster."""
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.check(_lib.lib().rfx_umx_pipe_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "rfx_umx_pipe_info")
+        return {"recurrence_sms": a.value, "other_sms": b.value, "recurrence_streams": c.value, "slots_per_cluster": d.value,
+                "partition": "green contexts" if a.value else ("grid caps" if b.value else "none")}
+
     def set_profiling(self, max_launches: int) -> None:
         """Time the next `max_launches` recurrence launches with cudaEvents on the recurrence stream (0 = off)."""
         _lib.check(_lib.lib().rfx_umx_pipe_set_profiling(self._h, int(max_launches)), "rfx_umx_pipe_set_profiling")

@@ -63,8 +63,34 @@ static int run(int n_fft) {
   return (maxerr < 2e-5 * maxref + 1e-5 && ierr < 1e-5) ? 0 : 1;
 }
 
+// radix 16 x 16 x 4 register-pass FFT (fft1024_*): compare with a double-precision DFT
+static int run1024() {
+  const int N = 1024;
+  std::vector<float2> tw(2048);
+  for (int m = 0; m < 2048; ++m) tw[m] = make_float2((float)cos(-2.0 * M_PI * m / 2048), (float)sin(-2.0 * M_PI * m / 2048));
+  std::vector<float2> a(FFT1024_BUF), b(FFT1024_BUF), x(N);
+  srand(7);
+  for (int n = 0; n < N; ++n) x[n] = a[n] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+  for (int j = 0; j < 64; ++j) fft1024_pass_r16<false, true>(a.data(), b.data(), tw.data(), 1, j);
+  for (int j = 0; j < 64; ++j) fft1024_pass_r16<true, true>(b.data(), a.data(), tw.data(), 16, j);
+  for (int j = 0; j < 256; ++j) fft1024_pass_r4_last(a.data(), b.data(), tw.data(), j);
+  double maxerr = 0, maxref = 0;
+  for (int k = 0; k < N; ++k) {
+    double re = 0, im = 0;
+    for (int n = 0; n < N; ++n) {
+      const double c = cos(-2.0 * M_PI * k * n / N), s = sin(-2.0 * M_PI * k * n / N);
+      re += x[n].x * c - x[n].y * s;
+      im += x[n].x * s + x[n].y * c;
+    }
+    maxerr = fmax(maxerr, hypot(b[k].x - re, b[k].y - im));
+    maxref = fmax(maxref, hypot(re, im));
+  }
+  printf("fft1024 (16x16x4) max err %.3e (max |X| %.2f)\n", maxerr, maxref);
+  return maxerr < 2e-5 * maxref ? 0 : 1;
+}
+
 int main() {
-  int bad = 0;
+  int bad = run1024();
   for (int n : {64, 128, 512, 1024, 2048, 4096}) bad += run(n);
   printf(bad ? "FAIL\n" : "OK\n");
   return bad;

@@ -77,6 +77,14 @@ def test_lstm_layer_multi_group_clusters(B, F, slots):
     assert relrms(out16, out8) < 2e-6
 
 
+@pytest.mark.parametrize("B,F", [(1, 5), (16, 20), (21, 33), (32, 64), (40, 17)])
+def test_lstm_layer_tcgen05(B, F):
+    """tcgen05 recurrence (W_hh as the TMEM A operand, 16 slots per cluster) vs the explicit-loop oracle and the mma.sync kernel."""
+    out_tc = _lstm_case(256, 512, B, F, "tc")
+    out_mma = _lstm_case(256, 512, B, F, "mma", slots=8)
+    assert relrms(out_tc, out_mma) < 2e-6
+
+
 def _lstm_case(H, I, B, F, impl, slots=0):
     ops = _ops()
     g = torch.Generator().manual_seed(B * 100 + F)

@@ -98,7 +98,8 @@ def test_bad_inputs_raise():
 
 @pytest.mark.parametrize("host", [False, True])
 def test_pipeline_equals_sample(host):
-    """The multi-lane pipeline runs the same kernels in the same per-step order: outputs are bit-identical to sample()."""
+    """The multi-lane pipeline vs sample(): same math per batch, but the pipeline's recurrences run on the tcgen05 kernel (same
+    bf16x3 products, different fp32 summation order than the mma.sync kernel sample() uses), so agreement is to ~1e-6, not bitwise."""
     sd = weights.umx_state(5)
     m = _model(sd)
     B, T, n = 5, 32768, 8
@@ -118,21 +119,22 @@ def test_pipeline_equals_sample(host):
         if i >= pipe.depth - 1:
             done = seqs[i - (pipe.depth - 1)]
             pipe.wait(done)  # step i - 2 has left the pipeline
-            assert torch.equal(outs[i - (pipe.depth - 1)].cpu(), refs[i - (pipe.depth - 1)])
+            assert relrms(outs[i - (pipe.depth - 1)].cpu(), refs[i - (pipe.depth - 1)]) < 5e-6
     pipe.flush()
     torch.cuda.synchronize()
     for i in range(n):
-        assert torch.equal(outs[i].cpu(), refs[i]), i
+        assert relrms(outs[i].cpu(), refs[i]) < 5e-6, i
     # a second burst on the same pipeline object (lanes restart cleanly after a flush), mixed with a shape change
     s = pipe.push(ins[0], outs[1])
     pipe.flush()
     pipe.wait(s)
-    assert torch.equal(outs[1].cpu(), refs[0])
+    assert relrms(outs[1].cpu(), refs[0]) < 5e-6
     x2 = weights.synth_audio(999, 2, 16384)
     s2 = pipe.push(x2.cuda())
     pipe.flush()
     o2 = pipe.wait(s2)
-    assert torch.equal(o2.cpu(), m.sample(x2.cuda()).cpu())
+    assert relrms(o2.cpu(), m.sample(x2.cuda()).cpu()) < 5e-6
+    assert relrms(o2.cpu(), oumx.sample(x2, sd)) < TOL
 
 
 def test_pipeline_wait_before_exit_raises():

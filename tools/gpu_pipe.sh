@@ -1,6 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 python tools/lstm_tc_probe.py 2>&1 | tail -3
-timeout 120 python tools/lstm_bench.py 32 2>&1 | tail -2
-RFX_LSTM_IMPL=2 RFX_UMX_PIPE_SLOTS=16 timeout 120 python tools/pipe_bench.py 32 40 2>&1 | tail -2
-RFX_LSTM_IMPL=2 RFX_UMX_PIPE_SLOTS=16 RFX_UMX_PIPE_REC_STREAMS=2 timeout 120 python tools/pipe_bench.py 32 40 2>&1 | tail -1
+for f in tests/test_gpu_stft.py tests/test_gpu_umx.py tests/test_gpu_cnn14.py tests/test_gpu_gemm_lstm.py; do
+timeout 600 python -m pytest $f -m gpu -q --timeout 200 --no-header -p no:cacheprovider > gpurun_out/t.log 2>&1; echo "$f exit=$? $(tail -n 1 gpurun_out/t.log)"; grep -E "^FAILED|^ERROR|rror:" gpurun_out/t.log | head -8
+done
+RFX_STFT_GENERIC=1 timeout 120 python tools/umx_quick_bench.py 32 2>&1 | tail -2
+timeout 120 python tools/umx_quick_bench.py 32 2>&1 | tail -2
+for i in 1 2; do timeout 120 python tools/pipe_bench.py 32 40 2>&1 | tail -1; done
+RFX_UMX_PIPE_LSTM_IMPL=0 timeout 120 python tools/pipe_bench.py 32 40 2>&1 | tail -1

@@ -43,4 +43,4 @@ e1.record()
 torch.cuda.synchronize()
 rt = pipe.recurrence_times_ms()
 print(f"pipeline: {e0.elapsed_time(e1) / K:.3f} ms/step  (recurrence launches: n={len(rt)} mean {statistics.mean(rt):.3f} median {statistics.median(rt):.3f} "
-      f"max {max(rt):.3f} ms)  env MAX_SMS={os.environ.get('RFX_UMX_PIPE_MAX_SMS')} SLOTS={os.environ.get('RFX_UMX_PIPE_SLOTS')} IMPL={os.environ.get('RFX_LSTM_IMPL')} STREAMS={os.environ.get('RFX_UMX_PIPE_REC_STREAMS')}")
+      f"max {max(rt):.3f} ms) {pipe.info()}  env MAX_SMS={os.environ.get('RFX_UMX_PIPE_MAX_SMS')} SLOTS={os.environ.get('RFX_UMX_PIPE_SLOTS')} IMPL={os.environ.get('RFX_LSTM_IMPL')} STREAMS={os.environ.get('RFX_UMX_PIPE_REC_STREAMS')}")
