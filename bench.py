@@ -282,15 +282,17 @@ def run_ours(args):
     lstm_bytes = M * 8 * H * 4 + M * 2 * H * 4 + 2 * 4 * H * H * 4  # read G, write h, read W_hh once
     lstm_t = statistics.mean(lstm_ms) / 1e3   # average over the recurrence launches of the timed region
     achieved = lstm_bytes / lstm_t / 1e9
+    pinfo = pipe.info()
     roofline = {
-        "kernel": "lstm_rec_mma_kernel (BiLSTM recurrence, 1 launch per layer)", "bound": "hbm", "achieved": achieved,
-        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-        "traffic": 155.4e6,  # dram read+write bytes per launch, ncu --set full (profiles/r1/ncu_lstm_rec_mma.txt)
+        "kernel": "lstm_rec_tc_kernel (BiLSTM recurrence on tcgen05, W_hh as the TMEM A operand; 1 launch per layer)", "bound": "hbm",
+        "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+        "traffic": 155.96e6,  # dram read+write bytes per launch, ncu --set full (profiles/r1/ncu_lstm_rec_tc.txt)
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": lstm_bytes, "ms_per_launch": lstm_t * 1e3,
         "launches_timed": len(lstm_ms),
-        "note": "513 strictly dependent steps per launch: latency-bound by construction, see DESIGN.md; in the pipeline it "
-                "holds 64 SMs while the other kernels of neighbouring steps use the remaining 84",
+        "note": "513 strictly dependent steps per launch: latency-bound by construction, see DESIGN.md; each launch holds 32 SMs, two "
+                "launches run side by side on a 64-SM green-context partition while the other kernels of neighbouring steps use the "
+                "remaining 84 SMs",
         "serial_stage_ms": {k: round(v, 4) for k, v in stage_acc.items()},
     }
 
@@ -303,7 +305,7 @@ def run_ours(args):
                    "gemm": "tcgen05 bf16x3 (fp32-grade)", "l2": f"inputs rotate over {NBUF} buffers (168 MB > 126 MB L2); "
                    "~575 MB of intermediates stream through HBM every step",
                    "schedule": f"{depth}-lane pipeline (OpenUnmixModel.pipeline / rfx_umx_pipe_push), fill + drain inside the timed region",
-                   "single_call_ms": serial_ms},
+                   "single_call_ms": serial_ms, "pipeline": pinfo},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": BATCH * T * 4,
                 "d2h_bytes_per_step": BATCH * T * 4,
                 "api": "OpenUnmixModel.pipeline().push/wait on pinned host tensors (rfx_umx_pipe_push), every result consumed",

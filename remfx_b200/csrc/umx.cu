@@ -609,7 +609,15 @@ int umx_pipe_setup(rfx_umx_t* h, int B, int T) {
   p.lstm_slots = slots;
   p.max_sms = 0;
   bool green = false;
-  static const bool allow_green = [] { const char* e = getenv("RFX_UMX_PIPE_GREEN"); return !e || atoi(e) != 0; }();
+  // Green contexts are skipped under the NVIDIA profilers / injection tools (Nsight Compute kills a process that creates one:
+  // observed with ncu 2025.2) -- the grid-cap partition below runs the same kernels and is what the ncu launch lists trace.
+  static const bool allow_green = [] {
+    if (const char* e = getenv("RFX_UMX_PIPE_GREEN")) return atoi(e) != 0;
+    for (const char* v : {"NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NV_NSIGHT_INJECTION_PORT_BASE", "NV_TPS_LAUNCH_TOKEN", "CUDA_INJECTION64_PATH",
+                          "NVTX_INJECTION64_PATH", "NSYS_PROFILING_SESSION_ID"})
+      if (getenv(v)) return false;
+    return true;
+  }();
   if (part && allow_green) {
     cudaStream_t rs[4] = {nullptr, nullptr, nullptr, nullptr}, ls[rfx_umx::kSlots] = {nullptr, nullptr, nullptr, nullptr};
     green = umx_green_partition(rec_sms, p.rec_n, rs, p.depth, ls, &p.gctx_rec, &p.gctx_rest, &p.rec_sms_granted, &p.rest_sms_granted);
