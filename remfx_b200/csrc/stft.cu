@@ -120,6 +120,16 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) stft_kernel(StftParams p, i
 // n_fft = 2048 (Open-Unmix, the Cnn14 mel front end, the widest loss resolution): FOUR frames per 256-thread CTA at once, one per
 // 64-thread group, on the register-pass FFT (fft1024_x4: radix 16, 16, 4; two shared-memory exchanges instead of five).
 // Every thread keeps 16 independent loads in flight in the load phase, which is what hides the HBM latency.
+template <int MODE>
+__device__ __forceinline__ float stft_mag_of(float pw, float in_mean, float in_scale, float alpha) {
+  if (MODE == STFT_UMX_MAG) return (sqrtf(pw) + in_mean) * in_scale;  // ComplexNorm (transforms.py:211) + input affine (model.py:127-128)
+  if (MODE == STFT_MAG) return sqrtf(pw);
+  if (MODE == STFT_POWER) return pw;
+  if (MODE == STFT_MAG_CLAMP) return sqrtf(fmaxf(pw, 1e-8f));
+  return powf(sqrtf(pw) + 1e-8f, alpha);  // STFT_MAG_POW
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(256) stft2048_kernel(StftParams p, int groups, int n_work) {
   constexpr int NC = 1024, NFFT = 2048;
   __shared__ float2 buf[4 * FFT1024_BUF];
@@ -151,36 +161,47 @@ __global__ void __launch_bounds__(256) stft2048_kernel(StftParams p, int groups,
     }
     fft1024_x4(buf, p.tw, tid);
     if (active) {
+      // epilogue: the mode is a compile-time constant and the row pointers are hoisted, so an iteration is ~30 instructions
       const size_t m = (size_t)b * p.F + f;
+      float2* __restrict__ Zrow = p.Z ? p.Z + m * p.ldz : nullptr;
+      float* __restrict__ Arow = p.A ? p.A + m * p.lda : nullptr;
+      __nv_bfloat16* __restrict__ Hrow = p.Ahi ? p.Ahi + m * p.ldas : nullptr;
+      __nv_bfloat16* __restrict__ Lrow = p.Ahi ? p.Alo + m * p.ldas : nullptr;
+      const float scale = p.scale;
       for (int k = t; k < p.nbins; k += 64) {
         float2 X = rfft_post(fb, p.tw, NC, k);
-        X.x *= p.scale;
-        X.y *= p.scale;
-        if (p.Z) p.Z[m * p.ldz + k] = X;
-        if (p.mode != STFT_COMPLEX) {
+        X.x *= scale;
+        X.y *= scale;
+        if (Zrow) Zrow[k] = X;
+        if (MODE != STFT_COMPLEX) {
           const float pw = X.x * X.x + X.y * X.y;
-          float a;
-          switch (p.mode) {
-            case STFT_UMX_MAG: a = (sqrtf(pw) + p.in_mean[k]) * p.in_scale[k]; break;  // ComplexNorm (transforms.py:211) + input affine (model.py:127-128)
-            case STFT_MAG: a = sqrtf(pw); break;
-            case STFT_POWER: a = pw; break;
-            case STFT_MAG_CLAMP: a = sqrtf(fmaxf(pw, 1e-8f)); break;
-            default: a = powf(sqrtf(pw) + 1e-8f, p.alpha); break;  // STFT_MAG_POW
-          }
-          if (p.A) p.A[m * p.lda + k] = a;
-          if (p.Ahi) {  // split-bf16 copy for the tensor-core layer that consumes it
+          const float a = stft_mag_of<MODE>(pw, MODE == STFT_UMX_MAG ? p.in_mean[k] : 0.f, MODE == STFT_UMX_MAG ? p.in_scale[k] : 1.f, p.alpha);
+          if (Arow) Arow[k] = a;
+          if (Hrow) {  // split-bf16 copy for the tensor-core layer that consumes it
             __nv_bfloat16 h, l;
             split_bf16(a, h, l);
-            p.Ahi[m * p.ldas + k] = h;
-            p.Alo[m * p.ldas + k] = l;
+            Hrow[k] = h;
+            Lrow[k] = l;
           }
         }
       }
-      if (p.A && p.lda > NC + 1) {
-        for (int k = NC + 1 + t; k < p.lda; k += 64) p.A[m * p.lda + k] = 0.0f;
+      if (Arow && p.lda > NC + 1) {
+        for (int k = NC + 1 + t; k < p.lda; k += 64) Arow[k] = 0.0f;
       }
     }
     __syncthreads();  // buf is refilled by the next work item
+  }
+}
+
+typedef void (*Stft2048Fn)(StftParams, int, int);
+static Stft2048Fn stft2048_fn(int mode) {
+  switch (mode) {
+    case STFT_COMPLEX: return stft2048_kernel<STFT_COMPLEX>;
+    case STFT_UMX_MAG: return stft2048_kernel<STFT_UMX_MAG>;
+    case STFT_MAG: return stft2048_kernel<STFT_MAG>;
+    case STFT_POWER: return stft2048_kernel<STFT_POWER>;
+    case STFT_MAG_CLAMP: return stft2048_kernel<STFT_MAG_CLAMP>;
+    default: return stft2048_kernel<STFT_MAG_POW>;
   }
 }
 
@@ -201,7 +222,7 @@ int launch_stft(const StftParams& p, int B, cudaStream_t stream) {
     switch (p.n_fft) {
       case 512: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel<8>, 64, 0); break;
       case 1024: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel<9>, 128, 0); break;
-      case 2048: e = fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft2048_kernel, 256, 0)
+      case 2048: e = fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft2048_fn(p.mode), 256, 0)
                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel<10>, 256, 0); break;
       case 4096: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_kernel<11>, 512, 0); break;
       default: break;
@@ -214,7 +235,7 @@ int launch_stft(const StftParams& p, int B, cudaStream_t stream) {
     case 512: stft_kernel<8><<<grid, 64, 0, stream>>>(p, groups, n_work); break;
     case 1024: stft_kernel<9><<<grid, 128, 0, stream>>>(p, groups, n_work); break;
     case 2048:
-      if (fast) stft2048_kernel<<<grid, 256, 0, stream>>>(p, groups, n_work);
+      if (fast) stft2048_fn(p.mode)<<<grid, 256, 0, stream>>>(p, groups, n_work);
       else stft_kernel<10><<<grid, 256, 0, stream>>>(p, groups, n_work);
       break;
     case 4096: stft_kernel<11><<<grid, 512, 0, stream>>>(p, groups, n_work); break;
@@ -324,7 +345,18 @@ __global__ void __launch_bounds__(256) istft2048_kernel(IstftParams p, int segs,
   const int tid = threadIdx.x, g = tid >> 6, tl = tid & 63;
   float2* fb = buf + g * FFT1024_BUF;
   const int S = p.hops_per_cta * p.hop;
+  float* env_int = ola + S;  // [hop] window envelope of an interior sample, by q mod hop (all NFFT / hop frames present)
   const float inv = p.scale / (float)NC;
+  const int fph = NFFT / p.hop;  // frames covering an interior sample
+  for (int r = tid; r < p.hop; r += 256) {
+    float e = 0.0f;
+    for (int j = 0; j < fph; ++j) {
+      const float w = p.window[r + j * p.hop];
+      e += w * w;
+    }
+    env_int[r] = e;
+  }
+  const bool pair_ok = ((p.hop | p.frame_off | S) & 1) == 0;  // frame samples (2n, 2n+1) land on an even output index: float2 overlap-add
   for (int work = blockIdx.x; work < n_work; work += gridDim.x) {  // work item = (batch item, output segment)
     const int b = work / segs;
     const int s0 = (work - b * segs) * S;  // first output sample of this segment
@@ -373,8 +405,18 @@ __global__ void __launch_bounds__(256) istft2048_kernel(IstftParams p, int segs,
           const float2 v = res[n];
           const float2 w = *reinterpret_cast<const float2*>(p.window + 2 * n);
           const int q = off + 2 * n;
-          if (q >= 0 && q < S) ola[q] += v.x * inv * w.x;
-          if (q + 1 >= 0 && q + 1 < S) ola[q + 1] += -v.y * inv * w.y;
+          if (pair_ok) {
+            if (q >= 0 && q < S) {
+              float2* o2 = reinterpret_cast<float2*>(ola + q);
+              float2 acc = *o2;
+              acc.x += v.x * inv * w.x;
+              acc.y += -v.y * inv * w.y;
+              *o2 = acc;
+            }
+          } else {
+            if (q >= 0 && q < S) ola[q] += v.x * inv * w.x;
+            if (q + 1 >= 0 && q + 1 < S) ola[q + 1] += -v.y * inv * w.y;
+          }
         }
         __syncthreads();
       }
@@ -386,14 +428,19 @@ __global__ void __launch_bounds__(256) istft2048_kernel(IstftParams p, int segs,
       if (s >= p.length) break;
       const int q = s + p.frame_off + p.env_pad * p.hop;  // shift so that frame indices start at 0
       const int Fe = p.F + 2 * p.env_pad;
-      int ta = (q - NFFT + p.hop) / p.hop;  // ceil((q - NFFT + 1) / hop) for q - NFFT + 1 >= 0
-      if (q - NFFT + 1 <= 0) ta = 0;
-      int tbb = q / p.hop;
-      if (tbb > Fe - 1) tbb = Fe - 1;
-      float env = 0.0f;
-      for (int tt = ta; tt <= tbb; ++tt) {
-        const float w = p.window[q - tt * p.hop];
-        env += w * w;
+      const int tq = q / p.hop;
+      float env;
+      if (tq >= fph - 1 && tq <= Fe - 1) {  // interior: every frame tq - fph + 1 .. tq exists -> tabulated envelope
+        env = env_int[q - tq * p.hop];
+      } else {
+        int ta = (q - NFFT + p.hop) / p.hop;  // ceil((q - NFFT + 1) / hop) for q - NFFT + 1 >= 0
+        if (q - NFFT + 1 <= 0) ta = 0;
+        const int tbb = tq > Fe - 1 ? Fe - 1 : tq;
+        env = 0.0f;
+        for (int tt = ta; tt <= tbb; ++tt) {
+          const float w = p.window[q - tt * p.hop];
+          env += w * w;
+        }
       }
       out[s] = (env > 1e-11f) ? ola[i] / env : 0.0f;
     }
@@ -403,7 +450,8 @@ __global__ void __launch_bounds__(256) istft2048_kernel(IstftParams p, int segs,
 
 static int launch_istft2048(const IstftParams& p, int B, cudaStream_t stream) {
   const int S = p.hops_per_cta * p.hop;
-  const size_t smem = sizeof(float2) * 4 * FFT1024_BUF + sizeof(float) * S;
+  const size_t smem = sizeof(float2) * 4 * FFT1024_BUF + sizeof(float) * (S + p.hop);
+  RFX_REQUIRE(2048 % p.hop == 0, "istft: hop must divide n_fft");
   RFX_CHECK_CUDA(cudaFuncSetAttribute(istft2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int segs = ceil_div(p.length, S);
   const long long n_work_ll = (long long)segs * B;
