@@ -66,11 +66,12 @@ int rfx_gemm(int impl, const float* A, int lda, int M, const float* W, int N, in
 /* Scheduling facts of the recurrence kernel on the current device: how many 8-CTA clusters are co-resident
  * and how many batch items each cluster takes for batch size B (all clusters of a launch run as one wave). */
 int rfx_lstm_info(int B, int* max_active_clusters, int* batch_per_cluster);
-/* Process-wide choice of the recurrence kernel: 0 = tensor-core (mma.sync bf16x3, default), 1 = fp32 FFMA. */
+/* Process-wide choice of the recurrence kernel: 0 = tensor-core (mma.sync bf16x3, default), 1 = fp32 FFMA, 2 = tcgen05 (H = 256). */
 int rfx_lstm_set_impl(int impl);
 int rfx_lstm_layer(const float* G, const float* Whh, float* Hout, int ldh, int B, int F, int H, void* stream);
-/* Same with the batch slots per 8-CTA cluster fixed by the caller: 1..8 = one MMA n-tile, 9..16 = two n-tiles per cluster
- * (H = 256 only; half the SMs per launch, used by the Open-Unmix pipeline); 0 = automatic as above. */
+/* Same with the batch slots per 8-CTA cluster fixed by the caller: 1..8 for the mma.sync / FFMA kernels, 1..16 for the tcgen05
+ * kernel (rfx_lstm_set_impl(2): H = 256, W_hh as the TMEM A operand, 16 slots per cluster = half the SMs per launch, used by
+ * the Open-Unmix pipeline); 0 = automatic as above. */
 int rfx_lstm_layer_slots(const float* G, const float* Whh, float* Hout, int ldh, int B, int F, int H, int slots, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -479,251 +479,6 @@ static int launch_mma(const float* G, int ldg, const float* Whh, float* Hout, in
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Warp-specialised recurrence (H = 256): NG independent GROUPS of 8 batch slots per cluster, running out of phase.
-//
-// In the kernel above a step is four serial phases -- wait for h, HMMA, gate math, DSMEM exchange -- and the tensor pipe
-// (the busiest unit: 750 of ~2300 cycles) idles during the other three.  Here the phases of different groups overlap:
-//   * warps 0-7  (MMA warps, 168 registers after setmaxnreg.inc) keep the W_hh hi/lo fragments in registers and do
-//     nothing but  wait h(g) -> 48 HMMA (six independent accumulation chains) -> pre-activations to shared memory ->
-//     signal, for g = 0, 1, .. round robin;
-//   * warps 8-15 (gate warps, 88 registers) add the input projections, do the gate math, stage the new h of the group
-//     (gate warp 0 pushes it to the 8 CTAs with DSMEM bulk copies once all eight have arrived on an mbarrier -- the
-//     other seven do not wait) and store h to HBM.
-// While the gate warps and the exchange work on group g, the MMA warps are already multiplying group g+1, so a cluster
-// serves 8 NG slots per ~max(850 NG, 2200) cycles on the same 8 SMs.
-// ------------------------------------------------------------------------------------------------------
-#ifndef LSTM_WS_MREG
-#define LSTM_WS_MREG 168  // registers per thread of the MMA warps / gate warps after setmaxnreg (256 * (MREG + GREG) = 64 K)
-#define LSTM_WS_GREG 88
-#endif
-template <int NG>
-__global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(512, 1)
-    lstm_rec_ws_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Whh, float* __restrict__ Hout, int ldh,
-                       __nv_bfloat16* __restrict__ Hhi, __nv_bfloat16* __restrict__ Hlo, int ldhs, int B, int F, int NB) {
-  constexpr int H = 256;
-  constexpr int UPC = H / LSTM_CL;  // 32 units per CTA
-  constexpr int MW = UPC / 4;       // 8 MMA warps (and 8 gate warps)
-  constexpr int KS = H / 16, NP = H / 32;
-  constexpr int BLK_BYTES = 2 * LSTM_SLOTS * UPC * 2;  // one CTA's h block of one group: 2 planes x 8 slots x 32 units bf16
-  constexpr int TX = LSTM_CL * BLK_BYTES;
-  extern __shared__ __align__(128) uint8_t lstm_smem[];
-  uint8_t* h_buf = lstm_smem;                                                       // [NG][2][CL][BLK_BYTES]
-  uint8_t* stage = h_buf + NG * 2 * LSTM_CL * BLK_BYTES;                            // [NG][2][BLK_BYTES]
-  float4* pre = reinterpret_cast<float4*>(stage + NG * 2 * BLK_BYTES);              // [NG][2][MW][32]
-  uint64_t* h_bar = reinterpret_cast<uint64_t*>(pre + NG * 2 * MW * 32);            // [NG][2]
-  uint64_t* pre_full = h_bar + NG * 2;                                              // [NG][MW]
-  uint64_t* stage_full = pre_full + NG * MW;                                        // [NG]
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int dir = blockIdx.z;
-  const int b0 = blockIdx.y * NB;
-  const int gid = lane >> 2, tig = lane & 3;
-  const int u = gid >> 1, pp = gid & 1;  // unit within the warp; pp = 0: rows (i, g), pp = 1: rows (f, o)
-  const int gate0 = pp ? 1 : 0, gate1 = pp ? 3 : 2;
-
-  for (int i = tid; i < NG * 2 * LSTM_CL * BLK_BYTES / 4; i += 512) reinterpret_cast<uint32_t*>(h_buf)[i] = 0u;
-  if (tid == 0) {
-    for (int i = 0; i < NG * 2; ++i) mbar_init(&h_bar[i], 1);
-    for (int i = 0; i < NG * MW; ++i) mbar_init(&pre_full[i], 1);
-    for (int i = 0; i < NG; ++i) mbar_init(&stage_full[i], MW);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  cluster_arrive();  // barriers initialised and h zeroed everywhere before anyone sends
-  cluster_wait();
-
-  if (warp < MW) {
-    // =============================== MMA warps ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(LSTM_WS_MREG));
-    const int unit = rank * UPC + warp * 4 + u;
-    uint32_t a_hi[KS][4], a_lo[KS][4];
-    {
-      const float* w0 = Whh + ((size_t)dir * 4 * H + (size_t)gate0 * H + unit) * H + 8 * tig;
-      const float* w1 = Whh + ((size_t)dir * 4 * H + (size_t)gate1 * H + unit) * H + 8 * tig;
-#pragma unroll
-      for (int P = 0; P < NP; ++P) {
-        const float4 x0 = *reinterpret_cast<const float4*>(w0 + 32 * P), x1 = *reinterpret_cast<const float4*>(w0 + 32 * P + 4);
-        const float4 y0 = *reinterpret_cast<const float4*>(w1 + 32 * P), y1 = *reinterpret_cast<const float4*>(w1 + 32 * P + 4);
-        float rx, ry;
-        a_hi[2 * P][0] = pack_hi2(x0.x, x0.y, rx, ry); a_lo[2 * P][0] = pack2(rx, ry);
-        a_hi[2 * P][1] = pack_hi2(y0.x, y0.y, rx, ry); a_lo[2 * P][1] = pack2(rx, ry);
-        a_hi[2 * P][2] = pack_hi2(x0.z, x0.w, rx, ry); a_lo[2 * P][2] = pack2(rx, ry);
-        a_hi[2 * P][3] = pack_hi2(y0.z, y0.w, rx, ry); a_lo[2 * P][3] = pack2(rx, ry);
-        a_hi[2 * P + 1][0] = pack_hi2(x1.x, x1.y, rx, ry); a_lo[2 * P + 1][0] = pack2(rx, ry);
-        a_hi[2 * P + 1][1] = pack_hi2(y1.x, y1.y, rx, ry); a_lo[2 * P + 1][1] = pack2(rx, ry);
-        a_hi[2 * P + 1][2] = pack_hi2(x1.z, x1.w, rx, ry); a_lo[2 * P + 1][2] = pack2(rx, ry);
-        a_hi[2 * P + 1][3] = pack_hi2(y1.z, y1.w, rx, ry); a_lo[2 * P + 1][3] = pack2(rx, ry);
-      }
-    }
-    // B-fragment byte offsets inside one h buffer: true k0 = 32 P + 8 tig lives in source CTA k0 / UPC at unit k0 % UPC
-    uint32_t boffs[NP];
-#pragma unroll
-    for (int P = 0; P < NP; ++P) {
-      const int k0 = 32 * P + 8 * tig;
-      boffs[P] = (uint32_t)((k0 / UPC) * BLK_BYTES + gid * (UPC * 2) + (k0 % UPC) * 2);
-    }
-    for (int step = 0; step < F; ++step) {
-      const int cur = step & 1;
-#pragma unroll 1
-      for (int g = 0; g < NG; ++g) {
-        if (step > 0) mbar_wait(&h_bar[g * 2 + cur], ((step - 1) >> 1) & 1);  // all of h_{t-1} of group g has landed
-        // six independent accumulation chains (lo*hi, hi*lo, hi*hi for the even and for the odd k-step of each pair):
-        // the legacy HMMA pipe, not the dependency latency, then sets the pace
-        float d[6][4];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) d[c][0] = d[c][1] = d[c][2] = d[c][3] = 0.f;
-        const uint8_t* hb = h_buf + (g * 2 + cur) * (LSTM_CL * BLK_BYTES);
-#pragma unroll
-        for (int P = 0; P < NP; ++P) {
-          const uint4 bh = *reinterpret_cast<const uint4*>(hb + boffs[P]);
-          const uint4 bl = *reinterpret_cast<const uint4*>(hb + boffs[P] + LSTM_SLOTS * UPC * 2);
-          hmma16816(d[0], a_lo[2 * P], bh.x, bh.y);
-          hmma16816(d[1], a_hi[2 * P], bl.x, bl.y);
-          hmma16816(d[2], a_hi[2 * P], bh.x, bh.y);
-          hmma16816(d[3], a_lo[2 * P + 1], bh.z, bh.w);
-          hmma16816(d[4], a_hi[2 * P + 1], bl.z, bl.w);
-          hmma16816(d[5], a_hi[2 * P + 1], bh.z, bh.w);
-        }
-        // d[.][0], [1]: row gate0, slots 2 tig, 2 tig + 1 ; [2], [3]: row gate1.  Small terms first.
-        float4 o;
-        o.x = ((d[0][0] + d[3][0]) + (d[1][0] + d[4][0])) + (d[2][0] + d[5][0]);
-        o.y = ((d[0][1] + d[3][1]) + (d[1][1] + d[4][1])) + (d[2][1] + d[5][1]);
-        o.z = ((d[0][2] + d[3][2]) + (d[1][2] + d[4][2])) + (d[2][2] + d[5][2]);
-        o.w = ((d[0][3] + d[3][3]) + (d[1][3] + d[4][3])) + (d[2][3] + d[5][3]);
-        pre[((g * 2 + cur) * MW + warp) * 32 + lane] = o;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&pre_full[g * MW + warp]);
-      }
-    }
-    // Nobody may exit while peers can still write into its shared memory: wait for the last h of every group to land.
-    for (int g = 0; g < NG; ++g) mbar_wait(&h_bar[g * 2 + (F & 1)], ((F - 1) >> 1) & 1);
-  } else {
-    // =============================== gate warps ===============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LSTM_WS_GREG));
-    const int j = warp - MW;
-    const int unit = rank * UPC + j * 4 + u;
-    const int n0 = 2 * tig;  // this lane's accumulator columns of group g are batch slots 8 g + 2 tig, + 1
-    const uint32_t gc0 = (uint32_t)(dir * 4 * H + gate0 * H + unit);
-    const uint32_t gdelta = (uint32_t)((gate1 - gate0) * H);
-    const uint32_t col = (uint32_t)(dir * H + unit);
-    // Row b F of item b = b0 + 8 g + n0 + k is row0 + (8 g + k) F; all element offsets fit 32 bits (checked on the host).
-    const uint32_t row0 = (uint32_t)(b0 + n0) * (uint32_t)F;
-    uint32_t vmask = 0;  // bit 2 g + k: slot 8 g + n0 + k holds a real item
-#pragma unroll
-    for (int g = 0; g < NG; ++g)
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-        if ((8 * g + n0 + k) < NB && (b0 + 8 * g + n0 + k) < B) vmask |= 1u << (2 * g + k);
-    float c_state[NG][2];
-    float gq[NG][4];  // next step's input projections: (gate0, n0), (gate0, n0+1), (gate1, n0), (gate1, n0+1)
-    auto load_g = [&](int g, int st, float (&dst)[4]) {
-      dst[0] = dst[1] = dst[2] = dst[3] = 0.f;
-      if (st < F) {
-        const uint32_t tq = (uint32_t)(dir ? F - 1 - st : st);
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-          if (vmask >> (2 * g + k) & 1u) {
-            const float* gp = G + (size_t)((row0 + (uint32_t)(8 * g + k) * (uint32_t)F + tq) * (uint32_t)ldg + gc0);
-            dst[k] = __ldg(gp);
-            dst[2 + k] = __ldg(gp + gdelta);
-          }
-      }
-    };
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      c_state[g][0] = c_state[g][1] = 0.f;
-      load_g(g, 0, gq[g]);
-    }
-    const uint32_t dst_h = mapa_u32(smem_u32(h_buf) + rank * BLK_BYTES, lane & 7);
-    const uint32_t dst_bar = mapa_u32(smem_u32(&h_bar[0]), lane & 7);
-    const float sc = pp ? 1.0f : 2.0f;
-    for (int step = 0; step < F; ++step) {
-      const int cur = step & 1, nxt = cur ^ 1;
-      const uint32_t tt = (uint32_t)(dir ? F - 1 - step : step);
-#pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        float gin[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) gin[q] = gq[g][q];
-        load_g(g, step + 1, gq[g]);  // a whole step ahead of its use: the scattered HBM loads stay off the critical path
-        mbar_wait(&pre_full[g * MW + j], step & 1);
-        const float4 p4 = pre[((g * 2 + cur) * MW + j) * 32 + lane];
-        const float pre0 = p4.x + gin[0], pre1 = p4.y + gin[1], pre2 = p4.z + gin[2], pre3 = p4.w + gin[3];
-        // ---- gate math.  pp = 0: (i, g) -> i * tanh(g);  pp = 1: (f, o).  tanh(x) = 2 sigmoid(2x) - 1 keeps it branch-free ----
-        const float sa0 = lean_sigmoid(pre0), sa1 = lean_sigmoid(pre1);  // sigmoid(i) | sigmoid(f)
-        float sb0 = lean_sigmoid(sc * pre2), sb1 = lean_sigmoid(sc * pre3);  // sigmoid(o) | sigmoid(2g)
-        if (!pp) { sb0 = 2.0f * sb0 - 1.0f; sb1 = 2.0f * sb1 - 1.0f; }      // tanh(g)
-        const float ig0 = __shfl_xor_sync(0xffffffffu, sa0 * sb0, 4);       // partner lane (gid ^ 1): i * tanh(g)
-        const float ig1 = __shfl_xor_sync(0xffffffffu, sa1 * sb1, 4);
-        float h0 = 0.f, h1 = 0.f;
-        uint32_t hh = 0u, hl = 0u;
-        __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(stage + (g * 2 + nxt) * BLK_BYTES);
-        if (pp) {
-          c_state[g][0] = sa0 * c_state[g][0] + ig0;
-          c_state[g][1] = sa1 * c_state[g][1] + ig1;
-          h0 = sb0 * (2.0f * lean_sigmoid(2.0f * c_state[g][0]) - 1.0f);
-          h1 = sb1 * (2.0f * lean_sigmoid(2.0f * c_state[g][1]) - 1.0f);
-          float r0, r1;
-          hh = pack_hi2(h0, h1, r0, r1);
-          hl = pack2(r0, r1);
-          __nv_bfloat16* st = stg + n0 * UPC + j * 4 + u;
-          st[0] = reinterpret_cast<const __nv_bfloat16*>(&hh)[0];
-          st[UPC] = reinterpret_cast<const __nv_bfloat16*>(&hh)[1];
-          st[LSTM_SLOTS * UPC] = reinterpret_cast<const __nv_bfloat16*>(&hl)[0];
-          st[LSTM_SLOTS * UPC + UPC] = reinterpret_cast<const __nv_bfloat16*>(&hl)[1];
-        }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy (async proxy) reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&stage_full[g]);
-        if (j == 0) {  // only the sending warp waits for the other seven
-          mbar_wait(&stage_full[g], step & 1);
-          if (lane < LSTM_CL) {
-            if (lane == 0) mbar_arrive_expect_tx(&h_bar[g * 2 + nxt], TX);  // phase that receives h_t of this group
-            bulk_s2cluster(dst_h + (uint32_t)((g * 2 + nxt) * LSTM_CL * BLK_BYTES), smem_u32(stg), BLK_BYTES,
-                           dst_bar + (uint32_t)((g * 2 + nxt) * sizeof(uint64_t)));
-          }
-        }
-        // layer output to HBM: off the critical path (overlaps the DSMEM exchange)
-        if (pp) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            if (vmask >> (2 * g + k) & 1u) {
-              const uint32_t row = row0 + (uint32_t)(8 * g + k) * (uint32_t)F + tt;
-              if (Hout) Hout[(size_t)(row * (uint32_t)ldh + col)] = k ? h1 : h0;
-              if (Hhi) {
-                const size_t o = (size_t)(row * (uint32_t)ldhs + col);
-                Hhi[o] = reinterpret_cast<const __nv_bfloat16*>(&hh)[k];
-                Hlo[o] = reinterpret_cast<const __nv_bfloat16*>(&hl)[k];
-              }
-            }
-        }
-      }
-    }
-  }
-  __syncthreads();
-  cluster_arrive();
-  cluster_wait();
-}
-
-template <int NG>
-static int launch_ws(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs, int B,
-                     int F, int slots, cudaStream_t stream) {
-  constexpr int BLK = 2 * LSTM_SLOTS * (256 / LSTM_CL) * 2;
-  const size_t smem = (size_t)NG * 2 * LSTM_CL * BLK + (size_t)NG * 2 * BLK + (size_t)NG * 2 * 8 * 32 * 16 + (size_t)(NG * 2 + NG * 8 + NG) * 8 + 128;
-  // the gate warps index G and the outputs with 32-bit element offsets
-  RFX_REQUIRE((long long)B * F * (long long)ldg < (1ll << 32) && (long long)B * F * (long long)std::max(ldh, ldhs) < (1ll << 32),
-              "lstm: tensors too large for 32-bit element offsets");
-  RFX_CHECK_CUDA(cudaFuncSetAttribute(lstm_rec_ws_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int nb = slots < LSTM_SLOTS * NG ? slots : LSTM_SLOTS * NG;
-  dim3 grid(LSTM_CL, ceil_div(B, nb), 2);
-  lstm_rec_ws_kernel<NG><<<grid, 512, smem, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb);
-  RFX_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------------------
 // tcgen05 recurrence (H = 256): the per-step product W_hh h_{t-1} on the 5th-generation tensor cores.
 //
 //   D[128 gate rows x 16 slots] (TMEM, fp32)  =  A[128 x 256] (TMEM)  x  B[256 x 16] (shared memory),  bf16x3
@@ -1044,7 +799,7 @@ void lstm_set_impl(int impl) { g_lstm_impl = impl; }
 int lstm_get_impl() { return g_lstm_impl; }
 
 int lstm_clusters_for(int B, int slots) {
-  const int s = slots <= 0 ? LSTM_SLOTS : (slots < 4 * LSTM_SLOTS ? slots : 4 * LSTM_SLOTS);
+  const int s = slots <= 0 ? LSTM_SLOTS : (slots < TC_N ? slots : TC_N);
   return 2 * ceil_div(B, s);
 }
 
@@ -1067,12 +822,7 @@ int launch_lstm_layer_impl(const float* G, int ldg, const float* Whh, float* Hou
   RFX_REQUIRE(Hout || (Hhi && Hlo), "lstm: no output given");
   if (g_lstm_impl == 2 && H == LSTM_H) return launch_tc(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
   if (g_lstm_impl == 0 || H != LSTM_H) {
-    // more than 8 slots per cluster asked for: the warp-specialised multi-group kernel (H = 256 only)
-    if (H == 256 && slots > LSTM_SLOTS) {
-      if (slots <= 2 * LSTM_SLOTS) return launch_ws<2>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
-      if (slots <= 3 * LSTM_SLOTS) return launch_ws<3>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
-      return launch_ws<4>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
-    }
+    RFX_REQUIRE(slots <= LSTM_SLOTS, "lstm: more than 8 slots per cluster needs the tcgen05 kernel (impl 2)");
     if (H == 256) return launch_mma<256, false>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
     if (H == 192) return launch_mma<192, false>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
     return launch_mma<384, true>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);

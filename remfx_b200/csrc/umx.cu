@@ -374,6 +374,8 @@ namespace {
 struct HostIO {
   const float* x_host; float* out_host;  // either may be null (that side is device-resident)
   int slot;
+  int chunks;  // item chunks the copies (and the STFT / iSTFT launches) are split into: 4 hides PCIe time inside ONE blocking call;
+               // the multi-lane pipeline overlaps whole steps instead and uses 1 (no launch-quantisation loss on its 84 SMs)
 };
 
 // One call = nb_layers STAGES.  Stage l: [l == 0: STFT, fc1] -> W_ih GEMM of layer l -> recurrence of layer l ->
@@ -415,7 +417,7 @@ int umx_stage(rfx_umx_t* h, const UmxCall& c, int l) {
     ++h->mark_idx;
     return 0;
   };
-  const int nch = io ? std::min(B, (int)rfx_umx::kChunks) : 1;
+  const int nch = io ? std::max(1, std::min(B, std::min(io->chunks, (int)rfx_umx::kChunks))) : 1;
 
   if (l == 0) {
     // (1) STFT (transforms.py:106-116) + ComplexNorm (:211) + input shift/scale (model.py:127-128) -> split planes
@@ -659,7 +661,7 @@ int umx_pipe_superstep(rfx_umx_t* h) {
     for (int i = 0; i < p.depth; ++i) {
       rfx_umx::Lane& ln = p.lane[i];
       if (!ln.live || ln.next_stage != st) continue;
-      HostIO io{ln.x_host, ln.out_host, i};
+      HostIO io{ln.x_host, ln.out_host, i, 1};
       UmxCall c{};
       c.B = p.B; c.T = p.T;
       c.ws = reinterpret_cast<uint8_t*>(p.ws) + (size_t)i * L.total;
@@ -843,7 +845,7 @@ int rfx_umx_submit_host(rfx_umx_t* h, int slot, const float* x_host, int B, int 
   int rc;
   if ((rc = umx_host_setup(h)) || (rc = rfx_umx_wait_host(h, slot))) return rc;  // the slot's staging buffers must be free
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  HostIO io{x_host, out_host, slot};
+  HostIO io{x_host, out_host, slot, rfx_umx::kChunks};
   rc = umx_forward(h, reinterpret_cast<float*>(ws + L.off_x[slot]), B, T, reinterpret_cast<float*>(ws + L.off_out[slot]), workspace,
                    workspace_bytes, stream, &io);
   if (rc) return rc;

@@ -135,8 +135,8 @@ def linear(A: torch.Tensor, W: torch.Tensor, s1=None, t1=None, s2=None, t2=None,
 
 def lstm_layer(G: torch.Tensor, Whh: torch.Tensor, B: int, F: int, impl: str = "mma", slots: int = 0) -> torch.Tensor:
     """Recurrent half of one bidirectional LSTM layer.  G: (B*F, 8H) input projections (+biases),
-    Whh: (2, 4H, H) -> (B*F, 2H).  impl: "mma" (tensor-core bf16x3, default) or "ffma" (fp32).
-    slots: batch slots per cluster (0 = automatic, 9..16 = the two-n-tile kernel, H = 256)."""
+    Whh: (2, 4H, H) -> (B*F, 2H).  impl: "mma" (mma.sync bf16x3, default), "ffma" (fp32) or "tc" (tcgen05, H = 256).
+    slots: batch slots per cluster (0 = automatic; at most 8, or 16 for "tc")."""
     _lib.check(_lib.lib().rfx_lstm_set_impl({"mma": 0, "ffma": 1, "tc": 2}[impl]), "rfx_lstm_set_impl")
     try:
         return _lstm_layer(G, Whh, B, F, slots)
