@@ -146,3 +146,46 @@ def test_pipeline_wait_before_exit_raises():
         pipe.wait(s)  # still inside the pipeline: needs depth-1 more pushes or a flush
     pipe.flush()
     pipe.wait(s)
+
+
+@pytest.mark.parametrize("B,T", [(1, 8192), (19, 16384), (33, 8192)])
+def test_pipeline_ragged_batches_and_mixed_buffers(B, T):
+    """Batch sizes that do not fill the 16-slot recurrence clusters; host input with device output and the reverse."""
+    sd = weights.umx_state(11)
+    m = _model(sd)
+    pipe = m.pipeline("cuda:0")
+    xs = [weights.synth_audio(500 + i, B, T) for i in range(4)]
+    refs = [oumx.sample(x, sd) for x in xs[:2]]
+    outs, seqs = [], []
+    for i, x in enumerate(xs):
+        if i % 2 == 0:   # pinned host input -> device output
+            xin, out = x.pin_memory(), torch.empty(B, 1, T, device="cuda")
+        else:            # device input -> pinned host output
+            xin, out = x.cuda(), torch.empty(B, 1, T).pin_memory()
+        outs.append(out)
+        seqs.append(pipe.push(xin, out))
+    pipe.flush()
+    for s in seqs:
+        pipe.wait(s)
+    torch.cuda.synchronize()
+    info = pipe.info()
+    assert info["recurrence_streams"] >= 1 and info["partition"] in ("green contexts", "grid caps", "none")
+    for i in range(2):
+        assert relrms(outs[i].cpu(), refs[i]) < TOL
+    for i, x in enumerate(xs):
+        assert relrms(outs[i].cpu(), m.sample(x.cuda()).cpu()) < 5e-6
+
+
+def test_pipeline_flush_without_work_and_reuse():
+    sd = weights.umx_state(5)
+    m = _model(sd)
+    pipe = m.pipeline("cuda:0")
+    pipe.flush()  # nothing pushed yet: a no-op
+    x = weights.synth_audio(3, 2, 16384).cuda()
+    s = pipe.push(x)
+    pipe.flush()
+    a = pipe.wait(s).clone()
+    pipe.flush()  # idempotent
+    s2 = pipe.push(x)
+    pipe.flush()
+    assert torch.equal(pipe.wait(s2), a)  # same input, same schedule -> bit-identical (deterministic kernels)
