@@ -1,4 +1,5 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_umx.py -m gpu -q --timeout 200 --no-header -p no:cacheprovider > gpurun_out/t.log 2>&1; echo "umx tests exit=$? $(tail -n 1 gpurun_out/t.log)"; grep -E "^FAILED|^ERROR|rror" gpurun_out/t.log | head
-RFX_UMX_PIPE_GREEN=0 timeout 600 python -m pytest tests/test_gpu_umx.py -m gpu -q --timeout 200 --no-header -p no:cacheprovider -k pipeline > gpurun_out/t2.log 2>&1; echo "umx pipeline tests (grid caps) exit=$? $(tail -n 1 gpurun_out/t2.log)"
+for h in 8 16 24 32; do
+RFX_ISTFT_HPC=$h timeout 120 python tools/umx_quick_bench.py 32 2>&1 | tail -1 | sed "s/^/hpc=$h /"
+RFX_ISTFT_HPC=$h timeout 120 python tools/pipe_bench.py 32 40 2>&1 | tail -1 | cut -c1-40 | sed "s/^/hpc=$h /"
+done
