@@ -290,6 +290,19 @@ int rfx_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
                    float eps, float weight_decay, int step, float grad_scale, float max_norm, const void* workspace, float* total_norm,
                    void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * N2  Batch ingest (the step in front of the hot path)
+ *   replaces remfx/datasets.py:461-468 (EffectDataset.__getitem__: two torchaudio.load per item) + the DataLoader collate
+ * Host-side, no GPU work: decodes n mono RIFF/WAVE files (IEEE float 32/64, integer PCM 8/16/24/32, plain or
+ * WAVE_FORMAT_EXTENSIBLE headers, unknown chunks skipped; integer samples scaled like torchaudio.load(normalize=True)) with a
+ * pool of n_threads threads straight into row i of dst_host[n][T] -- meant to be one pinned (B, 1, T) buffer that
+ * rfx_umx_pipe_push / rfx_umx_sample_host consume.  Files shorter than T are zero-padded, longer ones cut; frames[i] /
+ * sample_rates[i] (optional) report what each file holds.  Returns 2 and sets rfx_last_error() on the first unreadable file.
+ * ------------------------------------------------------------------------------------------- */
+int rfx_wav_info(const char* path, int* sample_rate, int* channels, long long* frames, int* format_tag, int* bits);
+int rfx_ingest_wav_batch(const char* const* paths, int n, float* dst_host, long long T, int n_threads, long long* frames,
+                         int* sample_rates);
+
 #ifdef __cplusplus
 }
 #endif
