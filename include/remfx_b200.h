@@ -266,6 +266,14 @@ size_t rfx_loss_workspace_bytes(int B, int T);
 int rfx_remfx_loss(const float* out, long long out_bstride, const float* target, long long target_bstride, int B, int T,
                    const float* win1024, const float* win2048, const float* win512, float l1_weight, float* result,
                    void* workspace, size_t workspace_bytes, void* stream);
+/* Gradient of that loss with respect to `out` (the first link of the training step, remfx/models.py:299 under autograd):
+ * grad_out (B rows, stride grad_bstride) = *grad_loss * dL/d out.  `workspace` must be the one rfx_remfx_loss just ran in on the
+ * same (out, target): it holds the per-item spectral norms.  Overlapping frames accumulate with fp32 atomic adds (the last bits
+ * of the gradient vary from run to run). */
+int rfx_remfx_loss_backward(const float* out, long long out_bstride, const float* target, long long target_bstride, int B, int T,
+                            const float* win1024, const float* win2048, const float* win512, float l1_weight,
+                            const float* grad_loss, float* grad_out, long long grad_bstride, const void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* L3  SI-SDR metric: auraloss.time.SISDRLoss() as constructed at remfx/models.py:41,173 (zero_mean, eps 1e-8, mean
  * over the batch; returns the NEGATIVE SI-SDR in dB -- the reference negates it again when logging, models.py:230-233).

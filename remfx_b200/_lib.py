@@ -102,6 +102,8 @@ _SIGNATURES = {
     "rfx_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "rfx_remfx_loss": (C.c_int, [_f32p, C.c_longlong, _f32p, C.c_longlong, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_float, _f32p,
                                  C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rfx_remfx_loss_backward": (C.c_int, [_f32p, C.c_longlong, _f32p, C.c_longlong, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_float, _f32p,
+                                          _f32p, C.c_longlong, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rfx_sisdr_workspace_bytes": (C.c_size_t, [C.c_int]),
     "rfx_sisdr_loss": (C.c_int, [_f32p, C.c_longlong, _f32p, C.c_longlong, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rfx_wav_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_int),

@@ -180,6 +180,123 @@ __global__ void loss_final_kernel(LossFinalParams p) {
   p.result[0] = (float)(mr + p.l1_weight * l1);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Backward of the loss with respect to the prediction (the first link of the training step):
+//   d/dX [ (1/3) sum_r ( mean_b ||Y-X||_F / ||Y||_F + mean |log X - log Y| ) ]  with X = sqrt(clamp(|STFT(out)|^2, 1e-8)),
+// chained through the magnitude (zero where the clamp is active), the real FFT (adjoint = un-normalised inverse real FFT with the
+// DC / Nyquist bins counted once), the window and the reflect-padded framing (overlapping frames and mirrored edge samples
+// accumulate with atomic adds).  Per frame the CTA recomputes both spectra exactly as the forward kernel does -- nothing is
+// stored between the passes except the per-item norms the forward already leaves in its workspace.
+// ---------------------------------------------------------------------------------------------------------
+struct LossBwdParams {
+  const float* x;  // prediction
+  const float* y;  // target
+  long long x_bstride, y_bstride, g_bstride;
+  int T, x_al8, y_al8;
+  const float* window;
+  const float2* tw;
+  int hop, F, B;
+  const double* sums;      // [B][3] of this resolution: sum (Y-X)^2, sum Y^2, (unused)
+  const float* grad_loss;  // upstream scalar (device)
+  float* grad;             // (B, T): accumulated into
+};
+
+template <int LOG2NC>
+__global__ void __launch_bounds__((1 << LOG2NC) / 4) stft_loss_bwd_kernel(LossBwdParams p) {
+  constexpr int NC = 1 << LOG2NC;
+  constexpr int T4 = NC / 4;
+  constexpr int NFFT = 2 * NC;
+  __shared__ float2 sa[NC];
+  __shared__ float2 sb[NC];
+  __shared__ float2 hbuf[NC + 1];
+  __shared__ float magy[NC + 1];
+  const int j = threadIdx.x;
+  const int b = blockIdx.y;
+  const float gl = p.grad_loss[0];
+  const double s0 = p.sums[(size_t)b * 3], s1 = p.sums[(size_t)b * 3 + 1];
+  const float c_sc = (s0 > 0.0 && s1 > 0.0) ? (float)((double)gl / (3.0 * p.B) / (sqrt(s0) * sqrt(s1))) : 0.0f;
+  const float c_lm = (float)((double)gl / (3.0 * (double)p.B * (double)(NC + 1) * (double)p.F));
+  float* __restrict__ grow = p.grad + (size_t)b * p.g_bstride;
+  const int f_end = min(p.F, (int)(blockIdx.x + 1) * LOSS_FPC);
+  for (int f = blockIdx.x * LOSS_FPC; f < f_end; ++f) {
+    const int base = f * p.hop - NC;
+    const bool interior = (base >= 0) && (base + NFFT <= p.T);
+#pragma unroll
+    for (int sig = 1; sig >= 0; --sig) {  // target first (its magnitudes are needed while the prediction's spectrum is walked)
+      const float* __restrict__ s = sig ? p.y + (size_t)b * p.y_bstride : p.x + (size_t)b * p.x_bstride;
+      const bool al8 = sig ? p.y_al8 : p.x_al8;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int n = j + r * T4;
+        const float2 w = *reinterpret_cast<const float2*>(p.window + 2 * n);
+        float2 v;
+        if (interior && al8) {
+          v = *reinterpret_cast<const float2*>(s + base + 2 * n);
+        } else {
+          v.x = s[reflect_idx(base + 2 * n, p.T)];
+          v.y = s[reflect_idx(base + 2 * n + 1, p.T)];
+        }
+        sa[n] = make_float2(v.x * w.x, v.y * w.y);
+      }
+      const float2* Zp = fft_block<LOG2NC>(sa, sb, p.tw, j);
+      for (int k = j; k <= NC; k += T4) {
+        const float2 X = rfft_post(Zp, p.tw, NC, k);
+        const float pw = X.x * X.x + X.y * X.y;
+        const float mag = sqrtf(fmaxf(pw, 1e-8f));
+        if (sig == 1) {
+          magy[k] = mag;  // read back by the same thread in the prediction pass
+        } else {
+          const float ym = magy[k];
+          const float d = mag - ym;
+          const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+          const float gm = c_sc * d + c_lm * sgn / mag;           // dL / d mag
+          const float q = pw > 1e-8f ? gm / mag : 0.f;            // clamp active -> constant magnitude -> no gradient
+          float2 H = make_float2(q * X.x, q * X.y);
+          if (k == 0 || k == NC) H = make_float2(2.f * H.x, 0.f);  // bins without a mirror image count once
+          hbuf[k] = H;
+        }
+      }
+      __syncthreads();  // sa/sb reused; hbuf complete after the prediction pass
+    }
+    // adjoint of the real FFT: packed inverse transform of H (same pre-twiddle as the iSTFT)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int k = j + r * T4;  // k in [0, NC/2)
+      const float2 xk = hbuf[k], xn = hbuf[NC - k];
+      if (k == 0) {
+        sa[0] = irfft_pre(xk, xn, p.tw[0]);
+      } else {
+        sa[k] = irfft_pre(xk, xn, p.tw[k]);
+        sa[NC - k] = irfft_pre(xn, xk, p.tw[NC - k]);
+      }
+    }
+    if (j == 0) sa[NC / 2] = irfft_pre(hbuf[NC / 2], hbuf[NC / 2], p.tw[NC / 2]);
+    const float2* res = fft_block<LOG2NC>(sa, sb, p.tw, j);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int n = j + r * T4;
+      const float2 v = res[n];
+      const float2 w = *reinterpret_cast<const float2*>(p.window + 2 * n);
+      const float g0 = v.x * w.x, g1 = -v.y * w.y;
+      if (g0 != 0.f) atomicAdd(grow + reflect_idx(base + 2 * n, p.T), g0);
+      if (g1 != 0.f) atomicAdd(grow + reflect_idx(base + 2 * n + 1, p.T), g1);
+    }
+    __syncthreads();  // sa/sb/hbuf reused by the next frame
+  }
+}
+
+// grad = grad_loss * l1_weight / (B T) * sign(out - target): WRITES the gradient buffer (the spectral kernels then accumulate)
+__global__ void __launch_bounds__(256) l1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, long long xbs, long long ybs,
+                                                     long long gbs, int B, int T, float l1_weight, const float* __restrict__ grad_loss,
+                                                     float* __restrict__ grad) {
+  const int b = blockIdx.y;
+  const float c = grad_loss[0] * l1_weight / ((float)B * (float)T);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) {
+    const float d = x[(size_t)b * xbs + i] - y[(size_t)b * ybs + i];
+    grad[(size_t)b * gbs + i] = d > 0.f ? c : (d < 0.f ? -c : 0.f);
+  }
+}
+
 static const int kRes[3][2] = {{1024, 120}, {2048, 240}, {512, 50}};  // (n_fft, hop); win lengths 600/1200/240 come via the windows
 constexpr int L1_BLOCKS = 32;
 
@@ -248,6 +365,46 @@ int rfx_remfx_loss(const float* out, long long out_bstride, const float* target,
   RFX_CHECK_CUDA(cudaGetLastError());
   loss_final_kernel<<<1, 32, 0, s>>>(fp);
   RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int rfx_remfx_loss_backward(const float* out, long long out_bstride, const float* target, long long target_bstride, int B, int T,
+                            const float* win1024, const float* win2048, const float* win512, float l1_weight, const float* grad_loss,
+                            float* grad_out, long long grad_bstride, const void* workspace, size_t workspace_bytes, void* stream) {
+  RFX_REQUIRE(out && target && win1024 && win2048 && win512 && grad_loss && grad_out && workspace, "null argument");
+  RFX_REQUIRE(B > 0 && T > 1024, "need B > 0 and T > 1024 (reflect padding of the 2048-point STFT)");
+  RFX_REQUIRE(workspace_bytes >= rfx_loss_workspace_bytes(B, T), "workspace too small: pass the workspace rfx_remfx_loss ran in");
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint8_t* ws = reinterpret_cast<const uint8_t*>(workspace);
+  size_t off = 0;
+  for (int r = 0; r < 3; ++r) off += align_up(loss_part_floats(B, T, r) * 4, 256);
+  off += align_up((size_t)B * L1_BLOCKS * 4, 256);
+  const double* sums = reinterpret_cast<const double*>(ws + off);  // [4][B][3], left there by the forward's reduction
+  l1_bwd_kernel<<<dim3(64, B), 256, 0, s>>>(out, target, out_bstride, target_bstride, grad_bstride, B, T, l1_weight, grad_loss, grad_out);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  const float* wins[3] = {win1024, win2048, win512};
+  for (int r = 0; r < 3; ++r) {
+    const int n_fft = kRes[r][0], hop = kRes[r][1];
+    LossBwdParams p{};
+    p.x = out; p.y = target; p.x_bstride = out_bstride; p.y_bstride = target_bstride; p.g_bstride = grad_bstride;
+    p.T = T; p.B = B;
+    p.x_al8 = (((uintptr_t)out & 7) == 0 && out_bstride % 2 == 0) ? 1 : 0;
+    p.y_al8 = (((uintptr_t)target & 7) == 0 && target_bstride % 2 == 0) ? 1 : 0;
+    RFX_REQUIRE(((uintptr_t)wins[r] & 7) == 0, "windows must be 8-byte aligned");
+    p.window = wins[r];
+    p.tw = twiddles(n_fft);
+    RFX_REQUIRE(p.tw != nullptr, "twiddle table allocation failed");
+    p.hop = hop;
+    p.F = T / hop + 1;
+    p.sums = sums + (size_t)r * B * 3;
+    p.grad_loss = grad_loss;
+    p.grad = grad_out;
+    dim3 grid(ceil_div(p.F, LOSS_FPC), B);
+    if (n_fft == 1024) stft_loss_bwd_kernel<9><<<grid, 128, 0, s>>>(p);
+    else if (n_fft == 2048) stft_loss_bwd_kernel<10><<<grid, 256, 0, s>>>(p);
+    else stft_loss_bwd_kernel<8><<<grid, 64, 0, s>>>(p);
+    RFX_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 

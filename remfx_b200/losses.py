@@ -1,7 +1,8 @@
 """RemFx loss on the GPU: MRSTFT(out, target) + 100 * L1(out, target) (remfx/models.py:299,320,385).
 
-Forward value only (inference / evaluation configs); the fused kernels never materialise a
-spectrogram in HBM.  See csrc/loss.cu and oracle/loss.py (auraloss restatement, parity unpinned).
+The fused kernels never materialise a spectrogram in HBM.  `remfx_loss` is differentiable with respect to `out`
+(`rfx_remfx_loss_backward`: the first link of the training step); the networks' own backward kernels are not built yet.
+See csrc/loss.cu and oracle/loss.py (auraloss restatement, parity unpinned).
 """
 from __future__ import annotations
 
@@ -51,8 +52,59 @@ def remfx_loss_terms(out: Tensor, target: Tensor, l1_weight: float = 100.0) -> T
     return res
 
 
+def _rows2(t: Tensor):
+    T = t.shape[-1]
+    t2 = t.reshape(-1, T)
+    if t2.stride(-1) != 1:
+        t2 = t2.contiguous()
+    return t2, (t2.stride(0) if t2.shape[0] > 1 else T)
+
+
+class _RemfxLossFn(torch.autograd.Function):
+    """loss = MRSTFT(out, target) + l1_weight * L1(out, target) with d loss / d out from rfx_remfx_loss_backward."""
+
+    @staticmethod
+    def forward(ctx, out: Tensor, target: Tensor, l1_weight: float):
+        o2, obs = _rows2(out.detach())
+        t2, tbs = _rows2(target.detach())
+        B, T = o2.shape
+        L = _lib.lib()
+        with torch.cuda.device(out.device):
+            ws = torch.empty(L.rfx_loss_workspace_bytes(B, T), dtype=torch.uint8, device=out.device)
+            res = torch.empty(9, dtype=torch.float32, device=out.device)
+            w = _windows(out.device)
+            rc = L.rfx_remfx_loss(o2.data_ptr(), obs, t2.data_ptr(), tbs, B, T, w[0].data_ptr(), w[1].data_ptr(), w[2].data_ptr(),
+                                  float(l1_weight), res.data_ptr(), ws.data_ptr(), ws.numel(), _lib.cur_stream())
+            _lib.check(rc, "rfx_remfx_loss")
+        ctx.save_for_backward(o2, t2, ws)
+        ctx.meta = (obs, tbs, B, T, float(l1_weight), out.shape)
+        return res[0]
+
+    @staticmethod
+    def backward(ctx, grad_loss: Tensor):
+        o2, t2, ws = ctx.saved_tensors
+        obs, tbs, B, T, l1w, shape = ctx.meta
+        L = _lib.lib()
+        with torch.cuda.device(o2.device):
+            g = torch.empty(B, T, dtype=torch.float32, device=o2.device)
+            gl = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+            w = _windows(o2.device)
+            rc = L.rfx_remfx_loss_backward(o2.data_ptr(), obs, t2.data_ptr(), tbs, B, T, w[0].data_ptr(), w[1].data_ptr(), w[2].data_ptr(),
+                                           l1w, gl.data_ptr(), g.data_ptr(), T, ws.data_ptr(), ws.numel(), _lib.cur_stream())
+            _lib.check(rc, "rfx_remfx_loss_backward")
+        return g.reshape(shape), None, None
+
+
 def remfx_loss(out: Tensor, target: Tensor) -> Tensor:
-    """0-d loss tensor, as the reference wrappers return."""
+    """0-d loss tensor, as the reference wrappers return; differentiable with respect to `out`."""
+    if out.requires_grad and torch.is_grad_enabled():
+        _lib.require_device(out)
+        _lib.require_device(target)
+        if out.shape != target.shape:
+            raise ValueError(f"shape mismatch {tuple(out.shape)} vs {tuple(target.shape)}")
+        if out.dtype != torch.float32 or target.dtype != torch.float32:
+            raise ValueError("expected float32")
+        return _RemfxLossFn.apply(out, target, 100.0)
     return remfx_loss_terms(out, target)[0]
 
 
