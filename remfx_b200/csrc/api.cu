@@ -116,7 +116,7 @@ int rfx_lstm_layer(const float* G, const float* Whh, float* Hout, int ldh, int B
 
 int rfx_lstm_layer_slots(const float* G, const float* Whh, float* Hout, int ldh, int B, int F, int H, int slots, void* stream) {
   RFX_REQUIRE(G && Whh && Hout, "null argument");
-  RFX_REQUIRE(slots >= 0 && slots <= 16, "slots per cluster must be 0 (automatic) or 1..16");
+  RFX_REQUIRE(slots >= 0 && slots <= 32, "slots per cluster must be 0 (automatic) or 1..32");
   return launch_lstm_layer_slots(G, 8 * H, Whh, Hout, ldh, nullptr, nullptr, 0, B, F, H, slots, (cudaStream_t)stream);
 }
 

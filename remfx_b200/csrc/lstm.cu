@@ -497,9 +497,8 @@ static int launch_mma(const float* G, int ldg, const float* Whh, float* Hout, in
 //   HBM, split planes to the staging block) and the block is pushed to the 8 CTAs.
 // A cluster serves 16 slots, so B = 32 needs 4 clusters = 32 SMs per launch.
 // ------------------------------------------------------------------------------------------------------
-constexpr int TC_N = 16;             // batch slots per cluster = MMA N
-constexpr int TC_BLKP = TC_N * 64;   // bytes of one plane of one CTA's h block: N slots x 32 units bf16
-constexpr int TC_BLK = 2 * TC_BLKP;  // hi + lo
+constexpr int TC_N = 16;             // batch slots per cluster = MMA N (default); a 32-slot instantiation serves B = 32 per direction
+constexpr int TC_N_MAX = 32;         //   with ONE cluster (8 SMs): slower per launch, half the SMs again
 constexpr int TC_ISSUERS = 4;        // MMA-issue warps: each issues the k-steps of a quarter of K into its own accumulator
 constexpr int TC_THREADS = 256 + 32 * TC_ISSUERS;  // 8 epilogue warps + the issue warps
 
@@ -507,6 +506,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem desc]
@@ -546,17 +553,22 @@ __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t
   return d;
 }
 
+template <int N>  // batch slots per cluster = MMA N (16 or 32)
 __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
     lstm_rec_tc_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Whh, float* __restrict__ Hout, int ldh,
                        __nv_bfloat16* __restrict__ Hhi, __nv_bfloat16* __restrict__ Hlo, int ldhs, int B, int F, int NB) {
   constexpr int H = 256;
   constexpr int UPC = H / LSTM_CL;  // 32 units per CTA -> 128 gate rows = MMA M
+  constexpr int TC_BLKP = N * 64;   // bytes of one plane of one CTA's h block: N slots x 32 units bf16
+  constexpr int TC_BLK = 2 * TC_BLKP;  // hi + lo
+  constexpr int HS = N / 2;         // slots per epilogue thread in the activation phase
+  constexpr int SPT = N / 16;       // slots per epilogue thread in the cell phase
   constexpr int TX = LSTM_CL * TC_BLK;
   extern __shared__ __align__(128) uint8_t lstm_smem[];
   uint8_t* h_buf = lstm_smem;                                                // [2][CL][TC_BLK]
   uint8_t* stage = h_buf + 2 * LSTM_CL * TC_BLK;                             // [2][TC_BLK]
-  float* act = reinterpret_cast<float*>(stage + 2 * TC_BLK);                 // [4 gates][TC_N slots][32 units]
-  uint64_t* h_bar = reinterpret_cast<uint64_t*>(act + 4 * TC_N * UPC);       // [2]
+  float* act = reinterpret_cast<float*>(stage + 2 * TC_BLK);                 // [4 gates][N slots][32 units]
+  uint64_t* h_bar = reinterpret_cast<uint64_t*>(act + 4 * N * UPC);          // [2]
   uint64_t* mma_bar = h_bar + 2;                                             // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
 
@@ -582,7 +594,7 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d = tmem_base + 256;  // columns [0,128) A hi, [128,256) A lo, [256, 256 + N) accumulator
+  const uint32_t tmem_d = tmem_base + 256;  // columns [0,128) A hi, [128,256) A lo, [256, 256 + 4 N) the four accumulators
 
   // ---- W_hh -> tensor memory (once).  Warps 0-3: thread = row (gate = warp, unit = lane). ----
   if (warp < 4) {
@@ -617,10 +629,10 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
     const uint32_t tb_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t hb_u = __shfl_sync(0xffffffffu, smem_u32(h_buf), 0);
     const uint32_t mb_u = __shfl_sync(0xffffffffu, smem_u32(mma_bar), 0);
-    constexpr uint32_t idesc = umma_idesc_bf16(128, TC_N);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N);
     constexpr uint32_t lbo = 128u, sbo = 512u;
     constexpr uint32_t desc_hi = (sbo >> 4) | (1u << 14);  // SBO, descriptor version 1, no swizzle
-    const uint32_t d_acc = tb_u + 256u + (uint32_t)(w * TC_N);
+    const uint32_t d_acc = tb_u + 256u + (uint32_t)(w * N);
     for (int step = 0; step < F; ++step) {
       const int cur = step & 1;
       if (step > 0) mbar_wait(&h_bar[cur], ((step - 1) >> 1) & 1);  // all of h_{t-1} has landed
@@ -646,18 +658,18 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
   } else {
     // =============================== epilogue warps ===============================
     const int q = warp & 3;    // TMEM lane quarter = gate
-    const int ch = warp >> 2;  // column half: slots 8 ch .. 8 ch + 7
-    const uint32_t t_ld = tmem_d + ((uint32_t)(32 * q) << 16) + 8u * ch;
+    const int ch = warp >> 2;  // column half: slots HS ch .. HS ch + HS - 1
+    const uint32_t t_ld = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(HS * ch);
     const uint32_t gcol = (uint32_t)(dir * 4 * H + q * H + rank * UPC + lane);
-    uint32_t vmask = 0;  // bit s: slot 8 ch + s holds a real item
+    uint32_t vmask = 0;  // bit s: slot HS ch + s holds a real item
 #pragma unroll
-    for (int s2 = 0; s2 < 8; ++s2)
-      if ((8 * ch + s2) < NB && (b0 + 8 * ch + s2) < B) vmask |= 1u << s2;
-    const uint32_t row0 = (uint32_t)(b0 + 8 * ch) * (uint32_t)F;  // G row of slot 8 ch at t = 0
-    float gq[8];
+    for (int s2 = 0; s2 < HS; ++s2)
+      if ((HS * ch + s2) < NB && (b0 + HS * ch + s2) < B) vmask |= 1u << s2;
+    const uint32_t row0 = (uint32_t)(b0 + HS * ch) * (uint32_t)F;  // G row of slot HS ch at t = 0
+    float gq[HS];
     auto load_g = [&](int st) {
 #pragma unroll
-      for (int s2 = 0; s2 < 8; ++s2) {
+      for (int s2 = 0; s2 < HS; ++s2) {
         gq[s2] = 0.f;
         if (st < F && (vmask >> s2 & 1u)) {
           const uint32_t tq = (uint32_t)(dir ? F - 1 - st : st);
@@ -667,13 +679,12 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
     };
     load_g(0);
     const float sc = (q == 2) ? 2.0f : 1.0f;  // tanh(x) = 2 sigmoid(2x) - 1 for the cell gate
-    // phase-2 role: one thread per (unit pair, slot)
-    const int up = tid & 15, cs = tid >> 4;  // units 2 up, 2 up + 1; slot cs (0..15)
-    const bool cvalid = cs < NB && (b0 + cs) < B;
-    const uint32_t crow0 = (uint32_t)(b0 + cs) * (uint32_t)F;
+    // cell-phase role: one thread per (unit pair, slot cs + 16 jj)
+    const int up = tid & 15, cs = tid >> 4;  // units 2 up, 2 up + 1; slots cs, cs + 16, ...
     const uint32_t ccol = (uint32_t)(dir * H + rank * UPC + 2 * up);
-    const uint32_t st_off = (uint32_t)(((cs >> 3) * 4 + (up >> 2)) * 128 + (cs & 7) * 16 + (up & 3) * 4);  // core-matrix layout
-    float c0 = 0.f, c1 = 0.f;
+    float c0[SPT], c1[SPT];
+#pragma unroll
+    for (int jj = 0; jj < SPT; ++jj) c0[jj] = c1[jj] = 0.f;
     const uint32_t dst_h = mapa_u32(smem_u32(h_buf) + rank * TC_BLK, lane & 7);
     const uint32_t dst_bar = mapa_u32(smem_u32(&h_bar[0]), lane & 7);
     for (int step = 0; step < F; ++step) {
@@ -681,40 +692,54 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const uint32_t tt = (uint32_t)(dir ? F - 1 - step : step);
       mbar_wait(mma_bar, step & 1);
       tc_fence_after();
-      uint32_t v[TC_ISSUERS][8];
+      float acc[HS];
+      {
+        uint32_t v[TC_ISSUERS][HS];
 #pragma unroll
-      for (int a = 0; a < TC_ISSUERS; ++a) tmem_ld8(t_ld + (uint32_t)(a * TC_N), v[a]);
-      tmem_ld_wait();
-      tc_fence_before();
-      float a8[8];
+        for (int a = 0; a < TC_ISSUERS; ++a) {
+          if (HS == 8) tmem_ld8(t_ld + (uint32_t)(a * N), reinterpret_cast<uint32_t(&)[8]>(v[a]));
+          else tmem_ld16(t_ld + (uint32_t)(a * N), reinterpret_cast<uint32_t(&)[16]>(v[a]));
+        }
+        tmem_ld_wait();
+        tc_fence_before();
 #pragma unroll
-      for (int s2 = 0; s2 < 8; ++s2) {
-        float acc = __uint_as_float(v[0][s2]);
+        for (int s2 = 0; s2 < HS; ++s2) {
+          float t = __uint_as_float(v[0][s2]);
 #pragma unroll
-        for (int a = 1; a < TC_ISSUERS; ++a) acc += __uint_as_float(v[a][s2]);
-        const float sg = lean_sigmoid(sc * (acc + gq[s2]));
-        a8[s2] = (q == 2) ? 2.0f * sg - 1.0f : sg;
+          for (int a = 1; a < TC_ISSUERS; ++a) t += __uint_as_float(v[a][s2]);
+          acc[s2] = t;
+        }
       }
-      float* acol = act + (q * TC_N + 8 * ch) * UPC + lane;  // [gate][slot][unit]: conflict-free both ways
+      float* acol = act + (q * N + HS * ch) * UPC + lane;  // [gate][slot][unit]: conflict-free both ways
 #pragma unroll
-      for (int s2 = 0; s2 < 8; ++s2) acol[s2 * UPC] = a8[s2];
+      for (int s2 = 0; s2 < HS; ++s2) {
+        const float sg = lean_sigmoid(sc * (acc[s2] + gq[s2]));
+        acol[s2 * UPC] = (q == 2) ? 2.0f * sg - 1.0f : sg;
+      }
       named_bar_sync(1, 256);
       // ---- (unit pair, slot): c = f c + i g ; h = o tanh(c) ----
-      const float* ap = act + cs * UPC + 2 * up;
-      const float2 gi = *reinterpret_cast<const float2*>(ap);
-      const float2 gf = *reinterpret_cast<const float2*>(ap + TC_N * UPC);
-      const float2 gg = *reinterpret_cast<const float2*>(ap + 2 * TC_N * UPC);
-      const float2 go = *reinterpret_cast<const float2*>(ap + 3 * TC_N * UPC);
-      c0 = gf.x * c0 + gi.x * gg.x;
-      c1 = gf.y * c1 + gi.y * gg.y;
-      const float h0 = go.x * (2.0f * lean_sigmoid(2.0f * c0) - 1.0f);
-      const float h1 = go.y * (2.0f * lean_sigmoid(2.0f * c1) - 1.0f);
-      float r0, r1;
-      const uint32_t hh = pack_hi2(h0, h1, r0, r1);
-      const uint32_t hl = pack2(r0, r1);
       uint8_t* stg = stage + nxt * TC_BLK;
-      *reinterpret_cast<uint32_t*>(stg + st_off) = hh;
-      *reinterpret_cast<uint32_t*>(stg + TC_BLKP + st_off) = hl;
+      float h0[SPT], h1[SPT];
+      uint32_t hh[SPT], hl[SPT];
+#pragma unroll
+      for (int jj = 0; jj < SPT; ++jj) {
+        const int sl = cs + 16 * jj;
+        const float* ap = act + sl * UPC + 2 * up;
+        const float2 gi = *reinterpret_cast<const float2*>(ap);
+        const float2 gf = *reinterpret_cast<const float2*>(ap + N * UPC);
+        const float2 gg = *reinterpret_cast<const float2*>(ap + 2 * N * UPC);
+        const float2 go = *reinterpret_cast<const float2*>(ap + 3 * N * UPC);
+        c0[jj] = gf.x * c0[jj] + gi.x * gg.x;
+        c1[jj] = gf.y * c1[jj] + gi.y * gg.y;
+        h0[jj] = go.x * (2.0f * lean_sigmoid(2.0f * c0[jj]) - 1.0f);
+        h1[jj] = go.y * (2.0f * lean_sigmoid(2.0f * c1[jj]) - 1.0f);
+        float r0, r1;
+        hh[jj] = pack_hi2(h0[jj], h1[jj], r0, r1);
+        hl[jj] = pack2(r0, r1);
+        const uint32_t st_off = (uint32_t)(((sl >> 3) * 4 + (up >> 2)) * 128 + (sl & 7) * 16 + (up & 3) * 4);  // core-matrix layout
+        *reinterpret_cast<uint32_t*>(stg + st_off) = hh[jj];
+        *reinterpret_cast<uint32_t*>(stg + TC_BLKP + st_off) = hl[jj];
+      }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy (async proxy) reads
       named_bar_sync(2, 256);
       if (warp == 0 && lane < LSTM_CL) {
@@ -722,13 +747,17 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
         bulk_s2cluster(dst_h + (uint32_t)(nxt * LSTM_CL * TC_BLK), smem_u32(stg), TC_BLK, dst_bar + (uint32_t)(nxt * sizeof(uint64_t)));
       }
       load_g(step + 1);  // next step's input projections: in flight during the exchange, never in front of the proxy fence
-      if (cvalid) {  // layer output to HBM: off the critical path
-        const uint32_t row = crow0 + tt;
-        if (Hout) *reinterpret_cast<float2*>(Hout + (size_t)(row * (uint32_t)ldh + ccol)) = make_float2(h0, h1);
-        if (Hhi) {
-          const size_t o = (size_t)(row * (uint32_t)ldhs + ccol);
-          *reinterpret_cast<uint32_t*>(Hhi + o) = hh;
-          *reinterpret_cast<uint32_t*>(Hlo + o) = hl;
+#pragma unroll
+      for (int jj = 0; jj < SPT; ++jj) {  // layer output to HBM: off the critical path
+        const int sl = cs + 16 * jj;
+        if (sl < NB && (b0 + sl) < B) {
+          const uint32_t row = (uint32_t)(b0 + sl) * (uint32_t)F + tt;
+          if (Hout) *reinterpret_cast<float2*>(Hout + (size_t)(row * (uint32_t)ldh + ccol)) = make_float2(h0[jj], h1[jj]);
+          if (Hhi) {
+            const size_t o = (size_t)(row * (uint32_t)ldhs + ccol);
+            *reinterpret_cast<uint32_t*>(Hhi + o) = hh[jj];
+            *reinterpret_cast<uint32_t*>(Hlo + o) = hl[jj];
+          }
         }
       }
     }
@@ -743,19 +772,27 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
   }
 }
 
-static int launch_tc(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs, int B,
-                     int F, int slots, cudaStream_t stream) {
-  const size_t smem = (size_t)2 * LSTM_CL * TC_BLK + 2 * TC_BLK + (size_t)4 * TC_N * 32 * 4 + 64 + 128;
-  auto kern = lstm_rec_tc_kernel;
+template <int N>
+static int launch_tc_n(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs, int B,
+                       int F, int slots, cudaStream_t stream) {
+  constexpr int BLK = 2 * N * 64;
+  const size_t smem = (size_t)2 * LSTM_CL * BLK + 2 * BLK + (size_t)4 * N * 32 * 4 + 64 + 128;
+  auto kern = lstm_rec_tc_kernel<N>;
   RFX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  RFX_REQUIRE((long long)B * F * (long long)ldg < (1ll << 32) && (long long)B * F * (long long)std::max(ldh, ldhs) < (1ll << 32),
-              "lstm: tensors too large for 32-bit element offsets");
-  RFX_REQUIRE((!Hout || ldh % 2 == 0) && (!Hhi || ldhs % 2 == 0), "lstm: output row strides must be even");
-  const int nb = (slots > 0 && slots < TC_N) ? slots : TC_N;
+  const int nb = (slots > 0 && slots < N) ? slots : N;
   dim3 grid(LSTM_CL, ceil_div(B, nb), 2);
   kern<<<grid, TC_THREADS, smem, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb);
   RFX_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+static int launch_tc(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs, int B,
+                     int F, int slots, cudaStream_t stream) {
+  RFX_REQUIRE((long long)B * F * (long long)ldg < (1ll << 32) && (long long)B * F * (long long)std::max(ldh, ldhs) < (1ll << 32),
+              "lstm: tensors too large for 32-bit element offsets");
+  RFX_REQUIRE((!Hout || ldh % 2 == 0) && (!Hhi || ldhs % 2 == 0), "lstm: output row strides must be even");
+  if (slots > TC_N) return launch_tc_n<TC_N_MAX>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
+  return launch_tc_n<TC_N>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
 }
 
 template <int NB>
@@ -799,7 +836,7 @@ void lstm_set_impl(int impl) { g_lstm_impl = impl; }
 int lstm_get_impl() { return g_lstm_impl; }
 
 int lstm_clusters_for(int B, int slots) {
-  const int s = slots <= 0 ? LSTM_SLOTS : (slots < TC_N ? slots : TC_N);
+  const int s = slots <= 0 ? LSTM_SLOTS : (slots < TC_N_MAX ? slots : TC_N_MAX);
   return 2 * ceil_div(B, s);
 }
 

@@ -136,10 +136,10 @@ struct rfx_umx {
   int mark_idx = 0;
   // host-buffer pipeline (rfx_umx_sample_host / submit_host / wait_host): two slots, item-chunked copies on two internal streams.
   // The multi-lane pipeline (rfx_umx_pipe_*) reuses the same copy streams and per-slot events with slot = lane.
-  static constexpr int kSlots = 4, kHostSlots = 2, kChunks = 4;
+  static constexpr int kSlots = 8, kHostSlots = 2, kChunks = 4;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev_in[kSlots][kChunks] = {}, ev_ist[kSlots][kChunks] = {}, ev_out[kSlots] = {};
-  bool pending[kSlots] = {false, false, false, false};
+  bool pending[kSlots] = {};
   // multi-lane pipeline state (see rfx_umx_pipe_push)
   struct Lane {
     cudaStream_t s = nullptr;
@@ -163,6 +163,7 @@ struct rfx_umx {
     Done done[kRing];
     long long pushed = 0;
     void* ws = nullptr;
+    bool free_run = false;
     int sms = 0, max_sms = 0, lstm_slots = 0, lstm_impl = -1;
     // SM partition (CUDA green contexts): the recurrence streams own `rec_sms_granted` SMs, every other stream the rest.
     // When the driver cannot provide it the pipeline falls back to capping the grids of the non-recurrent kernels.
@@ -575,6 +576,16 @@ int umx_host_setup(rfx_umx_t* h) {
 }
 
 // ---- multi-lane pipeline ------------------------------------------------------------------------------------------
+// Lanes (batches in flight).  nb_layers lanes = the staggered schedule (push(n) runs stage l of step n - l; recurrences
+// round-robin over the recurrence streams); more lanes = the free-running schedule (push(n) enqueues the whole step on lane
+// n mod lanes, layer l's recurrences all go to recurrence stream l, so each of those streams runs back to back as long as enough
+// steps are in flight to cover one step's latency).
+int umx_pipe_lanes(const rfx_umx_t* h) {
+  int lanes = h->cfg.nb_layers + 3;
+  if (const char* e = getenv("RFX_UMX_PIPE_LANES")) lanes = atoi(e);
+  return std::max(h->cfg.nb_layers, std::min(lanes, (int)rfx_umx::kSlots));
+}
+
 int umx_pipe_setup(rfx_umx_t* h, int B, int T) {
   rfx_umx::Pipe& p = h->pipe;
   int rc;
@@ -582,15 +593,19 @@ int umx_pipe_setup(rfx_umx_t* h, int B, int T) {
   if (p.ready && p.B == B && p.T == T) return 0;
   if (p.ready)
     for (int i = 0; i < p.depth; ++i) RFX_REQUIRE(!p.lane[i].live, "pipeline: batch shape changed while steps are in flight (flush first)");
-  RFX_REQUIRE(h->cfg.nb_layers <= rfx_umx::kSlots, "the pipeline supports at most 4 LSTM layers");
+  RFX_REQUIRE(h->cfg.nb_layers <= 4, "the pipeline supports at most 4 LSTM layers");
+  const int lanes = umx_pipe_lanes(h);
+  const bool free_run = lanes > h->cfg.nb_layers;
   int dev = 0;
   cudaGetDevice(&dev);
   RFX_CHECK_CUDA(cudaDeviceGetAttribute(&p.sms, cudaDevAttrMultiProcessorCount, dev));
   // Schedule: `slots` batch slots per recurrence cluster, `streams` recurrence launches side by side.  The recurrences are
   // packed into the fewest SMs; every other kernel keeps to the rest of the chip so that a recurrence launch never waits
   // for SMs.  Too small a remainder -> no partition.
-  // Default: the tcgen05 recurrence (16 slots per cluster, half the SMs of the mma.sync kernel per launch) on two streams.
-  int impl = h->H == 256 ? 2 : -1, slots = impl == 2 ? 16 : 8, streams = impl == 2 ? 2 : 1;
+  // Default: the tcgen05 recurrence.  Free-running lanes: 32 slots per cluster (one cluster = 8 SMs per direction at B = 32) and
+  // one recurrence stream per LSTM layer; staggered lanes: 16 slots per cluster on two streams.
+  int impl = h->H == 256 ? 2 : -1;
+  int slots = impl == 2 ? (free_run ? 32 : 16) : 8, streams = impl == 2 ? (free_run ? h->cfg.nb_layers : 2) : 1;
   if (const char* e = getenv("RFX_UMX_PIPE_LSTM_IMPL")) { impl = atoi(e); slots = impl == 2 ? 16 : 8; streams = impl == 2 ? 2 : 1; }  // tuning overrides
   if (const char* e = getenv("RFX_UMX_PIPE_SLOTS")) slots = atoi(e);
   if (const char* e = getenv("RFX_UMX_PIPE_REC_STREAMS")) streams = std::min(4, std::max(1, atoi(e)));
@@ -606,7 +621,8 @@ int umx_pipe_setup(rfx_umx_t* h, int B, int T) {
     umx_green_destroy(p.gctx_rec, p.gctx_rest);
     p.gctx_rec = p.gctx_rest = nullptr;
   }
-  p.depth = h->cfg.nb_layers;
+  p.depth = lanes;
+  p.free_run = free_run;
   p.rec_n = streams;
   p.lstm_slots = slots;
   p.max_sms = 0;
@@ -621,7 +637,7 @@ int umx_pipe_setup(rfx_umx_t* h, int B, int T) {
     return true;
   }();
   if (part && allow_green) {
-    cudaStream_t rs[4] = {nullptr, nullptr, nullptr, nullptr}, ls[rfx_umx::kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t rs[4] = {nullptr, nullptr, nullptr, nullptr}, ls[rfx_umx::kSlots] = {};
     green = umx_green_partition(rec_sms, p.rec_n, rs, p.depth, ls, &p.gctx_rec, &p.gctx_rest, &p.rec_sms_granted, &p.rest_sms_granted);
     if (green) {
       for (int i = 0; i < p.rec_n; ++i) p.rec[i] = rs[i];
@@ -668,7 +684,7 @@ int umx_pipe_superstep(rfx_umx_t* h) {
       c.L = L;
       c.x = ln.x_host ? reinterpret_cast<const float*>(c.ws + L.off_x[0]) : ln.x;
       c.out = ln.out_host ? reinterpret_cast<float*>(c.ws + L.off_out[0]) : ln.out;
-      c.s = ln.s; c.s_rec = p.rec[p.rec_count++ % p.rec_n];
+      c.s = ln.s; c.s_rec = p.free_run ? p.rec[st % p.rec_n] : p.rec[p.rec_count++ % p.rec_n];
       c.ev_pre = ln.ev_pre; c.ev_rec = ln.ev_rec; c.ev_stft = ln.ev_stft;
       c.io = (ln.x_host || ln.out_host) ? &io : nullptr;
       c.max_sms = p.max_sms; c.lstm_slots = p.lstm_slots; c.lstm_impl = p.lstm_impl;
@@ -700,10 +716,10 @@ int rfx_umx_sample(rfx_umx_t* h, const float* x, int B, int T, float* out, void*
 
 size_t rfx_umx_pipe_workspace_bytes(const rfx_umx_t* h, int B, int T) {
   if (!h || B <= 0 || T <= 0) return 0;
-  return (size_t)h->cfg.nb_layers * umx_layout(h, B, T).total;
+  return (size_t)umx_pipe_lanes(h) * umx_layout(h, B, T).total;
 }
 
-int rfx_umx_pipe_depth(const rfx_umx_t* h) { return h ? h->cfg.nb_layers : 0; }
+int rfx_umx_pipe_depth(const rfx_umx_t* h) { return h ? umx_pipe_lanes(h) : 0; }
 
 int rfx_umx_pipe_info(const rfx_umx_t* h, int* rec_sms, int* rest_sms, int* rec_streams, int* slots_per_cluster) {
   RFX_REQUIRE(h && rec_sms && rest_sms && rec_streams && slots_per_cluster, "null argument");
@@ -742,7 +758,10 @@ int rfx_umx_pipe_push(rfx_umx_t* h, const float* x, int x_on_host, int B, int T,
   ln.seq = seq; ln.next_stage = 0; ln.live = true;
   p.pushed = seq + 1;
   if (seq_out) *seq_out = seq;
-  return umx_pipe_superstep(h);
+  if (!p.free_run) return umx_pipe_superstep(h);
+  for (int st = 0; st < h->cfg.nb_layers; ++st)  // free-running: the new step is the only live lane; walk it through every stage
+    if ((rc = umx_pipe_superstep(h))) return rc;
+  return 0;
 }
 
 int rfx_umx_pipe_flush(rfx_umx_t* h, void* stream) {

@@ -74,6 +74,8 @@ def test_lstm_layer_tcgen05(B, F):
     out_tc = _lstm_case(256, 512, B, F, "tc")
     out_mma = _lstm_case(256, 512, B, F, "mma", slots=8)
     assert relrms(out_tc, out_mma) < 2e-6
+    out_tc32 = _lstm_case(256, 512, B, F, "tc", slots=32)   # 32 slots per cluster (MMA N = 32)
+    assert relrms(out_tc32, out_mma) < 2e-6
 
 
 def _lstm_case(H, I, B, F, impl, slots=0):

@@ -106,7 +106,7 @@ def test_pipeline_equals_sample(host):
     xs = [weights.synth_audio(300 + i, B, T) for i in range(n)]
     refs = [m.sample(x.cuda()).cpu() for x in xs]
     pipe = m.pipeline("cuda:0")
-    assert pipe.depth == 3
+    assert pipe.depth >= 3
     if host:
         ins = [x.pin_memory() for x in xs]
         outs = [torch.empty(B, 1, T).pin_memory() for _ in range(n)]
@@ -137,15 +137,20 @@ def test_pipeline_equals_sample(host):
     assert relrms(o2.cpu(), oumx.sample(x2, sd)) < TOL
 
 
-def test_pipeline_wait_before_exit_raises():
+def test_pipeline_wait_right_after_push():
+    """Free-running lanes: a step's completion event exists as soon as push returns.  In the staggered schedule (as many lanes as
+    LSTM layers) the step is still inside the pipeline then and wait() must refuse instead of returning early."""
     sd = weights.umx_state(5)
     m = _model(sd)
     pipe = m.pipeline("cuda:0")
-    s = pipe.push(weights.synth_audio(1, 2, 16384).cuda())
-    with pytest.raises(Exception):
-        pipe.wait(s)  # still inside the pipeline: needs depth-1 more pushes or a flush
-    pipe.flush()
-    pipe.wait(s)
+    x = weights.synth_audio(1, 2, 16384)
+    s = pipe.push(x.cuda())
+    if pipe.depth == m.model.nb_layers:
+        with pytest.raises(Exception):
+            pipe.wait(s)
+        pipe.flush()
+    out = pipe.wait(s)
+    assert relrms(out.cpu(), oumx.sample(x, sd)) < TOL
 
 
 @pytest.mark.parametrize("B,T", [(1, 8192), (19, 16384), (33, 8192)])

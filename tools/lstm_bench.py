@@ -12,7 +12,7 @@ F = 513
 H = 256
 G = torch.randn(B * F, 8 * H, device="cuda") * 0.5
 Whh = (torch.rand(2, 4 * H, H, device="cuda") * 2 - 1) * H ** -0.5
-for impl, slots in (("mma", 8), ("tc", 16)):
+for impl, slots in (("mma", 8), ("tc", 16), ("tc", 32)):
     for _ in range(2):
         ops.lstm_layer(G, Whh, B, F, impl=impl, slots=slots)
     torch.cuda.synchronize()
