@@ -192,7 +192,7 @@ def run_ours(args):
 
     # ---- device-resident throughput: the multi-lane pipeline (model.pipeline(): rfx_umx_pipe_*) ------------
     # Inputs already in HBM.  K steps are pushed back to back and the pipeline is flushed inside the timed region, so the
-    # number includes the fill and drain of the 3-deep pipeline.  CUDA events on the launching (current) stream: the first
+    # number includes the fill and drain of the pipeline (one step's latency, ~5 ms, against ~1.35 ms per step in steady state).  CUDA events on the launching (current) stream: the first
     # lane waits for everything enqueued before the push, and flush() makes the current stream wait for every output.
     pipe = model.pipeline(dev)
     depth = pipe.depth
@@ -286,13 +286,14 @@ def run_ours(args):
     roofline = {
         "kernel": "lstm_rec_tc_kernel (BiLSTM recurrence on tcgen05, W_hh as the TMEM A operand; 1 launch per layer)", "bound": "hbm",
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-        "traffic": 155.96e6,  # dram read+write bytes per launch, ncu --set full (profiles/r1/ncu_lstm_rec_tc.txt)
+        "traffic": 154.62e6,  # dram read+write bytes per launch, ncu --set full (profiles/r1/ncu_lstm_rec_tc32.txt)
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": lstm_bytes, "ms_per_launch": lstm_t * 1e3,
         "launches_timed": len(lstm_ms),
-        "note": "513 strictly dependent steps per launch: latency-bound by construction, see DESIGN.md; each launch holds 32 SMs, two "
-                "launches run side by side on a 64-SM green-context partition while the other kernels of neighbouring steps use the "
-                "remaining 84 SMs",
+        "note": "513 strictly dependent steps per launch: latency-bound by construction, see DESIGN.md; in the pipeline a launch holds "
+                f"{8 * 2 * ((BATCH + pinfo['slots_per_cluster'] - 1) // max(1, pinfo['slots_per_cluster']))} SMs and {pinfo['recurrence_streams']} launches "
+                f"(one per LSTM layer) run side by side on a {pinfo['recurrence_sms']}-SM partition while the other kernels of the steps in "
+                f"flight use the remaining {pinfo['other_sms']} SMs",
         "serial_stage_ms": {k: round(v, 4) for k, v in stage_acc.items()},
     }
 
@@ -331,7 +332,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

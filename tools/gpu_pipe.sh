@@ -1,7 +1,17 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_umx.py tests/test_gpu_ingest.py -m gpu -q --timeout 200 --no-header -p no:cacheprovider > gpurun_out/t.log 2>&1; echo "umx tests exit=$? $(tail -n 1 gpurun_out/t.log)"; grep -E "^FAILED|^ERROR|rror|assert" gpurun_out/t.log | head -8
-RFX_UMX_PIPE_LANES=3 timeout 600 python -m pytest tests/test_gpu_umx.py -m gpu -q --timeout 200 --no-header -p no:cacheprovider -k pipeline > gpurun_out/t2.log 2>&1; echo "staggered-mode pipeline tests exit=$? $(tail -n 1 gpurun_out/t2.log)"
-for cfg in "6 32 3" "5 32 3" "8 32 3" "6 16 2" "6 16 3" "3 16 2"; do set -- $cfg
-RFX_UMX_PIPE_LANES=$1 RFX_UMX_PIPE_SLOTS=$2 RFX_UMX_PIPE_REC_STREAMS=$3 timeout 120 python tools/pipe_bench.py 32 60 2>&1 | tail -1 | cut -c1-230 | sed "s/^/lanes=$1 /"
-done
+python bench.py --warmup 3 > gpurun_out/bench_k200.json 2> gpurun_out/bench_k200.err; echo "bench K=200 exit=$?"
+python -c "
+import json; d=json.load(open('gpurun_out/bench_k200.json')); print('value',d['value'], d['ms_per_step'], 'steps',d['steps'],'e2e', d['e2e']['value'], d['e2e']['ms_per_step'])"
+cat > /tmp/one.py <<'PY'
+import os, sys, torch
+sys.path.insert(0, os.getcwd())
+from remfx_b200 import ops
+B, F, H = 32, 513, 256
+G = torch.randn(B * F, 8 * H, device="cuda") * 0.5
+Whh = (torch.rand(2, 4 * H, H, device="cuda") * 2 - 1) * H ** -0.5
+for _ in range(3):
+    ops.lstm_layer(G, Whh, B, F, impl="tc", slots=32)
+torch.cuda.synchronize()
+PY
+ncu --set full --clock-control none --import-source on -k regex:lstm_rec_tc -s 2 -c 1 -o gpurun_out/prof_lstm_tc32 python /tmp/one.py > gpurun_out/ncu_tc32.log 2>&1; echo "ncu exit=$?"
