@@ -115,19 +115,21 @@ int rfx_umx_submit_host(rfx_umx_t* h, int slot, const float* x_host, int B, int 
                         size_t workspace_bytes, void* stream);
 int rfx_umx_wait_host(rfx_umx_t* h, int slot);
 /* Multi-lane pipeline: the throughput form of rfx_umx_sample for a stream of equally shaped batches (a serving loop over
- * remfx/models.py:303-304).  One call is nb_layers stages (stage l = [STFT, fc1 if l = 0] + W_ih GEMM + recurrence of LSTM
- * layer l [+ fc2, fc3, iSTFT if l = last]); the bidirectional recurrence is a chain of strictly dependent steps that occupies
- * only 8 * 2 * ceil(B/8) SMs, so push(n) runs stage l of step n - l for every l: the recurrences of nb_layers consecutive
- * steps go back to back on one internal high-priority stream while all the other kernels of those steps run beside them,
- * capped to the remaining SMs.  Results are identical to rfx_umx_sample (same kernels, same order per step).
- *   push   enqueues step `*seq` (0, 1, 2, ... since the handle was created) and returns; x / out are device buffers, or
+ * remfx/models.py:303-304).  The bidirectional recurrence is a chain of strictly dependent steps that occupies a fraction of
+ * the chip, and nothing inside one batch can overlap it; consecutive batches can.  push(n) enqueues the whole of batch n on lane
+ * n mod depth (a stream + private workspace; depth = rfx_umx_pipe_depth batches in flight); the recurrence of LSTM layer l
+ * always goes to recurrence stream l, so those streams run back to back (tcgen05 kernel, 32 slots per cluster), on their own SM
+ * partition (CUDA green contexts; grid caps as the fallback), while every other kernel of the batches in flight runs beside
+ * them.  Results equal rfx_umx_sample's to ~1e-6 (same math, the recurrence kernel sums in a different order).
+ *   push   enqueues batch `*seq` (0, 1, 2, ... since the handle was created) and returns; x / out are device buffers, or
  *          (pinned) host buffers when x_on_host / out_on_host is non-zero (H2D / D2H then ride the internal copy streams).
  *          The lane starts after the work already enqueued on `stream`.  x and out must stay valid and untouched until
- *          the step's output is complete.  Step s leaves the pipeline during push(s + depth - 1) or flush.
- *   flush  runs the stages still owed to the steps in flight and makes `stream` wait for every finished output.
- *   wait / stream_wait  block the host / make `stream` wait until step seq's output is complete (the step must have left the
- *          pipeline; completion records are kept for the last 16 steps).  A consumer that waits for step n - depth - 1
- *          before push(n) keeps a full super-step queued behind the one that is executing.
+ *          the batch's output is complete.
+ *   flush  makes `stream` wait for every output enqueued so far (and, in the staggered schedule -- as many lanes as LSTM
+ *          layers, RFX_UMX_PIPE_LANES -- first runs the stages still owed to the batches in flight).
+ *   wait / stream_wait  block the host / make `stream` wait until batch seq's output is complete (completion records are kept
+ *          for the last 16 batches; in the staggered schedule a batch must first have left the pipeline).  A consumer that
+ *          stays `depth` or more batches behind its pushes never starves the device.
  * workspace: rfx_umx_pipe_workspace_bytes (= depth private lanes), the same pointer for every push until a flush. */
 size_t rfx_umx_pipe_workspace_bytes(const rfx_umx_t* h, int B, int T);
 int rfx_umx_pipe_depth(const rfx_umx_t* h);
