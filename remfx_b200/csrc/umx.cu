@@ -351,7 +351,9 @@ int rfx_umx_finalize(rfx_umx_t* h, void* stream) {
   struct { const char* key; int N, K; SplitW* dst; } fcs[3] = {
       {"fc1.weight", hid, bins, &h->fc1p}, {"fc2.weight", hid, 2 * hid, &h->fc2p}, {"fc3.weight", bins, hid, &h->fc3p}};
   for (int i = 0; i < 3; ++i) {
-    const int BN = g2_choose_bn(fcs[i].N);
+    // fc3 (N = bins = 1025): 256-wide tiles -> 5 column tiles (the last one ragged, its MMAs shrink to N = 16) instead of 9,
+    // i.e. the activations are re-read 5x instead of 9x
+    const int BN = (i == 2 && fcs[i].N > 256) ? 256 : g2_choose_bn(fcs[i].N);
     if (h->packed_store[L + i].alloc(split_weight_elems(fcs[i].N, fcs[i].K, BN))) return 1;
     if ((rc = pack_split_weights(P(h, fcs[i].key), fcs[i].K, fcs[i].N, fcs[i].K, BN,
                                  reinterpret_cast<__nv_bfloat16*>(h->packed_store[L + i].p), fcs[i].dst, s)))

@@ -1,4 +1,4 @@
-"""Probe / check of the tcgen05 recurrence against the explicit-loop oracle (one small case and the bench shape)."""
+"""Quick check of the tcgen05 recurrence (both instantiations) and the mma.sync kernel against the explicit-loop oracle."""
 import os
 import sys
 
@@ -31,6 +31,5 @@ def case(B, F, impl, slots=0):
 
 
 if __name__ == "__main__":
-    v = os.environ.get("RFX_LSTM_TC_VARIANT", "0")
     for B, F in ((3, 4), (16, 20), (21, 33)):
-        print(f"variant {v}: B={B} F={F} tc rel-RMS {case(B, F, 'tc'):.3e}   (mma: {case(B, F, 'mma'):.3e})", flush=True)
+        print(f"B={B} F={F} rel-RMS vs oracle: tc<16> {case(B, F, 'tc'):.3e}  tc<32> {case(B, F, 'tc', slots=32):.3e}  mma {case(B, F, 'mma'):.3e}", flush=True)
