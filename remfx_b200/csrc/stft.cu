@@ -130,7 +130,7 @@ __device__ __forceinline__ float stft_mag_of(float pw, float in_mean, float in_s
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) stft2048_kernel(StftParams p, int groups, int n_work) {
+__global__ void __launch_bounds__(256, 4) stft2048_kernel(StftParams p, int groups, int n_work) {
   constexpr int NC = 1024, NFFT = 2048;
   __shared__ float2 buf[4 * FFT1024_BUF];
   const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
