@@ -669,8 +669,10 @@ int umx_pipe_setup(rfx_umx_t* h, int B, int T) {
   return 0;
 }
 
-// One super-step: every live lane advances by one stage, deepest stage first, so the recurrences reach the shared
-// stream in the order (last layer of the oldest step, ..., first layer of the newest step).
+// One super-step: every live lane advances by one stage, deepest stage first.  Staggered schedule: called once per push, so the
+// recurrences reach the round-robin streams in the order (last layer of the oldest step, ..., first layer of the newest step).
+// Free-running schedule: called nb_layers times per push with the new step as the only live lane, i.e. it walks that step through
+// all its stages; the recurrence of stage l goes to recurrence stream l.
 int umx_pipe_superstep(rfx_umx_t* h) {
   rfx_umx::Pipe& p = h->pipe;
   const int nl = h->cfg.nb_layers;
