@@ -164,7 +164,7 @@ struct rfx_umx {
     long long pushed = 0;
     void* ws = nullptr;
     bool free_run = false;
-    int sms = 0, max_sms = 0, lstm_slots = 0, lstm_impl = -1;
+    int sms = 0, max_sms = 0, gemm_ctas = 0, lstm_slots = 0, lstm_impl = -1;
     // SM partition (CUDA green contexts): the recurrence streams own `rec_sms_granted` SMs, every other stream the rest.
     // When the driver cannot provide it the pipeline falls back to capping the grids of the non-recurrent kernels.
     CUgreenCtx gctx_rec = nullptr, gctx_rest = nullptr;
@@ -393,7 +393,8 @@ struct UmxCall {
   cudaStream_t s_rec;   // stream of the recurrence launches (== s outside the pipeline)
   cudaEvent_t ev_pre, ev_rec, ev_stft;  // pipeline only: W_ih done -> recurrence may start; recurrence done; x consumed
   const HostIO* io;
-  int max_sms;          // > 0: non-recurrent kernels keep to this many SMs
+  int max_sms;          // > 0: STFT / iSTFT grids keep to this many SMs (grid-cap partition)
+  int gemm_ctas;        // > 0: persistent GEMM grids of this many CTAs (the SMs its stream can actually use)
   int lstm_slots;       // batch slots per recurrence cluster (0 = automatic)
   int lstm_impl;        // recurrence kernel (-1 = process default: mma.sync; 2 = tcgen05)
 };
@@ -458,7 +459,7 @@ int umx_stage(rfx_umx_t* h, const UmxCall& c, int l) {
 
     // (2) fc1 + bn1 + tanh (model.py:132-138) -> first half of the skip-concat buffer
     Epilogue e1; e1.s1 = h->bn_s[0].p; e1.t1 = h->bn_t[0].p; e1.act = ACT_TANH;
-    if ((rc = dense(A1, L.plane_A1, L.lda1, L.M, h->bins, h->fc1p, nullptr, 0, XC, L.plane_XC, 2 * hid, e1, s, c.max_sms)) || (rc = mark()))
+    if ((rc = dense(A1, L.plane_A1, L.lda1, L.M, h->bins, h->fc1p, nullptr, 0, XC, L.plane_XC, 2 * hid, e1, s, c.gemm_ctas)) || (rc = mark()))
       return rc;
   }
 
@@ -468,7 +469,7 @@ int umx_stage(rfx_umx_t* h, const UmxCall& c, int l) {
     if (l == 0) { lin = XC; lin_plane = L.plane_XC; ldin = 2 * hid; }
     else { lin = Hb[(l - 1) & 1]; lin_plane = L.plane_H; ldin = hid; }
     Epilogue eb; eb.t1 = h->lstm_bias[l].p;
-    if ((rc = dense(lin, lin_plane, ldin, L.M, hid, h->wihp[l], G, 8 * H, nullptr, 0, 0, eb, s, c.max_sms)) || (rc = mark())) return rc;
+    if ((rc = dense(lin, lin_plane, ldin, L.M, hid, h->wihp[l], G, 8 * H, nullptr, 0, 0, eb, s, c.gemm_ctas)) || (rc = mark())) return rc;
     __nv_bfloat16* hout; size_t hplane; int ldh;
     if (l == nl - 1) { hout = XC + hid; hplane = L.plane_XC; ldh = 2 * hid; }  // torch.cat([x, lstm_out], -1) (model.py:144) for free
     else { hout = Hb[l & 1]; hplane = L.plane_H; ldh = hid; }
@@ -492,11 +493,11 @@ int umx_stage(rfx_umx_t* h, const UmxCall& c, int l) {
   if (l == nl - 1) {
     // (4) fc2 + bn2 + ReLU (model.py:147-150)
     Epilogue e2; e2.s1 = h->bn_s[1].p; e2.t1 = h->bn_t[1].p; e2.act = ACT_RELU;
-    if ((rc = dense(XC, L.plane_XC, 2 * hid, L.M, 2 * hid, h->fc2p, nullptr, 0, Y2, L.plane_Y2, hid, e2, s, c.max_sms)) || (rc = mark())) return rc;
+    if ((rc = dense(XC, L.plane_XC, 2 * hid, L.M, 2 * hid, h->fc2p, nullptr, 0, Y2, L.plane_Y2, hid, e2, s, c.gemm_ctas)) || (rc = mark())) return rc;
 
     // (5) fc3 + bn3 + output scale/mean + ReLU (model.py:153-164) = the non-negative ratio mask
     Epilogue e3; e3.s1 = h->bn_s[2].p; e3.t1 = h->bn_t[2].p; e3.s2 = P(h, "output_scale"); e3.t2 = P(h, "output_mean"); e3.act = ACT_RELU;
-    if ((rc = dense(Y2, L.plane_Y2, hid, L.M, hid, h->fc3p, mask, L.ldm, nullptr, 0, 0, e3, s, c.max_sms)) || (rc = mark())) return rc;
+    if ((rc = dense(Y2, L.plane_Y2, hid, L.M, hid, h->fc3p, mask, L.ldm, nullptr, 0, 0, e3, s, c.gemm_ctas)) || (rc = mark())) return rc;
 
     // (6) `* mix` (model.py:164) + wiener niter=0 (filtering.py:442-451) + iSTFT (transforms.py:168-177)
     IstftParams ip{};
@@ -654,6 +655,10 @@ int umx_pipe_setup(rfx_umx_t* h, int B, int T) {
     p.rec_sms_granted = p.rest_sms_granted = 0;
     if (part) p.max_sms = p.sms - rec_sms;  // fallback: cap the grids of the non-recurrent kernels instead
   }
+  // A persistent GEMM launched with one CTA per SM of the DEVICE would run as two uneven waves inside a partition: size its grid
+  // to the SMs its stream can use.
+  p.gemm_ctas = green ? p.rest_sms_granted : p.max_sms;
+  if (const char* e = getenv("RFX_UMX_PIPE_GEMM_CTAS")) p.gemm_ctas = atoi(e);
   if (const char* e = getenv("RFX_UMX_PIPE_MAX_SMS")) p.max_sms = atoi(e);
   if (!p.ready) {
     for (int i = 0; i < p.depth; ++i) {
@@ -691,7 +696,7 @@ int umx_pipe_superstep(rfx_umx_t* h) {
       c.s = ln.s; c.s_rec = p.free_run ? p.rec[st % p.rec_n] : p.rec[p.rec_count++ % p.rec_n];
       c.ev_pre = ln.ev_pre; c.ev_rec = ln.ev_rec; c.ev_stft = ln.ev_stft;
       c.io = (ln.x_host || ln.out_host) ? &io : nullptr;
-      c.max_sms = p.max_sms; c.lstm_slots = p.lstm_slots; c.lstm_impl = p.lstm_impl;
+      c.max_sms = p.max_sms; c.gemm_ctas = p.gemm_ctas; c.lstm_slots = p.lstm_slots; c.lstm_impl = p.lstm_impl;
       if (st == 0 && ln.x_host && ln.stft_recorded) RFX_CHECK_CUDA(cudaStreamWaitEvent(h->copy_in, ln.ev_stft, 0));  // staging free
       int rc;
       if ((rc = umx_stage(h, c, st))) return rc;
