@@ -563,13 +563,12 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
   constexpr int TC_BLK = 2 * TC_BLKP;  // hi + lo
   constexpr int HS = N / 2;         // slots per epilogue thread in the activation phase
   constexpr int SPT = N / 16;       // slots per epilogue thread in the cell phase
-  constexpr int TX = LSTM_CL * TC_BLK;
   extern __shared__ __align__(128) uint8_t lstm_smem[];
   uint8_t* h_buf = lstm_smem;                                                // [2][CL][TC_BLK]
   uint8_t* stage = h_buf + 2 * LSTM_CL * TC_BLK;                             // [2][TC_BLK]
   float* act = reinterpret_cast<float*>(stage + 2 * TC_BLK);                 // [4 gates][N slots][32 units]
-  uint64_t* h_bar = reinterpret_cast<uint64_t*>(act + 4 * N * UPC);          // [2]
-  uint64_t* mma_bar = h_bar + 2;                                             // [1]
+  uint64_t* h_bar = reinterpret_cast<uint64_t*>(act + 4 * N * UPC);          // [2][CL]: one per (buffer, source CTA)
+  uint64_t* mma_bar = h_bar + 2 * LSTM_CL;                                   // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
 
   const int tid = threadIdx.x;
@@ -580,8 +579,7 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
 
   for (int i = tid; i < 2 * LSTM_CL * TC_BLK / 4; i += TC_THREADS) reinterpret_cast<uint32_t*>(h_buf)[i] = 0u;
   if (tid == 0) {
-    mbar_init(&h_bar[0], 1);
-    mbar_init(&h_bar[1], 1);
+    for (int i = 0; i < 2 * LSTM_CL; ++i) mbar_init(&h_bar[i], 1);
     mbar_init(mma_bar, TC_ISSUERS);
     mbar_fence_init();
   }
@@ -635,26 +633,33 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
     const uint32_t d_acc = tb_u + 256u + (uint32_t)(w * N);
     for (int step = 0; step < F; ++step) {
       const int cur = step & 1;
-      if (step > 0) mbar_wait(&h_bar[cur], ((step - 1) >> 1) & 1);  // all of h_{t-1} has landed
-      tc_fence_after();
-      // units [16 kk, 16 kk + 16) live in source CTA kk / 2, unit groups 2 (kk & 1), + 1 of its block
+      // units [16 kk, 16 kk + 16) live in source CTA kk / 2, unit groups 2 (kk & 1), + 1 of its block.  Every source block has
+      // its own mbarrier and the senders rotate their destinations, so the blocks of a step land spread over the exchange:
+      // this issuer starts on source 2 w as soon as THAT block is here, then source 2 w + 1.
       const uint32_t lo0 = (((hb_u + (uint32_t)cur * (LSTM_CL * TC_BLK) + (uint32_t)(2 * w) * TC_BLK) & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16);
       const uint32_t a0 = tb_u + 32u * w;
-      if (elect_one()) {
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {  // W_lo h_hi, W_hi h_lo, W_hi h_hi (small terms first)
+      for (int half = 0; half < 2; ++half) {
+        if (step > 0) mbar_wait(&h_bar[cur * LSTM_CL + 2 * w + half], ((step - 1) >> 1) & 1);  // h_{t-1} of source CTA 2 w + half
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const uint32_t boff = (uint32_t)((k4 >> 1) * TC_BLK + (k4 & 1) * 256 + (pass == 1 ? TC_BLKP : 0));
-            umma_ts_f16_split(d_acc, a0 + (pass == 0 ? 128u : 0u) + 8u * k4, lo0 + (boff >> 4), desc_hi, idesc, (pass | k4) ? 1u : 0u);
+          for (int pass = 0; pass < 3; ++pass) {  // W_lo h_hi, W_hi h_lo, W_hi h_hi (small terms first)
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) {
+              const int k4 = 2 * half + k2;
+              const uint32_t boff = (uint32_t)(half * TC_BLK + k2 * 256 + (pass == 1 ? TC_BLKP : 0));
+              umma_ts_f16_split(d_acc, a0 + (pass == 0 ? 128u : 0u) + 8u * k4, lo0 + (boff >> 4), desc_hi, idesc, (half | pass | k2) ? 1u : 0u);
+            }
           }
+          if (half == 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb_u) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb_u) : "memory");
+        __syncwarp();
       }
-      __syncwarp();
     }
-    // Nobody may exit while peers can still write into its shared memory: wait for the last h to land.
-    mbar_wait(&h_bar[F & 1], ((F - 1) >> 1) & 1);
+    // Nobody may exit while peers can still write into its shared memory: wait for the last h blocks to land.
+    mbar_wait(&h_bar[(F & 1) * LSTM_CL + 2 * w], ((F - 1) >> 1) & 1);
+    mbar_wait(&h_bar[(F & 1) * LSTM_CL + 2 * w + 1], ((F - 1) >> 1) & 1);
   } else {
     // =============================== epilogue warps ===============================
     const int q = warp & 3;    // TMEM lane quarter = gate
@@ -685,8 +690,10 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
     float c0[SPT], c1[SPT];
 #pragma unroll
     for (int jj = 0; jj < SPT; ++jj) c0[jj] = c1[jj] = 0.f;
-    const uint32_t dst_h = mapa_u32(smem_u32(h_buf) + rank * TC_BLK, lane & 7);
-    const uint32_t dst_bar = mapa_u32(smem_u32(&h_bar[0]), lane & 7);
+    // sender lane i pushes this CTA's block to CTA (rank + i) mod 8: rotated, so every destination's eight blocks arrive in turn
+    const uint32_t dst_cta = (rank + (uint32_t)lane) & 7u;
+    const uint32_t dst_h = mapa_u32(smem_u32(h_buf) + rank * TC_BLK, dst_cta);
+    const uint32_t dst_bar = mapa_u32(smem_u32(&h_bar[rank]), dst_cta);
     for (int step = 0; step < F; ++step) {
       const int cur = step & 1, nxt = cur ^ 1;
       const uint32_t tt = (uint32_t)(dir ? F - 1 - step : step);
@@ -743,8 +750,8 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy (async proxy) reads
       named_bar_sync(2, 256);
       if (warp == 0 && lane < LSTM_CL) {
-        if (lane == 0) mbar_arrive_expect_tx(&h_bar[nxt], TX);
-        bulk_s2cluster(dst_h + (uint32_t)(nxt * LSTM_CL * TC_BLK), smem_u32(stg), TC_BLK, dst_bar + (uint32_t)(nxt * sizeof(uint64_t)));
+        mbar_arrive_expect_tx(&h_bar[nxt * LSTM_CL + lane], TC_BLK);  // lane s arms the local barrier of source CTA s
+        bulk_s2cluster(dst_h + (uint32_t)(nxt * LSTM_CL * TC_BLK), smem_u32(stg), TC_BLK, dst_bar + (uint32_t)(nxt * LSTM_CL * sizeof(uint64_t)));
       }
       load_g(step + 1);  // next step's input projections: in flight during the exchange, never in front of the proxy fence
 #pragma unroll
@@ -776,7 +783,7 @@ template <int N>
 static int launch_tc_n(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs, int B,
                        int F, int slots, cudaStream_t stream) {
   constexpr int BLK = 2 * N * 64;
-  const size_t smem = (size_t)2 * LSTM_CL * BLK + 2 * BLK + (size_t)4 * N * 32 * 4 + 64 + 128;
+  const size_t smem = (size_t)2 * LSTM_CL * BLK + 2 * BLK + (size_t)4 * N * 32 * 4 + 256 + 128;
   auto kern = lstm_rec_tc_kernel<N>;
   RFX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nb = (slots > 0 && slots < N) ? slots : N;
