@@ -286,7 +286,7 @@ def run_ours(args):
     roofline = {
         "kernel": "lstm_rec_tc_kernel (BiLSTM recurrence on tcgen05, W_hh as the TMEM A operand; 1 launch per layer)", "bound": "hbm",
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-        "traffic": 154.62e6,  # dram read+write bytes per launch, ncu --set full (profiles/r1/ncu_lstm_rec_tc32.txt)
+        "traffic": 154.66e6,  # dram read+write bytes per launch, ncu --set full (profiles/r1/ncu_lstm_rec_tc32.txt)
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": lstm_bytes, "ms_per_launch": lstm_t * 1e3,
         "launches_timed": len(lstm_ms),
