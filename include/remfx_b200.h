@@ -185,6 +185,23 @@ size_t rfx_tcn_workspace_bytes(const rfx_tcn_t* h, int B, long long T);
 int rfx_tcn_forward(rfx_tcn_t* h, const float* x, int B, long long T, float* out, void* workspace, size_t workspace_bytes, void* stream);
 int rfx_tcn_launches_per_call(const rfx_tcn_t* h);
 
+/* Training path of the TCN (config 5's step for this network: remfx/models.py:217-220 -> loss.backward() differentiates
+ * remfx/tcn.py:48-59,126-130 through torch autograd; here the same gradients come from hand-written kernels).
+ *   rfx_tcn_forward_train  = rfx_tcn_forward that keeps every block's output in `workspace` (split-bf16 planes);
+ *   rfx_tcn_backward       = dL/d(parameters) from dL/d(out): `x`, `out` and `workspace` are those of the matching
+ *                            rfx_tcn_forward_train call; `dout` is (B, 1, rfx_tcn_out_length(T)) fp32.
+ * keys[i] names a parameter as in rfx_tcn_load_param and grads[i] is a device buffer of that parameter's size; every
+ * parameter of the network must be listed; each buffer is OVERWRITTEN with the gradient (summed over the batch).
+ * Sums over time use fp32 atomics: reproducible to rounding, not bit-for-bit. */
+size_t rfx_tcn_train_workspace_bytes(const rfx_tcn_t* h, int B, long long T);
+int rfx_tcn_forward_train(rfx_tcn_t* h, const float* x, int B, long long T, float* out, void* workspace, size_t workspace_bytes, void* stream);
+int rfx_tcn_backward(rfx_tcn_t* h, const float* x, const float* out, const float* dout, int B, long long T, const char* const* keys,
+                     float* const* grads, int nkeys, void* workspace, size_t workspace_bytes, void* stream);
+int rfx_tcn_backward_launches_per_call(const rfx_tcn_t* h);
+/* Weight-gradient kernel selector, process-wide: 0 = mma.sync bf16x3 (default, the product path), 1 = plain fp32 FFMA
+ * kernel (slow; cross-check in tests only). */
+int rfx_tcn_set_wgrad_impl(int impl);
+
 /* ---------------------------------------------------------------------------------------------
  * C1-C4  Cnn14 effect classifier (eval mode)
  *   replaces remfx/classifier.py:193-233 (Cnn14.forward) as called by FXClassifier.forward

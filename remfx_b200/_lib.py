@@ -84,6 +84,12 @@ _SIGNATURES = {
     "rfx_tcn_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_longlong]),
     "rfx_tcn_forward": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_longlong, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rfx_tcn_launches_per_call": (C.c_int, [C.c_void_p]),
+    "rfx_tcn_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_longlong]),
+    "rfx_tcn_forward_train": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_longlong, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rfx_tcn_backward": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, C.c_int, C.c_longlong, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p),
+                                   C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rfx_tcn_backward_launches_per_call": (C.c_int, [C.c_void_p]),
+    "rfx_tcn_set_wgrad_impl": (C.c_int, [C.c_int]),
     "rfx_cnn14_create": (C.c_int, [C.POINTER(Cnn14Config), C.POINTER(C.c_void_p)]),
     "rfx_cnn14_destroy": (None, [C.c_void_p]),
     "rfx_cnn14_load_param": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int64, C.c_void_p]),

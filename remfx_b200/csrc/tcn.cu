@@ -7,12 +7,7 @@
 //   tail:    tanh(1x1 conv C -> 1)  (remfx/tcn.py:129)
 // Activations are channel-last ([B][L][C]) split-bf16 planes, so every tap of the dilated convolution is a
 // plain 2-D TMA box at a shifted row -- no im2col, no padding copies.  Two ping-pong buffers.
-#include "kernels.h"
-#include "../../include/remfx_b200.h"
-
-#include <map>
-#include <string>
-#include <vector>
+#include "tcn_internal.h"
 
 namespace rfx {
 
@@ -92,55 +87,58 @@ __global__ void tcn_gather_w_kernel(const float* __restrict__ wconv, const float
   }
 }
 
-struct TcnBuf {
-  float* p = nullptr;
-  size_t n = 0;
-  int alloc(size_t count) {
-    if (p) cudaFree(p);
-    p = nullptr;
-    RFX_CHECK_CUDA(cudaMalloc(&p, count * sizeof(float)));
-    n = count;
-    return 0;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    n = 0;
-  }
-};
-
 }  // namespace rfx
 
 using namespace rfx;
 
-struct rfx_tcn {
-  rfx_tcn_config cfg;
-  std::map<std::string, TcnBuf> params;
-  std::vector<TcnBuf> wsplit;  // per block >= 1: split-bf16 planes of Wcat
-  std::vector<SplitW> wpack;
-  bool finalized = false;
-  ~rfx_tcn() {
-    for (auto& kv : params) kv.second.release();
-    for (auto& b : wsplit) b.release();
-  }
-};
+namespace rfx {
 
-namespace {
-int dilation_of(const rfx_tcn* h, int n) {
-  int d = 1;
-  for (int i = 0; i < n % h->cfg.stack_size; ++i) d *= h->cfg.dilation_growth;
-  return d;
+int tcn_run_forward(rfx_tcn* h, const float* x, int B, long long T, float* out, __nv_bfloat16* const* block_out, long long plane_elems,
+                    cudaStream_t s) {
+  const int C = h->cfg.channel_width, K = h->cfg.kernel_size, NBk = h->cfg.nblocks;
+  const long long Lout = tcn_len_after(h, T, NBk);
+  const long long L1 = tcn_len_after(h, T, 1);
+  const long long bs = L1 * C;  // batch stride (elements) of every activation buffer
+  // block 0
+  {
+    const int d = tcn_dilation_of(h, 0);
+    const long long items = L1 * (C / 8);
+    dim3 grid((unsigned)((items + 255) / 256), B);
+    tcn_first_kernel<<<grid, 256, 0, s>>>(x, T, (int)L1, C, K, d, tcn_res_off(h, d), tcn_param(h, "process_blocks.0.conv1.weight"),
+                                          tcn_param(h, "process_blocks.0.conv1.bias"), tcn_param(h, "process_blocks.0.res.weight"),
+                                          tcn_param(h, "process_blocks.0.relu.weight"), block_out[0], block_out[0] + plane_elems, bs);
+    RFX_CHECK_CUDA(cudaGetLastError());
+  }
+  long long Lin = L1;
+  for (int n = 1; n < NBk; ++n) {
+    const int d = tcn_dilation_of(h, n);
+    const long long Lo = Lin - (long long)(K - 1) * d;
+    const std::string p = "process_blocks." + std::to_string(n);
+    G2Problem pr;
+    pr.A.hi = block_out[n - 1]; pr.A.rows = Lin; pr.A.ld = C; pr.A.batch_stride = bs; pr.A.plane_stride = plane_elems;
+    pr.W = h->wpack[n];
+    pr.M = (int)Lo; pr.N = C; pr.batch = B; pr.Ktap = C; pr.taps = K + 1;
+    for (int j = 0; j < K; ++j) pr.row_off[j] = j * d;
+    pr.row_off[K] = tcn_res_off(h, d);  // causal_crop drops the last sample: offset (K-1) d - 1; center_crop: (K-1) d / 2
+    pr.dual = true;
+    pr.Chi = block_out[n]; pr.Clo = block_out[n] + plane_elems; pr.ldcs = C; pr.bscs = bs;
+    pr.epi.t1 = tcn_param(h, p + ".conv1.bias");
+    pr.epi.slope = tcn_param(h, p + ".relu.weight");
+    pr.epi.act = ACT_PRELU;
+    int rc = launch_gemm2(pr, s);
+    if (rc) return rc;
+    Lin = Lo;
+  }
+  {
+    dim3 grid((unsigned)((Lin + 7) / 8), B);
+    tcn_tail_kernel<<<grid, 256, 0, s>>>(block_out[NBk - 1], block_out[NBk - 1] + plane_elems, bs, (int)Lin, C, tcn_param(h, "output.weight"),
+                                         tcn_param(h, "output.bias"), out, Lout);
+    RFX_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
 }
-const float* TP(const rfx_tcn* h, const std::string& k) {
-  auto it = h->params.find(k);
-  return it == h->params.end() ? nullptr : it->second.p;
-}
-long long len_after(const rfx_tcn* h, long long T, int nblocks) {
-  long long L = T;
-  for (int n = 0; n < nblocks; ++n) L -= (long long)(h->cfg.kernel_size - 1) * dilation_of(h, n);
-  return L;
-}
-}  // namespace
+
+}  // namespace rfx
 
 extern "C" {
 
@@ -168,6 +166,7 @@ int rfx_tcn_load_param(rfx_tcn_t* h, const char* key, const float* src, int64_t 
   }
   RFX_CHECK_CUDA(cudaMemcpyAsync(b.p, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   h->finalized = false;
+  h->transposed_ready = false;
   return 0;
 }
 
@@ -185,6 +184,7 @@ int rfx_tcn_finalize(rfx_tcn_t* h, void* stream) {
   for (auto& b : h->wsplit) b.release();
   h->wsplit.assign(NBk, TcnBuf());
   h->wpack.assign(NBk, SplitW());
+  h->transposed_ready = false;
   TcnBuf wcat;
   if (NBk > 1 && wcat.alloc((size_t)C * (K + 1) * C)) return 1;
   for (int n = 0; n < NBk; ++n) {
@@ -196,7 +196,7 @@ int rfx_tcn_finalize(rfx_tcn_t* h, void* stream) {
       return rc;
     }
     if (n == 0) continue;
-    tcn_gather_w_kernel<<<148 * 4, 256, 0, s>>>(TP(h, p + ".conv1.weight"), TP(h, p + ".res.weight"), C, K, wcat.p);
+    tcn_gather_w_kernel<<<148 * 4, 256, 0, s>>>(tcn_param(h, p + ".conv1.weight"), tcn_param(h, p + ".res.weight"), C, K, wcat.p);
     RFX_CHECK_CUDA(cudaGetLastError());
     if (h->wsplit[n].alloc(split_weight_elems(C, (K + 1) * C, 256))) { wcat.release(); return 1; }
     if ((rc = pack_split_weights(wcat.p, (long long)(K + 1) * C, C, (K + 1) * C, 256, reinterpret_cast<__nv_bfloat16*>(h->wsplit[n].p), &h->wpack[n], s))) {
@@ -211,73 +211,26 @@ int rfx_tcn_finalize(rfx_tcn_t* h, void* stream) {
   return 0;
 }
 
-long long rfx_tcn_out_length(const rfx_tcn_t* h, long long T) { return h ? len_after(h, T, h->cfg.nblocks) : 0; }
+long long rfx_tcn_out_length(const rfx_tcn_t* h, long long T) { return h ? tcn_len_after(h, T, h->cfg.nblocks) : 0; }
 
 size_t rfx_tcn_workspace_bytes(const rfx_tcn_t* h, int B, long long T) {
   if (!h || B <= 0) return 0;
-  const long long L1 = len_after(h, T, 1);
-  if (L1 <= 0) return 0;
-  const size_t plane = align_up((size_t)B * L1 * h->cfg.channel_width * 2, 256);
-  return 4 * plane;  // two ping-pong buffers x (hi, lo)
+  if (tcn_len_after(h, T, 1) <= 0) return 0;
+  return 4 * tcn_plane_bytes(h, B, T);  // two ping-pong buffers x (hi, lo)
 }
 
 int rfx_tcn_forward(rfx_tcn_t* h, const float* x, int B, long long T, float* out, void* workspace, size_t workspace_bytes, void* stream) {
   RFX_REQUIRE(h && x && out && workspace, "null argument");
   RFX_REQUIRE(h->finalized, "rfx_tcn_finalize has not been called since the last parameter load");
-  const int C = h->cfg.channel_width, K = h->cfg.kernel_size, NBk = h->cfg.nblocks;
-  const long long Lout = len_after(h, T, NBk);
-  RFX_REQUIRE(B > 0 && Lout > 0, "input shorter than the receptive field");
+  RFX_REQUIRE(B > 0 && tcn_len_after(h, T, h->cfg.nblocks) > 0, "input shorter than the receptive field");
   RFX_REQUIRE(T < (1ll << 31), "T too large");
   RFX_REQUIRE(workspace_bytes >= rfx_tcn_workspace_bytes(h, B, T), "workspace too small (rfx_tcn_workspace_bytes)");
   RFX_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
-  cudaStream_t s = (cudaStream_t)stream;
-  const long long L1 = len_after(h, T, 1);
-  const size_t plane_bytes = align_up((size_t)B * L1 * C * 2, 256);
-  const long long plane_elems = (long long)(plane_bytes / 2);
+  const size_t plane_bytes = tcn_plane_bytes(h, B, T);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  __nv_bfloat16* buf[2] = {reinterpret_cast<__nv_bfloat16*>(ws), reinterpret_cast<__nv_bfloat16*>(ws + 2 * plane_bytes)};
-  const long long bs = L1 * C;  // batch stride (elements) of every activation buffer
-  const int centre = h->cfg.causal ? -1 : 0;  // causal_crop drops the last sample: offset (K-1) d - 1; center_crop: (K-1) d / 2
-
-  // block 0
-  {
-    const int d = dilation_of(h, 0);
-    const int res_off = h->cfg.causal ? (K - 1) * d - 1 : ((K - 1) * d) / 2;
-    (void)centre;
-    const long long items = L1 * (C / 8);
-    dim3 grid((unsigned)((items + 255) / 256), B);
-    tcn_first_kernel<<<grid, 256, 0, s>>>(x, T, (int)L1, C, K, d, res_off, TP(h, "process_blocks.0.conv1.weight"), TP(h, "process_blocks.0.conv1.bias"),
-                                          TP(h, "process_blocks.0.res.weight"), TP(h, "process_blocks.0.relu.weight"), buf[0], buf[0] + plane_elems, bs);
-    RFX_CHECK_CUDA(cudaGetLastError());
-  }
-  long long Lin = L1;
-  int cur = 0;
-  for (int n = 1; n < NBk; ++n) {
-    const int d = dilation_of(h, n);
-    const long long Lo = Lin - (long long)(K - 1) * d;
-    const std::string p = "process_blocks." + std::to_string(n);
-    G2Problem pr;
-    pr.A.hi = buf[cur]; pr.A.rows = Lin; pr.A.ld = C; pr.A.batch_stride = bs; pr.A.plane_stride = plane_elems;
-    pr.W = h->wpack[n];
-    pr.M = (int)Lo; pr.N = C; pr.batch = B; pr.Ktap = C; pr.taps = K + 1;
-    for (int j = 0; j < K; ++j) pr.row_off[j] = j * d;
-    pr.row_off[K] = h->cfg.causal ? (K - 1) * d - 1 : ((K - 1) * d) / 2;
-    pr.dual = true;
-    pr.Chi = buf[cur ^ 1]; pr.Clo = buf[cur ^ 1] + plane_elems; pr.ldcs = C; pr.bscs = bs;
-    pr.epi.t1 = TP(h, p + ".conv1.bias");
-    pr.epi.slope = TP(h, p + ".relu.weight");
-    pr.epi.act = ACT_PRELU;
-    int rc = launch_gemm2(pr, s);
-    if (rc) return rc;
-    Lin = Lo;
-    cur ^= 1;
-  }
-  {
-    dim3 grid((unsigned)((Lin + 7) / 8), B);
-    tcn_tail_kernel<<<grid, 256, 0, s>>>(buf[cur], buf[cur] + plane_elems, bs, (int)Lin, C, TP(h, "output.weight"), TP(h, "output.bias"), out, Lout);
-    RFX_CHECK_CUDA(cudaGetLastError());
-  }
-  return 0;
+  std::vector<__nv_bfloat16*> outs(h->cfg.nblocks);
+  for (int n = 0; n < h->cfg.nblocks; ++n) outs[n] = reinterpret_cast<__nv_bfloat16*>(ws + (size_t)(n & 1) * 2 * plane_bytes);  // ping-pong
+  return tcn_run_forward(h, x, B, T, out, outs.data(), (long long)(plane_bytes / 2), (cudaStream_t)stream);
 }
 
 int rfx_tcn_launches_per_call(const rfx_tcn_t* h) { return h ? h->cfg.nblocks + 1 : 0; }

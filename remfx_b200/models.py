@@ -425,18 +425,76 @@ class TCNModel(nn.Module):
         return out
 
     def forward(self, batch):
-        """(x, target) -> (loss, output); the target is causal-cropped to the output length (models.py:379-386)."""
+        """(x, target) -> (loss, output); the target is causal-cropped to the output length (models.py:379-386).
+
+        With autograd enabled and trainable parameters, `output` carries a graph node whose backward is
+        `rfx_tcn_backward` (csrc/tcn_bwd.cu), so `loss.backward()` fills every parameter's `.grad` the way the
+        reference's Lightning step does (remfx/models.py:217-220)."""
         from .losses import remfx_loss
         from .ops import causal_crop
 
         x, target = batch
-        output = self.sample(x)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
+            output = self._sample_train(x)
+        else:
+            output = self.sample(x)
         if output.shape[-1] < target.shape[-1]:
             target = causal_crop(target, output.shape[-1])
         return remfx_loss(output, target), output
 
+    def _sample_train(self, x: Tensor) -> Tensor:
+        if x.dim() != 3 or x.shape[1] != 1:
+            raise ValueError(f"expected input of shape (batch, 1, time), got {tuple(x.shape)}")
+        _lib.require_device(x)
+        if x.dtype != torch.float32:
+            raise ValueError("expected float32 audio")
+        names = [k for k, _ in self.model.named_parameters()]
+        params = [p for _, p in self.model.named_parameters()]
+        return _TcnTrainFn.apply(self, names, x.contiguous(), *params)
+
     def launches_per_call(self) -> int:
         return self.model.nblocks + 1
+
+
+class _TcnTrainFn(torch.autograd.Function):
+    """TCN forward that keeps the block outputs + hand-written backward (rfx_tcn_forward_train / rfx_tcn_backward).
+
+    Gradients are produced for the parameters only: the reference never differentiates with respect to the audio."""
+
+    @staticmethod
+    def forward(ctx, owner: "TCNModel", names, x: Tensor, *params: Tensor):
+        B, _, T = x.shape
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            h = owner._sync(x.device)
+            Lout = L.rfx_tcn_out_length(h, T)
+            if Lout <= 0:
+                raise ValueError(f"input length {T} is shorter than the receptive field {owner.model.receptive_field}")
+            ws = torch.empty(L.rfx_tcn_train_workspace_bytes(h, B, T), dtype=torch.uint8, device=x.device)
+            out = torch.empty(B, 1, Lout, dtype=torch.float32, device=x.device)
+            rc = L.rfx_tcn_forward_train(h, x.data_ptr(), B, T, out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.cur_stream())
+            _lib.check(rc, "rfx_tcn_forward_train")
+        ctx.owner, ctx.names = owner, list(names)
+        ctx.save_for_backward(x, out, ws, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        x, out, ws, *params = ctx.saved_tensors
+        owner, names = ctx.owner, ctx.names
+        B, _, T = x.shape
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            h = owner._sync(x.device)  # parameters unchanged since the forward: a no-op stamp check
+            grads = [torch.empty_like(p, memory_format=torch.contiguous_format) for p in params]
+            n = len(names)
+            keys = (C.c_char_p * n)(*[k.encode() for k in names])
+            ptrs = (C.c_void_p * n)(*[g.data_ptr() for g in grads])
+            d = dout.detach().to(torch.float32).contiguous()
+            rc = L.rfx_tcn_backward(h, x.data_ptr(), out.data_ptr(), d.data_ptr(), B, T, keys, ptrs, n, ws.data_ptr(), ws.numel(),
+                                    _lib.cur_stream())
+            _lib.check(rc, "rfx_tcn_backward")
+        return (None, None, None, *[g if p.requires_grad else None for g, p in zip(grads, params)])
 
 
 # ======================================================================================================
