@@ -181,32 +181,29 @@ int rfx_tcn_finalize(rfx_tcn_t* h, void* stream) {
     return 0;
   };
   int rc;
-  for (auto& b : h->wsplit) b.release();
-  h->wsplit.assign(NBk, TcnBuf());
+  if ((int)h->wsplit.size() != NBk) {
+    for (auto& b : h->wsplit) b.release();
+    h->wsplit.assign(NBk, TcnBuf());
+  }
   h->wpack.assign(NBk, SplitW());
   h->transposed_ready = false;
-  TcnBuf wcat;
-  if (NBk > 1 && wcat.alloc((size_t)C * (K + 1) * C)) return 1;
+  // all work below is ordered on `s`; the staging buffer and the packed planes are kept across calls (same sizes), so a
+  // training loop that re-finalizes after every optimiser step neither allocates nor synchronises here
+  if (NBk > 1 && h->wcat.alloc((size_t)C * (K + 1) * C)) return 1;
   for (int n = 0; n < NBk; ++n) {
     const std::string p = "process_blocks." + std::to_string(n);
     const int cin = n == 0 ? 1 : C;
     if ((rc = need(p + ".conv1.weight", (size_t)C * cin * K)) || (rc = need(p + ".conv1.bias", C)) || (rc = need(p + ".res.weight", (size_t)C * cin)) ||
-        (rc = need(p + ".relu.weight", C))) {
-      wcat.release();
+        (rc = need(p + ".relu.weight", C)))
       return rc;
-    }
     if (n == 0) continue;
-    tcn_gather_w_kernel<<<148 * 4, 256, 0, s>>>(tcn_param(h, p + ".conv1.weight"), tcn_param(h, p + ".res.weight"), C, K, wcat.p);
+    tcn_gather_w_kernel<<<148 * 4, 256, 0, s>>>(tcn_param(h, p + ".conv1.weight"), tcn_param(h, p + ".res.weight"), C, K, h->wcat.p);
     RFX_CHECK_CUDA(cudaGetLastError());
-    if (h->wsplit[n].alloc(split_weight_elems(C, (K + 1) * C, 256))) { wcat.release(); return 1; }
-    if ((rc = pack_split_weights(wcat.p, (long long)(K + 1) * C, C, (K + 1) * C, 256, reinterpret_cast<__nv_bfloat16*>(h->wsplit[n].p), &h->wpack[n], s))) {
-      wcat.release();
+    if (h->wsplit[n].alloc(split_weight_elems(C, (K + 1) * C, 256))) return 1;
+    if ((rc = pack_split_weights(h->wcat.p, (long long)(K + 1) * C, C, (K + 1) * C, 256, reinterpret_cast<__nv_bfloat16*>(h->wsplit[n].p), &h->wpack[n], s)))
       return rc;
-    }
   }
-  if ((rc = need("output.weight", C)) || (rc = need("output.bias", 1))) { wcat.release(); return rc; }
-  RFX_CHECK_CUDA(cudaStreamSynchronize(s));  // wcat is a temporary
-  wcat.release();
+  if ((rc = need("output.weight", C)) || (rc = need("output.bias", 1))) return rc;
   h->finalized = true;
   return 0;
 }

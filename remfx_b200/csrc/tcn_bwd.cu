@@ -412,25 +412,24 @@ TrainLayout train_layout(const rfx_tcn* h, int B, long long T) {
 int ensure_transposed(rfx_tcn* h, cudaStream_t s) {
   if (h->transposed_ready) return 0;
   const int C = h->cfg.channel_width, K = h->cfg.kernel_size, NBk = h->cfg.nblocks;
-  for (auto& b : h->wsplit_t) b.release();
-  h->wsplit_t.assign(NBk, TcnBuf());
+  if ((int)h->wsplit_t.size() != NBk) {
+    for (auto& b : h->wsplit_t) b.release();
+    h->wsplit_t.assign(NBk, TcnBuf());
+  }
   h->wpack_t.assign(NBk, SplitW());
   if (NBk <= 1) { h->transposed_ready = true; return 0; }
-  TcnBuf wcat;
-  if (wcat.alloc((size_t)C * (K + 1) * C)) return 1;
+  if (h->wcat.alloc((size_t)C * (K + 1) * C)) return 1;  // stream-ordered reuse of the finalize staging buffer
   const int BN = g2_choose_bn(C);
-  int rc = 0;
-  for (int n = 1; n < NBk && !rc; ++n) {
+  for (int n = 1; n < NBk; ++n) {
     const std::string p = "process_blocks." + std::to_string(n);
-    tcn_gather_wt_kernel<<<148 * 4, 256, 0, s>>>(tcn_param(h, p + ".conv1.weight"), tcn_param(h, p + ".res.weight"), C, K, wcat.p);
-    if (cudaGetLastError() != cudaSuccess) { set_error("tcn_gather_wt_kernel launch failed"); rc = 1; break; }
-    if (h->wsplit_t[n].alloc(split_weight_elems(C, (K + 1) * C, BN))) { rc = 1; break; }
-    rc = pack_split_weights(wcat.p, (long long)(K + 1) * C, C, (K + 1) * C, BN, reinterpret_cast<__nv_bfloat16*>(h->wsplit_t[n].p), &h->wpack_t[n], s);
+    tcn_gather_wt_kernel<<<148 * 4, 256, 0, s>>>(tcn_param(h, p + ".conv1.weight"), tcn_param(h, p + ".res.weight"), C, K, h->wcat.p);
+    RFX_CHECK_CUDA(cudaGetLastError());
+    if (h->wsplit_t[n].alloc(split_weight_elems(C, (K + 1) * C, BN))) return 1;
+    int rc = pack_split_weights(h->wcat.p, (long long)(K + 1) * C, C, (K + 1) * C, BN, reinterpret_cast<__nv_bfloat16*>(h->wsplit_t[n].p), &h->wpack_t[n], s);
+    if (rc) return rc;
   }
-  if (cudaStreamSynchronize(s) != cudaSuccess && !rc) { set_error("ensure_transposed: stream synchronise failed"); rc = 1; }
-  wcat.release();
-  if (!rc) h->transposed_ready = true;
-  return rc;
+  h->transposed_ready = true;
+  return 0;
 }
 
 int rows_per_cta_for(long long L, int B) {

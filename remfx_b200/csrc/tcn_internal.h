@@ -13,6 +13,7 @@ struct TcnBuf {
   float* p = nullptr;
   size_t n = 0;
   int alloc(size_t count) {
+    if (p && n == count) return 0;  // same size: keep the buffer (a training loop re-finalizes after every optimiser step)
     if (p) cudaFree(p);
     p = nullptr;
     RFX_CHECK_CUDA(cudaMalloc(&p, count * sizeof(float)));
@@ -35,12 +36,14 @@ struct rfx_tcn {
   std::vector<rfx::SplitW> wpack;
   std::vector<rfx::TcnBuf> wsplit_t;  // per block >= 1: split-bf16 planes of WcatT [ci][tap * C + co]   (input gradient), built lazily
   std::vector<rfx::SplitW> wpack_t;
+  rfx::TcnBuf wcat;  // fp32 staging of one block's gathered weights (finalize / transposed pack), reused stream-ordered
   bool finalized = false;
   bool transposed_ready = false;
   ~rfx_tcn() {
     for (auto& kv : params) kv.second.release();
     for (auto& b : wsplit) b.release();
     for (auto& b : wsplit_t) b.release();
+    wcat.release();
   }
 };
 

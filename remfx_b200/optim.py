@@ -146,6 +146,9 @@ class FusedAdamW(torch.optim.Optimizer):
                                         b.numel, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
                                         float(g["weight_decay"]), self.step_count, float(scale), clip, self._ws.data_ptr(),
                                         self.total_norm.data_ptr(), s), "rfx_adamw_step")
+        # the kernel wrote the parameters through raw pointers: tell autograd (and the model handles, whose cached
+        # packed weights are keyed on `_version`) that they changed
+        torch.autograd.graph.increment_version(b.params)
         return loss
 
     # state_dict in torch.optim.AdamW's layout (per-parameter exp_avg / exp_avg_sq / step) so checkpoints interchange

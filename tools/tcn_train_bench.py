@@ -1,0 +1,73 @@
+"""TCN training step at the benchmark size: forward (kept activations) + MRSTFT/L1 loss + backward + clip + AdamW.
+
+    python tools/tcn_train_bench.py [--batch 1] [--steps 5] [--warmup 2] [--T 262144]
+
+Prints one JSON line: ms per stage (CUDA events on the launching stream), audio-seconds/s of the whole step, algorithmic
+TFLOP/s (3 x the forward's 5.136 TFLOP per chunk: forward, input gradient, weight gradient; the recomputed pre-activations
+are extra work and not counted), and the loss of every step.  Synthetic data, seeded random weights (oracle.weights)."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--T", type=int, default=262144)
+    a = ap.parse_args()
+    from oracle import weights  # seeded synthetic weights / audio only; nothing is computed by the oracle here
+    from remfx_b200.models import TCNModel
+    from remfx_b200.optim import configure_optimizers
+
+    m = TCNModel(sample_rate=48000, num_bins=1025, ninputs=1, noutputs=1, nblocks=20, channel_growth=0, channel_width=256,
+                 kernel_size=7, stack_size=10, dilation_growth=2, condition=False, latent_dim=2, norm_type="identity", causal=False,
+                 estimate_loudness=False)
+    m.load_state_dict(weights.tcn_state(0), strict=True)
+    m = m.cuda()
+    opt = configure_optimizers(m, max_steps=1000)["optimizer"]
+    x = weights.synth_audio(12345, a.batch, a.T).cuda()
+    t = weights.synth_audio(54321, a.batch, a.T).cuda()
+    names = ["forward", "loss+backward", "optimizer"]
+    acc = [0.0] * 3
+    losses = []
+    for it in range(a.warmup + a.steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        opt.zero_grad()
+        ev[0].record()
+        out = m._sample_train(x)
+        ev[1].record()
+        from remfx_b200.losses import remfx_loss
+        from remfx_b200.ops import causal_crop
+
+        loss = remfx_loss(out, causal_crop(t, out.shape[-1]))
+        loss.backward()
+        ev[2].record()
+        opt.step()
+        ev[3].record()
+        torch.cuda.synchronize()
+        losses.append(float(loss.detach()))
+        if it >= a.warmup:
+            for i in range(3):
+                acc[i] += ev[i].elapsed_time(ev[i + 1])
+    ms = [v / a.steps for v in acc]
+    total = sum(ms)
+    audio_s = a.batch * a.T / 48000.0
+    L = m.out_length(a.T)
+    fwd_tflop = 5.1355 * a.batch * (a.T / 262144.0)
+    print(json.dumps({
+        "workload": f"TCN training step (forward_train + MRSTFT/100 L1 + backward + clip 10 + AdamW), batch {a.batch}x{a.T}",
+        "ms_per_step": total, "stage_ms": dict(zip(names, ms)), "audio_s_per_s": audio_s / (total * 1e-3),
+        "algorithmic_tflops": 3 * fwd_tflop / (total * 1e-3), "out_length": L, "losses": losses,
+        "grad_norm_last": float(opt.total_norm), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
+        "steps": a.steps, "warmup": a.warmup}))
+
+
+if __name__ == "__main__":
+    main()
