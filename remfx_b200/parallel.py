@@ -127,3 +127,81 @@ def _gloo_optim_worker(rank: int, world: int, port: int, q) -> None:
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
+
+
+class _StubNet(torch.nn.Module):
+    """CPU stand-in for a network wrapper in the host-logic tests: `forward((x, y)) -> (loss, out)` with a per-item-mean loss."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(3)
+        self.conv = torch.nn.Conv1d(1, 1, 5, padding=2)
+
+    def forward(self, batch):
+        x, y = batch
+        out = self.conv(x)
+        return (out - y).square().mean(), out
+
+
+class _BucketSGD:
+    """CPU stand-in with FusedAdamW's structure (flat bucket, `sync_grads` inside `step`) for the gloo tests."""
+
+    def __init__(self, params, lr: float, group=None):
+        from .optim import FlatBucket
+
+        self.bucket, self.lr, self.group = FlatBucket(params), lr, group
+
+    def zero_grad(self):
+        self.bucket.zero_grad()
+
+    def step(self):
+        from .optim import sync_grads
+
+        self.bucket.collect_grads()
+        scale = sync_grads(self.bucket.grad, self.group)
+        with torch.no_grad():
+            self.bucket.param.add_(self.bucket.grad, alpha=-self.lr * scale)
+
+
+def _stub_metrics(monkeypatch_target) -> None:
+    """Point remfx_b200.train's metric kernels at torch-CPU functions (host-logic tests only; never used by the product)."""
+    monkeypatch_target.sisdr_loss = lambda a, b: -(a * b).mean()
+    monkeypatch_target.mrstft_loss = lambda a, b: (a - b).abs().mean()
+
+
+def _gloo_train_worker(rank: int, world: int, port: int, q) -> None:
+    """world_size>1 CPU test of the L4/L5 host logic in remfx_b200.train (tests/test_train_cpu.py): every rank runs
+    `RemFX.fit_step` on its shard of a global batch; parameters must stay identical across ranks and equal to a single-process
+    step on the whole batch, and `sync_dist` metrics must be the mean over ranks."""
+    import os
+
+    import torch.distributed as dist
+
+    from . import train as T
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _stub_metrics(T)
+        g = torch.Generator().manual_seed(7)
+        x, y = torch.randn(4 * world, 1, 64, generator=g), torch.randn(4 * world, 1, 64, generator=g)
+        lo, hi = shard_range(x.shape[0], rank, world)
+        mod = T.RemFX(1e-4, 0.95, 0.999, 1e-6, 1e-3, 48000, _StubNet(), max_steps=10)
+        opt = _BucketSGD(mod.model.parameters(), lr=0.1)
+        for _ in range(3):
+            mod.fit_step((x[lo:hi], y[lo:hi], None, None), optimizer=opt)
+        # single-process reference on the whole batch
+        ref = _StubNet()
+        ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+        for _ in range(3):
+            ropt.zero_grad()
+            ref((x, y))[0].backward()
+            ropt.step()
+        ok = all(torch.allclose(a, b, rtol=1e-5, atol=1e-6) for a, b in zip(mod.model.parameters(), ref.parameters()))
+        # sync_dist metric = mean over ranks of the per-shard values of the LAST step (taken before that step's update)
+        local = mod.logged["Input_STFT"].clone()
+        want = (x - y).abs().mean()  # equal shard sizes: mean of shard means
+        ok = ok and abs(float(local) - float(want)) < 1e-6 and mod.global_step == 3
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
