@@ -7,7 +7,9 @@ all-reduce-less FusedAdamW, the handle re-sync after the update), each of which 
 lr = 1e-5 (a ctor argument of the reference module) keeps three steps in the regime where the loss falls monotonically.
 Tolerances: first loss 1e-4 relative (pure forward), later losses 2e-3 (PReLU-kink sign flips perturb single gradient
 elements, and AdamW's normalised update turns a flipped tiny gradient into a 2 lr parameter difference -- see
-test_gpu_tcn_backward.py), metrics 1e-3 relative / 1e-2 dB, direction of the total parameter change cosine > 0.98.
+test_gpu_tcn_backward.py), metrics 1e-3 relative / 1e-2 dB.  Direction of the total parameter change: cosine > 0.9 -- AdamW's first updates are
+lr * sign(g), so the ~2 % of gradient elements smaller than the kink noise flip their update; emulating 3e-6 relative
+noise on the CPU oracle alone gives cosine 0.957 against its own noise-free run, with losses within 5e-4.
 """
 import pytest
 import torch
@@ -75,7 +77,7 @@ def test_fit_step_matches_torch_training_step():
         db = (ref_params["model." + k] - sd["model." + k]).double().flatten()
         num += float(da @ db); den_a += float(da @ da); den_b += float(db @ db)
     cos = num / (den_a ** 0.5 * den_b ** 0.5)
-    assert cos > 0.98 and 0.9 < (den_a / den_b) ** 0.5 < 1.1, (cos, den_a, den_b)
+    assert cos > 0.9 and 0.9 < (den_a / den_b) ** 0.5 < 1.1, (cos, den_a, den_b)
 
 
 def test_eval_steps_do_not_build_a_graph_under_no_grad():
