@@ -114,3 +114,28 @@ def test_oracle_matches_live_reference():
     assert relrms(oumx.sample(x, sd), ref) < 1e-5
     X = R.utils.spectrogram(x, torch.hann_window(2048), 2048, 512, 0.3)
     assert relrms(ostft.spectrogram(x, torch.hann_window(2048), 2048, 512, 0.3), X) < 1e-6
+
+
+def test_training_loss_decomposes_over_data_parallel_shards():
+    """with the per-item spectral-convergence ratio (auraloss >= 0.4, the form restated in oracle/loss.py) the
+    training loss of a batch is the mean of its shards' losses, so averaging the shards' gradients (what the one all-reduce
+    of a data-parallel step does) reproduces the single-process gradient exactly up to rounding."""
+    from oracle import loss as oloss
+    from oracle import tcn as otcn
+
+    sd = weights.tcn_state(3, nblocks=3, width=64)
+    x = weights.synth_audio(50, 4, 3000)
+    y = weights.synth_audio(51, 4, 3000)
+
+    def grads(lo, hi):
+        st = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+        loss, _ = otcn.forward((x[lo:hi].double(), y[lo:hi].double()), st)
+        loss.backward()
+        return float(loss.detach()), {k: v.grad for k, v in st.items()}
+
+    full_loss, full = grads(0, 4)
+    (la, a), (lb, b) = grads(0, 2), grads(2, 4)
+    assert abs(0.5 * (la + lb) - full_loss) < 1e-12 * abs(full_loss)
+    for k in full:
+        assert torch.allclose(0.5 * (a[k] + b[k]), full[k], rtol=1e-9, atol=1e-12), k
+    assert abs(float(oloss.remfx_loss(x, y)) - 0.5 * (float(oloss.remfx_loss(x[:2], y[:2])) + float(oloss.remfx_loss(x[2:], y[2:])))) < 1e-5
