@@ -18,8 +18,6 @@
 // rounding, not bit-for-bit.
 #include "tcn_internal.h"
 
-#include <cstring>
-
 namespace rfx {
 
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
@@ -473,6 +471,7 @@ int rfx_tcn_backward(rfx_tcn_t* h, const float* x, const float* out, const float
   const int C = h->cfg.channel_width, K = h->cfg.kernel_size, NBk = h->cfg.nblocks;
   const long long Lout = tcn_len_after(h, T, NBk);
   RFX_REQUIRE(B > 0 && Lout > 0, "input shorter than the receptive field");
+  RFX_REQUIRE(T < (1ll << 31) && B <= 65535, "T or B too large");
   RFX_REQUIRE(workspace_bytes >= rfx_tcn_train_workspace_bytes(h, B, T), "workspace too small (rfx_tcn_train_workspace_bytes)");
   RFX_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;

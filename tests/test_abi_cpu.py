@@ -72,3 +72,24 @@ def test_no_cpu_fallback():
     m = OpenUnmixModel()
     with pytest.raises(_lib.RfxError):
         m.sample(torch.zeros(1, 1, 8192))
+
+
+def test_tcn_training_path_refuses_cpu_tensors():
+    """With trainable parameters and autograd on, TCNModel.forward takes the training path (rfx_tcn_forward_train /
+    rfx_tcn_backward); like every product path it must refuse CPU tensors instead of computing somewhere else."""
+    import pytest
+    import torch
+
+    from remfx_b200._lib import RfxError
+    from remfx_b200.models import TCNModel
+
+    m = TCNModel(sample_rate=48000, num_bins=1025, ninputs=1, noutputs=1, nblocks=2, channel_width=64, kernel_size=7, stack_size=10,
+                 dilation_growth=2)
+    x = torch.zeros(1, 1, 2000)
+    assert any(p.requires_grad for p in m.parameters())
+    with pytest.raises(RfxError):
+        m((x, x))
+    with torch.no_grad(), pytest.raises(RfxError):
+        m((x, x))
+    with pytest.raises(ValueError):
+        m._sample_train(torch.zeros(1, 2, 2000))
