@@ -62,7 +62,46 @@ def main():
     _save("tcn_forward.npz", wseed=0, xseed=31, tseed=32, B=1, T=16384, wsum=weights.checksum(sdt),
           out=out.numpy(), loss=float(loss))
 
+    tcn_backward_golden(R)
     cnn14_golden(R)
+
+
+TCN_BWD = dict(wseed=41, xseed=43, rseed=44, B=2, T=3000, nblocks=3, width=64)
+
+
+def tcn_backward_inputs():
+    """Seeded inputs of the TCN gradient fixture: weights with every PReLU slope set to 1 (a kink-free network, so that
+    two fp32 implementations agree to rounding -- tests/test_gpu_tcn_backward.py explains), audio, and the weights r of
+    the objective sum(out * r)."""
+    c = TCN_BWD
+    sd = weights.tcn_state(c["wseed"], nblocks=c["nblocks"], width=c["width"])
+    for k in sd:
+        if k.endswith("relu.weight"):
+            sd[k] = torch.ones_like(sd[k])
+    x = weights.synth_audio(c["xseed"], c["B"], c["T"])
+    Lout = c["T"] - sum(6 * 2 ** (n % 10) for n in range(c["nblocks"]))
+    r = torch.randn(c["B"], 1, Lout, generator=torch.Generator().manual_seed(c["rseed"]))
+    return sd, x, r
+
+
+def reference_tcn_gradients(R, sd, x, r, nblocks, width):
+    """Parameter gradients of sum(out * r) through the UNCHANGED reference `TCNModel` (remfx/models.py:370-390 ->
+    remfx/tcn.py) under torch autograd -- what `loss.backward()` does to the network in the reference's training step."""
+    kw = dict(TCN_KW, nblocks=nblocks, channel_width=width)
+    tm = R.models.TCNModel(sample_rate=48000, num_bins=1025, **kw)
+    tm.load_state_dict(sd, strict=True)
+    tm.zero_grad()
+    out = tm.sample(x)
+    (out * r).sum().backward()
+    return out.detach(), {k: p.grad.detach().clone() for k, p in tm.named_parameters()}
+
+
+def tcn_backward_golden(R):
+    c = TCN_BWD
+    sd, x, r = tcn_backward_inputs()
+    out, grads = reference_tcn_gradients(R, sd, x, r, c["nblocks"], c["width"])
+    _save("tcn_backward.npz", wsum=weights.checksum(sd), out=out.numpy(), **{k: int(v) for k, v in c.items()},
+          **{"grad/" + k: g.numpy() for k, g in grads.items()})
 
 
 def cnn14_golden(R, n_chunks: int = 1024, T: int = 262144):
@@ -87,4 +126,10 @@ def cnn14_golden(R, n_chunks: int = 1024, T: int = 262144):
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+
+    if len(sys.argv) > 1 and sys.argv[1] == "tcn_backward":   # add this one fixture without regenerating the others
+        torch.set_flush_denormal(True)
+        tcn_backward_golden(refshim.ref_modules())
+    else:
+        main()

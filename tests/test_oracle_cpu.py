@@ -139,3 +139,42 @@ def test_training_loss_decomposes_over_data_parallel_shards():
     for k in full:
         assert torch.allclose(0.5 * (a[k] + b[k]), full[k], rtol=1e-9, atol=1e-12), k
     assert abs(float(oloss.remfx_loss(x, y)) - 0.5 * (float(oloss.remfx_loss(x[:2], y[:2])) + float(oloss.remfx_loss(x[2:], y[2:])))) < 1e-5
+
+
+def _oracle_tcn_grads(sd, x, r):
+    from oracle import tcn as otcn
+
+    st = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = otcn.sample(x, st)
+    (out * r).sum().backward()
+    return out.detach(), {k: v.grad for k, v in st.items()}
+
+
+def test_tcn_oracle_gradients_match_reference_golden():
+    """The gradient oracle of the TCN backward tests = torch autograd through oracle/tcn.py; pinned here against gradients
+    the UNCHANGED reference TCNModel produced under autograd (tests/golden/tcn_backward.npz, oracle/make_golden.py)."""
+    from tests.util import tcn_backward_case
+
+    sd, x, r, out_ref, g_ref, _ = tcn_backward_case(golden("tcn_backward.npz"))
+    out, g = _oracle_tcn_grads(sd, x, r)
+    assert relrms(out, out_ref) < 1e-6
+    assert set(g) == set(g_ref) and len(g) == 14
+    for k in g_ref:
+        assert relrms(g[k], g_ref[k]) < 1e-5, k
+
+
+@pytest.mark.skipif(not refshim.available(), reason="/root/reference not present (GPU box)")
+def test_tcn_oracle_gradients_match_live_reference_with_prelu_kinks():
+    """Same check with the reference's PReLU slopes, run live: the oracle issues the same torch ops as the reference, so even
+    the kink decisions agree and the gradients are equal to rounding."""
+    from oracle.make_golden import reference_tcn_gradients
+
+    sd = weights.tcn_state(45, nblocks=4, width=64)
+    x = weights.synth_audio(46, 2, 2500)
+    Lout = 2500 - sum(6 * 2 ** n for n in range(4))
+    r = torch.randn(2, 1, Lout, generator=torch.Generator().manual_seed(47))
+    out_ref, g_ref = reference_tcn_gradients(refshim.ref_modules(), sd, x, r, 4, 64)
+    out, g = _oracle_tcn_grads(sd, x, r)
+    assert relrms(out, out_ref) < 1e-6
+    for k in g_ref:
+        assert relrms(g[k], g_ref[k]) < 1e-5, k
