@@ -21,7 +21,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--T", type=int, default=262144)
+    ap.add_argument("--cpu-baseline", action="store_true",
+                    help="time the same step done by torch on the host cores instead (oracle network under autograd + oracle loss + "
+                         "clip_grad_norm_ + torch.optim.AdamW), on --cpu-T samples per item; no GPU needed")
+    ap.add_argument("--cpu-T", type=int, default=32768)
     a = ap.parse_args()
+    if a.cpu_baseline:
+        return cpu_baseline(a)
     from oracle import weights  # seeded synthetic weights / audio only; nothing is computed by the oracle here
     from remfx_b200.models import TCNModel
     from remfx_b200.optim import configure_optimizers
@@ -67,6 +73,38 @@ def main():
         "algorithmic_tflops": 3 * fwd_tflop / (total * 1e-3), "out_length": L, "losses": losses,
         "grad_norm_last": float(opt.total_norm), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
         "steps": a.steps, "warmup": a.warmup}))
+
+
+def cpu_baseline(a):
+    """The reference's way of doing the step (torch autograd on the CPU; oracle/tcn.py issues the same torch ops as
+    remfx/tcn.py), on a bounded sample: audio-seconds of OUTPUT-producing input per second of step time."""
+    import time
+
+    from oracle import tcn as otcn
+    from oracle import weights
+
+    torch.set_flush_denormal(True)
+    sd = {k: v.clone().requires_grad_(True) for k, v in weights.tcn_state(0).items()}
+    params = list(sd.values())
+    opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.95, 0.999), eps=1e-6, weight_decay=1e-3)
+    x = weights.synth_audio(12345, a.batch, a.cpu_T)
+    t = weights.synth_audio(54321, a.batch, a.cpu_T)
+    times, losses = [], []
+    for _ in range(max(1, min(a.steps, 3))):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss, _ = otcn.forward((x, t), sd)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 10.0)
+        opt.step()
+        times.append(time.perf_counter() - t0)
+        losses.append(float(loss.detach()))
+    best = min(times)
+    print(json.dumps({
+        "workload": f"TCN training step on the host CPU (torch autograd through the oracle), batch {a.batch}x{a.cpu_T}",
+        "seconds_per_step": best, "audio_s_per_s": a.batch * a.cpu_T / 48000.0 / best, "cores": torch.get_num_threads(),
+        "cpu_count": os.cpu_count(), "losses": losses, "kind": "port",
+        "sample": f"{a.batch}x{a.cpu_T} samples per step (receptive field 12277), best of {len(times)}"}))
 
 
 if __name__ == "__main__":
