@@ -93,3 +93,37 @@ def test_tcn_training_path_refuses_cpu_tensors():
         m((x, x))
     with pytest.raises(ValueError):
         m._sample_train(torch.zeros(1, 2, 2000))
+
+
+def test_tcn_training_abi_host_side_contract():
+    """Host-only parts of the TCN training entry points (no kernel runs): workspace size formula, launch
+    count, and loud refusal of an un-finalized handle."""
+    import ctypes as C
+
+    from remfx_b200 import _lib
+
+    L = _lib.lib()
+    cfg = _lib.TcnConfig(1, 1, 20, 256, 7, 10, 2, 0)
+    h = C.c_void_p()
+    _lib.check(L.rfx_tcn_create(C.byref(cfg), C.byref(h)), "rfx_tcn_create")
+    try:
+        B, T = 1, 262144
+        L1 = T - 6
+        plane = -(-(B * L1 * 256 * 2) // 256) * 256
+        f32 = -(-(B * L1 * 256 * 4) // 256) * 256
+        want = 20 * 2 * plane + 3 * f32 + 4 * plane + 8 * 256 * 256 * 4
+        assert L.rfx_tcn_train_workspace_bytes(h, B, T) == want
+        assert 6.2 < want / 2**30 < 6.3                                   # "6.4 GB per chunk" with parameters and loss buffers
+        assert L.rfx_tcn_train_workspace_bytes(h, B, 12000) == 0          # shorter than the receptive field (12277)
+        assert L.rfx_tcn_workspace_bytes(h, B, T) == 4 * plane            # inference: two ping-pong buffers
+        assert L.rfx_tcn_backward_launches_per_call(h) == 2 + 5 * 19
+        dummy = C.c_void_p(256)
+        keys = (C.c_char_p * 1)(b"output.bias")
+        ptrs = (C.c_void_p * 1)(256)
+        rc = L.rfx_tcn_backward(h, dummy, dummy, dummy, B, T, keys, ptrs, 1, dummy, want, None)
+        assert rc == 2 and b"finalize" in L.rfx_last_error()
+        rc = L.rfx_tcn_forward_train(h, dummy, B, T, dummy, dummy, want, None)
+        assert rc == 2 and b"finalize" in L.rfx_last_error()
+        assert L.rfx_tcn_set_wgrad_impl(7) == 2 and L.rfx_tcn_set_wgrad_impl(0) == 0
+    finally:
+        L.rfx_tcn_destroy(h)
