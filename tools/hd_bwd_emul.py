@@ -1,6 +1,7 @@
-"""Development aid for the Hybrid-Demucs backward: the backward of a time-branch encoder layer and of a
-time-branch decoder layer written ONLY in terms of the primitives the CUDA path has (or will have), checked in fp64 against
-torch autograd through the torchaudio modules themselves (TA = torchaudio/models/_hdemucs.py).  Runs on the CPU:
+"""Development aid for the Hybrid-Demucs backward: the backward of a time-branch encoder layer, a
+time-branch decoder layer, the framed 2-layer BiLSTM (_BLSTM) and the local attention (_LocalState), written ONLY in terms of
+the primitives the CUDA path has (or will have), checked in fp64 against torch autograd through the torchaudio modules
+themselves (TA = torchaudio/models/_hdemucs.py).  Runs on the CPU:
 
     python tools/hd_bwd_emul.py
 
@@ -14,7 +15,11 @@ What it pins down for the kernels:
     its dgrad a 3-tap launch with offsets (+1, 0, -1) on the transposed repacked weights;
   * transposed conv k8 s4 (TA:243) == 2-tap conv (offsets 0, -1) producing N = 4 Cout viewed as (4X+4, Cout); its dgrad is a
     2-tap launch with offsets (0, +1) reading the output gradient through the same view (crop = zero rows);
-  * GroupNorm backward needs exactly two sums per (item, group): sum(dy gamma) and sum(dy gamma xhat).
+  * GroupNorm backward needs exactly two sums per (item, group): sum(dy gamma) and sum(dy gamma xhat);
+  * LSTM backward = one GEMM that recomputes every step's gates from the saved h, an elementwise scan for the cell state,
+    and a reverse-time chain with W_hh^T that has the forward recurrence kernel's structure; dW_hh / dW_ih are time
+    contractions; the 200 / 100 framing's adjoint is a scatter (stitch) and an overlap-add (unfold);
+  * local attention backward per (item, head) from q, k, content, decay and the recomputed softmax, diagonal masked.
 """
 import math
 import os
@@ -308,7 +313,202 @@ def check_decoder(norm: bool, last: bool):
     return max(errs.values())
 
 
+# ----------------------------------------------------------------------------------------------- _BLSTM (TA:742-788)
+def lstm_dir_fwd(Gx, Whh, reverse):
+    """One direction of one layer, the recurrence kernel's job: Gx (T, B, 4H) = W_ih x + b_ih + b_hh; gate order i, f, g, o.
+    Returns h (T, B, H) and what the backward keeps: h only (gates and c are recomputed)."""
+    T, B, H4 = Gx.shape
+    H = H4 // 4
+    h = Gx.new_zeros(B, H)
+    c = Gx.new_zeros(B, H)
+    hs = Gx.new_zeros(T, B, H)
+    order = range(T - 1, -1, -1) if reverse else range(T)
+    for t in order:
+        g = Gx[t] + h @ Whh.T
+        i, f, gg, o = torch.sigmoid(g[:, :H]), torch.sigmoid(g[:, H:2 * H]), torch.tanh(g[:, 2 * H:3 * H]), torch.sigmoid(g[:, 3 * H:])
+        c = f * c + i * gg
+        h = o * torch.tanh(c)
+        hs[t] = h
+    return hs
+
+
+def lstm_dir_bwd(Gx, Whh, hs, dhs, reverse):
+    """Backward of lstm_dir_fwd in three kernel-shaped steps:
+      1. gates for ALL steps at once: Gfull = Gx + h_prev W_hh^T  (one GEMM over the saved h, no recurrence);
+      2. the cell state by an elementwise scan c_t = f c_prev + i g  (no matrix product);
+      3. the reverse-time chain: dh_total = dh_t + W_hh^T dG_{t+1}, gate derivatives, dc carry  (matvec with W_hh^T per step:
+         the forward recurrence kernel's structure with the transposed matrix).
+    Returns dGx (T, B, 4H) -- from which dW_ih, db, dx follow as GEMMs / time contractions -- and dW_hh = sum_t dG_t (x) h_prev."""
+    T, B, H4 = Gx.shape
+    H = H4 // 4
+    step = -1 if reverse else 1
+    h_prev = torch.zeros_like(hs)
+    if reverse:
+        h_prev[:-1] = hs[1:]
+    else:
+        h_prev[1:] = hs[:-1]
+    Gfull = Gx + h_prev @ Whh.T                                                         # step 1
+    i, f = torch.sigmoid(Gfull[..., :H]), torch.sigmoid(Gfull[..., H:2 * H])
+    gg, o = torch.tanh(Gfull[..., 2 * H:3 * H]), torch.sigmoid(Gfull[..., 3 * H:])
+    cs = torch.zeros_like(hs)                                                          # step 2
+    c = Gx.new_zeros(B, H)
+    order = list(range(T - 1, -1, -1) if reverse else range(T))
+    for t in order:
+        c = f[t] * c + i[t] * gg[t]
+        cs[t] = c
+    dGx = torch.zeros_like(Gx)                                                         # step 3
+    dh_next = Gx.new_zeros(B, H)
+    dc = Gx.new_zeros(B, H)
+    for t in reversed(order):
+        dh = dhs[t] + dh_next
+        tc = torch.tanh(cs[t])
+        c_prev = cs[t - step] if 0 <= t - step < T else torch.zeros_like(dc)
+        dc = dc + dh * o[t] * (1 - tc * tc)
+        dG = torch.cat([dc * gg[t] * i[t] * (1 - i[t]), dc * c_prev * f[t] * (1 - f[t]), dc * i[t] * (1 - gg[t] * gg[t]),
+                        dh * tc * o[t] * (1 - o[t])], dim=-1)
+        dGx[t] = dG
+        dh_next = dG @ Whh
+        dc = dc * f[t]
+    dWhh = torch.einsum("tbg,tbh->gh", dGx, h_prev)                                    # time contraction
+    return dGx, dWhh
+
+
+def check_blstm():
+    from torchaudio.models._hdemucs import _BLSTM
+
+    torch.manual_seed(2)
+    H, B, T = 6, 2, 230                                                                # T > 200: the framed path (width 200, stride 100)
+    mod = _BLSTM(H, layers=2, skip=True)
+    x = torch.randn(B, H, T, requires_grad=True)
+    y = mod(x)
+    r = torch.randn_like(y)
+    (y * r).sum().backward()
+    P = {k: v.detach() for k, v in mod.lstm.named_parameters()}
+
+    # ---- forward: frames (B * nframes, width) rows in time-major (T, Bf, H) form
+    width, stride = 200, 100
+    nframes = math.ceil(T / stride)
+    pad_len = (nframes - 1) * stride + width
+    xp = F.pad(x.detach(), (0, pad_len - T))
+    fr = torch.stack([xp[:, :, k * stride:k * stride + width] for k in range(nframes)], dim=1)      # (B, nf, H, width)
+    inp = fr.reshape(B * nframes, H, width).permute(2, 0, 1).contiguous()                           # (width, Bf, H)
+    acts = [inp]
+    saved = []
+    for layer in range(2):
+        outs = []
+        for d, suf in enumerate(["", "_reverse"]):
+            Wih, Whh = P[f"weight_ih_l{layer}{suf}"], P[f"weight_hh_l{layer}{suf}"]
+            Gx = acts[-1] @ Wih.T + P[f"bias_ih_l{layer}{suf}"] + P[f"bias_hh_l{layer}{suf}"]
+            hs = lstm_dir_fwd(Gx, Whh, reverse=bool(d))
+            outs.append(hs)
+            saved.append((Gx, hs))
+        acts.append(torch.cat(outs, dim=-1))
+    lin = acts[-1] @ mod.linear.weight.detach().T + mod.linear.bias.detach()                        # (width, Bf, H)
+    frames = lin.permute(1, 2, 0).reshape(B, nframes, H, width)
+    limit = stride // 2
+    pieces = [frames[:, k, :, (0 if k == 0 else limit):(width if k == nframes - 1 else width - limit)] for k in range(nframes)]
+    out = torch.cat(pieces, -1)[..., :T] + x.detach()
+    print(f"blstm forward   {rel(out, y.detach()):.1e}")
+
+    # ---- backward
+    errs = {}
+    g = r                                                                                           # (B, H, T)
+    gfr = torch.zeros(B, nframes, H, width)
+    pos = 0
+    for k in range(nframes):                                                                        # adjoint of the stitching: scatter
+        lo, hi = (0 if k == 0 else limit), (width if k == nframes - 1 else width - limit)
+        n = min(hi - lo, T - pos)
+        if n > 0:
+            gfr[:, k, :, lo:lo + n] = g[..., pos:pos + n]
+        pos += hi - lo
+    glin = gfr.reshape(B * nframes, H, width).permute(2, 0, 1)                                      # (width, Bf, H)
+    errs["linear.weight"] = rel(torch.einsum("tbo,tbi->oi", glin, acts[-1]), mod.linear.weight.grad)
+    errs["linear.bias"] = rel(glin.sum(dim=(0, 1)), mod.linear.bias.grad)
+    gact = glin @ mod.linear.weight.detach()
+    for layer in (1, 0):
+        gin = torch.zeros_like(acts[layer])
+        for d, suf in enumerate(["", "_reverse"]):
+            Wih, Whh = P[f"weight_ih_l{layer}{suf}"], P[f"weight_hh_l{layer}{suf}"]
+            Gx, hs = saved[2 * layer + d]
+            dGx, dWhh = lstm_dir_bwd(Gx, Whh, hs, gact[..., d * H:(d + 1) * H], reverse=bool(d))
+            G = dict(mod.lstm.named_parameters())
+            errs[f"l{layer}{suf}"] = max(rel(dWhh, G[f"weight_hh_l{layer}{suf}"].grad),
+                                         rel(torch.einsum("tbg,tbi->gi", dGx, acts[layer]), G[f"weight_ih_l{layer}{suf}"].grad),
+                                         rel(dGx.sum(dim=(0, 1)), G[f"bias_ih_l{layer}{suf}"].grad),
+                                         rel(dGx.sum(dim=(0, 1)), G[f"bias_hh_l{layer}{suf}"].grad))
+            gin = gin + dGx @ Wih
+        gact = gin
+    gfr_in = gact.permute(1, 2, 0).reshape(B, nframes, H, width)
+    dxp = torch.zeros(B, H, pad_len)
+    for k in range(nframes):                                                                        # adjoint of _unfold: overlap-add
+        dxp[:, :, k * stride:k * stride + width] += gfr_in[:, k]
+    dx = dxp[..., :T] + r                                                                           # + skip
+    errs["input"] = rel(dx, x.grad)
+    print(f"blstm backward  max {max(errs.values()):.1e}   " + ", ".join(f"{k} {v:.0e}" for k, v in errs.items()))
+    return max(errs.values())
+
+
+# ----------------------------------------------------------------------------------------------- _LocalState (TA:822-857)
+def check_local_state():
+    from torchaudio.models._hdemucs import _LocalState
+
+    torch.manual_seed(3)
+    C, heads, nd, B, T = 8, 4, 4, 2, 24
+    mod = _LocalState(C, heads=heads, ndecay=nd)
+    for p in mod.parameters():
+        p.data.add_(0.2 * torch.randn_like(p))
+    x = torch.randn(B, C, T, requires_grad=True)
+    y = mod(x)
+    r = torch.randn_like(y)
+    (y * r).sum().backward()
+
+    xl = x.detach().permute(0, 2, 1)                                         # (B, T, C)
+    lin = lambda m: xl @ m.weight.detach()[:, :, 0].T + m.bias.detach()      # 1x1 convs = the projection GEMMs
+    q, k, ct, dr = lin(mod.query), lin(mod.key), lin(mod.content), lin(mod.query_decay)
+    dh = C // heads
+    idx = torch.arange(T, dtype=x.dtype)
+    dist = (idx[:, None] - idx[None, :]).abs()                               # [t (key), s (query)]
+    kern = -torch.arange(1, nd + 1, dtype=x.dtype).view(-1, 1, 1) * dist / math.sqrt(nd)     # (f, t, s)
+    res = torch.zeros(B, T, C)
+    saved = {}
+    for b in range(B):
+        for h in range(heads):                                               # one CTA per (item, head): everything below lives in smem
+            qh, kh, ch = q[b, :, h * dh:(h + 1) * dh], k[b, :, h * dh:(h + 1) * dh], ct[b, :, h * dh:(h + 1) * dh]       # (T, dh)
+            sg = torch.sigmoid(dr[b, :, h * nd:(h + 1) * nd])                # (s, f)
+            dots = kh @ qh.T / math.sqrt(dh) + torch.einsum("fts,sf->ts", kern, sg / 2)
+            dots.fill_diagonal_(-100.0)
+            W = torch.softmax(dots, dim=0)                                   # over keys t
+            res[b, :, h * dh:(h + 1) * dh] = W.T @ ch                        # result[s, c] = sum_t W[t, s] content[t, c]
+            saved[b, h] = (qh, kh, ch, sg, W)
+    out = xl + res @ mod.proj.weight.detach()[:, :, 0].T + mod.proj.bias.detach()
+    print(f"local_state forward   {rel(out, y.detach().permute(0, 2, 1)):.1e}")
+
+    g = r.permute(0, 2, 1)
+    errs = {"proj.weight": rel(torch.einsum("bto,bti->oi", g, res), mod.proj.weight.grad[:, :, 0]), "proj.bias": rel(g.sum(dim=(0, 1)), mod.proj.bias.grad)}
+    gres = g @ mod.proj.weight.detach()[:, :, 0]
+    gq, gk, gc, gd = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(ct), torch.zeros_like(dr)
+    for b in range(B):
+        for h in range(heads):
+            qh, kh, ch, sg, W = saved[b, h]
+            gr_ = gres[b, :, h * dh:(h + 1) * dh]                            # (s, c)
+            gc[b, :, h * dh:(h + 1) * dh] = W @ gr_                          # dcontent[t, c] = sum_s W[t, s] dres[s, c]
+            dW = ch @ gr_.T                                                  # [t, s]
+            dd = W * (dW - (W * dW).sum(dim=0, keepdim=True))                # softmax backward over t
+            dd.fill_diagonal_(0.0)                                           # masked_fill: no gradient through the diagonal
+            gk[b, :, h * dh:(h + 1) * dh] = dd @ qh / math.sqrt(dh)
+            gq[b, :, h * dh:(h + 1) * dh] = dd.T @ kh / math.sqrt(dh)
+            gd[b, :, h * nd:(h + 1) * nd] = torch.einsum("ts,fts->sf", dd, kern) * sg * (1 - sg) / 2
+    gx = g.clone()
+    for name, m, gg in (("query", mod.query, gq), ("key", mod.key, gk), ("content", mod.content, gc), ("query_decay", mod.query_decay, gd)):
+        errs[name] = max(rel(torch.einsum("bto,bti->oi", gg, xl), m.weight.grad[:, :, 0]), rel(gg.sum(dim=(0, 1)), m.bias.grad))
+        gx = gx + gg @ m.weight.detach()[:, :, 0]
+    errs["input"] = rel(gx, x.grad.permute(0, 2, 1))
+    print(f"local_state backward  max {max(errs.values()):.1e}   " + ", ".join(f"{k} {v:.0e}" for k, v in errs.items()))
+    return max(errs.values())
+
+
 if __name__ == "__main__":
-    worst = max(check_encoder(False), check_encoder(True), check_decoder(False, False), check_decoder(True, False), check_decoder(False, True))
+    worst = max(check_encoder(False), check_encoder(True), check_decoder(False, False), check_decoder(True, False), check_decoder(False, True),
+                check_blstm(), check_local_state())
     print("worst relative error", f"{worst:.1e}")
     sys.exit(0 if worst < 1e-10 else 1)
