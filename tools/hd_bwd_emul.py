@@ -1,5 +1,6 @@
 """Development aid for the Hybrid-Demucs backward: the backward of a time-branch encoder layer, a
-time-branch decoder layer, the framed 2-layer BiLSTM (_BLSTM) and the local attention (_LocalState), written ONLY in terms of
+time-branch decoder layer, the framed 2-layer BiLSTM (_BLSTM), the local attention (_LocalState) and the spectral front / back
+end (_spec / _ispec), written ONLY in terms of
 the primitives the CUDA path has (or will have), checked in fp64 against torch autograd through the torchaudio modules
 themselves (TA = torchaudio/models/_hdemucs.py).  Runs on the CPU:
 
@@ -19,7 +20,9 @@ What it pins down for the kernels:
   * LSTM backward = one GEMM that recomputes every step's gates from the saved h, an elementwise scan for the cell state,
     and a reverse-time chain with W_hh^T that has the forward recurrence kernel's structure; dW_hh / dW_ih are time
     contractions; the 200 / 100 framing's adjoint is a scatter (stitch) and an overlap-add (unfold);
-  * local attention backward per (item, head) from q, k, content, decay and the recomputed softmax, diagonal masked.
+  * local attention backward per (item, head) from q, k, content, decay and the recomputed softmax, diagonal masked;
+  * `_spec` backward = adjoint rfft of the kept frames, overlap-add into the once-reflected signal, reflection folded back;
+    `_ispec` backward = a forward STFT of (g / envelope) with a per-bin factor c_k / sqrt(N) (c_0 = 1, else 2).
 """
 import math
 import os
@@ -507,8 +510,79 @@ def check_local_state():
     return max(errs.values())
 
 
+# ----------------------------------------------------------------------------------------------- _spec / _ispec (TA:465-497)
+def check_spec_adjoints():
+    """Backward of the spectral front / back end in terms of the STFT-family kernels:
+      * d/dx of `_spec`  = window / sqrt(N) * adjoint-rfft of the kept frames' gradients, overlap-added into the ONCE-reflected
+        signal (the kept frames 2 .. le+1 never touch torch.stft's own centre padding) and folded back over the reflection;
+      * d/dZ of `_ispec` = c_k / sqrt(N) * rfft(window * (g / envelope)) on the kept frames and bins, c_0 = 1, c_k = 2:
+        an ordinary forward STFT launch with a per-bin factor."""
+    from torchaudio.models._hdemucs import _ispectro, _spectro
+
+    torch.manual_seed(4)
+    N, hl, B, L = 64, 16, 2, 200                                         # scaled-down nfft 4096 / hop 1024; L not a hop multiple
+    le = math.ceil(L / hl)
+    pad = hl // 2 * 3
+    win = torch.hann_window(N)
+    n = torch.arange(N, dtype=torch.float64)
+    kk = torch.arange(N // 2, dtype=torch.float64)
+    cos, sin = torch.cos(2 * math.pi * kk[:, None] * n[None, :] / N), torch.sin(2 * math.pi * kk[:, None] * n[None, :] / N)   # (k, n)
+
+    # ---- _spec
+    x = torch.randn(B, L, requires_grad=True)
+    right = pad + le * hl - L
+    xp = F.pad(x[:, None], (pad, right), mode="reflect")[:, 0]
+    z = _spectro(xp, N, hl)[..., :-1, :][..., 2:2 + le]                  # (B, N/2, le) complex
+    zr = torch.view_as_real(z)
+    r = torch.randn_like(zr)
+    (zr * r).sum().backward()
+    Lp = xp.shape[-1]
+    gxp = torch.zeros(B, Lp)
+    for t in range(le):                                                  # kept frame t covers xp[t hl, t hl + N)
+        gfr = (r[:, :, t, 0] @ cos - r[:, :, t, 1] @ sin) * win / math.sqrt(N)
+        gxp[:, t * hl:t * hl + N] += gfr
+    gx = gxp[:, pad:pad + L].clone()                                     # fold the reflections back: xp[pad - j] = x[j], xp[pad + L - 1 + j] = x[L - 1 - j]
+    for j in range(1, pad + 1):
+        gx[:, j] += gxp[:, pad - j]
+    for j in range(1, right + 1):
+        gx[:, L - 1 - j] += gxp[:, pad + L - 1 + j]
+    e_spec = rel(gx, x.grad)
+
+    # ---- _ispec
+    zin = torch.randn(B, N // 2, le, 2, requires_grad=True)
+    zc = torch.view_as_complex(zin)
+    zc = F.pad(F.pad(zc, [0, 0, 0, 1]), [2, 2])
+    lfull = hl * le + 2 * pad
+    y = _ispectro(zc, hl, length=lfull)[..., pad:pad + L]
+    ry = torch.randn_like(y)
+    (y * ry).sum().backward()
+    nfr = le + 4
+    env = torch.zeros((nfr - 1) * hl + N)
+    for f in range(nfr):
+        env[f * hl:f * hl + N] += win * win
+    env = env[N // 2:N // 2 + lfull]                                      # centre trim
+    gfull = torch.zeros(B, lfull)
+    gfull[:, pad:pad + L] = ry
+    gq = gfull / env
+    gz = torch.zeros(B, N // 2, le, 2)
+    ck = torch.full((N // 2,), 2.0)
+    ck[0] = 1.0
+    for t in range(le):
+        f = t + 2                                                        # frame f covers trimmed positions [f hl - N/2, f hl + N/2)
+        lo = f * hl - N // 2
+        seg = torch.zeros(B, N)
+        a, b_ = max(lo, 0), min(lo + N, lfull)
+        seg[:, a - lo:b_ - lo] = gq[:, a:b_]
+        seg = seg * win
+        gz[:, :, t, 0] = ck / math.sqrt(N) * (seg @ cos.T)
+        gz[:, :, t, 1] = -ck / math.sqrt(N) * (seg @ sin.T)
+    e_ispec = rel(gz, zin.grad)
+    print(f"spec backward {e_spec:.1e}   ispec backward {e_ispec:.1e}")
+    return max(e_spec, e_ispec)
+
+
 if __name__ == "__main__":
     worst = max(check_encoder(False), check_encoder(True), check_decoder(False, False), check_decoder(True, False), check_decoder(False, True),
-                check_blstm(), check_local_state())
+                check_blstm(), check_local_state(), check_spec_adjoints())
     print("worst relative error", f"{worst:.1e}")
     sys.exit(0 if worst < 1e-10 else 1)
