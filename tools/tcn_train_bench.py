@@ -1,6 +1,7 @@
 """TCN training step at the benchmark size: forward (kept activations) + MRSTFT/L1 loss + backward + clip + AdamW.
 
     python tools/tcn_train_bench.py [--batch 1] [--steps 5] [--warmup 2] [--T 262144]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/tcn_train_bench.py ...
 
 Prints one JSON line: ms per stage (CUDA events on the launching stream), audio-seconds/s of the whole step, algorithmic
 TFLOP/s (3 x the forward's 5.136 TFLOP per chunk: forward, input gradient, weight gradient; the recomputed pre-activations
@@ -32,14 +33,22 @@ def main():
     from remfx_b200.models import TCNModel
     from remfx_b200.optim import configure_optimizers
 
+    # data parallel: one process per GPU under torch.distributed.run; every rank trains on its own shard (weak scaling) and
+    # FusedAdamW.step() runs the one gradient all-reduce of the step over NCCL
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
     m = TCNModel(sample_rate=48000, num_bins=1025, ninputs=1, noutputs=1, nblocks=20, channel_growth=0, channel_width=256,
                  kernel_size=7, stack_size=10, dilation_growth=2, condition=False, latent_dim=2, norm_type="identity", causal=False,
                  estimate_loudness=False)
     m.load_state_dict(weights.tcn_state(0), strict=True)
     m = m.cuda()
     opt = configure_optimizers(m, max_steps=1000)["optimizer"]
-    x = weights.synth_audio(12345, a.batch, a.T).cuda()
-    t = weights.synth_audio(54321, a.batch, a.T).cuda()
+    x = weights.synth_audio(12345 + rank, a.batch, a.T).cuda()
+    t = weights.synth_audio(54321 + rank, a.batch, a.T).cuda()
     names = ["forward", "loss+backward", "optimizer"]
     acc = [0.0] * 3
     losses = []
@@ -63,12 +72,23 @@ def main():
             for i in range(3):
                 acc[i] += ev[i].elapsed_time(ev[i + 1])
     ms = [v / a.steps for v in acc]
+    if world > 1:
+        import torch.distributed as dist
+
+        tms = torch.tensor(ms, device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)   # the step is as slow as its slowest rank
+        ms = [float(v) for v in tms]
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
     total = sum(ms)
-    audio_s = a.batch * a.T / 48000.0
+    audio_s = world * a.batch * a.T / 48000.0
     L = m.out_length(a.T)
-    fwd_tflop = 5.1355 * a.batch * (a.T / 262144.0)
+    fwd_tflop = 5.1355 * world * a.batch * (a.T / 262144.0)
     print(json.dumps({
-        "workload": f"TCN training step (forward_train + MRSTFT/100 L1 + backward + clip 10 + AdamW), batch {a.batch}x{a.T}",
+        "workload": f"TCN training step (forward_train + MRSTFT/100 L1 + backward + clip 10 + AdamW), batch {a.batch}x{a.T} per GPU",
+        "n_gpus": world, "scaling": "weak", "collective": "one NCCL all-reduce of the flat fp32 gradient bucket per step" if world > 1 else "none",
         "ms_per_step": total, "stage_ms": dict(zip(names, ms)), "audio_s_per_s": audio_s / (total * 1e-3),
         "algorithmic_tflops": 3 * fwd_tflop / (total * 1e-3), "out_length": L, "losses": losses,
         "grad_norm_last": float(opt.total_norm), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
