@@ -62,3 +62,37 @@ def taps(x: torch.Tensor, m, names) -> Dict[str, torch.Tensor]:
     for h in hooks:
         h.remove()
     return out
+
+
+def grad_taps(x: torch.Tensor, target: torch.Tensor, m, names=(), objective=None):
+    """Backward oracle for the Hybrid-Demucs training step (remfx/models.py:317-321 under `loss.backward()`): runs the module
+    under torch autograd and returns
+      loss            the training loss MRSTFT + 100 L1 (oracle/loss.py) of the (B, 1, T) output, or `objective(out)` when given,
+      output          (B, 1, T),
+      param_grads     {state_dict key: gradient},
+      act_grads       {sub-module name: dLoss / d(that sub-module's output)}  for layer-by-layer parity of a backward pass
+                      (tensor hooks on the forward outputs of the named sub-modules; tuple outputs -> first element).
+    The module is left with zeroed gradients."""
+    from oracle import loss as oloss
+
+    act_grads, hooks = {}, []
+    mods = dict(m.named_modules())
+
+    def fwd_hook(name):
+        def hook(mod, inp, o):
+            t = o[0] if isinstance(o, tuple) else o
+            if t.requires_grad:
+                t.register_hook(lambda g, name=name: act_grads.__setitem__(name, g.detach().clone()))
+        return hook
+
+    for n in names:
+        hooks.append(mods[n].register_forward_hook(fwd_hook(n)))
+    m.zero_grad(set_to_none=True)
+    out = m(x).squeeze(1)
+    loss = objective(out) if objective is not None else oloss.remfx_loss(out, target)
+    loss.backward()
+    for h in hooks:
+        h.remove()
+    param_grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad(set_to_none=True)
+    return dict(loss=loss.detach(), output=out.detach(), param_grads=param_grads, act_grads=act_grads)

@@ -178,3 +178,46 @@ def test_tcn_oracle_gradients_match_live_reference_with_prelu_kinks():
     assert relrms(out, out_ref) < 1e-6
     for k in g_ref:
         assert relrms(g[k], g_ref[k]) < 1e-5, k
+
+
+def test_hdemucs_gradient_oracle_taps():
+    """Backward oracle of the Hybrid-Demucs step (oracle/hdemucs.py:grad_taps): every parameter receives a gradient, the
+    per-layer activation gradients have the layers' output shapes, and a directional finite difference of the training loss
+    agrees with <grad, direction> -- the harness the GPU backward will be checked against layer by layer."""
+    from oracle import hdemucs as ohd
+
+    m = ohd.build(seed=2, layerscale=0.1).double()
+    T = 16384
+    x = weights.synth_audio(70, 1, T).double()
+    y = weights.synth_audio(71, 1, T).double()
+    names = ["freq_encoder.0", "freq_encoder.4.dconv.layers.0.3", "freq_encoder.4.dconv.layers.0.4", "time_encoder.1", "freq_decoder.5",
+             "time_decoder.4"]
+    r = ohd.grad_taps(x, y, m, names)
+    assert r["output"].shape == (1, 1, T) and r["loss"].dim() == 0
+    # the "empty" last time-encoder layer only runs its conv (TA:163-164): its norm1 parameters are never used
+    assert {k for k, _ in m.named_parameters()} - set(r["param_grads"]) == {"time_encoder.4.norm1.weight", "time_encoder.4.norm1.bias"}
+    assert set(r["act_grads"]) == set(names)
+    fwd = ohd.taps(x, m, names)
+    for n in names:
+        assert r["act_grads"][n].shape == fwd[n].shape, n
+    # directional derivative along a seeded direction restricted to a few tensors of each kind
+    g = torch.Generator().manual_seed(9)
+    keys = ["freq_encoder.0.conv.weight", "freq_encoder.4.dconv.layers.0.3.lstm.weight_hh_l0", "freq_encoder.5.dconv.layers.1.4.query_decay.weight",
+            "time_decoder.2.conv_tr.weight", "freq_decoder.1.norm1.weight", "freq_emb.embedding.weight"]
+    params = dict(m.named_parameters())
+    dirs = {k: torch.randn(params[k].shape, generator=g, dtype=torch.float64) for k in keys}
+    from oracle import loss as oloss
+
+    def loss_at(eps):
+        with torch.no_grad():
+            for k in keys:
+                params[k].add_(eps * dirs[k])
+            val = float(oloss.remfx_loss(m(x).squeeze(1), y))
+            for k in keys:
+                params[k].sub_(eps * dirs[k])
+        return val
+
+    eps = 1e-7  # the weights are O(1e-2): a larger step leaves the linear regime (central difference, fp64)
+    fd = (loss_at(eps) - loss_at(-eps)) / (2 * eps)
+    an = sum(float((r["param_grads"][k] * dirs[k]).sum()) for k in keys)
+    assert abs(fd - an) < 1e-5 * max(1.0, abs(an)), (fd, an)
