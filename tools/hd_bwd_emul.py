@@ -581,8 +581,33 @@ def check_spec_adjoints():
     return max(e_spec, e_ispec)
 
 
+# ----------------------------------------------------------------------------------------------- per-item normalisation (TA:553-563, 624-631)
+def check_item_norm():
+    """x_n = (x - mu) / (1e-5 + sigma) on the way in (sigma unbiased, over the whole item) and out = v sigma + mu on the way out:
+    mu and sigma are functions of the input, so the input gradient collects three terms -- two fp64 reductions per item:
+      d_mu = sum(g_out) - sum(g_n) / (eps + sigma),   d_sigma = sum(g_out v) - sum(g_n (x - mu)) / (eps + sigma)^2,
+      dx = g_n / (eps + sigma) + d_mu / n + d_sigma (x - mu) / ((n - 1) sigma)."""
+    torch.manual_seed(5)
+    B, n = 2, 300
+    x = torch.randn(B, n, requires_grad=True)
+    v = torch.randn(B, n, requires_grad=True)                                # what the network hands to the de-normalisation
+    mu = x.mean(dim=1, keepdim=True)
+    sd = x.std(dim=1, keepdim=True)
+    xn = (x - mu) / (1e-5 + sd)
+    out = v * sd + mu
+    gn, go = torch.randn_like(xn), torch.randn_like(out)
+    ((xn * gn).sum() + (out * go).sum()).backward()
+    xd, vd, mud, sdd = x.detach(), v.detach(), mu.detach(), sd.detach()
+    d_mu = go.sum(dim=1, keepdim=True) - gn.sum(dim=1, keepdim=True) / (1e-5 + sdd)
+    d_sd = (go * vd).sum(dim=1, keepdim=True) - (gn * (xd - mud)).sum(dim=1, keepdim=True) / (1e-5 + sdd) ** 2
+    dx = gn / (1e-5 + sdd) + d_mu / n + d_sd * (xd - mud) / ((n - 1) * sdd)
+    e = max(rel(dx, x.grad), rel(go * sdd, v.grad))
+    print(f"item normalisation backward {e:.1e}")
+    return e
+
+
 if __name__ == "__main__":
     worst = max(check_encoder(False), check_encoder(True), check_decoder(False, False), check_decoder(True, False), check_decoder(False, True),
-                check_blstm(), check_local_state(), check_spec_adjoints())
+                check_blstm(), check_local_state(), check_spec_adjoints(), check_item_norm())
     print("worst relative error", f"{worst:.1e}")
     sys.exit(0 if worst < 1e-10 else 1)
