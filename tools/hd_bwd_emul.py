@@ -1,6 +1,6 @@
-"""Development aid for the Hybrid-Demucs backward: the backward of a time-branch encoder layer, a
-time-branch decoder layer, the framed 2-layer BiLSTM (_BLSTM), the local attention (_LocalState) and the spectral front / back
-end (_spec / _ispec), written ONLY in terms of
+"""Development aid for the Hybrid-Demucs backward: the backward of the time- and frequency-branch encoder
+and decoder layers, the framed 2-layer BiLSTM (_BLSTM), the local attention (_LocalState), the spectral front / back end
+(_spec / _ispec) and the per-item normalisation, written ONLY in terms of
 the primitives the CUDA path has (or will have), checked in fp64 against torch autograd through the torchaudio modules
 themselves (TA = torchaudio/models/_hdemucs.py).  Runs on the CPU:
 
@@ -316,6 +316,161 @@ def check_decoder(norm: bool, last: bool):
     return max(errs.values())
 
 
+# ----------------------------------------------------------------------------------------------- encoder layer (frequency branch)
+def check_freq_encoder():
+    """Frequency-branch encoder layer in the CUDA path's layout (B, T, Fr, C): the strided conv runs along Fr (the (Fr/4, 4C) view
+    is free because Fr and C are adjacent), the DConv branch runs along T on (b, fr) rows, GroupNorm(4) takes its statistics over
+    (C/4, Fr, T) per item.  Folding (B, T) resp. (B, Fr) into the batch reduces everything to the 1-D primitives above."""
+    from torchaudio.models._hdemucs import _HEncLayer
+
+    torch.manual_seed(6)
+    Ci, Co, B, Fr, T = 4, 8, 2, 16, 12
+    enc = _HEncLayer(Ci, Co, freq=True, norm_type="group_norm", norm_groups=4, dconv_kw=dict(depth=2, compress=4, init=0.3))
+    for p in enc.parameters():
+        p.data.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(B, Ci, Fr, T, requires_grad=True)
+    z = enc(x)                                                            # (B, Co, Fr/4, T)
+    r = torch.randn_like(z)
+    (z * r).sum().backward()
+    Fo = Fr // 4
+
+    def gn4_fwd(v, gamma, beta):                                          # v: (B, T, F, C): statistics over (T, F, C/4) per item
+        Bv, Tv, Fv, Cv = v.shape
+        y, sv = gn_fwd(v.reshape(Bv, Tv * Fv, Cv), 4, gamma, beta)
+        return y.reshape(v.shape), sv
+
+    def gn4_bwd(g, sv, gamma):
+        Bv, Tv, Fv, Cv = g.shape
+        dx, dgam, dbet = gn_bwd(g.reshape(Bv, Tv * Fv, Cv), sv, 4, gamma)
+        return dx.reshape(g.shape), dgam, dbet
+
+    xl = x.detach().permute(0, 3, 2, 1).contiguous()                      # (B, T, Fr, Ci)
+    W3 = pack_strided(enc.conv.weight.detach()[:, :, :, 0])
+    y0 = (conv_taps(xl.reshape(B * T, Fr // 4, 4 * Ci), W3, [-1, 0, 1], Fo) + enc.conv.bias.detach()).reshape(B, T, Fo, Co)
+    y1, sn1 = gn4_fwd(y0, enc.norm1.weight.detach(), enc.norm1.bias.detach())
+    y2 = F.gelu(y1)
+    rows = y2.permute(0, 2, 1, 3).reshape(B * Fo, T, Co)                  # (b, fr) rows along T
+    layers = dconv_params(enc.dconv)
+    y3r, sdc = dconv_fwd(rows, layers)
+    y3 = y3r.reshape(B, Fo, T, Co).permute(0, 2, 1, 3)
+    Wr = enc.rewrite.weight.detach()[:, :, 0, 0][:, None, :]             # (2Co, 1, Co)
+    z0 = (conv_taps(y3.reshape(B, T * Fo, Co), Wr, [0], T * Fo) + enc.rewrite.bias.detach()).reshape(B, T, Fo, 2 * Co)
+    z1, sn2 = gn4_fwd(z0, enc.norm2.weight.detach(), enc.norm2.bias.detach())
+    zz = glu_fwd(z1)
+    print(f"freq encoder forward   {rel(zz, z.detach().permute(0, 3, 2, 1)):.1e}")
+
+    errs = {}
+    g = glu_bwd(z1, r.permute(0, 3, 2, 1))
+    g, dg2, db2 = gn4_bwd(g, sn2, enc.norm2.weight.detach())
+    errs["norm2"] = max(rel(dg2, enc.norm2.weight.grad), rel(db2, enc.norm2.bias.grad))
+    gf = g.reshape(B, T * Fo, 2 * Co)
+    errs["rewrite"] = max(rel(conv_taps_wgrad(gf, y3.reshape(B, T * Fo, Co), [0])[:, 0], enc.rewrite.weight.grad[:, :, 0, 0]),
+                          rel(gf.sum(dim=(0, 1)), enc.rewrite.bias.grad))
+    g = conv_taps_dgrad(gf, Wr, [0], T * Fo).reshape(B, T, Fo, Co)
+    gr, gdc = dconv_bwd(g.permute(0, 2, 1, 3).reshape(B * Fo, T, Co), layers, sdc)
+    for d, gd in enumerate(gdc):
+        c1, n1, _, c2, n2, _, ls = enc.dconv.layers[d]
+        errs[f"dconv{d}"] = max(rel(gd["w1"].permute(0, 2, 1), c1.weight.grad), rel(gd["g1"], n1.weight.grad), rel(gd["w2"].permute(0, 2, 1), c2.weight.grad),
+                                rel(gd["g2"], n2.weight.grad), rel(gd["scale"], ls.scale.grad))
+    g = gr.reshape(B, Fo, T, Co).permute(0, 2, 1, 3)
+    g = gelu_bwd(y1, g)
+    g, dg1, db1 = gn4_bwd(g, sn1, enc.norm1.weight.detach())
+    errs["norm1"] = max(rel(dg1, enc.norm1.weight.grad), rel(db1, enc.norm1.bias.grad))
+    gb = g.reshape(B * T, Fo, Co)
+    errs["conv"] = max(rel(unpack_strided_grad(conv_taps_wgrad(gb, xl.reshape(B * T, Fr // 4, 4 * Ci), [-1, 0, 1]), Ci), enc.conv.weight.grad[:, :, :, 0]),
+                       rel(gb.sum(dim=(0, 1)), enc.conv.bias.grad))
+    dx = conv_taps_dgrad(gb, W3, [-1, 0, 1], Fr // 4).reshape(B, T, Fr, Ci)
+    errs["input"] = rel(dx, x.grad.permute(0, 3, 2, 1))
+    print(f"freq encoder backward  max {max(errs.values()):.1e}   " + ", ".join(f"{k} {v:.0e}" for k, v in errs.items()))
+    return max(errs.values())
+
+
+# ----------------------------------------------------------------------------------------------- decoder layer (frequency branch)
+def conv_taps2d(A, W, offs, Yout, Xout):
+    """2-D tap form of the engine: A (B, Y, X, K), offs = [(dy, dx)], out[b,y,x,n] = sum_tap A[b, y+dy, x+dx, :] . W[n, tap, :]."""
+    B, Yin, Xin, K = A.shape
+    out = A.new_zeros(B, Yout, Xout, W.shape[0])
+    for tap, (dy, dx) in enumerate(offs):
+        y0, y1, x0, x1 = max(0, -dy), min(Yout, Yin - dy), max(0, -dx), min(Xout, Xin - dx)
+        if y1 > y0 and x1 > x0:
+            out[:, y0:y1, x0:x1] += A[:, y0 + dy:y1 + dy, x0 + dx:x1 + dx] @ W[:, tap].T
+    return out
+
+
+def conv_taps2d_wgrad(G, A, offs):
+    B, Yout, Xout, N = G.shape
+    Yin, Xin, K = A.shape[1:]
+    dW = G.new_zeros(N, len(offs), K)
+    for tap, (dy, dx) in enumerate(offs):
+        y0, y1, x0, x1 = max(0, -dy), min(Yout, Yin - dy), max(0, -dx), min(Xout, Xin - dx)
+        if y1 > y0 and x1 > x0:
+            dW[:, tap] = torch.einsum("byxn,byxk->nk", G[:, y0:y1, x0:x1], A[:, y0 + dy:y1 + dy, x0 + dx:x1 + dx])
+    return dW
+
+
+def check_freq_decoder():
+    """Frequency-branch decoder layer, layout (B, T, Fr, C): 3x3 `rewrite` = 9 two-dimensional taps, GLU, transposed conv along Fr
+    as the 2-tap N = 4 Cout launch, GroupNorm over the UNcropped (Fr 4X+4) tensor, crop [2:-2] along Fr, GELU."""
+    from torchaudio.models._hdemucs import _HDecLayer
+
+    torch.manual_seed(7)
+    Ci, Co, B, X, T = 8, 4, 2, 4, 10
+    dec = _HDecLayer(Ci, Co, last=False, freq=True, norm_type="group_norm", norm_groups=4, context=1)
+    for p in dec.parameters():
+        p.data.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(B, Ci, X, T, requires_grad=True)
+    skip = torch.randn(B, Ci, X, T, requires_grad=True)
+    z, _ = dec(x, skip, 4 * X)
+    r = torch.randn_like(z)                                               # (B, Co, 4X, T)
+    (z * r).sum().backward()
+
+    def gn4_fwd(v, gamma, beta):
+        Bv, Tv, Fv, Cv = v.shape
+        y, sv = gn_fwd(v.reshape(Bv, Tv * Fv, Cv), 4, gamma, beta)
+        return y.reshape(v.shape), sv
+
+    def gn4_bwd(g, sv, gamma):
+        Bv, Tv, Fv, Cv = g.shape
+        dx, dgam, dbet = gn_bwd(g.reshape(Bv, Tv * Fv, Cv), sv, 4, gamma)
+        return dx.reshape(g.shape), dgam, dbet
+
+    a = (x + skip).detach().permute(0, 3, 2, 1).contiguous()              # (B, T, Fr, Ci): Y = T, X = Fr
+    offs = [(dt, df) for df in (-1, 0, 1) for dt in (-1, 0, 1)]            # Conv2d weight (2Ci, Ci, kF, kT): tap (df, dt)
+    wr = dec.rewrite.weight.detach()
+    Wr = torch.stack([wr[:, :, df + 1, dt + 1] for (dt, df) in offs], dim=1)   # (2Ci, 9, Ci)
+    y0 = conv_taps2d(a, Wr, offs, T, X) + dec.rewrite.bias.detach()
+    y1, sn1 = gn4_fwd(y0, dec.norm1.weight.detach(), dec.norm1.bias.detach())
+    y2 = glu_fwd(y1)
+    W2 = pack_transposed(dec.conv_tr.weight.detach()[:, :, :, 0])
+    u = (conv_taps(y2.reshape(B * T, X, Ci), W2, [0, -1], X + 1).reshape(B, T, 4 * X + 4, Co) + dec.conv_tr.bias.detach())
+    u1, sn2 = gn4_fwd(u, dec.norm2.weight.detach(), dec.norm2.bias.detach())
+    v = u1[:, :, 2:-2]
+    zz = F.gelu(v)
+    print(f"freq decoder forward   {rel(zz, z.detach().permute(0, 3, 2, 1)):.1e}")
+
+    errs = {}
+    g = gelu_bwd(v, r.permute(0, 3, 2, 1))
+    gfull = g.new_zeros(B, T, 4 * X + 4, Co)
+    gfull[:, :, 2:-2] = g
+    gfull, dg2, db2 = gn4_bwd(gfull, sn2, dec.norm2.weight.detach())
+    errs["norm2"] = max(rel(dg2, dec.norm2.weight.grad), rel(db2, dec.norm2.bias.grad))
+    gv = gfull.reshape(B * T, X + 1, 4 * Co)
+    errs["conv_tr"] = rel(unpack_transposed_grad(conv_taps_wgrad(gv, y2.reshape(B * T, X, Ci), [0, -1]), Co), dec.conv_tr.weight.grad[:, :, :, 0])
+    g = conv_taps_dgrad(gv, W2, [0, -1], X).reshape(B, T, X, Ci)
+    g = glu_bwd(y1, g)
+    g, dg1, db1 = gn4_bwd(g, sn1, dec.norm1.weight.detach())
+    errs["norm1"] = max(rel(dg1, dec.norm1.weight.grad), rel(db1, dec.norm1.bias.grad))
+    dWr = conv_taps2d_wgrad(g, a, offs)
+    dwr = torch.zeros_like(wr)
+    for tap, (dt, df) in enumerate(offs):
+        dwr[:, :, df + 1, dt + 1] = dWr[:, tap]
+    errs["rewrite"] = max(rel(dwr, dec.rewrite.weight.grad), rel(g.sum(dim=(0, 1, 2)), dec.rewrite.bias.grad))
+    dx = conv_taps2d(g, Wr.permute(2, 1, 0).contiguous(), [(-dt, -df) for (dt, df) in offs], T, X)   # dgrad: transposed weights, negated taps
+    errs["input"] = max(rel(dx, x.grad.permute(0, 3, 2, 1)), rel(dx, skip.grad.permute(0, 3, 2, 1)))
+    print(f"freq decoder backward  max {max(errs.values()):.1e}   " + ", ".join(f"{k} {v:.0e}" for k, v in errs.items()))
+    return max(errs.values())
+
+
 # ----------------------------------------------------------------------------------------------- _BLSTM (TA:742-788)
 def lstm_dir_fwd(Gx, Whh, reverse):
     """One direction of one layer, the recurrence kernel's job: Gx (T, B, 4H) = W_ih x + b_ih + b_hh; gate order i, f, g, o.
@@ -608,6 +763,6 @@ def check_item_norm():
 
 if __name__ == "__main__":
     worst = max(check_encoder(False), check_encoder(True), check_decoder(False, False), check_decoder(True, False), check_decoder(False, True),
-                check_blstm(), check_local_state(), check_spec_adjoints(), check_item_norm())
+                check_freq_encoder(), check_freq_decoder(), check_blstm(), check_local_state(), check_spec_adjoints(), check_item_norm())
     print("worst relative error", f"{worst:.1e}")
     sys.exit(0 if worst < 1e-10 else 1)
