@@ -63,6 +63,7 @@ def main():
           out=out.numpy(), loss=float(loss))
 
     tcn_backward_golden(R)
+    example_wav_golden(R)
     cnn14_golden(R)
 
 
@@ -104,6 +105,55 @@ def tcn_backward_golden(R):
           **{"grad/" + k: g.numpy() for k, g in grads.items()})
 
 
+EXAMPLE_DECIM = 16   # outputs are stored every 16th sample (rel-RMS on the subset); the input is stored whole
+EXAMPLE_TCN_T = 65536
+
+
+def example_input(pcm16) -> torch.Tensor:
+    """(1, 1, 262144) fp32 audio from the 16-bit fixture: the same expression in the generator and in every test."""
+    return (torch.from_numpy(pcm16.astype("float32")) / 32767.0).reshape(1, 1, -1)
+
+
+def example_wav_golden(R):
+    """Real audio (SURVEY 8d parity gates: "... + example.wav"): the reference repository's one audio file,
+    /root/reference/example.wav (48 kHz mono float32, exactly one 262144-sample chunk, RMS 0.101), quantised to 16-bit PCM so the
+    fixture stays small, run through the UNCHANGED reference modules with the seeded weights of the other fixtures:
+    Open-Unmix sample, TCN sample (first 65536 samples), Cnn14 probabilities / decisions, and torchaudio's HDemucs (oracle
+    of the Demucs wrapper).  Outputs are stored decimated by 16."""
+    from scipy.io import wavfile
+
+    from oracle import hdemucs as ohd
+
+    sr, wav = wavfile.read(os.path.join(refshim.REF_ROOT, "example.wav"))
+    assert sr == 48000 and wav.ndim == 1 and wav.shape[0] == 262144 and wav.dtype == np.float32
+    pcm16 = np.clip(np.round(wav * 32767.0), -32768, 32767).astype(np.int16)
+    x = example_input(pcm16)
+    D = EXAMPLE_DECIM
+    with torch.no_grad():
+        sdu = weights.umx_state(0)
+        um = R.models.OpenUnmixModel(n_fft=2048, hop_length=512, n_channels=1, alpha=0.3, sample_rate=48000)
+        um.load_state_dict(sdu, strict=True)
+        um.eval()
+        umx_out = um.sample(x)
+        sdt = weights.tcn_state(0)
+        tm = R.models.TCNModel(sample_rate=48000, num_bins=1025, **TCN_KW)
+        tm.load_state_dict(sdt, strict=True)
+        tm.eval()
+        tcn_out = tm.sample(x[..., :EXAMPLE_TCN_T])
+        sdc = weights.cnn14_state(0)
+        cm = R.classifier.Cnn14(num_classes=5, n_fft=2048, hop_length=512, n_mels=128, sample_rate=48000, model_sample_rate=48000,
+                                specaugment=True)
+        cm.load_state_dict(sdc, strict=True)
+        cm.eval()
+        probs = torch.hstack(cm(x))
+        hd_out = ohd.sample(x, ohd.build(0))
+    logits = torch.log(probs.double() / (1 - probs.double())).float()
+    _save("example_wav.npz", pcm16=pcm16, decim=D, tcn_T=EXAMPLE_TCN_T,
+          umx_wsum=weights.checksum(sdu), tcn_wsum=weights.checksum(sdt), cnn14_wsum=weights.checksum(sdc),
+          umx_out=umx_out[0, 0, ::D].numpy(), tcn_out=tcn_out[0, 0, ::D].numpy(), tcn_len=tcn_out.shape[-1],
+          hdemucs_out=hd_out[0, 0, ::D].numpy(), probs=probs.numpy(), logits=logits.numpy(), decisions=(probs > 0.5).numpy())
+
+
 def cnn14_golden(R, n_chunks: int = 1024, T: int = 262144):
     """Cnn14 (remfx/classifier.py:193-233, eval): logits + decisions of the reference on 1024 seeded diverse chunks
     (generated in 64 batches of 16 with seeds 1000..1063) -- the bit-exact per-effect decision gate of BASELINE.json."""
@@ -128,8 +178,8 @@ def cnn14_golden(R, n_chunks: int = 1024, T: int = 262144):
 if __name__ == "__main__":
     import sys
 
-    if len(sys.argv) > 1 and sys.argv[1] == "tcn_backward":   # add this one fixture without regenerating the others
+    if len(sys.argv) > 1 and sys.argv[1] in ("tcn_backward", "example_wav"):   # add one fixture without regenerating the others
         torch.set_flush_denormal(True)
-        tcn_backward_golden(refshim.ref_modules())
+        {"tcn_backward": tcn_backward_golden, "example_wav": example_wav_golden}[sys.argv[1]](refshim.ref_modules())
     else:
         main()

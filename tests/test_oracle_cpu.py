@@ -221,3 +221,26 @@ def test_hdemucs_gradient_oracle_taps():
     fd = (loss_at(eps) - loss_at(-eps)) / (2 * eps)
     an = sum(float((r["param_grads"][k] * dirs[k]).sum()) for k in keys)
     assert abs(fd - an) < 1e-5 * max(1.0, abs(an)), (fd, an)
+
+
+def test_oracles_match_reference_on_example_wav():
+    """Real audio: the oracle restatements against the unchanged reference modules' outputs on example.wav."""
+    from oracle import cnn14 as ocnn
+    from oracle import hdemucs as ohd
+    from tests.util import example_case
+
+    g = golden("example_wav.npz")
+    x, D = example_case(g)
+    assert abs(float(x.pow(2).mean().sqrt()) - 0.1012) < 1e-3      # the file's level (SURVEY 8d: RMS 0.101)
+    sdu = weights.umx_state(0)
+    assert abs(weights.checksum(sdu) - float(g["umx_wsum"])) < 1e-6 * abs(float(g["umx_wsum"]))
+    assert relrms(oumx.sample(x, sdu)[0, 0, ::D], torch.from_numpy(g["umx_out"])) < 1e-5
+    sdt = weights.tcn_state(0)
+    out = otcn.sample(x[..., :int(g["tcn_T"])], sdt)
+    assert out.shape[-1] == int(g["tcn_len"])
+    assert relrms(out[0, 0, ::D], torch.from_numpy(g["tcn_out"])) < 1e-5
+    sdc = weights.cnn14_state(0)
+    lg = ocnn.logits(x, sdc)
+    assert (lg - torch.from_numpy(g["logits"])).abs().max() < 1e-3
+    assert torch.equal(ocnn.decisions(x, sdc), torch.from_numpy(g["decisions"]).long())
+    assert relrms(ohd.sample(x, ohd.build(0))[0, 0, ::D], torch.from_numpy(g["hdemucs_out"])) < 1e-5

@@ -38,3 +38,10 @@ def tcn_backward_case(g):
     r = torch.randn(B, 1, out_ref.shape[-1], generator=torch.Generator().manual_seed(int(g["rseed"])))
     grads = {k[len("grad/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("grad/")}
     return sd, x, r, out_ref, grads, dict(nblocks=nblocks, channel_width=width)
+
+
+def example_case(g):
+    """tests/golden/example_wav.npz: the reference repository's example.wav at 16 bits -> (1, 1, 262144) fp32 audio, plus the
+    decimation step the stored outputs use (oracle/make_golden.py:example_wav_golden)."""
+    x = (torch.from_numpy(g["pcm16"].astype("float32")) / 32767.0).reshape(1, 1, -1)
+    return x, int(g["decim"])
