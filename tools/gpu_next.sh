@@ -3,7 +3,7 @@
 #   gpurun --timeout 900 -- 'bash tools/gpu_next.sh'
 mkdir -p gpurun_out
 # 1. the GPU tests that have not run on hardware yet (train-step harness, gradient golden), then the TCN files again
-for f in tests/test_gpu_zz_train_step.py tests/test_gpu_tcn_backward.py tests/test_gpu_tcn.py; do
+for f in tests/test_gpu_zz_example_wav.py tests/test_gpu_zz_train_step.py tests/test_gpu_tcn_backward.py tests/test_gpu_tcn.py; do
   n=$(basename $f .py)
   timeout 300 python -m pytest $f -m gpu -q --timeout 200 --no-header -p no:cacheprovider > gpurun_out/$n.log 2>&1
   echo "$n exit=$? $(tail -n 1 gpurun_out/$n.log)"
