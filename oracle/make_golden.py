@@ -64,6 +64,7 @@ def main():
 
     tcn_backward_golden(R)
     example_wav_golden(R)
+    chain_golden(R)
     cnn14_golden(R)
 
 
@@ -154,6 +155,45 @@ def example_wav_golden(R):
           hdemucs_out=hd_out[0, 0, ::D].numpy(), probs=probs.numpy(), logits=logits.numpy(), decisions=(probs > 0.5).numpy())
 
 
+CHAIN_ORDER = ["RandomPedalboardDistortion", "RandomPedalboardCompressor", "RandomPedalboardReverb", "RandomPedalboardChorus",
+               "RandomPedalboardDelay"]  # cfg/exp/remfx_detect.yaml:80-85
+CHAIN = dict(T=65536, B=4, xseed=77, yseed=78, member_seed0=50, decim=16)
+
+
+def reference_chain(R, x, y, member_seed0, use_all=False):
+    """The UNCHANGED `remfx.models.RemFXChainInference.forward` (remfx/models.py:52-108) with the unchanged Cnn14 as the
+    classifier and five unchanged Open-Unmix wrappers as the effect-specific members (member e = ALL_EFFECTS[i] carries
+    weights.umx_state(member_seed0 + i)); members are reached as `self.model[effect].model.sample`, like the Lightning
+    `RemFX` modules the reference stores."""
+    import types
+
+    names = [e.__name__ for e in R.models.ALL_EFFECTS]
+    members = {}
+    for i, e in enumerate(names):
+        m = R.models.OpenUnmixModel(n_fft=2048, hop_length=512, n_channels=1, alpha=0.3, sample_rate=48000)
+        m.load_state_dict(weights.umx_state(member_seed0 + i), strict=True)
+        members[e] = types.SimpleNamespace(model=m.eval())
+    cm = R.classifier.Cnn14(num_classes=5, n_fft=2048, hop_length=512, n_mels=128, sample_rate=48000, model_sample_rate=48000,
+                            specaugment=True)
+    cm.load_state_dict(weights.cnn14_state(0), strict=True)
+    cm.eval()
+    chain = R.models.RemFXChainInference(members, sample_rate=48000, num_bins=1025, effect_order=list(CHAIN_ORDER), classifier=cm,
+                                         use_all_effect_models=use_all)
+    with torch.no_grad():
+        loss, out = chain((x, y, None, None), 0)
+        labels = torch.where(torch.hstack(cm(x)) > 0.5, 1.0, 0.0)
+    return loss, out, labels, names
+
+
+def chain_golden(R):
+    c = CHAIN
+    x, y = weights.synth_diverse(c["xseed"], c["B"], c["T"]), weights.synth_audio(c["yseed"], c["B"], c["T"])
+    loss, out, labels, names = reference_chain(R, x, y, c["member_seed0"])
+    assert names == ["RandomPedalboardReverb", "RandomPedalboardChorus", "RandomPedalboardDelay", "RandomPedalboardDistortion",
+                     "RandomPedalboardCompressor"]   # remfx/effects.py:699-705: the label order the drop-in hard-codes
+    _save("chain_forward.npz", loss=float(loss), labels=labels.numpy(), out=out[:, 0, ::c["decim"]].numpy(), **{k: int(v) for k, v in c.items()})
+
+
 def cnn14_golden(R, n_chunks: int = 1024, T: int = 262144):
     """Cnn14 (remfx/classifier.py:193-233, eval): logits + decisions of the reference on 1024 seeded diverse chunks
     (generated in 64 batches of 16 with seeds 1000..1063) -- the bit-exact per-effect decision gate of BASELINE.json."""
@@ -178,8 +218,9 @@ def cnn14_golden(R, n_chunks: int = 1024, T: int = 262144):
 if __name__ == "__main__":
     import sys
 
-    if len(sys.argv) > 1 and sys.argv[1] in ("tcn_backward", "example_wav"):   # add one fixture without regenerating the others
+    one = {"tcn_backward": tcn_backward_golden, "example_wav": example_wav_golden, "chain": chain_golden}
+    if len(sys.argv) > 1 and sys.argv[1] in one:   # add one fixture without regenerating the others
         torch.set_flush_denormal(True)
-        {"tcn_backward": tcn_backward_golden, "example_wav": example_wav_golden}[sys.argv[1]](refshim.ref_modules())
+        one[sys.argv[1]](refshim.ref_modules())
     else:
         main()

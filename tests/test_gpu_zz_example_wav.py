@@ -73,3 +73,20 @@ def test_hybrid_demucs_on_example_wav(case):
     assert out.shape == (1, 1, 262144)
     err = relrms(out[0, 0, ::D], torch.from_numpy(g["hdemucs_out"]))
     assert err < TOL, err
+
+
+def test_chain_matches_reference_golden():
+    """Detect-then-remove cascade against the UNCHANGED RemFXChainInference.forward (tests/golden/chain_forward.npz; the same
+    inputs as tests/test_gpu_chain.py::test_chain_matches_oracle[False], whose oracle tests/test_oracle_cpu.py pins to this file)."""
+    from tests.test_gpu_chain import ORDER, _build
+
+    g = golden("chain_forward.npz")
+    T, B, D = int(g["T"]), int(g["B"]), int(g["decim"])
+    assert int(g["member_seed0"]) == 50   # what _build loads into the five members
+    _, _, members, clf, Chain = _build(T)
+    x, y = weights.synth_diverse(int(g["xseed"]), B, T), weights.synth_audio(int(g["yseed"]), B, T)
+    chain = Chain(members, 48000, 1025, ORDER, classifier=clf)
+    loss, out = chain((x.cuda(), y.cuda(), None, None), 0)
+    assert torch.equal(chain.last_labels.cpu(), torch.from_numpy(g["labels"]))
+    assert relrms(out[:, 0, ::D], torch.from_numpy(g["out"])) < TOL
+    assert abs(float(loss) - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))

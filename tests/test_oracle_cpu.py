@@ -244,3 +244,37 @@ def test_oracles_match_reference_on_example_wav():
     assert (lg - torch.from_numpy(g["logits"])).abs().max() < 1e-3
     assert torch.equal(ocnn.decisions(x, sdc), torch.from_numpy(g["decisions"]).long())
     assert relrms(ohd.sample(x, ohd.build(0))[0, 0, ::D], torch.from_numpy(g["hdemucs_out"])) < 1e-5
+
+
+def _oracle_chain(x, y, member_seed0, use_all=False):
+    from oracle import chain as ochain
+    from oracle import cnn14 as ocnn
+    from oracle.make_golden import CHAIN_ORDER
+
+    sds = {e: weights.umx_state(member_seed0 + i) for i, e in enumerate(ochain.ALL_EFFECTS)}
+    members = {e: (lambda sd: (lambda z: oumx.sample(z, sd)))(sd) for e, sd in sds.items()}
+    csd = weights.cnn14_state(0)
+    return ochain.forward(x, y, None, members, list(CHAIN_ORDER), classify=lambda z: torch.hstack(ocnn.forward(z, csd)), use_all=use_all)
+
+
+def test_chain_oracle_matches_reference_golden():
+    """oracle/chain.py against the UNCHANGED RemFXChainInference.forward (tests/golden/chain_forward.npz): detected labels,
+    per-item cascade in cfg order, loss."""
+    g = golden("chain_forward.npz")
+    x, y = weights.synth_diverse(int(g["xseed"]), int(g["B"]), int(g["T"])), weights.synth_audio(int(g["yseed"]), int(g["B"]), int(g["T"]))
+    loss, out, labels = _oracle_chain(x, y, int(g["member_seed0"]))
+    assert torch.equal(labels, torch.from_numpy(g["labels"]))
+    assert 0 < labels.sum() < labels.numel() and len({tuple(r.tolist()) for r in labels}) > 1   # the items take different paths
+    assert relrms(out[:, 0, ::int(g["decim"])], torch.from_numpy(g["out"])) < 1e-5
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+
+
+@pytest.mark.skipif(not refshim.available(), reason="/root/reference not present (GPU box)")
+def test_chain_oracle_matches_live_reference_use_all():
+    """`use_all_effect_models=True` (remfx/models.py:65-69) live against the reference: every member applied to every item."""
+    from oracle.make_golden import reference_chain
+
+    x, y = weights.synth_diverse(90, 2, 32768), weights.synth_audio(91, 2, 32768)
+    rloss, rout, _, _ = reference_chain(refshim.ref_modules(), x, y, 60, use_all=True)
+    loss, out, _ = _oracle_chain(x, y, 60, use_all=True)
+    assert relrms(out, rout) < 1e-5 and abs(float(loss) - float(rloss)) < 1e-5 * abs(float(rloss))
