@@ -116,3 +116,51 @@ def test_data_parallel_fit_step_gloo_world2(monkeypatch):
         p.join(120)
         assert p.exitcode == 0
     assert sorted(q.get(timeout=5) for _ in range(2)) == [(0, True), (1, True)]
+
+
+def test_common_step_matches_the_unchanged_reference_harness(monkeypatch):
+    """Live against `remfx.models.RemFX.common_step` (remfx/models.py:217-256) run through the shim (skipped where
+    /root/reference is absent): same stub network, the metric classes both sides use are the oracle restatements of auraloss --
+    logged names, the SISDR negation, the causal crop of the target and the returned loss must agree."""
+    from oracle import loss as oloss
+    from oracle import refshim
+
+    if not refshim.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    R = refshim.ref_modules()
+
+    class Short(_StubNet):   # output shorter than the target: exercises the crop
+        def forward(self, batch):
+            x, y = batch
+            out = self.conv(x)[..., 5:-4]
+            return (out - y[..., 8:-1]).abs().mean(), out
+
+    ref = R.models.RemFX(lr=1e-4, lr_beta1=0.95, lr_beta2=0.999, lr_eps=1e-6, lr_weight_decay=1e-3, sample_rate=48000, network=Short())
+    ref_logged = {}
+    ref.log = lambda name, value, *a, **k: ref_logged.__setitem__(name, float(value.detach()))
+    monkeypatch.setattr(T, "sisdr_loss", oloss.sisdr_loss)
+    monkeypatch.setattr(T, "mrstft_loss", oloss.mrstft)
+    mine = T.RemFX(1e-4, 0.95, 0.999, 1e-6, 1e-3, 48000, Short())
+    g = torch.Generator().manual_seed(11)
+    x, y = 0.1 * torch.randn(2, 1, 6000, generator=g), 0.1 * torch.randn(2, 1, 6000, generator=g)
+    for mode, method in (("train", "training_step"), ("valid", "validation_step"), ("test", "test_step")):
+        ref_logged.clear()
+        mine.logged.clear()
+        rl = getattr(ref, method)((x, y, None, None), 0)
+        ml = getattr(mine, method)((x, y, None, None), 0)
+        assert float(ml.detach()) == pytest.approx(float(rl.detach()), rel=1e-6)
+        assert set(mine.logged) == set(ref_logged) == {f"{mode}_loss", f"{mode}_SISDR", f"{mode}_STFT", "Input_SISDR", "Input_STFT"}
+        for k, v in ref_logged.items():
+            assert float(mine.logged[k]) == pytest.approx(v, rel=1e-6), (mode, k)
+    # configure_optimizers (remfx/models.py:185-206): same hyper-parameters, schedule and return structure
+    ref.trainer = type("Trainer", (), {"max_steps": 50})()
+    mine.trainer = ref.trainer
+    rc, mc = ref.configure_optimizers(), mine.configure_optimizers()
+    assert set(rc) == set(mc) and {k: v for k, v in rc["lr_scheduler"].items() if k != "scheduler"} == \
+        {k: v for k, v in mc["lr_scheduler"].items() if k != "scheduler"}
+    rg, mg = rc["optimizer"].param_groups[0], mc["optimizer"].param_groups[0]
+    for k in ("lr", "betas", "eps", "weight_decay"):
+        assert tuple(rg[k]) == tuple(mg[k]) if k == "betas" else rg[k] == mg[k], k
+    rs, ms = rc["lr_scheduler"]["scheduler"], mc["lr_scheduler"]["scheduler"]
+    assert type(rs) is type(ms) and rs.milestones == ms.milestones and rs.gamma == ms.gamma
+    assert len(rg["params"]) == len(mg["params"]) == len(list(Short().parameters()))
