@@ -61,7 +61,7 @@ class _SeparatorParams(nn.Module):
         self.stft = _WindowHolder(n_fft)
         self.istft = _WindowHolder(n_fft)
         self.target_models = nn.ModuleDict(target_models)
-        self.register_buffer("sample_rate", torch.as_tensor(float(sample_rate)))
+        self.register_buffer("sample_rate", torch.as_tensor(sample_rate))  # dtype follows the argument, as in the reference (int -> int64)
 
 
 class OpenUnmixModel(nn.Module):
