@@ -141,6 +141,8 @@ int rfx_umx_pipe_push(rfx_umx_t* h, const float* x, int x_on_host, int B, int T,
                       size_t workspace_bytes, void* stream, long long* seq);
 int rfx_umx_pipe_flush(rfx_umx_t* h, void* stream);
 int rfx_umx_pipe_wait(rfx_umx_t* h, long long seq);
+/* Non-blocking: *done = 1 once batch `seq`'s output (and, in host mode, its D2H copy) is complete; 0 while it is in flight. */
+int rfx_umx_pipe_query(rfx_umx_t* h, long long seq, int* done);
 int rfx_umx_pipe_stream_wait(rfx_umx_t* h, long long seq, void* stream);
 /* Timing of the pipeline's recurrence launches: set_profiling(n > 0) brackets the next n launches with cudaEvents on the
  * recurrence stream (0 switches it off); rec_times returns their durations in ms, in launch order, once they have run. */

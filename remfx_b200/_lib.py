@@ -69,6 +69,7 @@ _SIGNATURES = {
                                     C.POINTER(C.c_longlong)]),
     "rfx_umx_pipe_flush": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rfx_umx_pipe_wait": (C.c_int, [C.c_void_p, C.c_longlong]),
+    "rfx_umx_pipe_query": (C.c_int, [C.c_void_p, C.c_longlong, C.POINTER(C.c_int)]),
     "rfx_umx_pipe_stream_wait": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p]),
     "rfx_umx_pipe_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "rfx_umx_pipe_rec_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),

@@ -808,6 +808,21 @@ int rfx_umx_pipe_wait(rfx_umx_t* h, long long seq) {
   return 0;
 }
 
+int rfx_umx_pipe_query(rfx_umx_t* h, long long seq, int* done) {
+  RFX_REQUIRE(h && done, "null argument");
+  *done = 0;
+  rfx_umx::Pipe& p = h->pipe;
+  if (!p.ready || seq < 0 || seq >= p.pushed) return 0;
+  rfx_umx::Done& d = p.done[seq % rfx_umx::kRing];
+  RFX_REQUIRE(d.seq == seq, "pipeline: completion records are kept for the last 16 steps only");
+  if (!d.recorded) return 0;  // still inside the pipeline
+  const cudaError_t e = cudaEventQuery(d.ev);
+  if (e == cudaSuccess) *done = 1;
+  else if (e != cudaErrorNotReady) RFX_CHECK_CUDA(e);
+  else (void)cudaGetLastError();
+  return 0;
+}
+
 int rfx_umx_pipe_stream_wait(rfx_umx_t* h, long long seq, void* stream) {
   cudaEvent_t ev = nullptr;
   int rc;

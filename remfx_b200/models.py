@@ -97,6 +97,16 @@ class OpenUnmixModel(nn.Module):
         L = _lib.lib()
         if self._handle is not None and stamp == self._stamp:
             return self._handle
+        if self._handle is not None:
+            # parameters changed: steps still in flight on the library's lane / recurrence / copy streams read the handle's
+            # weight buffers, and rfx_umx_load_param overwrites them on the caller's stream -- drain everything first
+            for ref in list(self.__dict__.get("_pipes", [])):
+                pipe = ref()
+                if pipe is not None:
+                    pipe.drain()
+            for slot in (0, 1):
+                _lib.check(L.rfx_umx_wait_host(self._handle, slot), "rfx_umx_wait_host")
+            torch.cuda.current_stream(device).synchronize()
         if self._handle is None:
             cfg = _lib.UmxConfig(self.n_fft, self.hop_length, self.model.hidden_size, self.model.nb_layers, 0)
             h = C.c_void_p()
@@ -231,14 +241,19 @@ class UmxPipeline:
     """
 
     def __init__(self, model: OpenUnmixModel, device="cuda:0"):
+        import weakref
+
         self.model = model
         self.device = torch.device(device)
         self._ws: Optional[Tensor] = None
         self._shape = None
-        self._keep = {}
+        self._keep = {}   # seq -> (x, out): the buffers of every step whose completion has not been OBSERVED yet
+        self._outs = {}   # seq -> out for the last _RING steps
+        self._last_seq = -1
         with torch.cuda.device(self.device):
             self._h = model._sync(self.device)
         self.depth = _lib.lib().rfx_umx_pipe_depth(self._h)
+        model.__dict__.setdefault("_pipes", []).append(weakref.ref(self))
 
     @staticmethod
     def _check(t: Tensor, name: str) -> bool:
@@ -273,10 +288,40 @@ class UmxPipeline:
             rc = L.rfx_umx_pipe_push(h, x.data_ptr(), int(x_host), B, T, out.data_ptr(), int(out_host), self._ws.data_ptr(),
                                      self._ws.numel(), _lib.cur_stream(), C.byref(seq))
             _lib.check(rc, "rfx_umx_pipe_push")
-        self._keep[seq.value] = (x, out)  # keep the buffers alive while the step is in flight
-        for old in [k for k in self._keep if k <= seq.value - 2 * self.depth]:
-            del self._keep[old]
+        # The library's lane / recurrence / copy streams are unknown to torch's caching allocators, so the buffers must stay
+        # referenced until the step's completion event has actually fired (a push only enqueues: the host can run far ahead).
+        self._keep[seq.value] = (x, out)
+        self._outs[seq.value] = out   # wait(seq) hands the output back for as long as the library keeps the completion record
+        self._outs.pop(seq.value - self._RING, None)
+        self._last_seq = seq.value
+        self._release_done(seq.value)
         return seq.value
+
+    _RING = 16  # rfx_umx::kRing: completion records are kept for the last 16 steps
+
+    def _release_done(self, newest: int) -> None:
+        L = _lib.lib()
+        done = C.c_int(0)
+        for k in sorted(self._keep):
+            if k == newest:
+                continue
+            if k <= newest - (self._RING - 1):
+                # its completion record is about to be recycled: block on it (long finished in any sane schedule)
+                _lib.check(L.rfx_umx_pipe_wait(self._h, k), "rfx_umx_pipe_wait")
+                del self._keep[k]
+                continue
+            _lib.check(L.rfx_umx_pipe_query(self._h, k, C.byref(done)), "rfx_umx_pipe_query")
+            if done.value:
+                del self._keep[k]
+
+    def drain(self) -> None:
+        """Flush and block until every step pushed so far is complete (used before the model's weights are re-uploaded)."""
+        if self._last_seq < 0:
+            return
+        self.flush()
+        _lib.check(_lib.lib().rfx_umx_pipe_wait(self._h, self._last_seq), "rfx_umx_pipe_wait")
+        torch.cuda.current_stream(self.device).synchronize()
+        self._keep.clear()   # (_outs stays: wait() on a drained step returns at once)
 
     def flush(self) -> None:
         """Run the stages still owed to the batches in flight; the current stream then waits for all their outputs."""
@@ -285,8 +330,14 @@ class UmxPipeline:
 
     def wait(self, seq: int) -> Tensor:
         """Block the host until batch `seq`'s output is complete; returns the output tensor given to push."""
-        _lib.check(_lib.lib().rfx_umx_pipe_wait(self._h, int(seq)), "rfx_umx_pipe_wait")
-        return self._keep[seq][1] if seq in self._keep else None
+        seq = int(seq)
+        if seq not in self._outs:
+            raise _lib.RfxError(f"UmxPipeline.wait({seq}): unknown step, or older than the last {self._RING} pushes (completion records "
+                                "are kept for that many steps only); keep your own reference to `out` and wait earlier")
+        if seq in self._keep:  # completion not observed yet
+            _lib.check(_lib.lib().rfx_umx_pipe_wait(self._h, seq), "rfx_umx_pipe_wait")
+            del self._keep[seq]
+        return self._outs[seq]
 
     def info(self) -> dict:
         """Schedule facts (valid after the first push): SM partition, recurrence streams, slots per recurrence cluster."""

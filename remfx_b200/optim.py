@@ -58,19 +58,44 @@ class FlatBucket:
         p, o = self.params[i], self.offsets[i]
         return self.grad[o:o + p.numel()].view(p.shape)
 
-    def collect_grads(self) -> None:
+    def param_view(self, i: int) -> Tensor:
+        p, o = self.params[i], self.offsets[i]
+        return self.param[o:o + p.numel()].view(p.shape)
+
+    def collect_grads(self) -> List[int]:
         """Make `self.grad` hold every parameter's gradient: a no-op while `.grad` still aliases the bucket (autograd
-        accumulates in place), a copy for gradients that were re-created (e.g. after zero_grad(set_to_none=True))."""
+        accumulates in place), a copy for gradients that were re-created (e.g. after zero_grad(set_to_none=True)).
+        Returns the indices of parameters that have NO gradient this step (torch.optim skips those entirely)."""
+        missing: List[int] = []
         with torch.no_grad():
             for i, p in enumerate(self.params):
                 view = self.grad_view(i)
                 g = p.grad
                 if g is None:
                     view.zero_()
-                    p.grad = view
+                    missing.append(i)
                 elif g.data_ptr() != view.data_ptr():
                     view.copy_(g)
                     p.grad = view
+        return missing
+
+    def rebind_params(self) -> int:
+        """Re-point every parameter whose storage left the bucket (module.to / .float() / load with assign=True after the
+        optimiser was built) at its bucket view, copying its current value in; returns how many were re-bound.  Without this
+        the update kernel would keep training the bucket while the live parameters silently stopped moving."""
+        n = 0
+        with torch.no_grad():
+            for i, p in enumerate(self.params):
+                view = self.param_view(i)
+                if p.data_ptr() == view.data_ptr():
+                    continue
+                if p.device != self.param.device or p.dtype != torch.float32 or p.numel() != view.numel():
+                    raise RuntimeError(f"FlatBucket: parameter {i} moved to {p.device}/{p.dtype} after the optimiser was built; "
+                                       "rebuild the optimiser")
+                view.copy_(p.data.reshape(view.shape))
+                p.data = view
+                n += 1
+        return n
 
     def zero_grad(self) -> None:
         self.grad.zero_()
@@ -113,7 +138,9 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self.max_grad_norm = max_grad_norm
         self.process_group = process_group
-        self.bucket = FlatBucket(self.param_groups[0]["params"])
+        # torch.optim.AdamW never touches parameters without a gradient: frozen ones (requires_grad=False) stay out of the
+        # bucket altogether; trainable ones that happen to have no gradient in a step are restored after the kernel (step()).
+        self.bucket = FlatBucket([p for p in self.param_groups[0]["params"] if p.requires_grad])
         dev = self.bucket.param.device
         self.exp_avg = torch.zeros_like(self.bucket.param)
         self.exp_avg_sq = torch.zeros_like(self.bucket.param)
@@ -132,7 +159,10 @@ class FusedAdamW(torch.optim.Optimizer):
                 loss = closure()
         b = self.bucket
         _lib.require_device(b.param)
-        b.collect_grads()
+        b.rebind_params()
+        missing = b.collect_grads()
+        kept = [(i, b.param_view(i).clone(), self._moment_views(i)) for i in missing]
+        kept = [(i, pv, (m.clone(), v.clone())) for i, pv, (m, v) in kept]
         scale = sync_grads(b.grad, self.process_group)
         g = self.param_groups[0]
         self.step_count += 1
@@ -148,21 +178,36 @@ class FusedAdamW(torch.optim.Optimizer):
                                         self.total_norm.data_ptr(), s), "rfx_adamw_step")
         # the kernel wrote the parameters through raw pointers: tell autograd (and the model handles, whose cached
         # packed weights are keyed on `_version`) that they changed
+        for i, pv, (m0, v0) in kept:  # no gradient this step: no decay, no moment update (what torch.optim.AdamW does)
+            b.param_view(i).copy_(pv)
+            m, v = self._moment_views(i)
+            m.copy_(m0)
+            v.copy_(v0)
         torch.autograd.graph.increment_version(b.params)
         return loss
+
+    def _group_indices(self) -> List[int]:
+        """Position of every bucketed (trainable) parameter in the optimiser's parameter group (torch's state_dict index)."""
+        pos = {id(p): k for k, p in enumerate(self.param_groups[0]["params"])}
+        return [pos[id(p)] for p in self.bucket.params]
+
+    def _moment_views(self, i: int):
+        p, o = self.bucket.params[i], self.bucket.offsets[i]
+        return self.exp_avg[o:o + p.numel()].view(p.shape), self.exp_avg_sq[o:o + p.numel()].view(p.shape)
 
     # state_dict in torch.optim.AdamW's layout (per-parameter exp_avg / exp_avg_sq / step) so checkpoints interchange
     def state_dict(self):
         b = self.bucket
         state = {}
+        gidx = self._group_indices()
         for i, (p, o) in enumerate(zip(b.params, b.offsets)):
-            state[i] = {
+            state[gidx[i]] = {
                 "step": torch.tensor(float(self.step_count)),
                 "exp_avg": self.exp_avg[o:o + p.numel()].view(p.shape).clone(),
                 "exp_avg_sq": self.exp_avg_sq[o:o + p.numel()].view(p.shape).clone(),
             }
         g = {k: v for k, v in self.param_groups[0].items() if k != "params"}
-        g["params"] = list(range(len(b.params)))
+        g["params"] = list(range(len(self.param_groups[0]["params"])))
         return {"state": state, "param_groups": [g]}
 
     def load_state_dict(self, sd) -> None:
@@ -171,8 +216,9 @@ class FusedAdamW(torch.optim.Optimizer):
             if k != "params":
                 self.param_groups[0][k] = v
         with torch.no_grad():
+            gidx = self._group_indices()
             for i, (p, o) in enumerate(zip(b.params, b.offsets)):
-                st = sd["state"].get(i)
+                st = sd["state"].get(gidx[i])
                 if st is None:
                     continue
                 self.exp_avg[o:o + p.numel()].view(p.shape).copy_(st["exp_avg"])

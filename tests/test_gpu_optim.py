@@ -59,3 +59,35 @@ def test_grad_sumsq_large_unaligned_tail():
     assert float(ws[0]) == pytest.approx(want, rel=1e-9)
     _lib.check(L.rfx_grad_sumsq(g.data_ptr(), n, ws.data_ptr(), 1, _lib.cur_stream()))
     assert float(ws[0]) == pytest.approx(2 * want, rel=1e-9)
+
+
+def test_frozen_parameters_are_left_alone_and_moved_storage_is_rebound():
+    """torch.optim.AdamW skips parameters without a gradient (no decay, no moments); and a module cast / moved after
+    the optimiser was built must keep training (the bucket re-binds the live parameters) instead of silently freezing."""
+    ref = _net()
+    ours = _net().cuda()
+    for net in (ref, ours):
+        net[2].weight.requires_grad_(False)   # frozen fine-tuning
+    kw = dict(lr=1e-3, betas=(0.95, 0.999), eps=1e-6, weight_decay=1e-2)
+    opt_ref = torch.optim.AdamW(ref.parameters(), **kw)
+    opt = FusedAdamW(ours.parameters(), max_grad_norm=None, **kw)
+    frozen0 = ours[2].weight.detach().clone()
+    g = torch.Generator().manual_seed(2)
+    for step in range(4):
+        x = torch.randn(8, 130, generator=g)
+        opt_ref.zero_grad()
+        opt.zero_grad()
+        ref(x).square().sum().backward()
+        ours(x.cuda()).square().sum().backward()
+        if step == 2:  # storage leaves the bucket (what module.float() / .to() do to p.data)
+            for p in ours.parameters():
+                p.data = p.data.clone()
+        opt_ref.step()
+        opt.step()
+        for a, b in zip(ref.parameters(), ours.parameters()):
+            err = (a.detach() - b.detach().cpu()).norm() / a.detach().norm()
+            assert float(err) < 2e-6, (step, float(err))
+    assert torch.equal(ours[2].weight.detach(), frozen0)
+    # the live parameters alias the bucket again
+    b = opt.bucket
+    assert all(p.data_ptr() == b.param_view(i).data_ptr() for i, p in enumerate(b.params))

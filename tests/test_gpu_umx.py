@@ -194,3 +194,39 @@ def test_pipeline_flush_without_work_and_reuse():
     s2 = pipe.push(x)
     pipe.flush()
     assert torch.equal(pipe.wait(s2), a)  # same input, same schedule -> bit-identical (deterministic kernels)
+
+
+def test_pipeline_keeps_unreferenced_buffers_alive_and_refuses_stale_waits():
+    """the library's streams are invisible to torch's caching allocator, so the pipeline must hold x / out until
+    the step's completion event has fired -- the caller here drops every reference at once and churns the allocator."""
+    sd = weights.umx_state(5)
+    m = _model(sd)
+    pipe = m.pipeline("cuda:0")
+    xs = [weights.synth_audio(700 + i, 2, 16384) for i in range(3)]
+    refs = [oumx.sample(x, sd) for x in xs]
+    seqs = []
+    for i in range(40):
+        seqs.append(pipe.push(xs[i % 3].cuda()))          # temporaries: no reference kept by the caller
+        junk = torch.full((2, 1, 16384), float(i), device="cuda")  # would recycle a freed block immediately
+        del junk
+    pipe.flush()
+    for i in (37, 38, 39):
+        assert relrms(pipe.wait(seqs[i]).cpu(), refs[i % 3]) < TOL, i
+    with pytest.raises(Exception):
+        pipe.wait(seqs[0])  # older than the completion ring: refuse, do not return None
+
+
+def test_pipeline_survives_a_weight_update_mid_stream():
+    """re-uploading parameters while steps are in flight must not corrupt them (the model drains its pipelines)."""
+    sd = weights.umx_state(5)
+    m = _model(sd)
+    pipe = m.pipeline("cuda:0")
+    x = weights.synth_audio(710, 2, 16384)
+    ref_a = oumx.sample(x, sd)
+    s1 = pipe.push(x.cuda())
+    sd2 = weights.umx_state(6)
+    m.load_state_dict(sd2)               # bumps every parameter version
+    s2 = pipe.push(x.cuda())             # _sync sees the new stamp: drains, then re-uploads
+    pipe.flush()
+    assert relrms(pipe.wait(s1).cpu(), ref_a) < TOL
+    assert relrms(pipe.wait(s2).cpu(), oumx.sample(x, sd2)) < TOL

@@ -4,13 +4,20 @@ reference's hyper-parameters + MultiStepLR (remfx/models.py:185-256, cfg/config.
 
 The file sorts last on purpose: it chains every training component (forward_train, loss forward/backward, TCN backward,
 all-reduce-less FusedAdamW, the handle re-sync after the update), each of which has its own tighter test.
-lr = 1e-5 (a ctor argument of the reference module) keeps three steps in the regime where the loss falls monotonically.
-Tolerances: first loss 1e-4 relative (pure forward), later losses 3e-3 (PReLU-kink sign flips perturb single gradient
-elements, and AdamW's normalised update turns a flipped tiny gradient into a 2 lr parameter difference -- see
-test_gpu_tcn_backward.py; with 1e-6 .. 1e-5 relative noise injected into the CPU oracle alone the later losses move by
-either < 1e-4 or ~4.6e-4, the second when the update of one near-zero-gradient scalar such as output.bias flips), metrics 1e-3 relative / 1e-2 dB.  Direction of the total parameter change: cosine > 0.9 -- AdamW's first updates are
-lr * sign(g), so the ~2 % of gradient elements smaller than the kink noise flip their update; emulating 3e-6 relative
-noise on the CPU oracle alone gives cosine 0.957 against its own noise-free run, with losses within 5e-4.
+
+What is asserted, and why (round-1 lesson: one assert on a step-3 SI-SDR of -50 dB could not tell a kernel bug from drift):
+
+* step 0 (before any update) -- loss 1e-4 relative and all four logged metrics against the CPU step, SI-SDR in dB.  The
+  network output is uncorrelated with the target (|rho| ~ 3e-3, SI-SDR ~ -50 dB), so SI-SDR is ill-conditioned:
+  d(dB) = 20/ln10 * d<x,y>/<x,y>, and an output error of relative size e moves <x,y> by ~ e / (|rho| sqrt(N)) relative.
+  The gate is derived from that (e = 1e-4, the forward parity bound) instead of being a constant.
+* every step -- the metric KERNELS against the oracle evaluated on the GPU's own output of that step (copied to the host):
+  this isolates sisdr_partial/final_kernel and the MR-STFT kernels on the causal-cropped strided target from optimiser drift.
+* later steps -- losses 3e-3 relative to the CPU run (PReLU-kink sign flips perturb single gradient elements and AdamW's
+  normalised update turns a flipped tiny gradient into a 2 lr parameter difference, see test_gpu_tcn_backward.py), the
+  output drift itself bounded, and the SI-SDR difference bounded by the conditioning formula applied to the MEASURED drift.
+* direction of the total parameter change: cosine > 0.9, size within 10 %.
+All mismatches are collected and reported together.
 """
 import pytest
 import torch
@@ -28,25 +35,39 @@ HP = dict(lr=1e-5, lr_beta1=0.95, lr_beta2=0.999, lr_eps=1e-6, lr_weight_decay=1
 STEPS, MAX_STEPS = 3, 50
 
 
+def _metrics(out, tgt, x, y):
+    with torch.no_grad():
+        return {"train_SISDR": float(-oloss.sisdr_loss(out, tgt)), "Input_SISDR": float(-oloss.sisdr_loss(x, y)),
+                "train_STFT": float(oloss.mrstft(out, tgt)), "Input_STFT": float(oloss.mrstft(x, y))}
+
+
 def _reference_steps(sd, x, y):
     st = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     params = list(st.values())
     opt = torch.optim.AdamW(params, lr=HP["lr"], betas=(HP["lr_beta1"], HP["lr_beta2"]), eps=HP["lr_eps"], weight_decay=HP["lr_weight_decay"])
     sched = torch.optim.lr_scheduler.MultiStepLR(opt, [0.8 * MAX_STEPS, 0.95 * MAX_STEPS], gamma=0.1)
-    losses, metrics = [], {}
+    losses, metrics, outs = [], [], []
     for _ in range(STEPS):
         opt.zero_grad()
         loss, out = otcn.forward((x, y), st)
         tgt = ostft.causal_crop(y, out.shape[-1])
-        with torch.no_grad():
-            metrics = {"train_SISDR": -oloss.sisdr_loss(out, tgt), "Input_SISDR": -oloss.sisdr_loss(x, y),
-                       "train_STFT": oloss.mrstft(out, tgt), "Input_STFT": oloss.mrstft(x, y)}
+        metrics.append(_metrics(out.detach(), tgt, x, y))
+        outs.append(out.detach().clone())
         loss.backward()
         torch.nn.utils.clip_grad_norm_(params, 10.0)
         opt.step()
         sched.step()
         losses.append(float(loss.detach()))
-    return losses, {k: float(v) for k, v in metrics.items()}, {k: v.detach() for k, v in st.items()}
+    return losses, metrics, outs, {k: v.detach() for k, v in st.items()}
+
+
+def _sisdr_db_sensitivity(out, tgt, rel_err):
+    """|d SI-SDR| in dB for an output perturbation of relative l2 size `rel_err` in a random direction (4 sigma):
+    SI-SDR = 10 log10(a^2 |y|^2 / |x - a y|^2), a = <x,y>/|y|^2;  d<x,y> ~ rel_err |x| |y| / 1 (one random direction of N)."""
+    o = (out - out.mean(-1, keepdim=True)).double().flatten(1)
+    t = (tgt - tgt.mean(-1, keepdim=True)).double().flatten(1)
+    rho = ((o * t).sum(-1) / (o.norm(dim=-1) * t.norm(dim=-1))).abs().clamp_min(1e-12)
+    return float((20.0 / 2.302585 * 4.0 * rel_err / rho).mean())  # the metric is the batch mean of the per-item dB values
 
 
 def test_fit_step_matches_torch_training_step():
@@ -56,21 +77,57 @@ def test_fit_step_matches_torch_training_step():
     sd = weights.tcn_state(21, nblocks=KW["nblocks"])
     x = weights.synth_audio(400, 2, 4000)
     y = weights.synth_audio(401, 2, 4000)
-    ref_losses, ref_metrics, ref_params = _reference_steps(sd, x, y)
+    ref_losses, ref_metrics, ref_outs, ref_params = _reference_steps(sd, x, y)
 
     net = TCNModel(sample_rate=48000, num_bins=1025, **KW)
     net.load_state_dict(sd, strict=True)
+    outs = []
+    inner = net.forward
+
+    def recording_forward(batch):  # keep the GPU's own output of every step (nn.Module.__call__ picks up the instance attribute)
+        loss, out = inner(batch)
+        outs.append(out.detach().clone())
+        return loss, out
+
+    net.forward = recording_forward
     mod = RemFX(sample_rate=48000, network=net.cuda(), max_steps=MAX_STEPS, **HP)
     batch = (x.cuda(), y.cuda(), None, None)
-    losses = [float(mod.fit_step(batch, i)) for i in range(STEPS)]
-    assert mod.global_step == STEPS
-    assert abs(losses[0] - ref_losses[0]) < 1e-4 * abs(ref_losses[0]), (losses, ref_losses)
-    for a, b in zip(losses, ref_losses):
-        assert abs(a - b) < 3e-3 * abs(b), (losses, ref_losses)
-    assert losses[-1] < losses[0]
-    for k, v in ref_metrics.items():
-        got = float(mod.logged[k])
-        assert abs(got - v) < max(1e-2 if "SISDR" in k else 0.0, 1e-3 * abs(v)), (k, got, v)
+    losses, logged = [], []
+    for i in range(STEPS):
+        losses.append(float(mod.fit_step(batch, i)))
+        logged.append({k: float(v) for k, v in mod.logged.items()})
+    assert mod.global_step == STEPS and len(outs) == STEPS
+    bad = []
+
+    def check(what, got, want, tol):
+        if not abs(got - want) <= tol:
+            bad.append(f"{what}: got {got:.6g}, want {want:.6g}, |diff| {abs(got - want):.3g} > tol {tol:.3g}")
+
+    names = ("train_SISDR", "Input_SISDR", "train_STFT", "Input_STFT")
+    tgt = ostft.causal_crop(y, ref_outs[0].shape[-1])
+    # ---- step 0: pure forward + loss + metric kernels against the CPU step
+    check("loss[0]", losses[0], ref_losses[0], 1e-4 * abs(ref_losses[0]))
+    drift0 = float((outs[0].cpu().double() - ref_outs[0].double()).norm() / ref_outs[0].double().norm())
+    check("output[0] rel-RMS", drift0, 0.0, 1e-4)
+    for k in names:
+        tol = (1e-2 + _sisdr_db_sensitivity(ref_outs[0], tgt, 1e-4)) if k == "train_SISDR" else (1e-2 if "SISDR" in k else 1e-3 * abs(ref_metrics[0][k]))
+        check(f"step 0 {k} vs CPU step", logged[0][k], ref_metrics[0][k], tol)
+    # ---- every step: the metric kernels against the oracle on the GPU's OWN output (no drift in this comparison)
+    for i in range(STEPS):
+        own = _metrics(outs[i].cpu(), tgt, x, y)
+        for k in names:
+            tol = 1e-2 if "SISDR" in k else 1e-3 * abs(own[k])
+            check(f"step {i} {k} kernel vs oracle on the GPU output", logged[i][k], own[k], tol)
+    # ---- later steps against the CPU run: drift-aware
+    for i in range(1, STEPS):
+        check(f"loss[{i}]", losses[i], ref_losses[i], 3e-3 * abs(ref_losses[i]))
+        drift = float((outs[i].cpu().double() - ref_outs[i].double()).norm() / ref_outs[i].double().norm())
+        check(f"output[{i}] drift", drift, 0.0, 2e-2)
+        check(f"step {i} train_SISDR vs CPU step (gate from measured drift {drift:.2e})", logged[i]["train_SISDR"], ref_metrics[i]["train_SISDR"],
+              1e-2 + _sisdr_db_sensitivity(ref_outs[i], tgt, max(drift, 1e-4)))
+        check(f"step {i} train_STFT vs CPU step", logged[i]["train_STFT"], ref_metrics[i]["train_STFT"], 3e-3 * abs(ref_metrics[i]["train_STFT"]))
+    if not losses[-1] < losses[0]:
+        bad.append(f"loss did not fall: {losses}")
     # total parameter movement: same direction, same size
     num = den_a = den_b = 0.0
     for k, p in net.model.state_dict().items():
@@ -78,7 +135,9 @@ def test_fit_step_matches_torch_training_step():
         db = (ref_params["model." + k] - sd["model." + k]).double().flatten()
         num += float(da @ db); den_a += float(da @ da); den_b += float(db @ db)
     cos = num / (den_a ** 0.5 * den_b ** 0.5)
-    assert cos > 0.9 and 0.9 < (den_a / den_b) ** 0.5 < 1.1, (cos, den_a, den_b)
+    if not (cos > 0.9 and 0.9 < (den_a / den_b) ** 0.5 < 1.1):
+        bad.append(f"parameter movement: cosine {cos:.4f}, size ratio {(den_a / den_b) ** 0.5:.4f}")
+    assert not bad, "\n".join(bad) + f"\nlosses {losses} vs {ref_losses}"
 
 
 def test_eval_steps_do_not_build_a_graph_under_no_grad():

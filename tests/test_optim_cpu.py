@@ -8,7 +8,7 @@ import torch.multiprocessing as mp
 
 from remfx_b200._lib import RfxError
 from remfx_b200.optim import FlatBucket, FusedAdamW, configure_optimizers, multistep_lr
-from remfx_b200.parallel import _gloo_optim_worker
+from dist_workers import _gloo_optim_worker
 
 
 def _net():
@@ -81,7 +81,7 @@ def _free_port():
 
 def test_sync_grads_gloo_world2(monkeypatch):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    monkeypatch.setenv("PYTHONPATH", root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    monkeypatch.setenv("PYTHONPATH", root + os.pathsep + os.path.join(root, "tests") + os.pathsep + os.environ.get("PYTHONPATH", ""))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

@@ -7,7 +7,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from remfx_b200.parallel import _gloo_selftest_worker, shard_range, shard_sizes
+from dist_workers import _gloo_selftest_worker
+from remfx_b200.parallel import shard_range, shard_sizes
 
 
 def test_shard_range_partitions_exactly():
@@ -33,7 +34,7 @@ def _free_port():
 @pytest.mark.parametrize("world,n_items", [(2, 5), (2, 4), (3, 2)])
 def test_run_sharded_gloo(world, n_items, monkeypatch):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    monkeypatch.setenv("PYTHONPATH", root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    monkeypatch.setenv("PYTHONPATH", root + os.pathsep + os.path.join(root, "tests") + os.pathsep + os.environ.get("PYTHONPATH", ""))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

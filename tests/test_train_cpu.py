@@ -9,7 +9,7 @@ import torch.multiprocessing as mp
 
 from remfx_b200 import train as T
 from remfx_b200.optim import FusedAdamW
-from remfx_b200.parallel import _gloo_train_worker, _stub_metrics, _StubNet
+from dist_workers import _gloo_train_worker, _stub_metrics, _StubNet
 
 
 def _batch(B=3, n=64, seed=1):
@@ -105,7 +105,7 @@ def _free_port():
 
 def test_data_parallel_fit_step_gloo_world2(monkeypatch):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    monkeypatch.setenv("PYTHONPATH", root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    monkeypatch.setenv("PYTHONPATH", root + os.pathsep + os.path.join(root, "tests") + os.pathsep + os.environ.get("PYTHONPATH", ""))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
