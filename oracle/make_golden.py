@@ -66,6 +66,7 @@ def main():
     example_wav_golden(R)
     chain_golden(R)
     cnn14_golden(R)
+    tcn_full_size_golden(R)
 
 
 TCN_BWD = dict(wseed=41, xseed=43, rseed=44, B=2, T=3000, nblocks=3, width=64)
@@ -153,6 +154,23 @@ def example_wav_golden(R):
           umx_wsum=weights.checksum(sdu), tcn_wsum=weights.checksum(sdt), cnn14_wsum=weights.checksum(sdc),
           umx_out=umx_out[0, 0, ::D].numpy(), tcn_out=tcn_out[0, 0, ::D].numpy(), tcn_len=tcn_out.shape[-1],
           hdemucs_out=hd_out[0, 0, ::D].numpy(), probs=probs.numpy(), logits=logits.numpy(), decisions=(probs > 0.5).numpy())
+
+
+def tcn_full_size_golden(R):
+    """VERDICT r1 'parity gaps at BASELINE sizes': the UNCHANGED reference TCNModel (20 blocks, cfg/model/tcn.yaml) on ONE FULL
+    262144-sample chunk (config 1 of BASELINE.json) -- example.wav whole, where example_wav.npz stops at 65536 samples.
+    5.1 TFLOP on the host: about a minute.  Output (1, 1, 249868) stored every 16th sample."""
+    g = np.load(os.path.join(OUT, "example_wav.npz"))
+    x = example_input(g["pcm16"])
+    with torch.no_grad():
+        sdt = weights.tcn_state(0)
+        tm = R.models.TCNModel(sample_rate=48000, num_bins=1025, **TCN_KW)
+        tm.load_state_dict(sdt, strict=True)
+        tm.eval()
+        out = tm.sample(x)
+    assert out.shape[-1] == 262144 - 12276
+    _save("tcn_full_size.npz", decim=EXAMPLE_DECIM, tcn_wsum=weights.checksum(sdt), out=out[0, 0, ::EXAMPLE_DECIM].numpy(),
+          out_len=out.shape[-1], out_rms=float(out.double().square().mean().sqrt()))
 
 
 CHAIN_ORDER = ["RandomPedalboardDistortion", "RandomPedalboardCompressor", "RandomPedalboardReverb", "RandomPedalboardChorus",

@@ -1,9 +1,11 @@
 """Import the UNCHANGED reference modules from /root/reference behind stubs.
 
-TEST INFRASTRUCTURE.  Only usable in the build container (the GPU box has no
-/root/reference); used by ``oracle/make_golden.py`` to generate the committed
-fixtures under ``tests/golden/`` and by the ``not gpu`` tests (skipped when the
-reference tree is absent) to pin the oracle restatements.
+TEST / MEASUREMENT INFRASTRUCTURE.  Reads ``/root/reference`` in the build container
+and the unmodified, git-ignored copy ``oracle/_ref/`` (recipe: ``oracle/make_ref.py``)
+where that does not exist (the GPU box).  Used by ``oracle/make_golden.py`` to generate
+the committed fixtures under ``tests/golden/``, by the ``not gpu`` tests (skipped when
+no reference tree is available) to pin the oracle restatements, and by ``bench.py``'s
+reference arm / GPU-eager bar to time the unchanged reference modules.
 
 The reference imports a number of third-party packages that are not installed
 in this image.  None of them is on the numerical hot path
@@ -19,7 +21,19 @@ import types
 import torch
 from torch import nn
 
-REF_ROOT = os.environ.get("REMFX_REFERENCE", "/root/reference")
+_LOCAL_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # oracle/make_ref.py: unmodified copy that travels
+
+
+def _pick_root() -> str:
+    env = os.environ.get("REMFX_REFERENCE")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/remfx"):
+        return "/root/reference"
+    return _LOCAL_COPY
+
+
+REF_ROOT = _pick_root()
 
 
 def available() -> bool:

@@ -1,7 +1,8 @@
 """RemFx loss on the GPU: MRSTFT(out, target) + 100 * L1(out, target) (remfx/models.py:299,320,385).
 
 The fused kernels never materialise a spectrogram in HBM.  `remfx_loss` is differentiable with respect to `out`
-(`rfx_remfx_loss_backward`: the first link of the training step); the networks' own backward kernels are not built yet.
+(`rfx_remfx_loss_backward`: the first link of the training step; the TCN's and Hybrid Demucs' backward kernels continue
+from its gradient -- csrc/tcn_bwd.cu, csrc/hdemucs_bwd.cu).
 See csrc/loss.cu and oracle/loss.py (auraloss restatement, parity unpinned).
 """
 from __future__ import annotations

@@ -219,6 +219,11 @@ class OpenUnmixModel(nn.Module):
         from .losses import remfx_loss
 
         x, target = batch
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
+            # the reference trains this wrapper (dead pass + BatchNorm batch statistics + LSTM dropout 0.4 under autograd,
+            # remfx/models.py:294-301); only the eval-mode forward is built here -- fail here, not at loss.backward()
+            raise NotImplementedError("remfx_b200.OpenUnmixModel: training-mode forward / backward kernels are not built "
+                                      "(TCNModel and DemucsModel train); call .eval() or run under torch.no_grad()")
         sep_out = self.sample(x)
         return remfx_loss(sep_out, target), sep_out
 

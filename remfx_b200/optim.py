@@ -163,7 +163,12 @@ class FusedAdamW(torch.optim.Optimizer):
         missing = b.collect_grads()
         kept = [(i, b.param_view(i).clone(), self._moment_views(i)) for i in missing]
         kept = [(i, pv, (m.clone(), v.clone())) for i, pv, (m, v) in kept]
-        scale = sync_grads(b.grad, self.process_group)
+        ev = self._timing_events()
+        if ev:
+            ev[0].record()
+        scale = sync_grads(b.grad, self.process_group)   # the ONE collective of a data-parallel step
+        if ev:
+            ev[1].record()
         g = self.param_groups[0]
         self.step_count += 1
         L = _lib.lib()
@@ -178,6 +183,8 @@ class FusedAdamW(torch.optim.Optimizer):
                                         self.total_norm.data_ptr(), s), "rfx_adamw_step")
         # the kernel wrote the parameters through raw pointers: tell autograd (and the model handles, whose cached
         # packed weights are keyed on `_version`) that they changed
+        if ev:
+            ev[2].record()
         for i, pv, (m0, v0) in kept:  # no gradient this step: no decay, no moment update (what torch.optim.AdamW does)
             b.param_view(i).copy_(pv)
             m, v = self._moment_views(i)
@@ -185,6 +192,22 @@ class FusedAdamW(torch.optim.Optimizer):
             v.copy_(v0)
         torch.autograd.graph.increment_version(b.params)
         return loss
+
+    # ---- optional per-step device timing of the collective and the update kernels (bench.py's train leg)
+    def set_timing(self, on: bool) -> None:
+        self._timing = bool(on)
+        self._timed = []
+
+    def _timing_events(self):
+        if not getattr(self, "_timing", False):
+            return None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        self._timed.append(ev)
+        return ev
+
+    def timing_ms(self):
+        """[(all_reduce_ms, clip+adamw_ms)] of every timed step; the device must be synchronised first."""
+        return [(e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])) for e in getattr(self, "_timed", [])]
 
     def _group_indices(self) -> List[int]:
         """Position of every bucketed (trainable) parameter in the optimiser's parameter group (torch's state_dict index)."""
