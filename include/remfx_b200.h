@@ -274,6 +274,24 @@ int rfx_hdemucs_launches_per_call(rfx_hdemucs_t* h, int B, int T);
 int rfx_hdemucs_set_taps(rfx_hdemucs_t* h, int on);
 int rfx_hdemucs_tap(rfx_hdemucs_t* h, const char* name, float* dst, int64_t capacity, int* dims, void* stream);
 
+/* Training (row L5 with Hybrid Demucs, the network of cfg/exp/5-5_full.yaml:3): what `loss.backward()` does to
+ * `DemucsModel.forward`'s output in the reference's Lightning step (remfx/models.py:217-221, 317-321).
+ *   rfx_hdemucs_forward_train  the forward with every pre-activation kept in `workspace` and a tape of its ops in the handle;
+ *                              same result as rfx_hdemucs_forward to rounding (activations are un-fused from the GEMM epilogues)
+ *   rfx_hdemucs_backward       given dout = dLoss / dout (B, T), writes dLoss / dparameter for every state_dict key passed in
+ *                              keys[] / grads[] (device fp32 buffers of the parameter's size; all are overwritten).  Must be
+ *                              called with the SAME workspace pointer as the matching forward_train.  No gradient is produced for x.
+ * workspace: rfx_hdemucs_train_workspace_bytes(h, B, T) bytes (forward + backward scratch), 256-byte aligned. */
+size_t rfx_hdemucs_train_workspace_bytes(rfx_hdemucs_t* h, int B, int T);
+int rfx_hdemucs_forward_train(rfx_hdemucs_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes,
+                              void* stream);
+int rfx_hdemucs_backward(rfx_hdemucs_t* h, const float* x, const float* dout, int B, int T, const char* const* keys,
+                         float* const* grads, int nkeys, void* workspace, size_t workspace_bytes, void* stream);
+/* Debug: after a backward, the gradient of a tapped activation (fp32, (B, Y, X, C)); and a way to substitute a reference
+ * gradient at a tap during the following backward calls so that each layer can be judged on its own (grad NULL removes it). */
+int rfx_hdemucs_grad_tap(rfx_hdemucs_t* h, const char* name, float* dst, int64_t capacity, int* dims, void* stream);
+int rfx_hdemucs_inject_grad(rfx_hdemucs_t* h, const char* name, const float* grad);
+
 /* ---------------------------------------------------------------------------------------------
  * L1/L2  RemFx loss = MultiResolutionSTFTLoss(out, target) + l1_weight * mean|out - target|
  *   replaces `self.mrstftloss(out, target) + self.l1loss(out, target) * 100`

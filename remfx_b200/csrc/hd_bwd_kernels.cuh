@@ -1,0 +1,945 @@
+// Backward kernels of the Hybrid-Demucs training step (torchaudio/models/_hdemucs.py under torch autograd, as the reference's
+// Lightning step differentiates it: remfx/models.py:217-220 -> loss.backward(); cfg/exp/5-5_full.yaml:3).  Included by
+// hdemucs_bwd.cu only.  Conventions (see hd_internal.h): activations are channel-last (B, Y, X, C); the gradient of a split-bf16
+// ACTIVATION is an fp32 tensor of the same shape; the gradient of an fp32 PRE-ACTIVATION (a conv output) is written as split
+// planes (B, Y, X, Cg = ceil8(C)) because it is the A operand of the input-gradient GEMM and of the weight-gradient contraction.
+// tools/hd_bwd_emul.py holds the same formulas in fp64 against autograd.
+#pragma once
+#include "hd_internal.h"
+
+namespace rfx {
+namespace hd {
+
+__device__ __forceinline__ void bw_store_split8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, const float (&o)[8]) {
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(o[2 * i] - hf.x, o[2 * i + 1] - hf.y);
+    ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  *reinterpret_cast<uint4*>(lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+__device__ __forceinline__ void bw_load_split8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t off, float (&o)[8]) {
+  const uint4 h = *reinterpret_cast<const uint4*>(hi + off);
+  const uint4 l = *reinterpret_cast<const uint4*>(lo + off);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[i]));
+    const float2 lf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[i]));
+    o[2 * i] = hf.x + lf.x;
+    o[2 * i + 1] = hf.y + lf.y;
+  }
+}
+// d/du gelu(u), erf form:  Phi(u) + u phi(u)
+__device__ __forceinline__ float gelu_grad(float u) {
+  const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * u * u);
+  return fmaf(u, pdf, cdf);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm (optional) + activation (+ LayerScale, + residual, + crop) backward.  Forward: gn_apply_kernel (hd_kernels.cuh).
+//   u = stats ? xhat * gamma + beta : raw,  xhat = (raw - mean) * rstd;   v = act(u);   out = v * scale + res
+//   PASS 1 (only when stats != nullptr): per-channel sums  dbeta += du, dgamma += du xhat, dscale += dout v   and the two
+//          per-(segment, group) sums  S1 = sum(gamma du), S2 = sum(gamma du xhat)  (fp64 atomics)
+//   PASS 2: d raw = stats ? rstd (gamma du - S1 / n - xhat S2 / n) : du  -> split planes;  d res (+)= dout
+// Work split: grid = (chunks, segments); a thread owns one octet of OUTPUT channels and strides over the segment's pixels, so
+// per-channel sums stay in registers (the tcn_act_bwd_kernel pattern).  The pixel domain is the whole UNcropped raw extent:
+// positions outside the crop window have dout = 0 but, under GroupNorm, a non-zero d raw.
+// ------------------------------------------------------------------------------------------------
+struct GnBwd {
+  GnApply a;              // the forward arguments
+  const float* dy;        // gradient of out, fp32 (B, Y, Xo, Co)
+  float* dres;            // gradient of res (same shape as out) or nullptr
+  int res_accum;          // 1: dres += dout, 0: dres = dout
+  __nv_bfloat16* ghi;     // d raw planes (B, Y, Xr, Cg)
+  __nv_bfloat16* glo;
+  int Cg;
+  double* gsum;           // [segments * G][2]
+  float* dgamma; float* dbeta; float* dscale;
+  long long count;        // elements per (segment, group)
+  int rows_per_cta;       // pixels per CTA
+};
+
+template <int PASS>
+__global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwd p) {
+  extern __shared__ __align__(16) float gb_smem[];  // PASS 1: [2 * Cr] (dbeta, dgamma) + [Co] (dscale), then doubles [2 * G] (16-byte aligned)
+  const GnApply& a = p.a;
+  const int groups = a.Co / 8;
+  const int rows = 256 / groups;
+  const int g8 = threadIdx.x % groups, r = threadIdx.x / groups;
+  const int c0 = g8 * 8;
+  const int seg = blockIdx.y;
+  const int b = a.per_x ? seg / a.Xr : seg;
+  const int xfix = a.per_x ? seg % a.Xr : 0;
+  const long long npix = a.per_x ? a.Y : (long long)a.Y * a.Xr;
+  const int mode = a.mode;
+  const int Ch = mode >= 2 ? a.Cr / 2 : a.Cr;  // valid output channels
+  const int cpg = a.Cr / a.G;
+  const bool has_stats = a.stats != nullptr;
+  double* sm_d = nullptr;
+  if (PASS == 1) {
+    const int nf = 2 * a.Cr + a.Co;
+    for (int i = threadIdx.x; i < nf; i += 256) gb_smem[i] = 0.0f;
+    sm_d = reinterpret_cast<double*>(gb_smem + ((nf + 3) & ~3));
+    if (threadIdx.x < 2 * a.G) sm_d[threadIdx.x] = 0.0;
+    __syncthreads();
+  }
+  // per-thread constants: affine parameters of the value octet and (GLU) the gate octet
+  float ga[8], be[8], ga2[8], be2[8], sc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    ga[i] = 1.0f; be[i] = 0.0f; ga2[i] = 1.0f; be2[i] = 0.0f; sc[i] = 1.0f;
+    if (c < Ch) {
+      if (has_stats) {
+        ga[i] = a.gamma[c]; be[i] = a.beta[c];
+        if (mode == 2) { ga2[i] = a.gamma[c + Ch]; be2[i] = a.beta[c + Ch]; }
+      }
+      if (a.scale) sc[i] = a.scale[c];
+    }
+  }
+  const int grp1 = has_stats ? min(c0, a.Cr - 1) / cpg : 0;
+  const int grp2 = (has_stats && mode == 2) ? min(c0 + Ch, a.Cr - 1) / cpg : 0;
+  float mean1 = 0.0f, rstd1 = 1.0f, mean2 = 0.0f, rstd2 = 1.0f;
+  double s1a = 0.0, s2a = 0.0, s1b = 0.0, s2b = 0.0;   // PASS 1 group sums (value / gate groups); PASS 2: means
+  if (has_stats) {
+    const float* st = a.stats + ((size_t)seg * a.G + grp1) * 2;
+    mean1 = st[0]; rstd1 = st[1];
+    if (mode == 2) { const float* st2 = a.stats + ((size_t)seg * a.G + grp2) * 2; mean2 = st2[0]; rstd2 = st2[1]; }
+    if (PASS == 2) {
+      s1a = p.gsum[((size_t)seg * a.G + grp1) * 2] / (double)p.count;
+      s2a = p.gsum[((size_t)seg * a.G + grp1) * 2 + 1] / (double)p.count;
+      if (mode == 2) {
+        s1b = p.gsum[((size_t)seg * a.G + grp2) * 2] / (double)p.count;
+        s2b = p.gsum[((size_t)seg * a.G + grp2) * 2 + 1] / (double)p.count;
+      }
+    }
+  }
+  const float m1a = (float)s1a, m2a = (float)s2a, m1b = (float)s1b, m2b = (float)s2b;
+  float acc_b[8] = {}, acc_g[8] = {}, acc_b2[8] = {}, acc_g2[8] = {}, acc_s[8] = {};
+  const long long p_begin = (long long)blockIdx.x * p.rows_per_cta;
+  const long long p_end = min(npix, p_begin + p.rows_per_cta);
+  if (r < rows && c0 < a.Co) {
+    for (long long pp = p_begin + r; pp < p_end; pp += rows) {
+      int y, xr;
+      if (a.per_x) { y = (int)pp; xr = xfix; }
+      else { y = (int)(pp / a.Xr); xr = (int)(pp % a.Xr); }
+      const int xo = xr - a.x_off;
+      const bool inwin = xo >= 0 && xo < a.Xo;
+      const float* rawp = a.raw + (((size_t)b * a.Y + y) * a.Xr + xr) * a.Cr;
+      float dout[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dout[i] = 0.0f;
+      size_t ooff = 0;
+      if (inwin) {
+        ooff = (((size_t)b * a.Y + y) * a.Xo + xo) * a.Co + c0;
+        const float4 d0 = *reinterpret_cast<const float4*>(p.dy + ooff), d1 = *reinterpret_cast<const float4*>(p.dy + ooff + 4);
+        dout[0] = d0.x; dout[1] = d0.y; dout[2] = d0.z; dout[3] = d0.w; dout[4] = d1.x; dout[5] = d1.y; dout[6] = d1.z; dout[7] = d1.w;
+        if (PASS == 2 && p.dres) {
+          float4 r0 = d0, r1 = d1;
+          if (p.res_accum) {
+            const float4 o0 = *reinterpret_cast<const float4*>(p.dres + ooff), o1 = *reinterpret_cast<const float4*>(p.dres + ooff + 4);
+            r0.x += o0.x; r0.y += o0.y; r0.z += o0.z; r0.w += o0.w; r1.x += o1.x; r1.y += o1.y; r1.z += o1.z; r1.w += o1.w;
+          }
+          *reinterpret_cast<float4*>(p.dres + ooff) = r0;
+          *reinterpret_cast<float4*>(p.dres + ooff + 4) = r1;
+        }
+      }
+      float dr1[8], dr2[8];   // d raw of the value octet / the gate octet
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        dr1[i] = 0.0f; dr2[i] = 0.0f;
+        if (c >= Ch) continue;
+        float raw1, raw2 = 0.0f;
+        if (mode == 3) { const float2 pr = *reinterpret_cast<const float2*>(rawp + 2 * c); raw1 = pr.x; raw2 = pr.y; }
+        else { raw1 = rawp[c]; if (mode == 2) raw2 = rawp[c + Ch]; }
+        const float xh1 = (raw1 - mean1) * rstd1, xh2 = (raw2 - mean2) * rstd2;
+        const float u1 = has_stats ? fmaf(xh1, ga[i], be[i]) : raw1;
+        const float u2 = has_stats ? fmaf(xh2, ga2[i], be2[i]) : raw2;
+        const float dv = dout[i] * sc[i];
+        float du1, du2 = 0.0f, v;
+        if (mode == 0) { du1 = dv; v = u1; }
+        else if (mode == 1) { du1 = dv * gelu_grad(u1); v = gelu_fast(u1); }
+        else {
+          const float s = sigmoidf_acc(u2);
+          du1 = dv * s;
+          du2 = dv * u1 * s * (1.0f - s);
+          v = u1 * s;
+        }
+        if (PASS == 1) {
+          acc_b[i] += du1; acc_g[i] += du1 * xh1; acc_s[i] += dout[i] * v;
+          s1a += (double)(ga[i] * du1); s2a += (double)(ga[i] * du1 * xh1);
+          if (mode == 2) {
+            acc_b2[i] += du2; acc_g2[i] += du2 * xh2;
+            s1b += (double)(ga2[i] * du2); s2b += (double)(ga2[i] * du2 * xh2);
+          }
+        } else {
+          dr1[i] = has_stats ? rstd1 * (ga[i] * du1 - m1a - xh1 * m2a) : du1;
+          if (mode >= 2) dr2[i] = has_stats ? rstd2 * (ga2[i] * du2 - m1b - xh2 * m2b) : du2;
+        }
+      }
+      if (PASS == 2) {
+        const size_t gpix = (((size_t)b * a.Y + y) * a.Xr + xr) * p.Cg;
+        if (mode == 3) {  // interleaved (value, gate) pairs: raw channels 2 c0 .. 2 c0 + 15
+          if (c0 < Ch) {
+            float lo8[8], hi8[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { lo8[2 * i] = dr1[i]; lo8[2 * i + 1] = dr2[i]; hi8[2 * i] = dr1[4 + i]; hi8[2 * i + 1] = dr2[4 + i]; }
+            bw_store_split8(p.ghi, p.glo, gpix + 2 * c0, lo8);
+            bw_store_split8(p.ghi, p.glo, gpix + 2 * c0 + 8, hi8);
+          }
+        } else {
+          if (c0 < p.Cg) bw_store_split8(p.ghi, p.glo, gpix + c0, dr1);   // channels in [Cr, Cg) are written as zero
+          if (mode == 2 && c0 < Ch) bw_store_split8(p.ghi, p.glo, gpix + Ch + c0, dr2);
+        }
+      }
+    }
+  }
+  if (PASS == 1) {
+    float* sm_b = gb_smem;             // [Cr] dbeta
+    float* sm_g = gb_smem + a.Cr;      // [Cr] dgamma
+    float* sm_s = gb_smem + 2 * a.Cr;  // [Co] dscale
+    if (r < rows && c0 < a.Co) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        if (c >= Ch) continue;
+        atomicAdd(&sm_b[c], acc_b[i]); atomicAdd(&sm_g[c], acc_g[i]); atomicAdd(&sm_s[c], acc_s[i]);
+        if (mode == 2) { atomicAdd(&sm_b[c + Ch], acc_b2[i]); atomicAdd(&sm_g[c + Ch], acc_g2[i]); }
+      }
+      atomicAdd(&sm_d[2 * grp1], s1a); atomicAdd(&sm_d[2 * grp1 + 1], s2a);
+      if (mode == 2) { atomicAdd(&sm_d[2 * grp2], s1b); atomicAdd(&sm_d[2 * grp2 + 1], s2b); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.Cr; i += 256) {
+      if (p.dbeta) atomicAdd(p.dbeta + i, sm_b[i]);
+      if (p.dgamma) atomicAdd(p.dgamma + i, sm_g[i]);
+    }
+    if (p.dscale)
+      for (int i = threadIdx.x; i < Ch; i += 256) atomicAdd(p.dscale + i, sm_s[i]);
+    if (p.gsum && threadIdx.x < 2 * a.G) atomicAdd(p.gsum + (size_t)seg * a.G * 2 + threadIdx.x, sm_d[threadIdx.x]);
+  }
+}
+
+// ---- out = a[x + x_off] + skip  backward:  d a = (dout inside the crop window, 0 outside);  d skip (+)= dout ----
+__global__ void __launch_bounds__(256) addcrop_bwd_kernel(const float* __restrict__ dy, int Y, int X, int C, float* __restrict__ da, int Xa, int x_off,
+                                                          float* __restrict__ dskip, int skip_accum) {
+  const int groups = C / 4;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= (long long)Y * Xa * groups) return;
+  const int c0 = (int)(idx % groups) * 4;
+  const int xa = (int)((idx / groups) % Xa);
+  const int y = (int)(idx / ((long long)groups * Xa));
+  const int x = xa - x_off;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (x >= 0 && x < X) {
+    const size_t off = (((size_t)b * Y + y) * X + x) * C + c0;
+    g = *reinterpret_cast<const float4*>(dy + off);
+    if (dskip) {
+      float4 o = g;
+      if (skip_accum) { const float4 q = *reinterpret_cast<const float4*>(dskip + off); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+      *reinterpret_cast<float4*>(dskip + off) = o;
+    }
+  }
+  *reinterpret_cast<float4*>(da + (((size_t)b * Y + y) * Xa + xa) * C + c0) = g;
+}
+
+// ---- dst (+)= src, fp32 ----
+__global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(dst)[i];
+    const float4 b = reinterpret_cast<const float4*>(src)[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(dst)[i] = a;
+  }
+}
+
+// ---- frequency embedding backward:  demb[x][c] += w * sum_{b, y} dz[b][y][x][c]  (TA:586-591; z itself passes through) ----
+__global__ void __launch_bounds__(256) freqemb_bwd_kernel(const float* __restrict__ dz, int B, int Y, int X, int C, float w, float* __restrict__ demb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (x, c)
+  if (i >= X * C) return;
+  const int yb = blockIdx.y, ny = gridDim.y;             // slices of the (b, y) range
+  const long long rows = (long long)B * Y;
+  float acc = 0.0f;
+  for (long long ry = yb; ry < rows; ry += ny) acc += dz[(size_t)ry * X * C + i];
+  atomicAdd(demb + i, w * acc);
+}
+
+// ---- _BLSTM framing backward (adjoint of _unfold, TA:888-905): dx[b][t][c] (+)= sum over the frames covering t ----
+__global__ void __launch_bounds__(256) frame_bwd_kernel(const float* __restrict__ dfr /*(B*nf, width, C)*/, int T, int C, int nf, int width, int stride,
+                                                        float* __restrict__ dx, int accum) {
+  const int groups = C / 4;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= (long long)T * groups) return;
+  const int c0 = (int)(idx % groups) * 4;
+  const int t = (int)(idx / groups);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int k_hi = min(nf - 1, t / stride);
+  for (int k = k_hi; k >= 0 && t - k * stride < width; --k) {
+    const float4 v = *reinterpret_cast<const float4*>(dfr + (((size_t)b * nf + k) * width + (t - k * stride)) * C + c0);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float* o = dx + ((size_t)b * T + t) * C + c0;
+  if (accum) { const float4 q = *reinterpret_cast<const float4*>(o); acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w; }
+  *reinterpret_cast<float4*>(o) = acc;
+}
+
+// ---- _BLSTM stitch + skip backward (TA:772-788): d lin[(b, k), pos][c] = dout[b][t][c] where frame(t) == k, else 0 -> split planes;
+//      d skip (+)= dout.  One thread per (frame row, 8 channels) of lin. ----
+__global__ void __launch_bounds__(256) merge_bwd_kernel(const float* __restrict__ dy /*(B, T, C)*/, int T, int C, int nf, int width, int stride,
+                                                        __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo) {
+  const int groups = C / 8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int bf = blockIdx.y;  // b * nf + k
+  if (idx >= (long long)width * groups) return;
+  const int c0 = (int)(idx % groups) * 8;
+  const int pos = (int)(idx / groups);
+  const int b = bf / nf, k = bf % nf;
+  const int t = k * stride + pos;
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (t < T) {
+    int ksel = 0;
+    if (nf > 1) {
+      ksel = (t - stride / 2) / stride;
+      if (t < stride / 2) ksel = 0;
+      if (ksel > nf - 1) ksel = nf - 1;
+    }
+    if (ksel == k) {
+      const float* s = dy + ((size_t)b * T + t) * C + c0;
+      const float4 d0 = *reinterpret_cast<const float4*>(s), d1 = *reinterpret_cast<const float4*>(s + 4);
+      o[0] = d0.x; o[1] = d0.y; o[2] = d0.z; o[3] = d0.w; o[4] = d1.x; o[5] = d1.y; o[6] = d1.z; o[7] = d1.w;
+    }
+  }
+  bw_store_split8(ghi, glo, ((size_t)bf * width + pos) * C + c0, o);
+}
+
+// ---- fp32 (rows, cols) -> split planes (rows, cols_pad) with zero padding columns ----
+__global__ void __launch_bounds__(256) split_pad_kernel(const float* __restrict__ src, long long rows, int cols, int cols_pad,
+                                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int groups = cols_pad / 8;
+  const long long total = rows * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long rr = i / groups;
+    const int c0 = (int)(i % groups) * 8;
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (c0 + k < cols) ? src[(size_t)rr * cols + c0 + k] : 0.0f;
+    bw_store_split8(hi, lo, (size_t)rr * cols_pad + c0, o);
+  }
+}
+
+// ---- column sums of split planes: out[n] += sum_rows G[row][col0 + n]   (bias gradients); grid = (row chunks, column blocks of 2048) ----
+__global__ void __launch_bounds__(256) colsum_split_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long rows, int ld,
+                                                           int col0, int N, float* __restrict__ out, int rows_per_cta) {
+  __shared__ float cs_smem[2048];
+  const int cb = blockIdx.y * 2048;
+  const int nloc = min(2048, N - cb);
+  const int groups = (nloc + 7) / 8;
+  const int nrow = 256 / groups;
+  const int g8 = threadIdx.x % groups, r = threadIdx.x / groups;
+  for (int i = threadIdx.x; i < groups * 8; i += 256) cs_smem[i] = 0.0f;
+  __syncthreads();
+  float acc[8] = {};
+  const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  if (r < nrow) {
+    for (long long rr = r0 + r; rr < r1; rr += nrow) {
+      float v[8];
+      bw_load_split8(hi, lo, (size_t)rr * ld + col0 + cb + g8 * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&cs_smem[g8 * 8 + i], acc[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nloc; i += 256) atomicAdd(out + cb + i, cs_smem[i]);
+}
+// staged column sums [Nout] -> the bias parameter's gradient (inverse of gather_w_kernel's bias re-ordering)
+__global__ void scatter_bias_kernel(const float* __restrict__ stage, GatherSpec g, float* __restrict__ db, float* __restrict__ db2) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= g.Nout) return;
+  int idx;
+  if (g.kind == 2) idx = n % g.Co;
+  else if (g.glu) idx = (n & 1) ? (g.Co / 2 + n / 2) : n / 2;
+  else idx = n;
+  atomicAdd(db + idx, stage[n]);
+  if (db2) atomicAdd(db2 + idx, stage[n]);
+}
+
+// ---- weight-gradient staging [Nout][taps][Kp] -> the parameter's layout (inverse of gather_w_kernel; every parameter element
+//      has exactly one staging slot, so this WRITES) ----
+__global__ void scatter_w_kernel(const float* __restrict__ stage, GatherSpec g, float* __restrict__ dw) {
+  const long long total = (long long)g.Nout * g.taps * g.Kp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % g.Kp);
+    const int tap = (int)((i / g.Kp) % g.taps);
+    const int n = (int)(i / ((long long)g.Kp * g.taps));
+    if (g.kind == 0) {
+      int co = n;
+      if (g.glu) co = (n & 1) ? (g.Co / 2 + n / 2) : n / 2;
+      if (col < g.Ci) dw[((size_t)co * g.Ci + col) * g.k + tap] = stage[i];
+    } else if (g.kind == 1) {
+      const int rr = col / g.Ci, ci = col % g.Ci;
+      const int j = g.s * (g.tau_min + tap) + rr + g.p;
+      if (col < g.s * g.Ci && j >= 0 && j < g.k) dw[((size_t)n * g.Ci + ci) * g.k + j] = stage[i];
+    } else {
+      const int rr = n / g.Co, co = n % g.Co;  // weight [Ci][Co][k]
+      const int j = rr + g.s * tap;
+      if (col < g.Ci && j < g.k) dw[((size_t)col * g.Co + co) * g.k + j] = stage[i];
+    }
+  }
+}
+
+// ---- transposed weights for the input gradient:  Wt[k][tap * Np + n] = Wcat[n][tap * Kp + k]   (k < Kt rows, Np = ceil64(Nout)) ----
+__global__ void transpose_w_kernel(const float* __restrict__ wcat, int Nout, int taps, int Kp, int Kt, int Np, float* __restrict__ wt) {
+  const long long total = (long long)Kt * taps * Np;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % Np);
+    const int tap = (int)((i / Np) % taps);
+    const int k = (int)(i / ((long long)Np * taps));
+    wt[i] = (n < Nout && k < Kp) ? wcat[((size_t)n * taps + tap) * Kp + k] : 0.0f;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient of an implicit-GEMM convolution (the generalisation of tcn_wgrad_kernel, tcn_bwd.cu):
+//   dW[n][tap][k] += sum_{b, y, x} G[b, y, x, gcol0 + n] * A[b, y + dy[tap], x + dx[tap], k]      (A reads outside its extent are 0)
+// The contraction runs over PIXELS and both operands are pixel-major in HBM ([pixel][channel]), i.e. MN-major for the MMA:
+// fragments come out of ldmatrix.trans; mma.sync.m16n8k16 bf16x3 (lo*hi + hi*lo + hi*hi) with fp32 accumulation; a 3-stage
+// cp.async ring of 32 pixels x 4 plane tiles; one CTA = (tap, 128 n x 128 k tile, item, pixel chunk); fp32 atomics into the
+// [N][taps][Kp] staging buffer.
+// ------------------------------------------------------------------------------------------------
+constexpr int HW_BM = 128, HW_BN = 128, HW_BK = 32, HW_LD = 136, HW_STAGES = 3;
+constexpr int HW_TILE = HW_BK * HW_LD;
+constexpr int HW_STAGE_ELEMS = 4 * HW_TILE;
+constexpr int HW_SMEM = HW_STAGES * HW_STAGE_ELEMS * 2;
+
+struct WgP {
+  const __nv_bfloat16* g; long long g_bs, g_ldy, g_ld, g_plane; int gcol0;
+  const __nv_bfloat16* a; long long a_bs, a_ldy, a_ld, a_plane;
+  int Y, X, Ay, Ax;
+  int N, K, taps, Kp;
+  int dx[16], dy[16];
+  int nchunks, rchunk;
+  float* dW;
+};
+
+__device__ __forceinline__ void hw_cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void hw_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void hw_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void hw_ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void hw_mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 2) hd_wgrad_kernel(const WgP p) {
+  extern __shared__ __align__(16) unsigned char hw_smem[];
+  __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(hw_smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tilesN = (p.N + HW_BM - 1) / HW_BM, tilesK = (p.K + HW_BN - 1) / HW_BN;
+  int bx = blockIdx.x;
+  const int tk = bx % tilesK; bx /= tilesK;
+  const int tn = bx % tilesN;
+  const int tap = bx / tilesN;
+  const int b = blockIdx.y / p.nchunks, chunk = blockIdx.y % p.nchunks;
+  const long long R = (long long)p.Y * p.X;
+  const long long r_begin = (long long)chunk * p.rchunk, r_end = min(R, r_begin + p.rchunk);
+  const int n0 = tn * HW_BM, k0 = tk * HW_BN;
+  const int ddx = p.dx[tap], ddy = p.dy[tap];
+  const __nv_bfloat16* gsrc = p.g + (size_t)b * p.g_bs + p.gcol0;
+  const __nv_bfloat16* asrc = p.a + (size_t)b * p.a_bs;
+  const int iters = (int)((r_end - r_begin + HW_BK - 1) / HW_BK);
+
+  auto load_stage = [&](int it, int stage) {
+    const long long rr0 = r_begin + (long long)it * HW_BK;
+    __nv_bfloat16* st = sm + (size_t)stage * HW_STAGE_ELEMS;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int idx = tid + h * 256;  // 512 16-byte pieces per plane tile: 32 rows x 16
+      const int rr = idx >> 4, cc = (idx & 15) * 8;
+      const long long pix = rr0 + rr;
+      const bool row_ok = pix < r_end;
+      const int y = row_ok ? (int)(pix / p.X) : 0, x = row_ok ? (int)(pix % p.X) : 0;
+      const int ya = y + ddy, xa = x + ddx;
+      const bool gok = row_ok && (n0 + cc < p.N);
+      const bool aok = row_ok && (k0 + cc < p.K) && ya >= 0 && ya < p.Ay && xa >= 0 && xa < p.Ax;
+      const __nv_bfloat16* gp = gok ? gsrc + (size_t)y * p.g_ldy + (size_t)x * p.g_ld + n0 + cc : p.g;
+      const __nv_bfloat16* ap = aok ? asrc + (size_t)ya * p.a_ldy + (size_t)xa * p.a_ld + k0 + cc : p.a;
+      const uint32_t d = smem_u32(st + rr * HW_LD + cc);
+      hw_cp_async16(d, gp, gok);
+      hw_cp_async16(d + HW_TILE * 2, gok ? gp + p.g_plane : p.g, gok);
+      hw_cp_async16(d + 2 * HW_TILE * 2, ap, aok);
+      hw_cp_async16(d + 3 * HW_TILE * 2, aok ? ap + p.a_plane : p.a, aok);
+    }
+  };
+
+  float acc[4][4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.0f;
+
+  for (int s = 0; s < HW_STAGES - 1; ++s) {
+    if (s < iters) load_stage(s, s);
+    hw_cp_async_commit();
+  }
+  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps: 64 n x 32 k each
+  const int lj = lane >> 3, lr = lane & 7;
+  const int a_row = (lj >> 1) * 8 + lr, a_col = wm * 64 + (lj & 1) * 8;
+  const int b_row = (lj & 1) * 8 + lr, b_col = wn * 32 + (lj >> 1) * 8;
+
+  for (int it = 0; it < iters; ++it) {
+    hw_cp_async_wait<HW_STAGES - 2>();
+    __syncthreads();
+    {
+      const int nx = it + HW_STAGES - 1;
+      if (nx < iters) load_stage(nx, nx % HW_STAGES);
+      hw_cp_async_commit();
+    }
+    const __nv_bfloat16* st = sm + (size_t)(it % HW_STAGES) * HW_STAGE_ELEMS;
+    const uint32_t g_hi = smem_u32(st), g_lo = g_hi + HW_TILE * 2, x_hi = g_hi + 2 * HW_TILE * 2, x_lo = g_hi + 3 * HW_TILE * 2;
+#pragma unroll
+    for (int kk = 0; kk < HW_BK; kk += 16) {
+      uint32_t bh[2][4], bl[2][4];
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        const uint32_t o = (uint32_t)(((kk + b_row) * HW_LD + b_col + np * 16) * 2);
+        hw_ldsm_x4_t(x_hi + o, bh[np]);
+        hw_ldsm_x4_t(x_lo + o, bl[np]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        uint32_t ah[4], al[4];
+        const uint32_t o = (uint32_t)(((kk + a_row) * HW_LD + a_col + mt * 16) * 2);
+        hw_ldsm_x4_t(g_hi + o, ah);
+        hw_ldsm_x4_t(g_lo + o, al);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int np = nt >> 1, q = (nt & 1) * 2;
+          hw_mma16816(acc[mt][nt], al, bh[np][q], bh[np][q + 1]);
+          hw_mma16816(acc[mt][nt], ah, bl[np][q], bl[np][q + 1]);
+          hw_mma16816(acc[mt][nt], ah, bh[np][q], bh[np][q + 1]);
+        }
+      }
+    }
+  }
+  hw_cp_async_wait<0>();
+
+  const size_t ldn = (size_t)p.taps * p.Kp;
+  float* dst = p.dW + (size_t)tap * p.Kp;
+  const int gq = lane >> 2, qq = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int n = n0 + wm * 64 + mt * 16 + gq;
+      const int k = k0 + wn * 32 + nt * 8 + qq * 2;
+      if (k < p.K) {  // K is a multiple of 8 here (channel counts are padded): k + 1 < K as well
+        if (n < p.N) {
+          atomicAdd(dst + (size_t)n * ldn + k, acc[mt][nt][0]);
+          atomicAdd(dst + (size_t)n * ldn + k + 1, acc[mt][nt][1]);
+        }
+        if (n + 8 < p.N) {
+          atomicAdd(dst + (size_t)(n + 8) * ldn + k, acc[mt][nt][2]);
+          atomicAdd(dst + (size_t)(n + 8) * ldn + k + 1, acc[mt][nt][3]);
+        }
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSTM backward (one bidirectional layer; tools/hd_bwd_emul.py:lstm_dir_bwd).  Gx = W_ih x + b (saved by the forward), R = W_hh h_prev
+// for every step at once (one GEMM over the saved h), both fp32 [Bs][T][8H], column = dir * 4H + gate * H + unit (gates i, f, g, o).
+// ------------------------------------------------------------------------------------------------
+// cell state by an element-wise scan: cs[b][t][dir * H + u]
+__global__ void __launch_bounds__(256) lstm_cscan_kernel(const float* __restrict__ Gx, const float* __restrict__ R, int Bs, int T, int H,
+                                                         float* __restrict__ cs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Bs * 2 * H) return;
+  const int u = i % H, dir = (i / H) % 2, b = i / (2 * H);
+  float c = 0.0f;
+  for (int k = 0; k < T; ++k) {
+    const int t = dir ? T - 1 - k : k;
+    const size_t go = ((size_t)b * T + t) * 8 * H + (size_t)dir * 4 * H + u;
+    const float gi = sigmoidf_acc(Gx[go] + R[go]);
+    const float gf = sigmoidf_acc(Gx[go + H] + R[go + H]);
+    const float gg = tanhf(Gx[go + 2 * H] + R[go + 2 * H]);
+    c = gf * c + gi * gg;
+    cs[((size_t)b * T + t) * 2 * H + dir * H + u] = c;
+  }
+}
+
+// One step of the reverse-time chain for both directions.  Step k handles time t = T - 1 - k (dir 0) / t = k (dir 1):
+//   dh = dH[t] + W_hh^T dG[t'] (t' = the step handled by launch k - 1),  gate derivatives -> dG[t],  dc carry.
+// grid = (ceil(H / 128), 2 dirs, ceil(Bs / 8)); 128 threads: thread = unit, 8 sequences per CTA share every W_hh load.
+constexpr int LB_NB = 8;
+__global__ void __launch_bounds__(128) lstm_bwd_step_kernel(const float* __restrict__ Gx, const float* __restrict__ R, const float* __restrict__ cs,
+                                                            const float* __restrict__ dH, const float* __restrict__ Whh /*[2][4H][H]*/,
+                                                            float* __restrict__ dG, float* __restrict__ dc_carry /*[Bs][2H]*/, int Bs, int T, int H,
+                                                            int k) {
+  extern __shared__ float lb_smem[];  // [LB_NB][4H]: dG of the previous launch's time step
+  const int dir = blockIdx.y;
+  const int b0 = blockIdx.z * LB_NB;
+  const int u = blockIdx.x * 128 + threadIdx.x;
+  const int t = dir ? k : T - 1 - k;
+  const int tn = dir ? t - 1 : t + 1;   // time step of the previous launch
+  const int tp = dir ? t + 1 : t - 1;   // forward-previous time (c_prev)
+  const int nb = min(LB_NB, Bs - b0);
+  float acc[LB_NB];
+#pragma unroll
+  for (int j = 0; j < LB_NB; ++j) acc[j] = 0.0f;
+  if (k > 0) {
+    for (int i = threadIdx.x; i < nb * 4 * H; i += 128) {
+      const int j = i / (4 * H), g = i % (4 * H);
+      lb_smem[j * 4 * H + g] = dG[((size_t)(b0 + j) * T + tn) * 8 * H + (size_t)dir * 4 * H + g];
+    }
+    __syncthreads();
+    if (u < H) {
+      const float* w = Whh + (size_t)dir * 4 * H * H + u;
+      for (int g = 0; g < 4 * H; ++g) {
+        const float wv = __ldg(w + (size_t)g * H);
+#pragma unroll
+        for (int j = 0; j < LB_NB; ++j)
+          if (j < nb) acc[j] = fmaf(lb_smem[j * 4 * H + g], wv, acc[j]);
+      }
+    }
+  }
+  if (u >= H) return;
+  for (int j = 0; j < nb; ++j) {
+    const int b = b0 + j;
+    const size_t go = ((size_t)b * T + t) * 8 * H + (size_t)dir * 4 * H + u;
+    const size_t ho = ((size_t)b * T + t) * 2 * H + dir * H + u;
+    const float gi = sigmoidf_acc(Gx[go] + R[go]);
+    const float gf = sigmoidf_acc(Gx[go + H] + R[go + H]);
+    const float gg = tanhf(Gx[go + 2 * H] + R[go + 2 * H]);
+    const float go_ = sigmoidf_acc(Gx[go + 3 * H] + R[go + 3 * H]);
+    const float c = cs[ho];
+    const float cprev = (tp >= 0 && tp < T) ? cs[((size_t)b * T + tp) * 2 * H + dir * H + u] : 0.0f;
+    const float tc = tanhf(c);
+    const float dh = dH[ho] + acc[j];
+    float dc = (k > 0 ? dc_carry[(size_t)b * 2 * H + dir * H + u] : 0.0f) + dh * go_ * (1.0f - tc * tc);
+    dG[go] = dc * gg * gi * (1.0f - gi);
+    dG[go + H] = dc * cprev * gf * (1.0f - gf);
+    dG[go + 2 * H] = dc * gi * (1.0f - gg * gg);
+    dG[go + 3 * H] = dh * tc * go_ * (1.0f - go_);
+    dc_carry[(size_t)b * 2 * H + dir * H + u] = dc * gf;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// _LocalState attention backward (TA:832-857; tools/hd_bwd_emul.py:check_local_state).  qkv fp32 [(b, t)][ld]: columns [0, C) query,
+// [C, 2C) key, [2C, 3C) content, [3C, 3C + heads * nd) decay logits; dres fp32 [(b, s)][C] = gradient of the attention output.
+// One CTA = (32 queries, head, item): recomputes the softmax column W[t][s] of its queries, then
+//   dcontent[t] += sum_s W[t][s] dres[s];   dW = content dres^T;   dd = W (dW - sum_t W dW), diagonal 0;
+//   dkey[t] += sum_s dd[t][s] q[s] / sqrt(Ch);   dquery[s] = sum_t dd[t][s] k[t] / sqrt(Ch);
+//   ddecay[s][f] = -(f + 1) / sqrt(nd) * (sum_t dd[t][s] |t - s|) * sg (1 - sg) / 2.
+// dqkv (fp32, same layout as qkv) must be zero on entry (keys / content accumulate with atomics across the query tiles).
+// ------------------------------------------------------------------------------------------------
+constexpr int LAB_QT = 32;
+__global__ void __launch_bounds__(256) local_attn_bwd_kernel(const float* __restrict__ qkv, int ld, int T, int C, int heads, int nd,
+                                                             const float* __restrict__ dres, float* __restrict__ dqkv) {
+  extern __shared__ float lab_smem[];
+  const int Ch = C / heads, Chp = Ch + 1;
+  float* Ks = lab_smem;                          // [T][Chp]
+  float* Vs = Ks + (size_t)T * Chp;              // [T][Chp]
+  float* Ws = Vs + (size_t)T * Chp;              // [T][LAB_QT + 1]  softmax weights
+  float* Ds = Ws + (size_t)T * (LAB_QT + 1);     // [T][LAB_QT + 1]  dW, then dd
+  float* Qs = Ds + (size_t)T * (LAB_QT + 1);     // [LAB_QT][Chp]
+  float* Gs = Qs + LAB_QT * Chp;                 // [LAB_QT][Chp]    dres tile
+  float* Dc = Gs + LAB_QT * Chp;                 // [LAB_QT]         decay slope
+  float* Rs = Dc + LAB_QT;                       // [LAB_QT]         sum_t W dW
+  float* As = Rs + LAB_QT;                       // [LAB_QT]         sum_t dd |t - s|
+  const int tid = threadIdx.x;
+  const int hd = blockIdx.y, b = blockIdx.z;
+  const int s0 = blockIdx.x * LAB_QT;
+  const float* base = qkv + (size_t)b * T * ld;
+  const float* gbase = dres + (size_t)b * T * C;
+  float* obase = dqkv + (size_t)b * T * ld;
+  for (int i = tid; i < T * Ch; i += 256) {
+    const int t = i / Ch, c = i % Ch;
+    Ks[t * Chp + c] = base[(size_t)t * ld + C + hd * Ch + c];
+    Vs[t * Chp + c] = base[(size_t)t * ld + 2 * C + hd * Ch + c];
+  }
+  for (int i = tid; i < LAB_QT * Ch; i += 256) {
+    const int sl = i / Ch, c = i % Ch;
+    const bool ok = s0 + sl < T;
+    Qs[sl * Chp + c] = ok ? base[(size_t)(s0 + sl) * ld + hd * Ch + c] : 0.0f;
+    Gs[sl * Chp + c] = ok ? gbase[(size_t)(s0 + sl) * C + hd * Ch + c] : 0.0f;
+  }
+  if (tid < LAB_QT) {
+    float d = 0.0f;
+    if (s0 + tid < T)
+      for (int f = 0; f < nd; ++f) d += (float)(f + 1) * (sigmoidf_acc(base[(size_t)(s0 + tid) * ld + 3 * C + hd * nd + f]) * 0.5f);
+    Dc[tid] = d / sqrtf((float)nd);
+  }
+  __syncthreads();
+  const float inv = 1.0f / sqrtf((float)Ch);
+  for (int i = tid; i < T * LAB_QT; i += 256) {
+    const int t = i / LAB_QT, sl = i % LAB_QT;
+    const int s = s0 + sl;
+    float acc = 0.0f, accd = 0.0f;
+    for (int c = 0; c < Ch; ++c) {
+      acc = fmaf(Ks[t * Chp + c], Qs[sl * Chp + c], acc);
+      accd = fmaf(Vs[t * Chp + c], Gs[sl * Chp + c], accd);
+    }
+    float v = acc * inv - fabsf((float)(t - s)) * Dc[sl];
+    if (t == s) v = -100.0f;
+    Ws[t * (LAB_QT + 1) + sl] = v;
+    Ds[t * (LAB_QT + 1) + sl] = accd;   // dW[t][s] = content[t] . dres[s]
+  }
+  __syncthreads();
+  {  // softmax over t per query, then rowsum = sum_t W dW: one warp handles 4 queries
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int sl = warp * 4; sl < warp * 4 + 4; ++sl) {
+      float mx = -INFINITY;
+      for (int t = lane; t < T; t += 32) mx = fmaxf(mx, Ws[t * (LAB_QT + 1) + sl]);
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.0f;
+      for (int t = lane; t < T; t += 32) {
+        const float e = expf(Ws[t * (LAB_QT + 1) + sl] - mx);
+        Ws[t * (LAB_QT + 1) + sl] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      const float rinv = 1.0f / sum;
+      float rs = 0.0f;
+      for (int t = lane; t < T; t += 32) {
+        const float w = Ws[t * (LAB_QT + 1) + sl] * rinv;
+        Ws[t * (LAB_QT + 1) + sl] = w;
+        rs = fmaf(w, Ds[t * (LAB_QT + 1) + sl], rs);
+      }
+      rs = warp_sum(rs);
+      const int s = s0 + sl;
+      float as = 0.0f;
+      for (int t = lane; t < T; t += 32) {
+        float dd = Ws[t * (LAB_QT + 1) + sl] * (Ds[t * (LAB_QT + 1) + sl] - rs);
+        if (t == s || s >= T) dd = 0.0f;   // masked diagonal: no gradient; padded queries contribute nothing
+        Ds[t * (LAB_QT + 1) + sl] = dd;
+        as = fmaf(dd, fabsf((float)(t - s)), as);
+      }
+      as = warp_sum(as);
+      if (lane == 0) { Rs[sl] = rs; As[sl] = as; }
+    }
+  }
+  __syncthreads();
+  // dcontent[t][c] += sum_s W[t][s] dres[s][c];  dkey[t][c] += sum_s dd[t][s] q[s][c] * inv
+  for (int i = tid; i < T * Ch; i += 256) {
+    const int t = i / Ch, c = i % Ch;
+    float av = 0.0f, ak = 0.0f;
+    for (int sl = 0; sl < LAB_QT; ++sl) {
+      if (s0 + sl >= T) break;
+      av = fmaf(Ws[t * (LAB_QT + 1) + sl], Gs[sl * Chp + c], av);
+      ak = fmaf(Ds[t * (LAB_QT + 1) + sl], Qs[sl * Chp + c], ak);
+    }
+    atomicAdd(obase + (size_t)t * ld + 2 * C + hd * Ch + c, av);
+    atomicAdd(obase + (size_t)t * ld + C + hd * Ch + c, ak * inv);
+  }
+  // dquery[s][c] = sum_t dd[t][s] k[t][c] * inv
+  for (int i = tid; i < LAB_QT * Ch; i += 256) {
+    const int sl = i / Ch, c = i % Ch;
+    const int s = s0 + sl;
+    if (s >= T) continue;
+    float aq = 0.0f;
+    for (int t = 0; t < T; ++t) aq = fmaf(Ds[t * (LAB_QT + 1) + sl], Ks[t * Chp + c], aq);
+    obase[(size_t)s * ld + hd * Ch + c] = aq * inv;
+  }
+  if (tid < LAB_QT * nd) {
+    const int sl = tid / nd, f = tid % nd;
+    const int s = s0 + sl;
+    if (s < T) {
+      const float sg = sigmoidf_acc(base[(size_t)s * ld + 3 * C + hd * nd + f]);
+      obase[(size_t)s * ld + 3 * C + hd * nd + f] = -(float)(f + 1) / sqrtf((float)nd) * As[sl] * sg * (1.0f - sg) * 0.5f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The four "narrow" layers: first encoders (1 or 2 input channels -> C, k 8, stride 4, TA:124) and last decoders (C -> 1 or 2,
+// transposed k 8 stride 4, TA:243).  With `wide` the C-channel side ([line][x][C]) and `narrow` the P-channel side ([line][n][P]):
+//   narrow position of (wide row x, tap j):  n = x * S + j - pad        weight w[c][p][j]  (Conv [Co][Ci][k] / ConvTranspose [Ci][Co][k])
+//   ENC:  pre[x][c] = b_c + sum_{j,p} w[c][p][j] nv[n][p];  wide value = dwide[x][c] * gelu'(pre)   (the forward fuses GELU: pre is recomputed)
+//         dW[c][p][j] += wide value * nv[n][p],  db[c] += wide value
+//   DEC:  wide value = y[x][c];  dW[c][p][j] += y * nv[n][p];  dy[x][c] = sum_{j,p} w[c][p][j] nv[n][p]  (nv = output gradient);  db[p] = sum nv
+// nv = (raw - sub_b) * mul_b * (ck ? (n == 0 ? 1 : 2) : 1): input normalisation (TA:553-563) on the way in, de-normalisation and the
+// irfft bin weights on the way out.
+// ------------------------------------------------------------------------------------------------
+struct NarrowP {
+  const float* narrow; long long n_line;   // line stride (elements); lines = B * Y
+  int Xn;                                   // narrow positions per line
+  const float* stats;                       // per item (mean, std) or nullptr
+  int norm_mode;                            // 0: nv = raw; 1: (raw - mean) / (1e-5 + std); 2: raw * std
+  int ck;                                   // 1: multiply by (n == 0 ? 1 : 2)
+  int Y;                                    // lines per item
+  int Xw, C, S, pad;                        // wide extent per line, channels, stride, padding
+  const float* w; const float* bias;        // [C][P][K], [C] (ENC) or [P] (DEC)
+  const float* dwide;                       // ENC: gradient of the wide activation, fp32
+  const __nv_bfloat16* yhi; const __nv_bfloat16* ylo;  // DEC: wide activation planes
+  float* dy;                                // DEC: gradient of the wide activation (written)
+  float* dW; float* db;
+  int rows_per_cta;
+};
+
+template <int K, int P, bool ENC>
+__global__ void __launch_bounds__(256) narrow_bwd_kernel(const NarrowP p) {
+  extern __shared__ float nb_smem[];  // [C * P * K] weights, [C * P * K + C] accumulators
+  const int C = p.C, WN = C * P * K;
+  float* sw = nb_smem;
+  float* sa = nb_smem + WN;
+  for (int i = threadIdx.x; i < WN; i += 256) sw[i] = p.w[i];
+  for (int i = threadIdx.x; i < WN + C; i += 256) sa[i] = 0.0f;
+  __syncthreads();
+  const int groups = C / 8, rows = 256 / groups;
+  const int g8 = threadIdx.x % groups, r = threadIdx.x / groups, c0 = g8 * 8;
+  const int line = blockIdx.y, b = line / p.Y;
+  float sub = 0.0f, mul = 1.0f;
+  if (p.stats) {
+    if (p.norm_mode == 1) { sub = p.stats[2 * b]; mul = 1.0f / (1e-5f + p.stats[2 * b + 1]); }
+    else if (p.norm_mode == 2) { mul = p.stats[2 * b + 1]; }
+  }
+  const float* nl = p.narrow + (size_t)line * p.n_line;
+  float accw[8][P * K];
+  float accb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    accb[i] = 0.0f;
+#pragma unroll
+    for (int q = 0; q < P * K; ++q) accw[i][q] = 0.0f;
+  }
+  const int x_begin = blockIdx.x * p.rows_per_cta, x_end = min(p.Xw, x_begin + p.rows_per_cta);
+  if (r < rows) {
+    for (int x = x_begin + r; x < x_end; x += rows) {
+      float nv[P * K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const int n = x * p.S + j - p.pad;
+        const bool ok = n >= 0 && n < p.Xn;
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+          float v = 0.0f;
+          if (ok) {
+            v = (nl[(size_t)n * P + q] - sub) * mul;
+            if (p.ck && n != 0) v *= 2.0f;
+          }
+          nv[q * K + j] = v;
+        }
+      }
+      const size_t woff = ((size_t)line * p.Xw + x) * C + c0;
+      float wide[8];
+      if (ENC) {
+        const float4 d0 = *reinterpret_cast<const float4*>(p.dwide + woff), d1 = *reinterpret_cast<const float4*>(p.dwide + woff + 4);
+        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float pre = p.bias[c0 + i];
+#pragma unroll
+          for (int q = 0; q < P * K; ++q) pre = fmaf(sw[(c0 + i) * P * K + q], nv[q], pre);
+          wide[i] = dv[i] * gelu_grad(pre);
+          accb[i] += wide[i];
+        }
+      } else {
+        bw_load_split8(p.yhi, p.ylo, woff, wide);
+        float dyv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a = 0.0f;
+#pragma unroll
+          for (int q = 0; q < P * K; ++q) a = fmaf(sw[(c0 + i) * P * K + q], nv[q], a);
+          dyv[i] = a;
+        }
+        *reinterpret_cast<float4*>(p.dy + woff) = make_float4(dyv[0], dyv[1], dyv[2], dyv[3]);
+        *reinterpret_cast<float4*>(p.dy + woff + 4) = make_float4(dyv[4], dyv[5], dyv[6], dyv[7]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int q = 0; q < P * K; ++q) accw[i][q] = fmaf(wide[i], nv[q], accw[i][q]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int q = 0; q < P * K; ++q) atomicAdd(&sa[(c0 + i) * P * K + q], accw[i][q]);
+      if (ENC) atomicAdd(&sa[WN + c0 + i], accb[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < WN; i += 256) atomicAdd(p.dW + i, sa[i]);
+  if (ENC)
+    for (int i = threadIdx.x; i < C; i += 256) atomicAdd(p.db + i, sa[WN + i]);
+}
+
+// DEC bias gradient: db[q] += sum over every narrow position of nv (each output position receives the bias once)
+template <int P>
+__global__ void __launch_bounds__(256) narrow_bias_kernel(const NarrowP p) {
+  __shared__ float red[P][8];
+  const int line = blockIdx.y, b = line / p.Y;
+  float mul = 1.0f;
+  if (p.stats && p.norm_mode == 2) mul = p.stats[2 * b + 1];
+  const float* nl = p.narrow + (size_t)line * p.n_line;
+  float acc[P];
+#pragma unroll
+  for (int q = 0; q < P; ++q) acc[q] = 0.0f;
+  for (int n = blockIdx.x * 256 + threadIdx.x; n < p.Xn; n += gridDim.x * 256) {
+    const float f = (p.ck && n != 0) ? 2.0f * mul : mul;
+#pragma unroll
+    for (int q = 0; q < P; ++q) acc[q] = fmaf(nl[(size_t)n * P + q], f, acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < P; ++q) {
+    acc[q] = warp_sum(acc[q]);
+    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = acc[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < P) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    atomicAdd(p.db + threadIdx.x, t);
+  }
+}
+
+// ---- iSTFT adjoint, step 1: ghat[b][P0 + i] = dout[b][i] / envelope(i), zero in the P0 / P1 pads (TA:941-961 backward).
+//      envelope(i) = sum over the frames t in [-env_pad, F + env_pad) covering i of window[i + frame_off - t * hop]^2 ----
+__global__ void __launch_bounds__(256) istft_adj_prep_kernel(const float* __restrict__ dout, int T, const float* __restrict__ window, int n_fft, int hop,
+                                                             int frame_off, int F, int env_pad, int P0, int Ltot, float* __restrict__ ghat) {
+  const long long j = blockIdx.x * 256ll + threadIdx.x;
+  const int b = blockIdx.y;
+  if (j >= Ltot) return;
+  const long long i = j - P0;
+  float v = 0.0f;
+  if (i >= 0 && i < T) {
+    const long long pos = i + frame_off;
+    long long t_hi = pos >= 0 ? pos / hop : -((-pos + hop - 1) / hop);
+    if (t_hi > F + env_pad - 1) t_hi = F + env_pad - 1;
+    float env = 0.0f;
+    for (long long t = t_hi; t >= -env_pad; --t) {
+      const long long n = pos - t * hop;
+      if (n >= n_fft) break;
+      const float w = window[n];
+      env = fmaf(w, w, env);
+    }
+    v = dout[(size_t)b * T + i] / env;
+  }
+  ghat[(size_t)b * Ltot + j] = v;
+}
+
+}  // namespace hd
+}  // namespace rfx

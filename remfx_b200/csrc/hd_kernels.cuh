@@ -2,7 +2,7 @@
 // Activations are channel-last (B, Y, X, C): freq-branch tensors use Y = time frame, X = frequency bin group;
 // time-branch tensors use Y = 1, X = time.  "split" = two bf16 planes (hi, lo), see gemm2.cu.
 #pragma once
-#include "kernels.h"
+#include "hd_internal.h"
 
 namespace rfx {
 namespace hd {
@@ -261,16 +261,9 @@ __global__ void gn_final_kernel(const double* __restrict__ accum, long long coun
 // mode 0: y = gn(raw)                     (Co >= Cr; padded channels are written as zero)
 // mode 1: y = gelu(gn(raw))
 // mode 2: y = gn(raw)[c] * sigmoid(gn(raw)[c + Co'])  with Co' = Cr / 2 (GLU over channels)
+// mode 3: y = raw[2c] * sigmoid(raw[2c + 1])            (GLU over interleaved (value, gate) column pairs: the layout the
+//         un-normalised layers' weights are packed in for the fused epilogue; training forward only, stats == nullptr)
 // then  y = y * scale[c] (if scale) ; y += res (if res: split (B, Y, Xo, Co)).  stats == nullptr -> identity norm.
-struct GnApply {
-  const float* raw; int Y, Xr, Cr;
-  const float* stats; int G, per_x;
-  const float* gamma; const float* beta;
-  int mode;
-  const float* scale;
-  const __nv_bfloat16* rhi; const __nv_bfloat16* rlo;
-  __nv_bfloat16* ohi; __nv_bfloat16* olo; int Xo, Co, x_off;
-};
 __device__ __forceinline__ void ld8f(const float* p, float (&o)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
@@ -289,10 +282,22 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApply a) {
   const int xr = x + a.x_off;
   const float* r = a.raw + (((size_t)b * a.Y + y) * a.Xr + xr) * a.Cr;
   const int seg = a.per_x ? b * a.Xr + xr : b;
-  const int cvalid = a.mode == 2 ? a.Cr / 2 : a.Cr;
+  const int cvalid = a.mode >= 2 ? a.Cr / 2 : a.Cr;
   const int cpg = a.Cr / a.G;
   float o[8];
-  if (VEC) {
+  if (a.mode == 3) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      float v = 0.0f;
+      if (c < cvalid) {
+        const float2 pr = *reinterpret_cast<const float2*>(r + 2 * c);
+        v = pr.x * sigmoidf_fast(pr.y);
+        if (a.scale) v *= a.scale[c];
+      }
+      o[i] = v;
+    }
+  } else if (VEC) {
     if (c0 < cvalid) {
       ld8f(r + c0, o);
       if (a.stats) {
@@ -572,16 +577,6 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const float* __restrict
 }
 
 // ---- weight gather for the implicit-GEMM convolutions (see hdemucs.cu: ConvSpec) ----
-struct GatherSpec {
-  int kind;      // 0 plain (taps = k, or kh*kw), 1 strided (regrouped by s), 2 transposed (regrouped by s)
-  int Co, Ci, k; // logical conv dims; k = kernel extent along the conv axis (kh * kw for 2-D plain)
-  int s, p;      // stride / padding (kinds 1, 2)
-  int tau_min;   // first group offset (kind 1)
-  int taps;      // number of GEMM taps
-  int Kp;        // padded K per tap (multiple of 64)
-  int glu;       // interleave output rows (value c, gate c) -> (2c, 2c+1)
-  int Nout;      // GEMM N
-};
 __global__ void gather_w_kernel(const float* __restrict__ w, const float* __restrict__ bias, GatherSpec g, float* __restrict__ wcat,
                                 float* __restrict__ bcat) {
   const long long total = (long long)g.Nout * g.taps * g.Kp;

@@ -19,82 +19,22 @@
 #include <string>
 #include <vector>
 
-namespace rfx {
-namespace hd {
-
-struct Buf {
-  float* p = nullptr;
-  size_t n = 0;
-  int alloc(size_t count) {
-    release();
-    RFX_CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(float)));
-    n = count;
-    return 0;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    n = 0;
-  }
-};
-
-// channel-last activation (B, Y, X, C): split planes (hi, lo = hi + plane) or fp32
-struct Ten {
-  int B = 0, Y = 1, X = 0, C = 0;
-  __nv_bfloat16* hi = nullptr;
-  size_t plane = 0;
-  float* f = nullptr;
-  __nv_bfloat16* lo() const { return hi + plane; }
-  size_t elems() const { return (size_t)B * Y * X * C; }
-};
-
-// one convolution prepared for gemm2
-struct Conv {
-  GatherSpec g{};
-  SplitW w;
-  Buf wbuf;   // split planes
-  Buf bias;   // [Nout] (re-ordered like the GEMM columns)
-  int Ci = 0, Co = 0;
-  int kh = 1, kw = 1;  // 2-D plain convs (kh along X = freq, kw along Y = time)
-  int crop = 0;        // transposed convs: samples cropped on each side of the output (TA:288-294)
-};
-
-}  // namespace hd
-}  // namespace rfx
-
 using namespace rfx;
 using namespace rfx::hd;
-
-struct rfx_hdemucs {
-  rfx_hdemucs_config cfg;
-  std::map<std::string, Buf> params;
-  std::map<std::string, Conv> convs;
-  std::map<std::string, Buf> whh;  // "<blstm>.l<layer>": W_hh of both directions [2][4H][H]
-  bool finalized = false;
-  // debug taps of the last call: name -> tensor descriptor
-  std::map<std::string, Ten> taps;
-  bool want_taps = false;
-  ~rfx_hdemucs() {
-    for (auto& kv : params) kv.second.release();
-    for (auto& kv : convs) { kv.second.wbuf.release(); kv.second.bias.release(); }
-    for (auto& kv : whh) kv.second.release();
-  }
-};
 
 __global__ void hd_unsplit_kernel(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* o, long long n) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) o[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
 }
-static void hd_unsplit(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* o, long long n, cudaStream_t s) {
+namespace rfx {
+namespace hd {
+void hd_unsplit(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* o, long long n, cudaStream_t s) {
   hd_unsplit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(hi, lo, o, n);
 }
+}  // namespace hd
+}  // namespace rfx
 
 namespace {
-
-const float* HP(const rfx_hdemucs* h, const std::string& k) {
-  auto it = h->params.find(k);
-  return it == h->params.end() ? nullptr : it->second.p;
-}
 
 int prep_conv(rfx_hdemucs* h, const std::string& name, int kind, int Co, int Ci, int k, int s, int p, int glu, int kh, int kw, Buf& tmp,
               cudaStream_t st, const std::string& wkey_in = "", const std::string& bkey_in = "") {
@@ -109,6 +49,8 @@ int prep_conv(rfx_hdemucs* h, const std::string& name, int kind, int Co, int Ci,
   }
   Conv& c = h->convs[name];
   c.Ci = Ci; c.Co = Co; c.kh = kh; c.kw = kw;
+  c.wkey = wkey; c.bkey = h->params.count(bkey) ? bkey : std::string();
+  c.wt_ready = false;  // the transposed pack of the backward is rebuilt lazily from the new weights
   GatherSpec& g = c.g;
   g.kind = kind; g.Co = Co; g.Ci = Ci; g.k = k; g.s = s; g.p = p; g.glu = glu;
   if (kind == 0) {
@@ -131,8 +73,7 @@ int prep_conv(rfx_hdemucs* h, const std::string& name, int kind, int Co, int Ci,
   if (c.wbuf.alloc(split_weight_elems(g.Nout, g.taps * g.Kp, BN))) return 1;
   int rc = pack_split_weights(tmp.p, (long long)g.taps * g.Kp, g.Nout, g.taps * g.Kp, BN, reinterpret_cast<__nv_bfloat16*>(c.wbuf.p), &c.w, st);
   if (rc) return rc;
-  RFX_CHECK_CUDA(cudaStreamSynchronize(st));  // tmp is reused by the next conv
-  return 0;
+  return 0;  // tmp is reused by the next conv: same stream, so the reuse is ordered
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -145,13 +86,18 @@ struct Runner {
   size_t off = 0;
   bool dry;
   cudaStream_t s;
+  bool train = false;  // training forward: every conv keeps its fp32 pre-activation, ops are recorded on h->tape
   int rc = 0;
   int launches = 0;
 
   void* take(size_t bytes) {
     const size_t r = off;
     off += align_up(bytes, 256);
-    return dry ? nullptr : ws + r;
+    // a dry run hands out distinct fake addresses (never dereferenced) so that a dry TRAINING run can still key its tape by tensor
+    return dry ? reinterpret_cast<void*>((uintptr_t)4096 + r) : ws + r;
+  }
+  void record(const Op& op) {
+    if (train) h->tape.push_back(op);
   }
   Ten split(int Bn, int Y, int X, int C) {
     Ten t; t.B = Bn; t.Y = Y; t.X = X; t.C = C;
@@ -165,7 +111,7 @@ struct Runner {
     return t;
   }
   void tap(const std::string& name, const Ten& t) {
-    if (h->want_taps && !dry) h->taps[name] = t;
+    if ((h->want_taps || train) && !dry) h->taps[name] = t;
   }
   bool ok() const { return rc == 0; }
   void chk() {
@@ -207,6 +153,12 @@ struct Runner {
       }
     }
     const int Nout = g.Nout;
+    if (train && !out_f32 && !dst) {
+      // training: keep the pre-activation.  conv (bias only) -> fp32, then the activation as its own (recorded) element-wise op
+      Ten raw = conv(name, in, axis, dil, pad, true, ACT_NONE);
+      const int mode = act == ACT_GELU ? 1 : (act == ACT_GLU_PAIR ? 3 : 0);
+      return gn_apply(raw, nullptr, 1, 0, nullptr, nullptr, mode, nullptr, nullptr, raw.X, 0, 0);
+    }
     const int Cout_store = act == ACT_GLU_PAIR ? Nout / 2 : Nout;
     Ten out;
     if (dst) out = *dst;  // write columns [dst_col, dst_col + N) of an existing fp32 tensor
@@ -223,6 +175,14 @@ struct Runner {
       gst = reinterpret_cast<float*>(take((size_t)nseg * gn_G * 2 * 4));
       gcount = (gn_per_x ? (long long)Yo : (long long)Yo * Xs) * (gn_cmod / gn_G);
       if (gn_out) *gn_out = gst;
+    }
+    pr.A.hi = in.hi; pr.A.rows = Xv; pr.A.rows_y = in.Y; pr.A.ld = Cv; pr.A.ld_y = (long long)Xv * Cv;
+    pr.A.batch_stride = (long long)in.Y * Xv * Cv; pr.A.plane_stride = (long long)in.plane;
+    pr.M = Xo; pr.My = Yo; pr.N = Nout; pr.batch = in.B; pr.Ktap = Cv; pr.taps = g.taps;
+    if (train) {  // (also in a dry run: the backward is sized from the tape)
+      if (!out_f32 && !dst) { set_error("hdemucs: internal: training conv must produce fp32"); rc = 2; return out; }
+      Op op; op.kind = OP_CONV; op.name = name; op.in = in; op.out = out; op.pr = pr; op.dst_col = dst ? dst_col : 0;
+      record(op);
     }
     if (dry || rc) { launches += gn_G > 0 ? 3 : 1; return out; }
     if (gn_G > 0 && cudaMemsetAsync(gacc, 0, (size_t)nseg * gn_G * 2 * 8, s) != cudaSuccess) { set_error("memset failed"); rc = 1; return out; }
@@ -267,12 +227,29 @@ struct Runner {
     return st;
   }
 
+  // parameter keys of the NEXT gn_apply's gamma / beta / scale (training: where their gradients go); set via P()
+  std::string pending_gamma, pending_beta, pending_scale;
+  const float* P(const std::string& key, int which) {
+    (which == 0 ? pending_gamma : (which == 1 ? pending_beta : pending_scale)) = key;
+    return HP(h, key);
+  }
+
   // ---- norm (optional) + activation (+ LayerScale, + residual) -> split ----
   Ten gn_apply(const Ten& raw, const float* stats, int G, int per_x, const float* gamma, const float* beta, int mode, const float* scale,
                const Ten* res, int Xo, int x_off, int Cpad) {
-    const int Cvalid = mode == 2 ? raw.C / 2 : raw.C;
+    const int Cvalid = mode >= 2 ? raw.C / 2 : raw.C;
     const int Co = Cpad > 0 ? Cpad : ceil_div(Cvalid, 8) * 8;
     Ten out = split(raw.B, raw.Y, Xo, Co);
+    if (train) {
+      Op op; op.kind = OP_GN; op.in = raw; op.out = out; if (res) op.in2 = *res;
+      GnApply& ga = op.gn;
+      ga.raw = raw.f; ga.Y = raw.Y; ga.Xr = raw.X; ga.Cr = raw.C; ga.stats = stats; ga.G = G; ga.per_x = per_x; ga.gamma = gamma; ga.beta = beta;
+      ga.mode = mode; ga.scale = scale; ga.rhi = res ? res->hi : nullptr; ga.rlo = res ? res->lo() : nullptr;
+      ga.ohi = out.hi; ga.olo = out.lo(); ga.Xo = Xo; ga.Co = Co; ga.x_off = x_off;
+      op.p_gamma = pending_gamma; op.p_beta = pending_beta; op.p_scale = pending_scale;
+      record(op);
+    }
+    pending_gamma.clear(); pending_beta.clear(); pending_scale.clear();
     if (dry || rc) { ++launches; return out; }
     GnApply a{};
     a.raw = raw.f; a.Y = raw.Y; a.Xr = raw.X; a.Cr = raw.C;
@@ -291,6 +268,7 @@ struct Runner {
 
   Ten add_crop(const Ten& a, int x_off, const Ten& skip) {
     Ten out = split(skip.B, skip.Y, skip.X, skip.C);
+    if (train) { Op op; op.kind = OP_ADDCROP; op.in = a; op.in2 = skip; op.out = out; op.i0 = x_off; record(op); }
     if (dry || rc) { ++launches; return out; }
     const long long items = (long long)skip.Y * skip.X * (skip.C / 8);
     add_crop_kernel<<<dim3((unsigned)((items + 255) / 256), skip.B), 256, 0, s>>>(a.hi, a.lo(), a.X, x_off, skip.hi, skip.lo(), out.hi, out.lo(),
@@ -309,6 +287,7 @@ struct Runner {
     Ten cur = x;
     if (framed) {
       cur = split(Bn * nf, 1, Tf, C);
+      if (train) { Op op; op.kind = OP_FRAME; op.in = x; op.out = cur; op.i0 = nf; op.i1 = width; op.i2 = stride; record(op); }
       if (!dry && ok()) {
         const long long items = (long long)Tf * (C / 8);
         blstm_frame_kernel<<<dim3((unsigned)((items + 255) / 256), Bn * nf), 256, 0, s>>>(x.hi, x.lo(), Tn, C, nf, width, stride, cur.hi, cur.lo());
@@ -321,6 +300,7 @@ struct Runner {
       conv(base + ".lstm.ih" + std::to_string(l) + "f", cur, 0, 1, 0, true, ACT_NONE, &G, 0);
       conv(base + ".lstm.ih" + std::to_string(l) + "r", cur, 0, 1, 0, true, ACT_NONE, &G, 4 * C);
       Ten hout = split(Bs, 1, Tf, 2 * C);
+      if (train) { Op op; op.kind = OP_LSTM; op.name = base; op.in = cur; op.aux = G; op.out = hout; op.i0 = l; record(op); }
       if (!dry && ok()) {
         rc = launch_lstm_layer(G.f, 8 * C, h->whh[base + ".l" + std::to_string(l)].p, nullptr, 0, hout.hi, hout.lo(), 2 * C, Bs, Tf, C, s);
       }
@@ -329,6 +309,7 @@ struct Runner {
     }
     Ten lin = conv(base + ".linear", cur, 0, 1, 0, true, ACT_NONE);  // fp32 (Bs, 1, Tf, C)
     Ten out = split(Bn, 1, Tn, C);
+    if (train) { Op op; op.kind = OP_MERGE; op.in = lin; op.in2 = x; op.out = out; op.i0 = nf; op.i1 = Tf; op.i2 = stride; record(op); }
     if (!dry && ok()) {
       const long long items = (long long)Tn * (C / 8);
       blstm_merge_kernel<<<dim3((unsigned)((items + 255) / 256), Bn), 256, 0, s>>>(lin.f, Tn, C, nf, Tf, stride, x.hi, x.lo(), out.hi, out.lo());
@@ -347,6 +328,7 @@ struct Runner {
     conv(base + ".content", x, 0, 1, 0, true, ACT_NONE, &qkv, 2 * C);
     conv(base + ".query_decay", x, 0, 1, 0, true, ACT_NONE, &qkv, 3 * C);
     Ten res = split(Bn, 1, Tn, C);
+    if (train) { Op op; op.kind = OP_ATTN; op.in = qkv; op.out = res; op.i0 = heads; op.i1 = nd; record(op); }
     if (!dry && ok()) {
       const int Ch = C / heads;
       const size_t smem = ((size_t)2 * Tn * (Ch + 1) + (size_t)Tn * (LA_QT + 1) + (size_t)LA_QT * (Ch + 1) + LA_QT) * 4;
@@ -368,7 +350,7 @@ struct Runner {
       // conv k=3 (dilated) -> GroupNorm(1, h) -> GELU
       float* st1 = nullptr;
       Ten r1 = conv(L + ".0", y, axis, dil, dil, true, ACT_NONE, nullptr, 0, 1, per_x, &st1);
-      Ten a1 = gn_apply(r1, st1, 1, per_x, HP(h, L + ".1.weight"), HP(h, L + ".1.bias"), 1, nullptr, nullptr, r1.X, 0, 0);
+      Ten a1 = gn_apply(r1, st1, 1, per_x, P(L + ".1.weight", 0), P(L + ".1.bias", 1), 1, nullptr, nullptr, r1.X, 0, 0);
       tap(L + ".2", a1);
       int ci = 3;
       if (lstm_attn) {
@@ -386,14 +368,17 @@ struct Runner {
       float* st2 = nullptr;
       Ten r2 = conv(L + "." + std::to_string(ci), a1, 0, 1, 0, true, ACT_NONE, nullptr, 0, 1, per_x, &st2);
       const std::string gn2 = L + "." + std::to_string(ci + 1), ls = L + "." + std::to_string(ci + 3);
-      y = gn_apply(r2, st2, 1, per_x, HP(h, gn2 + ".weight"), HP(h, gn2 + ".bias"), 2, HP(h, ls + ".scale"), &y, r2.X, 0, 0);
+      y = gn_apply(r2, st2, 1, per_x, P(gn2 + ".weight", 0), P(gn2 + ".bias", 1), 2, P(ls + ".scale", 2), &y, r2.X, 0, 0);
     }
     return y;
   }
 };
 
-int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_t* ws, bool dry, cudaStream_t s, size_t* bytes, int* launches) {
+int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_t* ws, bool dry, bool train, cudaStream_t s, size_t* bytes,
+                int* launches) {
   Runner R{h, B, T, ws, 0, dry, s};
+  R.train = train;
+  if (train) { h->tape.clear(); h->tape_B = B; h->tape_T = T; h->tape_ws = ws; h->act_grads.clear(); }
   const int nfft = h->cfg.nfft, hl = nfft / 4, bins = nfft / 2, depth = h->cfg.depth, ch0 = h->cfg.channels;
   const int le = ceil_div(T, hl);
   const bool lstm_attn_from = true;
@@ -405,6 +390,7 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
   float* st_f = reinterpret_cast<float*>(R.take((size_t)B * 2 * 4));
   float* st_t = reinterpret_cast<float*>(R.take((size_t)B * 2 * 4));
   float* xt = reinterpret_cast<float*>(R.take((size_t)B * T * 4));
+  if (train) { h->st_f = st_f; h->st_t = st_t; }
   if (!dry) {
     StftParams sp{};
     sp.x = x; sp.x_bstride = T; sp.T = T; sp.x_aligned8 = 0;
@@ -437,6 +423,10 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
       if (idx == 0) {
         const int Lo = T / h->cfg.stride;
         tcur = R.split(B, 1, Lo, ch0);
+        if (train) {
+          Op op; op.kind = OP_TIMEFIRST; op.name = te + ".conv"; op.out = tcur; op.fp0 = xt; op.i0 = T; op.i1 = h->cfg.stride; op.i2 = h->cfg.kernel_size / 4;
+          R.record(op);
+        }
         if (!dry) {
           const long long items = (long long)Lo * (ch0 / 8);
           time_first_kernel<8><<<dim3((unsigned)((items + 255) / 256), B), 256, (8 + 1) * ch0 * 4, s>>>(
@@ -458,6 +448,11 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
       if (idx == 0) {  // 2 -> C channels: SIMT kernel that normalises (TA:553-557) on the fly
         const int Fo = bins / h->cfg.stride;
         xcur = R.split(B, le, Fo, ch0);
+        if (train) {
+          Op op; op.kind = OP_FREQFIRST; op.name = fe + ".conv"; op.out = xcur; op.fp0 = reinterpret_cast<const float*>(Z); op.fp1 = st_f;
+          op.i0 = bins; op.i1 = h->cfg.stride; op.i2 = h->cfg.kernel_size / 4;
+          R.record(op);
+        }
         if (!dry && R.ok()) {
           const long long items = (long long)le * Fo * (ch0 / 8);
           freq_first_kernel<8><<<dim3((unsigned)((items + 255) / 256), B), 256, (2 * 8 + 1) * ch0 * 4, s>>>(
@@ -471,6 +466,7 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
         Ten raw = R.conv(fe + ".conv", xcur, 0, 1, 0, true, ACT_NONE);  // (B, T, 1, C)
         if (last_freq) {  // y = y + inject (TA:164-169); both are [B][T][C] in memory
           Ten sum = R.f32(raw.B, raw.Y, raw.X, raw.C);
+          if (train) { Op op; op.kind = OP_ADDF32; op.in = raw; op.in2 = inject; op.out = sum; R.record(op); }
           if (!dry && R.ok()) {
             add_f32_kernel<<<(unsigned)((raw.elems() + 255) / 256), 256, 0, s>>>(raw.f, inject.f, sum.f, (long long)raw.elems());
             R.chk();
@@ -478,7 +474,7 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
           raw = sum;
         }
         float* st = R.gn_stats(raw, h->cfg.norm_groups, 0);
-        xcur = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fe + ".norm1.weight"), HP(h, fe + ".norm1.bias"), 1, nullptr, nullptr, raw.X, 0, 0);
+        xcur = R.gn_apply(raw, st, h->cfg.norm_groups, 0, R.P(fe + ".norm1.weight", 0), R.P(fe + ".norm1.bias", 1), 1, nullptr, nullptr, raw.X, 0, 0);
       }
       R.tap(fe + ".act1", xcur);
       xcur = R.dconv(fe + ".dconv", xcur, 1, 1, lstm_attn);
@@ -487,9 +483,13 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
       } else {
         float* st = nullptr;
         Ten raw = R.conv(fe + ".rewrite", xcur, 0, 1, 0, true, ACT_NONE, nullptr, 0, h->cfg.norm_groups, 0, &st);
-        xcur = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fe + ".norm2.weight"), HP(h, fe + ".norm2.bias"), 2, nullptr, nullptr, raw.X, 0, 0);
+        xcur = R.gn_apply(raw, st, h->cfg.norm_groups, 0, R.P(fe + ".norm2.weight", 0), R.P(fe + ".norm2.bias", 1), 2, nullptr, nullptr, raw.X, 0, 0);
       }
       if (idx == 0 && h->cfg.freq_emb_weight != 0.0f) {  // TA:586-591
+        if (train) {
+          Op op; op.kind = OP_FREQEMB; op.name = "freq_emb.embedding.weight"; op.out = xcur; op.f0 = h->cfg.freq_emb_weight * h->cfg.freq_emb_scale;
+          R.record(op);
+        }
         if (!dry && R.ok()) {
           const long long items = (long long)xcur.Y * xcur.X * (xcur.C / 8);
           freq_emb_kernel<<<dim3((unsigned)((items + 255) / 256), B), 256, 0, s>>>(xcur.hi, xcur.lo(), xcur.Y, xcur.X, xcur.C,
@@ -507,11 +507,11 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
       xin.X = xcur.Y; xin.Y = 1;
       float* st = nullptr;
       Ten raw = R.conv(fe + ".conv", xin, 0, 1, 0, true, ACT_NONE, nullptr, 0, h->cfg.norm_groups, 0, &st);
-      Ten y = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fe + ".norm1.weight"), HP(h, fe + ".norm1.bias"), 1, nullptr, nullptr, raw.X, 0, 0);
+      Ten y = R.gn_apply(raw, st, h->cfg.norm_groups, 0, R.P(fe + ".norm1.weight", 0), R.P(fe + ".norm1.bias", 1), 1, nullptr, nullptr, raw.X, 0, 0);
       y = R.dconv(fe + ".dconv", y, 0, 0, lstm_attn);
       float* st2 = nullptr;
       Ten raw2 = R.conv(fe + ".rewrite", y, 0, 1, 0, true, ACT_NONE, nullptr, 0, h->cfg.norm_groups, 0, &st2);
-      xcur = R.gn_apply(raw2, st2, h->cfg.norm_groups, 0, HP(h, fe + ".norm2.weight"), HP(h, fe + ".norm2.bias"), 2, nullptr, nullptr, raw2.X, 0, 0);
+      xcur = R.gn_apply(raw2, st2, h->cfg.norm_groups, 0, R.P(fe + ".norm2.weight", 0), R.P(fe + ".norm2.bias", 1), 2, nullptr, nullptr, raw2.X, 0, 0);
       R.tap(fe, xcur);
       saved.push_back(xcur);
     }
@@ -547,7 +547,7 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
     } else {
       float* st = nullptr;
       Ten raw = R.conv(fd + ".rewrite", xin, xin.Y > 1 ? 1 : 0, 1, 1, true, ACT_NONE, nullptr, 0, h->cfg.norm_groups, 0, &st);
-      y = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fd + ".norm1.weight"), HP(h, fd + ".norm1.bias"), 2, nullptr, nullptr, raw.X, 0, 0);
+      y = R.gn_apply(raw, st, h->cfg.norm_groups, 0, R.P(fd + ".norm1.weight", 0), R.P(fd + ".norm1.bias", 1), 2, nullptr, nullptr, raw.X, 0, 0);
     }
     R.tap(fd + ".pre", y);
     // transposed conv [+ norm2] [+ GELU]
@@ -556,6 +556,10 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
     if (last) {
       // transposed conv (C -> 2) + crop + de-normalise -> complex, then iSTFT (TA:287-294, 516-521, 489-497, 624-633)
       float2* Zo = reinterpret_cast<float2*>(R.take((size_t)B * le * bins * 8));
+      if (train) {
+        Op op; op.kind = OP_FINALFREQ; op.name = fd + ".conv_tr"; op.in = y; op.i0 = pad; op.i1 = bins; op.i2 = le; op.i3 = nfft; op.fp1 = st_f;
+        R.record(op);
+      }
       if (!dry && R.ok()) {
         const long long items = (long long)le * bins;
         final_freq_convtr_kernel<8, 4><<<dim3((unsigned)((items + 255) / 256), B), 256, 8 * 2 * (y.C + 1) * 4, s>>>(
@@ -579,7 +583,7 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
       Ten raw = R.conv(fd + ".conv_tr", y, 0, 1, 0, true, ACT_NONE, nullptr, 0, h->cfg.norm_groups, 0, &st);
       raw.X *= ctr.g.s; raw.C /= ctr.g.s;
       const int len = raw.X - 2 * pad;
-      xd = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, fd + ".norm2.weight"), HP(h, fd + ".norm2.bias"), 1, nullptr, nullptr, len, pad, 0);
+      xd = R.gn_apply(raw, st, h->cfg.norm_groups, 0, R.P(fd + ".norm2.weight", 0), R.P(fd + ".norm2.bias", 1), 1, nullptr, nullptr, len, pad, 0);
       crop_f = 0;
     }
     if (!last) R.tap(fd, xd);
@@ -602,6 +606,10 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
         yt = R.conv(td + ".rewrite", tin, 0, 1, 1, false, ACT_GLU_PAIR);
       }
       if (last) {
+        if (train) {
+          Op op; op.kind = OP_FINALTIME; op.name = td + ".conv_tr"; op.in = yt; op.i0 = tpad; op.i1 = ttr.g.k; op.i2 = ttr.g.s; op.fp1 = st_t;
+          R.record(op);
+        }
         if (!dry && R.ok()) {
           final_time_kernel<<<dim3((unsigned)((T + 255) / 256), B), 256, 0, s>>>(yt.hi, yt.lo(), yt.X, yt.C, ttr.g.k, ttr.g.s, tpad,
                                                                                  HP(h, td + ".conv_tr.weight"), HP(h, td + ".conv_tr.bias"),
@@ -617,7 +625,7 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
         Ten raw = R.conv(td + ".conv_tr", yt, 0, 1, 0, true, ACT_NONE, nullptr, 0, h->cfg.norm_groups, 0, &st);
         raw.X *= ttr.g.s; raw.C /= ttr.g.s;
         const int len = raw.X - 2 * tpad;
-        xtd = R.gn_apply(raw, st, h->cfg.norm_groups, 0, HP(h, td + ".norm2.weight"), HP(h, td + ".norm2.bias"), 1, nullptr, nullptr, len, tpad, 0);
+        xtd = R.gn_apply(raw, st, h->cfg.norm_groups, 0, R.P(td + ".norm2.weight", 0), R.P(td + ".norm2.bias", 1), 1, nullptr, nullptr, len, tpad, 0);
         crop_t = 0;
       }
       if (!last) R.tap(td, xtd);
@@ -625,10 +633,28 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
   }
   if (bytes) *bytes = R.off;
   if (launches) *launches = R.launches;
+  if (train) h->fwd_bytes = R.off;
   return R.rc;
 }
 
 }  // namespace
+
+namespace rfx {
+namespace hd {
+// re-gather one prepared conv's fp32 weights [Nout][taps][Kp] (the backward transposes them for the input-gradient GEMM)
+int hd_gather_weights(rfx_hdemucs* h, const Conv& c, float* dst, cudaStream_t st) {
+  const float* w = HP(h, c.wkey);
+  RFX_REQUIRE(w != nullptr, "hdemucs: conv weight is not loaded");
+  gather_w_kernel<<<148 * 4, 256, 0, st>>>(w, nullptr, c.g, dst, nullptr);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int hd_run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_t* ws, bool dry, bool train, cudaStream_t s, size_t* bytes,
+                   int* launches) {
+  return run_forward(h, x, B, T, out, ws, dry, train, s, bytes, launches);
+}
+}  // namespace hd
+}  // namespace rfx
 
 extern "C" {
 
@@ -666,7 +692,7 @@ int rfx_hdemucs_finalize(rfx_hdemucs_t* h, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const rfx_hdemucs_config& c = h->cfg;
   RFX_REQUIRE(h->params.count("__window__") && h->params["__window__"].n == (size_t)c.nfft, "hdemucs: load the hann window as '__window__'");
-  Buf tmp;
+  Buf& tmp = h->gather_tmp;  // kept across calls: a training loop re-finalizes after every optimiser step
   int rc = 0;
   int chin = c.audio_channels, chin_z = 2 * c.audio_channels, chout = c.channels, chout_z = c.channels;
   int freqs = c.nfft / 2;
@@ -708,8 +734,14 @@ int rfx_hdemucs_finalize(rfx_hdemucs_t* h, void* stream) {
               if (bsum.alloc(4 * hid)) return 1;
               if ((r = launch_add_vec(bi, bh, bsum.p, 4 * hid, s))) return r;
               RFX_CHECK_CUDA(cudaMemcpyAsync(whh.p + (size_t)d2 * 4 * hid * hid, wh, (size_t)4 * hid * hid * 4, cudaMemcpyDeviceToDevice, s));
-              r = prep_conv(h, lb + ".lstm.ih" + std::to_string(l) + (d2 ? "r" : "f"), 0, 4 * hid, in, 1, 1, 0, 0, 1, 1, tmp, s,
-                            lb + ".lstm.weight_ih" + sfx, lb + ".lstm.bias_sum" + sfx);
+              const std::string ihname = lb + ".lstm.ih" + std::to_string(l) + (d2 ? "r" : "f");
+              r = prep_conv(h, ihname, 0, 4 * hid, in, 1, 1, 0, 0, 1, 1, tmp, s, lb + ".lstm.weight_ih" + sfx, lb + ".lstm.bias_sum" + sfx);
+              if (r) return r;
+              h->convs[ihname].bkey = lb + ".lstm.bias_ih" + sfx;   // both biases receive the column sums of the gate gradient
+              h->convs[ihname].bkey2 = lb + ".lstm.bias_hh" + sfx;
+              // W_hh as a 1-tap "conv" too: the backward recomputes every step's gates with one GEMM over the saved h
+              r = prep_conv(h, lb + ".lstm.hh" + std::to_string(l) + (d2 ? "r" : "f"), 0, 4 * hid, hid, 1, 1, 0, 0, 1, 1, tmp, s,
+                            lb + ".lstm.weight_hh" + sfx, "__none__");
               if (r) return r;
             }
           }
@@ -760,7 +792,6 @@ int rfx_hdemucs_finalize(rfx_hdemucs_t* h, void* stream) {
     chout *= c.growth; chout_z *= c.growth;
     if (freq) freqs = (freqs <= c.kernel_size) ? 1 : freqs / c.stride;
   }
-  tmp.release();
   if (rc) return rc;
   h->finalized = true;
   return 0;
@@ -770,7 +801,7 @@ size_t rfx_hdemucs_workspace_bytes(rfx_hdemucs_t* h, int B, int T) {
   if (!h || !h->finalized || B <= 0 || T <= 0) return 0;
   size_t bytes = 0;
   int launches = 0;
-  if (run_forward(h, nullptr, B, T, nullptr, nullptr, true, nullptr, &bytes, &launches)) return 0;
+  if (run_forward(h, nullptr, B, T, nullptr, nullptr, true, false, nullptr, &bytes, &launches)) return 0;
   return bytes;
 }
 
@@ -782,17 +813,17 @@ int rfx_hdemucs_forward(rfx_hdemucs_t* h, const float* x, int B, int T, float* o
   RFX_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
   size_t need = 0;
   int launches = 0;
-  int rc = run_forward(h, nullptr, B, T, nullptr, nullptr, true, nullptr, &need, &launches);
+  int rc = run_forward(h, nullptr, B, T, nullptr, nullptr, true, false, nullptr, &need, &launches);
   if (rc) return rc;
   RFX_REQUIRE(workspace_bytes >= need, "workspace too small (rfx_hdemucs_workspace_bytes)");
-  return run_forward(h, x, B, T, out, reinterpret_cast<uint8_t*>(workspace), false, (cudaStream_t)stream, nullptr, nullptr);
+  return run_forward(h, x, B, T, out, reinterpret_cast<uint8_t*>(workspace), false, false, (cudaStream_t)stream, nullptr, nullptr);
 }
 
 int rfx_hdemucs_launches_per_call(rfx_hdemucs_t* h, int B, int T) {
   if (!h || !h->finalized) return 0;
   size_t bytes = 0;
   int launches = 0;
-  run_forward(h, nullptr, B, T, nullptr, nullptr, true, nullptr, &bytes, &launches);
+  run_forward(h, nullptr, B, T, nullptr, nullptr, true, false, nullptr, &bytes, &launches);
   return launches;
 }
 

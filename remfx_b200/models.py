@@ -652,12 +652,108 @@ class DemucsModel(nn.Module):
         _lib.check(L.rfx_hdemucs_tap(self._handle, name.encode(), out.data_ptr(), out.numel(), dims, _lib.cur_stream()), f"tap {name}")
         return out
 
+    supports_training = True  # rfx_hdemucs_forward_train / rfx_hdemucs_backward (csrc/hdemucs_bwd.cu)
+
     def forward(self, batch):
+        """(x, target) -> (loss, output) (remfx/models.py:317-321).  With autograd enabled and trainable parameters the output
+        carries a graph node whose backward is `rfx_hdemucs_backward`, so `loss.backward()` fills every parameter's `.grad`
+        the way the reference's Lightning step does (remfx/models.py:217-220).  HDemucs has no BatchNorm / dropout: train and
+        eval mode compute the same function."""
         from .losses import remfx_loss
 
         x, target = batch
-        output = self.sample(x)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
+            output = self._sample_train(x)
+        else:
+            output = self.sample(x)
         return remfx_loss(output, target), output
+
+    def _check_input(self, x: Tensor) -> Tensor:
+        if x.ndim != 3:
+            raise ValueError(f"Expected 3D tensor with dimensions (batch, channel, frames). Found: {x.shape}")
+        if x.shape[1] != self.model.audio_channels:
+            raise ValueError("The channel dimension of input Tensor must match `audio_channels` of HDemucs model. "
+                             f"Found:{x.shape[1]}.")
+        _lib.require_device(x)
+        if x.dtype != torch.float32:
+            raise ValueError("expected float32 audio")
+        return x.contiguous()
+
+    def _unused_parameters(self):
+        te = getattr(self.model, "time_encoder", None)
+        if te is None or len(te) == 0:
+            return set()
+        last = len(te) - 1
+        return {f"time_encoder.{last}.norm1.weight", f"time_encoder.{last}.norm1.bias"}
+
+    def _sample_train(self, x: Tensor) -> Tensor:
+        x = self._check_input(x)
+        named = [(k, p) for k, p in self.model.named_parameters()]
+        return _HDemucsTrainFn.apply(self, [k for k, _ in named], x, *[p for _, p in named])
+
+    def grad_tap(self, name: str) -> Tensor:
+        """Debug: gradient of a tapped activation after the last backward, fp32 (B, Y, X, C)."""
+        L = _lib.lib()
+        dims = (C.c_int * 4)()
+        _lib.check(L.rfx_hdemucs_grad_tap(self._handle, name.encode(), None, 0, dims, _lib.cur_stream()), f"grad_tap {name}")
+        out = torch.empty(tuple(dims), dtype=torch.float32, device=next(self.model.parameters()).device)
+        _lib.check(L.rfx_hdemucs_grad_tap(self._handle, name.encode(), out.data_ptr(), out.numel(), dims, _lib.cur_stream()), f"grad_tap {name}")
+        return out
+
+    def inject_grad(self, name: str, grad: Optional[Tensor]) -> None:
+        """Debug: substitute `grad` (fp32 CUDA, the tap's (B, Y, X, C) layout; keep it alive) for the computed gradient of tap `name`
+        in the following backward calls; None removes the substitution."""
+        self.__dict__.setdefault("_injected", {})
+        if grad is None:
+            self._injected.pop(name, None)
+            _lib.check(_lib.lib().rfx_hdemucs_inject_grad(self._handle, name.encode(), None), "inject_grad")
+        else:
+            g = grad.detach().to(torch.float32).contiguous()
+            self._injected[name] = g
+            _lib.check(_lib.lib().rfx_hdemucs_inject_grad(self._handle, name.encode(), g.data_ptr()), "inject_grad")
 
     def launches_per_call(self, B: int = 1, T: int = 262144) -> int:
         return _lib.lib().rfx_hdemucs_launches_per_call(self._handle, B, T) if self._handle is not None else 0
+
+
+class _HDemucsTrainFn(torch.autograd.Function):
+    """Hybrid-Demucs forward that keeps its pre-activations + hand-written backward (rfx_hdemucs_forward_train /
+    rfx_hdemucs_backward).  Gradients are produced for the parameters only: the reference never differentiates with respect to
+    the audio."""
+
+    @staticmethod
+    def forward(ctx, owner: "DemucsModel", names, x: Tensor, *params: Tensor):
+        B, _, T = x.shape
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            h = owner._sync(x.device)
+            need = L.rfx_hdemucs_train_workspace_bytes(h, B, T)
+            if need == 0:
+                raise ValueError(f"unsupported input size (B={B}, T={T}): T must be a multiple of 1024 ({_lib.lib().rfx_last_error().decode()})")
+            ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            out = torch.empty_like(x)
+            rc = L.rfx_hdemucs_forward_train(h, x.data_ptr(), B, T, out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.cur_stream())
+            _lib.check(rc, "rfx_hdemucs_forward_train")
+        ctx.owner, ctx.names = owner, list(names)
+        ctx.save_for_backward(x, ws, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        x, ws, *params = ctx.saved_tensors
+        owner, names = ctx.owner, ctx.names
+        B, _, T = x.shape
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            h = owner._sync(x.device)  # parameters unchanged since the forward: a no-op stamp check
+            grads = [torch.empty_like(p, memory_format=torch.contiguous_format) for p in params]
+            n = len(names)
+            keys = (C.c_char_p * n)(*[k.encode() for k in names])
+            ptrs = (C.c_void_p * n)(*[g.data_ptr() for g in grads])
+            d = dout.detach().to(torch.float32).contiguous()
+            rc = L.rfx_hdemucs_backward(h, x.data_ptr(), d.data_ptr(), B, T, keys, ptrs, n, ws.data_ptr(), ws.numel(), _lib.cur_stream())
+            _lib.check(rc, "rfx_hdemucs_backward")
+        # parameters the network never uses get no gradient, like under torch autograd (the "empty" innermost time encoder
+        # has a norm1 that its forward skips, TA:_hdemucs.py:159-160), so that the optimiser leaves them alone
+        unused = owner._unused_parameters()
+        return (None, None, None, *[g if (p.requires_grad and k not in unused) else None for k, g, p in zip(names, grads, params)])

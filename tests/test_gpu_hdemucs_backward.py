@@ -1,0 +1,173 @@
+"""-m gpu: Hybrid-Demucs backward (csrc/hdemucs_bwd.cu) against torch autograd through torchaudio's HDemucs on the CPU
+(oracle/hdemucs.py:grad_taps -- the network of cfg/exp/5-5_full.yaml:3 under `loss.backward()`, remfx/models.py:217-221).
+
+Gates: every parameter gradient within TOL relative l2 error of autograd's (HDemucs has no kinks: GELU / GLU / softmax are
+smooth), every tapped activation gradient likewise, and the same through the real training loss.  The first test also prints a
+second table with the oracle's activation gradients INJECTED at every tap, so that one GPU run judges each layer's backward
+independently of the layers behind it (rfx_hdemucs_inject_grad)."""
+import pytest
+import torch
+
+from oracle import hdemucs as ohd
+from oracle import weights
+from tests.util import relrms
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-4
+TAPS = [f"freq_encoder.{i}" for i in range(6)] + [f"time_encoder.{i}" for i in range(4)] + \
+       [f"freq_decoder.{i}" for i in range(5)] + [f"time_decoder.{i}" for i in range(4)]
+
+
+def _pair(seed=0, **over):
+    from remfx_b200.models import DemucsModel
+
+    ref = ohd.build(seed, **over)
+    kw = dict(ohd.KW)
+    kw.update(over)
+    m = DemucsModel(sample_rate=48000, **kw)
+    m.model.load_state_dict(ref.state_dict(), strict=True)
+    return ref, m.cuda()
+
+
+def _ref_to_gpu_layout(r, shape):
+    """reference activation gradient -> the GPU tap's (B, Y, X, C) layout (zero rows where the GPU keeps an uncropped tensor)."""
+    B, Y, X, C = shape
+    g = r.permute(0, 3, 2, 1) if r.dim() == 4 else r.permute(0, 2, 1)[:, None]   # (B, T, Fr, C) / (B, 1, L, C)
+    if g.shape[1] != Y:   # time-like tensor stored as (B, T, 1, C)
+        g = g.reshape(B, Y, -1, C)
+    if g.shape[2] != X:
+        d = (X - g.shape[2]) // 2
+        full = torch.zeros(B, Y, X, C)
+        full[:, :, d:d + g.shape[2]] = g
+        g = full
+    return g.contiguous()
+
+
+def _gpu_to_ref_layout(g, r):
+    t = g.permute(0, 3, 2, 1) if r.dim() == 4 else g.reshape(g.shape[0], -1, g.shape[3]).permute(0, 2, 1)
+    if t.shape != r.shape:
+        if r.dim() == 4 and t.shape[2] != r.shape[2]:
+            d = (t.shape[2] - r.shape[2]) // 2
+            t = t[:, :, d:d + r.shape[2]]
+        elif r.dim() == 3 and t.shape[2] != r.shape[2]:
+            d = (t.shape[2] - r.shape[2]) // 2
+            t = t[:, :, d:d + r.shape[2]]
+    return t.contiguous()
+
+
+def _compare(m, ref_out, label):
+    rows, worst = [], 0.0
+    for k, gr in ref_out["param_grads"].items():
+        p = dict(m.model.named_parameters())[k]
+        if p.grad is None:
+            rows.append((k, float("inf")))
+            continue
+        e = relrms(p.grad, gr)
+        rows.append((k, e))
+    rows.sort(key=lambda kv: -kv[1])
+    print(f"---- {label}: parameter gradients, worst first ({len(rows)} tensors)")
+    for k, e in rows[:25]:
+        print(f"  {k:60s} {e:.2e}")
+    return rows
+
+
+@pytest.mark.parametrize("over", [dict(dconv_lstm=6, dconv_attn=6), {}], ids=["conv_only", "remfx_config"])
+def test_gradients_match_autograd_linear_objective(over):
+    """d/dparams of <out, r> for a fixed random r: isolates the network backward from the loss kernels."""
+    T, B = 16384, 2
+    ref, m = _pair(0, **over)
+    x = weights.synth_audio(3, B, T)
+    r = torch.randn(B, 1, T, generator=torch.Generator().manual_seed(5))
+    ro = ohd.grad_taps(x, None, ref, TAPS, objective=lambda out: (out * r).sum())
+    out = m._sample_train(x.cuda())
+    assert relrms(out, ro["output"]) < 1e-4
+    out.backward(r.cuda())
+    torch.cuda.synchronize()
+    rows = _compare(m, ro, "plain backward")
+    print("---- activation gradients at the taps")
+    act_bad = []
+    for n in TAPS:
+        if n not in ro["act_grads"]:
+            continue
+        g = m.grad_tap(n).cpu()
+        rr = ro["act_grads"][n]
+        e = relrms(_gpu_to_ref_layout(g, rr), rr)
+        print(f"  {n:20s} {e:.2e}")
+        if not e < TOL:
+            act_bad.append((n, e))
+    bad = [(k, e) for k, e in rows if not e < TOL]
+    if bad or act_bad:
+        # diagnosis: the oracle's gradient injected at every tap -> each layer judged on its own
+        for n in TAPS:
+            if n in ro["act_grads"]:
+                m.inject_grad(n, _ref_to_gpu_layout(ro["act_grads"][n], tuple(m.grad_tap(n).shape)).cuda())
+        for p in m.model.parameters():
+            p.grad = None
+        out2 = m._sample_train(x.cuda())
+        out2.backward(r.cuda())
+        torch.cuda.synchronize()
+        _compare(m, ro, "backward with the oracle's activation gradients injected at every tap")
+        for n in TAPS:
+            m.inject_grad(n, None)
+    assert not act_bad, act_bad
+    assert not bad, bad[:10]
+    unused = [k for k, p in m.model.named_parameters() if k not in ro["param_grads"]]
+    assert all(dict(m.model.named_parameters())[k].grad is None for k in unused), unused
+
+
+def test_training_loss_gradients_and_forward_equivalence():
+    """The real objective (MR-STFT + 100 L1 through csrc/loss.cu) at a length that frames the BLSTM (T = 262144 -> 256 steps > 200),
+    B = 1; also: the training forward equals the inference forward."""
+    T = 262144
+    ref, m = _pair(1)
+    x, y = weights.synth_audio(7, 1, T), weights.synth_audio(8, 1, T)
+    ro = ohd.grad_taps(x, y, ref)
+    loss, out = m((x.cuda(), y.cuda()))
+    assert out.requires_grad
+    assert abs(float(loss) - float(ro["loss"])) < 1e-4 * abs(float(ro["loss"]))
+    with torch.no_grad():
+        assert relrms(out, m.sample(x.cuda())) < 5e-6
+    loss.backward()
+    torch.cuda.synchronize()
+    rows = _compare(m, ro, "training loss, T = 262144")
+    bad = [(k, e) for k, e in rows if not e < TOL]
+    assert not bad, bad[:10]
+
+
+def test_fit_step_trains_hybrid_demucs():
+    """remfx_b200.train.RemFX.fit_step on the network of cfg/exp/5-5_full.yaml: three optimiser steps against the same steps done by
+    torch on the CPU (autograd through torchaudio's module + oracle loss + clip 10 + torch AdamW)."""
+    from oracle import loss as oloss
+    from remfx_b200.train import RemFX
+
+    T, B = 16384, 2
+    ref, m = _pair(2)
+    x, y = weights.synth_audio(11, B, T), weights.synth_audio(12, B, T)
+    hp = dict(lr=1e-5, lr_beta1=0.95, lr_beta2=0.999, lr_eps=1e-6, lr_weight_decay=1e-3)
+    ref.train()
+    params = [p for p in ref.parameters()]
+    opt = torch.optim.AdamW(params, lr=hp["lr"], betas=(0.95, 0.999), eps=1e-6, weight_decay=1e-3)
+    ref_losses = []
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        loss = oloss.remfx_loss(ref(x).squeeze(1), y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 10.0)
+        opt.step()
+        ref_losses.append(float(loss.detach()))
+    mod = RemFX(sample_rate=48000, network=m, max_steps=50, **hp)
+    losses = [float(mod.fit_step((x.cuda(), y.cuda(), None, None), i)) for i in range(3)]
+    print("losses", losses, "reference", ref_losses)
+    assert abs(losses[0] - ref_losses[0]) < 1e-4 * abs(ref_losses[0])
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 2e-3 * abs(b), (losses, ref_losses)
+    num = da2 = db2 = 0.0
+    sd0 = ohd.build(2).state_dict()
+    for k, p in m.model.named_parameters():
+        da = (p.detach().cpu() - sd0[k]).double().flatten()
+        db = (dict(ref.named_parameters())[k].detach() - sd0[k]).double().flatten()
+        num += float(da @ db); da2 += float(da @ da); db2 += float(db @ db)
+    cos = num / (da2 ** 0.5 * db2 ** 0.5)
+    assert cos > 0.9 and 0.9 < (da2 / db2) ** 0.5 < 1.1, (cos, da2, db2)
+    assert set(mod.logged) >= {"train_loss", "train_SISDR", "train_STFT", "Input_SISDR", "Input_STFT"}
