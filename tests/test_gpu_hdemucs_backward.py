@@ -2,9 +2,17 @@
 (oracle/hdemucs.py:grad_taps -- the network of cfg/exp/5-5_full.yaml:3 under `loss.backward()`, remfx/models.py:217-221).
 
 Gates: every parameter gradient within TOL relative l2 error of autograd's (HDemucs has no kinks: GELU / GLU / softmax are
-smooth), every tapped activation gradient likewise, and the same through the real training loss.  The first test also prints a
-second table with the oracle's activation gradients INJECTED at every tap, so that one GPU run judges each layer's backward
-independently of the layers behind it (rfx_hdemucs_inject_grad)."""
+smooth), every tapped activation gradient likewise.  The first test also prints a second table with the oracle's activation
+gradients INJECTED at every tap, so that one GPU run judges each layer's backward independently of the layers behind it
+(rfx_hdemucs_inject_grad).
+
+Where TOL = 2e-4 comes from (measured, profiles/r2/hdemucs_backward_first_run.log): activations and gradients travel between the
+tensor-core layers as two bf16 planes (16 mantissa bits, 7.6e-6 per element), so the forward already differs from torchaudio by
+1e-5 .. 9e-5 per layer (test_gpu_hdemucs.py gates it at 1e-4) and every gate / GELU' / softmax in the backward is evaluated at those
+slightly different activations; the error grows from 5e-6 at the last decoder to 1.0e-4 at the encoders (fp32 torch against fp64
+torch on the same graph: 3e-6).  With the oracle's gradient injected per layer every tensor is within 1e-4.
+`*.key.bias` of the local attention has an exactly zero gradient (a bias on every key shifts all scores of a query equally and
+softmax is shift-invariant): it is checked against the scale of `key.weight`'s gradient instead of relatively."""
 import pytest
 import torch
 
@@ -63,7 +71,11 @@ def _compare(m, ref_out, label):
         if p.grad is None:
             rows.append((k, float("inf")))
             continue
-        e = relrms(p.grad, gr)
+        if k.endswith(".key.bias"):   # exactly zero in theory: both sides hold rounding noise only
+            scale = float(ref_out["param_grads"][k[:-4] + "weight"].double().norm())
+            e = float((p.grad.detach().cpu().double() - gr.double()).norm()) / scale
+        else:
+            e = relrms(p.grad, gr)
         rows.append((k, e))
     rows.sort(key=lambda kv: -kv[1])
     print(f"---- {label}: parameter gradients, worst first ({len(rows)} tensors)")
@@ -116,23 +128,53 @@ def test_gradients_match_autograd_linear_objective(over):
     assert all(dict(m.model.named_parameters())[k].grad is None for k in unused), unused
 
 
-def test_training_loss_gradients_and_forward_equivalence():
-    """The real objective (MR-STFT + 100 L1 through csrc/loss.cu) at a length that frames the BLSTM (T = 262144 -> 256 steps > 200),
-    B = 1; also: the training forward equals the inference forward."""
+def test_full_length_gradients_and_training_loss():
+    """T = 262144 (frames the BLSTM: 256 steps > 200), B = 1.
+    (a) network backward alone at full length: both sides differentiate <out, g> with the SAME g = dLoss/dout taken from the oracle
+        (MR-STFT + 100 L1 evaluated at the oracle's output), gate TOL;
+    (b) the real objective end to end (csrc/loss.cu gradient evaluated at OUR output): the log-magnitude term's gradient is
+        ~1/|X| in quiet bins, so the 1e-4 forward difference alone moves dLoss/dout by ~5e-4 -- gate 2e-3 per tensor plus the
+        direction of the whole flattened gradient (cosine);
+    (c) the training forward equals the inference forward."""
+    from oracle import loss as oloss
+
     T = 262144
     ref, m = _pair(1)
     x, y = weights.synth_audio(7, 1, T), weights.synth_audio(8, 1, T)
-    ro = ohd.grad_taps(x, y, ref)
+    with torch.no_grad():
+        o_ref = ohd.sample(x, ref)
+    o_leaf = o_ref.clone().requires_grad_(True)
+    oloss.remfx_loss(o_leaf, y).backward()
+    g = o_leaf.grad.detach()
+    ro = ohd.grad_taps(x, None, ref, objective=lambda out: (out * g).sum())
+    out = m._sample_train(x.cuda())
+    out.backward(g.cuda())
+    torch.cuda.synchronize()
+    rows = _compare(m, ro, "network backward at T = 262144, oracle's dLoss/dout on both sides")
+    bad = [(k, e) for k, e in rows if not e < TOL]
+    assert not bad, bad[:10]
+    # (b) + (c)
+    for p in m.model.parameters():
+        p.grad = None
+    rl = ohd.grad_taps(x, y, ref)
     loss, out = m((x.cuda(), y.cuda()))
     assert out.requires_grad
-    assert abs(float(loss) - float(ro["loss"])) < 1e-4 * abs(float(ro["loss"]))
+    assert abs(float(loss) - float(rl["loss"])) < 1e-4 * abs(float(rl["loss"]))
     with torch.no_grad():
         assert relrms(out, m.sample(x.cuda())) < 5e-6
     loss.backward()
     torch.cuda.synchronize()
-    rows = _compare(m, ro, "training loss, T = 262144")
-    bad = [(k, e) for k, e in rows if not e < TOL]
+    rows = _compare(m, rl, "real training loss end to end, T = 262144")
+    bad = [(k, e) for k, e in rows if not e < 2e-3]
     assert not bad, bad[:10]
+    num = na = nb = 0.0
+    for k, gr in rl["param_grads"].items():
+        a = dict(m.model.named_parameters())[k].grad.detach().cpu().double().flatten()
+        b_ = gr.double().flatten()
+        num += float(a @ b_); na += float(a @ a); nb += float(b_ @ b_)
+    cos = num / (na ** 0.5 * nb ** 0.5)
+    print("whole-gradient cosine", cos, "norm ratio", (na / nb) ** 0.5)
+    assert cos > 0.99999 and abs((na / nb) ** 0.5 - 1.0) < 1e-4
 
 
 def test_fit_step_trains_hybrid_demucs():
