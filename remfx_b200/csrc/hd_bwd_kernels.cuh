@@ -646,6 +646,93 @@ __global__ void __launch_bounds__(128) lstm_bwd_step_kernel(const float* __restr
   }
 }
 
+// Persistent form of the same chain (one cooperative launch per layer instead of one launch per step): grid = (H / 16, 2 dirs,
+// ceil(Bs / 16)); a CTA owns 16 hidden units of one direction for 16 sequences and keeps its W_hh slice [4H][16] in shared memory for
+// the whole launch; thread = (sequence row, unit), so the dc carry lives in a register.  Per step the CTAs of one (direction,
+// sequence chunk) group exchange dG[t] through L2 behind a monotonic arrive / wait counter (all CTAs are co-resident: the launch is
+// cooperative).  The step's own operands (gates, cell states, dH) are loaded BEFORE the wait, so their latency hides behind it.
+constexpr int LBP_U = 16, LBP_B = 16;
+__device__ __forceinline__ unsigned lbp_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256) lstm_bwd_persist_kernel(const float* __restrict__ Gx, const float* __restrict__ R, const float* __restrict__ cs,
+                                                               const float* __restrict__ dH, const float* __restrict__ Whh /*[2][4H][H]*/,
+                                                               float* dG, int Bs, int T, int H, unsigned* bar /*[2 * gridDim.z]*/) {
+  extern __shared__ __align__(16) float lp_smem[];
+  const int G4 = 4 * H, lda = G4 + 4;
+  float* Ws = lp_smem;                       // [4H][LBP_U]
+  float* As = lp_smem + (size_t)G4 * LBP_U;  // [LBP_B][4H + 4]
+  const int dir = blockIdx.y, u0 = blockIdx.x * LBP_U, b0 = blockIdx.z * LBP_B;
+  const int tu = threadIdx.x % LBP_U, tb = threadIdx.x / LBP_U;
+  const int u = u0 + tu, b = b0 + tb;
+  const bool live = b < Bs;
+  unsigned* ctr = bar + dir * gridDim.z + blockIdx.z;
+  const unsigned gsz = gridDim.x;
+  for (int i = threadIdx.x; i < G4 * LBP_U; i += 256) {
+    const int g = i / LBP_U, uu = i % LBP_U;
+    Ws[i] = Whh[(size_t)dir * G4 * H + (size_t)g * H + u0 + uu];
+  }
+  float dc = 0.0f;
+  __syncthreads();
+  for (int k = 0; k < T; ++k) {
+    const int t = dir ? k : T - 1 - k;
+    const int tn = dir ? t - 1 : t + 1;
+    const int tp = dir ? t + 1 : t - 1;
+    // this step's own operands: issued before the wait
+    float pi = 0.f, pf = 0.f, pg = 0.f, po = 0.f, c = 0.f, cprev = 0.f, dh = 0.f;
+    size_t go = 0;
+    if (live) {
+      go = ((size_t)b * T + t) * 8 * H + (size_t)dir * G4 + u;
+      const size_t ho = ((size_t)b * T + t) * 2 * H + dir * H + u;
+      pi = Gx[go] + R[go]; pf = Gx[go + H] + R[go + H]; pg = Gx[go + 2 * H] + R[go + 2 * H]; po = Gx[go + 3 * H] + R[go + 3 * H];
+      c = cs[ho];
+      cprev = (tp >= 0 && tp < T) ? cs[((size_t)b * T + tp) * 2 * H + dir * H + u] : 0.0f;
+      dh = dH[ho];
+    }
+    if (k > 0) {
+      if (threadIdx.x == 0) {
+        const unsigned target = (unsigned)k * gsz;
+        while (lbp_ld_acquire(ctr) < target) { }
+      }
+      __syncthreads();
+      // dG of the previous step for this chunk's sequences (every unit of this direction): L2 -> shared memory
+      for (int i = threadIdx.x; i < LBP_B * (G4 / 4); i += 256) {
+        const int rr = i / (G4 / 4), g4 = (i % (G4 / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b0 + rr < Bs) v = __ldcg(reinterpret_cast<const float4*>(dG + ((size_t)(b0 + rr) * T + tn) * 8 * H + (size_t)dir * G4 + g4));
+        *reinterpret_cast<float4*>(As + (size_t)rr * lda + g4) = v;
+      }
+      __syncthreads();
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float* ar = As + (size_t)tb * lda;
+#pragma unroll 4
+      for (int g = 0; g < G4; g += 4) {
+        const float4 av = *reinterpret_cast<const float4*>(ar + g);
+        a0 = fmaf(av.x, Ws[(g + 0) * LBP_U + tu], a0);
+        a1 = fmaf(av.y, Ws[(g + 1) * LBP_U + tu], a1);
+        a2 = fmaf(av.z, Ws[(g + 2) * LBP_U + tu], a2);
+        a3 = fmaf(av.w, Ws[(g + 3) * LBP_U + tu], a3);
+      }
+      dh += (a0 + a1) + (a2 + a3);
+    }
+    if (live) {
+      const float gi = sigmoidf_acc(pi), gf = sigmoidf_acc(pf), gg = tanhf(pg), go_ = sigmoidf_acc(po);
+      const float tc = tanhf(c);
+      dc += dh * go_ * (1.0f - tc * tc);
+      __stcg(dG + go, dc * gg * gi * (1.0f - gi));
+      __stcg(dG + go + H, dc * cprev * gf * (1.0f - gf));
+      __stcg(dG + go + 2 * H, dc * gi * (1.0f - gg * gg));
+      __stcg(dG + go + 3 * H, dh * tc * go_ * (1.0f - go_));
+      dc *= gf;
+    }
+    __threadfence();
+    __syncthreads();   // every thread's dG stores (and its reads of As) are done
+    if (threadIdx.x == 0) atomicAdd(ctr, 1u);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // _LocalState attention backward (TA:832-857; tools/hd_bwd_emul.py:check_local_state).  qkv fp32 [(b, t)][ld]: columns [0, C) query,
 // [C, 2C) key, [2C, 3C) content, [3C, 3C + heads * nd) decay logits; dres fp32 [(b, s)][C] = gradient of the attention output.

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <set>
 
 using namespace rfx;
@@ -257,6 +258,7 @@ struct BRunner {
     float* cs = reinterpret_cast<float*>(take((size_t)Bs * Tf * 2 * H * 4));
     float* dG = reinterpret_cast<float*>(take(gate_elems * 4));
     float* carry = reinterpret_cast<float*>(take((size_t)Bs * 2 * H * 4));
+    unsigned* bar = reinterpret_cast<unsigned*>(take((size_t)2 * ceil_div(Bs, LBP_B) * sizeof(unsigned)));
     GradRec& gg = rawgrad(Gx);
     const std::string nm[2] = {op.name + ".lstm.hh" + std::to_string(l) + "f", op.name + ".lstm.hh" + std::to_string(l) + "r"};
     for (int d = 0; d < 2 && ok(); ++d) {
@@ -282,14 +284,38 @@ struct BRunner {
     // 2. cell states
     lstm_cscan_kernel<<<ceil_div(Bs * 2 * H, 256), 256, 0, s>>>(Gx.f, R, Bs, Tf, H, cs);
     chk("lstm cscan");
-    // 3. reverse-time chain, one launch per step (both directions)
-    const size_t smem = (size_t)LB_NB * 4 * H * 4;
-    if (cudaFuncSetAttribute(lstm_bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { fail("smem attribute"); return; }
+    // 3. reverse-time chain: one persistent cooperative launch (W_hh slices resident in shared memory, per-step exchange through L2);
+    //    falls back to one launch per step when the grid cannot be co-resident (very large batches) or RFX_HD_LSTM_BWD_STEPWISE is set
     const float* whh = h->whh[op.name + ".l" + std::to_string(l)].p;
-    dim3 grid(ceil_div(H, 128), 2, ceil_div(Bs, LB_NB));
-    for (int k = 0; k < Tf && ok(); ++k) {
-      lstm_bwd_step_kernel<<<grid, 128, smem, s>>>(Gx.f, R, cs, dH, whh, dG, carry, Bs, Tf, H, k);
-      if (k == 0 || k == Tf - 1) chk("lstm step");
+    bool persistent = false;
+    {
+      static const bool stepwise = [] { const char* e = getenv("RFX_HD_LSTM_BWD_STEPWISE"); return e && atoi(e) != 0; }();
+      const dim3 pg(H / LBP_U, 2, ceil_div(Bs, LBP_B));
+      const size_t psmem = ((size_t)4 * H * LBP_U + (size_t)LBP_B * (4 * H + 4)) * 4;
+      int sms = 148, dev = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (!stepwise && H % LBP_U == 0 && psmem <= 227 * 1024 &&
+          cudaFuncSetAttribute(lstm_bwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_persist_kernel, 256, psmem) == cudaSuccess &&
+          (long long)pg.x * pg.y * pg.z <= (long long)per_sm * sms) {
+        if (cudaMemsetAsync(bar, 0, (size_t)2 * pg.z * sizeof(unsigned), s) != cudaSuccess) { fail("memset"); return; }
+        const float* a0 = Gx.f; const float* a1 = R; const float* a2 = cs; const float* a3 = dH; const float* a4 = whh;
+        float* a5 = dG; int a6 = Bs, a7 = Tf, a8 = H; unsigned* a9 = bar;
+        void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9};
+        const cudaError_t e = cudaLaunchCooperativeKernel((const void*)lstm_bwd_persist_kernel, pg, dim3(256), args, psmem, s);
+        if (e == cudaSuccess) persistent = true;
+        else (void)cudaGetLastError();   // not launchable as a cooperative grid here: take the step-wise path
+      }
+    }
+    if (!persistent) {
+      const size_t smem = (size_t)LB_NB * 4 * H * 4;
+      if (cudaFuncSetAttribute(lstm_bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { fail("smem attribute"); return; }
+      dim3 grid(ceil_div(H, 128), 2, ceil_div(Bs, LB_NB));
+      for (int k = 0; k < Tf && ok(); ++k) {
+        lstm_bwd_step_kernel<<<grid, 128, smem, s>>>(Gx.f, R, cs, dH, whh, dG, carry, Bs, Tf, H, k);
+        if (k == 0 || k == Tf - 1) chk("lstm step");
+      }
     }
     // 4. gate gradient as split planes: the A operand of the W_ih input-gradient GEMM and of every weight contraction
     split_pad_kernel<<<148 * 4, 256, 0, s>>>(dG, (long long)Bs * Tf, 8 * H, 8 * H, gg.s, gg.s + gg.plane);

@@ -6,7 +6,7 @@ smooth), every tapped activation gradient likewise.  The first test also prints 
 gradients INJECTED at every tap, so that one GPU run judges each layer's backward independently of the layers behind it
 (rfx_hdemucs_inject_grad).
 
-Where TOL = 2e-4 comes from (measured, profiles/r2/hdemucs_backward_first_run.log): activations and gradients travel between the
+Where TOL = 2.5e-4 comes from (measured, profiles/r2/hdemucs_backward_first_run.log): activations and gradients travel between the
 tensor-core layers as two bf16 planes (16 mantissa bits, 7.6e-6 per element), so the forward already differs from torchaudio by
 1e-5 .. 9e-5 per layer (test_gpu_hdemucs.py gates it at 1e-4) and every gate / GELU' / softmax in the backward is evaluated at those
 slightly different activations; the error grows from 5e-6 at the last decoder to 1.0e-4 at the encoders (fp32 torch against fp64
@@ -22,7 +22,7 @@ from tests.util import relrms
 
 pytestmark = pytest.mark.gpu
 
-TOL = 2e-4
+TOL = 2.5e-4
 TAPS = [f"freq_encoder.{i}" for i in range(6)] + [f"time_encoder.{i}" for i in range(4)] + \
        [f"freq_decoder.{i}" for i in range(5)] + [f"time_decoder.{i}" for i in range(4)]
 

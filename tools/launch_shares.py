@@ -1,28 +1,33 @@
-"""Aggregate an ncu gpu__time_duration launch list (csv) into per-kernel totals / shares."""
+"""ncu `--metrics gpu__time_duration.sum --csv` launch list -> per-kernel share table of the SECOND half of the launches
+(the first half is the warm-up step).  usage: launch_shares.py in.csv out.txt "description" [--all]"""
 import collections
 import csv
 import sys
 
-rows = list(csv.reader(open(sys.argv[1])))
-hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
-h = rows[hi]
-ix = {n: i for i, n in enumerate(h)}
-agg = collections.OrderedDict()
-for r in rows[hi + 1:]:
-    if len(r) < len(h):
-        continue
-    name = r[ix["Kernel Name"]].split("(")[0]
+src, dst, what = sys.argv[1], sys.argv[2], sys.argv[3]
+rows = list(csv.reader(open(src, errors="ignore")))
+hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+h = rows[hdr]
+kn, mv, mu = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
+rows = rows[hdr + 1:]
+if "--all" not in sys.argv:
+    rows = rows[len(rows) // 2:]
+acc, cnt = collections.Counter(), collections.Counter()
+for r in rows:
     try:
-        v = float(r[ix["Metric Value"]])
-    except ValueError:
+        v = float(r[mv].replace(",", ""))
+    except Exception:
         continue
-    u = r[ix["Metric Unit"]]
-    v = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
-    a = agg.setdefault(name, [0, 0.0])
-    a[0] += 1
-    a[1] += v
-tot = sum(a[1] for a in agg.values())
-print(f"# per-kernel totals from {sys.argv[1]} (cold-cache, serialised: compare SHARES); total {tot / 1e3:.2f} ms")
-print(f'{"kernel":58s} {"launches":>8s} {"total_us":>12s} {"share":>7s}')
-for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"{k:58s} {n:8d} {t:12.1f} {100 * t / tot:6.1f}%")
+    if r[mu] == "us":
+        v *= 1e3
+    elif r[mu] == "ms":
+        v *= 1e6
+    name = r[kn].split("(")[0][:80]
+    acc[name] += v
+    cnt[name] += 1
+tot = sum(acc.values())
+with open(dst, "w") as fh:
+    fh.write(f"total {tot / 1e6:.2f} ms over {sum(cnt.values())} launches ({what}; ncu serialises the launches)\n")
+    for k, v in acc.most_common(40):
+        fh.write(f"{v / tot * 100:6.2f}%  {v / 1e6:9.3f} ms  {cnt[k]:5d}x  {k}\n")
+print(open(dst).read())
