@@ -200,8 +200,9 @@ int rfx_tcn_forward_train(rfx_tcn_t* h, const float* x, int B, long long T, floa
 int rfx_tcn_backward(rfx_tcn_t* h, const float* x, const float* out, const float* dout, int B, long long T, const char* const* keys,
                      float* const* grads, int nkeys, void* workspace, size_t workspace_bytes, void* stream);
 int rfx_tcn_backward_launches_per_call(const rfx_tcn_t* h);
-/* Weight-gradient kernel selector, process-wide: 0 = mma.sync bf16x3 (default, the product path), 1 = plain fp32 FFMA
- * kernel (slow; cross-check in tests only). */
+/* Weight-gradient kernel selector, process-wide: 0 = the product path (tcgen05 bf16x3 with MN-major operands when the channel
+ * width is 256 as in cfg/model/tcn.yaml, else mma.sync bf16x3), 1 = plain fp32 FFMA kernel (slow; cross-check in tests only),
+ * 2 = mma.sync bf16x3 for every width. */
 int rfx_tcn_set_wgrad_impl(int impl);
 
 /* ---------------------------------------------------------------------------------------------

@@ -81,6 +81,29 @@ static int make_split_map(CUtensorMap* map, const void* base, long long cols, lo
   return 0;
 }
 
+}  // namespace rfx
+// Generic bf16 tiled tensor-map encoder for the other translation units (tcn_bwd.cu): rank <= 5, strides in BYTES for dims 1..rank-1.
+int rfx_encode_tiled_bf16(void* map, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                          const unsigned* box, int swizzle128) {
+  using namespace rfx;
+  EncodeTiledFn fn = encode_fn();
+  RFX_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable");
+  RFX_REQUIRE(rank >= 1 && rank <= 5, "tensor map rank");
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return 1;
+  }
+  return 0;
+}
+namespace rfx {
+
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(

@@ -48,8 +48,9 @@ __device__ __forceinline__ float gelu_grad(float u) {
 //   PASS 1 (only when stats != nullptr): per-channel sums  dbeta += du, dgamma += du xhat, dscale += dout v   and the two
 //          per-(segment, group) sums  S1 = sum(gamma du), S2 = sum(gamma du xhat)  (fp64 atomics)
 //   PASS 2: d raw = stats ? rstd (gamma du - S1 / n - xhat S2 / n) : du  -> split planes;  d res (+)= dout
-// Work split: grid = (chunks, segments); a thread owns one octet of OUTPUT channels and strides over the segment's pixels, so
-// per-channel sums stay in registers (the tcn_act_bwd_kernel pattern).  The pixel domain is the whole UNcropped raw extent:
+// Work split: items = (segment, pixel chunk), a 1-D grid of at most four CTAs per SM strides over them; a thread owns one octet of
+// OUTPUT channels and strides over the item's pixels, so per-channel sums stay in registers for the CTA's whole life (the
+// tcn_act_bwd_kernel pattern) and reach global memory once per CTA.  The pixel domain is the whole UNcropped raw extent:
 // positions outside the crop window have dout = 0 but, under GroupNorm, a non-zero d raw.
 // ------------------------------------------------------------------------------------------------
 struct GnBwd {
@@ -63,7 +64,8 @@ struct GnBwd {
   double* gsum;           // [segments * G][2]
   float* dgamma; float* dbeta; float* dscale;
   long long count;        // elements per (segment, group)
-  int rows_per_cta;       // pixels per CTA
+  int rows_per_cta;       // pixels per work item
+  int nseg, nchunks;      // work items = nseg * nchunks; the grid strides over them
 };
 
 template <int PASS>
@@ -74,14 +76,11 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwd p) {
   const int rows = 256 / groups;
   const int g8 = threadIdx.x % groups, r = threadIdx.x / groups;
   const int c0 = g8 * 8;
-  const int seg = blockIdx.y;
-  const int b = a.per_x ? seg / a.Xr : seg;
-  const int xfix = a.per_x ? seg % a.Xr : 0;
-  const long long npix = a.per_x ? a.Y : (long long)a.Y * a.Xr;
   const int mode = a.mode;
   const int Ch = mode >= 2 ? a.Cr / 2 : a.Cr;  // valid output channels
   const int cpg = a.Cr / a.G;
   const bool has_stats = a.stats != nullptr;
+  const long long npix = a.per_x ? a.Y : (long long)a.Y * a.Xr;
   double* sm_d = nullptr;
   if (PASS == 1) {
     const int nf = 2 * a.Cr + a.Co;
@@ -106,107 +105,127 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwd p) {
   }
   const int grp1 = has_stats ? min(c0, a.Cr - 1) / cpg : 0;
   const int grp2 = (has_stats && mode == 2) ? min(c0 + Ch, a.Cr - 1) / cpg : 0;
-  float mean1 = 0.0f, rstd1 = 1.0f, mean2 = 0.0f, rstd2 = 1.0f;
-  double s1a = 0.0, s2a = 0.0, s1b = 0.0, s2b = 0.0;   // PASS 1 group sums (value / gate groups); PASS 2: means
-  if (has_stats) {
-    const float* st = a.stats + ((size_t)seg * a.G + grp1) * 2;
-    mean1 = st[0]; rstd1 = st[1];
-    if (mode == 2) { const float* st2 = a.stats + ((size_t)seg * a.G + grp2) * 2; mean2 = st2[0]; rstd2 = st2[1]; }
-    if (PASS == 2) {
-      s1a = p.gsum[((size_t)seg * a.G + grp1) * 2] / (double)p.count;
-      s2a = p.gsum[((size_t)seg * a.G + grp1) * 2 + 1] / (double)p.count;
-      if (mode == 2) {
-        s1b = p.gsum[((size_t)seg * a.G + grp2) * 2] / (double)p.count;
-        s2b = p.gsum[((size_t)seg * a.G + grp2) * 2 + 1] / (double)p.count;
+  float acc_b[8] = {}, acc_g[8] = {}, acc_b2[8] = {}, acc_g2[8] = {}, acc_s[8] = {};  // PASS 1: per-channel sums over ALL of this CTA's work
+  const bool active = r < rows && c0 < a.Co;
+  // work items = (segment, pixel chunk); a CTA strides over them so that the per-channel sums are flushed once per CTA, not per item
+  const long long n_items = (long long)p.nseg * p.nchunks;
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int seg = (int)(item / p.nchunks), chunk = (int)(item % p.nchunks);
+    const int b = a.per_x ? seg / a.Xr : seg;
+    const int xfix = a.per_x ? seg % a.Xr : 0;
+    float mean1 = 0.0f, rstd1 = 1.0f, mean2 = 0.0f, rstd2 = 1.0f;
+    double s1a = 0.0, s2a = 0.0, s1b = 0.0, s2b = 0.0;   // PASS 1: this item's group sums; PASS 2: the segment's means
+    if (has_stats) {
+      const float* st = a.stats + ((size_t)seg * a.G + grp1) * 2;
+      mean1 = st[0]; rstd1 = st[1];
+      if (mode == 2) { const float* st2 = a.stats + ((size_t)seg * a.G + grp2) * 2; mean2 = st2[0]; rstd2 = st2[1]; }
+      if (PASS == 2) {
+        s1a = p.gsum[((size_t)seg * a.G + grp1) * 2] / (double)p.count;
+        s2a = p.gsum[((size_t)seg * a.G + grp1) * 2 + 1] / (double)p.count;
+        if (mode == 2) {
+          s1b = p.gsum[((size_t)seg * a.G + grp2) * 2] / (double)p.count;
+          s2b = p.gsum[((size_t)seg * a.G + grp2) * 2 + 1] / (double)p.count;
+        }
       }
     }
-  }
-  const float m1a = (float)s1a, m2a = (float)s2a, m1b = (float)s1b, m2b = (float)s2b;
-  float acc_b[8] = {}, acc_g[8] = {}, acc_b2[8] = {}, acc_g2[8] = {}, acc_s[8] = {};
-  const long long p_begin = (long long)blockIdx.x * p.rows_per_cta;
-  const long long p_end = min(npix, p_begin + p.rows_per_cta);
-  if (r < rows && c0 < a.Co) {
-    for (long long pp = p_begin + r; pp < p_end; pp += rows) {
-      int y, xr;
-      if (a.per_x) { y = (int)pp; xr = xfix; }
-      else { y = (int)(pp / a.Xr); xr = (int)(pp % a.Xr); }
-      const int xo = xr - a.x_off;
-      const bool inwin = xo >= 0 && xo < a.Xo;
-      const float* rawp = a.raw + (((size_t)b * a.Y + y) * a.Xr + xr) * a.Cr;
-      float dout[8];
+    const float m1a = (float)s1a, m2a = (float)s2a, m1b = (float)s1b, m2b = (float)s2b;
+    if (PASS == 1) { s1a = s2a = s1b = s2b = 0.0; }
+    const long long p_begin = (long long)chunk * p.rows_per_cta;
+    const long long p_end = min(npix, p_begin + p.rows_per_cta);
+    if (active) {
+      for (long long pp = p_begin + r; pp < p_end; pp += rows) {
+        int y, xr;
+        if (a.per_x) { y = (int)pp; xr = xfix; }
+        else { y = (int)(pp / a.Xr); xr = (int)(pp % a.Xr); }
+        const int xo = xr - a.x_off;
+        const bool inwin = xo >= 0 && xo < a.Xo;
+        const float* rawp = a.raw + (((size_t)b * a.Y + y) * a.Xr + xr) * a.Cr;
+        float dout[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dout[i] = 0.0f;
-      size_t ooff = 0;
-      if (inwin) {
-        ooff = (((size_t)b * a.Y + y) * a.Xo + xo) * a.Co + c0;
-        const float4 d0 = *reinterpret_cast<const float4*>(p.dy + ooff), d1 = *reinterpret_cast<const float4*>(p.dy + ooff + 4);
-        dout[0] = d0.x; dout[1] = d0.y; dout[2] = d0.z; dout[3] = d0.w; dout[4] = d1.x; dout[5] = d1.y; dout[6] = d1.z; dout[7] = d1.w;
-        if (PASS == 2 && p.dres) {
-          float4 r0 = d0, r1 = d1;
-          if (p.res_accum) {
-            const float4 o0 = *reinterpret_cast<const float4*>(p.dres + ooff), o1 = *reinterpret_cast<const float4*>(p.dres + ooff + 4);
-            r0.x += o0.x; r0.y += o0.y; r0.z += o0.z; r0.w += o0.w; r1.x += o1.x; r1.y += o1.y; r1.z += o1.z; r1.w += o1.w;
+        for (int i = 0; i < 8; ++i) dout[i] = 0.0f;
+        if (inwin) {
+          const size_t ooff = (((size_t)b * a.Y + y) * a.Xo + xo) * a.Co + c0;
+          const float4 d0 = *reinterpret_cast<const float4*>(p.dy + ooff), d1 = *reinterpret_cast<const float4*>(p.dy + ooff + 4);
+          dout[0] = d0.x; dout[1] = d0.y; dout[2] = d0.z; dout[3] = d0.w; dout[4] = d1.x; dout[5] = d1.y; dout[6] = d1.z; dout[7] = d1.w;
+          if (PASS == 2 && p.dres) {
+            float4 r0 = d0, r1 = d1;
+            if (p.res_accum) {
+              const float4 o0 = *reinterpret_cast<const float4*>(p.dres + ooff), o1 = *reinterpret_cast<const float4*>(p.dres + ooff + 4);
+              r0.x += o0.x; r0.y += o0.y; r0.z += o0.z; r0.w += o0.w; r1.x += o1.x; r1.y += o1.y; r1.z += o1.z; r1.w += o1.w;
+            }
+            *reinterpret_cast<float4*>(p.dres + ooff) = r0;
+            *reinterpret_cast<float4*>(p.dres + ooff + 4) = r1;
           }
-          *reinterpret_cast<float4*>(p.dres + ooff) = r0;
-          *reinterpret_cast<float4*>(p.dres + ooff + 4) = r1;
+        }
+        float dr1[8], dr2[8];   // d raw of the value octet / the gate octet
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = c0 + i;
+          dr1[i] = 0.0f; dr2[i] = 0.0f;
+          if (c >= Ch) continue;
+          float raw1, raw2 = 0.0f;
+          if (mode == 3) { const float2 pr = *reinterpret_cast<const float2*>(rawp + 2 * c); raw1 = pr.x; raw2 = pr.y; }
+          else { raw1 = rawp[c]; if (mode == 2) raw2 = rawp[c + Ch]; }
+          const float xh1 = (raw1 - mean1) * rstd1, xh2 = (raw2 - mean2) * rstd2;
+          const float u1 = has_stats ? fmaf(xh1, ga[i], be[i]) : raw1;
+          const float u2 = has_stats ? fmaf(xh2, ga2[i], be2[i]) : raw2;
+          const float dv = dout[i] * sc[i];
+          float du1, du2 = 0.0f, v;
+          if (mode == 0) { du1 = dv; v = u1; }
+          else if (mode == 1) { du1 = dv * gelu_grad(u1); v = gelu_fast(u1); }
+          else {
+            const float s = sigmoidf_acc(u2);
+            du1 = dv * s;
+            du2 = dv * u1 * s * (1.0f - s);
+            v = u1 * s;
+          }
+          if (PASS == 1) {
+            acc_b[i] += du1; acc_g[i] += du1 * xh1; acc_s[i] += dout[i] * v;
+            s1a += (double)(ga[i] * du1); s2a += (double)(ga[i] * du1 * xh1);
+            if (mode == 2) {
+              acc_b2[i] += du2; acc_g2[i] += du2 * xh2;
+              s1b += (double)(ga2[i] * du2); s2b += (double)(ga2[i] * du2 * xh2);
+            }
+          } else {
+            dr1[i] = has_stats ? rstd1 * (ga[i] * du1 - m1a - xh1 * m2a) : du1;
+            if (mode >= 2) dr2[i] = has_stats ? rstd2 * (ga2[i] * du2 - m1b - xh2 * m2b) : du2;
+          }
+        }
+        if (PASS == 2) {
+          const size_t gpix = (((size_t)b * a.Y + y) * a.Xr + xr) * p.Cg;
+          if (mode == 3) {  // interleaved (value, gate) pairs: raw channels 2 c0 .. 2 c0 + 15
+            if (c0 < Ch) {
+              float lo8[8], hi8[8];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { lo8[2 * i] = dr1[i]; lo8[2 * i + 1] = dr2[i]; hi8[2 * i] = dr1[4 + i]; hi8[2 * i + 1] = dr2[4 + i]; }
+              bw_store_split8(p.ghi, p.glo, gpix + 2 * c0, lo8);
+              bw_store_split8(p.ghi, p.glo, gpix + 2 * c0 + 8, hi8);
+            }
+          } else {
+            if (c0 < p.Cg) bw_store_split8(p.ghi, p.glo, gpix + c0, dr1);   // channels in [Cr, Cg) are written as zero
+            if (mode == 2 && c0 < Ch) bw_store_split8(p.ghi, p.glo, gpix + Ch + c0, dr2);
+          }
         }
       }
-      float dr1[8], dr2[8];   // d raw of the value octet / the gate octet
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = c0 + i;
-        dr1[i] = 0.0f; dr2[i] = 0.0f;
-        if (c >= Ch) continue;
-        float raw1, raw2 = 0.0f;
-        if (mode == 3) { const float2 pr = *reinterpret_cast<const float2*>(rawp + 2 * c); raw1 = pr.x; raw2 = pr.y; }
-        else { raw1 = rawp[c]; if (mode == 2) raw2 = rawp[c + Ch]; }
-        const float xh1 = (raw1 - mean1) * rstd1, xh2 = (raw2 - mean2) * rstd2;
-        const float u1 = has_stats ? fmaf(xh1, ga[i], be[i]) : raw1;
-        const float u2 = has_stats ? fmaf(xh2, ga2[i], be2[i]) : raw2;
-        const float dv = dout[i] * sc[i];
-        float du1, du2 = 0.0f, v;
-        if (mode == 0) { du1 = dv; v = u1; }
-        else if (mode == 1) { du1 = dv * gelu_grad(u1); v = gelu_fast(u1); }
-        else {
-          const float s = sigmoidf_acc(u2);
-          du1 = dv * s;
-          du2 = dv * u1 * s * (1.0f - s);
-          v = u1 * s;
-        }
-        if (PASS == 1) {
-          acc_b[i] += du1; acc_g[i] += du1 * xh1; acc_s[i] += dout[i] * v;
-          s1a += (double)(ga[i] * du1); s2a += (double)(ga[i] * du1 * xh1);
-          if (mode == 2) {
-            acc_b2[i] += du2; acc_g2[i] += du2 * xh2;
-            s1b += (double)(ga2[i] * du2); s2b += (double)(ga2[i] * du2 * xh2);
-          }
-        } else {
-          dr1[i] = has_stats ? rstd1 * (ga[i] * du1 - m1a - xh1 * m2a) : du1;
-          if (mode >= 2) dr2[i] = has_stats ? rstd2 * (ga2[i] * du2 - m1b - xh2 * m2b) : du2;
-        }
+    }
+    if (PASS == 1 && p.gsum) {   // this item's group sums -> the segment's accumulators
+      if (active) {
+        atomicAdd(&sm_d[2 * grp1], s1a); atomicAdd(&sm_d[2 * grp1 + 1], s2a);
+        if (mode == 2) { atomicAdd(&sm_d[2 * grp2], s1b); atomicAdd(&sm_d[2 * grp2 + 1], s2b); }
       }
-      if (PASS == 2) {
-        const size_t gpix = (((size_t)b * a.Y + y) * a.Xr + xr) * p.Cg;
-        if (mode == 3) {  // interleaved (value, gate) pairs: raw channels 2 c0 .. 2 c0 + 15
-          if (c0 < Ch) {
-            float lo8[8], hi8[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { lo8[2 * i] = dr1[i]; lo8[2 * i + 1] = dr2[i]; hi8[2 * i] = dr1[4 + i]; hi8[2 * i + 1] = dr2[4 + i]; }
-            bw_store_split8(p.ghi, p.glo, gpix + 2 * c0, lo8);
-            bw_store_split8(p.ghi, p.glo, gpix + 2 * c0 + 8, hi8);
-          }
-        } else {
-          if (c0 < p.Cg) bw_store_split8(p.ghi, p.glo, gpix + c0, dr1);   // channels in [Cr, Cg) are written as zero
-          if (mode == 2 && c0 < Ch) bw_store_split8(p.ghi, p.glo, gpix + Ch + c0, dr2);
-        }
+      __syncthreads();
+      if (threadIdx.x < 2 * a.G) {
+        atomicAdd(p.gsum + (size_t)seg * a.G * 2 + threadIdx.x, sm_d[threadIdx.x]);
+        sm_d[threadIdx.x] = 0.0;
       }
+      __syncthreads();
     }
   }
   if (PASS == 1) {
     float* sm_b = gb_smem;             // [Cr] dbeta
     float* sm_g = gb_smem + a.Cr;      // [Cr] dgamma
     float* sm_s = gb_smem + 2 * a.Cr;  // [Co] dscale
-    if (r < rows && c0 < a.Co) {
+    if (active) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int c = c0 + i;
@@ -214,8 +233,6 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwd p) {
         atomicAdd(&sm_b[c], acc_b[i]); atomicAdd(&sm_g[c], acc_g[i]); atomicAdd(&sm_s[c], acc_s[i]);
         if (mode == 2) { atomicAdd(&sm_b[c + Ch], acc_b2[i]); atomicAdd(&sm_g[c + Ch], acc_g2[i]); }
       }
-      atomicAdd(&sm_d[2 * grp1], s1a); atomicAdd(&sm_d[2 * grp1 + 1], s2a);
-      if (mode == 2) { atomicAdd(&sm_d[2 * grp2], s1b); atomicAdd(&sm_d[2 * grp2 + 1], s2b); }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < a.Cr; i += 256) {
@@ -224,7 +241,6 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwd p) {
     }
     if (p.dscale)
       for (int i = threadIdx.x; i < Ch; i += 256) atomicAdd(p.dscale + i, sm_s[i]);
-    if (p.gsum && threadIdx.x < 2 * a.G) atomicAdd(p.gsum + (size_t)seg * a.G * 2 + threadIdx.x, sm_d[threadIdx.x]);
   }
 }
 
@@ -416,13 +432,20 @@ __global__ void transpose_w_kernel(const float* __restrict__ wcat, int Nout, int
 //   dW[n][tap][k] += sum_{b, y, x} G[b, y, x, gcol0 + n] * A[b, y + dy[tap], x + dx[tap], k]      (A reads outside its extent are 0)
 // The contraction runs over PIXELS and both operands are pixel-major in HBM ([pixel][channel]), i.e. MN-major for the MMA:
 // fragments come out of ldmatrix.trans; mma.sync.m16n8k16 bf16x3 (lo*hi + hi*lo + hi*hi) with fp32 accumulation; a 3-stage
-// cp.async ring of 32 pixels x 4 plane tiles; one CTA = (tap, 128 n x 128 k tile, item, pixel chunk); fp32 atomics into the
+// cp.async ring of 32 pixels x 4 plane tiles; one CTA = (tap, n x k tile, item, pixel chunk); fp32 atomics into the
 // [N][taps][Kp] staging buffer.
 // ------------------------------------------------------------------------------------------------
-constexpr int HW_BM = 128, HW_BN = 128, HW_BK = 32, HW_LD = 136, HW_STAGES = 3;
-constexpr int HW_TILE = HW_BK * HW_LD;
-constexpr int HW_STAGE_ELEMS = 4 * HW_TILE;
-constexpr int HW_SMEM = HW_STAGES * HW_STAGE_ELEMS * 2;
+constexpr int HW_BK = 32, HW_STAGES = 3;
+// CTA tile = (WM * MT * 16) output columns n  x  (WN * NT * 8) input channels k, 8 warps as WM x WN; the small-channel layers of the
+// network (N or K of 12 .. 96) would waste most of a 128 x 128 tile, so the launcher picks the variant with the least padding.
+template <int WM, int WN, int MT, int NT>
+struct HwCfg {
+  static constexpr int BM = WM * MT * 16, BN = WN * NT * 8;
+  static constexpr int LDG = BM + 8, LDA = BN + 8;          // padded rows: conflict-free ldmatrix
+  static constexpr int G_TILE = HW_BK * LDG, A_TILE = HW_BK * LDA;
+  static constexpr int STAGE_ELEMS = 2 * G_TILE + 2 * A_TILE;  // G hi, G lo, A hi, A lo
+  static constexpr int SMEM = HW_STAGES * STAGE_ELEMS * 2;
+};
 
 struct WgP {
   const __nv_bfloat16* g; long long g_bs, g_ldy, g_ld, g_plane; int gcol0;
@@ -450,11 +473,14 @@ __device__ __forceinline__ void hw_mma16816(float (&d)[4], const uint32_t (&a)[4
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+template <int WM, int WN, int MT, int NT>
 __global__ void __launch_bounds__(256, 2) hd_wgrad_kernel(const WgP p) {
+  using Cfg = HwCfg<WM, WN, MT, NT>;
+  static_assert(WM * WN == 8 && NT % 2 == 0, "8 warps; B fragments come in pairs of n-tiles");
   extern __shared__ __align__(16) unsigned char hw_smem[];
   __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(hw_smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tilesN = (p.N + HW_BM - 1) / HW_BM, tilesK = (p.K + HW_BN - 1) / HW_BN;
+  const int tilesN = (p.N + Cfg::BM - 1) / Cfg::BM, tilesK = (p.K + Cfg::BN - 1) / Cfg::BN;
   int bx = blockIdx.x;
   const int tk = bx % tilesK; bx /= tilesK;
   const int tn = bx % tilesN;
@@ -462,7 +488,7 @@ __global__ void __launch_bounds__(256, 2) hd_wgrad_kernel(const WgP p) {
   const int b = blockIdx.y / p.nchunks, chunk = blockIdx.y % p.nchunks;
   const long long R = (long long)p.Y * p.X;
   const long long r_begin = (long long)chunk * p.rchunk, r_end = min(R, r_begin + p.rchunk);
-  const int n0 = tn * HW_BM, k0 = tk * HW_BN;
+  const int n0 = tn * Cfg::BM, k0 = tk * Cfg::BN;
   const int ddx = p.dx[tap], ddy = p.dy[tap];
   const __nv_bfloat16* gsrc = p.g + (size_t)b * p.g_bs + p.gcol0;
   const __nv_bfloat16* asrc = p.a + (size_t)b * p.a_bs;
@@ -470,32 +496,37 @@ __global__ void __launch_bounds__(256, 2) hd_wgrad_kernel(const WgP p) {
 
   auto load_stage = [&](int it, int stage) {
     const long long rr0 = r_begin + (long long)it * HW_BK;
-    __nv_bfloat16* st = sm + (size_t)stage * HW_STAGE_ELEMS;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int idx = tid + h * 256;  // 512 16-byte pieces per plane tile: 32 rows x 16
-      const int rr = idx >> 4, cc = (idx & 15) * 8;
+    __nv_bfloat16* st = sm + (size_t)stage * Cfg::STAGE_ELEMS;
+    constexpr int GP = Cfg::BM / 8, AP = Cfg::BN / 8;  // 16-byte pieces per row
+    for (int idx = tid; idx < HW_BK * GP; idx += 256) {
+      const int rr = idx / GP, cc = (idx % GP) * 8;
       const long long pix = rr0 + rr;
-      const bool row_ok = pix < r_end;
+      const bool gok = pix < r_end && (n0 + cc < p.N);
+      const int y = gok ? (int)(pix / p.X) : 0, x = gok ? (int)(pix % p.X) : 0;
+      const __nv_bfloat16* gp = gok ? gsrc + (size_t)y * p.g_ldy + (size_t)x * p.g_ld + n0 + cc : p.g;
+      const uint32_t d = smem_u32(st + rr * Cfg::LDG + cc);
+      hw_cp_async16(d, gp, gok);
+      hw_cp_async16(d + Cfg::G_TILE * 2, gok ? gp + p.g_plane : p.g, gok);
+    }
+    for (int idx = tid; idx < HW_BK * AP; idx += 256) {
+      const int rr = idx / AP, cc = (idx % AP) * 8;
+      const long long pix = rr0 + rr;
+      const bool row_ok = pix < r_end && (k0 + cc < p.K);
       const int y = row_ok ? (int)(pix / p.X) : 0, x = row_ok ? (int)(pix % p.X) : 0;
       const int ya = y + ddy, xa = x + ddx;
-      const bool gok = row_ok && (n0 + cc < p.N);
-      const bool aok = row_ok && (k0 + cc < p.K) && ya >= 0 && ya < p.Ay && xa >= 0 && xa < p.Ax;
-      const __nv_bfloat16* gp = gok ? gsrc + (size_t)y * p.g_ldy + (size_t)x * p.g_ld + n0 + cc : p.g;
+      const bool aok = row_ok && ya >= 0 && ya < p.Ay && xa >= 0 && xa < p.Ax;
       const __nv_bfloat16* ap = aok ? asrc + (size_t)ya * p.a_ldy + (size_t)xa * p.a_ld + k0 + cc : p.a;
-      const uint32_t d = smem_u32(st + rr * HW_LD + cc);
-      hw_cp_async16(d, gp, gok);
-      hw_cp_async16(d + HW_TILE * 2, gok ? gp + p.g_plane : p.g, gok);
-      hw_cp_async16(d + 2 * HW_TILE * 2, ap, aok);
-      hw_cp_async16(d + 3 * HW_TILE * 2, aok ? ap + p.a_plane : p.a, aok);
+      const uint32_t d = smem_u32(st + 2 * Cfg::G_TILE + rr * Cfg::LDA + cc);
+      hw_cp_async16(d, ap, aok);
+      hw_cp_async16(d + Cfg::A_TILE * 2, aok ? ap + p.a_plane : p.a, aok);
     }
   };
 
-  float acc[4][4][4];
+  float acc[MT][NT][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NT; ++j)
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.0f;
 
@@ -503,10 +534,12 @@ __global__ void __launch_bounds__(256, 2) hd_wgrad_kernel(const WgP p) {
     if (s < iters) load_stage(s, s);
     hw_cp_async_commit();
   }
-  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps: 64 n x 32 k each
+  const int wm = warp / WN, wn = warp % WN;
   const int lj = lane >> 3, lr = lane & 7;
-  const int a_row = (lj >> 1) * 8 + lr, a_col = wm * 64 + (lj & 1) * 8;
-  const int b_row = (lj & 1) * 8 + lr, b_col = wn * 32 + (lj >> 1) * 8;
+  // ldmatrix.trans source rows are pixels.  A-operand (n x pixel) fragment order: (m lo, k lo), (m hi, k lo), (m lo, k hi), (m hi, k hi);
+  // B-operand (pixel x k) fragments for two n-tiles: (k lo, n0), (k hi, n0), (k lo, n1), (k hi, n1).
+  const int a_row = (lj >> 1) * 8 + lr, a_col = wm * (MT * 16) + (lj & 1) * 8;
+  const int b_row = (lj & 1) * 8 + lr, b_col = wn * (NT * 8) + (lj >> 1) * 8;
 
   for (int it = 0; it < iters; ++it) {
     hw_cp_async_wait<HW_STAGES - 2>();
@@ -516,25 +549,25 @@ __global__ void __launch_bounds__(256, 2) hd_wgrad_kernel(const WgP p) {
       if (nx < iters) load_stage(nx, nx % HW_STAGES);
       hw_cp_async_commit();
     }
-    const __nv_bfloat16* st = sm + (size_t)(it % HW_STAGES) * HW_STAGE_ELEMS;
-    const uint32_t g_hi = smem_u32(st), g_lo = g_hi + HW_TILE * 2, x_hi = g_hi + 2 * HW_TILE * 2, x_lo = g_hi + 3 * HW_TILE * 2;
+    const __nv_bfloat16* st = sm + (size_t)(it % HW_STAGES) * Cfg::STAGE_ELEMS;
+    const uint32_t g_hi = smem_u32(st), g_lo = g_hi + Cfg::G_TILE * 2, x_hi = g_hi + 2 * Cfg::G_TILE * 2, x_lo = x_hi + Cfg::A_TILE * 2;
 #pragma unroll
     for (int kk = 0; kk < HW_BK; kk += 16) {
-      uint32_t bh[2][4], bl[2][4];
+      uint32_t bh[NT / 2][4], bl[NT / 2][4];
 #pragma unroll
-      for (int np = 0; np < 2; ++np) {
-        const uint32_t o = (uint32_t)(((kk + b_row) * HW_LD + b_col + np * 16) * 2);
+      for (int np = 0; np < NT / 2; ++np) {
+        const uint32_t o = (uint32_t)(((kk + b_row) * Cfg::LDA + b_col + np * 16) * 2);
         hw_ldsm_x4_t(x_hi + o, bh[np]);
         hw_ldsm_x4_t(x_lo + o, bl[np]);
       }
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         uint32_t ah[4], al[4];
-        const uint32_t o = (uint32_t)(((kk + a_row) * HW_LD + a_col + mt * 16) * 2);
+        const uint32_t o = (uint32_t)(((kk + a_row) * Cfg::LDG + a_col + mt * 16) * 2);
         hw_ldsm_x4_t(g_hi + o, ah);
         hw_ldsm_x4_t(g_lo + o, al);
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
           const int np = nt >> 1, q = (nt & 1) * 2;
           hw_mma16816(acc[mt][nt], al, bh[np][q], bh[np][q + 1]);
           hw_mma16816(acc[mt][nt], ah, bl[np][q], bl[np][q + 1]);
@@ -549,11 +582,11 @@ __global__ void __launch_bounds__(256, 2) hd_wgrad_kernel(const WgP p) {
   float* dst = p.dW + (size_t)tap * p.Kp;
   const int gq = lane >> 2, qq = lane & 3;
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int n = n0 + wm * 64 + mt * 16 + gq;
-      const int k = k0 + wn * 32 + nt * 8 + qq * 2;
+    for (int nt = 0; nt < NT; ++nt) {
+      const int n = n0 + wm * (MT * 16) + mt * 16 + gq;
+      const int k = k0 + wn * (NT * 8) + nt * 8 + qq * 2;
       if (k < p.K) {  // K is a multiple of 8 here (channel counts are padded): k + 1 < K as well
         if (n < p.N) {
           atomicAdd(dst + (size_t)n * ldn + k, acc[mt][nt][0]);

@@ -132,7 +132,16 @@ struct BRunner {
       p.Y = Y; p.X = X; p.Ay = (int)(A.rows_y > 0 ? A.rows_y : 1); p.Ax = (int)A.rows;
       p.N = gs.Nout; p.K = Ktap; p.taps = gs.taps; p.Kp = gs.Kp;
       for (int t = 0; t < gs.taps; ++t) { p.dx[t] = dx[t]; p.dy[t] = dy[t]; }
-      const int tiles = ceil_div(p.N, HW_BM) * ceil_div(p.K, HW_BN) * gs.taps;
+      // tile variant with the least padded area (ties go to the larger tile)
+      static const int cfgs[6][2] = {{128, 128}, {64, 128}, {128, 64}, {64, 64}, {32, 128}, {128, 32}};
+      int best = 0;
+      long long best_cost = -1;
+      for (int i = 0; i < 6; ++i) {
+        const long long cost = (long long)ceil_div(p.N, cfgs[i][0]) * cfgs[i][0] * ceil_div(p.K, cfgs[i][1]) * cfgs[i][1];
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = i; }
+      }
+      const int BMt = cfgs[best][0], BNt = cfgs[best][1];
+      const int tiles = ceil_div(p.N, BMt) * ceil_div(p.K, BNt) * gs.taps;
       const long long R = (long long)Y * X;
       long long want = (148ll * 6 + (long long)tiles * Bn - 1) / ((long long)tiles * Bn);
       if (want < 1) want = 1;
@@ -143,7 +152,15 @@ struct BRunner {
       p.nchunks = (int)((R + rchunk - 1) / rchunk);
       p.dW = stage;
       if ((long long)Bn * p.nchunks > 65535) { fail("weight-gradient grid too large"); return; }
-      hd_wgrad_kernel<<<dim3(tiles, (unsigned)(Bn * p.nchunks)), 256, HW_SMEM, s>>>(p);
+      const dim3 grid(tiles, (unsigned)(Bn * p.nchunks));
+      switch (best) {
+        case 0: hd_wgrad_kernel<2, 4, 4, 4><<<grid, 256, HwCfg<2, 4, 4, 4>::SMEM, s>>>(p); break;
+        case 1: hd_wgrad_kernel<2, 4, 2, 4><<<grid, 256, HwCfg<2, 4, 2, 4>::SMEM, s>>>(p); break;
+        case 2: hd_wgrad_kernel<2, 4, 4, 2><<<grid, 256, HwCfg<2, 4, 4, 2>::SMEM, s>>>(p); break;
+        case 3: hd_wgrad_kernel<2, 4, 2, 2><<<grid, 256, HwCfg<2, 4, 2, 2>::SMEM, s>>>(p); break;
+        case 4: hd_wgrad_kernel<1, 8, 2, 2><<<grid, 256, HwCfg<1, 8, 2, 2>::SMEM, s>>>(p); break;
+        default: hd_wgrad_kernel<8, 1, 1, 4><<<grid, 256, HwCfg<8, 1, 1, 4>::SMEM, s>>>(p); break;
+      }
       chk("wgrad");
       scatter_w_kernel<<<148 * 4, 256, 0, s>>>(stage, gs, dw);
       chk("scatter_w");
@@ -233,7 +250,9 @@ struct BRunner {
     p.count = npix * (a.Cr / a.G);
     const int groups = a.Co / 8, rows = 256 / groups;
     p.rows_per_cta = rows_for(npix, nseg, rows * 8);
-    dim3 grid((unsigned)((npix + p.rows_per_cta - 1) / p.rows_per_cta), nseg);
+    p.nseg = nseg;
+    p.nchunks = (int)((npix + p.rows_per_cta - 1) / p.rows_per_cta);
+    const unsigned grid = (unsigned)std::min<long long>((long long)nseg * p.nchunks, 148 * 4);
     if (has_stats) {
       if (cudaMemsetAsync(gsum, 0, (size_t)nseg * a.G * 2 * 8, s) != cudaSuccess) { fail("memset"); return; }
       const size_t smem = (size_t)((2 * a.Cr + a.Co + 3) & ~3) * 4 + 2 * a.G * 8;
@@ -395,7 +414,14 @@ struct BRunner {
     bstage = reinterpret_cast<float*>(take(max_n * 4));
     tmpf = reinterpret_cast<float*>(take(max_in * 4));
     if (!dry) {
-      if (cudaFuncSetAttribute(hd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HW_SMEM) != cudaSuccess) { fail("smem attribute"); return; }
+      bool attr_ok = true;
+      attr_ok &= cudaFuncSetAttribute(hd_wgrad_kernel<2, 4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HwCfg<2, 4, 4, 4>::SMEM) == cudaSuccess;
+      attr_ok &= cudaFuncSetAttribute(hd_wgrad_kernel<2, 4, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HwCfg<2, 4, 2, 4>::SMEM) == cudaSuccess;
+      attr_ok &= cudaFuncSetAttribute(hd_wgrad_kernel<2, 4, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HwCfg<2, 4, 4, 2>::SMEM) == cudaSuccess;
+      attr_ok &= cudaFuncSetAttribute(hd_wgrad_kernel<2, 4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HwCfg<2, 4, 2, 2>::SMEM) == cudaSuccess;
+      attr_ok &= cudaFuncSetAttribute(hd_wgrad_kernel<1, 8, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HwCfg<1, 8, 2, 2>::SMEM) == cudaSuccess;
+      attr_ok &= cudaFuncSetAttribute(hd_wgrad_kernel<8, 1, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HwCfg<8, 1, 1, 4>::SMEM) == cudaSuccess;
+      if (!attr_ok) { fail("smem attribute"); return; }
       for (auto& kv : grads) {  // every parameter gradient starts from zero (kernels accumulate or overwrite)
         auto pit = h->params.find(kv.first);
         if (pit == h->params.end()) { fail("gradient buffer for unknown parameter '" + kv.first + "'"); return; }

@@ -18,6 +18,9 @@
 // rounding, not bit-for-bit.
 #include "tcn_internal.h"
 
+int rfx_encode_tiled_bf16(void* map, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                          const unsigned* box, int swizzle128);  // gemm2.cu
+
 namespace rfx {
 
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
@@ -340,6 +343,136 @@ __global__ void __launch_bounds__(256, 2) tcn_wgrad_kernel(const WgParams p) {
     }
 }
 
+// ---- weight gradient on tcgen05 (C = 256): MN-major shared-memory operands, both planes of a box in one TMA load ----
+// Contraction over TIME with both operands stored [t][c]: for the MMA that is "MN-major" (the M / N index is the contiguous one).
+// A TMA box of {64 channels, 32 time steps, 1 item, 2 planes} with SWIZZLE_128B lands in shared memory as the canonical MN-major
+// SW128 layout: 128-byte rows = 64 channels of one time step, 8 time steps per 1024-byte swizzle atom (SBO = 1024 B), the next
+// block of 64 channels one box further (LBO = box bytes); instruction descriptor bits 15 / 16 = MN-major A / B.
+// Roles are swapped relative to the maths so that the epilogue's atomics coalesce: M = ci (x tile, 2 halves of 128), N = co (g tile,
+// 256), D[ci][co] in TMEM (2 x 256 columns = all 512); a thread (= TMEM lane = ci) adds 32 consecutive co columns to dW[co][ci].
+// One CTA = (tap, time chunk, item); warp 0 TMA producer, warp 1 MMA issuer (bf16x3: lo*hi + hi*lo + hi*hi), warps 2-5 epilogue.
+// Brought up as tools/wgrad_tc_probe.cu (profiles/r2/wgrad_tc_probe.log: 2.5e-6 vs the fp32 sums, 0.45 ms against 2.32 ms for the
+// mma.sync kernel at 1 x 249868).
+constexpr int WT_C = 256, WT_BK = 32, WT_STAGES = 3;
+constexpr int WT_BOX = 64 * WT_BK * 2 * 2;   // 64 channels x 32 steps x (hi, lo) = 8 KB
+constexpr int WT_PLANE = 64 * WT_BK * 2;     // lo plane offset inside a box
+constexpr int WT_STAGE = 8 * WT_BOX;         // 4 x-boxes (ci) + 4 g-boxes (co)
+constexpr int WT_SMEM = WT_STAGES * WT_STAGE + 1024 + 256;
+
+struct WtParams {
+  int L;          // valid time steps of g (rows beyond are TMA zero fill)
+  int tchunk, nchunks;
+  int K;          // conv taps (tap K = residual, reads the dy rows through mapG1)
+  int off[16];
+  float* dW;      // [K + 1][C][C]
+};
+struct alignas(64) TmapBytes { unsigned char b[128]; };
+
+__device__ __forceinline__ void wt_tma_load_4d(void* dst, const void* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint64_t wt_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(192, 1) tcn_wgrad_tc_kernel(const __grid_constant__ TmapBytes mapG0, const __grid_constant__ TmapBytes mapG1,
+                                                              const __grid_constant__ TmapBytes mapX, const WtParams p) {
+  extern __shared__ uint8_t wt_smem_raw[];
+  const uint32_t raw = smem_u32(wt_smem_raw);
+  uint8_t* smem = wt_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WT_STAGES * WT_STAGE);
+  uint64_t* empty_bar = full_bar + WT_STAGES;
+  uint64_t* tfull_bar = empty_bar + WT_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tap = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z;
+  const int t_begin = chunk * p.tchunk;
+  const int t_end = min(p.L, t_begin + p.tchunk);
+  const int iters = (t_end - t_begin + WT_BK - 1) / WT_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WT_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const void* mg = tap == p.K ? (const void*)&mapG1 : (const void*)&mapG0;
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], WT_STAGE);
+        uint8_t* st = smem + s * WT_STAGE;
+        const int t0 = t_begin + it * WT_BK;
+        for (int cb = 0; cb < 4; ++cb) wt_tma_load_4d(st + cb * WT_BOX, &mapX, cb * 64, t0 + p.off[tap], b, 0, &full_bar[s]);   // x: ci blocks
+        for (int cb = 0; cb < 4; ++cb) wt_tma_load_4d(st + (4 + cb) * WT_BOX, mg, cb * 64, t0, b, 0, &full_bar[s]);             // g: co blocks
+        if (++s == WT_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && iters > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 256) | (1u << 15) | (1u << 16);   // M = 128 (ci half), N = 256 (co), MN-major A and B
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t xb = smem_u32(smem + s * WT_STAGE), gb = xb + 4 * WT_BOX;
+#pragma unroll
+        for (int kk = 0; kk < WT_BK / 16; ++kk) {
+          const uint32_t ko = kk * 2048;  // 16 time steps = two 1024-byte atoms
+          const uint64_t g_hi = wt_desc_mn_sw128(gb + ko, WT_BOX), g_lo = wt_desc_mn_sw128(gb + WT_PLANE + ko, WT_BOX);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t x_hi = wt_desc_mn_sw128(xb + h * 2 * WT_BOX + ko, WT_BOX), x_lo = wt_desc_mn_sw128(xb + h * 2 * WT_BOX + WT_PLANE + ko, WT_BOX);
+            const uint32_t d = tmem + h * 256;
+            const uint32_t first = (it == 0 && kk == 0) ? 0u : 1u;
+            umma_f16(d, x_lo, g_hi, idesc, first);
+            umma_f16(d, x_hi, g_lo, idesc, 1u);
+            umma_f16(d, x_hi, g_hi, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == WT_STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else if (iters > 0) {
+    // epilogue: warp w may only read TMEM lanes [32 (w % 4), +32)
+    const int q = warp & 3;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    float* dst = p.dW + (size_t)tap * WT_C * WT_C;
+    for (int h = 0; h < 2; ++h) {
+      const int ci = h * 128 + q * 32 + lane;
+      for (int cc = 0; cc < 8; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + h * 256 + cc * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)(cc * 32 + j) * WT_C + ci, __uint_as_float(v[j]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 // plain fp32 FFMA form of the same contraction (cross-check only, rfx_tcn_set_wgrad_impl(1)): thread = (tap, co, ci)
 __global__ void tcn_wgrad_simt_kernel(const WgParams p, int B) {
   const int C = p.C;
@@ -383,7 +516,7 @@ __global__ void tcn_gather_wt_kernel(const float* __restrict__ wconv, const floa
 
 namespace {
 
-int g_tcn_wgrad_impl = 0;  // 0 = mma.sync bf16x3 (product), 1 = fp32 SIMT cross-check
+int g_tcn_wgrad_impl = 0;  // 0 = tcgen05 bf16x3 when C == 256, else mma.sync (product); 1 = fp32 SIMT cross-check; 2 = mma.sync bf16x3
 
 struct TrainLayout {
   size_t plane_bytes;  // one bf16 plane of a saved block output
@@ -517,6 +650,8 @@ int rfx_tcn_backward(rfx_tcn_t* h, const float* x, const float* out, const float
   // G: element (plane, b, y, t, c) at plane * g_plane + b * g_bs + y * g_ldy + t * C + c
   const long long g_ldy = bs, g_bs = 2 * bs, g_plane = 2 * plane_elems;
   const bool simt_wgrad = g_tcn_wgrad_impl == 1;
+  const bool tc_wgrad = g_tcn_wgrad_impl == 0 && C == WT_C && K + 1 <= 16 && B <= 65535;
+  if (tc_wgrad) RFX_CHECK_CUDA(cudaFuncSetAttribute(tcn_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
   const int groups = C / 8;
   const int ew_threads = (256 / groups) * groups;  // whole time rows per CTA
   RFX_CHECK_CUDA(cudaFuncSetAttribute(tcn_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
@@ -566,6 +701,29 @@ int rfx_tcn_backward(rfx_tcn_t* h, const float* x, const float* out, const float
       const int per_t = (K + 1) * tiles * tiles;
       if (simt_wgrad) {
         tcn_wgrad_simt_kernel<<<148 * 8, 256, 0, s>>>(wp, B);
+      } else if (tc_wgrad) {
+        // tensor maps of this block's operands: {channel, time, item, plane}; rows beyond the valid length are zero-filled by the TMA unit
+        TmapBytes mg0, mg1, mx;
+        const unsigned box[4] = {64, (unsigned)WT_BK, 1, 2};
+        const unsigned long long gd[4] = {(unsigned long long)C, (unsigned long long)Lo, (unsigned long long)B, 2};
+        const unsigned long long gst[3] = {(unsigned long long)C * 2, (unsigned long long)g_bs * 2, (unsigned long long)g_plane * 2};
+        const unsigned long long xd[4] = {(unsigned long long)C, (unsigned long long)Lin, (unsigned long long)B, 2};
+        const unsigned long long xst[3] = {(unsigned long long)C * 2, (unsigned long long)bs * 2, (unsigned long long)plane_elems * 2};
+        if ((rc = rfx_encode_tiled_bf16(&mg0, G, 4, gd, gst, box, 1))) return rc;
+        if ((rc = rfx_encode_tiled_bf16(&mg1, G + g_ldy, 4, gd, gst, box, 1))) return rc;
+        if ((rc = rfx_encode_tiled_bf16(&mx, saved(n - 1), 4, xd, xst, box, 1))) return rc;
+        WtParams tp{};
+        tp.L = (int)Lo; tp.K = K;
+        for (int j = 0; j <= K; ++j) tp.off[j] = wp.off[j];
+        long long want = (148ll * 2 + (long long)(K + 1) * B - 1) / ((long long)(K + 1) * B);  // about two waves of CTAs
+        if (want < 1) want = 1;
+        long long tchunk = ((Lo + want - 1) / want + WT_BK - 1) / WT_BK * WT_BK;
+        if (tchunk < 8 * WT_BK) tchunk = 8 * WT_BK;
+        tp.tchunk = (int)tchunk;
+        tp.nchunks = (int)((Lo + tchunk - 1) / tchunk);
+        tp.dW = dWcat;
+        RFX_CHECK_CUDA(cudaMemsetAsync(dWcat, 0, (size_t)(K + 1) * C * C * sizeof(float), s));
+        tcn_wgrad_tc_kernel<<<dim3(K + 1, tp.nchunks, B), 192, WT_SMEM, s>>>(mg0, mg1, mx, tp);
       } else {
         // time chunks: about three waves of CTAs at two CTAs per SM, whole stages each
         long long want = (148ll * 6 + (long long)per_t * B - 1) / ((long long)per_t * B);
@@ -612,7 +770,7 @@ int rfx_tcn_backward(rfx_tcn_t* h, const float* x, const float* out, const float
 }
 
 int rfx_tcn_set_wgrad_impl(int impl) {
-  RFX_REQUIRE(impl == 0 || impl == 1, "impl 0 (mma.sync bf16x3) or 1 (fp32 SIMT cross-check)");
+  RFX_REQUIRE(impl >= 0 && impl <= 2, "impl 0 (tcgen05 bf16x3 when C = 256, else mma.sync), 1 (fp32 SIMT cross-check) or 2 (mma.sync bf16x3)");
   g_tcn_wgrad_impl = impl;
   return 0;
 }
