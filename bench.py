@@ -409,7 +409,9 @@ def run_ours(args):
     if use_dist:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     _lib.lib()  # fail loudly if the CUDA library is missing
 
     torch.manual_seed(0)
@@ -595,9 +597,12 @@ def run_ours(args):
             else:
                 others.append(fn(dev, rank, world, barrier, reduce_max, peaks))
         except Exception as exc:  # a secondary leg must not take the headline line down; it is reported as failed
-            if use_dist:
-                raise
             others.append({"config": tag, "error": f"{type(exc).__name__}: {exc}"[:400]})
+            try:
+                torch.cuda.synchronize()
+                torch.cuda.empty_cache()
+            except Exception:
+                pass
     if others:
         line["other_configs"] = others
     if rank == 0:
