@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwd p) {
   const int grp2 = (has_stats && mode == 2) ? min(c0 + Ch, a.Cr - 1) / cpg : 0;
   float acc_b[8] = {}, acc_g[8] = {}, acc_b2[8] = {}, acc_g2[8] = {}, acc_s[8] = {};  // PASS 1: per-channel sums over ALL of this CTA's work
   const bool active = r < rows && c0 < a.Co;
+  // whole, 16-byte aligned octets: Cr % 4 == 0 keeps every pixel row aligned, Ch % 8 == 0 keeps the octets whole
+  const bool vec_ok = (a.Cr % 4 == 0) && (Ch % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.raw) & 15) == 0);
   // work items = (segment, pixel chunk); a CTA strides over them so that the per-channel sums are flushed once per CTA, not per item
   const long long n_items = (long long)p.nseg * p.nchunks;
   for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -158,14 +160,40 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwd p) {
           }
         }
         float dr1[8], dr2[8];   // d raw of the value octet / the gate octet
+        float rv1[8], rv2[8];   // raw values of the two octets (16-byte loads when the octet is whole and aligned)
+        if (vec_ok) {
+          if (mode == 3) {
+            const float4 q0 = *reinterpret_cast<const float4*>(rawp + 2 * c0), q1 = *reinterpret_cast<const float4*>(rawp + 2 * c0 + 4);
+            const float4 q2 = *reinterpret_cast<const float4*>(rawp + 2 * c0 + 8), q3 = *reinterpret_cast<const float4*>(rawp + 2 * c0 + 12);
+            rv1[0] = q0.x; rv2[0] = q0.y; rv1[1] = q0.z; rv2[1] = q0.w; rv1[2] = q1.x; rv2[2] = q1.y; rv1[3] = q1.z; rv2[3] = q1.w;
+            rv1[4] = q2.x; rv2[4] = q2.y; rv1[5] = q2.z; rv2[5] = q2.w; rv1[6] = q3.x; rv2[6] = q3.y; rv1[7] = q3.z; rv2[7] = q3.w;
+          } else {
+            const float4 q0 = *reinterpret_cast<const float4*>(rawp + c0), q1 = *reinterpret_cast<const float4*>(rawp + c0 + 4);
+            rv1[0] = q0.x; rv1[1] = q0.y; rv1[2] = q0.z; rv1[3] = q0.w; rv1[4] = q1.x; rv1[5] = q1.y; rv1[6] = q1.z; rv1[7] = q1.w;
+            if (mode == 2) {
+              const float4 g0 = *reinterpret_cast<const float4*>(rawp + Ch + c0), g1 = *reinterpret_cast<const float4*>(rawp + Ch + c0 + 4);
+              rv2[0] = g0.x; rv2[1] = g0.y; rv2[2] = g0.z; rv2[3] = g0.w; rv2[4] = g1.x; rv2[5] = g1.y; rv2[6] = g1.z; rv2[7] = g1.w;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) rv2[i] = 0.0f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = c0 + i;
+            rv1[i] = 0.0f; rv2[i] = 0.0f;
+            if (c >= Ch) continue;
+            if (mode == 3) { rv1[i] = rawp[2 * c]; rv2[i] = rawp[2 * c + 1]; }
+            else { rv1[i] = rawp[c]; if (mode == 2) rv2[i] = rawp[c + Ch]; }
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int c = c0 + i;
           dr1[i] = 0.0f; dr2[i] = 0.0f;
           if (c >= Ch) continue;
-          float raw1, raw2 = 0.0f;
-          if (mode == 3) { const float2 pr = *reinterpret_cast<const float2*>(rawp + 2 * c); raw1 = pr.x; raw2 = pr.y; }
-          else { raw1 = rawp[c]; if (mode == 2) raw2 = rawp[c + Ch]; }
+          const float raw1 = rv1[i], raw2 = rv2[i];
           const float xh1 = (raw1 - mean1) * rstd1, xh2 = (raw2 - mean2) * rstd2;
           const float u1 = has_stats ? fmaf(xh1, ga[i], be[i]) : raw1;
           const float u2 = has_stats ? fmaf(xh2, ga2[i], be2[i]) : raw2;
@@ -209,9 +237,19 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwd p) {
       }
     }
     if (PASS == 1 && p.gsum) {   // this item's group sums -> the segment's accumulators
-      if (active) {
-        atomicAdd(&sm_d[2 * grp1], s1a); atomicAdd(&sm_d[2 * grp1 + 1], s2a);
-        if (mode == 2) { atomicAdd(&sm_d[2 * grp2], s1b); atomicAdd(&sm_d[2 * grp2 + 1], s2b); }
+      // warp-reduce per group first: shared-memory fp64 atomics are CAS loops, and 250 threads on two addresses serialise badly
+      for (int g = 0; g < a.G; ++g) {
+        double v1 = 0.0, v2 = 0.0;
+        if (active) {
+          if (grp1 == g) { v1 += s1a; v2 += s2a; }
+          if (mode == 2 && grp2 == g) { v1 += s1b; v2 += s2b; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        }
+        if ((threadIdx.x & 31) == 0 && (v1 != 0.0 || v2 != 0.0)) { atomicAdd(&sm_d[2 * g], v1); atomicAdd(&sm_d[2 * g + 1], v2); }
       }
       __syncthreads();
       if (threadIdx.x < 2 * a.G) {
