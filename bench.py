@@ -463,6 +463,42 @@ def run_ours(args):
     lstm_ms = pipe.recurrence_times_ms()   # every recurrence launch of the timed region (cudaEvents on its own stream)
     pipe.set_profiling(0)
 
+    # ---- bf16-fast mode (BASELINE.json configs[1] says "bf16"): single-pass products in gemm2 and the tcgen05 recurrence ------
+    # Same pipeline, same timed region as `value`; reported beside the fp32-parity headline with its measured error against it.
+    import remfx_b200
+
+    bf16_fast = None
+    try:
+        ref_out = outs_dev[(args.steps - 1) % nout].clone()          # parity-mode output of the last timed step
+        ref_in = xs[(args.steps - 1) % NBUF]
+        remfx_b200.set_precision("bf16")
+        for i in range(nwarm):
+            pipe.push(xs[i % NBUF], outs_dev[i % nout])
+        pipe.flush()
+        barrier()
+        fv0, fv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fv0.record()
+        for k in range(args.steps):
+            pipe.push(xs[k % NBUF], outs_dev[k % nout])
+        pipe.flush()
+        fv1.record()
+        barrier()
+        fast_ms = reduce_max(fv0.elapsed_time(fv1)) / args.steps
+        seq = pipe.push(ref_in, outs_dev[0])
+        pipe.flush()
+        fast_out = pipe.wait(seq)
+        torch.cuda.synchronize()
+        err = float((fast_out.double() - ref_out.double()).norm() / ref_out.double().norm())
+        bf16_fast = {"value": world * BATCH * CHUNK_S / (fast_ms / 1e3), "unit": "audio-s/s", "ms_per_step": fast_ms,
+                     "rel_rms_vs_fp32_parity_mode": err,
+                     "what": "remfx_b200.set_precision('bf16'): hi*hi pass only in gemm2 and the tcgen05 recurrence (3x fewer MMAs); "
+                             "activations still travel as hi/lo planes"}
+    except Exception as exc:
+        bf16_fast = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    finally:
+        remfx_b200.set_precision("fp32")
+        barrier()
+
     # ---- the same workload as one blocking call per step (latency form), with per-stage timing -----------
     model.set_profiling(True, dev)
     for i in range(3):
@@ -568,6 +604,7 @@ def run_ours(args):
                 "api": "OpenUnmixModel.pipeline().push/wait on pinned host tensors (rfx_umx_pipe_push), every result consumed",
                 "blocking_call": {"value": world * BATCH * CHUNK_S / (sync_ms / 1e3), "ms_per_step": sync_ms,
                                   "api": "OpenUnmixModel.sample_host (rfx_umx_sample_host), one blocking call per step"}},
+        "bf16_fast": bf16_fast,
         "gpu_launches": args.steps * model.launches_per_call(),
         "clocks": clocks,
         "roofline": roofline,

@@ -66,6 +66,14 @@ int rfx_gemm(int impl, const float* A, int lda, int M, const float* W, int N, in
 /* Scheduling facts of the recurrence kernel on the current device: how many 8-CTA clusters are co-resident
  * and how many batch items each cluster takes for batch size B (all clusters of a launch run as one wave). */
 int rfx_lstm_info(int B, int* max_active_clusters, int* batch_per_cluster);
+/* Matmul precision of the tensor-core kernels (gemm2 and the tcgen05 LSTM recurrence), process-wide:
+ *   0 = fp32-parity (default): every product as bf16x3 (lo*hi + hi*lo + hi*hi), the mode all parity gates are stated in
+ *       (the reference computes in fp32, cfg/config.yaml:112);
+ *   1 = bf16-fast: the hi*hi pass only -- what BASELINE.json configs[1] ("1xB200 bf16") names; ~3e-4 relative RMS on Open-Unmix
+ *       (3.5e-4), reported by bench.py beside the parity-mode headline. */
+int rfx_set_matmul_precision(int mode);
+int rfx_get_matmul_precision(void);
+
 /* Process-wide choice of the recurrence kernel: 0 = tensor-core (mma.sync bf16x3, default), 1 = fp32 FFMA, 2 = tcgen05 (H = 256). */
 int rfx_lstm_set_impl(int impl);
 int rfx_lstm_layer(const float* G, const float* Whh, float* Hout, int ldh, int B, int F, int H, void* stream);

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "rfx_gemm_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "rfx_gemm": (C.c_int, [C.c_int, _f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, _f32p, C.c_int, _f32p, _f32p, _f32p, _f32p,
                            C.c_int, C.c_void_p, C.c_void_p]),
+    "rfx_set_matmul_precision": (C.c_int, [C.c_int]),
+    "rfx_get_matmul_precision": (C.c_int, []),
     "rfx_lstm_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rfx_lstm_set_impl": (C.c_int, [C.c_int]),
     "rfx_lstm_layer": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -151,6 +153,17 @@ def lib() -> C.CDLL:
                 raise RfxError("libremfx_b200.so ABI version mismatch; rebuild")
             _lib = handle
     return _lib
+
+
+def set_precision(mode: str) -> None:
+    """Process-wide matmul precision of the tensor-core kernels: "fp32" (bf16x3, parity mode, default) or "bf16" (single pass)."""
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' (parity, bf16x3) or 'bf16' (fast, single pass)")
+    check(lib().rfx_set_matmul_precision(1 if mode == "bf16" else 0), "rfx_set_matmul_precision")
+
+
+def get_precision() -> str:
+    return "bf16" if lib().rfx_get_matmul_precision() == 1 else "fp32"
 
 
 def check(rc: int, what: str = "") -> None:

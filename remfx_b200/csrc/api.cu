@@ -103,6 +103,13 @@ int rfx_lstm_info(int B, int* max_active_clusters, int* batch_per_cluster) {
   return 0;
 }
 
+int rfx_set_matmul_precision(int mode) {
+  RFX_REQUIRE(mode == 0 || mode == 1, "mode 0 (fp32-parity: bf16x3) or 1 (bf16-fast: single pass)");
+  set_matmul_precision(mode);
+  return 0;
+}
+int rfx_get_matmul_precision(void) { return get_matmul_precision(); }
+
 int rfx_lstm_set_impl(int impl) {
   RFX_REQUIRE(impl >= 0 && impl <= 2, "impl 0 (mma.sync tensor-core), 1 (fp32 FFMA) or 2 (tcgen05, H = 256)");
   lstm_set_impl(impl);

@@ -156,6 +156,7 @@ struct G2Params {
   int b_bytes;     // one W k-block: 2 planes x n_box rows x 64 columns bf16
   int n_box;       // W rows per TMA box (= BN, or the 16-rounded N when a single n-tile covers the output)
   int w_res_bytes; // > 0: all KB k-blocks of W stay in shared memory for the whole kernel (loaded once); needs n_tiles == 1
+  int fast;        // 1 = bf16-fast: issue the hi*hi pass only (set_matmul_precision)
   int dbg_skip;    // timing experiments only (RFX_G2_DEBUG_SKIP): 1 = load W only for the first k-block of a tile, 2 = same for A
   int ktap;        // valid K per tap (the last 64-wide block of a tap may be partial: its dead 16-wide steps are skipped)
   int kb_per_tap;  // 64-wide K blocks per tap
@@ -548,9 +549,13 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
             const uint32_t ko = ks * 32;
             const uint64_t dah = umma_desc_sw128(a_hi + ko), dal = umma_desc_sw128(a_lo + ko);
             const uint64_t dbh = umma_desc_sw128(b_hi + ko), dbl = umma_desc_sw128(b_lo + ko);
-            umma_f16(d_tmem, dal, dbh, idesc, (!first_kb || ks > 0) ? 1u : 0u);
-            umma_f16(d_tmem, dah, dbl, idesc, 1u);
-            umma_f16(d_tmem, dah, dbh, idesc, 1u);
+            if (p.fast) {
+              umma_f16(d_tmem, dah, dbh, idesc, (!first_kb || ks > 0) ? 1u : 0u);
+            } else {
+              umma_f16(d_tmem, dal, dbh, idesc, (!first_kb || ks > 0) ? 1u : 0u);
+              umma_f16(d_tmem, dah, dbl, idesc, 1u);
+              umma_f16(d_tmem, dah, dbh, idesc, 1u);
+            }
           }
           umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -679,6 +684,7 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
     p.dbg_skip = dbg;
   }
   p.taps = pr.taps;
+  p.fast = get_matmul_precision() == 1 ? 1 : 0;
   for (int i = 0; i < pr.taps; ++i) { p.dx[i] = pr.row_off[i]; p.dy[i] = pr.row_off_y[i]; }
   p.Cf = pr.Cf; p.ldcf = pr.ldcf; p.bscf = pr.bscf; p.ldcy_f = pr.ldcf_y;
   p.Chi = pr.Chi; p.Clo = pr.Clo; p.ldcs = pr.ldcs; p.bscs = pr.bscs; p.ldcy_s = pr.ldcs_y;
@@ -729,6 +735,10 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   RFX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+static int g_matmul_precision = 0;
+void set_matmul_precision(int mode) { g_matmul_precision = mode == 1 ? 1 : 0; }
+int get_matmul_precision() { return g_matmul_precision; }
 
 size_t split_weight_elems(int N, int K, int BN) {
   return (size_t)(ceil_div(N, BN) * BN) * (size_t)(ceil_div(K, G2_BK) * G2_BK);

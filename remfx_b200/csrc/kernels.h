@@ -113,6 +113,11 @@ struct G2Problem {
   int gn_G = 1, gn_per_x = 0, gn_cmod = 0;
   int max_ctas = 0;  // > 0: persistent grid of at most this many CTAs (leaves the other SMs to concurrent kernels)
 };
+// Process-wide matmul precision of the tensor-core kernels (gemm2, the tcgen05 LSTM recurrence):
+//   0 = fp32-parity: bf16x3 (lo*hi + hi*lo + hi*hi), the default and the mode every parity gate is stated in;
+//   1 = bf16-fast: the hi*hi pass only (BASELINE.json configs[1] says "bf16"): 3x fewer MMAs, ~3e-4 relative error on Open-Unmix.
+void set_matmul_precision(int mode);
+int get_matmul_precision();
 int g2_choose_bn(int N);
 size_t split_weight_elems(int N, int K, int BN);  // elements of ONE plane
 int pack_split_weights(const float* W, long long ldw, int N, int K, int BN, __nv_bfloat16* dst, SplitW* out, cudaStream_t stream);

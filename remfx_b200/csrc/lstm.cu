@@ -556,7 +556,7 @@ __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t
 template <int N>  // batch slots per cluster = MMA N (16 or 32)
 __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
     lstm_rec_tc_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Whh, float* __restrict__ Hout, int ldh,
-                       __nv_bfloat16* __restrict__ Hhi, __nv_bfloat16* __restrict__ Hlo, int ldhs, int B, int F, int NB) {
+                       __nv_bfloat16* __restrict__ Hhi, __nv_bfloat16* __restrict__ Hlo, int ldhs, int B, int F, int NB, int fast) {
   constexpr int H = 256;
   constexpr int UPC = H / LSTM_CL;  // 32 units per CTA -> 128 gate rows = MMA M
   constexpr int TC_BLKP = N * 64;   // bytes of one plane of one CTA's h block: N slots x 32 units bf16
@@ -643,13 +643,22 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
         if (step > 0) mbar_wait(&h_bar[cur * LSTM_CL + 2 * w + half], ((step - 1) >> 1) & 1);  // h_{t-1} of source CTA 2 w + half
         tc_fence_after();
         if (elect_one()) {
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {  // W_lo h_hi, W_hi h_lo, W_hi h_hi (small terms first)
+          if (fast) {  // bf16-fast (set_matmul_precision(1)): W_hi h_hi only
 #pragma unroll
             for (int k2 = 0; k2 < 2; ++k2) {
               const int k4 = 2 * half + k2;
-              const uint32_t boff = (uint32_t)(half * TC_BLK + k2 * 256 + (pass == 1 ? TC_BLKP : 0));
-              umma_ts_f16_split(d_acc, a0 + (pass == 0 ? 128u : 0u) + 8u * k4, lo0 + (boff >> 4), desc_hi, idesc, (half | pass | k2) ? 1u : 0u);
+              const uint32_t boff = (uint32_t)(half * TC_BLK + k2 * 256);
+              umma_ts_f16_split(d_acc, a0 + 8u * k4, lo0 + (boff >> 4), desc_hi, idesc, (half | k2) ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {  // W_lo h_hi, W_hi h_lo, W_hi h_hi (small terms first)
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2) {
+                const int k4 = 2 * half + k2;
+                const uint32_t boff = (uint32_t)(half * TC_BLK + k2 * 256 + (pass == 1 ? TC_BLKP : 0));
+                umma_ts_f16_split(d_acc, a0 + (pass == 0 ? 128u : 0u) + 8u * k4, lo0 + (boff >> 4), desc_hi, idesc, (half | pass | k2) ? 1u : 0u);
+              }
             }
           }
           if (half == 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb_u) : "memory");
@@ -788,7 +797,7 @@ static int launch_tc_n(const float* G, int ldg, const float* Whh, float* Hout, i
   RFX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nb = (slots > 0 && slots < N) ? slots : N;
   dim3 grid(LSTM_CL, ceil_div(B, nb), 2);
-  kern<<<grid, TC_THREADS, smem, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb);
+  kern<<<grid, TC_THREADS, smem, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb, get_matmul_precision() == 1 ? 1 : 0);
   RFX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
