@@ -553,8 +553,12 @@ __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t
   return d;
 }
 
-template <int N>  // batch slots per cluster = MMA N (16 or 32)
-__global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
+// GROUPS = 2: TWO independent N-slot machines share a CTA (threads [0, TC_THREADS) and [TC_THREADS, 2 TC_THREADS)): each has its own
+// h buffers, barriers, accumulators and named barriers, only W_hh in tensor memory is shared.  Nothing synchronises the two after the
+// set-up, so the warp schedulers overlap one group's exchange / hand-off latencies with the other group's MMAs and gate math -- the
+// "two slot groups out of phase" of VERDICT r1 item 6 without a software pipeline.  A cluster then serves 2 N slots.
+template <int N, int GROUPS = 1>  // batch slots per group = MMA N (16 or 32)
+__global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS * GROUPS, 1)
     lstm_rec_tc_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Whh, float* __restrict__ Hout, int ldh,
                        __nv_bfloat16* __restrict__ Hhi, __nv_bfloat16* __restrict__ Hlo, int ldhs, int B, int F, int NB, int fast) {
   constexpr int H = 256;
@@ -564,18 +568,23 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
   constexpr int HS = N / 2;         // slots per epilogue thread in the activation phase
   constexpr int SPT = N / 16;       // slots per epilogue thread in the cell phase
   extern __shared__ __align__(128) uint8_t lstm_smem[];
-  uint8_t* h_buf = lstm_smem;                                                // [2][CL][TC_BLK]
+  constexpr int GROUP_SMEM = 2 * LSTM_CL * TC_BLK + 2 * TC_BLK + 4 * N * UPC * 4 + 256;  // per-group shared-memory region (multiple of 128)
+  const int grp = GROUPS > 1 ? (int)threadIdx.x / TC_THREADS : 0;
+  uint8_t* gbase = lstm_smem + (size_t)grp * GROUP_SMEM;
+  uint8_t* h_buf = gbase;                                                    // [2][CL][TC_BLK]
   uint8_t* stage = h_buf + 2 * LSTM_CL * TC_BLK;                             // [2][TC_BLK]
   float* act = reinterpret_cast<float*>(stage + 2 * TC_BLK);                 // [4 gates][N slots][32 units]
   uint64_t* h_bar = reinterpret_cast<uint64_t*>(act + 4 * N * UPC);          // [2][CL]: one per (buffer, source CTA)
   uint64_t* mma_bar = h_bar + 2 * LSTM_CL;                                   // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lstm_smem + 2 * LSTM_CL * TC_BLK + 2 * TC_BLK + 4 * N * UPC * 4 + (2 * LSTM_CL + 1) * 8);  // group 0's
 
-  const int tid = threadIdx.x;
+  const int tid = GROUPS > 1 ? (int)threadIdx.x % TC_THREADS : (int)threadIdx.x;   // thread index inside the group
   const int warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int dir = blockIdx.z;
-  const int b0 = blockIdx.y * NB;
+  const int b0 = blockIdx.y * NB + grp * N;           // first batch item of this group
+  const int NBg = GROUPS > 1 ? max(0, min(N, NB - grp * N)) : NB;   // slots of this group that hold items
+  const int bar1 = 1 + 2 * grp, bar2 = 2 + 2 * grp;   // named barriers of this group's epilogue warps
 
   for (int i = tid; i < 2 * LSTM_CL * TC_BLK / 4; i += TC_THREADS) reinterpret_cast<uint32_t*>(h_buf)[i] = 0u;
   if (tid == 0) {
@@ -583,7 +592,7 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
     mbar_init(mma_bar, TC_ISSUERS);
     mbar_fence_init();
   }
-  if (warp == 8) {
+  if (warp == 8 && grp == 0) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -592,10 +601,10 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d = tmem_base + 256;  // columns [0,128) A hi, [128,256) A lo, [256, 256 + 4 N) the four accumulators
+  const uint32_t tmem_d = tmem_base + 256 + (uint32_t)(grp * TC_ISSUERS * N);  // columns [0,128) A hi, [128,256) A lo, then 4 N accumulator columns per group
 
-  // ---- W_hh -> tensor memory (once).  Warps 0-3: thread = row (gate = warp, unit = lane). ----
-  if (warp < 4) {
+  // ---- W_hh -> tensor memory (once, shared by the groups).  Warps 0-3 of group 0: thread = row (gate = warp, unit = lane). ----
+  if (warp < 4 && grp == 0) {
     const float* wrow = Whh + ((size_t)dir * 4 * H + (size_t)warp * H + rank * UPC + lane) * H;
     const uint32_t t_row = tmem_base + ((uint32_t)(32 * warp) << 16);
     for (int c0 = 0; c0 < H / 2; c0 += 8) {  // 8 columns = 16 K-elements
@@ -630,7 +639,7 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
     constexpr uint32_t idesc = umma_idesc_bf16(128, N);
     constexpr uint32_t lbo = 128u, sbo = 512u;
     constexpr uint32_t desc_hi = (sbo >> 4) | (1u << 14);  // SBO, descriptor version 1, no swizzle
-    const uint32_t d_acc = tb_u + 256u + (uint32_t)(w * N);
+    const uint32_t d_acc = tb_u + 256u + (uint32_t)(grp * TC_ISSUERS * N) + (uint32_t)(w * N);
     for (int step = 0; step < F; ++step) {
       const int cur = step & 1;
       // units [16 kk, 16 kk + 16) live in source CTA kk / 2, unit groups 2 (kk & 1), + 1 of its block.  Every source block has
@@ -678,7 +687,7 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
     uint32_t vmask = 0;  // bit s: slot HS ch + s holds a real item
 #pragma unroll
     for (int s2 = 0; s2 < HS; ++s2)
-      if ((HS * ch + s2) < NB && (b0 + HS * ch + s2) < B) vmask |= 1u << s2;
+      if ((HS * ch + s2) < NBg && (b0 + HS * ch + s2) < B) vmask |= 1u << s2;
     const uint32_t row0 = (uint32_t)(b0 + HS * ch) * (uint32_t)F;  // G row of slot HS ch at t = 0
     float gq[HS];
     auto load_g = [&](int st) {
@@ -732,7 +741,7 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
         const float sg = lean_sigmoid(sc * (acc[s2] + gq[s2]));
         acol[s2 * UPC] = (q == 2) ? 2.0f * sg - 1.0f : sg;
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(bar1, 256);
       // ---- (unit pair, slot): c = f c + i g ; h = o tanh(c) ----
       uint8_t* stg = stage + nxt * TC_BLK;
       float h0[SPT], h1[SPT];
@@ -757,7 +766,7 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
         *reinterpret_cast<uint32_t*>(stg + TC_BLKP + st_off) = hl[jj];
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy (async proxy) reads
-      named_bar_sync(2, 256);
+      named_bar_sync(bar2, 256);
       if (warp == 0 && lane < LSTM_CL) {
         mbar_arrive_expect_tx(&h_bar[nxt * LSTM_CL + lane], TC_BLK);  // lane s arms the local barrier of source CTA s
         bulk_s2cluster(dst_h + (uint32_t)(nxt * LSTM_CL * TC_BLK), smem_u32(stg), TC_BLK, dst_bar + (uint32_t)(nxt * LSTM_CL * sizeof(uint64_t)));
@@ -766,7 +775,7 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
       for (int jj = 0; jj < SPT; ++jj) {  // layer output to HBM: off the critical path
         const int sl = cs + 16 * jj;
-        if (sl < NB && (b0 + sl) < B) {
+        if (sl < NBg && (b0 + sl) < B) {
           const uint32_t row = (uint32_t)(b0 + sl) * (uint32_t)F + tt;
           if (Hout) *reinterpret_cast<float2*>(Hout + (size_t)(row * (uint32_t)ldh + ccol)) = make_float2(h0[jj], h1[jj]);
           if (Hhi) {
@@ -782,10 +791,26 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   cluster_arrive();
   cluster_wait();
-  if (warp == 8) {
+  if (warp == 8 && grp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// two 16-slot groups per CTA: one cluster of 8 SMs per direction serves 32 slots, like <32>, with the groups overlapping each other
+static int launch_tc_dual(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs, int B,
+                          int F, int slots, cudaStream_t stream) {
+  constexpr int N = TC_N;
+  constexpr int BLK = 2 * N * 64;
+  constexpr size_t group_smem = (size_t)2 * LSTM_CL * BLK + 2 * BLK + (size_t)4 * N * 32 * 4 + 256;
+  const size_t smem = 2 * group_smem + 128;
+  auto kern = lstm_rec_tc_kernel<N, 2>;
+  RFX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nb = (slots > 0 && slots < 2 * N) ? slots : 2 * N;
+  dim3 grid(LSTM_CL, ceil_div(B, nb), 2);
+  kern<<<grid, 2 * TC_THREADS, smem, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb, get_matmul_precision() == 1 ? 1 : 0);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 template <int N>
@@ -807,7 +832,12 @@ static int launch_tc(const float* G, int ldg, const float* Whh, float* Hout, int
   RFX_REQUIRE((long long)B * F * (long long)ldg < (1ll << 32) && (long long)B * F * (long long)std::max(ldh, ldhs) < (1ll << 32),
               "lstm: tensors too large for 32-bit element offsets");
   RFX_REQUIRE((!Hout || ldh % 2 == 0) && (!Hhi || ldhs % 2 == 0), "lstm: output row strides must be even");
-  if (slots > TC_N) return launch_tc_n<TC_N_MAX>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
+  if (slots > TC_N) {
+    // 32 slots per cluster: two interleaved 16-slot groups (default) or one 32-wide machine (RFX_LSTM_TC32_SINGLE=1)
+    static const bool single = [] { const char* e = getenv("RFX_LSTM_TC32_SINGLE"); return e && atoi(e) != 0; }();
+    if (!single) return launch_tc_dual(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
+    return launch_tc_n<TC_N_MAX>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
+  }
   return launch_tc_n<TC_N>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, slots, stream);
 }
 
