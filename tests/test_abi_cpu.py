@@ -127,3 +127,40 @@ def test_tcn_training_abi_host_side_contract():
         assert L.rfx_tcn_set_wgrad_impl(7) == 2 and L.rfx_tcn_set_wgrad_impl(0) == 0
     finally:
         L.rfx_tcn_destroy(h)
+
+
+def test_precision_switch_and_hdemucs_training_entry_points_without_a_gpu():
+    """Host-only behaviour of the round-2 entry points: the process-wide precision switch, and the Hybrid-Demucs training calls
+    refusing an un-finalized handle / a workspace that does not belong to a recorded forward (no compute is launched)."""
+    import ctypes as C
+
+    import remfx_b200
+    from remfx_b200 import _lib
+
+    L = _lib.lib()
+    assert remfx_b200.get_precision() == "fp32"
+    remfx_b200.set_precision("bf16")
+    assert L.rfx_get_matmul_precision() == 1 and remfx_b200.get_precision() == "bf16"
+    remfx_b200.set_precision("fp32")
+    assert L.rfx_get_matmul_precision() == 0
+    assert L.rfx_set_matmul_precision(5) == 2 and b"mode" in L.rfx_last_error()
+    with pytest.raises(ValueError):
+        remfx_b200.set_precision("fp8")
+
+    cfg = _lib.HDemucsConfig(1, 1, 48, 2, 4096, 6, 8, 4, 2, 1, 0, 4, 4, 2, 4, 4, 4, 0.2, 10.0)
+    h = C.c_void_p()
+    _lib.check(L.rfx_hdemucs_create(C.byref(cfg), C.byref(h)), "rfx_hdemucs_create")
+    try:
+        dummy = C.c_void_p(256)
+        assert L.rfx_hdemucs_train_workspace_bytes(h, 2, 16384) == 0          # not finalized: no size
+        rc = L.rfx_hdemucs_forward_train(h, dummy, 2, 16384, dummy, dummy, 1 << 30, None)
+        assert rc == 2 and b"finalize" in L.rfx_last_error()
+        keys = (C.c_char_p * 1)(b"freq_emb.embedding.weight")
+        ptrs = (C.c_void_p * 1)(256)
+        rc = L.rfx_hdemucs_backward(h, dummy, dummy, 2, 16384, keys, ptrs, 1, dummy, 1 << 30, None)
+        assert rc == 2 and b"finalize" in L.rfx_last_error()
+        dims = (C.c_int * 4)()
+        assert L.rfx_hdemucs_grad_tap(h, b"freq_encoder.0", None, 0, dims, None) == 2   # no training forward has run
+        assert L.rfx_hdemucs_inject_grad(h, b"freq_encoder.0", None) == 0
+    finally:
+        L.rfx_hdemucs_destroy(h)

@@ -25,7 +25,12 @@ def test_reference_arm_line():
     assert line["metric"].startswith("audio-seconds/sec") and line["vs_baseline"] is None and line["data"] == "synthetic"
     assert line["value"] > 0 and line["steps"] == 1 and "workload" in line["config"]
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    # the UNCHANGED reference module when a reference tree is reachable (/root/reference here, oracle/_ref on the GPU box), else the port
+    from oracle import refshim
+
+    assert cb["kind"] == ("reference" if refshim.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert line["config"]["global_batch"] == 32   # the whole batch per step: same configuration as the product arm
     assert line["e2e"] == {"value": line["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0
 
