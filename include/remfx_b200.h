@@ -298,6 +298,9 @@ int rfx_hdemucs_backward(rfx_hdemucs_t* h, const float* x, const float* dout, in
                          float* const* grads, int nkeys, void* workspace, size_t workspace_bytes, void* stream);
 /* Debug: after a backward, the gradient of a tapped activation (fp32, (B, Y, X, C)); and a way to substitute a reference
  * gradient at a tap during the following backward calls so that each layer can be judged on its own (grad NULL removes it). */
+/* Weight-gradient contraction of the Hybrid-Demucs backward, process-wide: 0 = tcgen05 with MN-major TMA-staged operands (default),
+ * 1 = the mma.sync tile variants (cross-check in tests). */
+int rfx_hdemucs_set_wgrad_impl(int impl);
 int rfx_hdemucs_grad_tap(rfx_hdemucs_t* h, const char* name, float* dst, int64_t capacity, int* dims, void* stream);
 int rfx_hdemucs_inject_grad(rfx_hdemucs_t* h, const char* name, const float* grad);
 

@@ -639,6 +639,150 @@ __global__ void __launch_bounds__(256, 2) hd_wgrad_kernel(const WgP p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same contraction on tcgen05 (the generalisation of tcn_wgrad_tc_kernel, tcn_bwd.cu): both operands are pixel-major in HBM, i.e.
+// MN-major for the MMA.  A TMA box {64 channels, bx, by, 1 item, 2 planes} (bx * by = 32 pixels, SWIZZLE_128B) lands in shared memory as
+// the canonical MN-major SW128 layout (128-byte rows = 64 channels of one pixel, 8 pixels per 1024-byte atom); a conv tap is a shifted
+// box origin and the convolution's zero padding, ragged channel counts and ragged pixel extents are all TMA out-of-bounds fill.
+// Roles swapped for coalesced atomics: M = k (input channels, halves of 128), N = n (output-gradient channels, up to 256):
+// D[k][n] in TMEM (2 x 256 columns); a thread (= TMEM lane = k) adds 32 consecutive n to dW[n][tap][k].
+// One CTA = (tap, 256 n x 256 k tile, pixel-tile chunk, item); warp 0 TMA producer, warp 1 MMA issuer (bf16x3), warps 2-5 epilogue.
+// ------------------------------------------------------------------------------------------------
+constexpr int HT_BK = 32, HT_STAGES = 3;
+constexpr int HT_BOX = 64 * HT_BK * 2 * 2;   // one TMA box: 64 channels x 32 pixels x (hi, lo) = 8 KB
+constexpr int HT_PLANE = 64 * HT_BK * 2;     // lo plane offset inside a box
+constexpr int HT_STAGE_MAX = 8 * HT_BOX;     // up to 4 A boxes + 4 G boxes
+constexpr int HT_SMEM = HT_STAGES * HT_STAGE_MAX + 1024 + 256;
+
+struct HtParams {
+  int taps, N, K, Kp;
+  int dx[16], dy[16];
+  int bx, by;              // pixel box
+  int tiles_x, ptiles;     // pixel tiles per row of tiles / per item
+  int tchunk, nchunks;     // pixel tiles per CTA, chunks per item
+  int ntn, ntk;            // 256-wide n tiles / k tiles
+  float* dW;               // [N][taps][Kp]
+};
+struct alignas(64) HtMap { unsigned char b[128]; };
+
+__device__ __forceinline__ void ht_tma_load_5d(void* dst, const void* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ uint64_t ht_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(192, 1) hd_wgrad_tc_kernel(const __grid_constant__ HtMap mapG, const __grid_constant__ HtMap mapA, const HtParams p) {
+  extern __shared__ uint8_t ht_smem_raw[];
+  const uint32_t raw = smem_u32(ht_smem_raw);
+  uint8_t* smem = ht_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + HT_STAGES * HT_STAGE_MAX);
+  uint64_t* empty_bar = full_bar + HT_STAGES;
+  uint64_t* tfull_bar = empty_bar + HT_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int bxi = blockIdx.x;
+  const int tk = bxi % p.ntk; bxi /= p.ntk;
+  const int tn = bxi % p.ntn;
+  const int tap = bxi / p.ntn;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  const int n0 = tn * 256, k0 = tk * 256;
+  const int n_left = min(256, p.N - n0), k_left = min(256, p.K - k0);
+  const int nb_g = (n_left + 63) >> 6;            // G boxes (64 channels each)
+  const int halves = (k_left + 127) >> 7;         // M = 128 halves of the k tile; each half is two A boxes (a missing one is all OOB zero)
+  const int n_eff = (n_left + 15) & ~15;          // MMA N
+  const uint32_t stage_bytes = (uint32_t)(2 * halves + nb_g) * HT_BOX;
+  const int t_begin = chunk * p.tchunk, t_end = min(p.ptiles, t_begin + p.tchunk);
+  const int iters = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < HT_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        uint8_t* st = smem + s * HT_STAGE_MAX;
+        const int pt = t_begin + it;
+        const int x0 = (pt % p.tiles_x) * p.bx, y0 = (pt / p.tiles_x) * p.by;
+        for (int cb = 0; cb < 2 * halves; ++cb) ht_tma_load_5d(st + cb * HT_BOX, &mapA, k0 + cb * 64, x0 + p.dx[tap], y0 + p.dy[tap], b, 0, &full_bar[s]);
+        for (int cb = 0; cb < nb_g; ++cb) ht_tma_load_5d(st + (2 * halves + cb) * HT_BOX, &mapG, n0 + cb * 64, x0, y0, b, 0, &full_bar[s]);
+        if (++s == HT_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && iters > 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, n_eff) | (1u << 15) | (1u << 16);   // MN-major A and B
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t xb = smem_u32(smem + s * HT_STAGE_MAX), gb = xb + (uint32_t)(2 * halves) * HT_BOX;
+#pragma unroll
+        for (int kk = 0; kk < HT_BK / 16; ++kk) {
+          const uint32_t ko = kk * 2048;  // 16 pixels = two 1024-byte atoms
+          const uint64_t g_hi = ht_desc_mn_sw128(gb + ko, HT_BOX), g_lo = ht_desc_mn_sw128(gb + HT_PLANE + ko, HT_BOX);
+          for (int h = 0; h < halves; ++h) {
+            const uint64_t x_hi = ht_desc_mn_sw128(xb + h * 2 * HT_BOX + ko, HT_BOX), x_lo = ht_desc_mn_sw128(xb + h * 2 * HT_BOX + HT_PLANE + ko, HT_BOX);
+            const uint32_t d = tmem + h * 256;
+            const uint32_t first = (it == 0 && kk == 0) ? 0u : 1u;
+            umma_f16(d, x_lo, g_hi, idesc, first);
+            umma_f16(d, x_hi, g_lo, idesc, 1u);
+            umma_f16(d, x_hi, g_hi, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == HT_STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else if (iters > 0) {
+    // epilogue: warp w may only read TMEM lanes [32 (w % 4), +32)
+    const int q = warp & 3;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const size_t ldn = (size_t)p.taps * p.Kp;
+    float* dst = p.dW + (size_t)tap * p.Kp;
+    for (int h = 0; h < halves; ++h) {
+      const int k = k0 + h * 128 + q * 32 + lane;
+      for (int cc = 0; cc * 32 < n_eff; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + h * 256 + cc * 32, v);
+        tmem_ld_wait();
+        if (k < p.K) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + cc * 32 + j;
+            if (n < p.N) atomicAdd(dst + (size_t)n * ldn + k, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
 // LSTM backward (one bidirectional layer; tools/hd_bwd_emul.py:lstm_dir_bwd).  Gx = W_ih x + b (saved by the forward), R = W_hh h_prev
 // for every step at once (one GEMM over the saved h), both fp32 [Bs][T][8H], column = dir * 4H + gate * H + unit (gates i, f, g, o).
 // ------------------------------------------------------------------------------------------------

@@ -27,6 +27,10 @@ namespace hd {
 int hd_gather_weights(rfx_hdemucs* h, const Conv& c, float* dst, cudaStream_t st);  // hdemucs.cu
 }
 }  // namespace rfx
+int rfx_encode_tiled_bf16(void* map, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                          const unsigned* box, int swizzle128);  // gemm2.cu
+
+static int g_hd_wgrad_impl = 0;  // 0 = tcgen05 (MN-major operands), 1 = mma.sync tile variants
 
 namespace {
 
@@ -132,6 +136,43 @@ struct BRunner {
       p.Y = Y; p.X = X; p.Ay = (int)(A.rows_y > 0 ? A.rows_y : 1); p.Ax = (int)A.rows;
       p.N = gs.Nout; p.K = Ktap; p.taps = gs.taps; p.Kp = gs.Kp;
       for (int t = 0; t < gs.taps; ++t) { p.dx[t] = dx[t]; p.dy[t] = dy[t]; }
+      if (g_hd_wgrad_impl == 0 && (g_ld % 8) == 0 && (A.ld % 8) == 0 && (gcol0 % 8) == 0) {
+        // ---- tcgen05 path: 5-D tensor maps {channel, x, y, item, plane}; taps are shifted box origins, padding is OOB fill ----
+        const int Ay = (int)(A.rows_y > 0 ? A.rows_y : 1), Ax = (int)A.rows;
+        HtMap mg, ma;
+        int bx = 32;
+        while (bx > 1 && bx > X) bx >>= 1;           // largest power of two <= X, at most 32
+        const int by = 32 / bx;
+        const unsigned box[5] = {64, (unsigned)bx, (unsigned)by, 1, 2};
+        const unsigned long long gd[5] = {(unsigned long long)gs.Nout, (unsigned long long)X, (unsigned long long)Y, (unsigned long long)Bn, 2};
+        const unsigned long long gst[4] = {(unsigned long long)g_ld * 2, (unsigned long long)X * g_ld * 2, (unsigned long long)Y * X * g_ld * 2,
+                                           (unsigned long long)g_plane * 2};
+        const unsigned long long ad[5] = {(unsigned long long)Ktap, (unsigned long long)Ax, (unsigned long long)Ay, (unsigned long long)Bn, 2};
+        const unsigned long long ast[4] = {(unsigned long long)A.ld * 2, (unsigned long long)(A.ld_y > 0 ? A.ld_y : (long long)Ax * A.ld) * 2,
+                                           (unsigned long long)A.batch_stride * 2, (unsigned long long)A.plane_stride * 2};
+        if (rfx_encode_tiled_bf16(&mg, g + gcol0, 5, gd, gst, box, 1) || rfx_encode_tiled_bf16(&ma, A.hi, 5, ad, ast, box, 1)) { rc = 1; return; }
+        HtParams tp{};
+        tp.taps = gs.taps; tp.N = gs.Nout; tp.K = Ktap; tp.Kp = gs.Kp;
+        for (int t = 0; t < gs.taps; ++t) { tp.dx[t] = dx[t]; tp.dy[t] = dy[t]; }
+        tp.bx = bx; tp.by = by;
+        tp.tiles_x = ceil_div(X, bx);
+        tp.ptiles = tp.tiles_x * ceil_div(Y, by);
+        tp.ntn = ceil_div(gs.Nout, 256); tp.ntk = ceil_div(Ktap, 256);
+        const long long per = (long long)gs.taps * tp.ntn * tp.ntk * Bn;
+        long long want = (148ll * 2 + per - 1) / per;   // about two waves of CTAs
+        if (want < 1) want = 1;
+        long long tchunk = (tp.ptiles + want - 1) / want;
+        if (tchunk < 4) tchunk = 4;
+        tp.tchunk = (int)tchunk;
+        tp.nchunks = ceil_div(tp.ptiles, tp.tchunk);
+        tp.dW = stage;
+        if (tp.nchunks > 65535 || Bn > 65535) { fail("weight-gradient grid too large"); return; }
+        hd_wgrad_tc_kernel<<<dim3(gs.taps * tp.ntn * tp.ntk, tp.nchunks, Bn), 192, HT_SMEM, s>>>(mg, ma, tp);
+        chk("wgrad tcgen05");
+        scatter_w_kernel<<<148 * 4, 256, 0, s>>>(stage, gs, dw);
+        chk("scatter_w");
+        return;
+      }
       // tile variant with the least padded area (ties go to the larger tile)
       static const int cfgs[6][2] = {{128, 128}, {64, 128}, {128, 64}, {64, 64}, {32, 128}, {128, 32}};
       int best = 0;
@@ -421,6 +462,7 @@ struct BRunner {
       attr_ok &= cudaFuncSetAttribute(hd_wgrad_kernel<2, 4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HwCfg<2, 4, 2, 2>::SMEM) == cudaSuccess;
       attr_ok &= cudaFuncSetAttribute(hd_wgrad_kernel<1, 8, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HwCfg<1, 8, 2, 2>::SMEM) == cudaSuccess;
       attr_ok &= cudaFuncSetAttribute(hd_wgrad_kernel<8, 1, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HwCfg<8, 1, 1, 4>::SMEM) == cudaSuccess;
+      attr_ok &= cudaFuncSetAttribute(hd_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM) == cudaSuccess;
       if (!attr_ok) { fail("smem attribute"); return; }
       for (auto& kv : grads) {  // every parameter gradient starts from zero (kernels accumulate or overwrite)
         auto pit = h->params.find(kv.first);
@@ -655,6 +697,13 @@ int rfx_hdemucs_backward(rfx_hdemucs_t* h, const float* x, const float* dout, in
   int rc = hd_run_backward(h, x, dout, B, T, gmap, reinterpret_cast<uint8_t*>(workspace), h->fwd_bytes, false, (cudaStream_t)stream, &used);
   if (!rc && used > workspace_bytes) { set_error("hdemucs backward overran its workspace"); return 1; }
   return rc;
+}
+
+/* Weight-gradient kernel selector, process-wide: 0 = tcgen05 (default), 1 = the mma.sync tile variants (cross-check). */
+int rfx_hdemucs_set_wgrad_impl(int impl) {
+  RFX_REQUIRE(impl == 0 || impl == 1, "impl 0 (tcgen05, MN-major operands) or 1 (mma.sync tile variants)");
+  g_hd_wgrad_impl = impl;
+  return 0;
 }
 
 /* Debug: gradient of a tapped activation (names as rfx_hdemucs_tap) after rfx_hdemucs_backward, fp32 (B, Y, X, C). */

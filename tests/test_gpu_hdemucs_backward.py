@@ -213,3 +213,33 @@ def test_fit_step_trains_hybrid_demucs():
     cos = num / (da2 ** 0.5 * db2 ** 0.5)
     assert cos > 0.9 and 0.9 < (da2 / db2) ** 0.5 < 1.1, (cos, da2, db2)
     assert set(mod.logged) >= {"train_loss", "train_SISDR", "train_STFT", "Input_SISDR", "Input_STFT"}
+
+
+def test_tcgen05_and_mma_sync_weight_gradients_agree():
+    """The generic weight-gradient contraction has two forms: tcgen05 with MN-major TMA-staged operands (default) and mma.sync tile
+    variants (rfx_hdemucs_set_wgrad_impl(1)).  Same products (bf16x3), different summation order: every weight gradient ≤2e-5."""
+    from remfx_b200 import _lib
+
+    T, B = 16384, 2
+    _, m = _pair(3)
+    x = weights.synth_audio(21, B, T).cuda()
+    r = torch.randn(B, 1, T, generator=torch.Generator().manual_seed(9)).cuda()
+    L = _lib.lib()
+
+    def grads():
+        for p in m.model.parameters():
+            p.grad = None
+        out = m._sample_train(x)
+        out.backward(r)
+        torch.cuda.synchronize()
+        return {k: p.grad.detach().clone() for k, p in m.model.named_parameters() if p.grad is not None}
+
+    g_tc = grads()
+    try:
+        _lib.check(L.rfx_hdemucs_set_wgrad_impl(1))
+        g_mma = grads()
+    finally:
+        _lib.check(L.rfx_hdemucs_set_wgrad_impl(0))
+    worst = max(((relrms(g_tc[k], g_mma[k]), k) for k in g_tc if k.endswith("weight") and g_mma[k].dim() > 1), default=(0.0, ""))
+    print("worst weight-gradient difference between the two forms:", worst)
+    assert worst[0] < 2e-5, worst
