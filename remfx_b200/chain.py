@@ -15,7 +15,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 from torch import Tensor, nn
 
-from .losses import mrstft_loss, remfx_loss, sisdr_loss
+from .losses import mrstft_loss, remfx_loss_with_terms, sisdr_loss
 from .ops import causal_crop
 
 # remfx/effects.py:699-705 (Pedalboard_Effects): label index -> effect class name
@@ -89,7 +89,7 @@ class RemFXChainInference(nn.Module):
                         cloned = True
                     sel = idx.to(output.device)
                     output[sel] = net.sample(output[sel].contiguous())
-        loss = remfx_loss(output, y)
+        loss, self.last_loss_terms = remfx_loss_with_terms(output, y)
         return loss, output
 
     def sample(self, batch):
@@ -101,14 +101,16 @@ class RemFXChainInference(nn.Module):
         if self.shuffle_effect_order:
             random.shuffle(self.effect_order)
         loss, output = self.forward(batch, batch_idx, order=self.effect_order)
-        if output.shape[-1] < y.shape[-1]:
+        cropped = output.shape[-1] < y.shape[-1]
+        if cropped:
             y = causal_crop(y, output.shape[-1])
+        terms = None if cropped else self.__dict__.get("last_loss_terms")  # MR-STFT of (output, y): a by-product of the loss kernels
         with torch.no_grad():
             metrics = {
                 "test_loss": loss,
                 "test_SISDR": -sisdr_loss(output, y),
                 "Input_SISDR": -sisdr_loss(x, y),
-                "test_STFT": mrstft_loss(output, y),
+                "test_STFT": terms[1] if terms is not None else mrstft_loss(output, y),
                 "Input_STFT": mrstft_loss(x, y),
             }
         return loss, metrics

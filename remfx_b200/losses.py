@@ -79,10 +79,11 @@ class _RemfxLossFn(torch.autograd.Function):
             _lib.check(rc, "rfx_remfx_loss")
         ctx.save_for_backward(o2, t2, ws)
         ctx.meta = (obs, tbs, B, T, float(l1_weight), out.shape)
-        return res[0]
+        ctx.mark_non_differentiable(res)
+        return res[0].clone(), res
 
     @staticmethod
-    def backward(ctx, grad_loss: Tensor):
+    def backward(ctx, grad_loss: Tensor, _grad_terms=None):
         o2, t2, ws = ctx.saved_tensors
         obs, tbs, B, T, l1w, shape = ctx.meta
         L = _lib.lib()
@@ -96,8 +97,10 @@ class _RemfxLossFn(torch.autograd.Function):
         return g.reshape(shape), None, None
 
 
-def remfx_loss(out: Tensor, target: Tensor) -> Tensor:
-    """0-d loss tensor, as the reference wrappers return; differentiable with respect to `out`."""
+def remfx_loss_with_terms(out: Tensor, target: Tensor):
+    """(loss, terms): the 0-d loss the reference wrappers return (differentiable with respect to `out`) and the detached 9-vector
+    of `remfx_loss_terms`.  terms[1] is the MR-STFT value of (out, target) -- exactly what the reference's `no_grad` metric block
+    recomputes with six more STFTs (remfx/models.py:236-245); the training harness reuses it instead (row N3)."""
     if out.requires_grad and torch.is_grad_enabled():
         _lib.require_device(out)
         _lib.require_device(target)
@@ -105,8 +108,15 @@ def remfx_loss(out: Tensor, target: Tensor) -> Tensor:
             raise ValueError(f"shape mismatch {tuple(out.shape)} vs {tuple(target.shape)}")
         if out.dtype != torch.float32 or target.dtype != torch.float32:
             raise ValueError("expected float32")
-        return _RemfxLossFn.apply(out, target, 100.0)
-    return remfx_loss_terms(out, target)[0]
+        loss, terms = _RemfxLossFn.apply(out, target, 100.0)
+        return loss, terms.detach()
+    terms = remfx_loss_terms(out, target)
+    return terms[0], terms
+
+
+def remfx_loss(out: Tensor, target: Tensor) -> Tensor:
+    """0-d loss tensor, as the reference wrappers return; differentiable with respect to `out`."""
+    return remfx_loss_with_terms(out, target)[0]
 
 
 def mrstft_loss(out: Tensor, target: Tensor) -> Tensor:

@@ -216,7 +216,7 @@ class OpenUnmixModel(nn.Module):
 
     def forward(self, batch):
         """(x, target) -> (loss, sep_out) with loss = MRSTFT + 100 * L1 (models.py:294-301)."""
-        from .losses import remfx_loss
+        from .losses import remfx_loss_with_terms
 
         x, target = batch
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
@@ -225,7 +225,8 @@ class OpenUnmixModel(nn.Module):
             raise NotImplementedError("remfx_b200.OpenUnmixModel: training-mode forward / backward kernels are not built "
                                       "(TCNModel and DemucsModel train); call .eval() or run under torch.no_grad()")
         sep_out = self.sample(x)
-        return remfx_loss(sep_out, target), sep_out
+        loss, self.last_loss_terms = remfx_loss_with_terms(sep_out, target)
+        return loss, sep_out
 
     def launches_per_call(self) -> int:
         return 5 + 2 * self.model.nb_layers
@@ -486,7 +487,7 @@ class TCNModel(nn.Module):
         With autograd enabled and trainable parameters, `output` carries a graph node whose backward is
         `rfx_tcn_backward` (csrc/tcn_bwd.cu), so `loss.backward()` fills every parameter's `.grad` the way the
         reference's Lightning step does (remfx/models.py:217-220)."""
-        from .losses import remfx_loss
+        from .losses import remfx_loss_with_terms
         from .ops import causal_crop
 
         x, target = batch
@@ -496,7 +497,8 @@ class TCNModel(nn.Module):
             output = self.sample(x)
         if output.shape[-1] < target.shape[-1]:
             target = causal_crop(target, output.shape[-1])
-        return remfx_loss(output, target), output
+        loss, self.last_loss_terms = remfx_loss_with_terms(output, target)
+        return loss, output
 
     def _sample_train(self, x: Tensor) -> Tensor:
         if x.dim() != 3 or x.shape[1] != 1:
@@ -659,14 +661,15 @@ class DemucsModel(nn.Module):
         carries a graph node whose backward is `rfx_hdemucs_backward`, so `loss.backward()` fills every parameter's `.grad`
         the way the reference's Lightning step does (remfx/models.py:217-220).  HDemucs has no BatchNorm / dropout: train and
         eval mode compute the same function."""
-        from .losses import remfx_loss
+        from .losses import remfx_loss_with_terms
 
         x, target = batch
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
             output = self._sample_train(x)
         else:
             output = self.sample(x)
-        return remfx_loss(output, target), output
+        loss, self.last_loss_terms = remfx_loss_with_terms(output, target)
+        return loss, output
 
     def _check_input(self, x: Tensor) -> Tensor:
         if x.ndim != 3:
