@@ -13,6 +13,7 @@
 // Gradient formats: fp32 (B, Y, X, C) for split-bf16 activations, split planes for fp32 pre-activations (they feed the GEMMs).
 // No gradient is produced for the audio input (nothing upstream of the network has parameters; the reference never asks).
 #include "hd_bwd_kernels.cuh"
+#include "bwd_common.h"
 
 #include <algorithm>
 #include <cmath>
@@ -648,6 +649,147 @@ int hd_run_backward(rfx_hdemucs* h, const float* x, const float* dout, int B, in
   return R.rc;
 }
 }  // namespace hd
+}  // namespace rfx
+
+// ------------------------------------------------------------------------------------------------
+// Free-function forms of the building blocks (bwd_common.h), used by the Open-Unmix training path as well
+// ------------------------------------------------------------------------------------------------
+namespace rfx {
+namespace bw {
+
+int wgrad(const __nv_bfloat16* g, size_t g_plane, long long g_ld, int gcol0, int Bn, int Y, int X, const SplitAct& A, const int* dx, const int* dy,
+          int taps, int N, int K, int Kp, float* stage, cudaStream_t s) {
+  RFX_REQUIRE(taps >= 1 && taps <= 16 && (g_ld % 8) == 0 && (A.ld % 8) == 0 && (gcol0 % 8) == 0, "wgrad: operand strides must be multiples of 8");
+  static bool attr = false;
+  if (!attr) {
+    RFX_CHECK_CUDA(cudaFuncSetAttribute(hd_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
+    attr = true;
+  }
+  const int Ay = (int)(A.rows_y > 0 ? A.rows_y : 1), Ax = (int)A.rows;
+  HtMap mg, ma;
+  int bx = 32;
+  while (bx > 1 && bx > X) bx >>= 1;
+  const int by = 32 / bx;
+  const unsigned box[5] = {64, (unsigned)bx, (unsigned)by, 1, 2};
+  const unsigned long long gd[5] = {(unsigned long long)N, (unsigned long long)X, (unsigned long long)Y, (unsigned long long)Bn, 2};
+  const unsigned long long gst[4] = {(unsigned long long)g_ld * 2, (unsigned long long)X * g_ld * 2, (unsigned long long)Y * X * g_ld * 2,
+                                     (unsigned long long)g_plane * 2};
+  const unsigned long long ad[5] = {(unsigned long long)K, (unsigned long long)Ax, (unsigned long long)Ay, (unsigned long long)Bn, 2};
+  const long long a_ldy = A.ld_y > 0 ? A.ld_y : (long long)Ax * A.ld;
+  const long long a_bs = A.batch_stride > 0 ? A.batch_stride : a_ldy * Ay;
+  const unsigned long long ast[4] = {(unsigned long long)A.ld * 2, (unsigned long long)a_ldy * 2, (unsigned long long)a_bs * 2,
+                                     (unsigned long long)A.plane_stride * 2};
+  int rc;
+  if ((rc = rfx_encode_tiled_bf16(&mg, g + gcol0, 5, gd, gst, box, 1)) || (rc = rfx_encode_tiled_bf16(&ma, A.hi, 5, ad, ast, box, 1))) return rc;
+  HtParams tp{};
+  tp.taps = taps; tp.N = N; tp.K = K; tp.Kp = Kp;
+  for (int t = 0; t < taps; ++t) { tp.dx[t] = dx[t]; tp.dy[t] = dy[t]; }
+  tp.bx = bx; tp.by = by;
+  tp.tiles_x = ceil_div(X, bx);
+  tp.ptiles = tp.tiles_x * ceil_div(Y, by);
+  tp.ntn = ceil_div(N, 256); tp.ntk = ceil_div(K, 256);
+  const long long per = (long long)taps * tp.ntn * tp.ntk * Bn;
+  long long want = (148ll * 2 + per - 1) / per;
+  if (want < 1) want = 1;
+  long long tchunk = (tp.ptiles + want - 1) / want;
+  if (tchunk < 4) tchunk = 4;
+  tp.tchunk = (int)tchunk;
+  tp.nchunks = ceil_div(tp.ptiles, tp.tchunk);
+  tp.dW = stage;
+  RFX_REQUIRE(tp.nchunks <= 65535 && Bn <= 65535, "wgrad: grid too large");
+  hd_wgrad_tc_kernel<<<dim3(taps * tp.ntn * tp.ntk, tp.nchunks, Bn), 192, HT_SMEM, s>>>(mg, ma, tp);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int colsum(const __nv_bfloat16* g, size_t g_plane, long long rows, int ld, int col0, int N, float* out, cudaStream_t s) {
+  long long rpc = (rows + 591) / 592;
+  if (rpc < 64) rpc = 64;
+  colsum_split_kernel<<<dim3((unsigned)((rows + rpc - 1) / rpc), ceil_div(N, 2048)), 256, 0, s>>>(g, g + g_plane, rows, ld, col0, N, out, (int)rpc);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int split_pad(const float* src, long long rows, int cols, int cols_pad, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t s) {
+  RFX_REQUIRE(cols_pad % 8 == 0 && cols_pad >= cols, "split_pad: padded width must be a multiple of 8");
+  split_pad_kernel<<<148 * 4, 256, 0, s>>>(src, rows, cols, cols_pad, hi, lo);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t transposed_pack_floats(int N, int K) {
+  const int Np = ceil_div(N, 64) * 64;
+  return split_weight_elems(K, Np, g2_choose_bn(K));
+}
+
+int pack_transposed(const float* W, int N, int K, float* tmp, float* store, SplitW* out, cudaStream_t s) {
+  const int Np = ceil_div(N, 64) * 64;
+  transpose_w_kernel<<<148 * 4, 256, 0, s>>>(W, N, 1, K, K, Np, tmp);   // wcat [n][1][Kp = K] -> wt [k][Np]
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return pack_split_weights(tmp, Np, K, Np, g2_choose_bn(K), reinterpret_cast<__nv_bfloat16*>(store), out, s);
+}
+
+int lstm_layer_backward(const float* Gx, int Bs, int T, int H, const __nv_bfloat16* h_hi, size_t h_plane, int ldh, const SplitW& whh_f,
+                        const SplitW& whh_r, const float* whh_cat, const float* dH, float* R, float* cs, float* dG, float* carry, unsigned* bar,
+                        cudaStream_t s) {
+  int rc;
+  // 1. R = W_hh h_prev for every step: one GEMM per direction over the saved h shifted by one step
+  for (int d = 0; d < 2; ++d) {
+    G2Problem q;
+    q.A.hi = h_hi + d * H; q.A.rows = T; q.A.rows_y = 1; q.A.ld = ldh; q.A.ld_y = (long long)T * ldh;
+    q.A.batch_stride = (long long)T * ldh; q.A.plane_stride = (long long)h_plane;
+    q.W = d ? whh_r : whh_f;
+    q.M = T; q.My = 1; q.N = 4 * H; q.batch = Bs; q.Ktap = H; q.taps = 1;
+    q.row_off[0] = d ? 1 : -1;
+    int xt = 128;
+    while (xt > T && xt > 1) xt >>= 1;
+    q.xt = xt;
+    q.Cf = R + (size_t)d * 4 * H; q.ldcf = 8 * H; q.ldcf_y = (long long)T * 8 * H; q.bscf = (long long)T * 8 * H;
+    if ((rc = launch_gemm2(q, s))) return rc;
+  }
+  // 2. cell states
+  lstm_cscan_kernel<<<ceil_div(Bs * 2 * H, 256), 256, 0, s>>>(Gx, R, Bs, T, H, cs);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  // 3. reverse-time chain: persistent cooperative launch, or one launch per step when that cannot be co-resident
+  bool persistent = false;
+  {
+    static const bool stepwise = [] { const char* e = getenv("RFX_HD_LSTM_BWD_STEPWISE"); return e && atoi(e) != 0; }();
+    const dim3 pg(H / LBP_U, 2, ceil_div(Bs, LBP_B));
+    const size_t psmem = ((size_t)4 * H * LBP_U + (size_t)LBP_B * (4 * H + 4)) * 4;
+    int sms = 148, dev = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!stepwise && H % LBP_U == 0 && psmem <= 227 * 1024 &&
+        cudaFuncSetAttribute(lstm_bwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_persist_kernel, 256, psmem) == cudaSuccess &&
+        (long long)pg.x * pg.y * pg.z <= (long long)per_sm * sms) {
+      RFX_CHECK_CUDA(cudaMemsetAsync(bar, 0, (size_t)2 * pg.z * sizeof(unsigned), s));
+      const float* a0 = Gx; const float* a1 = R; const float* a2 = cs; const float* a3 = dH; const float* a4 = whh_cat;
+      float* a5 = dG; int a6 = Bs, a7 = T, a8 = H; unsigned* a9 = bar;
+      void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9};
+      const cudaError_t e = cudaLaunchCooperativeKernel((const void*)lstm_bwd_persist_kernel, pg, dim3(256), args, psmem, s);
+      if (e == cudaSuccess) persistent = true;
+      else (void)cudaGetLastError();
+    }
+  }
+  if (!persistent) {
+    const size_t smem = (size_t)LB_NB * 4 * H * 4;
+    RFX_CHECK_CUDA(cudaFuncSetAttribute(lstm_bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(H, 128), 2, ceil_div(Bs, LB_NB));
+    for (int k = 0; k < T; ++k) lstm_bwd_step_kernel<<<grid, 128, smem, s>>>(Gx, R, cs, dH, whh_cat, dG, carry, Bs, T, H, k);
+    RFX_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int istft_adjoint_prep(const float* dout, int B, int T, const float* window, int n_fft, int hop, int frame_off, int F, int env_pad, int P0, int Ltot,
+                       float* ghat, cudaStream_t s) {
+  istft_adj_prep_kernel<<<dim3(ceil_div(Ltot, 256), B), 256, 0, s>>>(dout, T, window, n_fft, hop, frame_off, F, env_pad, P0, Ltot, ghat);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bw
 }  // namespace rfx
 
 extern "C" {
