@@ -76,6 +76,28 @@ __host__ __device__ __forceinline__ float2 irfft_pre(float2 xk, float2 xn, float
   return make_float2(e.x - o.y, -(e.y + o.x));
 }
 
+// The bin pair (k, NC - k), 0 <= k < NC/2, from zk = Z[k], zn = Z[(NC - k) mod NC] and twk = tw[k] (tw[NC - k] = -conj(tw[k])):
+//   X[k] = E + T,  X[NC - k] = conj(E - T),  E = (zk + conj(zn)) / 2,  T = tw[k] (zk - conj(zn)) / (2 i).
+// Returns 2 X (the factor 1/2 is exact in binary floating point and is folded into the caller's scale), so the values equal
+// rfft_post()'s bit for bit up to the table rounding of tw[NC - k].  k = 0 gives the DC bin and the Nyquist bin (k = NC).
+__host__ __device__ __forceinline__ void rfft_post_pair2(float2 zk, float2 zn, float2 twk, float2& xk2, float2& xn2) {
+  const float2 e = make_float2(zk.x + zn.x, zk.y - zn.y);
+  const float2 d = make_float2(zk.x - zn.x, zk.y + zn.y);
+  const float2 t = cmul(make_float2(d.y, -d.x), twk);
+  xk2 = make_float2(e.x + t.x, e.y + t.y);
+  xn2 = make_float2(e.x - t.x, t.y - e.y);
+}
+
+// Inverse of the above for the packed-spectrum points k and NC - k (0 < k < NC/2) from the Hermitian half-spectrum bins
+// xk = X[k], xn = X[NC - k]: returns 2 conj(Zc[k]) and 2 conj(Zc[NC - k]) (see irfft_pre; the 1/2 is folded into the caller's scale).
+__host__ __device__ __forceinline__ void irfft_pre_pair2(float2 xk, float2 xn, float2 twk, float2& zk2, float2& zn2) {
+  const float2 e = make_float2(xk.x + xn.x, xk.y - xn.y);
+  const float2 d = make_float2(xk.x - xn.x, xk.y + xn.y);
+  const float2 o = cmul(d, make_float2(twk.x, -twk.y));  // d * exp(+2 pi i k / n_fft)
+  zk2 = make_float2(e.x - o.y, -(e.y + o.x));
+  zn2 = make_float2(e.x + o.y, e.y - o.x);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // 1024-point complex FFT (n_fft = 2048) as THREE register passes -- radix 16, 16, 4 -- by 64 threads:
 // two shared-memory exchanges per frame instead of five, 16-point butterflies entirely in registers.
@@ -181,14 +203,39 @@ __host__ __device__ __forceinline__ void fft1024_pass_r4_last(const float2* __re
 #ifdef __CUDACC__
 // Four 1024-point FFTs at once by a 256-thread CTA, IN PLACE: frame g = tid / 64 lives in buf + g FFT1024_BUF, natural order
 // on entry and on return.  Every pass is load-all / barrier / store-all.  Ends with a __syncthreads().
+template <bool LEAD_SYNC = true>
 __device__ __forceinline__ void fft1024_x4(float2* buf, const float2* __restrict__ tw, int tid) {
   const int t = tid & 63;
   float2* f = buf + (tid >> 6) * FFT1024_BUF;
   float2 v[16];
-  __syncthreads();
+  if (LEAD_SYNC) __syncthreads();  // false: the caller has already put a barrier behind the writes of the input
   fft1024_r16_load<false>(f, t, v);
   fft1024_r16_compute(tw, 1, t, v);
   __syncthreads();
+  fft1024_r16_store<true>(f, 1, t, v);
+  __syncthreads();
+  fft1024_r16_load<true>(f, t, v);
+  fft1024_r16_compute(tw, 16, t, v);
+  __syncthreads();
+  fft1024_r16_store<true>(f, 16, t, v);
+  __syncthreads();
+  float2 w[4][4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) fft1024_r4_last_load(f, tw, t + 64 * m, w[m]);
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) f[t + 64 * m + 256 * r] = w[m][r];
+  __syncthreads();
+}
+
+// Same, with the first pass's inputs already in registers (v[r] = element t + 64 r of the thread's frame): the windowed samples
+// (STFT) go from their staging buffer straight into the radix-16 butterflies.  The frame buffer must not be in use on entry.
+__device__ __forceinline__ void fft1024_x4_regs(float2* buf, const float2* __restrict__ tw, int tid, float2 (&v)[16]) {
+  const int t = tid & 63;
+  float2* f = buf + (tid >> 6) * FFT1024_BUF;
+  fft1024_r16_compute(tw, 1, t, v);
   fft1024_r16_store<true>(f, 1, t, v);
   __syncthreads();
   fft1024_r16_load<true>(f, t, v);

@@ -37,6 +37,7 @@ struct StftParams {
   const float* in_mean;   // STFT_UMX_MAG only
   const float* in_scale;
   int max_sms = 0;        // > 0: size the grid to fill at most this many SMs (grid-stride over the frame groups); 0 = one CTA per group
+  int sms_avail = 0;      // SMs the launching stream can use (a green-context partition); 0 = the whole device.  Sizes persistent grids
 };
 
 struct IstftParams {
@@ -55,6 +56,7 @@ struct IstftParams {
   long long out_bstride;
   int hops_per_cta;
   int max_sms = 0;    // > 0: size the grid to fill at most this many SMs (grid-stride over the output segments)
+  int sms_avail = 0;  // SMs the launching stream can use (a green-context partition); 0 = the whole device.  Sizes persistent grids
 };
 
 const float2* twiddles(int n_fft);

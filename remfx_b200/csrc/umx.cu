@@ -137,6 +137,7 @@ UmxLayout umx_layout(const rfx_umx* h, int B, int T) {
   L.M = B * L.F;
   L.lda1 = ceil_div(h->bins, 8) * 8;
   L.ldm = ceil_div(h->bins, 4) * 4;
+  L.ldz = ceil_div(h->bins, 2) * 2;  // even: spectrum rows stay 16-byte aligned for the bulk copies of the staged iSTFT
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
   const size_t M = L.M;
@@ -149,7 +150,7 @@ UmxLayout umx_layout(const rfx_umx* h, int B, int T) {
     L.off_x[i] = take((size_t)B * T * 4);
     L.off_out[i] = take((size_t)B * T * 4);
   }
-  L.off_Z = take(M * h->bins * 8);
+  L.off_Z = take(M * L.ldz * 8);
   L.off_A1 = take(L.plane_A1 * 2 * 2);
   L.off_XC = take(L.plane_XC * 2 * 2);
   L.off_G = take(M * 8 * h->H * 4);
@@ -357,10 +358,10 @@ int umx_stage(rfx_umx_t* h, const UmxCall& c, int l) {
     sp.n_fft = h->cfg.n_fft; sp.hop = h->cfg.hop; sp.F = L.F;
     sp.frame_off = h->cfg.n_fft / 2; sp.nbins = h->bins;
     sp.scale = 1.0f; sp.alpha = 1.0f; sp.mode = STFT_UMX_MAG;
-    sp.Z = Z; sp.ldz = h->bins; sp.A = nullptr; sp.lda = 0;
+    sp.Z = Z; sp.ldz = L.ldz; sp.A = nullptr; sp.lda = 0;
     sp.Ahi = A1; sp.Alo = A1 + L.plane_A1; sp.ldas = L.lda1;
     sp.in_mean = P(h, "input_mean"); sp.in_scale = P(h, "input_scale");
-    sp.max_sms = c.max_sms;
+    sp.max_sms = c.max_sms; sp.sms_avail = c.gemm_ctas;
     const bool h2d = io && io->x_host;
     for (int ch = 0; ch < nch; ++ch) {
       const int i0 = (int)((long long)B * ch / nch), i1 = (int)((long long)B * (ch + 1) / nch);
@@ -374,7 +375,7 @@ int umx_stage(rfx_umx_t* h, const UmxCall& c, int l) {
       const int i0 = (int)((long long)B * ch / nch), i1 = (int)((long long)B * (ch + 1) / nch);
       StftParams sc = sp;
       sc.x = c.x + (size_t)i0 * T;
-      sc.Z = Z + (size_t)i0 * L.F * h->bins;
+      sc.Z = Z + (size_t)i0 * L.F * L.ldz;
       sc.Ahi = A1 + (size_t)i0 * L.F * L.lda1; sc.Alo = sc.Ahi + L.plane_A1;
       if (h2d) RFX_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_in[io->slot][ch], 0));
       if ((rc = launch_stft(sc, i1 - i0, s))) return rc;
@@ -426,18 +427,18 @@ int umx_stage(rfx_umx_t* h, const UmxCall& c, int l) {
 
     // (6) `* mix` (model.py:164) + wiener niter=0 (filtering.py:442-451) + iSTFT (transforms.py:168-177)
     IstftParams ip{};
-    ip.Z = Z; ip.ldz = h->bins; ip.mask = mask; ip.ldm = L.ldm;
+    ip.Z = Z; ip.ldz = L.ldz; ip.mask = mask; ip.ldm = L.ldm;
     ip.window = P(h, "window"); ip.tw = tw;
     ip.n_fft = h->cfg.n_fft; ip.hop = h->cfg.hop; ip.F = L.F; ip.length = T;
     ip.frame_off = h->cfg.n_fft / 2; ip.env_pad = 0; ip.nbins = h->bins;
     ip.scale = 1.0f; ip.out = c.out; ip.out_bstride = T; ip.hops_per_cta = 16;
-    ip.max_sms = c.max_sms;
+    ip.max_sms = c.max_sms; ip.sms_avail = c.gemm_ctas;
     const bool d2h = io && io->out_host;
     const int nco = d2h ? nch : 1;
     for (int ch = 0; ch < nco; ++ch) {
       const int i0 = (int)((long long)B * ch / nco), i1 = (int)((long long)B * (ch + 1) / nco);
       IstftParams ic = ip;
-      ic.Z = Z + (size_t)i0 * L.F * h->bins;
+      ic.Z = Z + (size_t)i0 * L.F * L.ldz;
       ic.mask = mask + (size_t)i0 * L.F * L.ldm;
       ic.out = c.out + (size_t)i0 * T;
       if ((rc = launch_istft(ic, i1 - i0, s))) return rc;

@@ -93,7 +93,7 @@ namespace rfx {
 
 // Workspace layout.  Activations between tensor-core layers are split-bf16 planes (hi then lo).
 struct UmxLayout {
-  int F, M, lda1, ldm;
+  int F, M, lda1, ldm, ldz;
   size_t off_x[2], off_out[2], off_Z, off_A1, off_XC, off_G, off_H1, off_H2, off_Y2, off_mask, total;
   size_t plane_A1, plane_XC, plane_H, plane_Y2;  // elements per plane
 };

@@ -89,8 +89,45 @@ static int run1024() {
   return maxerr < 2e-5 * maxref ? 0 : 1;
 }
 
+// bin-pair forms used by the staged n_fft = 2048 kernels: rfft_post_pair2 / irfft_pre_pair2 against rfft_post / irfft_pre
+static int run_pairs() {
+  const int NC = 1024, n_fft = 2048;
+  std::vector<float2> tw(n_fft), Z(NC);
+  for (int m = 0; m < n_fft; ++m) tw[m] = make_float2((float)cos(-2.0 * M_PI * m / n_fft), (float)sin(-2.0 * M_PI * m / n_fft));
+  srand(11);
+  for (auto& v : Z) v = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+  double e1 = 0, e2 = 0;
+  std::vector<float2> X(NC + 1);
+  for (int k = 0; k <= NC; ++k) X[k] = rfft_post(Z.data(), tw.data(), NC, k);
+  for (int k = 0; k < NC / 2; ++k) {
+    float2 xk, xn;
+    rfft_post_pair2(Z[k], Z[(NC - k) & (NC - 1)], tw[k], xk, xn);
+    e1 = fmax(e1, hypot(0.5f * xk.x - X[k].x, 0.5f * xk.y - X[k].y));
+    e1 = fmax(e1, hypot(0.5f * xn.x - X[NC - k].x, 0.5f * xn.y - X[NC - k].y));
+  }
+  X[0].y = 0; X[NC].y = 0;
+  for (int k = 0; k < NC / 2; ++k) {
+    float2 zk2, zn2;
+    irfft_pre_pair2(X[k], X[NC - k], tw[k], zk2, zn2);
+    const float2 a = irfft_pre(X[k], X[NC - k], tw[k]);
+    e2 = fmax(e2, hypot(0.5f * zk2.x - a.x, 0.5f * zk2.y - a.y));
+    if (k) {
+      const float2 b = irfft_pre(X[NC - k], X[k], tw[NC - k]);
+      e2 = fmax(e2, hypot(0.5f * zn2.x - b.x, 0.5f * zn2.y - b.y));
+    }
+  }
+  {
+    float2 zk2, zn2;
+    irfft_pre_pair2(X[NC / 2], X[NC / 2], tw[NC / 2], zk2, zn2);
+    const float2 a = irfft_pre(X[NC / 2], X[NC / 2], tw[NC / 2]);
+    e2 = fmax(e2, hypot(0.5f * zk2.x - a.x, 0.5f * zk2.y - a.y));
+  }
+  printf("pair forms: forward max diff %.3e, inverse max diff %.3e\n", e1, e2);
+  return (e1 < 2e-7 && e2 < 2e-7) ? 0 : 1;
+}
+
 int main() {
-  int bad = run1024();
+  int bad = run1024() + run_pairs();
   for (int n : {64, 128, 512, 1024, 2048, 4096}) bad += run(n);
   printf(bad ? "FAIL\n" : "OK\n");
   return bad;
