@@ -201,57 +201,66 @@ __host__ __device__ __forceinline__ void fft1024_pass_r4_last(const float2* __re
 }
 
 #ifdef __CUDACC__
+// Barrier of one frame's 64 threads (named barrier 1 + frame slot) or of the whole CTA (GROUP_SYNC = false).  With the
+// per-frame form the four frames of a CTA drift apart, so one frame's shared-memory phases overlap another's butterflies.
+template <bool GROUP_SYNC>
+__device__ __forceinline__ void fft_sync(int tid) {
+  if (GROUP_SYNC) asm volatile("bar.sync %0, 64;" ::"r"(1 + (tid >> 6)) : "memory");
+  else __syncthreads();
+}
+
 // Four 1024-point FFTs at once by a 256-thread CTA, IN PLACE: frame g = tid / 64 lives in buf + g FFT1024_BUF, natural order
-// on entry and on return.  Every pass is load-all / barrier / store-all.  Ends with a __syncthreads().
-template <bool LEAD_SYNC = true>
+// on entry and on return.  Every pass is load-all / barrier / store-all.  Ends with a barrier (of the kind chosen).
+template <bool LEAD_SYNC = true, bool GROUP_SYNC = false>
 __device__ __forceinline__ void fft1024_x4(float2* buf, const float2* __restrict__ tw, int tid) {
   const int t = tid & 63;
   float2* f = buf + (tid >> 6) * FFT1024_BUF;
   float2 v[16];
-  if (LEAD_SYNC) __syncthreads();  // false: the caller has already put a barrier behind the writes of the input
+  if (LEAD_SYNC) fft_sync<GROUP_SYNC>(tid);  // false: the caller has already put a barrier behind the writes of the input
   fft1024_r16_load<false>(f, t, v);
   fft1024_r16_compute(tw, 1, t, v);
-  __syncthreads();
+  fft_sync<GROUP_SYNC>(tid);
   fft1024_r16_store<true>(f, 1, t, v);
-  __syncthreads();
+  fft_sync<GROUP_SYNC>(tid);
   fft1024_r16_load<true>(f, t, v);
   fft1024_r16_compute(tw, 16, t, v);
-  __syncthreads();
+  fft_sync<GROUP_SYNC>(tid);
   fft1024_r16_store<true>(f, 16, t, v);
-  __syncthreads();
+  fft_sync<GROUP_SYNC>(tid);
   float2 w[4][4];
 #pragma unroll
   for (int m = 0; m < 4; ++m) fft1024_r4_last_load(f, tw, t + 64 * m, w[m]);
-  __syncthreads();
+  fft_sync<GROUP_SYNC>(tid);
 #pragma unroll
   for (int m = 0; m < 4; ++m)
 #pragma unroll
     for (int r = 0; r < 4; ++r) f[t + 64 * m + 256 * r] = w[m][r];
-  __syncthreads();
+  fft_sync<GROUP_SYNC>(tid);
 }
 
 // Same, with the first pass's inputs already in registers (v[r] = element t + 64 r of the thread's frame): the windowed samples
 // (STFT) go from their staging buffer straight into the radix-16 butterflies.  The frame buffer must not be in use on entry.
+template <bool GROUP_SYNC = false>
 __device__ __forceinline__ void fft1024_x4_regs(float2* buf, const float2* __restrict__ tw, int tid, float2 (&v)[16]) {
   const int t = tid & 63;
   float2* f = buf + (tid >> 6) * FFT1024_BUF;
   fft1024_r16_compute(tw, 1, t, v);
   fft1024_r16_store<true>(f, 1, t, v);
-  __syncthreads();
+  fft_sync<GROUP_SYNC>(tid);
   fft1024_r16_load<true>(f, t, v);
   fft1024_r16_compute(tw, 16, t, v);
-  __syncthreads();
+  fft_sync<GROUP_SYNC>(tid);
   fft1024_r16_store<true>(f, 16, t, v);
-  __syncthreads();
+  fft_sync<GROUP_SYNC>(tid);
   float2 w[4][4];
 #pragma unroll
   for (int m = 0; m < 4; ++m) fft1024_r4_last_load(f, tw, t + 64 * m, w[m]);
-  __syncthreads();
+  fft_sync<GROUP_SYNC>(tid);
 #pragma unroll
   for (int m = 0; m < 4; ++m)
 #pragma unroll
     for (int r = 0; r < 4; ++r) f[t + 64 * m + 256 * r] = w[m][r];
-  __syncthreads();
+  fft_sync<GROUP_SYNC>(tid);
 }
 
 // Cooperative complex FFT of NC = 2^LOG2NC points by NC/4 threads.  Input in `a`; returns the buffer

@@ -36,6 +36,7 @@ struct StftParams {
   int ldas;
   const float* in_mean;   // STFT_UMX_MAG only
   const float* in_scale;
+  const float2* in_ms = nullptr;  // optional interleaved (mean, scale) copy of the two: one load per bin in the staged kernel
   int max_sms = 0;        // > 0: size the grid to fill at most this many SMs (grid-stride over the frame groups); 0 = one CTA per group
   int sms_avail = 0;      // SMs the launching stream can use (a green-context partition); 0 = the whole device.  Sizes persistent grids
 };

@@ -196,18 +196,30 @@ __global__ void __launch_bounds__(256, 4) stft2048_kernel(StftParams p, int grou
 
 // ---- n_fft = 2048, bulk-copy staged ("TMA-staged window" of the north star) ----------------------------------------------
 // Persistent CTAs; work item = (batch item, 4 consecutive frames).  The 3 hop + 2048 samples the four frames share are brought in
-// by ONE cp.async.bulk (SASS UBLKCP) into a double-buffered staging area -- item i + 1 is in flight while item i is transformed,
-// and every sample is read from L2 / HBM once per item instead of once per overlapping frame.  The windowed samples go from the
-// staging buffer straight into the first radix-16 butterflies (registers), the window lives in shared memory, and the epilogue
-// handles the bins in (k, NC - k) pairs: both come from the same two packed-FFT points and the same twiddle.
-// Items that touch the reflect padding (the first / last groups of an item) fill their staging buffer with ordinary loads.
+// by ONE cp.async.bulk (SASS UBLKCP): the copy of item i + 1 is issued as soon as every frame of item i has its samples in
+// registers and lands during item i's FFT and epilogue, and every sample is read from L2 / HBM once per item instead of once per
+// overlapping frame.  The windowed samples go from the staging buffer straight into the first radix-16 butterflies (registers); the
+// window AND the twiddle table live in shared memory (with three CTAs of shared memory per SM the L1 is down to ~28 KB and table
+// reads through it showed up as the kernel's main stall); the barriers inside the FFT are per frame (64 threads), so the four
+// frames of a CTA drift apart; the epilogue handles the bins in (k, NC - k) pairs -- both come from the same two packed-FFT points
+// and the same twiddle.  Items that touch the reflect padding (the first / last groups of an item) fill the staging buffer with
+// ordinary loads.
 template <int MODE>
 __device__ __forceinline__ void stft_emit_bin(const StftParams& p, int k, float2 X, float2* __restrict__ Zrow, float* __restrict__ Arow,
                                               __nv_bfloat16* __restrict__ Hrow, __nv_bfloat16* __restrict__ Lrow) {
   if (Zrow) Zrow[k] = X;
   if (MODE != STFT_COMPLEX) {
     const float pw = X.x * X.x + X.y * X.y;
-    const float a = stft_mag_of<MODE>(pw, MODE == STFT_UMX_MAG ? p.in_mean[k] : 0.f, MODE == STFT_UMX_MAG ? p.in_scale[k] : 1.f, p.alpha);
+    float mean = 0.f, scl = 1.f;
+    if (MODE == STFT_UMX_MAG) {
+      if (p.in_ms) {
+        const float2 ms = __ldg(p.in_ms + k);
+        mean = ms.x; scl = ms.y;
+      } else {
+        mean = p.in_mean[k]; scl = p.in_scale[k];
+      }
+    }
+    const float a = stft_mag_of<MODE>(pw, mean, scl, p.alpha);
     if (Arow) Arow[k] = a;
     if (Hrow) {  // split-bf16 copy for the tensor-core layer that consumes it
       __nv_bfloat16 h, l;
@@ -223,48 +235,44 @@ __global__ void __launch_bounds__(256, 3) stft2048_tma_kernel(StftParams p, int 
   constexpr int NC = 1024, NFFT = 2048;
   extern __shared__ __align__(128) unsigned char stft_smem[];
   float2* buf = reinterpret_cast<float2*>(stft_smem);            // [4][FFT1024_BUF]
-  float* win = reinterpret_cast<float*>(buf + 4 * FFT1024_BUF);  // [NFFT]
-  float* xs = win + NFFT;                                        // [2][seg] staged samples
-  uint64_t* bar = reinterpret_cast<uint64_t*>(xs + 2 * seg);     // [2]
+  float2* tws = buf + 4 * FFT1024_BUF;                           // [NFFT] twiddles
+  float* win = reinterpret_cast<float*>(tws + NFFT);             // [NFFT]
+  float* xs = win + NFFT;                                        // [seg] staged samples
+  uint64_t* bar = reinterpret_cast<uint64_t*>(xs + seg);
   const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
   float2* fb = buf + g * FFT1024_BUF;
   for (int i = tid; i < NC; i += 256) reinterpret_cast<float2*>(win)[i] = reinterpret_cast<const float2*>(p.window)[i];
+  for (int i = tid; i < NFFT; i += 256) tws[i] = p.tw[i];
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    mbar_init(bar, 1);
     mbar_fence_init();
   }
   __syncthreads();
   const int span = 4 * p.hop;
-  auto issue = [&](int work, int stage) {  // one thread: start the copy of a work item's samples (interior items only)
+  auto issue = [&](int work) {  // one thread: start the copy of a work item's samples (interior items only)
     const int b = work / groups;
     const int base = (work - b * groups) * span - p.frame_off;
     if (base >= 0 && base + seg <= p.T) {
-      mbar_arrive_expect_tx(&bar[stage], (uint32_t)seg * 4u);
-      bulk_g2s(xs + (size_t)stage * seg, p.x + (size_t)b * p.x_bstride + base, (uint32_t)seg * 4u, &bar[stage]);
+      mbar_arrive_expect_tx(bar, (uint32_t)seg * 4u);
+      bulk_g2s(xs, p.x + (size_t)b * p.x_bstride + base, (uint32_t)seg * 4u, bar);
     }
   };
-  if (tid == 0 && (int)blockIdx.x < n_work) issue(blockIdx.x, 0);
-  uint32_t phase = 0;  // bit s = parity the next completion of stage s will have
-  int it = 0;
-  for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++it) {
-    const int stage = it & 1;
-    // the other stage was last read in the load phase of the previous iteration, which every thread has left (barrier below)
-    if (tid == 0 && work + (int)gridDim.x < n_work) issue(work + gridDim.x, stage ^ 1);
+  if (tid == 0 && (int)blockIdx.x < n_work) issue(blockIdx.x);
+  uint32_t phase = 0;
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
     const int b = work / groups;
     const int fg = work - b * groups;
     const int base = fg * span - p.frame_off;
-    float* xst = xs + (size_t)stage * seg;
     if (base >= 0 && base + seg <= p.T) {
-      mbar_wait(&bar[stage], (phase >> stage) & 1u);
-      phase ^= 1u << stage;
+      mbar_wait(bar, phase);
+      phase ^= 1u;
     } else {
       const float* __restrict__ x = p.x + (size_t)b * p.x_bstride;
       for (int i = tid; i < seg; i += 256) {
         int r = base + i;
         if (r < 0) r = -r;
         if (r >= p.T) r = 2 * (p.T - 1) - r;
-        xst[i] = (r >= 0 && r < p.T) ? x[r] : 0.0f;  // beyond the reflected range only frames >= F read (and they are not emitted)
+        xs[i] = (r >= 0 && r < p.T) ? x[r] : 0.0f;  // beyond the reflected range only frames >= F read (and they are not emitted)
       }
       fence_proxy_async_smem();  // generic writes, later overwritten through the async proxy
       __syncthreads();
@@ -272,7 +280,7 @@ __global__ void __launch_bounds__(256, 3) stft2048_tma_kernel(StftParams p, int 
     const int f = fg * 4 + g;
     float2 v[16];
     {
-      const float* xf = xst + g * p.hop;
+      const float* xf = xs + g * p.hop;
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         const int n = t + 64 * r;
@@ -281,7 +289,9 @@ __global__ void __launch_bounds__(256, 3) stft2048_tma_kernel(StftParams p, int 
         v[r] = make_float2(xv.x * w.x, xv.y * w.y);
       }
     }
-    fft1024_x4_regs(buf, p.tw, tid, v);
+    __syncthreads();  // every frame has its samples: the staging buffer is free for the next item
+    if (tid == 0 && work + (int)gridDim.x < n_work) issue(work + gridDim.x);
+    fft1024_x4_regs<true>(buf, tws, tid, v);
     if (f < p.F) {
       const size_t m = (size_t)b * p.F + f;
       float2* __restrict__ Zrow = p.Z ? p.Z + m * p.ldz : nullptr;
@@ -293,19 +303,19 @@ __global__ void __launch_bounds__(256, 3) stft2048_tma_kernel(StftParams p, int 
       for (int i = 0; i < 8; ++i) {
         const int k = t + 64 * i;  // [0, NC/2)
         float2 xk, xn;
-        rfft_post_pair2(fb[k], fb[(NC - k) & (NC - 1)], p.tw[k], xk, xn);
+        rfft_post_pair2(fb[k], fb[(NC - k) & (NC - 1)], tws[k], xk, xn);
         stft_emit_bin<MODE>(p, k, make_float2(xk.x * hs, xk.y * hs), Zrow, Arow, Hrow, Lrow);
         if (NC - k < p.nbins) stft_emit_bin<MODE>(p, NC - k, make_float2(xn.x * hs, xn.y * hs), Zrow, Arow, Hrow, Lrow);
       }
       if (t == 0) {
-        float2 X = rfft_post(fb, p.tw, NC, NC / 2);
+        float2 X = rfft_post(fb, tws, NC, NC / 2);
         stft_emit_bin<MODE>(p, NC / 2, make_float2(X.x * p.scale, X.y * p.scale), Zrow, Arow, Hrow, Lrow);
       }
       if (Arow && p.lda > NC + 1) {
         for (int k = NC + 1 + t; k < p.lda; k += 64) Arow[k] = 0.0f;
       }
     }
-    __syncthreads();  // the frame buffers and this stage are free again
+    fft_sync<true>(tid);  // this frame's buffer is rewritten by the next item's first pass
   }
 }
 
@@ -341,7 +351,7 @@ static bool stft2048_tma_ok(const StftParams& p) {
 
 static int launch_stft2048_tma(const StftParams& p, int B, cudaStream_t stream) {
   const int seg = 3 * p.hop + 2048;
-  const size_t smem = sizeof(float2) * 4 * FFT1024_BUF + sizeof(float) * (2048 + 2 * seg) + 16;
+  const size_t smem = sizeof(float2) * (4 * FFT1024_BUF + 2048) + sizeof(float) * (2048 + seg) + 16;
   const int groups = ceil_div(p.F, 4);
   const long long n_work_ll = (long long)groups * B;
   RFX_REQUIRE(n_work_ll < (1ll << 31), "stft: too many frames");
@@ -629,9 +639,11 @@ __global__ void __launch_bounds__(256, 2) istft2048_tma_kernel(IstftParams p, in
   float* ola = reinterpret_cast<float*>(zst + 4 * (size_t)p.ldz);       // [S]
   const int S = p.hops_per_cta * p.hop;
   float* env_int = ola + S;  // [hop] window envelope of an interior sample, by q mod hop (all NFFT / hop frames present)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(env_int + p.hop);
+  float2* tws = reinterpret_cast<float2*>(env_int + p.hop);  // [NFFT] twiddles (the L1 left beside this much shared memory is too small)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tws + NFFT);
   const int tid = threadIdx.x, g = tid >> 6, tl = tid & 63;
   float2* fb = buf + g * FFT1024_BUF;
+  for (int i = tid; i < NFFT; i += 256) tws[i] = p.tw[i];
   const float inv = 0.5f * p.scale / (float)NC;  // the unpacking below returns twice the packed spectrum
   const int fph = NFFT / p.hop;                  // frames covering an interior sample
   for (int r = tid; r < p.hop; r += 256) {
@@ -709,7 +721,7 @@ __global__ void __launch_bounds__(256, 2) istft2048_tma_kernel(IstftParams p, in
           xn.y = 0.0f;
         }
         float2 zk2, zn2;
-        irfft_pre_pair2(xk, xn, p.tw[k], zk2, zn2);
+        irfft_pre_pair2(xk, xn, tws[k], zk2, zn2);
         fb[k] = zk2;
         if (k != 0) fb[NC - k] = zn2;
       }
@@ -717,7 +729,7 @@ __global__ void __launch_bounds__(256, 2) istft2048_tma_kernel(IstftParams p, in
         float2 xh = zr[NC / 2];
         xh.x *= mh; xh.y *= mh;
         float2 zk2, zn2;
-        irfft_pre_pair2(xh, xh, p.tw[NC / 2], zk2, zn2);
+        irfft_pre_pair2(xh, xh, tws[NC / 2], zk2, zn2);
         fb[NC / 2] = zk2;
       }
     }
@@ -734,7 +746,8 @@ __global__ void __launch_bounds__(256, 2) istft2048_tma_kernel(IstftParams p, in
       }
     }
     if (more) fetch(nb, ntb, nt_hi);
-    fft1024_x4<false>(buf, p.tw, tid);
+    fft1024_x4<false, true>(buf, tws, tid);
+    __syncthreads();  // all four frames transformed
     // ---- window + overlap-add into the segment ----
     if (OWN) {
       float2 acc[7];
@@ -839,7 +852,7 @@ static int launch_istft2048_tma(const IstftParams& p_in, int B, cudaStream_t str
   IstftParams p = p_in;
   const bool own = p.hop == 512 && p.frame_off % 512 == 0;
   auto kern = own ? istft2048_tma_kernel<true> : istft2048_tma_kernel<false>;
-  const size_t smem_fixed = sizeof(float2) * 4 * FFT1024_BUF + sizeof(float2) * 4 * (size_t)p.ldz + sizeof(float) * p.hop + 16;
+  const size_t smem_fixed = sizeof(float2) * (4 * FFT1024_BUF + 2048) + sizeof(float2) * 4 * (size_t)p.ldz + sizeof(float) * p.hop + 16;
   const int sms = p.max_sms > 0 ? p.max_sms : (p.sms_avail > 0 ? p.sms_avail : device_sms());
   const size_t smem_cap = (227 * 1024) / 2 - 1024;  // two CTAs per SM
   static const int force_hpc = [] { const char* e = getenv("RFX_ISTFT_HOPS"); return e ? atoi(e) : 0; }();

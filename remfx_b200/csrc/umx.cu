@@ -123,6 +123,7 @@ rfx_umx::~rfx_umx() {
     for (auto e : events) cudaEventDestroy(e);
     for (auto& kv : params) kv.second.release();
     for (int i = 0; i < 3; ++i) { bn_s[i].release(); bn_t[i].release(); }
+    in_ms.release();
     for (auto& b : lstm_bias) b.release();
     for (auto& b : wih_cat) b.release();
     for (auto& b : whh_cat) b.release();
@@ -246,6 +247,10 @@ int rfx_umx_finalize(rfx_umx_t* h, void* stream) {
                              h->bn_s[i].p, h->bn_t[i].p, bn_n[i], s)))
       return rc;
   }
+  // (input_mean, input_scale) interleaved: one 8-byte load per bin in the STFT epilogue
+  if (h->in_ms.alloc((size_t)2 * bins)) return 1;
+  RFX_CHECK_CUDA(cudaMemcpy2DAsync(h->in_ms.p, 8, P(h, "input_mean"), 4, 4, bins, cudaMemcpyDeviceToDevice, s));
+  RFX_CHECK_CUDA(cudaMemcpy2DAsync(h->in_ms.p + 1, 8, P(h, "input_scale"), 4, 4, bins, cudaMemcpyDeviceToDevice, s));
   for (auto& b : h->lstm_bias) b.release();
   for (auto& b : h->wih_cat) b.release();
   for (auto& b : h->whh_cat) b.release();
@@ -360,7 +365,7 @@ int umx_stage(rfx_umx_t* h, const UmxCall& c, int l) {
     sp.scale = 1.0f; sp.alpha = 1.0f; sp.mode = STFT_UMX_MAG;
     sp.Z = Z; sp.ldz = L.ldz; sp.A = nullptr; sp.lda = 0;
     sp.Ahi = A1; sp.Alo = A1 + L.plane_A1; sp.ldas = L.lda1;
-    sp.in_mean = P(h, "input_mean"); sp.in_scale = P(h, "input_scale");
+    sp.in_mean = P(h, "input_mean"); sp.in_scale = P(h, "input_scale"); sp.in_ms = reinterpret_cast<const float2*>(h->in_ms.p);
     sp.max_sms = c.max_sms; sp.sms_avail = c.gemm_ctas;
     const bool h2d = io && io->x_host;
     for (int ch = 0; ch < nch; ++ch) {

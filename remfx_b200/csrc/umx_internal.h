@@ -34,7 +34,7 @@ struct rfx_umx {
   int bins = 0, H = 0;
   std::map<std::string, rfx::DevBuf> params;
   // derived at finalize()
-  rfx::DevBuf bn_s[3], bn_t[3];
+  rfx::DevBuf bn_s[3], bn_t[3], in_ms;
   std::vector<rfx::DevBuf> lstm_bias, wih_cat, whh_cat;
   std::vector<rfx::DevBuf> packed_store;  // split-bf16 (hi, lo) weight planes
   rfx::SplitW fc1p, fc2p, fc3p;
