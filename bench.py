@@ -567,15 +567,15 @@ def run_ours(args):
     step_flops = 6.57e9 * BATCH  # FC 1.61 + LSTM 4.84 + FFT 0.12 GFLOP per chunk
     tpeak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     roofline = {
-        "kernel": "lstm_rec_tc_kernel (BiLSTM recurrence on tcgen05, W_hh as the TMEM A operand; 1 launch per layer)",
+        "kernel": "lstm_rec_tc_kernel<16,2> (BiLSTM recurrence on tcgen05, W_hh as the TMEM A operand, two phase-locked 16-slot groups per CTA; 1 launch per layer)",
         "bound": "latency",
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-        "traffic": 154.66e6,  # dram read+write bytes per launch, ncu --set full (profiles/r1/ncu_lstm_rec_tc32.txt)
+        "traffic": 157.8e6,  # dram read+write bytes per launch, ncu --set full (profiles/r2/ncu_lstm_rec_tc_dual_locked.txt)
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": lstm_bytes, "ms_per_launch": lstm_t * 1e3,
         "launches_timed": len(lstm_ms),
         "us_per_dependent_step": lstm_t * 1e6 / steps_per_launch, "dependent_steps_per_launch": steps_per_launch,
-        "tensor_pipe_active_frac_ncu": 0.205,  # sm__pipe_tensor_subunit active on the SMs the launch holds (same ncu capture)
+        "tensor_pipe_active_frac_ncu": 0.28,  # sm__pipe_tensor_subunit active on the SMs the launch holds (same ncu capture)
         "note": "513 strictly dependent steps per launch: neither HBM- nor tensor-bound but latency-bound (MMA -> TMEM epilogue -> "
                 "cluster exchange per step), so the HBM figure above is reported for the contract and the per-step latency is the "
                 "number to improve; in the pipeline a launch holds "

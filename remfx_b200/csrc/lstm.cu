@@ -562,6 +562,9 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS * G
     lstm_rec_tc_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Whh, float* __restrict__ Hout, int ldh,
                        __nv_bfloat16* __restrict__ Hhi, __nv_bfloat16* __restrict__ Hlo, int ldhs, int B, int F, int NB, int fast) {
   constexpr int H = 256;
+  const int dbg = fast >> 8;  // timing experiments only (RFX_LSTM_TC_DEBUG, wrong results on purpose): 1 = exchange the hi plane only, 4 = no MMAs,
+                              // 8 = no G loads, 16 = no phase lock between the two groups
+  fast &= 1;
   constexpr int UPC = H / LSTM_CL;  // 32 units per CTA -> 128 gate rows = MMA M
   constexpr int TC_BLKP = N * 64;   // bytes of one plane of one CTA's h block: N slots x 32 units bf16
   constexpr int TC_BLK = 2 * TC_BLKP;  // hi + lo
@@ -640,8 +643,35 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS * G
     constexpr uint32_t lbo = 128u, sbo = 512u;
     constexpr uint32_t desc_hi = (sbo >> 4) | (1u << 14);  // SBO, descriptor version 1, no swizzle
     const uint32_t d_acc = tb_u + 256u + (uint32_t)(grp * TC_ISSUERS * N) + (uint32_t)(w * N);
+    // The input projections G (134 MB per layer at B = 32: HBM-resident) are needed by the epilogue warps once per step, one 128-byte
+    // line per (slot, gate).  Issued one step ahead their DRAM latency is not always hidden (single-group launch: 0.739 -> 0.658 ms
+    // with this prefetch); the issue warps, idle most of the step, pull the lines of step + TC_PF into L2: issuer w = gate w, lane = slot.
+    constexpr int TC_PF = 4;
+    const bool pf_on = lane < N && lane < NBg && (b0 + lane) < B && !(dbg & 8);
+    const float* pf_base = G + (size_t)(b0 + lane) * (size_t)F * (size_t)ldg + (size_t)(dir * 4 * H + w * H + (int)rank * UPC);
+    auto prefetch_g = [&](int st) {
+      if (pf_on && st < F) {
+        const int tq = dir ? F - 1 - st : st;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + (size_t)tq * (size_t)ldg));
+      }
+    };
+    for (int st = 1; st < TC_PF; ++st) prefetch_g(st);
+    // Phase lock of the two groups (GROUPS = 2).  Left alone the groups settle at an arbitrary relative phase: out of phase a
+    // 32-slot launch takes ~0.75 ms, in phase (both on the tensor pipe, then both in the gate math, then both exchanging) 1.0+ ms,
+    // and which one a launch got changed with unrelated code edits.  The lock: group 1 issues the MMAs of step s only when group
+    // 0's MMAs of step s have completed, group 0 those of step s + 1 only when group 1's of step s have (each waits on the OTHER
+    // group's mma_bar, which the epilogue warps of that group wait on anyway).  That keeps the groups at least one MMA phase apart
+    // and at most one step minus an MMA phase, without adding a dependency longer than a step; measured 1.00 -> 0.76 ms.  Locks
+    // on later events (gate math done: 0.91 ms; h pushed: 1.10 ms) serialise too much of the two steps.
+    const bool lock = GROUPS > 1 && !(dbg & 16);
+    uint64_t* mma_bar_other = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(mma_bar) + (GROUPS > 1 ? (grp ? -GROUP_SMEM : GROUP_SMEM) : 0));
     for (int step = 0; step < F; ++step) {
       const int cur = step & 1;
+      prefetch_g(step + TC_PF);
+      if (lock) {
+        if (grp == 1) mbar_wait(mma_bar_other, step & 1);
+        else if (step > 0) mbar_wait(mma_bar_other, (step - 1) & 1);
+      }
       // units [16 kk, 16 kk + 16) live in source CTA kk / 2, unit groups 2 (kk & 1), + 1 of its block.  Every source block has
       // its own mbarrier and the senders rotate their destinations, so the blocks of a step land spread over the exchange:
       // this issuer starts on source 2 w as soon as THAT block is here, then source 2 w + 1.
@@ -652,7 +682,8 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS * G
         if (step > 0) mbar_wait(&h_bar[cur * LSTM_CL + 2 * w + half], ((step - 1) >> 1) & 1);  // h_{t-1} of source CTA 2 w + half
         tc_fence_after();
         if (elect_one()) {
-          if (fast) {  // bf16-fast (set_matmul_precision(1)): W_hi h_hi only
+          if (dbg & 4) {
+          } else if (fast) {  // bf16-fast (set_matmul_precision(1)): W_hi h_hi only
 #pragma unroll
             for (int k2 = 0; k2 < 2; ++k2) {
               const int k4 = 2 * half + k2;
@@ -694,7 +725,7 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS * G
 #pragma unroll
       for (int s2 = 0; s2 < HS; ++s2) {
         gq[s2] = 0.f;
-        if (st < F && (vmask >> s2 & 1u)) {
+        if (st < F && (vmask >> s2 & 1u) && !(dbg & 8)) {
           const uint32_t tq = (uint32_t)(dir ? F - 1 - st : st);
           gq[s2] = __ldg(G + (size_t)((row0 + (uint32_t)s2 * (uint32_t)F + tq) * (uint32_t)ldg + gcol));
         }
@@ -768,8 +799,9 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS * G
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy (async proxy) reads
       named_bar_sync(bar2, 256);
       if (warp == 0 && lane < LSTM_CL) {
-        mbar_arrive_expect_tx(&h_bar[nxt * LSTM_CL + lane], TC_BLK);  // lane s arms the local barrier of source CTA s
-        bulk_s2cluster(dst_h + (uint32_t)(nxt * LSTM_CL * TC_BLK), smem_u32(stg), TC_BLK, dst_bar + (uint32_t)(nxt * LSTM_CL * sizeof(uint64_t)));
+        const uint32_t xbytes = (dbg & 1) ? TC_BLKP : TC_BLK;
+        mbar_arrive_expect_tx(&h_bar[nxt * LSTM_CL + lane], xbytes);  // lane s arms the local barrier of source CTA s
+        bulk_s2cluster(dst_h + (uint32_t)(nxt * LSTM_CL * TC_BLK), smem_u32(stg), xbytes, dst_bar + (uint32_t)(nxt * LSTM_CL * sizeof(uint64_t)));
       }
       load_g(step + 1);  // next step's input projections: in flight during the exchange, never in front of the proxy fence
 #pragma unroll
@@ -797,6 +829,11 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(TC_THREADS * G
   }
 }
 
+static int tc_debug_flags() {  // timing experiments (wrong results on purpose): see `dbg` in the kernel
+  static const int f = [] { const char* e = getenv("RFX_LSTM_TC_DEBUG"); return e ? (atoi(e) & 0xff) << 8 : 0; }();
+  return f;
+}
+
 // two 16-slot groups per CTA: one cluster of 8 SMs per direction serves 32 slots, like <32>, with the groups overlapping each other
 static int launch_tc_dual(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo, int ldhs, int B,
                           int F, int slots, cudaStream_t stream) {
@@ -808,7 +845,7 @@ static int launch_tc_dual(const float* G, int ldg, const float* Whh, float* Hout
   RFX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nb = (slots > 0 && slots < 2 * N) ? slots : 2 * N;
   dim3 grid(LSTM_CL, ceil_div(B, nb), 2);
-  kern<<<grid, 2 * TC_THREADS, smem, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb, get_matmul_precision() == 1 ? 1 : 0);
+  kern<<<grid, 2 * TC_THREADS, smem, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb, (get_matmul_precision() == 1 ? 1 : 0) | tc_debug_flags());
   RFX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -822,7 +859,7 @@ static int launch_tc_n(const float* G, int ldg, const float* Whh, float* Hout, i
   RFX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nb = (slots > 0 && slots < N) ? slots : N;
   dim3 grid(LSTM_CL, ceil_div(B, nb), 2);
-  kern<<<grid, TC_THREADS, smem, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb, get_matmul_precision() == 1 ? 1 : 0);
+  kern<<<grid, TC_THREADS, smem, stream>>>(G, ldg, Whh, Hout, ldh, Hhi, Hlo, ldhs, B, F, nb, (get_matmul_precision() == 1 ? 1 : 0) | tc_debug_flags());
   RFX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
