@@ -166,6 +166,28 @@ int rfx_umx_stage_times(rfx_umx_t* h, float* ms, int capacity, int* n_out);
 /* Debug tap: copy the ratio mask (what = 3; M x ldm fp32) of the last call into dst; row stride via *ld. */
 int rfx_umx_debug_tap(rfx_umx_t* h, int what, const void* workspace, int B, int T, float* dst, int* ld, void* stream);
 
+/* Training (row L5 for Open-Unmix): the reference's Lightning step runs `OpenUnmixModel.forward` (remfx/models.py:294-301) in
+ * TRAINING mode and calls loss.backward() on its output (remfx/models.py:217-221):
+ *   rfx_umx_forward_train  one pass of the network with BatchNorm1d batch statistics (umx/openunmix/model.py:135,151,157) and
+ *                          inter-layer LSTM dropout (model.py:62-69), every pre-BatchNorm activation kept in `workspace`.
+ *        drop_masks   NULL (no dropout) or (nb_layers - 1, B * frames, hidden) fp32 inverted-dropout masks (0 or 1 / (1 - p)),
+ *                     drawn by the caller -- no reference RNG stream can be matched, and the parity tests inject theirs;
+ *        pow_pass     1 = the reference's extra pass `Y = self.model(spectrogram(x))` (remfx/models.py:296-297): the network
+ *                     input is ((|STFT| + 1e-8)^alpha + input_mean) * input_scale, the pass stops after the third BatchNorm
+ *                     (`out` may be NULL) and only bn_stats_out matters; 0 = the separator pass (|STFT| input, mask, iSTFT -> out);
+ *        bn_stats_out NULL or 2 * (hidden + hidden + bins) floats: [mean1, var1, mean2, var2, mean3, var3], biased batch
+ *                     variances, for the caller's running_mean / running_var update (torch: momentum 0.1, unbiased variance).
+ *   rfx_umx_backward       given dout = dLoss / dout (B, T): dLoss / dparameter for every state_dict key in keys[] / grads[] (device
+ *                          fp32 buffers of the parameter's size, overwritten).  Must follow a pow_pass = 0 forward_train with the
+ *                          same shape and workspace pointer, no rfx_umx_finalize in between.  No gradient is produced for x (the
+ *                          reference feeds the network a detached spectrogram, model.py:267).
+ * workspace: rfx_umx_train_workspace_bytes(h, B, T) bytes, 256-byte aligned.  Any T > n_fft / 2 with T % 4 == 0. */
+size_t rfx_umx_train_workspace_bytes(const rfx_umx_t* h, int B, int T);
+int rfx_umx_forward_train(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes,
+                          const float* drop_masks, int pow_pass, float alpha, float* bn_stats_out, void* stream);
+int rfx_umx_backward(rfx_umx_t* h, const float* x, const float* dout, int B, int T, const char* const* keys, float* const* grads,
+                     int nkeys, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * T1-T3  TCN effect-removal model
  *   replaces remfx/models.py:370-390 (TCNModel.forward / sample) = remfx/tcn.py:126-130 (TCN.forward):

@@ -12,6 +12,7 @@ enum StftMode {
   STFT_POWER = 3,      // A = |Z|^2                                         (MelSpectrogram power=2)
   STFT_MAG_CLAMP = 4,  // A = sqrt(max(|Z|^2, 1e-8))                        (auraloss STFT magnitude)
   STFT_MAG_POW = 5,    // A = (|Z| + 1e-8)^alpha                            (remfx.utils.spectrogram)
+  STFT_UMX_POW = 6,    // A = ((|Z| + 1e-8)^alpha + in_mean[k]) * in_scale[k]  (the reference's training-mode pass of the network on spectrogram(x))
 };
 
 struct StftParams {

@@ -99,6 +99,7 @@ __global__ void __launch_bounds__((1 << LOG2NC) / 4) stft_kernel(StftParams p, i
           case STFT_MAG: a = sqrtf(pw); break;
           case STFT_POWER: a = pw; break;
           case STFT_MAG_CLAMP: a = sqrtf(fmaxf(pw, 1e-8f)); break;
+          case STFT_UMX_POW: a = (powf(sqrtf(pw) + 1e-8f, p.alpha) + p.in_mean[k]) * p.in_scale[k]; break;
           default: a = powf(sqrtf(pw) + 1e-8f, p.alpha); break;  // STFT_MAG_POW
         }
         if (p.A) p.A[m * p.lda + k] = a;
@@ -127,6 +128,7 @@ __device__ __forceinline__ float stft_mag_of(float pw, float in_mean, float in_s
   if (MODE == STFT_MAG) return sqrtf(pw);
   if (MODE == STFT_POWER) return pw;
   if (MODE == STFT_MAG_CLAMP) return sqrtf(fmaxf(pw, 1e-8f));
+  if (MODE == STFT_UMX_POW) return (powf(sqrtf(pw) + 1e-8f, alpha) + in_mean) * in_scale;
   return powf(sqrtf(pw) + 1e-8f, alpha);  // STFT_MAG_POW
 }
 
@@ -176,7 +178,8 @@ __global__ void __launch_bounds__(256, 4) stft2048_kernel(StftParams p, int grou
         if (Zrow) Zrow[k] = X;
         if (MODE != STFT_COMPLEX) {
           const float pw = X.x * X.x + X.y * X.y;
-          const float a = stft_mag_of<MODE>(pw, MODE == STFT_UMX_MAG ? p.in_mean[k] : 0.f, MODE == STFT_UMX_MAG ? p.in_scale[k] : 1.f, p.alpha);
+          constexpr bool AFF = MODE == STFT_UMX_MAG || MODE == STFT_UMX_POW;
+          const float a = stft_mag_of<MODE>(pw, AFF ? p.in_mean[k] : 0.f, AFF ? p.in_scale[k] : 1.f, p.alpha);
           if (Arow) Arow[k] = a;
           if (Hrow) {  // split-bf16 copy for the tensor-core layer that consumes it
             __nv_bfloat16 h, l;
@@ -211,7 +214,7 @@ __device__ __forceinline__ void stft_emit_bin(const StftParams& p, int k, float2
   if (MODE != STFT_COMPLEX) {
     const float pw = X.x * X.x + X.y * X.y;
     float mean = 0.f, scl = 1.f;
-    if (MODE == STFT_UMX_MAG) {
+    if (MODE == STFT_UMX_MAG || MODE == STFT_UMX_POW) {
       if (p.in_ms) {
         const float2 ms = __ldg(p.in_ms + k);
         mean = ms.x; scl = ms.y;
@@ -327,6 +330,7 @@ static Stft2048TmaFn stft2048_tma_fn(int mode) {
     case STFT_MAG: return stft2048_tma_kernel<STFT_MAG>;
     case STFT_POWER: return stft2048_tma_kernel<STFT_POWER>;
     case STFT_MAG_CLAMP: return stft2048_tma_kernel<STFT_MAG_CLAMP>;
+    case STFT_UMX_POW: return stft2048_tma_kernel<STFT_UMX_POW>;
     default: return stft2048_tma_kernel<STFT_MAG_POW>;
   }
 }
@@ -375,6 +379,7 @@ static Stft2048Fn stft2048_fn(int mode) {
     case STFT_MAG: return stft2048_kernel<STFT_MAG>;
     case STFT_POWER: return stft2048_kernel<STFT_POWER>;
     case STFT_MAG_CLAMP: return stft2048_kernel<STFT_MAG_CLAMP>;
+    case STFT_UMX_POW: return stft2048_kernel<STFT_UMX_POW>;
     default: return stft2048_kernel<STFT_MAG_POW>;
   }
 }

@@ -128,6 +128,7 @@ rfx_umx::~rfx_umx() {
     for (auto& b : wih_cat) b.release();
     for (auto& b : whh_cat) b.release();
     for (auto& b : packed_store) b.release();
+    for (auto& b : train_store) b.release();
 }
 
 namespace rfx {
@@ -291,6 +292,8 @@ int rfx_umx_finalize(rfx_umx_t* h, void* stream) {
       return rc;
   }
   h->finalized = true;
+  h->train_ready = false;  // the backward's transposed packs follow the new weights (rebuilt by the next forward_train)
+  h->tape_ws = nullptr;
   return 0;
 }
 
@@ -464,7 +467,6 @@ int umx_check_call(rfx_umx_t* h, const void* x, int B, int T, const void* out, c
   RFX_REQUIRE(h && x && out && workspace, "null argument");
   RFX_REQUIRE(h->finalized, "rfx_umx_finalize has not been called since the last parameter load");
   RFX_REQUIRE(B > 0 && T > h->cfg.n_fft / 2, "need B > 0 and T > n_fft/2 (reflect padding)");
-  RFX_REQUIRE(T % h->cfg.hop == 0, "T must be a multiple of the hop length");
   RFX_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
   return 0;
 }

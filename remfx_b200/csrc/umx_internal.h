@@ -40,6 +40,15 @@ struct rfx_umx {
   rfx::SplitW fc1p, fc2p, fc3p;
   std::vector<rfx::SplitW> wihp;
   bool finalized = false;
+  // training path (umx_train.cu): packs of the backward GEMMs, built lazily after a finalize
+  bool train_ready = false;
+  std::vector<rfx::DevBuf> train_store;
+  std::vector<rfx::SplitW> whhp;   // [2 L] W_hh per (layer, direction) as forward packs (gate recompute of the backward)
+  std::vector<rfx::SplitW> wih_t;  // [L] transposed packs of [W_ih ; W_ih_reverse] (input gradient of a layer)
+  rfx::SplitW fc1_t, fc2_t, fc3_t;
+  int tape_B = 0, tape_T = 0;      // shape / workspace / dropout flag of the forward_train a backward may follow
+  const void* tape_ws = nullptr;
+  const float* tape_masks = nullptr;
   // optional per-stage timing (cudaEvents recorded on the caller's stream between the launches)
   bool profiling = false;
   std::vector<cudaEvent_t> events;

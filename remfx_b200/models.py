@@ -219,14 +219,56 @@ class OpenUnmixModel(nn.Module):
         from .losses import remfx_loss_with_terms
 
         x, target = batch
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
-            # the reference trains this wrapper (dead pass + BatchNorm batch statistics + LSTM dropout 0.4 under autograd,
-            # remfx/models.py:294-301); only the eval-mode forward is built here -- fail here, not at loss.backward()
-            raise NotImplementedError("remfx_b200.OpenUnmixModel: training-mode forward / backward kernels are not built "
-                                      "(TCNModel and DemucsModel train); call .eval() or run under torch.no_grad()")
-        sep_out = self.sample(x)
+        if self.training:
+            # training mode (remfx/models.py:294-301 under Lightning's training_step): BatchNorm batch statistics, LSTM dropout,
+            # the extra statistics-only pass on spectrogram(x), and a differentiable output
+            sep_out = self._forward_train(x)
+        else:
+            sep_out = self.sample(x)
         loss, self.last_loss_terms = remfx_loss_with_terms(sep_out, target)
         return loss, sep_out
+
+    # ------------------------------------------------------------------ training mode
+    def _dropout_masks(self, M: int, device) -> Optional[Tensor]:
+        """Inverted-dropout masks of the L - 1 inter-layer dropouts (nn.LSTM(dropout=0.4), umx/openunmix/model.py:62-69), drawn from
+        torch's generator; (L - 1, M, hidden) fp32 with entries 0 or 1 / (1 - p).  None when p == 0."""
+        p = float(self.model.lstm.dropout)
+        L = self.model.nb_layers
+        if p <= 0.0 or L < 2:
+            return None
+        keep = torch.rand(L - 1, M, self.model.hidden_size, device=device) >= p
+        return keep.to(torch.float32) / (1.0 - p)
+
+    def _forward_train(self, x: Tensor) -> Tensor:
+        if x.dim() != 3 or x.shape[1] != 1:
+            raise ValueError(f"expected input of shape (batch, 1, time), got {tuple(x.shape)}")
+        _lib.require_device(x)
+        if x.dtype != torch.float32:
+            raise ValueError("expected float32 audio")
+        x = x.contiguous()
+        names = [k for k, v in self.model.named_parameters()]
+        params = [v for k, v in self.model.named_parameters()]
+        M = x.shape[0] * (x.shape[2] // self.hop_length + 1)
+        forced = self.__dict__.get("_forced_masks")  # tests inject (dead-pass masks, real-pass masks)
+        masks_dead, masks_real = forced if forced is not None else (self._dropout_masks(M, x.device), self._dropout_masks(M, x.device))
+        return _UmxTrainFn.apply(self, names, x, masks_dead, masks_real, *params)
+
+    def _update_running_stats(self, stats: Tensor, M: int) -> None:
+        """torch.nn.BatchNorm1d's training-mode bookkeeping from one pass's batch statistics ([mean1, var1, mean2, var2, mean3,
+        var3], biased variances): running = (1 - momentum) running + momentum batch, the variance unbiased (M / (M - 1))."""
+        o = 0
+        unb = float(M) / float(max(M - 1, 1))
+        with torch.no_grad():
+            for bn in (self.model.bn1, self.model.bn2, self.model.bn3):
+                n = bn.num_features
+                mean, var = stats[o:o + n], stats[o + n:o + 2 * n]
+                o += 2 * n
+                if not bn.track_running_stats or bn.running_mean is None:
+                    continue
+                bn.num_batches_tracked += 1
+                mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                bn.running_mean.mul_(1.0 - mom).add_(mean, alpha=mom)
+                bn.running_var.mul_(1.0 - mom).add_(var * unb, alpha=mom)
 
     def launches_per_call(self) -> int:
         return 5 + 2 * self.model.nb_layers
@@ -234,6 +276,66 @@ class OpenUnmixModel(nn.Module):
     def pipeline(self, device="cuda:0") -> "UmxPipeline":
         """Throughput form of `sample` for a stream of equally shaped batches (see UmxPipeline)."""
         return UmxPipeline(self, device)
+
+
+class _UmxTrainFn(torch.autograd.Function):
+    """Open-Unmix training-mode forward + hand-written backward (rfx_umx_forward_train / rfx_umx_backward).  The forward runs the
+    reference's two passes: the statistics-only pass on spectrogram(x) (`Y = self.model(X)`, remfx/models.py:296-297 -- its output
+    is discarded there too) and the separator pass the loss sees; the BatchNorm running statistics move once per pass, as in the
+    reference.  Gradients go to the network's parameters only (the reference detaches the spectrogram it feeds the network)."""
+
+    @staticmethod
+    def forward(ctx, owner: "OpenUnmixModel", names, x: Tensor, masks_dead, masks_real, *params: Tensor):
+        B, _, T = x.shape
+        L = _lib.lib()
+        hid, bins = owner.model.hidden_size, owner.num_bins
+        with torch.cuda.device(x.device):
+            h = owner._sync(x.device)
+            need = L.rfx_umx_train_workspace_bytes(h, B, T)
+            if need == 0:
+                raise ValueError(f"unsupported input size (B={B}, T={T})")
+            ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            out = torch.empty_like(x)
+            M = B * (T // owner.hop_length + 1)
+            for m in (masks_dead, masks_real):
+                if m is not None and (m.dtype != torch.float32 or not m.is_contiguous() or m.numel() != (owner.model.nb_layers - 1) * M * hid
+                                      or m.device != x.device):
+                    raise ValueError("dropout masks must be contiguous float32 CUDA tensors of shape (layers - 1, B * frames, hidden)")
+            stats = torch.empty(2, 2 * (hid + hid + bins), dtype=torch.float32, device=x.device)
+            stream = _lib.cur_stream()
+            rc = L.rfx_umx_forward_train(h, x.data_ptr(), B, T, None, ws.data_ptr(), ws.numel(),
+                                         masks_dead.data_ptr() if masks_dead is not None else None, 1, float(owner.alpha),
+                                         stats[0].data_ptr(), stream)
+            _lib.check(rc, "rfx_umx_forward_train (statistics pass)")
+            rc = L.rfx_umx_forward_train(h, x.data_ptr(), B, T, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         masks_real.data_ptr() if masks_real is not None else None, 0, float(owner.alpha),
+                                         stats[1].data_ptr(), stream)
+            _lib.check(rc, "rfx_umx_forward_train")
+        owner._update_running_stats(stats[0], M)
+        owner._update_running_stats(stats[1], M)
+        ctx.owner, ctx.names = owner, list(names)
+        ctx.masks = masks_real  # kept alive: the backward reads them through the pointer the forward recorded
+        ctx.save_for_backward(x, ws, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        x, ws, *params = ctx.saved_tensors
+        owner, names = ctx.owner, ctx.names
+        B, _, T = x.shape
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            # no _sync here: the running statistics moved after the forward, which would re-upload the parameters and drop the
+            # tape; the handle still holds the weights the forward used
+            h = owner._handle
+            grads = [torch.empty_like(p, memory_format=torch.contiguous_format) for p in params]
+            n = len(names)
+            keys = (C.c_char_p * n)(*[k.encode() for k in names])
+            ptrs = (C.c_void_p * n)(*[g.data_ptr() for g in grads])
+            d = dout.detach().to(torch.float32).contiguous()
+            rc = L.rfx_umx_backward(h, x.data_ptr(), d.data_ptr(), B, T, keys, ptrs, n, ws.data_ptr(), ws.numel(), _lib.cur_stream())
+            _lib.check(rc, "rfx_umx_backward")
+        return (None, None, None, None, None, *[g if p.requires_grad else None for g, p in zip(grads, params)])
 
 
 class UmxPipeline:

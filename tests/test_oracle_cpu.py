@@ -278,3 +278,45 @@ def test_chain_oracle_matches_live_reference_use_all():
     rloss, rout, _, _ = reference_chain(refshim.ref_modules(), x, y, 60, use_all=True)
     loss, out, _ = _oracle_chain(x, y, 60, use_all=True)
     assert relrms(out, rout) < 1e-5 and abs(float(loss) - float(rloss)) < 1e-5 * abs(float(rloss))
+
+
+@pytest.mark.skipif(not refshim.available(), reason="/root/reference not present (GPU box)")
+def test_umx_train_oracle_matches_reference():
+    """oracle/umx_train.py against the UNCHANGED remfx.models.OpenUnmixModel in training mode (remfx/models.py:294-301): loss, output,
+    every parameter gradient and the BatchNorm running statistics after one step (they move twice: the pass on spectrogram(x), then
+    the separator pass).  The reference's LSTM dropout is set to 0 on the instance (no RNG stream can be shared); the masked form of
+    the oracle is checked against itself below."""
+    from oracle import umx_train as outr
+
+    R = refshim.ref_modules()
+    sd = weights.umx_state(5)
+    m = R.models.OpenUnmixModel(n_fft=2048, hop_length=512, n_channels=1, alpha=0.3, sample_rate=48000)
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    m.model.lstm.dropout = 0.0
+    x, t = weights.synth_audio(61, 2, 8192), weights.synth_audio(62, 2, 8192)
+    loss, out = m((x, t))
+    loss.backward()
+    oloss_, oout, grads, stats = outr.train_grads((x, t), sd, None, None, dtype=torch.float64)
+    assert abs(float(loss.detach()) - float(oloss_)) < 2e-5 * abs(float(oloss_))
+    assert relrms(oout, out.detach()) < 2e-5
+    for k, p in m.model.named_parameters():
+        assert p.grad is not None, k
+        if k == "input_mean":  # exactly zero: a constant added to every row of fc1's input is removed by bn1's batch mean
+            assert float(p.grad.norm()) < 1e-5 * float(m.model.input_scale.grad.norm())
+            assert float(grads[k].norm()) < 1e-9 * float(grads["input_scale"].norm())
+            continue
+        assert relrms(grads[k], p.grad) < 2e-3, (k, relrms(grads[k], p.grad))  # the reference runs in fp32, the oracle here in fp64
+    for bn in ("bn1", "bn2", "bn3"):
+        mod = getattr(m.model, bn)
+        assert int(mod.num_batches_tracked) == 2
+        assert relrms(stats[bn + ".running_mean"], mod.running_mean) < 1e-5, bn
+        assert relrms(stats[bn + ".running_var"], mod.running_var) < 1e-5, bn
+    # masks: an all-ones mask equals no mask; a real mask changes the loss
+    ones = torch.ones(2, 2 * 17, 512)
+    l1, _, _, _ = outr.train_grads((x, t), sd, ones, ones, dtype=torch.float64)
+    assert abs(float(l1) - float(oloss_)) < 1e-9 * abs(float(oloss_))
+    g = torch.Generator().manual_seed(0)
+    msk = (torch.rand(2, 2 * 17, 512, generator=g) >= 0.4).float() / 0.6
+    l2, _, _, _ = outr.train_grads((x, t), sd, msk, msk, dtype=torch.float64)
+    assert abs(float(l2) - float(oloss_)) > 1e-6 * abs(float(oloss_))
