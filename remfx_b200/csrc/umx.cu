@@ -129,6 +129,7 @@ rfx_umx::~rfx_umx() {
     for (auto& b : whh_cat) b.release();
     for (auto& b : packed_store) b.release();
     for (auto& b : train_store) b.release();
+    train_tmp.release();
 }
 
 namespace rfx {
@@ -252,15 +253,19 @@ int rfx_umx_finalize(rfx_umx_t* h, void* stream) {
   if (h->in_ms.alloc((size_t)2 * bins)) return 1;
   RFX_CHECK_CUDA(cudaMemcpy2DAsync(h->in_ms.p, 8, P(h, "input_mean"), 4, 4, bins, cudaMemcpyDeviceToDevice, s));
   RFX_CHECK_CUDA(cudaMemcpy2DAsync(h->in_ms.p + 1, 8, P(h, "input_scale"), 4, 4, bins, cudaMemcpyDeviceToDevice, s));
-  for (auto& b : h->lstm_bias) b.release();
-  for (auto& b : h->wih_cat) b.release();
-  for (auto& b : h->whh_cat) b.release();
-  for (auto& b : h->packed_store) b.release();
-  h->lstm_bias.assign(L, DevBuf());
-  h->wih_cat.assign(L, DevBuf());
-  h->whh_cat.assign(L, DevBuf());
+  // derived buffers keep their sizes from one finalize to the next (a training loop finalizes after every optimiser step): they are
+  // allocated once and re-filled in place, in stream order
+  if ((int)h->lstm_bias.size() != L) {
+    for (auto& b : h->lstm_bias) b.release();
+    for (auto& b : h->wih_cat) b.release();
+    for (auto& b : h->whh_cat) b.release();
+    for (auto& b : h->packed_store) b.release();
+    h->lstm_bias.assign(L, DevBuf());
+    h->wih_cat.assign(L, DevBuf());
+    h->whh_cat.assign(L, DevBuf());
+    h->packed_store.assign(L + 3, DevBuf());
+  }
   h->wihp.assign(L, SplitW());
-  h->packed_store.assign(L + 3, DevBuf());
   for (int l = 0; l < L; ++l) {
     if (h->lstm_bias[l].alloc(8 * H) || h->wih_cat[l].alloc((size_t)8 * H * hid) || h->whh_cat[l].alloc((size_t)8 * H * H)) return 1;
     for (int d = 0; d < 2; ++d) {

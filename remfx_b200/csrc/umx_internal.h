@@ -15,6 +15,8 @@ struct DevBuf {
   float* p = nullptr;
   size_t n = 0;
   int alloc(size_t count) {
+    if (p && n == count) return 0;  // same size: keep the buffer (every user overwrites it completely; a training loop re-finalizes
+                                    // after each optimiser step and cudaFree / cudaMalloc would synchronise the device every time)
     release();
     RFX_CHECK_CUDA(cudaMalloc(&p, count * sizeof(float)));
     n = count;
@@ -43,6 +45,7 @@ struct rfx_umx {
   // training path (umx_train.cu): packs of the backward GEMMs, built lazily after a finalize
   bool train_ready = false;
   std::vector<rfx::DevBuf> train_store;
+  rfx::DevBuf train_tmp;           // transposition scratch of the packs
   std::vector<rfx::SplitW> whhp;   // [2 L] W_hh per (layer, direction) as forward packs (gate recompute of the backward)
   std::vector<rfx::SplitW> wih_t;  // [L] transposed packs of [W_ih ; W_ih_reverse] (input gradient of a layer)
   rfx::SplitW fc1_t, fc2_t, fc3_t;

@@ -303,40 +303,38 @@ int bn_stats(const float* X, long long rows, int ld, int N, double* acc, float* 
 int train_prepare(rfx_umx* h, cudaStream_t s) {
   if (h->train_ready) return 0;
   const int hid = h->cfg.hidden, H = h->H, bins = h->bins, L = h->cfg.nb_layers;
-  for (auto& b : h->train_store) b.release();
-  h->train_store.clear();
-  h->train_store.reserve(2 * L + L + 4);
+  // the backing buffers keep their sizes from one finalize to the next: allocate once, re-pack in place
+  const size_t n_store = (size_t)2 * L + L + 3;
+  if (h->train_store.size() != n_store) {
+    for (auto& b : h->train_store) b.release();
+    h->train_store.assign(n_store, DevBuf());
+  }
+  size_t next = 0;
   h->whhp.assign(2 * L, SplitW());
   h->wih_t.assign(L, SplitW());
   int rc;
   for (int l = 0; l < L; ++l)
     for (int d = 0; d < 2; ++d) {
       const int BN = g2_choose_bn(4 * H);
-      h->train_store.emplace_back();
-      DevBuf& st = h->train_store.back();
+      DevBuf& st = h->train_store[next++];
       if (st.alloc(split_weight_elems(4 * H, H, BN))) return 1;
       if ((rc = pack_split_weights(h->whh_cat[l].p + (size_t)d * 4 * H * H, H, 4 * H, H, BN, reinterpret_cast<__nv_bfloat16*>(st.p), &h->whhp[2 * l + d], s)))
         return rc;
     }
-  DevBuf tmp;
+  DevBuf& tmp = h->train_tmp;
   const size_t tmp_n = std::max({(size_t)hid * (ceil_div(8 * H, 64) * 64), (size_t)hid * (ceil_div(bins, 64) * 64), (size_t)2 * hid * (ceil_div(hid, 64) * 64),
                                  (size_t)bins * (ceil_div(hid, 64) * 64)});
   if (tmp.alloc(tmp_n)) return 1;
-  auto tpack = [&](const float* W, int N, int K, SplitW* out) -> int {
-    h->train_store.emplace_back();
-    DevBuf& st = h->train_store.back();
+  auto tpack = [&](const float* W, int N, int K, SplitW* out) -> int {  // stream-ordered: the shared scratch is reused pack after pack
+    DevBuf& st = h->train_store[next++];
     if (st.alloc(bw::transposed_pack_floats(N, K))) return 1;
     return bw::pack_transposed(W, N, K, tmp.p, st.p, out, s);
   };
   for (int l = 0; l < L; ++l)
-    if ((rc = tpack(h->wih_cat[l].p, 8 * H, hid, &h->wih_t[l]))) { tmp.release(); return rc; }
+    if ((rc = tpack(h->wih_cat[l].p, 8 * H, hid, &h->wih_t[l]))) return rc;
   if ((rc = tpack(umx_param(h, "fc1.weight"), hid, bins, &h->fc1_t)) || (rc = tpack(umx_param(h, "fc2.weight"), hid, 2 * hid, &h->fc2_t)) ||
-      (rc = tpack(umx_param(h, "fc3.weight"), bins, hid, &h->fc3_t))) {
-    tmp.release();
+      (rc = tpack(umx_param(h, "fc3.weight"), bins, hid, &h->fc3_t)))
     return rc;
-  }
-  RFX_CHECK_CUDA(cudaStreamSynchronize(s));  // tmp is released below
-  tmp.release();
   h->train_ready = true;
   return 0;
 }
