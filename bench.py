@@ -588,6 +588,26 @@ def run_ours(args):
                        "tensor_frac": step_flops / (ms_step / 1e3) / 1e12 / tpeak},
         "serial_stage_ms": {k: round(v, 4) for k, v in stage_acc.items()},
     }
+    # every kernel family of the step against ITS roofline, from the live serial stage times (one blocking `sample` call, 148 SMs):
+    # dense layers on the tensor pipe (fp32-equivalent FLOPs; the bf16x3 split issues 3x as many), STFT / iSTFT on HBM bytes
+    bins, hid = 1025, 512
+    lda1, ldm, ldz = (bins + 7) // 8 * 8, (bins + 3) // 4 * 4, (bins + 1) // 2 * 2
+    fam = []
+    gemm_flops = {"fc1": 2.0 * M * hid * bins, "fc2": 2.0 * M * hid * 2 * hid, "fc3": 2.0 * M * bins * hid}
+    for l in range(3):
+        gemm_flops[f"wih{l}"] = 2.0 * M * 8 * H * hid
+    for k, fl_ in gemm_flops.items():
+        if k in stage_acc and stage_acc[k] > 0:
+            tf = fl_ / (stage_acc[k] / 1e3) / 1e12
+            fam.append({"kernel": f"gemm2_kernel ({k})", "bound": "tensor", "ms": round(stage_acc[k], 4), "achieved": tf, "unit": "TFLOP/s fp32-equivalent",
+                        "peak": tpeak, "frac": tf / tpeak, "frac_counting_the_3_bf16_passes": 3 * tf / tpeak})
+    byt = {"stft": BATCH * T * 4 + M * ldz * 8 + M * lda1 * 4, "istft": M * ldz * 8 + M * ldm * 4 + BATCH * T * 4}
+    for k, b_ in byt.items():
+        if k in stage_acc and stage_acc[k] > 0:
+            gb = b_ / (stage_acc[k] / 1e3) / 1e9
+            fam.append({"kernel": f"{k}2048_tma_kernel", "bound": "hbm", "ms": round(stage_acc[k], 4), "achieved": gb, "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                        "frac": gb / peaks["hbm_gbs"], "algorithmic_bytes": b_})
+    roofline["kernel_families_serial"] = fam
 
     line = {
         "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
