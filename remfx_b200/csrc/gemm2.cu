@@ -715,6 +715,13 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   RFX_REQUIRE(p.stages >= 2, "gemm2: operand stages do not fit in shared memory");
   if ((rc = make_split_map(&mapW, pr.W.hi, pr.W.Kpad, pr.W.Npad, 1, 1, pr.W.Kpad, 0, 0, (long long)pr.W.Npad * pr.W.Kpad, p.n_box, 1))) return rc;
   const int total = p.batch * p.m_tiles * p.n_tiles;
+  {  // RFX_G2_TRACE=1: one line per launch (shape, tiling, shared-memory plan) to match against an ncu launch list
+    static const bool trace = [] { const char* e = getenv("RFX_G2_TRACE"); return e && atoi(e) != 0; }();
+    if (trace)
+      fprintf(stderr, "g2trace batch=%d Y=%d X=%d N=%d Ktap=%d taps=%d BN=%d xt=%d tiles=%d n_tiles=%d resident=%d stages=%d act=%d gn=%d fp32out=%d split=%d\n",
+              pr.batch, Yo, pr.M, pr.N, pr.Ktap, pr.taps, BN, xt, total, p.n_tiles, resident ? 1 : 0, p.stages, pr.epi.act, pr.gn_acc ? 1 : 0,
+              pr.Cf ? 1 : 0, pr.Chi ? 1 : 0);
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -190,8 +190,20 @@ struct Runner {
     pr.A.batch_stride = (long long)in.Y * Xv * Cv; pr.A.plane_stride = (long long)in.plane;
     pr.W = c.w;
     pr.M = Xo; pr.My = Yo; pr.N = Nout; pr.batch = in.B; pr.Ktap = Cv; pr.taps = g.taps;
+    // pixel tile = xt x (128 / xt).  Default: the largest power of two <= Xo; when that pads the X axis by more than 10 % (Xo = 129,
+    // 33, 9: transposed-conv outputs before their crop -> half-empty tiles, the largest single launch of the forward ran at 145 TF/s
+    // instead of ~270) take the widest tile whose padded pixel count is within 3 % of the best
     int xt = 128;
-    while (xt > Xo && xt > 1) xt >>= 1;  // largest power of two <= Xo (pixel tile width), at most 128
+    while (xt > Xo && xt > 1) xt >>= 1;
+    {
+      auto padded = [&](int w) { return (long long)ceil_div(Xo, w) * w * ((long long)ceil_div(Yo, 128 / w) * (128 / w)); };
+      if (padded(xt) * 10 > (long long)Xo * Yo * 11) {
+        long long best = padded(1);
+        for (int w = 2; w <= xt; w <<= 1) best = std::min(best, padded(w));
+        for (int w = xt; w >= 1; w >>= 1)
+          if (padded(w) * 100 <= best * 103) { xt = w; break; }
+      }
+    }
     pr.xt = xt;
     if (dst) { pr.Cf = out.f + dst_col; pr.ldcf = out.C; pr.ldcf_y = (long long)Xo * out.C; pr.bscf = (long long)Yo * Xo * out.C; }
     else if (out_f32) { pr.Cf = out.f; pr.ldcf = Cout_store; pr.ldcf_y = (long long)Xo * Cout_store; pr.bscf = (long long)Yo * Xo * Cout_store; }
