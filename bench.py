@@ -360,7 +360,9 @@ def leg_train(dev, rank, world, barrier, reduce_max, peaks, use_dist):
     barrier()
     med = reduce_max(statistics.median(ts))
     tm = opt.timing_ms()
-    ar = reduce_max(statistics.median([a for a, _ in tm]))
+    ar_local = statistics.median([a for a, _ in tm])
+    ar = reduce_max(ar_local)        # the rank that waited longest: collective + the skew of the ranks' backward passes
+    ar_min = -reduce_max(-ar_local)  # the last rank to arrive: the collective itself
     upd = reduce_max(statistics.median([b for _, b in tm]))
     opt.set_timing(False)
     mod.compute_metrics = True
@@ -382,8 +384,11 @@ def leg_train(dev, rank, world, barrier, reduce_max, peaks, use_dist):
            "scaling": "weak", "ms_per_step": med, "value": world * B * CHUNK_S / (med / 1e3), "unit": "audio-s/s",
            "ms_per_step_with_metric_block": with_metrics,
            "all_reduce": {"collective": "one NCCL SUM all-reduce of the flat fp32 gradient bucket" if use_dist else "none (1 GPU)",
-                          "bytes": grad_bytes, "ms": ar, "ideal_ring_ms_at_900GBs": ideal_ar_ms,
-                          "busbw_GBs": (2.0 * (world - 1) / world * grad_bytes / (ar / 1e3) / 1e9) if (use_dist and ar > 0) else None,
+                          "bytes": grad_bytes, "ms": ar, "ms_last_rank_to_arrive": ar_min, "ideal_ring_ms_at_900GBs": ideal_ar_ms,
+                          "busbw_GBs": (2.0 * (world - 1) / world * grad_bytes / (ar_min / 1e3) / 1e9) if (use_dist and ar_min > 0) else None,
+                          "note": "ms = max over ranks of the time between the all-reduce's launch and its end on that rank's stream: it contains "
+                                  "the wait for the slowest rank's backward (rank skew); ms_last_rank_to_arrive = min over ranks = the collective "
+                                  "itself, which is what busbw is computed from",
                           "overlap_with_backward": False},
            "clip_adamw_ms": upd, "parameters": nparam, "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30,
            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
