@@ -352,7 +352,7 @@ struct BRunner {
     {
       static const bool stepwise = [] { const char* e = getenv("RFX_HD_LSTM_BWD_STEPWISE"); return e && atoi(e) != 0; }();
       const dim3 pg(H / LBP_U, 2, ceil_div(Bs, LBP_B));
-      const size_t psmem = ((size_t)4 * H * LBP_U + (size_t)LBP_B * (4 * H + 4)) * 4;
+      const size_t psmem = ((size_t)4 * H * LBP_U + (size_t)LBP_B * (4 * H + 4) + (size_t)4 * LBP_B * LBP_U) * 4;
       int sms = 148, dev = 0, per_sm = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -755,7 +755,7 @@ int lstm_layer_backward(const float* Gx, int Bs, int T, int H, const __nv_bfloat
   {
     static const bool stepwise = [] { const char* e = getenv("RFX_HD_LSTM_BWD_STEPWISE"); return e && atoi(e) != 0; }();
     const dim3 pg(H / LBP_U, 2, ceil_div(Bs, LBP_B));
-    const size_t psmem = ((size_t)4 * H * LBP_U + (size_t)LBP_B * (4 * H + 4)) * 4;
+    const size_t psmem = ((size_t)4 * H * LBP_U + (size_t)LBP_B * (4 * H + 4) + (size_t)4 * LBP_B * LBP_U) * 4;
     int sms = 148, dev = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
