@@ -72,3 +72,34 @@ def test_label_order_is_the_reference_effect_list():
 
     R = refshim.ref_modules()
     assert ALL_EFFECTS == [e.__name__ for e in R.models.ALL_EFFECTS]                                   # remfx/effects.py:699-705
+
+
+def test_open_unmix_training_mode_host_logic():
+    """Host side of OpenUnmixModel's training mode without a GPU: there is no CPU fallback (CPU tensors raise), the dropout masks have
+    the shape / rate / scaling of nn.LSTM(dropout=0.4), and the running-statistics bookkeeping equals torch.nn.BatchNorm1d's."""
+    from remfx_b200 import _lib
+    from remfx_b200.models import OpenUnmixModel
+
+    m = OpenUnmixModel(n_fft=2048, hop_length=512, n_channels=1, alpha=0.3, sample_rate=48000).train()
+    with pytest.raises(_lib.RfxError):
+        m((torch.zeros(1, 1, 8192), torch.zeros(1, 1, 8192)))
+    torch.manual_seed(0)
+    msk = m._dropout_masks(200, torch.device("cpu"))
+    assert msk.shape == (2, 200, 512) and set(torch.unique(msk).tolist()) <= {0.0, float(torch.tensor(1.0) / torch.tensor(0.6))}
+    assert abs(float((msk > 0).float().mean()) - 0.6) < 0.01
+    m.model.lstm.dropout = 0.0
+    assert m._dropout_masks(200, torch.device("cpu")) is None
+    # running statistics: feed the same batch through torch's BatchNorm1d in training mode twice and through the mirror's update
+    g = torch.Generator().manual_seed(1)
+    rows = 37
+    xs = [torch.randn(rows, n, generator=g) * 2 + 1 for n in (512, 512, 1025)]
+    ref = [torch.nn.BatchNorm1d(n).train() for n in (512, 512, 1025)]
+    stats = torch.cat([torch.cat([x.mean(0), x.var(0, unbiased=False)]) for x in xs])
+    for _ in range(2):
+        for bn, x in zip(ref, xs):
+            bn(x)
+        m._update_running_stats(stats, rows)
+    for bn, mine in zip(ref, (m.model.bn1, m.model.bn2, m.model.bn3)):
+        assert int(mine.num_batches_tracked) == int(bn.num_batches_tracked) == 2
+        assert torch.allclose(mine.running_mean, bn.running_mean, atol=1e-6)
+        assert torch.allclose(mine.running_var, bn.running_var, rtol=1e-5, atol=1e-6)
