@@ -129,7 +129,12 @@ struct rfx_hdemucs {
   const float* st_t = nullptr;
   std::map<const void*, float*> act_grads;  // after a backward: tensor key -> fp32 gradient (for rfx_hdemucs_grad_tap)
   std::map<std::string, const float*> inject;  // debug: tap name -> device gradient to substitute during the backward
+  // the time branch of the forward runs on its own stream beside the frequency branch (hdemucs.cu: run_forward)
+  cudaStream_t s_time = nullptr;
+  cudaEvent_t ev_branch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   ~rfx_hdemucs() {
+    if (s_time) cudaStreamDestroy(s_time);
+    for (auto e : ev_branch) if (e) cudaEventDestroy(e);
     for (auto& kv : params) kv.second.release();
     for (auto& kv : convs) { kv.second.wbuf.release(); kv.second.bias.release(); kv.second.wtbuf.release(); }
     for (auto& kv : whh) kv.second.release();
