@@ -56,6 +56,35 @@ struct BRunner {
   float* bstage = nullptr;  // bias staging [largest Nout]
   float* tmpf = nullptr;    // input-gradient scratch for accumulating GEMM outputs (largest conv input)
   std::set<std::string> injected;
+  // Parameter gradients (weight-gradient contraction, bias column sums, scatters) are off the critical path of the reverse replay --
+  // only the INPUT gradient feeds the next op -- so they run on a side stream (the handle's second stream) behind an event that
+  // marks "this op's output gradient is complete"; the shared staging buffers are only ever touched on that stream, which keeps
+  // their reuse stream-ordered.  The caller's stream joins at the end of the replay.  RFX_HD_OVERLAP=0 keeps one stream.
+  cudaStream_t s_side = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_join = nullptr;
+  void side_setup() {
+    static const bool on = [] { const char* e = getenv("RFX_HD_OVERLAP"); return !(e && atoi(e) == 0); }();
+    if (!on || dry) return;
+    if (!h->s_time && cudaStreamCreateWithFlags(&h->s_time, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); h->s_time = nullptr; return; }
+    for (int i = 0; i < 2; ++i)
+      if (!h->ev_branch[i] && cudaEventCreateWithFlags(&h->ev_branch[i], cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    s_side = h->s_time; ev_ready = h->ev_branch[0]; ev_join = h->ev_branch[1];
+  }
+  struct SideScope {  // while alive, the runner's launches go to the side stream
+    BRunner& r; cudaStream_t keep;
+    explicit SideScope(BRunner& rr) : r(rr), keep(rr.s) {
+      if (r.s_side && !r.dry && !r.rc) {
+        if (cudaEventRecord(r.ev_ready, r.s) != cudaSuccess || cudaStreamWaitEvent(r.s_side, r.ev_ready, 0) != cudaSuccess) r.fail("side-stream hand-over");
+        else r.s = r.s_side;
+      }
+    }
+    ~SideScope() { r.s = keep; }
+  };
+  void side_join() {
+    if (s_side && !dry) {
+      if (cudaEventRecord(ev_join, s_side) != cudaSuccess || cudaStreamWaitEvent(s, ev_join, 0) != cudaSuccess) fail("side-stream join");
+    }
+  }
 
   void* take(size_t bytes) {
     const size_t r = off;
@@ -118,6 +147,7 @@ struct BRunner {
     float* db = pgrad(c.bkey);
     float* db2 = pgrad(c.bkey2);
     if (dry || rc) return;
+    SideScope side(*this);
     if (db) {
       if (cudaMemsetAsync(bstage, 0, (size_t)gs.Nout * 4, s) != cudaSuccess) { fail("memset"); return; }
       const long long rows = (long long)Bn * Y * X;
@@ -455,6 +485,7 @@ struct BRunner {
     stage = reinterpret_cast<float*>(take(max_stage * 4));
     bstage = reinterpret_cast<float*>(take(max_n * 4));
     tmpf = reinterpret_cast<float*>(take(max_in * 4));
+    side_setup();
     if (!dry) {
       bool attr_ok = true;
       attr_ok &= cudaFuncSetAttribute(hd_wgrad_kernel<2, 4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HwCfg<2, 4, 4, 4>::SMEM) == cudaSuccess;
@@ -629,6 +660,7 @@ struct BRunner {
         default: fail("unknown tape op"); break;
       }
     }
+    side_join();
     if (!dry && ok()) {
       h->act_grads.clear();
       for (auto& kv : G)
