@@ -183,6 +183,9 @@ int rfx_umx_debug_tap(rfx_umx_t* h, int what, const void* workspace, int B, int 
  *                          reference feeds the network a detached spectrogram, model.py:267).
  * workspace: rfx_umx_train_workspace_bytes(h, B, T) bytes, 256-byte aligned.  Any T > n_fft / 2 with T % 4 == 0. */
 size_t rfx_umx_train_workspace_bytes(const rfx_umx_t* h, int B, int T);
+/* Builds the backward's weight packs (transposed / per-direction) for the current parameters on `stream`; forward_train does it
+ * implicitly, a caller that runs the two passes of a step on two streams calls it first so that both see finished packs. */
+int rfx_umx_train_prepare(rfx_umx_t* h, void* stream);
 int rfx_umx_forward_train(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes,
                           const float* drop_masks, int pow_pass, float alpha, float* bn_stats_out, void* stream);
 int rfx_umx_backward(rfx_umx_t* h, const float* x, const float* dout, int B, int T, const char* const* keys, float* const* grads,

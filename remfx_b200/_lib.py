@@ -109,6 +109,7 @@ _SIGNATURES = {
     "rfx_hdemucs_set_taps": (C.c_int, [C.c_void_p, C.c_int]),
     "rfx_hdemucs_tap": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int64, C.POINTER(C.c_int), C.c_void_p]),
     "rfx_umx_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "rfx_umx_train_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rfx_umx_forward_train": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_int, _f32p, C.c_void_p, C.c_size_t, _f32p, C.c_int, C.c_float, _f32p,
                                         C.c_void_p]),
     "rfx_umx_backward": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.c_int,

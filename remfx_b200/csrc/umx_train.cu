@@ -361,6 +361,12 @@ size_t rfx_umx_train_workspace_bytes(const rfx_umx_t* h, int B, int T) {
   return train_layout(h, B, T).total;
 }
 
+int rfx_umx_train_prepare(rfx_umx_t* h, void* stream) {
+  RFX_REQUIRE(h, "null handle");
+  RFX_REQUIRE(h->finalized, "rfx_umx_finalize has not been called since the last parameter load");
+  return train_prepare(h, (cudaStream_t)stream);
+}
+
 int rfx_umx_forward_train(rfx_umx_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, const float* drop_masks,
                           int pow_pass, float alpha, float* bn_stats_out, void* stream) {
   int rc;

@@ -302,15 +302,28 @@ class _UmxTrainFn(torch.autograd.Function):
                                       or m.device != x.device):
                     raise ValueError("dropout masks must be contiguous float32 CUDA tensors of shape (layers - 1, B * frames, hidden)")
             stats = torch.empty(2, 2 * (hid + hid + bins), dtype=torch.float32, device=x.device)
-            stream = _lib.cur_stream()
-            rc = L.rfx_umx_forward_train(h, x.data_ptr(), B, T, None, ws.data_ptr(), ws.numel(),
+            # The statistics pass only produces BatchNorm statistics and is independent of the pass the loss sees: it runs on a side
+            # stream in its own workspace, beside the separator pass (whose recurrences leave most of the chip idle), and the two
+            # join before the running statistics are updated -- in the reference's order, statistics pass first.
+            main = torch.cuda.current_stream(x.device)
+            side = owner.__dict__.get("_side_stream")
+            if side is None or side.device != x.device:
+                side = owner.__dict__["_side_stream"] = torch.cuda.Stream(device=x.device)
+            rc = L.rfx_umx_train_prepare(h, main.cuda_stream)  # the backward's weight packs (once per parameter change), on `main`
+            _lib.check(rc, "rfx_umx_train_prepare")
+            ws2 = torch.empty(need, dtype=torch.uint8, device=x.device)
+            side.wait_stream(main)  # x, the masks, the parameter upload and the packs are ready
+            rc = L.rfx_umx_forward_train(h, x.data_ptr(), B, T, None, ws2.data_ptr(), ws2.numel(),
                                          masks_dead.data_ptr() if masks_dead is not None else None, 1, float(owner.alpha),
-                                         stats[0].data_ptr(), stream)
+                                         stats[0].data_ptr(), side.cuda_stream)
             _lib.check(rc, "rfx_umx_forward_train (statistics pass)")
             rc = L.rfx_umx_forward_train(h, x.data_ptr(), B, T, out.data_ptr(), ws.data_ptr(), ws.numel(),
                                          masks_real.data_ptr() if masks_real is not None else None, 0, float(owner.alpha),
-                                         stats[1].data_ptr(), stream)
+                                         stats[1].data_ptr(), main.cuda_stream)
             _lib.check(rc, "rfx_umx_forward_train")
+            main.wait_stream(side)
+            for t_ in (ws2, x, stats) + ((masks_dead,) if masks_dead is not None else ()):
+                t_.record_stream(side)  # the caching allocator must not hand these blocks out before the side stream is done
         owner._update_running_stats(stats[0], M)
         owner._update_running_stats(stats[1], M)
         ctx.owner, ctx.names = owner, list(names)
