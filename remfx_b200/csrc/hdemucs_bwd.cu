@@ -782,8 +782,16 @@ int lstm_layer_backward(const float* Gx, int Bs, int T, int H, const __nv_bfloat
   // 2. cell states
   lstm_cscan_kernel<<<ceil_div(Bs * 2 * H, 256), 256, 0, s>>>(Gx, R, Bs, T, H, cs);
   RFX_CHECK_CUDA(cudaGetLastError());
-  // 3. reverse-time chain: persistent cooperative launch, or one launch per step when that cannot be co-resident
+  // 3. reverse-time chain: H = 256 (Open-Unmix) on the cluster / tensor-core kernel of lstm.cu; else the persistent cooperative
+  //    launch, or one launch per step when that cannot be co-resident
   bool persistent = false;
+  {
+    static const bool mma_on = [] { const char* e = getenv("RFX_LSTM_BWD_MMA"); return !(e && atoi(e) == 0); }();
+    if (mma_on && H == 256) {
+      if ((rc = launch_lstm_bwd_chain_mma(Gx, R, cs, dH, whh_cat, dG, Bs, T, H, s))) return rc;
+      return 0;
+    }
+  }
   {
     static const bool stepwise = [] { const char* e = getenv("RFX_HD_LSTM_BWD_STEPWISE"); return e && atoi(e) != 0; }();
     const dim3 pg(H / LBP_U, 2, ceil_div(Bs, LBP_B));

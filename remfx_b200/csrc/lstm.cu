@@ -437,6 +437,186 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(H / 8 / 4 * 32
   cluster_wait();
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Reverse-time chain of the LSTM backward (BPTT) on the same machinery, H = 256: one 8-CTA cluster per (direction, 8 sequences).
+//   dh_t = dH_t + W_hh^T dG_{t'}   (t' = the step handled before),   gate derivatives -> dG_t,   dc carry.
+// CTA r owns the hidden units [32 r, 32 r + 32) -- it produces dG_t for their 4 x 32 gate rows and needs dh_t for them -- and keeps
+// W_hh^T restricted to ITS OWN gate rows as mma.sync A fragments in registers (M = all 256 units, K = 128 own gate rows: warp w
+// holds units [32 w, 32 w + 32) = 2 m-tiles x 8 k-steps, hi and lo planes = 128 registers, the forward kernel's budget).  The B
+// operand is the CTA's OWN dG_{t'} (split bf16 in shared memory, written by its own threads at the end of the previous step), so
+// nothing has to be gathered: each warp's result is the partial sum over this CTA's gate rows of dh for the units of CTA w, sent
+// there as one 1152-byte DSMEM bulk copy (a reduce-scatter: 8 KB out and in per CTA and step instead of the 32 KB an all-gather of
+// dG would move), summed by the owner (thread = (unit, sequence)), followed by the gate-derivative math in fp32 with the
+// accurate transcendentals of the other backward kernels.  Inputs / outputs are those of hd::lstm_bwd_persist_kernel (Gx, R =
+// W_hh h_prev, cell states, dH -> dG), which it replaces for H = 256: 11 us -> ~1 us per time step.
+// ------------------------------------------------------------------------------------------------------
+constexpr int LBM_BLK = 8 * 36 * 4;  // one partial block: [8 sequences][32 units + 4 pad] fp32
+constexpr int LBM_KP = 136;          // row stride (bf16) of the dG operand: [8 sequences][128 own gate rows + 8 pad]
+__global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(256, 1)
+    lstm_bwd_mma_kernel(const float* __restrict__ Gx, const float* __restrict__ R, const float* __restrict__ cs, const float* __restrict__ dH,
+                        const float* __restrict__ Whh /*[2][4H][H]*/, float* __restrict__ dG, int Bs, int T) {
+  constexpr int H = 256, UPC = 32;
+  extern __shared__ __align__(128) uint8_t lbm_smem[];
+  uint8_t* recv = lbm_smem;                                   // [2][8 sources][LBM_BLK]
+  uint8_t* send = recv + 2 * LSTM_CL * LBM_BLK;               // [2][8 warps][LBM_BLK]
+  __nv_bfloat16* dgs = reinterpret_cast<__nv_bfloat16*>(send + 2 * 8 * LBM_BLK);  // [2 planes][8][LBM_KP]
+  uint64_t* rbar = reinterpret_cast<uint64_t*>(dgs + 2 * 8 * LBM_KP);             // [2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const uint32_t rank = cluster_ctarank();
+  const int dir = blockIdx.y, b0 = blockIdx.z * 8;
+
+  // ---- A fragments: A[m = unit 32 w + 16 mt + row][k] = W_hh[gate row (k / 32) * H + 32 rank + k % 32][unit] ----
+  uint32_t a_hi[2][8][4], a_lo[2][8][4];
+  {
+    const float* W = Whh + (size_t)dir * 4 * H * H;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int row = gid + (q & 1) * 8;                 // a0/a2: gid, a1/a3: gid + 8
+          const int k = 16 * ks + 2 * tig + (q >> 1) * 8;    // a0/a1: 2 tig, a2/a3: 2 tig + 8
+          const int unit = 32 * warp + 16 * mt + row;
+          const size_t g0 = (size_t)((k >> 5) * H + 32 * (int)rank + (k & 31));
+          const float w0 = W[g0 * H + unit], w1 = W[(g0 + 1) * H + unit];  // k and k + 1 are in the same gate (k is even)
+          float r0, r1;
+          a_hi[mt][ks][q] = pack_hi2(w0, w1, r0, r1);
+          a_lo[mt][ks][q] = pack2(r0, r1);
+        }
+  }
+  for (int i = tid; i < 2 * 8 * LBM_KP / 2; i += 256) reinterpret_cast<uint32_t*>(dgs)[i] = 0u;
+  if (tid == 0) {
+    mbar_init(&rbar[0], 1);
+    mbar_init(&rbar[1], 1);
+    mbar_fence_init();
+  }
+  // element role: thread = (unit uu of this CTA, sequence n)
+  const int uu = lane, n = warp;
+  const int u = 32 * (int)rank + uu, b = b0 + n;
+  const bool live = b < Bs;
+  const int G4 = 4 * H;
+  // destination of this warp's partial block: CTA `warp`, slot [source = rank]
+  const uint32_t dst_blk = mapa_u32(smem_u32(recv) + rank * LBM_BLK, (uint32_t)warp);
+  const uint32_t dst_bar = mapa_u32(smem_u32(&rbar[0]), (uint32_t)warp);
+  float dc = 0.0f;
+  __syncthreads();
+  cluster_arrive();
+  cluster_wait();
+
+  // operands of the step, fetched one step ahead
+  float pi = 0.f, pf = 0.f, pg = 0.f, po = 0.f, cc = 0.f, cprev = 0.f, dh0 = 0.f;
+  auto fetch = [&](int k) {
+    pi = pf = pg = po = cc = cprev = dh0 = 0.f;
+    if (live && k < T) {
+      const int t = dir ? k : T - 1 - k;
+      const int tp = dir ? t + 1 : t - 1;
+      const size_t go = ((size_t)b * T + t) * 8 * H + (size_t)dir * G4 + u;
+      const size_t ho = ((size_t)b * T + t) * 2 * H + dir * H + u;
+      pi = Gx[go] + R[go]; pf = Gx[go + H] + R[go + H]; pg = Gx[go + 2 * H] + R[go + 2 * H]; po = Gx[go + 3 * H] + R[go + 3 * H];
+      cc = cs[ho];
+      cprev = (tp >= 0 && tp < T) ? cs[((size_t)b * T + tp) * 2 * H + dir * H + u] : 0.0f;
+      dh0 = dH[ho];
+    }
+  };
+  fetch(0);
+  for (int k = 0; k < T; ++k) {
+    const int buf = k & 1;
+    const int t = dir ? k : T - 1 - k;
+    float dh = dh0;
+    const float xi = pi, xf = pf, xg = pg, xo = po, c = cc, cp = cprev;
+    if (k > 0) {
+      if (tid == 0) mbar_arrive_expect_tx(&rbar[buf], LSTM_CL * LBM_BLK);
+      // ---- partial dh of the units of CTA `warp` from this CTA's gate rows: 2 m-tiles x 8 k-steps x bf16x3 ----
+      float d[2][3][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d[mt][ch][q] = 0.f;
+      const uint8_t* bh = reinterpret_cast<const uint8_t*>(dgs) + gid * (LBM_KP * 2) + tig * 4;
+      const uint8_t* bl = bh + 8 * LBM_KP * 2;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t h0 = *reinterpret_cast<const uint32_t*>(bh + ks * 32), h1 = *reinterpret_cast<const uint32_t*>(bh + ks * 32 + 16);
+        const uint32_t l0 = *reinterpret_cast<const uint32_t*>(bl + ks * 32), l1 = *reinterpret_cast<const uint32_t*>(bl + ks * 32 + 16);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          hmma16816(d[mt][0], a_lo[mt][ks], h0, h1);
+          hmma16816(d[mt][1], a_hi[mt][ks], l0, l1);
+          hmma16816(d[mt][2], a_hi[mt][ks], h0, h1);
+        }
+      }
+      float* blk = reinterpret_cast<float*>(send + (buf * 8 + warp) * LBM_BLK);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float c0 = (d[mt][0][0] + d[mt][1][0]) + d[mt][2][0], c1 = (d[mt][0][1] + d[mt][1][1]) + d[mt][2][1];
+        const float c2 = (d[mt][0][2] + d[mt][1][2]) + d[mt][2][2], c3 = (d[mt][0][3] + d[mt][1][3]) + d[mt][2][3];
+        blk[(2 * tig) * 36 + 16 * mt + gid] = c0;
+        blk[(2 * tig + 1) * 36 + 16 * mt + gid] = c1;
+        blk[(2 * tig) * 36 + 16 * mt + gid + 8] = c2;
+        blk[(2 * tig + 1) * 36 + 16 * mt + gid + 8] = c3;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0)
+        bulk_s2cluster(dst_blk + (uint32_t)(buf * LSTM_CL * LBM_BLK), smem_u32(blk), LBM_BLK, dst_bar + (uint32_t)(buf * sizeof(uint64_t)));
+    }
+    fetch(k + 1);     // next step's operands: in flight during the exchange
+    __syncthreads();  // every warp is done reading dG_{t'} (the element phase below overwrites it)
+    if (k > 0) {
+      mbar_wait(&rbar[buf], ((k - 1) >> 1) & 1);
+      const float* rb = reinterpret_cast<const float*>(recv + buf * LSTM_CL * LBM_BLK) + n * 36 + uu;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int src = 0; src < LSTM_CL; src += 2) {
+        s0 += rb[src * (LBM_BLK / 4)];
+        s1 += rb[(src + 1) * (LBM_BLK / 4)];
+      }
+      dh += s0 + s1;
+    }
+    // ---- gate derivatives (tools/hd_bwd_emul.py: lstm_dir_bwd), as in hd::lstm_bwd_persist_kernel ----
+    float g4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      const float gi = sigmoidf_acc(xi), gf = sigmoidf_acc(xf), gg = tanhf(xg), go_ = sigmoidf_acc(xo);
+      const float tc = tanhf(c);
+      dc += dh * go_ * (1.0f - tc * tc);
+      g4[0] = dc * gg * gi * (1.0f - gi);
+      g4[1] = dc * cp * gf * (1.0f - gf);
+      g4[2] = dc * gi * (1.0f - gg * gg);
+      g4[3] = dh * tc * go_ * (1.0f - go_);
+      dc *= gf;
+      const size_t go = ((size_t)b * T + t) * 8 * H + (size_t)dir * G4 + u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dG[go + (size_t)q * H] = g4[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // this CTA's dG_t as the next step's B operand: [plane][sequence][k = gate * 32 + unit]
+      __nv_bfloat16 hq, lq;
+      split_bf16(g4[q], hq, lq);
+      dgs[n * LBM_KP + q * UPC + uu] = hq;
+      dgs[8 * LBM_KP + n * LBM_KP + q * UPC + uu] = lq;
+    }
+    __syncthreads();
+  }
+  // nobody leaves while a peer may still be writing into its receive buffers (all sends of the last step are consumed above)
+  cluster_arrive();
+  cluster_wait();
+}
+
+int launch_lstm_bwd_chain_mma(const float* Gx, const float* R, const float* cs, const float* dH, const float* Whh, float* dG, int Bs, int T, int H,
+                              cudaStream_t stream) {
+  RFX_REQUIRE(H == 256, "lstm_bwd_mma_kernel: H = 256 only");
+  const size_t smem = (size_t)2 * LSTM_CL * LBM_BLK + (size_t)2 * 8 * LBM_BLK + (size_t)2 * 8 * LBM_KP * 2 + 64;
+  RFX_CHECK_CUDA(cudaFuncSetAttribute(lstm_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(LSTM_CL, 2, ceil_div(Bs, 8));
+  lstm_bwd_mma_kernel<<<grid, 256, smem, stream>>>(Gx, R, cs, dH, Whh, dG, Bs, T);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int H, bool LO_SMEM>
 static size_t lstm_mma_smem() {
   constexpr int UPC = H / LSTM_CL;
