@@ -379,7 +379,11 @@ struct BRunner {
     //    falls back to one launch per step when the grid cannot be co-resident (very large batches) or RFX_HD_LSTM_BWD_STEPWISE is set
     const float* whh = h->whh[op.name + ".l" + std::to_string(l)].p;
     bool persistent = false;
-    {
+    static const bool mma_on = [] { const char* e = getenv("RFX_LSTM_BWD_MMA"); return !(e && atoi(e) == 0); }();
+    if (mma_on && lstm_bwd_chain_mma_supported(H)) {  // cluster / tensor-core chain (lstm.cu)
+      if ((rc = launch_lstm_bwd_chain_mma(Gx.f, R, cs, dH, whh, dG, Bs, Tf, H, s))) return;
+      persistent = true;
+    } else {
       static const bool stepwise = [] { const char* e = getenv("RFX_HD_LSTM_BWD_STEPWISE"); return e && atoi(e) != 0; }();
       const dim3 pg(H / LBP_U, 2, ceil_div(Bs, LBP_B));
       const size_t psmem = ((size_t)4 * H * LBP_U + (size_t)LBP_B * (4 * H + 4) + (size_t)4 * LBP_B * LBP_U) * 4;
@@ -787,7 +791,7 @@ int lstm_layer_backward(const float* Gx, int Bs, int T, int H, const __nv_bfloat
   bool persistent = false;
   {
     static const bool mma_on = [] { const char* e = getenv("RFX_LSTM_BWD_MMA"); return !(e && atoi(e) == 0); }();
-    if (mma_on && H == 256) {
+    if (mma_on && lstm_bwd_chain_mma_supported(H)) {
       if ((rc = launch_lstm_bwd_chain_mma(Gx, R, cs, dH, whh_cat, dG, Bs, T, H, s))) return rc;
       return 0;
     }

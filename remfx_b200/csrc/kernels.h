@@ -149,8 +149,9 @@ int launch_lstm_layer_slots(const float* G, int ldg, const float* Whh, float* Ho
 int launch_lstm_layer_impl(const float* G, int ldg, const float* Whh, float* Hout, int ldh, __nv_bfloat16* Hhi, __nv_bfloat16* Hlo,
                            int ldhs, int B, int F, int H, int impl, int slots, cudaStream_t stream);
 int lstm_clusters_for(int B, int slots);  // clusters (of 8 CTAs) one launch of the tensor-core recurrence uses
-// Reverse-time chain of the LSTM backward for H = 256 on the cluster / mma.sync machinery (see lstm.cu): Gx, R = W_hh h_prev, cell
+// Reverse-time chain of the LSTM backward for H = 192 / 256 / 384 on the cluster / mma.sync machinery (see lstm.cu): Gx, R = W_hh h_prev, cell
 // states cs, dH ([Bs][T][...] layouts of bw::lstm_layer_backward) -> dG.
+bool lstm_bwd_chain_mma_supported(int H);  // 192, 256, 384
 int launch_lstm_bwd_chain_mma(const float* Gx, const float* R, const float* cs, const float* dH, const float* Whh, float* dG, int Bs, int T, int H,
                               cudaStream_t stream);
 

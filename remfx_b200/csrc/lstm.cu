@@ -452,28 +452,38 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(H / 8 / 4 * 32
 // ------------------------------------------------------------------------------------------------------
 constexpr int LBM_BLK = 8 * 36 * 4;  // one partial block: [8 sequences][32 units + 4 pad] fp32
 constexpr int LBM_KP = 136;          // row stride (bf16) of the dG operand: [8 sequences][128 own gate rows + 8 pad]
-__global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(256, 1)
+// CL = CTAs per cluster = H / 32 (6: H = 192, 8: H = 256, 12: H = 384 -- a non-portable cluster size); one MMA warp per peer CTA,
+// eight element warps (32 units x 8 sequences); LO_SMEM keeps the lo-plane A fragments in shared memory (H = 384: 384 threads
+// cannot hold 128 fragment registers each).
+template <int CL, bool LO_SMEM>
+__global__ void __launch_bounds__(32 * (CL > 8 ? CL : 8), 1)
     lstm_bwd_mma_kernel(const float* __restrict__ Gx, const float* __restrict__ R, const float* __restrict__ cs, const float* __restrict__ dH,
                         const float* __restrict__ Whh /*[2][4H][H]*/, float* __restrict__ dG, int Bs, int T) {
-  constexpr int H = 256, UPC = 32;
+  constexpr int H = 32 * CL, UPC = 32;
+  constexpr int NW = CL > 8 ? CL : 8;  // warps per CTA
+  constexpr int THREADS = 32 * NW;
   extern __shared__ __align__(128) uint8_t lbm_smem[];
-  uint8_t* recv = lbm_smem;                                   // [2][8 sources][LBM_BLK]
-  uint8_t* send = recv + 2 * LSTM_CL * LBM_BLK;               // [2][8 warps][LBM_BLK]
-  __nv_bfloat16* dgs = reinterpret_cast<__nv_bfloat16*>(send + 2 * 8 * LBM_BLK);  // [2 planes][8][LBM_KP]
-  uint64_t* rbar = reinterpret_cast<uint64_t*>(dgs + 2 * 8 * LBM_KP);             // [2]
+  uint8_t* recv = lbm_smem;                                   // [2][CL sources][LBM_BLK]
+  uint8_t* send = recv + 2 * CL * LBM_BLK;                    // [2][CL warps][LBM_BLK]
+  __nv_bfloat16* dgs = reinterpret_cast<__nv_bfloat16*>(send + 2 * CL * LBM_BLK);  // [2 planes][8][LBM_KP]
+  uint64_t* rbar = reinterpret_cast<uint64_t*>(dgs + 2 * 8 * LBM_KP);              // [2]
+  uint4* alo_smem = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(rbar) + 64);  // [2 mt][8 ks][THREADS] (LO_SMEM only)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const uint32_t rank = cluster_ctarank();
   const int dir = blockIdx.y, b0 = blockIdx.z * 8;
+  const bool mma_warp = warp < CL;
 
   // ---- A fragments: A[m = unit 32 w + 16 mt + row][k] = W_hh[gate row (k / 32) * H + 32 rank + k % 32][unit] ----
-  uint32_t a_hi[2][8][4], a_lo[2][8][4];
-  {
+  uint32_t a_hi[2][8][4];
+  uint32_t a_lo[LO_SMEM ? 1 : 2][LO_SMEM ? 1 : 8][4];
+  if (mma_warp) {
     const float* W = Whh + (size_t)dir * 4 * H * H;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks)
+      for (int ks = 0; ks < 8; ++ks) {
+        uint32_t lo4[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int row = gid + (q & 1) * 8;                 // a0/a2: gid, a1/a3: gid + 8
@@ -483,23 +493,31 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(256, 1)
           const float w0 = W[g0 * H + unit], w1 = W[(g0 + 1) * H + unit];  // k and k + 1 are in the same gate (k is even)
           float r0, r1;
           a_hi[mt][ks][q] = pack_hi2(w0, w1, r0, r1);
-          a_lo[mt][ks][q] = pack2(r0, r1);
+          lo4[q] = pack2(r0, r1);
         }
+        if (LO_SMEM) {
+          alo_smem[(mt * 8 + ks) * THREADS + tid] = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a_lo[LO_SMEM ? 0 : mt][LO_SMEM ? 0 : ks][q] = lo4[q];
+        }
+      }
   }
-  for (int i = tid; i < 2 * 8 * LBM_KP / 2; i += 256) reinterpret_cast<uint32_t*>(dgs)[i] = 0u;
+  for (int i = tid; i < 2 * 8 * LBM_KP / 2; i += THREADS) reinterpret_cast<uint32_t*>(dgs)[i] = 0u;
   if (tid == 0) {
     mbar_init(&rbar[0], 1);
     mbar_init(&rbar[1], 1);
     mbar_fence_init();
   }
-  // element role: thread = (unit uu of this CTA, sequence n)
+  // element role (warps 0-7): thread = (unit uu of this CTA, sequence n)
+  const bool elem = warp < 8;
   const int uu = lane, n = warp;
   const int u = 32 * (int)rank + uu, b = b0 + n;
-  const bool live = b < Bs;
+  const bool live = elem && b < Bs;
   const int G4 = 4 * H;
   // destination of this warp's partial block: CTA `warp`, slot [source = rank]
-  const uint32_t dst_blk = mapa_u32(smem_u32(recv) + rank * LBM_BLK, (uint32_t)warp);
-  const uint32_t dst_bar = mapa_u32(smem_u32(&rbar[0]), (uint32_t)warp);
+  const uint32_t dst_blk = mma_warp ? mapa_u32(smem_u32(recv) + rank * LBM_BLK, (uint32_t)warp) : 0u;
+  const uint32_t dst_bar = mma_warp ? mapa_u32(smem_u32(&rbar[0]), (uint32_t)warp) : 0u;
   float dc = 0.0f;
   __syncthreads();
   cluster_arrive();
@@ -527,77 +545,87 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(256, 1)
     float dh = dh0;
     const float xi = pi, xf = pf, xg = pg, xo = po, c = cc, cp = cprev;
     if (k > 0) {
-      if (tid == 0) mbar_arrive_expect_tx(&rbar[buf], LSTM_CL * LBM_BLK);
-      // ---- partial dh of the units of CTA `warp` from this CTA's gate rows: 2 m-tiles x 8 k-steps x bf16x3 ----
-      float d[2][3][4];
+      if (tid == 0) mbar_arrive_expect_tx(&rbar[buf], CL * LBM_BLK);
+      if (mma_warp) {
+        // ---- partial dh of the units of CTA `warp` from this CTA's gate rows: 2 m-tiles x 8 k-steps x bf16x3 ----
+        float d[2][3][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
+          for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) d[mt][ch][q] = 0.f;
-      const uint8_t* bh = reinterpret_cast<const uint8_t*>(dgs) + gid * (LBM_KP * 2) + tig * 4;
-      const uint8_t* bl = bh + 8 * LBM_KP * 2;
+            for (int q = 0; q < 4; ++q) d[mt][ch][q] = 0.f;
+        const uint8_t* bh = reinterpret_cast<const uint8_t*>(dgs) + gid * (LBM_KP * 2) + tig * 4;
+        const uint8_t* bl = bh + 8 * LBM_KP * 2;
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint32_t h0 = *reinterpret_cast<const uint32_t*>(bh + ks * 32), h1 = *reinterpret_cast<const uint32_t*>(bh + ks * 32 + 16);
-        const uint32_t l0 = *reinterpret_cast<const uint32_t*>(bl + ks * 32), l1 = *reinterpret_cast<const uint32_t*>(bl + ks * 32 + 16);
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t h0 = *reinterpret_cast<const uint32_t*>(bh + ks * 32), h1 = *reinterpret_cast<const uint32_t*>(bh + ks * 32 + 16);
+          const uint32_t l0 = *reinterpret_cast<const uint32_t*>(bl + ks * 32), l1 = *reinterpret_cast<const uint32_t*>(bl + ks * 32 + 16);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            if (LO_SMEM) {
+              const uint4 lv = alo_smem[(mt * 8 + ks) * THREADS + tid];
+              const uint32_t al[4] = {lv.x, lv.y, lv.z, lv.w};
+              hmma16816(d[mt][0], al, h0, h1);
+            } else {
+              hmma16816(d[mt][0], a_lo[LO_SMEM ? 0 : mt][LO_SMEM ? 0 : ks], h0, h1);
+            }
+            hmma16816(d[mt][1], a_hi[mt][ks], l0, l1);
+            hmma16816(d[mt][2], a_hi[mt][ks], h0, h1);
+          }
+        }
+        float* blk = reinterpret_cast<float*>(send + (buf * CL + warp) * LBM_BLK);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-          hmma16816(d[mt][0], a_lo[mt][ks], h0, h1);
-          hmma16816(d[mt][1], a_hi[mt][ks], l0, l1);
-          hmma16816(d[mt][2], a_hi[mt][ks], h0, h1);
+          const float c0 = (d[mt][0][0] + d[mt][1][0]) + d[mt][2][0], c1 = (d[mt][0][1] + d[mt][1][1]) + d[mt][2][1];
+          const float c2 = (d[mt][0][2] + d[mt][1][2]) + d[mt][2][2], c3 = (d[mt][0][3] + d[mt][1][3]) + d[mt][2][3];
+          blk[(2 * tig) * 36 + 16 * mt + gid] = c0;
+          blk[(2 * tig + 1) * 36 + 16 * mt + gid] = c1;
+          blk[(2 * tig) * 36 + 16 * mt + gid + 8] = c2;
+          blk[(2 * tig + 1) * 36 + 16 * mt + gid + 8] = c3;
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0)
+          bulk_s2cluster(dst_blk + (uint32_t)(buf * CL * LBM_BLK), smem_u32(blk), LBM_BLK, dst_bar + (uint32_t)(buf * sizeof(uint64_t)));
       }
-      float* blk = reinterpret_cast<float*>(send + (buf * 8 + warp) * LBM_BLK);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const float c0 = (d[mt][0][0] + d[mt][1][0]) + d[mt][2][0], c1 = (d[mt][0][1] + d[mt][1][1]) + d[mt][2][1];
-        const float c2 = (d[mt][0][2] + d[mt][1][2]) + d[mt][2][2], c3 = (d[mt][0][3] + d[mt][1][3]) + d[mt][2][3];
-        blk[(2 * tig) * 36 + 16 * mt + gid] = c0;
-        blk[(2 * tig + 1) * 36 + 16 * mt + gid] = c1;
-        blk[(2 * tig) * 36 + 16 * mt + gid + 8] = c2;
-        blk[(2 * tig + 1) * 36 + 16 * mt + gid + 8] = c3;
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0)
-        bulk_s2cluster(dst_blk + (uint32_t)(buf * LSTM_CL * LBM_BLK), smem_u32(blk), LBM_BLK, dst_bar + (uint32_t)(buf * sizeof(uint64_t)));
     }
     fetch(k + 1);     // next step's operands: in flight during the exchange
     __syncthreads();  // every warp is done reading dG_{t'} (the element phase below overwrites it)
-    if (k > 0) {
-      mbar_wait(&rbar[buf], ((k - 1) >> 1) & 1);
-      const float* rb = reinterpret_cast<const float*>(recv + buf * LSTM_CL * LBM_BLK) + n * 36 + uu;
-      float s0 = 0.f, s1 = 0.f;
+    if (elem) {
+      if (k > 0) {
+        mbar_wait(&rbar[buf], ((k - 1) >> 1) & 1);
+        const float* rb = reinterpret_cast<const float*>(recv + buf * CL * LBM_BLK) + n * 36 + uu;
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int src = 0; src < LSTM_CL; src += 2) {
-        s0 += rb[src * (LBM_BLK / 4)];
-        s1 += rb[(src + 1) * (LBM_BLK / 4)];
+        for (int src = 0; src < CL; src += 2) {
+          s0 += rb[src * (LBM_BLK / 4)];
+          s1 += rb[(src + 1) * (LBM_BLK / 4)];
+        }
+        dh += s0 + s1;
       }
-      dh += s0 + s1;
-    }
-    // ---- gate derivatives (tools/hd_bwd_emul.py: lstm_dir_bwd), as in hd::lstm_bwd_persist_kernel ----
-    float g4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (live) {
-      const float gi = sigmoidf_acc(xi), gf = sigmoidf_acc(xf), gg = tanhf(xg), go_ = sigmoidf_acc(xo);
-      const float tc = tanhf(c);
-      dc += dh * go_ * (1.0f - tc * tc);
-      g4[0] = dc * gg * gi * (1.0f - gi);
-      g4[1] = dc * cp * gf * (1.0f - gf);
-      g4[2] = dc * gi * (1.0f - gg * gg);
-      g4[3] = dh * tc * go_ * (1.0f - go_);
-      dc *= gf;
-      const size_t go = ((size_t)b * T + t) * 8 * H + (size_t)dir * G4 + u;
+      // ---- gate derivatives (tools/hd_bwd_emul.py: lstm_dir_bwd), as in hd::lstm_bwd_persist_kernel ----
+      float g4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (live) {
+        const float gi = sigmoidf_acc(xi), gf = sigmoidf_acc(xf), gg = tanhf(xg), go_ = sigmoidf_acc(xo);
+        const float tc = tanhf(c);
+        dc += dh * go_ * (1.0f - tc * tc);
+        g4[0] = dc * gg * gi * (1.0f - gi);
+        g4[1] = dc * cp * gf * (1.0f - gf);
+        g4[2] = dc * gi * (1.0f - gg * gg);
+        g4[3] = dh * tc * go_ * (1.0f - go_);
+        dc *= gf;
+        const size_t go = ((size_t)b * T + t) * 8 * H + (size_t)dir * G4 + u;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) dG[go + (size_t)q * H] = g4[q];
-    }
+        for (int q = 0; q < 4; ++q) dG[go + (size_t)q * H] = g4[q];
+      }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {  // this CTA's dG_t as the next step's B operand: [plane][sequence][k = gate * 32 + unit]
-      __nv_bfloat16 hq, lq;
-      split_bf16(g4[q], hq, lq);
-      dgs[n * LBM_KP + q * UPC + uu] = hq;
-      dgs[8 * LBM_KP + n * LBM_KP + q * UPC + uu] = lq;
+      for (int q = 0; q < 4; ++q) {  // this CTA's dG_t as the next step's B operand: [plane][sequence][k = gate * 32 + unit]
+        __nv_bfloat16 hq, lq;
+        split_bf16(g4[q], hq, lq);
+        dgs[n * LBM_KP + q * UPC + uu] = hq;
+        dgs[8 * LBM_KP + n * LBM_KP + q * UPC + uu] = lq;
+      }
     }
     __syncthreads();
   }
@@ -606,15 +634,35 @@ __global__ void __cluster_dims__(LSTM_CL, 1, 1) __launch_bounds__(256, 1)
   cluster_wait();
 }
 
+template <int CL, bool LO_SMEM>
+static int launch_lbm(const float* Gx, const float* R, const float* cs, const float* dH, const float* Whh, float* dG, int Bs, int T, cudaStream_t stream) {
+  constexpr int NW = CL > 8 ? CL : 8;
+  const size_t smem = (size_t)4 * CL * LBM_BLK + (size_t)2 * 8 * LBM_KP * 2 + 16 + 64 + (LO_SMEM ? (size_t)16 * 32 * NW * 16 : 0);
+  auto kern = lstm_bwd_mma_kernel<CL, LO_SMEM>;
+  RFX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (CL > 8) RFX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(CL, 2, ceil_div(Bs, 8));
+  cfg.blockDim = dim3(32 * NW);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  RFX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, Gx, R, cs, dH, Whh, dG, Bs, T));
+  return 0;
+}
+
+bool lstm_bwd_chain_mma_supported(int H) { return H == 192 || H == 256 || H == 384; }
+
 int launch_lstm_bwd_chain_mma(const float* Gx, const float* R, const float* cs, const float* dH, const float* Whh, float* dG, int Bs, int T, int H,
                               cudaStream_t stream) {
-  RFX_REQUIRE(H == 256, "lstm_bwd_mma_kernel: H = 256 only");
-  const size_t smem = (size_t)2 * LSTM_CL * LBM_BLK + (size_t)2 * 8 * LBM_BLK + (size_t)2 * 8 * LBM_KP * 2 + 64;
-  RFX_CHECK_CUDA(cudaFuncSetAttribute(lstm_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(LSTM_CL, 2, ceil_div(Bs, 8));
-  lstm_bwd_mma_kernel<<<grid, 256, smem, stream>>>(Gx, R, cs, dH, Whh, dG, Bs, T);
-  RFX_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  if (H == 256) return launch_lbm<8, false>(Gx, R, cs, dH, Whh, dG, Bs, T, stream);
+  if (H == 192) return launch_lbm<6, false>(Gx, R, cs, dH, Whh, dG, Bs, T, stream);
+  if (H == 384) return launch_lbm<12, true>(Gx, R, cs, dH, Whh, dG, Bs, T, stream);
+  set_error("lstm_bwd_mma_kernel: H must be 192, 256 or 384");
+  return 2;
 }
 
 template <int H, bool LO_SMEM>
