@@ -176,6 +176,7 @@ struct G2Params {
   const float* t2;
   const float* slope;  // ACT_PRELU: per-column negative slope
   int act;
+  int cf_accum;  // 1: the fp32 output accumulates (Cf += v; ACT_NONE without GLU only) -- the input-gradient GEMMs of residual branches
   // fused GroupNorm statistics of the (post-bias) output: accum[(seg * G + g) * 2 + {0,1}] += (sum, sum of squares)
   double* gn_acc;
   int gn_G, gn_per_x, gn_cpg, gn_cmod;  // group of column n = ((n % cmod) / cpg); seg = per_x ? b * X + px : b
@@ -311,6 +312,18 @@ __device__ __forceinline__ void g2_chunk(const uint32_t (&v)[32], const uint32_t
     return;
   }
   if (r.cf) {
+    if (ACT == ACT_NONE && p.cf_accum) {
+      if (r.cf_vec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 q = *reinterpret_cast<const float4*>(r.cf + nb + 4 * i);
+          o[4 * i] += q.x; o[4 * i + 1] += q.y; o[4 * i + 2] += q.z; o[4 * i + 3] += q.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] += r.cf[nb + i];
+      }
+    }
     if (r.cf_vec) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(r.cf + nb + 4 * i) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
@@ -419,7 +432,7 @@ __device__ __forceinline__ void g2_chunk_ragged(uint32_t taddr, uint32_t taddr2,
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (n8 + i < p.N) {
-        if (r.cf) r.cf[n8 + i] = o[i];
+        if (r.cf) r.cf[n8 + i] = p.cf_accum ? r.cf[n8 + i] + o[i] : o[i];
         if (r.chi) {
           __nv_bfloat16 h, l;
           split_bf16(o[i], h, l);
@@ -689,6 +702,8 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   p.Cf = pr.Cf; p.ldcf = pr.ldcf; p.bscf = pr.bscf; p.ldcy_f = pr.ldcf_y;
   p.Chi = pr.Chi; p.Clo = pr.Clo; p.ldcs = pr.ldcs; p.bscs = pr.bscs; p.ldcy_s = pr.ldcs_y;
   p.s1 = pr.epi.s1; p.t1 = pr.epi.t1; p.s2 = pr.epi.s2; p.t2 = pr.epi.t2; p.slope = pr.epi.slope; p.act = pr.epi.act;
+  p.cf_accum = pr.cf_accum ? 1 : 0;
+  RFX_REQUIRE(!pr.cf_accum || (pr.Cf && !pr.Chi && pr.epi.act == ACT_NONE && !pr.gn_acc), "accumulating output: fp32 only, no activation, no fused statistics");
   p.gn_acc = pr.gn_acc; p.gn_G = pr.gn_G > 0 ? pr.gn_G : 1; p.gn_per_x = pr.gn_per_x;
   p.gn_cmod = pr.gn_cmod > 0 ? pr.gn_cmod : pr.N;
   p.gn_cpg = p.gn_cmod / p.gn_G;

@@ -68,15 +68,15 @@ struct GnBwd {
   int nseg, nchunks;      // work items = nseg * nchunks; the grid strides over them
 };
 
-template <int PASS>
-__global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwd p) {
+template <int PASS, int MODE>   // MODE = GnApply::mode, a compile-time constant: the plain / GELU forms carry none of the gate octet's state
+__global__ void __launch_bounds__(256, ((PASS == 2 && MODE != 2) || (PASS == 1 && MODE <= 1)) ? 3 : 2) gn_bwd_kernel(const GnBwd p) {
   extern __shared__ __align__(16) float gb_smem[];  // PASS 1: [2 * Cr] (dbeta, dgamma) + [Co] (dscale), then doubles [2 * G] (16-byte aligned)
   const GnApply& a = p.a;
   const int groups = a.Co / 8;
   const int rows = 256 / groups;
   const int g8 = threadIdx.x % groups, r = threadIdx.x / groups;
   const int c0 = g8 * 8;
-  const int mode = a.mode;
+  constexpr int mode = MODE;
   const int Ch = mode >= 2 ? a.Cr / 2 : a.Cr;  // valid output channels
   const int cpg = a.Cr / a.G;
   const bool has_stats = a.stats != nullptr;
@@ -1142,87 +1142,132 @@ struct NarrowP {
   float* dy;                                // DEC: gradient of the wide activation (written)
   float* dW; float* db;
   int rows_per_cta;
+  int nlines, nchunks;                      // work items = nlines * nchunks; the grid strides over them
 };
 
-template <int K, int P, bool ENC>
-__global__ void __launch_bounds__(256) narrow_bwd_kernel(const NarrowP p) {
-  extern __shared__ float nb_smem[];  // [C * P * K] weights, [C * P * K + C] accumulators
-  const int C = p.C, WN = C * P * K;
+// Persistent: a 1-D grid of (at most) two CTAs per SM strides over the work items (line, chunk of wide rows), a thread owns CH
+// wide channels (CH * P * K = 64 weight-gradient sums in registers for the CTA's whole life) and the sums reach shared / global
+// memory once per CTA.  The weights sit in shared memory TRANSPOSED ([P * K][C]): the threads of a warp read consecutive channels of
+// one tap (conflict-free; the [C][P * K] order put every channel group on the same bank).
+template <int CH>
+__device__ __forceinline__ void nb_load_wide(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t off, float (&o)[CH]) {
+  if constexpr (CH == 8) {
+    bw_load_split8(hi, lo, off, o);
+  } else {
+    static_assert(CH == 4, "narrow layers: 4 or 8 channels per thread");
+    const uint2 h = *reinterpret_cast<const uint2*>(hi + off), l = *reinterpret_cast<const uint2*>(lo + off);
+    const uint32_t hw[2] = {h.x, h.y}, lw[2] = {l.x, l.y};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[i]));
+      const float2 lf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[i]));
+      o[2 * i] = hf.x + lf.x;
+      o[2 * i + 1] = hf.y + lf.y;
+    }
+  }
+}
+template <int K, int P, bool ENC, int CH>
+__global__ void __launch_bounds__(256, 2) narrow_bwd_kernel(const NarrowP p) {
+  extern __shared__ __align__(16) float nb_smem[];  // [P * K][C] weights (transposed), [C * P * K + C] accumulators
+  constexpr int PK = P * K;
+  const int C = p.C, WN = C * PK;
   float* sw = nb_smem;
   float* sa = nb_smem + WN;
-  for (int i = threadIdx.x; i < WN; i += 256) sw[i] = p.w[i];
+  for (int i = threadIdx.x; i < WN; i += 256) sw[(i % PK) * C + i / PK] = p.w[i];
   for (int i = threadIdx.x; i < WN + C; i += 256) sa[i] = 0.0f;
   __syncthreads();
-  const int groups = C / 8, rows = 256 / groups;
-  const int g8 = threadIdx.x % groups, r = threadIdx.x / groups, c0 = g8 * 8;
-  const int line = blockIdx.y, b = line / p.Y;
-  float sub = 0.0f, mul = 1.0f;
-  if (p.stats) {
-    if (p.norm_mode == 1) { sub = p.stats[2 * b]; mul = 1.0f / (1e-5f + p.stats[2 * b + 1]); }
-    else if (p.norm_mode == 2) { mul = p.stats[2 * b + 1]; }
-  }
-  const float* nl = p.narrow + (size_t)line * p.n_line;
-  float accw[8][P * K];
-  float accb[8];
+  const int groups = C / CH, rows = 256 / groups;
+  const int g8 = threadIdx.x % groups, r = threadIdx.x / groups, c0 = g8 * CH;
+  float accw[CH][PK];
+  float accb[CH], bias[CH];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < CH; ++i) {
     accb[i] = 0.0f;
+    bias[i] = (ENC && r < rows) ? p.bias[c0 + i] : 0.0f;
 #pragma unroll
-    for (int q = 0; q < P * K; ++q) accw[i][q] = 0.0f;
+    for (int q = 0; q < PK; ++q) accw[i][q] = 0.0f;
   }
-  const int x_begin = blockIdx.x * p.rows_per_cta, x_end = min(p.Xw, x_begin + p.rows_per_cta);
+  const long long n_items = (long long)p.nlines * p.nchunks;
   if (r < rows) {
-    for (int x = x_begin + r; x < x_end; x += rows) {
-      float nv[P * K];
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int line = (int)(item / p.nchunks), chunk = (int)(item % p.nchunks), b = line / p.Y;
+      float sub = 0.0f, mul = 1.0f;
+      if (p.stats) {
+        if (p.norm_mode == 1) { sub = p.stats[2 * b]; mul = 1.0f / (1e-5f + p.stats[2 * b + 1]); }
+        else if (p.norm_mode == 2) { mul = p.stats[2 * b + 1]; }
+      }
+      const float* nl = p.narrow + (size_t)line * p.n_line;
+      const int x_begin = chunk * p.rows_per_cta, x_end = min(p.Xw, x_begin + p.rows_per_cta);
+      for (int x = x_begin + r; x < x_end; x += rows) {
+        float nv[PK];
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const int n = x * p.S + j - p.pad;
-        const bool ok = n >= 0 && n < p.Xn;
+        for (int j = 0; j < K; ++j) {
+          const int n = x * p.S + j - p.pad;
+          const bool ok = n >= 0 && n < p.Xn;
 #pragma unroll
-        for (int q = 0; q < P; ++q) {
-          float v = 0.0f;
-          if (ok) {
-            v = (nl[(size_t)n * P + q] - sub) * mul;
-            if (p.ck && n != 0) v *= 2.0f;
+          for (int q = 0; q < P; ++q) {
+            float v = 0.0f;
+            if (ok) {
+              v = (__ldg(nl + (size_t)n * P + q) - sub) * mul;
+              if (p.ck && n != 0) v *= 2.0f;
+            }
+            nv[q * K + j] = v;
           }
-          nv[q * K + j] = v;
         }
+        const size_t woff = ((size_t)line * p.Xw + x) * C + c0;
+        float wide[CH];
+        if (ENC) {
+          float dv[CH];
+#pragma unroll
+          for (int i = 0; i < CH; i += 4) {
+            const float4 d = *reinterpret_cast<const float4*>(p.dwide + woff + i);
+            dv[i] = d.x; dv[i + 1] = d.y; dv[i + 2] = d.z; dv[i + 3] = d.w;
+          }
+          float pre[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) pre[i] = bias[i];
+#pragma unroll
+          for (int q = 0; q < PK; ++q) {
+#pragma unroll
+            for (int i = 0; i < CH; i += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(sw + q * C + c0 + i);
+              pre[i] = fmaf(w4.x, nv[q], pre[i]); pre[i + 1] = fmaf(w4.y, nv[q], pre[i + 1]);
+              pre[i + 2] = fmaf(w4.z, nv[q], pre[i + 2]); pre[i + 3] = fmaf(w4.w, nv[q], pre[i + 3]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            wide[i] = dv[i] * gelu_grad(pre[i]);
+            accb[i] += wide[i];
+          }
+        } else {
+          nb_load_wide<CH>(p.yhi, p.ylo, woff, wide);
+          float dyv[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) dyv[i] = 0.0f;
+#pragma unroll
+          for (int q = 0; q < PK; ++q) {
+#pragma unroll
+            for (int i = 0; i < CH; i += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(sw + q * C + c0 + i);
+              dyv[i] = fmaf(w4.x, nv[q], dyv[i]); dyv[i + 1] = fmaf(w4.y, nv[q], dyv[i + 1]);
+              dyv[i + 2] = fmaf(w4.z, nv[q], dyv[i + 2]); dyv[i + 3] = fmaf(w4.w, nv[q], dyv[i + 3]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < CH; i += 4)
+            *reinterpret_cast<float4*>(p.dy + woff + i) = make_float4(dyv[i], dyv[i + 1], dyv[i + 2], dyv[i + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+#pragma unroll
+          for (int q = 0; q < PK; ++q) accw[i][q] = fmaf(wide[i], nv[q], accw[i][q]);
       }
-      const size_t woff = ((size_t)line * p.Xw + x) * C + c0;
-      float wide[8];
-      if (ENC) {
-        const float4 d0 = *reinterpret_cast<const float4*>(p.dwide + woff), d1 = *reinterpret_cast<const float4*>(p.dwide + woff + 4);
-        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float pre = p.bias[c0 + i];
-#pragma unroll
-          for (int q = 0; q < P * K; ++q) pre = fmaf(sw[(c0 + i) * P * K + q], nv[q], pre);
-          wide[i] = dv[i] * gelu_grad(pre);
-          accb[i] += wide[i];
-        }
-      } else {
-        bw_load_split8(p.yhi, p.ylo, woff, wide);
-        float dyv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float a = 0.0f;
-#pragma unroll
-          for (int q = 0; q < P * K; ++q) a = fmaf(sw[(c0 + i) * P * K + q], nv[q], a);
-          dyv[i] = a;
-        }
-        *reinterpret_cast<float4*>(p.dy + woff) = make_float4(dyv[0], dyv[1], dyv[2], dyv[3]);
-        *reinterpret_cast<float4*>(p.dy + woff + 4) = make_float4(dyv[4], dyv[5], dyv[6], dyv[7]);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int q = 0; q < P * K; ++q) accw[i][q] = fmaf(wide[i], nv[q], accw[i][q]);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < CH; ++i) {
 #pragma unroll
-      for (int q = 0; q < P * K; ++q) atomicAdd(&sa[(c0 + i) * P * K + q], accw[i][q]);
+      for (int q = 0; q < PK; ++q) atomicAdd(&sa[(c0 + i) * PK + q], accw[i][q]);
       if (ENC) atomicAdd(&sa[WN + c0 + i], accb[i]);
     }
   }

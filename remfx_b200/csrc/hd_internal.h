@@ -76,6 +76,7 @@ struct Conv {
   SplitW wt;
   Buf wtbuf;
   bool wt_ready = false;
+  int pack_ev = -1;   // backward: index of the event (rfx_hdemucs::ev_pack) that marks this pack complete on the preparation stream; -1 = none pending
 };
 
 // ---- training tape: one record per forward op, replayed in reverse by hdemucs_bwd.cu ----
@@ -132,8 +133,13 @@ struct rfx_hdemucs {
   // the time branch of the forward runs on its own stream beside the frequency branch (hdemucs.cu: run_forward)
   cudaStream_t s_time = nullptr;
   cudaEvent_t ev_branch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // the backward builds the transposed weight packs of its input-gradient GEMMs on a third stream, ahead of the reverse replay
+  cudaStream_t s_prep = nullptr;
+  std::vector<cudaEvent_t> ev_pack;
   ~rfx_hdemucs() {
     if (s_time) cudaStreamDestroy(s_time);
+    if (s_prep) cudaStreamDestroy(s_prep);
+    for (auto e : ev_pack) if (e) cudaEventDestroy(e);
     for (auto e : ev_branch) if (e) cudaEventDestroy(e);
     for (auto& kv : params) kv.second.release();
     for (auto& kv : convs) { kv.second.wbuf.release(); kv.second.bias.release(); kv.second.wtbuf.release(); }

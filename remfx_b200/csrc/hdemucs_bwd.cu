@@ -54,7 +54,6 @@ struct BRunner {
   std::map<const void*, GradRec> G;
   float* stage = nullptr;   // weight-gradient staging [Nout][taps][Kp] (largest conv)
   float* bstage = nullptr;  // bias staging [largest Nout]
-  float* tmpf = nullptr;    // input-gradient scratch for accumulating GEMM outputs (largest conv input)
   std::set<std::string> injected;
   // Parameter gradients (weight-gradient contraction, bias column sums, scatters) are off the critical path of the reverse replay --
   // only the INPUT gradient feeds the next op -- so they run on a side stream (the handle's second stream) behind an event that
@@ -239,7 +238,7 @@ struct BRunner {
     }
   }
 
-  int ensure_transposed(Conv& c, int Kt) {
+  int ensure_transposed(Conv& c, int Kt, cudaStream_t s) {   // (s shadows the runner's stream: the pack is built on the stream given)
     if (c.wt_ready) return 0;
     const GatherSpec& gs = c.g;
     const int Np = ceil_div(gs.Nout, 64) * 64;
@@ -273,7 +272,11 @@ struct BRunner {
     // input gradient
     GradRec& gi = actgrad(op.in);
     if (dry || rc) { gi.init = true; return; }
-    if ((rc = ensure_transposed(c, pr.Ktap))) return;
+    if (c.pack_ev >= 0) {   // built ahead on the preparation stream: this stream continues behind its event
+      if (cudaStreamWaitEvent(s, h->ev_pack[c.pack_ev], 0) != cudaSuccess) { fail("pack event"); return; }
+      c.pack_ev = -1;
+    }
+    if ((rc = ensure_transposed(c, pr.Ktap, s))) return;
     G2Problem q;
     q.A.hi = gr.s + op.dst_col; q.A.rows = Xo; q.A.rows_y = Yo; q.A.ld = ldg; q.A.ld_y = (long long)Xo * ldg;
     q.A.batch_stride = (long long)Yo * Xo * ldg; q.A.plane_stride = (long long)gr.plane;
@@ -284,14 +287,9 @@ struct BRunner {
     int xt = 128;
     while (xt > Xv && xt > 1) xt >>= 1;
     q.xt = xt;
-    float* dst = gi.init ? tmpf : gi.f;
-    q.Cf = dst; q.ldcf = Cv; q.ldcf_y = (long long)Xv * Cv; q.bscf = (long long)Yv * Xv * Cv;
+    // residual branches: the second and later contributions accumulate in the GEMM's epilogue (Cf += ...)
+    q.Cf = gi.f; q.cf_accum = gi.init; q.ldcf = Cv; q.ldcf_y = (long long)Xv * Cv; q.bscf = (long long)Yv * Xv * Cv;
     if ((rc = launch_gemm2(q, s))) return;
-    if (gi.init) {
-      const size_t n = (size_t)pr.batch * Yv * Xv * Cv;
-      add_inplace_kernel<<<(unsigned)std::min<size_t>((n / 4 + 255) / 256, 148 * 8), 256, 0, s>>>(gi.f, tmpf, (long long)(n / 4));
-      chk("dgrad add");
-    }
     gi.init = true;
   }
 
@@ -328,10 +326,22 @@ struct BRunner {
     if (has_stats) {
       if (cudaMemsetAsync(gsum, 0, (size_t)nseg * a.G * 2 * 8, s) != cudaSuccess) { fail("memset"); return; }
       const size_t smem = (size_t)((2 * a.Cr + a.Co + 3) & ~3) * 4 + 2 * a.G * 8;
-      gn_bwd_kernel<1><<<grid, 256, smem, s>>>(p);
+      switch (a.mode) {
+        case 0: gn_bwd_kernel<1, 0><<<grid, 256, smem, s>>>(p); break;
+        case 1: gn_bwd_kernel<1, 1><<<grid, 256, smem, s>>>(p); break;
+        case 2: gn_bwd_kernel<1, 2><<<grid, 256, smem, s>>>(p); break;
+        case 3: gn_bwd_kernel<1, 3><<<grid, 256, smem, s>>>(p); break;
+        default: fail("gn backward: unknown activation mode"); return;
+      }
       chk("gn pass 1");
     }
-    gn_bwd_kernel<2><<<grid, 256, 0, s>>>(p);
+    switch (a.mode) {
+      case 0: gn_bwd_kernel<2, 0><<<grid, 256, 0, s>>>(p); break;
+      case 1: gn_bwd_kernel<2, 1><<<grid, 256, 0, s>>>(p); break;
+      case 2: gn_bwd_kernel<2, 2><<<grid, 256, 0, s>>>(p); break;
+      case 3: gn_bwd_kernel<2, 3><<<grid, 256, 0, s>>>(p); break;
+      default: fail("gn backward: unknown activation mode"); return;
+    }
     chk("gn pass 2");
     graw.init = true;
     if (gres) gres->init = true;
@@ -453,12 +463,19 @@ struct BRunner {
   // ---- first / last (narrow) layers ----
   template <int P, bool ENC>
   void narrow(NarrowP p, int lines) {
+    constexpr int CH = (P == 2 || ENC) ? 4 : 8;   // at most 64 weight-gradient sums per thread (no spills at two CTAs per SM)
     const int WN = p.C * P * 8;
     const size_t smem = (size_t)(2 * WN + p.C) * 4;
-    const int groups = p.C / 8, rows = 256 / groups;
-    p.rows_per_cta = rows_for(p.Xw, lines, rows * 4);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(narrow_bwd_kernel<8, P, ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    narrow_bwd_kernel<8, P, ENC><<<dim3(ceil_div(p.Xw, p.rows_per_cta), lines), 256, smem, s>>>(p);
+    const int groups = p.C / CH, rows = 256 / groups;
+    if (p.C % 8 || groups > 256) { fail("narrow layer: channels must be a multiple of 8 (at most 1024)"); return; }
+    // chunks of wide rows: enough items to balance 296 CTAs, at least four rows per thread
+    const long long want = std::max<long long>(1, (8 * 296 + lines - 1) / lines);
+    p.rows_per_cta = (int)std::max<long long>((p.Xw + want - 1) / want, rows * 4);
+    p.nlines = lines;
+    p.nchunks = ceil_div(p.Xw, p.rows_per_cta);
+    const int grid = (int)std::min<long long>((long long)lines * p.nchunks, 296);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(narrow_bwd_kernel<8, P, ENC, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    narrow_bwd_kernel<8, P, ENC, CH><<<grid, 256, smem, s>>>(p);
     chk("narrow layer");
     if (!ENC) {
       narrow_bias_kernel<P><<<dim3(std::min(32, ceil_div(p.Xn, 256)), lines), 256, 0, s>>>(p);
@@ -466,17 +483,49 @@ struct BRunner {
     }
   }
 
+  // The transposed packs depend on the weights only.  Built inside conv_bwd they sat on the critical path of the replay (three small
+  // launches per conv, 118 convs); here they are all queued on a third stream in the order the replay needs them, one event per
+  // pack, and conv_bwd waits on its conv's event.  The staging buffers (gather_tmp / gather_tmp2) are only touched on that stream
+  // during a backward; the caller's stream joins it at the end so that the next finalize finds them free.
+  bool prep_joined = true;
+  void prepare_packs() {
+    if (!s_side || dry || rc) return;   // RFX_HD_OVERLAP=0: packs are built lazily on the caller's stream
+    if (!h->s_prep && cudaStreamCreateWithFlags(&h->s_prep, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); h->s_prep = nullptr; return; }
+    if (cudaEventRecord(ev_join, s) != cudaSuccess || cudaStreamWaitEvent(h->s_prep, ev_join, 0) != cudaSuccess) { fail("preparation-stream fork"); return; }
+    prep_joined = false;
+    size_t n_ev = 0;
+    for (auto op = h->tape.rbegin(); op != h->tape.rend() && !rc; ++op) {
+      if (op->kind != OP_CONV) continue;
+      auto it = h->convs.find(op->name);
+      if (it == h->convs.end() || it->second.wt_ready) continue;
+      Conv& c = it->second;
+      if ((rc = ensure_transposed(c, op->pr.Ktap, h->s_prep))) return;
+      if (n_ev == h->ev_pack.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { fail("event"); return; }
+        h->ev_pack.push_back(e);
+      }
+      if (cudaEventRecord(h->ev_pack[n_ev], h->s_prep) != cudaSuccess) { fail("pack event record"); return; }
+      c.pack_ev = (int)n_ev++;
+    }
+  }
+  void prep_join() {
+    if (prep_joined || dry) return;
+    prep_joined = true;
+    for (auto& kv : h->convs) kv.second.pack_ev = -1;
+    if (cudaEventRecord(ev_join, h->s_prep) != cudaSuccess || cudaStreamWaitEvent(s, ev_join, 0) != cudaSuccess) fail("preparation-stream join");
+  }
+
   void run(const float* x, const float* dout) {
     (void)x;
     // scratch sized from the tape
-    size_t max_stage = 1, max_in = 1, max_n = 1;
+    size_t max_stage = 1, max_n = 1;
     for (const Op& op : h->tape) {
       if (op.kind != OP_CONV) continue;
       auto it = h->convs.find(op.name);
       if (it == h->convs.end()) { fail("conv '" + op.name + "' not prepared"); return; }
       const GatherSpec& g = it->second.g;
       max_stage = std::max(max_stage, (size_t)g.Nout * g.taps * g.Kp);
-      max_in = std::max(max_in, op.in.elems());
       max_n = std::max(max_n, (size_t)g.Nout);
     }
     for (auto& kv : h->convs) {  // LSTM recurrent weights are not on the tape as convs
@@ -488,7 +537,6 @@ struct BRunner {
     }
     stage = reinterpret_cast<float*>(take(max_stage * 4));
     bstage = reinterpret_cast<float*>(take(max_n * 4));
-    tmpf = reinterpret_cast<float*>(take(max_in * 4));
     side_setup();
     if (!dry) {
       bool attr_ok = true;
@@ -506,6 +554,8 @@ struct BRunner {
         if (cudaMemsetAsync(kv.second, 0, pit->second.n * 4, s) != cudaSuccess) { fail("memset"); return; }
       }
     }
+    prepare_packs();
+    if (rc) return;
     // debug: map injected taps to tensor keys
     std::map<const void*, std::string> inject_at;
     if (!dry)
@@ -664,6 +714,7 @@ struct BRunner {
         default: fail("unknown tape op"); break;
       }
     }
+    prep_join();
     side_join();
     if (!dry && ok()) {
       h->act_grads.clear();

@@ -108,6 +108,7 @@ struct G2Problem {
   bool dual = false;            // last tap -> second accumulator, added after the activation (TCN residual)
   float* Cf = nullptr;          // fp32 output (optional): element (b, y, x, n) at b * bscf + y * ldcf_y + x * ldcf + n
   long long ldcf = 0, ldcf_y = 0, bscf = 0;
+  bool cf_accum = false;        // Cf += result instead of Cf = result (fp32 output only, ACT_NONE)
   __nv_bfloat16* Chi = nullptr;  // split-bf16 output (optional)
   __nv_bfloat16* Clo = nullptr;
   long long ldcs = 0, ldcs_y = 0, bscs = 0;
