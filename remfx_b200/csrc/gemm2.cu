@@ -150,6 +150,8 @@ struct G2Params {
   int N;           // valid output columns
   int batch;       // batch items (grid tiles = batch * m_tiles * n_tiles)
   int m_tiles, n_tiles;
+  int chunk;       // > 0: CTA c owns the tiles [c * chunk, (c + 1) * chunk) and the tiles of an item run y-fastest (launches with fused
+                   // GroupNorm statistics: consecutive tiles share their statistics segment); 0: tiles strided over the grid, x-fastest
   // shared-memory plan (host-chosen): [resident W: w_res_bytes][stages x stage_bytes][barriers]
   int stages;      // ring depth (2..G2_MAX_STAGES)
   int stage_bytes; // A tile (+ W tile when W is not resident); multiple of 1024
@@ -450,7 +452,8 @@ constexpr int g2_threads(bool dual) { return 64 + 32 * g2_epi_warps(dual); }
 
 constexpr int G2_MAX_STAGES = 6;
 
-template <int BN, bool DUAL>
+template <int BN, bool DUAL, bool GN>   // GN: fused GroupNorm statistics (chunked tile schedule, running fp64 sums) -- its own instantiation so
+                                        // that the plain kernels carry none of that state in their register-tight epilogue
 __global__ void __launch_bounds__(g2_threads(DUAL), 1)
     gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const G2Params p) {
   const int STAGES = p.stages;
@@ -474,6 +477,13 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
   const int KB = p.kb_per_tap * p.taps;
   const int tiles_per_batch = p.m_tiles * p.n_tiles;
   const int total_tiles = p.batch * tiles_per_batch;
+  // tile schedule of this CTA (identical in the three roles): my_tiles tiles, the i-th one being tile_at(i)
+  const int my_tiles = GN ? max(0, min(p.chunk, total_tiles - (int)blockIdx.x * p.chunk))
+                          : ((int)blockIdx.x < total_tiles ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+  auto tile_at = [&](int i) { return GN ? (int)blockIdx.x * p.chunk + i : (int)blockIdx.x + i * (int)gridDim.x; };
+  const int tiles_y = p.m_tiles / p.tiles_x;
+  auto tile_x = [&](int mt) { return GN ? mt / tiles_y : mt % p.tiles_x; };
+  auto tile_y = [&](int mt) { return GN ? mt % tiles_y : mt / p.tiles_x; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -507,11 +517,12 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
       }
       int s = 0;
       uint32_t ph = 0;  // ring position and its phase bit
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int tile = tile_at(ti);
         const int b = tile / tiles_per_batch;
         const int r = tile % tiles_per_batch;
         const int mt = r / p.n_tiles;
-        const int x0 = (mt % p.tiles_x) * p.xt, y0 = (mt / p.tiles_x) * p.yt;
+        const int x0 = tile_x(mt) * p.xt, y0 = tile_y(mt) * p.yt;
         const int n0 = (r % p.n_tiles) * BN;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -535,7 +546,8 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
         mbar_wait(wfull_bar, 0);
         tc_fence_after();
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      for (; local < my_tiles; ++local) {
+        const int tile = tile_at(local);
         const int as = DUAL ? 0 : (local & 1);
         const int aphase = DUAL ? (local & 1) : ((local >> 1) & 1);
         mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
@@ -582,8 +594,31 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
     const int half = (warp - 2) >> 2;   // which slice of the tile's columns this warp drains
     constexpr int CH = BN / (8 * g2_epi_warps(DUAL));  // 32-column chunks per warp
     const bool vec_al = (((uintptr_t)p.s1 | (uintptr_t)p.t1 | (uintptr_t)p.s2 | (uintptr_t)p.t2 | (uintptr_t)p.slope) & 15) == 0;
-    int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    // Fused GroupNorm statistics: a thread's (sum, sum of squares) run in fp64 across the CTA's tiles for as long as the
+    // (segment, group) they belong to stays the same, and reach the global accumulators only when it changes (chunked schedule:
+    // once or twice per CTA instead of once per warp and tile -- the atomics on one item's two addresses were what bound the thin
+    // GroupNorm layers).  per_x segments: per thread; per-item segments: warp-reduced first.
+    double gsd = 0.0, gssd = 0.0;
+    int gkey = -1;   // seg * G + group of the running sums (host: segments * G < 2^31)
+    auto gn_flush = [&]() {
+      if (gkey >= 0) {
+        double* dst = p.gn_acc + (size_t)gkey * 2;
+        if (p.gn_per_x) {
+          if (gsd != 0.0 || gssd != 0.0) { atomicAdd(dst, gsd); atomicAdd(dst + 1, gssd); }
+        } else {
+          double ws = gsd, wss = gssd;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            ws += __shfl_xor_sync(0xffffffffu, ws, o);
+            wss += __shfl_xor_sync(0xffffffffu, wss, o);
+          }
+          if (lane == 0) { atomicAdd(dst, ws); atomicAdd(dst + 1, wss); }
+        }
+      }
+      gsd = 0.0; gssd = 0.0;
+    };
+    for (int local = 0; local < my_tiles; ++local) {
+      const int tile = tile_at(local);
       const int b = tile / tiles_per_batch;
       const int r = tile % tiles_per_batch;
       const int mt = r / p.n_tiles;
@@ -593,8 +628,8 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int rt = q * 32 + lane;  // row inside the tile = TMEM lane
-      const int px = (mt % p.tiles_x) * p.xt + rt % p.xt;
-      const int py = (mt / p.tiles_x) * p.yt + rt / p.xt;
+      const int px = tile_x(mt) * p.xt + rt % p.xt;
+      const int py = tile_y(mt) * p.yt + rt / p.xt;
       const uint32_t trow = tmem_base + (DUAL ? 0 : as * BN) + ((uint32_t)(q * 32) << 16);
       const bool row_ok = px < p.X && py < p.Y;
       float* cf = p.Cf ? p.Cf + (size_t)b * p.bscf + (size_t)py * p.ldcy_f + (size_t)px * p.ldcf : nullptr;
@@ -605,32 +640,21 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
       row.cf_vec = cf && ((p.ldcf & 3) == 0) && ((p.bscf & 3) == 0) && ((p.ldcy_f & 3) == 0) && (((uintptr_t)p.Cf & 15) == 0);
       row.cs_vec = chi && ((p.ldcs & 7) == 0) && ((p.bscs & 7) == 0) && ((p.ldcy_s & 7) == 0) && (((uintptr_t)p.Chi & 15) == 0) &&
                    (((uintptr_t)p.Clo & 15) == 0);
-      float gs = 0.0f, gss = 0.0f;  // running GroupNorm sums of this thread's row for the current group
-      int gcur = -1;
-      auto gn_flush = [&]() {
-        if (gcur < 0) return;
-        const size_t seg = p.gn_per_x ? (size_t)b * p.X + px : (size_t)b;
-        double* dst = p.gn_acc + (seg * p.gn_G + gcur) * 2;
-        if (p.gn_per_x) {
-          if (row_ok) { atomicAdd(dst, (double)gs); atomicAdd(dst + 1, (double)gss); }
-        } else {
-          const float ws = warp_sum(row_ok ? gs : 0.0f), wss = warp_sum(row_ok ? gss : 0.0f);
-          if (lane == 0) { atomicAdd(dst, (double)ws); atomicAdd(dst + 1, (double)wss); }
-        }
-        gs = 0.0f; gss = 0.0f;
-      };
+      const int gseg = p.gn_per_x ? b * p.X + min(px, p.X - 1) : b;
 #pragma unroll 1
       for (int cc = 0; cc < CH; ++cc) {
         const int c = half * CH + cc;
         const int nb = n0 + c * 32;
-        if (!DUAL && p.gn_acc) {  // chunk-uniform (hence warp-uniform) group id; flush when it changes
-          const int gnew = nb < p.N ? ((nb % p.gn_cmod) / p.gn_cpg) : gcur;
-          if (gnew != gcur) { gn_flush(); gcur = gnew; }
+        float gs = 0.0f, gss = 0.0f;  // this chunk's sums of the thread's row
+        if (GN && nb < p.N) {  // the group id is chunk-uniform, the segment tile-uniform (per_x: per thread, changing for all lanes at once)
+          const int knew = gseg * p.gn_G + (nb % p.gn_cmod) / p.gn_cpg;
+          if (knew != gkey) { gn_flush(); gkey = knew; }
         }
         if (nb >= p.N) continue;  // warp-uniform: nothing to drain
         const bool generic = (nb + 32 > p.N) || (DUAL && p.act != ACT_PRELU);  // warp-uniform
         if (generic) {
           g2_chunk_ragged<DUAL>(trow + c * 32, trow + BN + c * 32, nb, p, row, row_ok, gs, gss);
+          if (GN) { gsd += (double)gs; gssd += (double)gss; }
           continue;
         }
         uint32_t v[32];
@@ -641,8 +665,9 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
         if (!row_ok) continue;
         if (DUAL) {
           g2_chunk<ACT_PRELU, true, false>(v, v2, nb, p, row, gs, gss);
-        } else if (p.gn_acc) {
+        } else if (GN) {
           g2_chunk<ACT_NONE, false, true>(v, v2, nb, p, row, gs, gss);
+          gsd += (double)gs; gssd += (double)gss;
         } else {
           switch (p.act) {
             case ACT_TANH: g2_chunk<ACT_TANH, false, false>(v, v2, nb, p, row, gs, gss); break;
@@ -655,11 +680,11 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
           }
         }
       }
-      if (!DUAL && p.gn_acc) gn_flush();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
+    if (GN) gn_flush();
   }
   __syncthreads();
   if (warp == 1) {
@@ -710,6 +735,7 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   if (pr.gn_acc) {
     RFX_REQUIRE(p.gn_cmod % p.gn_G == 0 && (p.gn_G == 1 || p.gn_cpg % 32 == 0), "fused GroupNorm statistics need 32-column aligned groups");
     RFX_REQUIRE(pr.epi.act == ACT_NONE && !pr.dual, "fused GroupNorm statistics are taken on the linear (bias-only) output");
+    RFX_REQUIRE((long long)pr.batch * (pr.gn_per_x ? pr.M : 1) * p.gn_G < (1ll << 31), "fused GroupNorm statistics: too many segments");
   }
   RFX_REQUIRE(pr.W.Kpad >= p.kb_per_tap * p.taps * G2_BK, "packed weight K extent too small for taps * Ktap");
   CUtensorMap mapA, mapW;
@@ -742,17 +768,28 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = total < sms ? total : sms;
   if (pr.max_ctas > 0 && grid > pr.max_ctas) grid = pr.max_ctas;
+  p.chunk = pr.gn_acc ? ceil_div(total, grid) : 0;
   const int smem = p.w_res_bytes + p.stages * p.stage_bytes + 1024 + 256;
   if (pr.dual) {
     RFX_REQUIRE(BN == 256 && pr.N <= 256 * p.n_tiles && pr.taps >= 2, "dual-accumulator mode needs BN = 256 and >= 2 taps");
-    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    gemm2_kernel<256, true><<<grid, g2_threads(true), smem, stream>>>(mapA, mapW, p);
+    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    gemm2_kernel<256, true, false><<<grid, g2_threads(true), smem, stream>>>(mapA, mapW, p);
   } else if (BN == 256) {
-    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    gemm2_kernel<256, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
+    if (pr.gn_acc) {
+      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      gemm2_kernel<256, false, true><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
+    } else {
+      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      gemm2_kernel<256, false, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
+    }
   } else {
-    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    gemm2_kernel<128, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
+    if (pr.gn_acc) {
+      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      gemm2_kernel<128, false, true><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
+    } else {
+      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      gemm2_kernel<128, false, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
+    }
   }
   RFX_CHECK_CUDA(cudaGetLastError());
   return 0;
