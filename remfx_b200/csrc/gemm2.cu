@@ -449,12 +449,17 @@ __device__ __forceinline__ void g2_chunk_ragged(uint32_t taddr, uint32_t taddr2,
 // warp 0 TMA, warp 1 MMA, then the epilogue warps: 16 (8 in DUAL mode, whose second accumulator costs 32 more registers)
 constexpr int g2_epi_warps(bool dual) { return dual ? 8 : 16; }
 constexpr int g2_threads(bool dual) { return 64 + 32 * g2_epi_warps(dual); }
+// TWO = the "two CTAs per SM" plan of thin layers (BN = 128, small K): 8 epilogue warps, at most half the registers and shared
+// memory, 2 x 256 TMEM columns.  Those layers are bound by the latency of their per-tile chain (load -> MMA -> drain), not by
+// any throughput; a second resident CTA doubles the tiles in flight.
+constexpr int g2_epi_warps2(bool dual, bool two) { return (dual || two) ? 8 : 16; }
+constexpr int g2_threads2(bool dual, bool two) { return 64 + 32 * g2_epi_warps2(dual, two); }
 
 constexpr int G2_MAX_STAGES = 6;
 
-template <int BN, bool DUAL, bool GN>   // GN: fused GroupNorm statistics (chunked tile schedule, running fp64 sums) -- its own instantiation so
+template <int BN, bool DUAL, bool GN, bool TWO>   // GN: fused GroupNorm statistics (chunked tile schedule, running fp64 sums) -- its own instantiation so
                                         // that the plain kernels carry none of that state in their register-tight epilogue
-__global__ void __launch_bounds__(g2_threads(DUAL), 1)
+__global__ void __launch_bounds__(g2_threads2(DUAL, TWO), TWO ? 2 : 1)
     gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const G2Params p) {
   const int STAGES = p.stages;
   const uint32_t STAGE_BYTES = (uint32_t)p.stage_bytes;
@@ -493,7 +498,7 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
     mbar_init(wfull_bar, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], g2_epi_warps(DUAL));  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], g2_epi_warps2(DUAL, TWO));  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -592,7 +597,7 @@ __global__ void __launch_bounds__(g2_threads(DUAL), 1)
     // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // which slice of the tile's columns this warp drains
-    constexpr int CH = BN / (8 * g2_epi_warps(DUAL));  // 32-column chunks per warp
+    constexpr int CH = BN / (8 * g2_epi_warps2(DUAL, TWO));  // 32-column chunks per warp
     const bool vec_al = (((uintptr_t)p.s1 | (uintptr_t)p.t1 | (uintptr_t)p.s2 | (uintptr_t)p.t2 | (uintptr_t)p.slope) & 15) == 0;
     // Fused GroupNorm statistics: a thread's (sum, sum of squares) run in fp64 across the CTA's tiles for as long as the
     // (segment, group) they belong to stays the same, and reach the global accumulators only when it changes (chunked schedule:
@@ -768,27 +773,47 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = total < sms ? total : sms;
   if (pr.max_ctas > 0 && grid > pr.max_ctas) grid = pr.max_ctas;
+  // thin layers (resident W, at most three k-blocks per tile, many tiles): two CTAs per SM, each with half the shared memory
+  bool two = false;
+  {
+    static const bool allow = [] { const char* e = getenv("RFX_G2_TWO"); return !(e && atoi(e) == 0); }();
+    constexpr int HALF_CAP = (227 * 1024) / 2 - 1024 - 1280;   // per-CTA dynamic shared memory when two CTAs share an SM
+    if (allow && BN == 128 && !pr.dual && resident && pr.max_ctas == 0 && KB <= 3 && total >= 4 * sms &&
+        p.w_res_bytes + 2 * p.stage_bytes <= HALF_CAP) {
+      two = true;
+      p.stages = std::min(4, (HALF_CAP - p.w_res_bytes) / p.stage_bytes);
+      grid = std::min(total, 2 * sms);
+    }
+  }
   p.chunk = pr.gn_acc ? ceil_div(total, grid) : 0;
   const int smem = p.w_res_bytes + p.stages * p.stage_bytes + 1024 + 256;
   if (pr.dual) {
     RFX_REQUIRE(BN == 256 && pr.N <= 256 * p.n_tiles && pr.taps >= 2, "dual-accumulator mode needs BN = 256 and >= 2 taps");
-    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    gemm2_kernel<256, true, false><<<grid, g2_threads(true), smem, stream>>>(mapA, mapW, p);
+    RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    gemm2_kernel<256, true, false, false><<<grid, g2_threads(true), smem, stream>>>(mapA, mapW, p);
   } else if (BN == 256) {
     if (pr.gn_acc) {
-      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      gemm2_kernel<256, false, true><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
+      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      gemm2_kernel<256, false, true, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
     } else {
-      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      gemm2_kernel<256, false, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
+      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      gemm2_kernel<256, false, false, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
+    }
+  } else if (two) {
+    if (pr.gn_acc) {
+      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      gemm2_kernel<128, false, true, true><<<grid, g2_threads2(false, true), smem, stream>>>(mapA, mapW, p);
+    } else {
+      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      gemm2_kernel<128, false, false, true><<<grid, g2_threads2(false, true), smem, stream>>>(mapA, mapW, p);
     }
   } else {
     if (pr.gn_acc) {
-      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      gemm2_kernel<128, false, true><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
+      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      gemm2_kernel<128, false, true, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
     } else {
-      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      gemm2_kernel<128, false, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
+      RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<128, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      gemm2_kernel<128, false, false, false><<<grid, g2_threads(false), smem, stream>>>(mapA, mapW, p);
     }
   }
   RFX_CHECK_CUDA(cudaGetLastError());
