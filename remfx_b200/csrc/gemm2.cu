@@ -178,6 +178,7 @@ struct G2Params {
   const float* t2;
   const float* slope;  // ACT_PRELU: per-column negative slope
   int act;
+  int cst;       // 1: fp32 rows are staged through shared memory (GN instantiations; see G2Row)
   int cf_accum;  // 1: the fp32 output accumulates (Cf += v; ACT_NONE without GLU only) -- the input-gradient GEMMs of residual branches
   // fused GroupNorm statistics of the (post-bias) output: accum[(seg * G + g) * 2 + {0,1}] += (sum, sum of squares)
   double* gn_acc;
@@ -215,7 +216,16 @@ struct G2Row {  // where this thread's output row lives
   __nv_bfloat16* chi;
   __nv_bfloat16* clo;
   bool cf_vec, cs_vec, vec_al;
+  // GN instantiations only: fp32 rows leave through a per-warp staging block in shared memory so that every store instruction
+  // writes whole 128-byte lines (a thread owns a ROW: written directly, one instruction scatters 16-byte pieces over 32 lines and
+  // the L1 / L2 request rate -- not HBM -- bounds the thin layers).  cst = the warp's [32][33] floats, rowp = its 32 row pointers
+  // (null for rows outside the output), lane = this thread's row.  Null cst = direct stores.
+  float* cst;
+  float* const* rowp;
+  int lane;
+  bool ok;
 };
+constexpr int G2_CST_WARP_BYTES = 32 * 33 * 4 + 32 * 8;  // staging block + row pointers of one epilogue warp
 
 // One full 32-column chunk [nb, nb + 32) of this thread's row, activation known at compile time: straight-line code, so the
 // compiler hoists every scale / bias load to the top and the instruction cache only holds the variant in use.
@@ -270,7 +280,7 @@ __device__ __forceinline__ void g2_chunk(const uint32_t (&v)[32], const uint32_t
 #pragma unroll
     for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(v2[i]);
   }
-  if (GN) {
+  if (GN && r.ok) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) { gs += o[i]; gss = fmaf(o[i], o[i], gss); }
   }
@@ -313,7 +323,25 @@ __device__ __forceinline__ void g2_chunk(const uint32_t (&v)[32], const uint32_t
     }
     return;
   }
-  if (r.cf) {
+  if (GN && r.cst) {  // warp-collective: every lane stages its row (16-byte pieces XOR-swizzled by the row: conflict-free both ways)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(r.cst + r.lane * 32 + ((j ^ (r.lane & 7)) << 2)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    __syncwarp();
+    const int pc = r.lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {  // one instruction = 4 rows x 128 contiguous bytes
+      const int row = it * 4 + (r.lane >> 3);
+      float* rp = r.rowp[row];
+      if (rp) {
+        float4 q = *reinterpret_cast<const float4*>(r.cst + row * 32 + ((pc ^ (row & 7)) << 2));
+        float4* dst = reinterpret_cast<float4*>(rp + nb + 4 * pc);
+        if (p.cf_accum) { const float4 old = *dst; q.x += old.x; q.y += old.y; q.z += old.z; q.w += old.w; }
+        *dst = q;
+      }
+    }
+    __syncwarp();
+  } else if (r.cf) {
     if (ACT == ACT_NONE && p.cf_accum) {
       if (r.cf_vec) {
 #pragma unroll
@@ -362,17 +390,18 @@ __device__ __forceinline__ void g2_chunk(const uint32_t (&v)[32], const uint32_t
 
 // Ragged chunks (N % 32 != 0, or an activation without a specialised path): groups of 8 columns with per-column bounds
 // predicates and run-time switches.  Warp-collective (tcgen05.ld): every lane must call it; only lanes with row_ok store.
-template <bool DUAL>
+template <bool DUAL, bool GN>
 __device__ __forceinline__ void g2_chunk_ragged(uint32_t taddr, uint32_t taddr2, int nb, const G2Params& p, const G2Row& r, bool row_ok, float& gs,
                                              float& gss) {
   const int ncol = min(32, p.N - nb);
+  const bool staged = GN && r.cst && p.act != ACT_GLU_PAIR;  // warp-uniform
 #pragma unroll 1
   for (int g8 = 0; g8 < ncol; g8 += 8) {
     uint32_t a1[8], a2[8];
     tmem_ld8(taddr + g8, a1);
     if (DUAL) tmem_ld8(taddr2 + g8, a2);
     tmem_ld_wait();
-    if (!row_ok) continue;
+    if (!row_ok && !staged) continue;
     const int n8 = nb + g8;
     float o[8];
 #pragma unroll
@@ -409,10 +438,16 @@ __device__ __forceinline__ void g2_chunk_ragged(uint32_t taddr, uint32_t taddr2,
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] += __uint_as_float(a2[i]);
     }
-    if (p.gn_acc) {
+    if (p.gn_acc && row_ok) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (n8 + i < p.N) { gs += o[i]; gss = fmaf(o[i], o[i], gss); }
+    }
+    if (staged) {  // [32 rows][33]: scalar writes by row and the row-major read-out below are both conflict-free
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (g8 + i < ncol) r.cst[r.lane * 33 + g8 + i] = o[i];
+      continue;
     }
     if (p.act == ACT_GLU_PAIR) {
 #pragma unroll
@@ -443,6 +478,19 @@ __device__ __forceinline__ void g2_chunk_ragged(uint32_t taddr, uint32_t taddr2,
         }
       }
     }
+  }
+  if (staged) {  // the warp's 32 x ncol block in row-major order: consecutive lanes write consecutive addresses
+    __syncwarp();
+    const int total = 32 * ncol;
+    for (int idx = r.lane; idx < total; idx += 32) {
+      const int row = idx / ncol, col = idx - row * ncol;
+      float* rp = r.rowp[row];
+      if (rp) {
+        const float v = r.cst[row * 33 + col];
+        rp[nb + col] = p.cf_accum ? rp[nb + col] + v : v;
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -642,6 +690,16 @@ __global__ void __launch_bounds__(g2_threads2(DUAL, TWO), TWO ? 2 : 1)
       __nv_bfloat16* clo = p.Clo ? p.Clo + (size_t)b * p.bscs + (size_t)py * p.ldcy_s + (size_t)px * p.ldcs : nullptr;
       G2Row row;
       row.cf = cf; row.chi = chi; row.clo = clo; row.vec_al = vec_al;
+      row.lane = lane; row.ok = row_ok; row.cst = nullptr; row.rowp = nullptr;
+      if (GN && p.cst) {
+        uint8_t* blk = ring + STAGES * STAGE_BYTES + 256 + (size_t)(warp - 2) * G2_CST_WARP_BYTES;
+        row.cst = reinterpret_cast<float*>(blk);
+        float** rp = reinterpret_cast<float**>(blk + 32 * 33 * 4);
+        __syncwarp();   // the previous tile's read-out is complete
+        rp[lane] = row_ok ? cf : nullptr;
+        __syncwarp();
+        row.rowp = rp;
+      }
       row.cf_vec = cf && ((p.ldcf & 3) == 0) && ((p.bscf & 3) == 0) && ((p.ldcy_f & 3) == 0) && (((uintptr_t)p.Cf & 15) == 0);
       row.cs_vec = chi && ((p.ldcs & 7) == 0) && ((p.bscs & 7) == 0) && ((p.ldcy_s & 7) == 0) && (((uintptr_t)p.Chi & 15) == 0) &&
                    (((uintptr_t)p.Clo & 15) == 0);
@@ -658,7 +716,7 @@ __global__ void __launch_bounds__(g2_threads2(DUAL, TWO), TWO ? 2 : 1)
         if (nb >= p.N) continue;  // warp-uniform: nothing to drain
         const bool generic = (nb + 32 > p.N) || (DUAL && p.act != ACT_PRELU);  // warp-uniform
         if (generic) {
-          g2_chunk_ragged<DUAL>(trow + c * 32, trow + BN + c * 32, nb, p, row, row_ok, gs, gss);
+          g2_chunk_ragged<DUAL, GN>(trow + c * 32, trow + BN + c * 32, nb, p, row, row_ok, gs, gss);
           if (GN) { gsd += (double)gs; gssd += (double)gss; }
           continue;
         }
@@ -667,7 +725,7 @@ __global__ void __launch_bounds__(g2_threads2(DUAL, TWO), TWO ? 2 : 1)
         uint32_t v2[32];
         if (DUAL) tmem_ld32(trow + BN + c * 32, v2);
         tmem_ld_wait();
-        if (!row_ok) continue;
+        if (!row_ok && !(GN && row.cst)) continue;   // (staged stores are warp-collective: every lane takes part)
         if (DUAL) {
           g2_chunk<ACT_PRELU, true, false>(v, v2, nb, p, row, gs, gss);
         } else if (GN) {
@@ -773,20 +831,36 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = total < sms ? total : sms;
   if (pr.max_ctas > 0 && grid > pr.max_ctas) grid = pr.max_ctas;
-  // thin layers (resident W, at most three k-blocks per tile, many tiles): two CTAs per SM, each with half the shared memory
+  // Plans beyond the default (one CTA per SM, direct stores), both for launches with a resident W:
+  //   two  -- thin layers (at most three k-blocks per tile, many tiles): two CTAs per SM, each with half the shared memory
+  //   cst  -- fp32 rows staged through shared memory (GN instantiations; see G2Row), when the staging block fits beside at least
+  //           two operand stages
+  // Preference: two + cst, one + cst, two, default.
   bool two = false;
+  p.cst = 0;
+  int cst_bytes = 0;
   {
-    static const bool allow = [] { const char* e = getenv("RFX_G2_TWO"); return !(e && atoi(e) == 0); }();
+    static const bool allow_two = [] { const char* e = getenv("RFX_G2_TWO"); return !(e && atoi(e) == 0); }();
+    static const bool allow_cst = [] { const char* e = getenv("RFX_G2_CST"); return !(e && atoi(e) == 0); }();
     constexpr int HALF_CAP = (227 * 1024) / 2 - 1024 - 1280;   // per-CTA dynamic shared memory when two CTAs share an SM
-    if (allow && BN == 128 && !pr.dual && resident && pr.max_ctas == 0 && KB <= 3 && total >= 4 * sms &&
-        p.w_res_bytes + 2 * p.stage_bytes <= HALF_CAP) {
+    const bool aligned = (pr.ldcf % 4 == 0) && (pr.bscf % 4 == 0) && (pr.ldcf_y % 4 == 0) && (((uintptr_t)pr.Cf & 15) == 0);
+    const bool can_two = allow_two && BN == 128 && !pr.dual && resident && pr.max_ctas == 0 && KB <= 3 && total >= 4 * sms;
+    const bool can_cst = allow_cst && pr.gn_acc && pr.Cf && !pr.Chi && !pr.dual && aligned && resident && pr.epi.act != ACT_GLU_PAIR;
+    const int need2 = g2_epi_warps2(false, true) * G2_CST_WARP_BYTES, need1 = g2_epi_warps2(false, false) * G2_CST_WARP_BYTES;
+    if (can_two && can_cst && p.w_res_bytes + 2 * p.stage_bytes + need2 <= HALF_CAP) {
+      two = true; p.cst = 1; cst_bytes = need2;
+      p.stages = std::min(4, (HALF_CAP - p.w_res_bytes - need2) / p.stage_bytes);
+    } else if (can_cst && p.w_res_bytes + 2 * p.stage_bytes + need1 <= SMEM_CAP) {
+      p.cst = 1; cst_bytes = need1;
+      p.stages = std::min(p.stages, (SMEM_CAP - p.w_res_bytes - need1) / p.stage_bytes);
+    } else if (can_two && p.w_res_bytes + 2 * p.stage_bytes <= HALF_CAP) {
       two = true;
       p.stages = std::min(4, (HALF_CAP - p.w_res_bytes) / p.stage_bytes);
-      grid = std::min(total, 2 * sms);
     }
+    if (two) grid = std::min(total, 2 * sms);
   }
   p.chunk = pr.gn_acc ? ceil_div(total, grid) : 0;
-  const int smem = p.w_res_bytes + p.stages * p.stage_bytes + 1024 + 256;
+  const int smem = p.w_res_bytes + p.stages * p.stage_bytes + 1024 + 256 + cst_bytes;
   if (pr.dual) {
     RFX_REQUIRE(BN == 256 && pr.N <= 256 * p.n_tiles && pr.taps >= 2, "dual-accumulator mode needs BN = 256 and >= 2 taps");
     RFX_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel<256, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

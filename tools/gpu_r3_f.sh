@@ -1,0 +1,7 @@
+#!/bin/bash
+# gemm2: fp32 rows staged through shared memory (whole-line stores) in the GroupNorm-statistics instantiations
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_hdemucs.py tests/test_gpu_hdemucs_backward.py tests/test_gpu_gemm_lstm.py -x -q > gpurun_out/r3f_tests.log 2>&1; echo "tests exit=$?"; tail -3 gpurun_out/r3f_tests.log
+timeout 300 python tools/hd_bench.py 1 16 32 2>&1 | grep HDemucs | tee gpurun_out/r3f_hd_fwd.txt
+RFX_G2_CST=0 timeout 300 python tools/hd_bench.py 32 2>&1 | grep HDemucs | tee gpurun_out/r3f_hd_fwd_nocst.txt
+timeout 600 python tools/hd_train_bench.py --batch 16 --steps 4 --warmup 2 > gpurun_out/r3f_hd_train.json 2> gpurun_out/r3f_hd.err; echo "hd train exit=$?"; cut -c1-420 gpurun_out/r3f_hd_train.json
