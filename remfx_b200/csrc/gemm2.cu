@@ -538,6 +538,12 @@ __global__ void __launch_bounds__(g2_threads2(DUAL, TWO), TWO ? 2 : 1)
   auto tile_x = [&](int mt) { return GN ? mt / tiles_y : mt % p.tiles_x; };
   auto tile_y = [&](int mt) { return GN ? mt % tiles_y : mt / p.tiles_x; };
 
+  // Epilogue warps whose column slice lies beyond N in every tile (single n-tile launches with N < BN) have nothing to drain: they
+  // stay out of the tile loop instead of spinning on the accumulator barriers beside the warps that work.
+  constexpr int EPI_CH = BN / (8 * g2_epi_warps2(DUAL, TWO));                      // 32-column chunks per epilogue warp
+  const int epi_slices = (DUAL || p.n_tiles > 1) ? g2_epi_warps2(DUAL, TWO) / 4    // column slices (of EPI_CH chunks) with work
+                                                 : min(g2_epi_warps2(DUAL, TWO) / 4, (p.N + EPI_CH * 32 - 1) / (EPI_CH * 32));
+  const int epi_active = 4 * epi_slices;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -546,7 +552,7 @@ __global__ void __launch_bounds__(g2_threads2(DUAL, TWO), TWO ? 2 : 1)
     mbar_init(wfull_bar, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], g2_epi_warps2(DUAL, TWO));  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], epi_active);  // one arrive per epilogue warp that has columns to drain
     }
     mbar_fence_init();
   }
@@ -670,7 +676,7 @@ __global__ void __launch_bounds__(g2_threads2(DUAL, TWO), TWO ? 2 : 1)
       }
       gsd = 0.0; gssd = 0.0;
     };
-    for (int local = 0; local < my_tiles; ++local) {
+    for (int local = 0; local < (half < epi_slices ? my_tiles : 0); ++local) {
       const int tile = tile_at(local);
       const int b = tile / tiles_per_batch;
       const int r = tile % tiles_per_batch;
@@ -678,7 +684,7 @@ __global__ void __launch_bounds__(g2_threads2(DUAL, TWO), TWO ? 2 : 1)
       const int n0 = (r % p.n_tiles) * BN;
       const int as = DUAL ? 0 : (local & 1);
       const int aphase = DUAL ? (local & 1) : ((local >> 1) & 1);
-      mbar_wait(&tfull_bar[as], aphase);
+      mbar_wait_backoff(&tfull_bar[as], aphase);   // (the drain is not latency-critical: a sleeping warp leaves the issue slots to the others)
       tc_fence_after();
       const int rt = q * 32 + lane;  // row inside the tile = TMEM lane
       const int px = tile_x(mt) * p.xt + rt % p.xt;
