@@ -326,6 +326,10 @@ int rfx_hdemucs_backward(rfx_hdemucs_t* h, const float* x, const float* dout, in
 /* Weight-gradient contraction of the Hybrid-Demucs backward, process-wide: 0 = tcgen05 with MN-major TMA-staged operands (default),
  * 1 = the mma.sync tile variants (cross-check in tests). */
 int rfx_hdemucs_set_wgrad_impl(int impl);
+/* on != 0: the caller guarantees that the gradient buffers of the following rfx_hdemucs_backward calls are already zero (views of
+ * one freshly zeroed flat bucket -- what remfx_b200.optim.FlatBucket hands out), so the backward skips its per-parameter memsets.
+ * Replaces nothing in the reference: torch autograd allocates each parameter gradient itself (remfx/models.py:217-220). */
+int rfx_hdemucs_set_grads_prezeroed(rfx_hdemucs_t* h, int on);
 int rfx_hdemucs_grad_tap(rfx_hdemucs_t* h, const char* name, float* dst, int64_t capacity, int* dims, void* stream);
 int rfx_hdemucs_inject_grad(rfx_hdemucs_t* h, const char* name, const float* grad);
 

@@ -119,6 +119,7 @@ _SIGNATURES = {
     "rfx_hdemucs_backward": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.c_int,
                                        C.c_void_p, C.c_size_t, C.c_void_p]),
     "rfx_hdemucs_set_wgrad_impl": (C.c_int, [C.c_int]),
+    "rfx_hdemucs_set_grads_prezeroed": (C.c_int, [C.c_void_p, C.c_int]),
     "rfx_hdemucs_grad_tap": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int64, C.POINTER(C.c_int), C.c_void_p]),
     "rfx_hdemucs_inject_grad": (C.c_int, [C.c_void_p, C.c_char_p, _f32p]),
     "rfx_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),

@@ -135,6 +135,7 @@ struct rfx_hdemucs {
   cudaEvent_t ev_branch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // the backward builds the transposed weight packs of its input-gradient GEMMs on a third stream, ahead of the reverse replay
   cudaStream_t s_prep = nullptr;
+  bool grads_prezeroed = false;  // rfx_hdemucs_set_grads_prezeroed: the caller hands over gradient buffers that are already zero
   std::vector<cudaEvent_t> ev_pack;
   ~rfx_hdemucs() {
     if (s_time) cudaStreamDestroy(s_time);

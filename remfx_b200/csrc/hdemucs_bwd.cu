@@ -551,7 +551,7 @@ struct BRunner {
       for (auto& kv : grads) {  // every parameter gradient starts from zero (kernels accumulate or overwrite)
         auto pit = h->params.find(kv.first);
         if (pit == h->params.end()) { fail("gradient buffer for unknown parameter '" + kv.first + "'"); return; }
-        if (cudaMemsetAsync(kv.second, 0, pit->second.n * 4, s) != cudaSuccess) { fail("memset"); return; }
+        if (!h->grads_prezeroed && cudaMemsetAsync(kv.second, 0, pit->second.n * 4, s) != cudaSuccess) { fail("memset"); return; }
       }
     }
     prepare_packs();
@@ -934,6 +934,14 @@ int rfx_hdemucs_backward(rfx_hdemucs_t* h, const float* x, const float* dout, in
   int rc = hd_run_backward(h, x, dout, B, T, gmap, reinterpret_cast<uint8_t*>(workspace), h->fwd_bytes, false, (cudaStream_t)stream, &used);
   if (!rc && used > workspace_bytes) { set_error("hdemucs backward overran its workspace"); return 1; }
   return rc;
+}
+
+/* The caller guarantees that every gradient buffer handed to the following rfx_hdemucs_backward calls is already zero (e.g. views
+ * of one freshly zeroed flat buffer): the backward then skips its ~400 per-parameter memsets. */
+int rfx_hdemucs_set_grads_prezeroed(rfx_hdemucs_t* h, int on) {
+  RFX_REQUIRE(h != nullptr, "null handle");
+  h->grads_prezeroed = on != 0;
+  return 0;
 }
 
 /* Weight-gradient kernel selector, process-wide: 0 = tcgen05 (default), 1 = the mma.sync tile variants (cross-check). */

@@ -341,7 +341,8 @@ class _UmxTrainFn(torch.autograd.Function):
             # no _sync here: the running statistics moved after the forward, which would re-upload the parameters and drop the
             # tape; the handle still holds the weights the forward used
             h = owner._handle
-            grads = [torch.empty_like(p, memory_format=torch.contiguous_format) for p in params]
+            from .optim import alloc_param_grads
+            grads, _ = alloc_param_grads(params)
             n = len(names)
             keys = (C.c_char_p * n)(*[k.encode() for k in names])
             ptrs = (C.c_void_p * n)(*[g.data_ptr() for g in grads])
@@ -659,7 +660,8 @@ class _TcnTrainFn(torch.autograd.Function):
         L = _lib.lib()
         with torch.cuda.device(x.device):
             h = owner._sync(x.device)  # parameters unchanged since the forward: a no-op stamp check
-            grads = [torch.empty_like(p, memory_format=torch.contiguous_format) for p in params]
+            from .optim import alloc_param_grads
+            grads, _ = alloc_param_grads(params)
             n = len(names)
             keys = (C.c_char_p * n)(*[k.encode() for k in names])
             ptrs = (C.c_void_p * n)(*[g.data_ptr() for g in grads])
@@ -864,7 +866,9 @@ class _HDemucsTrainFn(torch.autograd.Function):
         L = _lib.lib()
         with torch.cuda.device(x.device):
             h = owner._sync(x.device)  # parameters unchanged since the forward: a no-op stamp check
-            grads = [torch.empty_like(p, memory_format=torch.contiguous_format) for p in params]
+            from .optim import alloc_param_grads
+            grads, zeroed = alloc_param_grads(params)   # views of one zeroed flat bucket when a FusedAdamW owns the parameters
+            _lib.check(L.rfx_hdemucs_set_grads_prezeroed(h, 1 if zeroed else 0), "rfx_hdemucs_set_grads_prezeroed")
             n = len(names)
             keys = (C.c_char_p * n)(*[k.encode() for k in names])
             ptrs = (C.c_void_p * n)(*[g.data_ptr() for g in grads])

@@ -12,7 +12,8 @@ drive it unchanged.  The kernels have no CPU fallback: `step()` on CPU tensors r
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional
+import weakref
+from typing import Iterable, List, Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -53,6 +54,18 @@ class FlatBucket:
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
                 if old_grad is not None:
                     p.grad.copy_(old_grad)
+        # gradient sink (alloc_param_grads below): a network's hand-written backward can ask for its parameter gradients as views
+        # of ONE zeroed flat buffer laid out like this bucket; collect_grads() then adopts that buffer instead of copying
+        self._incoming: Optional[Tensor] = None
+        ref = weakref.ref(self)
+        for i, p in enumerate(self.params):
+            p._rfx_sink = (ref, i)
+
+    def sink_alloc(self) -> Tensor:
+        """A zeroed flat gradient buffer with this bucket's layout (one memset for the whole model); remembered until the
+        next collect_grads()."""
+        self._incoming = torch.zeros(self.numel, dtype=torch.float32, device=self.param.device)
+        return self._incoming
 
     def grad_view(self, i: int) -> Tensor:
         p, o = self.params[i], self.offsets[i]
@@ -67,6 +80,26 @@ class FlatBucket:
         accumulates in place), a copy for gradients that were re-created (e.g. after zero_grad(set_to_none=True)).
         Returns the indices of parameters that have NO gradient this step (torch.optim skips those entirely)."""
         missing: List[int] = []
+        inc, self._incoming = self._incoming, None
+        if inc is not None and inc.numel() == self.numel and inc.device == self.grad.device:
+            # fast path: every gradient autograd stored is (still) the view of the sink buffer at this bucket's offset -> the
+            # buffer BECOMES the bucket's gradient storage: no per-parameter accumulate / copy kernels at all
+            base = inc.data_ptr()
+            ok = True
+            for i, p in enumerate(self.params):
+                g = p.grad
+                if g is None:
+                    missing.append(i)
+                elif g.data_ptr() != base + 4 * self.offsets[i] or g.numel() != p.numel() or not g.is_contiguous():
+                    ok = False
+                    break
+            if ok:
+                self.grad = inc
+                with torch.no_grad():
+                    for i in missing:
+                        self.grad_view(i).zero_()
+                return missing
+            missing = []
         with torch.no_grad():
             for i, p in enumerate(self.params):
                 view = self.grad_view(i)
@@ -97,11 +130,46 @@ class FlatBucket:
                 n += 1
         return n
 
-    def zero_grad(self) -> None:
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """Default: gradients stay zeroed views of the bucket (autograd accumulates in place).  set_to_none=True (torch's own
+        default): every `.grad` is dropped, so that autograd STORES the next gradients instead of adding them -- with the
+        gradient sink that makes a step free of per-parameter kernels."""
+        if set_to_none:
+            for p in self.params:
+                p.grad = None
+            return
         self.grad.zero_()
         for i, p in enumerate(self.params):
             if p.grad is None or p.grad.data_ptr() != self.grad_view(i).data_ptr():
                 p.grad = self.grad_view(i)
+
+
+def alloc_param_grads(params: Sequence[Tensor]) -> Tuple[List[Tensor], bool]:
+    """Gradient buffers for a hand-written backward.  When every trainable parameter belongs to one live FlatBucket and holds no
+    gradient yet (zero_grad(set_to_none=True)), they are views of one zeroed flat buffer in the bucket's layout (second value
+    True: the buffers are already zero); otherwise plain uninitialised tensors (False)."""
+    bucket = None
+    usable = True
+    for p in params:
+        if not p.requires_grad:
+            continue
+        sink = getattr(p, "_rfx_sink", None)
+        b = sink[0]() if sink is not None else None
+        if b is None or (bucket is not None and b is not bucket) or p.grad is not None or b.params[sink[1]] is not p:
+            usable = False
+            break
+        bucket = b
+    if not usable or bucket is None:
+        return [torch.empty_like(p, memory_format=torch.contiguous_format) for p in params], False
+    flat = bucket.sink_alloc()
+    grads = []
+    for p in params:
+        if p.requires_grad:
+            o = bucket.offsets[p._rfx_sink[1]]
+            grads.append(flat[o:o + p.numel()].view(p.shape))
+        else:
+            grads.append(torch.zeros_like(p, memory_format=torch.contiguous_format))
+    return grads, True
 
 
 def sync_grads(bucket_grad: Tensor, group=None) -> float:
@@ -148,8 +216,9 @@ class FusedAdamW(torch.optim.Optimizer):
         self._ws = torch.zeros(32, dtype=torch.float64, device=dev)      # [0] = sum of squares
         self.total_norm = torch.zeros(1, dtype=torch.float32, device=dev)  # pre-clip global norm of the last step
 
-    def zero_grad(self, set_to_none: bool = False) -> None:  # gradients stay views of the bucket
-        self.bucket.zero_grad()
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        # default: gradients stay views of the bucket; set_to_none=True: dropped, the gradient sink stores the next ones
+        self.bucket.zero_grad(set_to_none)
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -127,7 +127,7 @@ class RemFX(nn.Module):
                 cfg = self.configure_optimizers()
                 self._optim, self._sched = cfg["optimizer"], cfg["lr_scheduler"]["scheduler"]
             optimizer, scheduler = self._optim, self._sched
-        optimizer.zero_grad()
+        optimizer.zero_grad(set_to_none=True)  # torch's (and Lightning's) default; with FusedAdamW the next gradients land in one flat buffer
         loss = self.training_step(batch, batch_idx)
         loss.backward()
         optimizer.step()  # FusedAdamW: gradient all-reduce (if distributed) + clip-by-global-norm + AdamW

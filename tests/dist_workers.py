@@ -95,8 +95,8 @@ class _BucketSGD:
 
         self.bucket, self.lr, self.group = FlatBucket(params), lr, group
 
-    def zero_grad(self):
-        self.bucket.zero_grad()
+    def zero_grad(self, set_to_none: bool = False):
+        self.bucket.zero_grad(set_to_none)
 
     def step(self):
         from remfx_b200.optim import sync_grads

@@ -7,7 +7,7 @@ import torch
 import torch.multiprocessing as mp
 
 from remfx_b200._lib import RfxError
-from remfx_b200.optim import FlatBucket, FusedAdamW, configure_optimizers, multistep_lr
+from remfx_b200.optim import FlatBucket, FusedAdamW, alloc_param_grads, configure_optimizers, multistep_lr
 from dist_workers import _gloo_optim_worker
 
 
@@ -43,6 +43,66 @@ def test_flat_bucket_aliases_params_and_grads():
         assert torch.equal(b.grad_view(i), w) and p.grad.data_ptr() == b.grad_view(i).data_ptr()
     b.zero_grad()
     assert float(b.grad.abs().sum()) == 0
+
+
+class _SinkFn(torch.autograd.Function):
+    """A hand-written backward in the style of the network wrappers: gradients written into buffers from alloc_param_grads."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        ctx.save_for_backward(x, *params)
+        return sum((p * p).sum() for p in params) + 0.0 * x.sum()
+
+    @staticmethod
+    def backward(ctx, d):
+        x, *params = ctx.saved_tensors
+        grads, zeroed = alloc_param_grads(params)
+        _SinkFn.zeroed = zeroed
+        for g, p in zip(grads, params):
+            if not zeroed:
+                g.zero_()
+            g.add_(2.0 * p.detach() * d)
+        return (None, *[g if p.requires_grad else None for g, p in zip(grads, params)])
+
+
+def test_gradient_sink_is_adopted_without_copies():
+    net = _net()
+    ps = list(net.parameters())
+    b = FlatBucket(ps)
+    x = torch.ones(3)
+    # (1) gradients dropped -> one flat zeroed buffer in the bucket's layout, stored by autograd as is, adopted by collect_grads
+    b.zero_grad(set_to_none=True)
+    assert all(p.grad is None for p in ps)
+    _SinkFn.apply(x, *ps).backward()
+    assert _SinkFn.zeroed and b._incoming is not None
+    flat = b._incoming
+    for p, o in zip(ps, b.offsets):
+        assert p.grad.data_ptr() == flat.data_ptr() + 4 * o       # autograd kept the view (no clone, no accumulate kernel)
+    assert b.collect_grads() == [] and b.grad.data_ptr() == flat.data_ptr()
+    for i, p in enumerate(ps):
+        assert torch.equal(b.grad_view(i), 2.0 * p.detach()) and p.grad.data_ptr() == b.grad_view(i).data_ptr()
+    mask = torch.ones(b.numel, dtype=torch.bool)
+    for p, o in zip(ps, b.offsets):
+        mask[o:o + p.numel()] = False
+    assert float(b.grad[mask].abs().sum()) == 0                   # padding stays zero: whole-bucket kernels remain safe
+    # (2) gradients kept as bucket views (the default zero_grad): no sink, autograd accumulates in place as before
+    b.zero_grad()
+    _SinkFn.apply(x, *ps).backward()
+    assert not _SinkFn.zeroed and b.collect_grads() == []
+    for i, p in enumerate(ps):
+        assert torch.equal(b.grad_view(i), 2.0 * p.detach())
+    # (3) a parameter without a gradient this step is reported missing and its slice is zero; a frozen one is skipped
+    b.zero_grad(set_to_none=True)
+    _SinkFn.apply(x, *ps).backward()
+    ps[1].grad = None
+    assert b.collect_grads() == [1] and float(b.grad_view(1).abs().sum()) == 0
+    # (4) accumulation over two backward calls falls back to the copy path and still sums
+    b.zero_grad(set_to_none=True)
+    _SinkFn.apply(x, *ps).backward()
+    _SinkFn.apply(x, *ps).backward()
+    assert b.collect_grads() == []
+    for i, p in enumerate(ps):
+        assert torch.allclose(b.grad_view(i), 4.0 * p.detach())
 
 
 def test_multistep_lr_matches_torch_schedule():

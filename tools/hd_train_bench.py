@@ -45,7 +45,7 @@ def main():
     torch.cuda.reset_peak_memory_stats()
     for it in range(a.warmup + a.steps):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        opt.zero_grad()
+        opt.zero_grad(set_to_none=True)
         ev[0].record()
         out = m._sample_train(x)
         ev[1].record()

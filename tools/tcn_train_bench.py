@@ -54,7 +54,7 @@ def main():
     losses = []
     for it in range(a.warmup + a.steps):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        opt.zero_grad()
+        opt.zero_grad(set_to_none=True)
         ev[0].record()
         out = m._sample_train(x)
         ev[1].record()
@@ -112,7 +112,7 @@ def cpu_baseline(a):
     times, losses = [], []
     for _ in range(max(1, min(a.steps, 3))):
         t0 = time.perf_counter()
-        opt.zero_grad()
+        opt.zero_grad(set_to_none=True)
         loss, _ = otcn.forward((x, t), sd)
         loss.backward()
         torch.nn.utils.clip_grad_norm_(params, 10.0)
