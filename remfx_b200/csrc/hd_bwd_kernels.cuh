@@ -783,6 +783,109 @@ __global__ void __launch_bounds__(192, 1) hd_wgrad_tc_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+// Narrow layers (N <= 128 output-gradient channels, K <= 64 input channels: the 48 -> 96 3x3 / k = 3 convs and DConv's 12 ... 48 channel
+// convs at full resolution).  The kernel above is bound by shared-memory fill there: one CTA per tap re-loads the output-gradient
+// boxes for every tap and the M = 128 MMA needs a second, all-zero activation box (a 9-tap 48 -> 96 conv: 288 KB per 32-pixel tile).
+// Here the roles are swapped -- M = n (the two output-gradient boxes, loaded ONCE per pixel tile), N = ceil16(K) input channels (one
+// activation box per tap) -- and the accumulators of ALL taps sit side by side in tensor memory (taps * kcols <= 512 columns), so one
+// CTA = (pixel chunk, item) and a pixel tile costs (2 + taps) boxes: 88 KB for the 9-tap conv.  Same maps, same staging layout
+// dW[n][tap][k] as above (thread = TMEM lane = n).
+// ------------------------------------------------------------------------------------------------
+constexpr int HF_MAX_STAGE_BOXES = 2 + 16;
+__global__ void __launch_bounds__(192, 1) hd_wgrad_tc_fused_kernel(const __grid_constant__ HtMap mapG, const __grid_constant__ HtMap mapA, const HtParams p,
+                                                                    int stages, int kcols, int tmem_cols) {
+  extern __shared__ uint8_t hf_smem_raw[];
+  const uint32_t raw = smem_u32(hf_smem_raw);
+  uint8_t* smem = hf_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  const uint32_t stage_bytes = (uint32_t)(2 + p.taps) * HT_BOX;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + 4;
+  uint64_t* tfull_bar = empty_bar + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int k_eff = (p.K + 15) & ~15;   // MMA N
+  const int t_begin = chunk * p.tchunk, t_end = min(p.ptiles, t_begin + p.tchunk);
+  const int iters = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, (uint32_t)tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        const int pt = t_begin + it;
+        const int x0 = (pt % p.tiles_x) * p.bx, y0 = (pt / p.tiles_x) * p.by;
+        for (int cb = 0; cb < 2; ++cb) ht_tma_load_5d(st + cb * HT_BOX, &mapG, cb * 64, x0, y0, b, 0, &full_bar[s]);   // (n >= N: zero fill)
+        for (int t = 0; t < p.taps; ++t) ht_tma_load_5d(st + (2 + t) * HT_BOX, &mapA, 0, x0 + p.dx[t], y0 + p.dy[t], b, 0, &full_bar[s]);
+        if (++s == stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && iters > 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, k_eff) | (1u << 15) | (1u << 16);   // MN-major A and B
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t gb = smem_u32(smem + (size_t)s * stage_bytes), xb = gb + 2 * HT_BOX;
+#pragma unroll
+        for (int kk = 0; kk < HT_BK / 16; ++kk) {
+          const uint32_t ko = kk * 2048;  // 16 pixels = two 1024-byte atoms
+          const uint64_t g_hi = ht_desc_mn_sw128(gb + ko, HT_BOX), g_lo = ht_desc_mn_sw128(gb + HT_PLANE + ko, HT_BOX);
+          const uint32_t first = (it == 0 && kk == 0) ? 0u : 1u;
+          for (int t = 0; t < p.taps; ++t) {
+            const uint64_t x_hi = ht_desc_mn_sw128(xb + t * HT_BOX + ko, HT_BOX), x_lo = ht_desc_mn_sw128(xb + t * HT_BOX + HT_PLANE + ko, HT_BOX);
+            const uint32_t d = tmem + (uint32_t)(t * kcols);
+            umma_f16(d, g_lo, x_hi, idesc, first);
+            umma_f16(d, g_hi, x_lo, idesc, 1u);
+            umma_f16(d, g_hi, x_hi, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else if (iters > 0) {
+    // epilogue: warp w may only read TMEM lanes [32 (w % 4), +32); lane = n
+    const int q = warp & 3;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const int n = q * 32 + lane;
+    const size_t ldn = (size_t)p.taps * p.Kp;
+    float* dst = p.dW + (size_t)n * ldn;
+    for (int t = 0; t < p.taps; ++t) {
+      for (int c8 = 0; c8 < k_eff; c8 += 8) {
+        uint32_t v[8];
+        tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * kcols + c8), v);
+        tmem_ld_wait();
+        if (n < p.N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c8 + j < p.K) atomicAdd(dst + (size_t)t * p.Kp + c8 + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, (uint32_t)tmem_cols); }
+}
+
+// ------------------------------------------------------------------------------------------------
 // LSTM backward (one bidirectional layer; tools/hd_bwd_emul.py:lstm_dir_bwd).  Gx = W_ih x + b (saved by the forward), R = W_hh h_prev
 // for every step at once (one GEMM over the saved h), both fp32 [Bs][T][8H], column = dir * 4H + gate * H + unit (gates i, f, g, o).
 // ------------------------------------------------------------------------------------------------

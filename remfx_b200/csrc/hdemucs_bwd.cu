@@ -33,6 +33,38 @@ int rfx_encode_tiled_bf16(void* map, const void* base, int rank, const unsigned 
 
 static int g_hd_wgrad_impl = 0;  // 0 = tcgen05 (MN-major operands), 1 = mma.sync tile variants
 
+// The fused narrow-layer form of the tcgen05 contraction (hd_wgrad_tc_fused_kernel): N <= 128, K <= 64, every tap's accumulator in
+// tensor memory at once.  Returns -1 when the shape does not qualify (the caller takes the general kernel), else a status.
+static int launch_wgrad_fused(const HtMap& mg, const HtMap& ma, HtParams tp, int Bn, cudaStream_t s) {
+  static const bool allow = [] { const char* e = getenv("RFX_HD_WGRAD_FUSED"); return !(e && atoi(e) == 0); }();
+  const int k_eff = (tp.K + 15) & ~15;
+  if (!allow || tp.N > 128 || tp.K > 64 || tp.taps * k_eff > 512 || tp.taps > 16) return -1;
+  const int kcols = tp.taps * 64 <= 512 ? 64 : k_eff;
+  int tmem_cols = 32;
+  while (tmem_cols < tp.taps * kcols) tmem_cols <<= 1;
+  const int stage_bytes = (2 + tp.taps) * HT_BOX;
+  const int stages = std::min(4, (227 * 1024 - 2048) / stage_bytes);
+  if (stages < 2) return -1;
+  // one CTA per SM (tensor memory), a single balanced wave: chunks per item = floor(SMs / items)
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int want = std::max(1, sms / std::max(1, Bn));
+  int tchunk = std::max(4, ceil_div(tp.ptiles, want));
+  tp.tchunk = tchunk;
+  tp.nchunks = ceil_div(tp.ptiles, tchunk);
+  if (tp.nchunks > 65535 || Bn > 65535) return -1;
+  const int smem = stages * stage_bytes + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    RFX_CHECK_CUDA(cudaFuncSetAttribute(hd_wgrad_tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  hd_wgrad_tc_fused_kernel<<<dim3(tp.nchunks, Bn), 192, smem, s>>>(mg, ma, tp, stages, kcols, tmem_cols);
+  RFX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 namespace {
 
 struct GradRec {
@@ -188,6 +220,17 @@ struct BRunner {
         tp.tiles_x = ceil_div(X, bx);
         tp.ptiles = tp.tiles_x * ceil_div(Y, by);
         tp.ntn = ceil_div(gs.Nout, 256); tp.ntk = ceil_div(Ktap, 256);
+        tp.dW = stage;
+        {
+          const int fr = launch_wgrad_fused(mg, ma, tp, Bn, s);
+          if (fr > 0) { rc = fr; return; }
+          if (fr == 0) {
+            chk("wgrad tcgen05 (fused taps)");
+            scatter_w_kernel<<<148 * 4, 256, 0, s>>>(stage, gs, dw);
+            chk("scatter_w");
+            return;
+          }
+        }
         const long long per = (long long)gs.taps * tp.ntn * tp.ntk * Bn;
         long long want = (148ll * 2 + per - 1) / per;   // about two waves of CTAs
         if (want < 1) want = 1;
@@ -775,6 +818,11 @@ int wgrad(const __nv_bfloat16* g, size_t g_plane, long long g_ld, int gcol0, int
   tp.tiles_x = ceil_div(X, bx);
   tp.ptiles = tp.tiles_x * ceil_div(Y, by);
   tp.ntn = ceil_div(N, 256); tp.ntk = ceil_div(K, 256);
+  tp.dW = stage;
+  {
+    const int fr = launch_wgrad_fused(mg, ma, tp, Bn, s);
+    if (fr >= 0) return fr;
+  }
   const long long per = (long long)taps * tp.ntn * tp.ntk * Bn;
   long long want = (148ll * 2 + per - 1) / per;
   if (want < 1) want = 1;
