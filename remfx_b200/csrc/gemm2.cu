@@ -178,6 +178,7 @@ struct G2Params {
   const float* t2;
   const float* slope;  // ACT_PRELU: per-column negative slope
   int act;
+  int cf_pre;    // 1: the fp32 output receives the PRE-activation (after scale / shift), the split output the activated value
   int cst;       // 1: fp32 rows are staged through shared memory (GN instantiations; see G2Row)
   int cf_accum;  // 1: the fp32 output accumulates (Cf += v; ACT_NONE without GLU only) -- the input-gradient GEMMs of residual branches
   // fused GroupNorm statistics of the (post-bias) output: accum[(seg * G + g) * 2 + {0,1}] += (sum, sum of squares)
@@ -264,6 +265,15 @@ __device__ __forceinline__ void g2_chunk(const uint32_t (&v)[32], const uint32_t
       for (int i = 0; i < 8; ++i) o[8 * j + i] = fmaf(o[8 * j + i], sc[i], sh[i]);
     }
   }
+  if (ACT != ACT_NONE && !DUAL && p.cf_pre && r.cf) {  // training forward: keep the pre-activation beside the activated split output
+    if (r.cf_vec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(r.cf + nb + 4 * i) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r.cf[nb + i] = o[i];
+    }
+  }
   if (ACT == ACT_PRELU) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -289,7 +299,7 @@ __device__ __forceinline__ void g2_chunk(const uint32_t (&v)[32], const uint32_t
 #pragma unroll
     for (int i = 0; i < 16; ++i) g[i] = o[2 * i] * sigmoidf_fast(o[2 * i + 1]);
     const int c0 = nb >> 1;
-    if (r.cf) {
+    if (r.cf && !p.cf_pre) {
       if (r.cf_vec) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(r.cf + c0 + 4 * i) = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
@@ -341,7 +351,7 @@ __device__ __forceinline__ void g2_chunk(const uint32_t (&v)[32], const uint32_t
       }
     }
     __syncwarp();
-  } else if (r.cf) {
+  } else if (r.cf && !(ACT != ACT_NONE && p.cf_pre)) {
     if (ACT == ACT_NONE && p.cf_accum) {
       if (r.cf_vec) {
 #pragma unroll
@@ -411,6 +421,12 @@ __device__ __forceinline__ void g2_chunk_ragged(uint32_t taddr, uint32_t taddr2,
       if (p.s2 || p.t2) val = fmaf(val, p.s2 ? p.s2[n] : 1.0f, p.t2 ? p.t2[n] : 0.0f);
       o[i] = val;
     }
+    const bool pre = p.cf_pre && p.act != ACT_NONE;
+    if (pre && r.cf) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (n8 + i < p.N) r.cf[n8 + i] = o[i];
+    }
     switch (p.act) {
       case ACT_TANH:
 #pragma unroll
@@ -455,7 +471,7 @@ __device__ __forceinline__ void g2_chunk_ragged(uint32_t taddr, uint32_t taddr2,
         if (n8 + 2 * i + 1 < p.N) {
           const float gv = o[2 * i] * sigmoidf_fast(o[2 * i + 1]);
           const int c = (n8 >> 1) + i;
-          if (r.cf) r.cf[c] = gv;
+          if (r.cf && !pre) r.cf[c] = gv;
           if (r.chi) {
             __nv_bfloat16 h, l;
             split_bf16(gv, h, l);
@@ -469,7 +485,7 @@ __device__ __forceinline__ void g2_chunk_ragged(uint32_t taddr, uint32_t taddr2,
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (n8 + i < p.N) {
-        if (r.cf) r.cf[n8 + i] = p.cf_accum ? r.cf[n8 + i] + o[i] : o[i];
+        if (r.cf && !pre) r.cf[n8 + i] = p.cf_accum ? r.cf[n8 + i] + o[i] : o[i];
         if (r.chi) {
           __nv_bfloat16 h, l;
           split_bf16(o[i], h, l);
@@ -797,6 +813,8 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   p.Chi = pr.Chi; p.Clo = pr.Clo; p.ldcs = pr.ldcs; p.bscs = pr.bscs; p.ldcy_s = pr.ldcs_y;
   p.s1 = pr.epi.s1; p.t1 = pr.epi.t1; p.s2 = pr.epi.s2; p.t2 = pr.epi.t2; p.slope = pr.epi.slope; p.act = pr.epi.act;
   p.cf_accum = pr.cf_accum ? 1 : 0;
+  p.cf_pre = pr.cf_pre_act ? 1 : 0;
+  RFX_REQUIRE(!pr.cf_pre_act || (pr.Cf && pr.Chi && !pr.dual && !pr.cf_accum && !pr.gn_acc), "pre-activation output: needs both outputs, no dual / accumulate / statistics");
   RFX_REQUIRE(!pr.cf_accum || (pr.Cf && !pr.Chi && pr.epi.act == ACT_NONE && !pr.gn_acc), "accumulating output: fp32 only, no activation, no fused statistics");
   p.gn_acc = pr.gn_acc; p.gn_G = pr.gn_G > 0 ? pr.gn_G : 1; p.gn_per_x = pr.gn_per_x;
   p.gn_cmod = pr.gn_cmod > 0 ? pr.gn_cmod : pr.N;

@@ -126,8 +126,10 @@ struct Runner {
   // axis: 0 = taps along X, 1 = taps along Y (plain 1-D convs); dil = dilation; pad = zero padding (plain)
   // out_f32: write fp32 (pre-norm) instead of split; act: epilogue activation (ACT_NONE / GELU / GLU_PAIR)
   // gn_G > 0: also accumulate GroupNorm statistics of the output in the GEMM epilogue; *gn_out receives (mean, rstd) stats
+  // also_act (training only, with out_f32): the same launch also writes the ACTIVATED output as split planes into *also_act (created
+  // and recorded here as the element-wise op the backward expects) while the fp32 tensor receives the pre-activation.
   Ten conv(const std::string& name, const Ten& in, int axis, int dil, int pad, bool out_f32, int act, const Ten* dst = nullptr,
-           int dst_col = 0, int gn_G = 0, int gn_per_x = 0, float** gn_out = nullptr) {
+           int dst_col = 0, int gn_G = 0, int gn_per_x = 0, float** gn_out = nullptr, Ten* also_act = nullptr) {
     auto it = h->convs.find(name);
     if (it == h->convs.end()) { set_error("hdemucs: conv '" + name + "' was not prepared"); rc = 2; return Ten(); }
     Conv& c = it->second;
@@ -155,11 +157,19 @@ struct Runner {
     const int Nout = g.Nout;
     if (train && !out_f32 && !dst) {
       // training: keep the pre-activation.  conv (bias only) -> fp32, then the activation as its own (recorded) element-wise op
+      static const bool fuse = [] { const char* e = getenv("RFX_HD_TRAIN_FUSE_ACT"); return !(e && atoi(e) == 0); }();
+      const int Cact = act == ACT_GLU_PAIR ? Nout / 2 : Nout;
+      if (fuse && (act == ACT_GELU || act == ACT_GLU_PAIR) && Cact % 8 == 0 && Nout % 4 == 0) {
+        // one launch: pre-activation -> fp32 (kept for the backward), activation -> split planes (G2Problem::cf_pre_act)
+        Ten act_out;
+        conv(name, in, axis, dil, pad, true, act, nullptr, 0, 0, 0, nullptr, &act_out);
+        return act_out;
+      }
       Ten raw = conv(name, in, axis, dil, pad, true, ACT_NONE);
       const int mode = act == ACT_GELU ? 1 : (act == ACT_GLU_PAIR ? 3 : 0);
       return gn_apply(raw, nullptr, 1, 0, nullptr, nullptr, mode, nullptr, nullptr, raw.X, 0, 0);
     }
-    const int Cout_store = act == ACT_GLU_PAIR ? Nout / 2 : Nout;
+    const int Cout_store = (act == ACT_GLU_PAIR && !also_act) ? Nout / 2 : Nout;
     Ten out;
     if (dst) out = *dst;  // write columns [dst_col, dst_col + N) of an existing fp32 tensor
     else out = out_f32 ? f32(in.B, Yo, Xo, Cout_store) : split(in.B, Yo, Xo, Cout_store);
@@ -183,6 +193,10 @@ struct Runner {
       if (!out_f32 && !dst) { set_error("hdemucs: internal: training conv must produce fp32"); rc = 2; return out; }
       Op op; op.kind = OP_CONV; op.name = name; op.in = in; op.out = out; op.pr = pr; op.dst_col = dst ? dst_col : 0;
       record(op);
+    }
+    if (also_act) {  // the element-wise op's output tensor + tape record, without its launch
+      const int mode = act == ACT_GELU ? 1 : (act == ACT_GLU_PAIR ? 3 : 0);
+      *also_act = gn_apply(out, nullptr, 1, 0, nullptr, nullptr, mode, nullptr, nullptr, out.X, 0, 0, /*launch=*/false);
     }
     if (dry || rc) { launches += gn_G > 0 ? 3 : 1; return out; }
     if (gn_G > 0 && cudaMemsetAsync(gacc, 0, (size_t)nseg * gn_G * 2 * 8, s) != cudaSuccess) { set_error("memset failed"); rc = 1; return out; }
@@ -208,6 +222,11 @@ struct Runner {
     if (dst) { pr.Cf = out.f + dst_col; pr.ldcf = out.C; pr.ldcf_y = (long long)Xo * out.C; pr.bscf = (long long)Yo * Xo * out.C; }
     else if (out_f32) { pr.Cf = out.f; pr.ldcf = Cout_store; pr.ldcf_y = (long long)Xo * Cout_store; pr.bscf = (long long)Yo * Xo * Cout_store; }
     else { pr.Chi = out.hi; pr.Clo = out.lo(); pr.ldcs = Cout_store; pr.ldcs_y = (long long)Xo * Cout_store; pr.bscs = (long long)Yo * Xo * Cout_store; }
+    if (also_act) {
+      const int Ca = also_act->C;
+      pr.Chi = also_act->hi; pr.Clo = also_act->lo(); pr.ldcs = Ca; pr.ldcs_y = (long long)Xo * Ca; pr.bscs = (long long)Yo * Xo * Ca;
+      pr.cf_pre_act = true;
+    }
     pr.epi.t1 = c.bias.p;
     pr.epi.act = act;
     pr.gn_acc = gacc; pr.gn_G = gn_G > 0 ? gn_G : 1; pr.gn_per_x = gn_per_x; pr.gn_cmod = gn_cmod;
@@ -248,7 +267,7 @@ struct Runner {
 
   // ---- norm (optional) + activation (+ LayerScale, + residual) -> split ----
   Ten gn_apply(const Ten& raw, const float* stats, int G, int per_x, const float* gamma, const float* beta, int mode, const float* scale,
-               const Ten* res, int Xo, int x_off, int Cpad) {
+               const Ten* res, int Xo, int x_off, int Cpad, bool launch = true) {
     const int Cvalid = mode >= 2 ? raw.C / 2 : raw.C;
     const int Co = Cpad > 0 ? Cpad : ceil_div(Cvalid, 8) * 8;
     Ten out = split(raw.B, raw.Y, Xo, Co);
@@ -262,6 +281,7 @@ struct Runner {
       record(op);
     }
     pending_gamma.clear(); pending_beta.clear(); pending_scale.clear();
+    if (!launch) return out;   // the producing GEMM writes `out` itself (conv(..., also_act))
     if (dry || rc) { ++launches; return out; }
     GnApply a{};
     a.raw = raw.f; a.Y = raw.Y; a.Xr = raw.X; a.Cr = raw.C;

@@ -109,6 +109,7 @@ struct G2Problem {
   float* Cf = nullptr;          // fp32 output (optional): element (b, y, x, n) at b * bscf + y * ldcf_y + x * ldcf + n
   long long ldcf = 0, ldcf_y = 0, bscf = 0;
   bool cf_accum = false;        // Cf += result instead of Cf = result (fp32 output only, ACT_NONE)
+  bool cf_pre_act = false;      // both outputs given: Cf receives the pre-activation (bias / scale applied), Chi / Clo the activated value
   __nv_bfloat16* Chi = nullptr;  // split-bf16 output (optional)
   __nv_bfloat16* Clo = nullptr;
   long long ldcs = 0, ldcs_y = 0, bscs = 0;
