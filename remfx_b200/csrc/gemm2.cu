@@ -164,6 +164,14 @@ struct G2Params {
   int kb_per_tap;  // 64-wide K blocks per tap
   int taps;
   int dx[16], dy[16];  // A origin offset of each tap
+  // Tap groups (ngroups > 0; pixel tiles of one row, yt == 1): the taps of a group differ by an x offset only, so ONE A box of
+  // a_rows = 128 + 8 consecutive pixels serves them all -- each tap's MMAs read it from a start address shifted by whole 128-byte
+  // rows (descriptor base offset = the row phase inside the 1024-byte swizzle atom).  A 3x3 conv loads 3 boxes per k-block instead of 9.
+  int ngroups;
+  int g_start[17];     // group g = taps g_taps[g_start[g] .. g_start[g + 1])
+  int g_taps[16];
+  int g_dx0[16], g_dy[16];   // A origin offset of the group's box
+  int a_plane;         // bytes of one plane of the group's A box (a_rows * 128); the lo plane follows the hi plane
   long long ldcy_f, ldcy_s;  // output y strides (elements) for the fp32 / split outputs
   // outputs: fp32 (Cf) and/or split planes (Chi/Clo); row stride ld*, batch stride bs* (elements)
   float* Cf;
@@ -599,6 +607,24 @@ __global__ void __launch_bounds__(g2_threads2(DUAL, TWO), TWO ? 2 : 1)
         const int mt = r / p.n_tiles;
         const int x0 = tile_x(mt) * p.xt, y0 = tile_y(mt) * p.yt;
         const int n0 = (r % p.n_tiles) * BN;
+        if (p.ngroups > 0) {  // one stage = (tap group, k-block): the group's A box + (W not resident) one W box per tap of the group
+          for (int g = 0; g < p.ngroups; ++g) {
+            const int nt = p.g_start[g + 1] - p.g_start[g];
+            for (int kbt = 0; kbt < p.kb_per_tap; ++kbt) {
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * p.a_plane + (w_res ? 0 : nt * p.b_bytes)));
+              uint8_t* st = ring + s * STAGE_BYTES;
+              tma_load_5d(st, &mapA, kbt * G2_BK, x0 + p.g_dx0[g], y0 + p.g_dy[g], b, 0, &full_bar[s]);
+              if (!w_res)
+                for (int j = 0; j < nt; ++j) {
+                  const int tap = p.g_taps[p.g_start[g] + j];
+                  tma_load_5d(st + 2 * p.a_plane + j * p.b_bytes, &mapW, (tap * p.kb_per_tap + kbt) * G2_BK, n0, 0, 0, 0, &full_bar[s]);
+                }
+              if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+          continue;
+        }
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           const bool ldA = !(p.dbg_skip == 2 && kb > 0), ldW = !w_res && !(p.dbg_skip == 1 && kb > 0);
@@ -632,6 +658,47 @@ __global__ void __launch_bounds__(g2_threads2(DUAL, TWO), TWO ? 2 : 1)
         const int n0t = ((tile % tiles_per_batch) % p.n_tiles) * BN;
         const int n_eff = min(BN, ((p.N - n0t) + 15) & ~15);
         const uint32_t idesc = umma_idesc_bf16(G2_BM, n_eff);
+        if (p.ngroups > 0) {
+          const uint32_t d_tmem = tmem_base + as * BN;
+          uint32_t acc = 0u;  // the tile's first MMA overwrites the accumulator
+          for (int g = 0; g < p.ngroups; ++g) {
+            const int nt = p.g_start[g + 1] - p.g_start[g];
+            for (int kbt = 0; kbt < p.kb_per_tap; ++kbt) {
+              mbar_wait(&full_bar[s], ph);
+              tc_fence_after();
+              const uint32_t a_hi = smem_u32(ring + s * STAGE_BYTES);
+              const uint32_t a_lo = a_hi + (uint32_t)p.a_plane;
+              const int kvalid = p.ktap - kbt * G2_BK;
+              const int nks = kvalid >= G2_BK ? G2_BK / 16 : (kvalid + 15) >> 4;
+              for (int j = 0; j < nt; ++j) {
+                const int tap = p.g_taps[p.g_start[g] + j];
+                const uint32_t shift = (uint32_t)(p.dx[tap] - p.g_dx0[g]) * 128u;   // whole rows inside the group's box
+                const uint32_t b_hi = w_res ? smem_u32(wres) + (uint32_t)((tap * p.kb_per_tap + kbt) * p.b_bytes)
+                                            : a_hi + 2u * (uint32_t)p.a_plane + (uint32_t)(j * p.b_bytes);
+                const uint32_t b_lo = b_hi + (uint32_t)p.n_box * (G2_BK * 2);
+#pragma unroll
+                for (int ks = 0; ks < G2_BK / 16; ++ks) {
+                  if (ks >= nks) break;
+                  const uint32_t ko = ks * 32;
+                  const uint64_t dah = umma_desc_sw128_row(a_hi + shift + ko), dal = umma_desc_sw128_row(a_lo + shift + ko);
+                  const uint64_t dbh = umma_desc_sw128(b_hi + ko), dbl = umma_desc_sw128(b_lo + ko);
+                  if (p.fast) {
+                    umma_f16(d_tmem, dah, dbh, idesc, acc);
+                  } else {
+                    umma_f16(d_tmem, dal, dbh, idesc, acc);
+                    umma_f16(d_tmem, dah, dbl, idesc, 1u);
+                    umma_f16(d_tmem, dah, dbh, idesc, 1u);
+                  }
+                  acc = 1u;
+                }
+              }
+              umma_commit(&empty_bar[s]);
+              if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+          umma_commit(&tfull_bar[as]);
+          continue;
+        }
         for (int kb = 0; kb < KB; ++kb) {
           const uint32_t d_tmem = tmem_base + (DUAL ? (kb >= kb_res ? BN : 0) : as * BN);
           const bool first_kb = (kb == 0) || (kb == kb_res);
@@ -825,30 +892,64 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
     RFX_REQUIRE((long long)pr.batch * (pr.gn_per_x ? pr.M : 1) * p.gn_G < (1ll << 31), "fused GroupNorm statistics: too many segments");
   }
   RFX_REQUIRE(pr.W.Kpad >= p.kb_per_tap * p.taps * G2_BK, "packed weight K extent too small for taps * Ktap");
-  CUtensorMap mapA, mapW;
-  int rc;
-  if ((rc = make_split_map(&mapA, pr.A.hi, pr.Ktap, pr.A.rows, pr.A.rows_y > 0 ? pr.A.rows_y : 1, pr.batch, pr.A.ld, pr.A.ld_y,
-                           pr.A.batch_stride, pr.A.plane_stride, p.xt, p.yt)))
-    return rc;
+  // Tap groups (see G2Params): pixel tiles of one row, taps sorted by (dy, dx), a group = equal dy and x offsets within 8 pixels
+  constexpr int G2_GROUP_SPAN = 8;
+  p.ngroups = 0;
+  int max_group = 1;
+  {
+    static const bool allow = [] { const char* e = getenv("RFX_G2_TAPGROUPS"); return e && atoi(e) != 0; }();   // opt-in until verified on hardware
+    if (allow && !pr.dual && p.yt == 1 && pr.taps > 1) {
+      int order[16];
+      for (int i = 0; i < pr.taps; ++i) order[i] = i;
+      std::sort(order, order + pr.taps, [&](int a, int b) { return p.dy[a] != p.dy[b] ? p.dy[a] < p.dy[b] : p.dx[a] < p.dx[b]; });
+      int ng = 0;
+      for (int i = 0; i < pr.taps; ++i) {
+        const int t = order[i];
+        if (ng > 0 && p.dy[t] == p.g_dy[ng - 1] && p.dx[t] - p.g_dx0[ng - 1] <= G2_GROUP_SPAN) {
+          max_group = std::max(max_group, i + 1 - p.g_start[ng - 1]);
+        } else {
+          p.g_start[ng] = i; p.g_dx0[ng] = p.dx[t]; p.g_dy[ng] = p.dy[t];
+          ++ng;
+        }
+        p.g_taps[i] = t;
+      }
+      p.g_start[ng] = pr.taps;
+      if (max_group > 1) p.ngroups = ng;
+    }
+  }
+  const int a_rows = p.ngroups > 0 ? G2_BM + G2_GROUP_SPAN : G2_BM;
+  p.a_plane = a_rows * G2_BK * 2;
+  const int a_stage = 2 * p.a_plane;   // = G2_A_STAGE without tap groups
   // shared-memory plan: narrow single-tile outputs fetch only the rows they need; small weight matrices stay resident
   constexpr int SMEM_CAP = 227 * 1024 - 2048;  // barriers + 1024-byte alignment slack
   const int KB = p.kb_per_tap * p.taps;
   p.n_box = p.n_tiles == 1 ? std::min(BN, ceil_div(pr.N, 16) * 16) : BN;
   p.b_bytes = 2 * p.n_box * G2_BK * 2;
   const long long w_total = (long long)KB * p.b_bytes;
-  const bool resident = !pr.dual && p.n_tiles == 1 && w_total + 3 * G2_A_STAGE <= SMEM_CAP;
+  const bool resident = !pr.dual && p.n_tiles == 1 && w_total + 3 * a_stage <= SMEM_CAP;
   p.w_res_bytes = resident ? (int)w_total : 0;
-  p.stage_bytes = G2_A_STAGE + (resident ? 0 : p.b_bytes);
+  p.stage_bytes = a_stage + (resident ? 0 : (p.ngroups > 0 ? max_group : 1) * p.b_bytes);
   p.stages = std::min(G2_MAX_STAGES, (SMEM_CAP - p.w_res_bytes) / p.stage_bytes);
+  if (p.ngroups > 0 && p.stages < 2) {  // the grouped stages do not fit: back to one tap per stage
+    p.ngroups = 0;
+    p.a_plane = G2_BM * G2_BK * 2;
+    p.stage_bytes = G2_A_STAGE + (resident ? 0 : p.b_bytes);
+    p.stages = std::min(G2_MAX_STAGES, (SMEM_CAP - p.w_res_bytes) / p.stage_bytes);
+  }
   RFX_REQUIRE(p.stages >= 2, "gemm2: operand stages do not fit in shared memory");
+  CUtensorMap mapA, mapW;
+  int rc;
+  if ((rc = make_split_map(&mapA, pr.A.hi, pr.Ktap, pr.A.rows, pr.A.rows_y > 0 ? pr.A.rows_y : 1, pr.batch, pr.A.ld, pr.A.ld_y,
+                           pr.A.batch_stride, pr.A.plane_stride, p.ngroups > 0 ? G2_BM + G2_GROUP_SPAN : p.xt, p.yt)))
+    return rc;
   if ((rc = make_split_map(&mapW, pr.W.hi, pr.W.Kpad, pr.W.Npad, 1, 1, pr.W.Kpad, 0, 0, (long long)pr.W.Npad * pr.W.Kpad, p.n_box, 1))) return rc;
   const int total = p.batch * p.m_tiles * p.n_tiles;
   {  // RFX_G2_TRACE=1: one line per launch (shape, tiling, shared-memory plan) to match against an ncu launch list
     static const bool trace = [] { const char* e = getenv("RFX_G2_TRACE"); return e && atoi(e) != 0; }();
     if (trace)
-      fprintf(stderr, "g2trace batch=%d Y=%d X=%d N=%d Ktap=%d taps=%d BN=%d xt=%d tiles=%d n_tiles=%d resident=%d stages=%d act=%d gn=%d fp32out=%d split=%d\n",
+      fprintf(stderr, "g2trace batch=%d Y=%d X=%d N=%d Ktap=%d taps=%d BN=%d xt=%d tiles=%d n_tiles=%d resident=%d stages=%d act=%d gn=%d fp32out=%d split=%d groups=%d\n",
               pr.batch, Yo, pr.M, pr.N, pr.Ktap, pr.taps, BN, xt, total, p.n_tiles, resident ? 1 : 0, p.stages, pr.epi.act, pr.gn_acc ? 1 : 0,
-              pr.Cf ? 1 : 0, pr.Chi ? 1 : 0);
+              pr.Cf ? 1 : 0, pr.Chi ? 1 : 0, p.ngroups);
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
