@@ -793,7 +793,9 @@ __global__ void __launch_bounds__(192, 1) hd_wgrad_tc_kernel(const __grid_consta
 // ------------------------------------------------------------------------------------------------
 constexpr int HF_MAX_STAGE_BOXES = 2 + 16;
 __global__ void __launch_bounds__(192, 1) hd_wgrad_tc_fused_kernel(const __grid_constant__ HtMap mapG, const __grid_constant__ HtMap mapA, const HtParams p,
-                                                                    int stages, int kcols, int tmem_cols) {
+                                                                    int stages, int kcols, int tmem_cols, float* __restrict__ dB) {
+  // dB != nullptr: the four epilogue warps, idle during the main loop, also sum the output-gradient boxes of every stage over their
+  // 32 pixels (thread = channel n) -- the bias gradient, for which a separate pass would read the whole gradient tensor again
   extern __shared__ uint8_t hf_smem_raw[];
   const uint32_t raw = smem_u32(hf_smem_raw);
   uint8_t* smem = hf_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -809,7 +811,7 @@ __global__ void __launch_bounds__(192, 1) hd_wgrad_tc_fused_kernel(const __grid_
   const int iters = t_end - t_begin;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], dB ? 5 : 1); }   // MMA commit (+ 4 summing warps)
     mbar_init(tfull_bar, 1);
     mbar_fence_init();
   }
@@ -862,6 +864,28 @@ __global__ void __launch_bounds__(192, 1) hd_wgrad_tc_fused_kernel(const __grid_
   } else if (iters > 0) {
     // epilogue: warp w may only read TMEM lanes [32 (w % 4), +32); lane = n
     const int q = warp & 3;
+    if (dB) {
+      const int nn = q * 32 + lane;
+      // SW128 MN-major box: pixel p = 128-byte row, channel c of the box in 16-byte chunk ((c >> 3) ^ (p & 7)), hi plane then lo plane
+      const uint32_t coff = (uint32_t)(nn >> 6) * HT_BOX + (uint32_t)(nn & 7) * 2u;
+      const uint32_t cch = (uint32_t)((nn & 63) >> 3);
+      float acc = 0.0f;
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait_backoff(&full_bar[s], ph);
+        const uint8_t* st = smem + (size_t)s * stage_bytes + coff;
+#pragma unroll 8
+        for (int px = 0; px < HT_BK; ++px) {
+          const uint32_t o = (uint32_t)px * 128u + ((cch ^ (uint32_t)(px & 7)) << 4);
+          acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(st + o)) +
+                 __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(st + HT_PLANE + o));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (++s == stages) { s = 0; ph ^= 1; }
+      }
+      if (nn < p.N) atomicAdd(dB + nn, acc);
+    }
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     const int n = q * 32 + lane;

@@ -33,9 +33,17 @@ int rfx_encode_tiled_bf16(void* map, const void* base, int rank, const unsigned 
 
 static int g_hd_wgrad_impl = 0;  // 0 = tcgen05 (MN-major operands), 1 = mma.sync tile variants
 
+// Shapes the fused narrow-layer kernel takes (launch_wgrad_fused) AND whose bias column sums it may produce on the side
+static bool wgrad_fused_sums_bias(int N, int K, int taps) {
+  static const bool allow = [] { const char* e = getenv("RFX_HD_WGRAD_FUSED"); return !(e && atoi(e) == 0); }();
+  static const bool sums = [] { const char* e = getenv("RFX_HD_WGRAD_COLSUM"); return e && atoi(e) != 0; }();   // opt-in until verified on hardware
+  const int k_eff = (K + 15) & ~15;
+  return allow && sums && N <= 128 && K <= 64 && taps <= 16 && taps * k_eff <= 512 && (2 + taps) * HT_BOX * 2 <= 227 * 1024 - 2048;
+}
+
 // The fused narrow-layer form of the tcgen05 contraction (hd_wgrad_tc_fused_kernel): N <= 128, K <= 64, every tap's accumulator in
 // tensor memory at once.  Returns -1 when the shape does not qualify (the caller takes the general kernel), else a status.
-static int launch_wgrad_fused(const HtMap& mg, const HtMap& ma, HtParams tp, int Bn, cudaStream_t s) {
+static int launch_wgrad_fused(const HtMap& mg, const HtMap& ma, HtParams tp, int Bn, cudaStream_t s, float* dB = nullptr) {
   static const bool allow = [] { const char* e = getenv("RFX_HD_WGRAD_FUSED"); return !(e && atoi(e) == 0); }();
   const int k_eff = (tp.K + 15) & ~15;
   if (!allow || tp.N > 128 || tp.K > 64 || tp.taps * k_eff > 512 || tp.taps > 16) return -1;
@@ -60,7 +68,7 @@ static int launch_wgrad_fused(const HtMap& mg, const HtMap& ma, HtParams tp, int
     RFX_CHECK_CUDA(cudaFuncSetAttribute(hd_wgrad_tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  hd_wgrad_tc_fused_kernel<<<dim3(tp.nchunks, Bn), 192, smem, s>>>(mg, ma, tp, stages, kcols, tmem_cols);
+  hd_wgrad_tc_fused_kernel<<<dim3(tp.nchunks, Bn), 192, smem, s>>>(mg, ma, tp, stages, kcols, tmem_cols, dB);
   RFX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -179,7 +187,12 @@ struct BRunner {
     float* db2 = pgrad(c.bkey2);
     if (dry || rc) return;
     SideScope side(*this);
-    if (db) {
+    // narrow layers: the fused weight-gradient kernel sums the bias columns from the boxes it has in shared memory anyway
+    const bool bias_in_wgrad = db && dw && g_hd_wgrad_impl == 0 && (g_ld % 8) == 0 && (A.ld % 8) == 0 && (gcol0 % 8) == 0 &&
+                               wgrad_fused_sums_bias(gs.Nout, Ktap, gs.taps);
+    if (db && bias_in_wgrad) {
+      if (cudaMemsetAsync(bstage, 0, (size_t)gs.Nout * 4, s) != cudaSuccess) { fail("memset"); return; }
+    } else if (db) {
       if (cudaMemsetAsync(bstage, 0, (size_t)gs.Nout * 4, s) != cudaSuccess) { fail("memset"); return; }
       const long long rows = (long long)Bn * Y * X;
       const int rpc = rows_for(rows, 1, 64);
@@ -222,14 +235,19 @@ struct BRunner {
         tp.ntn = ceil_div(gs.Nout, 256); tp.ntk = ceil_div(Ktap, 256);
         tp.dW = stage;
         {
-          const int fr = launch_wgrad_fused(mg, ma, tp, Bn, s);
+          const int fr = launch_wgrad_fused(mg, ma, tp, Bn, s, bias_in_wgrad ? bstage : nullptr);
           if (fr > 0) { rc = fr; return; }
           if (fr == 0) {
             chk("wgrad tcgen05 (fused taps)");
             scatter_w_kernel<<<148 * 4, 256, 0, s>>>(stage, gs, dw);
             chk("scatter_w");
+            if (bias_in_wgrad) {
+              scatter_bias_kernel<<<ceil_div(gs.Nout, 256), 256, 0, s>>>(bstage, gs, db, db2);
+              chk("scatter_bias");
+            }
             return;
           }
+          if (bias_in_wgrad) { fail("internal: fused weight-gradient kernel refused a shape it was expected to take"); return; }
         }
         const long long per = (long long)gs.taps * tp.ntn * tp.ntk * Bn;
         long long want = (148ll * 2 + per - 1) / per;   // about two waves of CTAs
