@@ -165,11 +165,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// Same for a tile that starts at a whole 128-byte row INSIDE a 1024-byte swizzle atom (an operand read from a shifted row of a larger
-// TMA box): bits 49-51 carry the "matrix base offset" = the start row's phase in the atom, (address >> 7) & 7.
-__device__ __forceinline__ uint64_t umma_desc_sw128_row(uint32_t smem_addr) {
-  return umma_desc_sw128(smem_addr) | ((uint64_t)((smem_addr >> 7) & 7u) << 49);
-}
 // Instruction descriptor for kind::f16 with BF16 A/B (K-major both), FP32 accumulate, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -166,7 +166,7 @@ struct G2Params {
   int dx[16], dy[16];  // A origin offset of each tap
   // Tap groups (ngroups > 0; pixel tiles of one row, yt == 1): the taps of a group differ by an x offset only, so ONE A box of
   // a_rows = 128 + 8 consecutive pixels serves them all -- each tap's MMAs read it from a start address shifted by whole 128-byte
-  // rows (descriptor base offset = the row phase inside the 1024-byte swizzle atom).  A 3x3 conv loads 3 boxes per k-block instead of 9.
+  // rows.  A 3x3 conv loads 3 boxes per k-block instead of 9.
   int ngroups;
   int g_start[17];     // group g = taps g_taps[g_start[g] .. g_start[g + 1])
   int g_taps[16];
@@ -680,7 +680,10 @@ __global__ void __launch_bounds__(g2_threads2(DUAL, TWO), TWO ? 2 : 1)
                 for (int ks = 0; ks < G2_BK / 16; ++ks) {
                   if (ks >= nks) break;
                   const uint32_t ko = ks * 32;
-                  const uint64_t dah = umma_desc_sw128_row(a_hi + shift + ko), dal = umma_desc_sw128_row(a_lo + shift + ko);
+                  // start address shifted by whole rows, descriptor otherwise unchanged: the swizzle is a function of the absolute
+                  // shared-memory address on both the TMA and the MMA side (measured: setting the descriptor's base-offset field to the
+                  // row phase gives wrong products, leaving it 0 is bit-compatible with per-tap boxes)
+                  const uint64_t dah = umma_desc_sw128(a_hi + shift + ko), dal = umma_desc_sw128(a_lo + shift + ko);
                   const uint64_t dbh = umma_desc_sw128(b_hi + ko), dbl = umma_desc_sw128(b_lo + ko);
                   if (p.fast) {
                     umma_f16(d_tmem, dah, dbh, idesc, acc);
@@ -897,7 +900,9 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
   p.ngroups = 0;
   int max_group = 1;
   {
-    static const bool allow = [] { const char* e = getenv("RFX_G2_TAPGROUPS"); return e && atoi(e) != 0; }();   // opt-in until verified on hardware
+    // opt-in: parity-green (tests under RFX_G2_TAPGROUPS=1) but no net gain on Hybrid Demucs -- see DESIGN 4.5
+    static const bool allow = [] { const char* e = getenv("RFX_G2_TAPGROUPS"); return e && atoi(e) != 0; }();
+    const int span = G2_GROUP_SPAN;
     if (allow && !pr.dual && p.yt == 1 && pr.taps > 1) {
       int order[16];
       for (int i = 0; i < pr.taps; ++i) order[i] = i;
@@ -905,7 +910,7 @@ int launch_gemm2(const G2Problem& pr, cudaStream_t stream) {
       int ng = 0;
       for (int i = 0; i < pr.taps; ++i) {
         const int t = order[i];
-        if (ng > 0 && p.dy[t] == p.g_dy[ng - 1] && p.dx[t] - p.g_dx0[ng - 1] <= G2_GROUP_SPAN) {
+        if (ng > 0 && p.dy[t] == p.g_dy[ng - 1] && p.dx[t] - p.g_dx0[ng - 1] <= span) {
           max_group = std::max(max_group, i + 1 - p.g_start[ng - 1]);
         } else {
           p.g_start[ng] = i; p.g_dx0[ng] = p.dx[t]; p.g_dy[ng] = p.dy[t];
