@@ -380,29 +380,34 @@ struct BRunner {
     const long long npix = a.per_x ? a.Y : (long long)a.Y * a.Xr;
     p.count = npix * (a.Cr / a.G);
     const int groups = a.Co / 8, rows = 256 / groups;
-    p.rows_per_cta = rows_for(npix, nseg, rows * 8);
+    if (a.mode < 0 || a.mode > 3) { fail("gn backward: unknown activation mode"); return; }
+    // The instantiations hold two or three CTAs per SM (registers).  The work is cut into ~888 = 148 x 6 items so that a grid of
+    // 148 x (CTAs per SM) is ONE wave whose CTAs each stride over the same number of items, whichever the occupancy (a fixed grid of
+    // 592 ran as 1.33 waves at three CTAs per SM).
+    using GnFn = void (*)(GnBwd);
+    static const GnFn fn1[4] = {gn_bwd_kernel<1, 0>, gn_bwd_kernel<1, 1>, gn_bwd_kernel<1, 2>, gn_bwd_kernel<1, 3>};
+    static const GnFn fn2[4] = {gn_bwd_kernel<2, 0>, gn_bwd_kernel<2, 1>, gn_bwd_kernel<2, 2>, gn_bwd_kernel<2, 3>};
+    const size_t smem1 = (size_t)((2 * a.Cr + a.Co + 3) & ~3) * 4 + 2 * a.G * 8;
+    auto ctas_per_sm = [&](GnFn f, size_t smem) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, f, 256, smem) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = 1; }
+      return std::min(n, 6);
+    };
+    {
+      const long long want = std::max<long long>(1, 888 / std::max(1, nseg));
+      p.rows_per_cta = (int)std::min<long long>(std::max<long long>((npix + want - 1) / want, rows * 8), 1 << 30);
+    }
     p.nseg = nseg;
     p.nchunks = (int)((npix + p.rows_per_cta - 1) / p.rows_per_cta);
-    const unsigned grid = (unsigned)std::min<long long>((long long)nseg * p.nchunks, 148 * 4);
+    const long long items = (long long)nseg * p.nchunks;
     if (has_stats) {
       if (cudaMemsetAsync(gsum, 0, (size_t)nseg * a.G * 2 * 8, s) != cudaSuccess) { fail("memset"); return; }
-      const size_t smem = (size_t)((2 * a.Cr + a.Co + 3) & ~3) * 4 + 2 * a.G * 8;
-      switch (a.mode) {
-        case 0: gn_bwd_kernel<1, 0><<<grid, 256, smem, s>>>(p); break;
-        case 1: gn_bwd_kernel<1, 1><<<grid, 256, smem, s>>>(p); break;
-        case 2: gn_bwd_kernel<1, 2><<<grid, 256, smem, s>>>(p); break;
-        case 3: gn_bwd_kernel<1, 3><<<grid, 256, smem, s>>>(p); break;
-        default: fail("gn backward: unknown activation mode"); return;
-      }
+      const unsigned grid1 = (unsigned)std::min<long long>(items, 148 * ctas_per_sm(fn1[a.mode], smem1));
+      fn1[a.mode]<<<grid1, 256, smem1, s>>>(p);
       chk("gn pass 1");
     }
-    switch (a.mode) {
-      case 0: gn_bwd_kernel<2, 0><<<grid, 256, 0, s>>>(p); break;
-      case 1: gn_bwd_kernel<2, 1><<<grid, 256, 0, s>>>(p); break;
-      case 2: gn_bwd_kernel<2, 2><<<grid, 256, 0, s>>>(p); break;
-      case 3: gn_bwd_kernel<2, 3><<<grid, 256, 0, s>>>(p); break;
-      default: fail("gn backward: unknown activation mode"); return;
-    }
+    const unsigned grid2 = (unsigned)std::min<long long>(items, 148 * ctas_per_sm(fn2[a.mode], 0));
+    fn2[a.mode]<<<grid2, 256, 0, s>>>(p);
     chk("gn pass 2");
     graw.init = true;
     if (gres) gres->init = true;
