@@ -82,6 +82,31 @@ __global__ void __launch_bounds__(256) item_normalize_kernel(const float* __rest
   }
 }
 
+// same, one element per thread: lengths that are not a multiple of 8 (whole files; the benchmark chunks take the vector form)
+__global__ void __launch_bounds__(256) item_normalize_scalar_kernel(const float* __restrict__ x, long long n, const float* __restrict__ stats,
+                                                                    float* __restrict__ of) {
+  const int b = blockIdx.y;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  of[(size_t)b * n + i] = (x[(size_t)b * n + i] - stats[2 * b]) * (1.0f / (1e-5f + stats[2 * b + 1]));
+}
+
+// ---- (B, Y, X, C) split planes -> (B, Y, Xp, C) with zero rows in [X, Xp): the zero padding a strided time conv applies to an input
+//      whose length is not a multiple of its stride (TA:147-150); only taken for lengths off the 1024-sample grid ----
+__global__ void __launch_bounds__(256) pad_rows_kernel(const __nv_bfloat16* __restrict__ ihi, const __nv_bfloat16* __restrict__ ilo, int Y, int X, int Xp,
+                                                       int C, __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo) {
+  const int groups = C / 8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= (long long)Y * Xp * groups) return;
+  const int c0 = (int)(idx % groups) * 8;
+  const int x = (int)((idx / groups) % Xp);
+  const int y = (int)(idx / ((long long)groups * Xp));
+  float u[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (x < X) load_split8(ihi, ilo, (((size_t)b * Y + y) * X + x) * C + c0, u);
+  store_split8(ohi, olo, (((size_t)b * Y + y) * Xp + x) * C + c0, u);
+}
+
 // ---- first time-branch conv: Conv1d(1 -> C, k, stride s, pad p) + bias + GELU on the normalised waveform ----
 // xt fp32 [B][T] -> split [B][T/s][C]; one thread per (output step, 8 channels); weights transposed into smem [K][C]
 template <int K>
@@ -376,7 +401,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApply a) {
 }
 
 // ---- out = a[(b, y, x + x_off)] + skip[(b, y, x)]  (decoder `x + skip` with the transposed-conv crop folded in) ----
-__global__ void __launch_bounds__(256) add_crop_kernel(const __nv_bfloat16* __restrict__ ahi, const __nv_bfloat16* __restrict__ alo, int Xa, int x_off,
+__global__ void __launch_bounds__(256) add_crop_kernel(const __nv_bfloat16* __restrict__ ahi, const __nv_bfloat16* __restrict__ alo, int Ya, int Xa, int x_off,
                                                        const __nv_bfloat16* __restrict__ shi, const __nv_bfloat16* __restrict__ slo,
                                                        __nv_bfloat16* __restrict__ ohi, __nv_bfloat16* __restrict__ olo, int Y, int X, int C) {
   const int groups = C / 8;
@@ -387,7 +412,7 @@ __global__ void __launch_bounds__(256) add_crop_kernel(const __nv_bfloat16* __re
   const int x = (int)((idx / groups) % X);
   const int y = (int)(idx / ((long long)groups * X));
   float u[8], v[8];
-  load_split8(ahi, alo, (((size_t)b * Y + y) * Xa + x + x_off) * C + c0, u);
+  load_split8(ahi, alo, (((size_t)b * Ya + y) * Xa + x + x_off) * C + c0, u);   // (a may have more rows than the skip: Ya >= Y)
   const size_t off = (((size_t)b * Y + y) * X + x) * C + c0;
   load_split8(shi, slo, off, v);
 #pragma unroll

@@ -134,6 +134,18 @@ struct Runner {
     if (it == h->convs.end()) { set_error("hdemucs: conv '" + name + "' was not prepared"); rc = 2; return Ten(); }
     Conv& c = it->second;
     const GatherSpec& g = c.g;
+    if (g.kind == 1 && in.X % g.s != 0) {
+      // a strided conv zero-pads its input to a multiple of the stride (TA:147-150): lengths off the 1024-sample grid only
+      if (train) { set_error("hdemucs: training needs chunk lengths that are multiples of 1024 samples"); rc = 2; return Ten(); }
+      const int Xp = ceil_div(in.X, g.s) * g.s;
+      Ten padded = split(in.B, in.Y, Xp, in.C);
+      if (!dry && rc == 0) {
+        const long long items = (long long)in.Y * Xp * (in.C / 8);
+        pad_rows_kernel<<<dim3((unsigned)((items + 255) / 256), in.B), 256, 0, s>>>(in.hi, in.lo(), in.Y, in.X, Xp, in.C, padded.hi, padded.lo());
+        chk();
+      } else ++launches;
+      return conv(name, padded, axis, dil, pad, out_f32, act, dst, dst_col, gn_G, gn_per_x, gn_out, also_act);
+    }
     G2Problem pr;
     int Xv = in.X, Cv = in.C;  // input view
     int Xo = in.X, Yo = in.Y;  // output pixel grid
@@ -303,7 +315,8 @@ struct Runner {
     if (train) { Op op; op.kind = OP_ADDCROP; op.in = a; op.in2 = skip; op.out = out; op.i0 = x_off; record(op); }
     if (dry || rc) { ++launches; return out; }
     const long long items = (long long)skip.Y * skip.X * (skip.C / 8);
-    add_crop_kernel<<<dim3((unsigned)((items + 255) / 256), skip.B), 256, 0, s>>>(a.hi, a.lo(), a.X, x_off, skip.hi, skip.lo(), out.hi, out.lo(),
+    if (a.Y < skip.Y || a.X < skip.X + x_off) { set_error("hdemucs: internal: skip sum reads beyond its input"); rc = 2; return out; }
+    add_crop_kernel<<<dim3((unsigned)((items + 255) / 256), skip.B), 256, 0, s>>>(a.hi, a.lo(), a.Y, a.X, x_off, skip.hi, skip.lo(), out.hi, out.lo(),
                                                                                   skip.Y, skip.X, skip.C);
     chk();
     return out;
@@ -451,7 +464,10 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
     if ((R.rc = launch_stft(sp, B, s))) return R.rc;
     item_stats_kernel<<<B, 1024, 0, s>>>(reinterpret_cast<const float*>(Z), (long long)le * bins * 2, st_f);
     item_stats_kernel<<<B, 1024, 0, s>>>(x, (long long)T, st_t);
-    item_normalize_kernel<<<dim3((unsigned)((T / 8 + 255) / 256), B), 256, 0, s>>>(x, (long long)T, st_t, nullptr, nullptr, xt);
+    if (T % 8 == 0 && ((uintptr_t)x & 15) == 0)
+      item_normalize_kernel<<<dim3((unsigned)((T / 8 + 255) / 256), B), 256, 0, s>>>(x, (long long)T, st_t, nullptr, nullptr, xt);
+    else
+      item_normalize_scalar_kernel<<<dim3((unsigned)((T + 255) / 256), B), 256, 0, s>>>(x, (long long)T, st_t, xt);
     R.chk();
   }
   R.launches += 4;
@@ -473,7 +489,7 @@ int run_forward(rfx_hdemucs* h, const float* x, int B, int T, float* out, uint8_
       // ---- time branch ----
       R.s = st;
       if (idx == 0) {
-        const int Lo = T / h->cfg.stride;
+        const int Lo = ceil_div(T, h->cfg.stride);   // (the conv zero-pads T to a multiple of its stride)
         tcur = R.split(B, 1, Lo, ch0);
         if (train) {
           Op op; op.kind = OP_TIMEFIRST; op.name = te + ".conv"; op.out = tcur; op.fp0 = xt; op.i0 = T; op.i1 = h->cfg.stride; op.i2 = h->cfg.kernel_size / 4;
@@ -867,8 +883,9 @@ size_t rfx_hdemucs_workspace_bytes(rfx_hdemucs_t* h, int B, int T) {
 int rfx_hdemucs_forward(rfx_hdemucs_t* h, const float* x, int B, int T, float* out, void* workspace, size_t workspace_bytes, void* stream) {
   RFX_REQUIRE(h && x && out && workspace, "null argument");
   RFX_REQUIRE(h->finalized, "rfx_hdemucs_finalize has not been called since the last parameter load");
-  RFX_REQUIRE(B > 0 && T > 0 && T % (h->cfg.nfft / 4) == 0 && T % 1024 == 0, "T must be a positive multiple of 1024");
-  RFX_REQUIRE(T > h->cfg.nfft / 8 * 3, "input shorter than the reflect padding");
+  // any length the reference's reflect padding accepts without its zero-extension path (TA:465-487: left pad 3/8 nfft, right pad up
+  // to 3/8 nfft + hop - 1); lengths off the hop grid run the zero-padded strided convs of the time branch (TA:147-150)
+  RFX_REQUIRE(B > 0 && T >= h->cfg.nfft, "T must be at least nfft samples");
   RFX_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
   size_t need = 0;
   int launches = 0;

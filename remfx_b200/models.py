@@ -752,7 +752,7 @@ class DemucsModel(nn.Module):
             _lib.check(L.rfx_hdemucs_set_taps(h, int(taps)), "rfx_hdemucs_set_taps")
             need = L.rfx_hdemucs_workspace_bytes(h, B, T)
             if need == 0:
-                raise ValueError(f"unsupported input size (B={B}, T={T}): T must be a multiple of 1024")
+                raise ValueError(f"unsupported input size (B={B}, T={T}): {L.rfx_last_error().decode() or 'T must be at least nfft samples'}")
             if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
                 self._ws = None
                 self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)

@@ -63,6 +63,22 @@ def test_layerwise_and_output(T, over):
     assert e < TOL, e
 
 
+@pytest.mark.parametrize("T", [20000, 50001, 4096 + 7, 133333])
+def test_any_length_matches_torchaudio(T):
+    """Whole files (scripts/remfx_detect.py feeds one item of arbitrary length): lengths off the 1024-sample hop grid take the
+    reference's reflect padding up to a whole number of hops (TA:465-487) and the zero-padded strided convs of the time branch
+    (TA:147-150); 50001 / 4103 / 133333 also leave odd frame counts (49, 5, 131) for the stride-2 merged layer and lengths that are
+    not multiples of 4 or 8 at every level of the time branch."""
+    ref, m = _pair(2)
+    x = weights.synth_audio(11, 2, T)
+    r = ohd.sample(x, ref)
+    out = m.sample(x.cuda())
+    assert out.shape == r.shape == (2, 1, T)
+    e = relrms(out, r)
+    print(f"T = {T}: output rel-RMS {e:.2e}")
+    assert e < TOL, e
+
+
 def test_forward_returns_loss_and_matches_oracle_sample():
     from oracle import loss as oloss
 
