@@ -64,3 +64,40 @@ def test_chain_with_given_labels_and_metrics():
     # item 2 has no effect detected: it must pass through untouched (models.py:96-104)
     out = chain.sample((x.cuda(), y.cuda(), None, labels))
     assert torch.equal(out[2].cpu(), x[2])
+
+
+def test_whole_file_with_the_shipped_architecture_mix():
+    """scripts/remfx_detect.py: ONE item of arbitrary length (a whole file, here 100003 samples -- off every grid the kernels tile by)
+    through the classifier and the shipped member mix (cfg/exp/remfx_detect.yaml:63-78: Hybrid Demucs removes distortion and
+    compressor, here Open-Unmix stands in for the three DCUNet members), every effect applied."""
+    from oracle import hdemucs as ohd
+    from remfx_b200.chain import RemFXChainInference
+    from remfx_b200.classifier import Cnn14
+    from remfx_b200.models import DemucsModel, OpenUnmixModel
+
+    T = 100003
+    refs, members, omem = {}, {}, {}
+    for i, e in enumerate(ochain.ALL_EFFECTS):
+        if e in ("RandomPedalboardDistortion", "RandomPedalboardCompressor"):
+            ref = ohd.build(20 + i)
+            m = DemucsModel(sample_rate=48000, **ohd.KW)
+            m.model.load_state_dict(ref.state_dict(), strict=True)
+            omem[e] = (lambda r: (lambda z: ohd.sample(z, r)))(ref)
+        else:
+            sd = weights.umx_state(60 + i)
+            m = OpenUnmixModel(sample_rate=48000)
+            m.load_state_dict(sd)
+            omem[e] = (lambda sd: (lambda z: oumx.sample(z, sd)))(sd)
+        members[e] = m.cuda().eval()
+    csd = weights.cnn14_state(0)
+    clf = Cnn14(num_classes=5, sample_rate=48000, model_sample_rate=48000, n_fft=2048, hop_length=512, n_mels=128, specaugment=True)
+    clf.load_state_dict(csd)
+    x = weights.synth_diverse(91, 1, T)
+    chain = RemFXChainInference(members, 48000, 1025, ORDER, classifier=clf.cuda().eval(), use_all_effect_models=True)
+    loss, out = chain((x.cuda(), x.cuda(), None, None), 0)
+    rloss, rout, rlabels = ochain.forward(x, x, None, omem, ORDER, classify=lambda z: torch.hstack(ocnn.forward(z, csd)), use_all=True)
+    assert torch.equal(chain.last_labels.cpu(), rlabels)
+    assert out.shape == rout.shape == (1, 1, T)
+    assert relrms(out, rout) < 2e-4   # five networks in sequence: the per-network 1e-4 gate compounds
+    assert abs(float(loss) - float(rloss)) < 2e-3 * abs(float(rloss))
+
