@@ -243,3 +243,19 @@ def test_tcgen05_and_mma_sync_weight_gradients_agree():
     worst = max(((relrms(g_tc[k], g_mma[k]), k) for k in g_tc if k.endswith("weight") and g_mma[k].dim() > 1), default=(0.0, ""))
     print("worst weight-gradient difference between the two forms:", worst)
     assert worst[0] < 2e-5, worst
+
+
+@pytest.mark.parametrize("T", [20000, 16383])
+def test_training_off_the_hop_grid_fails_loudly(T):
+    """Inference takes any length (test_gpu_hdemucs.py::test_any_length_matches_torchaudio); the training step is built for the
+    reference's chunks (multiples of 1024 samples) and says so instead of producing untested gradients."""
+    ref, m = _pair(0)
+    m.train()
+    x, y = weights.synth_audio(1, 1, T).cuda(), weights.synth_audio(2, 1, T).cuda()
+    with pytest.raises((ValueError, RuntimeError), match="1024"):
+        m((x, y))
+    m.eval()
+    with torch.no_grad():
+        loss, out = m((x, y))          # the same length in eval mode is fine
+    assert out.shape == (1, 1, T) and torch.isfinite(loss)
+
